@@ -1,0 +1,106 @@
+/*
+ * nmmo_b200.h -- C ABI of the B200-native batched Neural MMO simulator.
+ *
+ * Drop-in boundary.  The reference drives its environments through the pufferlib
+ * vectorisation object (`recv/send/async_reset/close`,
+ * /root/reference/reinforcement_learning/clean_pufferl.py:106-118,175,293,357,563) that wraps
+ * `nmmo.Env -> RewardWrapper -> PettingZooPufferEnv`
+ * (/root/reference/reinforcement_learning/environment.py:55-74).  The reference has no FFI of
+ * its own (100 % Python), so these entry points are what a ctypes binding for that seam binds;
+ * nmmo_b200/vecenv.py is that binding and INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success or a negative
+ * nm_status code, with a message in nmmo_last_error(); no exceptions cross the ABI.  All device
+ * buffers are owned by the handle and stay valid until nmmo_destroy; the *_ptr accessors return
+ * device pointers (wrap them zero-copy, e.g. __cuda_array_interface__ / DLPack).  One handle per
+ * GPU; calls on a handle are serialised by the caller; `stream` is a cudaStream_t (NULL = the
+ * legacy default stream).  There is no CPU fallback: creating a handle without a CUDA device
+ * fails with NM_ERR_CUDA.
+ */
+#ifndef NMMO_B200_H
+#define NMMO_B200_H
+
+#include <stdint.h>
+#include "nmmo_spec.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nmmo_handle nmmo_handle;
+
+enum nm_err { NM_OK = 0, NM_ERR_ARG = -1, NM_ERR_CUDA = -2, NM_ERR_LIMIT = -3, NM_ERR_STATE = -4 };
+
+/* Replaces: the vectorization constructor building `num_envs` x env_creator()
+ * (clean_pufferl.py:106-114; environment.py:57-58 `nmmo.Env(Config(env))`, RewardWrapper kwargs).
+ * cfg / fcfg: the vectors of nmmo_spec.h (built by nmmo_b200/config.py from the same
+ * env / reward_wrapper namespaces).  maps: uint8 [n_maps][S][S] host memory (the reference loads
+ * them from PATH_MAPS, environment.py:41).  tasks / task_embed: the curriculum
+ * (environment.py:49) as int32 [n_tasks][8] predicate rows + fp16 [n_tasks][task_dim].
+ * env_base: global index of this handle's env 0 (env sharding across GPUs). */
+int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, int n_fcfg, int n_envs, int device,
+                int env_base, const uint8_t *maps, int n_maps, const int32_t *tasks,
+                const uint16_t *task_embed, int n_tasks, nmmo_handle **out);
+
+/* Replaces: vectorization.close() (clean_pufferl.py:563). */
+int nmmo_destroy(nmmo_handle *h);
+
+/* Replaces: vectorization.async_reset(seed) -> BaseStatWrapper.reset -> nmmo.Env.reset
+ * (clean_pufferl.py:175; stat_wrapper.py:48-55).  seeds: host uint64 [E].  map_ids (host int32 [E])
+ * and task_ids (host int32 [E][P]) may be NULL: then they are drawn from the env seed like
+ * Env.reset draws map_id, and like the curriculum sampler assigns tasks.  env_mask (host uint8
+ * [E], NULL = all) selects which envs reset.  Observations/masks of the reset envs are written. */
+int nmmo_reset(nmmo_handle *h, const uint64_t *seeds, const int32_t *map_ids, const int32_t *task_ids,
+               const uint8_t *env_mask, void *stream);
+
+/* Replaces: vectorization.send(actions) + the worker-side step + recv()
+ * (clean_pufferl.py:293,357; stat_wrapper.py:57-97; nmmo.Env.step).  actions: DEVICE int32
+ * [E][P][12], column order of nmmo_spec.h nm_action (agent_zoo/takeru/policy.py:293-307).  Envs whose
+ * episode ended on the previous call are reset instead of stepped (pufferlib semantics).
+ * Launches 2 kernels on `stream`; results are in the buffers returned by the accessors. */
+int nmmo_step(nmmo_handle *h, const int32_t *actions_dev, void *stream);
+
+/* Same call with HOST buffers (the copy-in / copy-out path the reference pays today,
+ * clean_pufferl.py:302-304,329): H2D of actions, step, D2H of reward/terminated/truncated/mask;
+ * obs_out may be NULL (observations stay on the device for the policy) or a host buffer of
+ * E*P*stride bytes.  Synchronises `stream` before returning. */
+int nmmo_step_host(nmmo_handle *h, const int32_t *actions_host, float *rew_out, uint8_t *term_out,
+                   uint8_t *trunc_out, uint8_t *mask_out, uint8_t *obs_out, void *stream);
+
+/* Uniform-random valid actions from the current ActionTargets masks (BASELINE.json config 2),
+ * keyed (seed, global env, tick, agent, head); writes DEVICE int32 [E][P][12]. */
+int nmmo_sample_actions(nmmo_handle *h, uint64_t seed, int32_t *actions_dev, void *stream);
+
+/* Device pointers to the step outputs (valid until nmmo_destroy, rewritten by each step). */
+void *nmmo_obs_ptr(nmmo_handle *h);          /* uint8 [E*P][stride]  flat observation records */
+void *nmmo_reward_ptr(nmmo_handle *h);       /* float [E*P] */
+void *nmmo_terminated_ptr(nmmo_handle *h);   /* uint8 [E*P] */
+void *nmmo_truncated_ptr(nmmo_handle *h);    /* uint8 [E*P] */
+void *nmmo_mask_ptr(nmmo_handle *h);         /* uint8 [E*P]  agent present in this step's output */
+void *nmmo_info_ptr(nmmo_handle *h);         /* float [E*P][IN_N]  episode-end info records */
+void *nmmo_info_valid_ptr(nmmo_handle *h);   /* uint8 [E*P] */
+void *nmmo_episode_done_ptr(nmmo_handle *h); /* uint8 [E]    infos[..]["episode_done"], stat_wrapper.py:93-95 */
+int nmmo_obs_stride(nmmo_handle *h);
+int nmmo_num_envs(nmmo_handle *h);
+int nmmo_num_agents(nmmo_handle *h);
+
+/* Recorded-RNG injection: draws of env `env` whose key (nm_rng_key) appears in `keys` (host,
+ * any order) return the paired value instead of the counter hash.  Replaces the draws the
+ * reference takes from its numpy Generator.  n = 0 clears. */
+int nmmo_inject_rng(nmmo_handle *h, int env, const uint64_t *keys, const uint32_t *vals, int n);
+
+/* Full state of one env for parity diffs: int16 ent[R][EA_N] (row-major), int16
+ * items[CAP][IS_N], uint8 map[S*S]; also the tick, map id and error flags. */
+int nmmo_snapshot(nmmo_handle *h, int env, int16_t *ent, int16_t *items, uint8_t *map, int32_t *scalars16);
+
+/* Episode statistics of finished agents since the last clear: sums[IN_N], counts[IN_N] (means
+ * are sums/counts, clean_pufferl.py:381-390), counters[4] = slot-steps, agent-steps (mask
+ * sum), finished episodes, event-ring overflows.  Plain sums so ranks can all-reduce them. */
+int nmmo_stats(nmmo_handle *h, double *sums, double *counts, uint64_t *counters, int clear);
+
+const char *nmmo_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMMO_B200_H */

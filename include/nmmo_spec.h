@@ -16,6 +16,12 @@
 
 #include <stdint.h>
 
+#ifdef __CUDACC__
+#define NM_HD __host__ __device__
+#else
+#define NM_HD
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -280,9 +286,9 @@ typedef struct nm_obs_layout {
   int32_t alg_bytes;    /* unpadded payload bytes (roofline accounting) */
 } nm_obs_layout;
 
-static inline int32_t nm_align16(int32_t x) { return (x + 15) & ~15; }
+static inline NM_HD int32_t nm_align16(int32_t x) { return (x + 15) & ~15; }
 
-static inline void nm_obs_layout_init(const int32_t *cfg, nm_obs_layout *L) {
+static inline NM_HD void nm_obs_layout_init(const int32_t *cfg, nm_obs_layout *L) {
   int32_t o = 0;
   L->n_ent = cfg[NC_N_ENT_OBS]; L->n_mkt = cfg[NC_N_MKT_OBS]; L->n_inv = cfg[NC_N_INV];
   L->n_price = cfg[NC_N_PRICE]; L->task_dim = cfg[NC_TASK_DIM]; L->win = 2 * cfg[NC_VISION] + 1;
@@ -311,7 +317,7 @@ static inline void nm_obs_layout_init(const int32_t *cfg, nm_obs_layout *L) {
 }
 
 /* rng key packing for injected draws: tick 20b | site 4b | idx 24b | k 8b */
-static inline uint64_t nm_rng_key(uint32_t tick, uint32_t site, uint32_t idx, uint32_t k) {
+static inline NM_HD uint64_t nm_rng_key(uint32_t tick, uint32_t site, uint32_t idx, uint32_t k) {
   return ((uint64_t)(tick & 0xFFFFFu) << 36) | ((uint64_t)(site & 0xFu) << 32) |
          ((uint64_t)(idx & 0xFFFFFFu) << 8) | (uint64_t)(k & 0xFFu);
 }

@@ -1,0 +1,314 @@
+// nmmo_api.cu -- host side of the C ABI (include/nmmo_b200.h): allocation, launches, copies.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "nmmo_device.cuh"
+#include "../../include/nmmo_b200.h"
+
+// unity build: the kernels live in their own files but compile into this translation unit
+#include "nmmo_step.cu"
+#include "nmmo_obs.cu"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) return fail(NM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct nmmo_handle {
+  NmParams prm;
+  int device;
+  size_t step_smem, obs_smem;
+  std::vector<void *> allocs;
+  int32_t *d_actions;             // staging for the host-buffer path
+  int32_t *h_actions_pinned; float *h_rew; uint8_t *h_flags;
+  // injected rng (host mirror, rebuilt on change)
+  std::vector<std::vector<std::pair<uint64_t, uint32_t>>> inj;
+  uint64_t *d_inj_keys; uint32_t *d_inj_vals; int32_t *d_inj_off;
+  uint8_t *d_env_mask;
+};
+
+static size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+static size_t step_smem_bytes(const NmParams &p) {
+  size_t s = 0;
+  int NINV = p.cfg[NC_N_INV];
+  s += a16((size_t)EA_N * p.R * 2); s += a16((size_t)IS_N * p.CAP * 2); s += a16((size_t)p.S * p.S);
+  s += a16((size_t)((p.S * p.S + 31) / 32) * 4); s += 2 * a16((size_t)((p.CAP + 31) / 32) * 4);
+  s += a16((size_t)p.P * NINV * 2); s += a16(p.P); s += a16((size_t)12 * p.P * 2);
+  s += a16(p.N); s += a16((size_t)p.N * 2); s += a16(NM_EV_CAP * 8); s += a16((size_t)p.P * 4) * 2; s += a16(64); s += 16;
+  return s + 128;
+}
+static size_t obs_smem_bytes(const NmParams &p) {
+  size_t s = 0;
+  int NINV = p.cfg[NC_N_INV];
+  int NW = NM_OBS_THREADS / 32;
+  s += a16((size_t)EA_N_OBS * p.R * 2); s += a16((size_t)p.R * 2); s += a16((size_t)IS_N * p.CAP * 2); s += a16((size_t)p.S * p.S);
+  s += a16((size_t)p.L.n_mkt * IA_N_OBS * 2); s += a16((size_t)p.L.n_mkt * 2);
+  s += a16((size_t)p.P * NINV * 2); s += a16((size_t)p.P * 4); s += a16(64 * 4);
+  s += a16((size_t)NW * a16(p.L.m_end)); s += a16((size_t)NW * a16((size_t)p.L.n_ent * 2)); s += 16;
+  return s + 128;
+}
+
+template <typename T>
+static int dalloc(nmmo_handle *h, T **ptr, size_t count, bool zero = true) {
+  void *q = nullptr;
+  size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+  CU(cudaMalloc(&q, bytes));
+  if (zero) CU(cudaMemset(q, 0, bytes));
+  h->allocs.push_back(q);
+  *ptr = (T *)q;
+  return 0;
+}
+#define DA(ptr, count) do { int rc_ = dalloc(h, &(ptr), (count)); if (rc_) return rc_; } while (0)
+
+extern "C" const char *nmmo_last_error(void) { return g_err.c_str(); }
+
+extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, int n_fcfg, int n_envs, int device,
+                           int env_base, const uint8_t *maps, int n_maps, const int32_t *tasks,
+                           const uint16_t *task_embed, int n_tasks, nmmo_handle **out) {
+  if (!cfg || !fcfg || !maps || !tasks || !task_embed || !out) return fail(NM_ERR_ARG, "null argument");
+  if (n_cfg != NC_COUNT || n_fcfg != NF_COUNT) return fail(NM_ERR_ARG, "config vector length does not match nmmo_spec.h");
+  if (n_envs <= 0 || n_maps <= 0 || n_tasks <= 0) return fail(NM_ERR_ARG, "n_envs, n_maps, n_tasks must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(NM_ERR_CUDA, "no CUDA device: nmmo_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(NM_ERR_ARG, "bad device index");
+  CU(cudaSetDevice(device));
+  nmmo_handle *h = new nmmo_handle();
+  h->device = device;
+  NmParams &p = h->prm;
+  memset(&p, 0, sizeof(p));
+  memcpy(p.cfg, cfg, sizeof(int32_t) * NC_COUNT);
+  memcpy(p.fcfg, fcfg, sizeof(double) * NF_COUNT);
+  nm_obs_layout_init(p.cfg, &p.L);
+  p.E = n_envs; p.P = cfg[NC_N_PLAYERS]; p.N = cfg[NC_N_NPCS]; p.R = p.P + p.N; p.S = cfg[NC_MAP_SIZE]; p.CAP = cfg[NC_ITEM_CAP];
+  p.n_maps = n_maps; p.n_tasks = n_tasks; p.env_base = env_base;
+  if (p.P <= 0 || p.P > NM_STEP_THREADS) { delete h; return fail(NM_ERR_LIMIT, "PLAYER_N must be in 1..256 for the per-env CTA design"); }
+  if (p.R % 8 || p.CAP % 8 || (p.S * p.S) % 16) { delete h; return fail(NM_ERR_LIMIT, "P+N and item cap must be multiples of 8, S*S of 16 (bulk copies)"); }
+  if (p.S > 255) { delete h; return fail(NM_ERR_LIMIT, "MAP_SIZE must be <= 255"); }
+  if (p.L.n_ent > 255 || p.cfg[NC_N_INV] > 16) { delete h; return fail(NM_ERR_LIMIT, "N_ENT_OBS <= 255, N_INV <= 16"); }
+  h->step_smem = step_smem_bytes(p);
+  h->obs_smem = obs_smem_bytes(p);
+  int max_smem = 0;
+  CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  if ((int)h->step_smem > max_smem || (int)h->obs_smem > max_smem) { delete h; return fail(NM_ERR_LIMIT, "environment does not fit in shared memory"); }
+  CU(cudaFuncSetAttribute(nmmo_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
+  CU(cudaFuncSetAttribute(nmmo_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->obs_smem));
+  size_t E = p.E, P = p.P;
+  DA(p.ent, E * EA_N * p.R); DA(p.item, E * IS_N * p.CAP); DA(p.map, E * p.S * p.S);
+  uint8_t *dmaps; DA(dmaps, (size_t)n_maps * p.S * p.S); p.maps = dmaps;
+  CU(cudaMemcpy(dmaps, maps, (size_t)n_maps * p.S * p.S, cudaMemcpyHostToDevice));
+  DA(p.scalars, E * NM_SC_N); DA(p.seed, E); DA(p.danger, E * p.N);
+  DA(p.stats, E * P * ST_N); DA(p.dstats, E * P * DS_N); DA(p.uniq, E * P * NM_UNIQ_WORDS); DA(p.task_id, E * P);
+  int32_t *dtasks; DA(dtasks, (size_t)n_tasks * NM_TASK_COLS); p.tasks = dtasks;
+  CU(cudaMemcpy(dtasks, tasks, sizeof(int32_t) * n_tasks * NM_TASK_COLS, cudaMemcpyHostToDevice));
+  uint16_t *demb; DA(demb, (size_t)n_tasks * p.L.task_dim); p.embed = demb;
+  CU(cudaMemcpy(demb, task_embed, sizeof(uint16_t) * n_tasks * p.L.task_dim, cudaMemcpyHostToDevice));
+  DA(p.obs, E * P * p.L.stride);
+  DA(p.rew, E * P); DA(p.term, E * P); DA(p.trunc, E * P); DA(p.mask, E * P);
+  DA(p.info, E * P * IN_N); DA(p.info_valid, E * P); DA(p.episode_done, E);
+  DA(p.agg, 2 * IN_N); DA(p.counters, 4);
+  DA(h->d_actions, E * P * AC_N);
+  DA(h->d_inj_off, E + 1);
+  DA(h->d_env_mask, E);
+  h->d_inj_keys = nullptr; h->d_inj_vals = nullptr;
+  p.inj_off = nullptr; p.inj_keys = nullptr; p.inj_vals = nullptr;
+  h->inj.resize(E);
+  CU(cudaMallocHost((void **)&h->h_actions_pinned, E * P * AC_N * sizeof(int32_t)));
+  CU(cudaMallocHost((void **)&h->h_rew, E * P * sizeof(float)));
+  CU(cudaMallocHost((void **)&h->h_flags, E * P * 3));
+  // every env starts "done" so that a step before any reset resets from seed 0
+  std::vector<int32_t> sc(E * NM_SC_N, 0);
+  for (size_t e = 0; e < E; e++) sc[e * NM_SC_N + SC_DONE] = 1;
+  CU(cudaMemcpy(p.scalars, sc.data(), sizeof(int32_t) * sc.size(), cudaMemcpyHostToDevice));
+  *out = h;
+  return NM_OK;
+}
+
+extern "C" int nmmo_destroy(nmmo_handle *h) {
+  if (!h) return NM_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void *q : h->allocs) cudaFree(q);
+  if (h->d_inj_keys) cudaFree(h->d_inj_keys);
+  if (h->d_inj_vals) cudaFree(h->d_inj_vals);
+  cudaFreeHost(h->h_actions_pinned); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_flags);
+  delete h;
+  return NM_OK;
+}
+
+static int launch_step(nmmo_handle *h, int mode, cudaStream_t st) {
+  NmParams prm = h->prm;
+  prm.mode = mode;
+  nmmo_step_kernel<<<prm.E, NM_STEP_THREADS, h->step_smem, st>>>(prm);
+  CU(cudaGetLastError());
+  nmmo_obs_kernel<<<prm.E, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
+  CU(cudaGetLastError());
+  return NM_OK;
+}
+
+extern "C" int nmmo_reset(nmmo_handle *h, const uint64_t *seeds, const int32_t *map_ids, const int32_t *task_ids,
+                          const uint8_t *env_mask, void *stream) {
+  if (!h || !seeds) return fail(NM_ERR_ARG, "null argument");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  NmParams &p = h->prm;
+  size_t E = p.E, P = p.P;
+  CU(cudaStreamSynchronize(st));
+  std::vector<int32_t> sc(E * NM_SC_N);
+  CU(cudaMemcpy(sc.data(), p.scalars, sizeof(int32_t) * sc.size(), cudaMemcpyDeviceToHost));
+  std::vector<uint64_t> sd(E);
+  CU(cudaMemcpy(sd.data(), p.seed, sizeof(uint64_t) * E, cudaMemcpyDeviceToHost));
+  for (size_t e = 0; e < E; e++) {
+    if (env_mask && !env_mask[e]) continue;
+    int32_t *s = &sc[e * NM_SC_N];
+    s[SC_NEED_RESET] = 1; s[SC_EPISODE] = 0; s[SC_ERROR] = 0;
+    s[SC_EXPLICIT_MAP] = map_ids ? 1 : 0;
+    if (map_ids) {
+      if (map_ids[e] < 0 || map_ids[e] >= p.n_maps) return fail(NM_ERR_ARG, "map id out of range");
+      s[SC_MAP_ID] = map_ids[e];
+    }
+    s[SC_EXPLICIT_TASKS] = task_ids ? 1 : 0;
+    sd[e] = seeds[e];
+  }
+  CU(cudaMemcpy(p.scalars, sc.data(), sizeof(int32_t) * sc.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(p.seed, sd.data(), sizeof(uint64_t) * E, cudaMemcpyHostToDevice));
+  if (task_ids) {
+    for (size_t e = 0; e < E; e++) {
+      if (env_mask && !env_mask[e]) continue;
+      for (size_t a = 0; a < P; a++)
+        if (task_ids[e * P + a] < 0 || task_ids[e * P + a] >= p.n_tasks) return fail(NM_ERR_ARG, "task id out of range");
+      CU(cudaMemcpy(p.task_id + e * P, task_ids + e * P, sizeof(int32_t) * P, cudaMemcpyHostToDevice));
+    }
+  }
+  int rc = launch_step(h, 1, st);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(st));
+  return NM_OK;
+}
+
+extern "C" int nmmo_step(nmmo_handle *h, const int32_t *actions_dev, void *stream) {
+  if (!h || !actions_dev) return fail(NM_ERR_ARG, "null argument");
+  CU(cudaSetDevice(h->device));
+  h->prm.actions = actions_dev;
+  return launch_step(h, 0, (cudaStream_t)stream);
+}
+
+extern "C" int nmmo_step_host(nmmo_handle *h, const int32_t *actions_host, float *rew_out, uint8_t *term_out,
+                              uint8_t *trunc_out, uint8_t *mask_out, uint8_t *obs_out, void *stream) {
+  if (!h || !actions_host) return fail(NM_ERR_ARG, "null argument");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  NmParams &p = h->prm;
+  size_t n = (size_t)p.E * p.P;
+  memcpy(h->h_actions_pinned, actions_host, n * AC_N * sizeof(int32_t));
+  CU(cudaMemcpyAsync(h->d_actions, h->h_actions_pinned, n * AC_N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  p.actions = h->d_actions;
+  int rc = launch_step(h, 0, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h->h_rew, p.rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->h_flags, p.term, n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->h_flags + n, p.trunc, n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->h_flags + 2 * n, p.mask, n, cudaMemcpyDeviceToHost, st));
+  if (obs_out) CU(cudaMemcpyAsync(obs_out, p.obs, n * p.L.stride, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (rew_out) memcpy(rew_out, h->h_rew, n * sizeof(float));
+  if (term_out) memcpy(term_out, h->h_flags, n);
+  if (trunc_out) memcpy(trunc_out, h->h_flags + n, n);
+  if (mask_out) memcpy(mask_out, h->h_flags + 2 * n, n);
+  return NM_OK;
+}
+
+extern "C" int nmmo_sample_actions(nmmo_handle *h, uint64_t seed, int32_t *actions_dev, void *stream) {
+  if (!h || !actions_dev) return fail(NM_ERR_ARG, "null argument");
+  CU(cudaSetDevice(h->device));
+  NmParams prm = h->prm;
+  long long total = (long long)prm.E * prm.P * AC_N;
+  int threads = 256;
+  int blocks = (int)((total + threads - 1) / threads);
+  nmmo_sample_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(prm, seed, actions_dev);
+  CU(cudaGetLastError());
+  return NM_OK;
+}
+
+extern "C" void *nmmo_obs_ptr(nmmo_handle *h) { return h->prm.obs; }
+extern "C" void *nmmo_reward_ptr(nmmo_handle *h) { return h->prm.rew; }
+extern "C" void *nmmo_terminated_ptr(nmmo_handle *h) { return h->prm.term; }
+extern "C" void *nmmo_truncated_ptr(nmmo_handle *h) { return h->prm.trunc; }
+extern "C" void *nmmo_mask_ptr(nmmo_handle *h) { return h->prm.mask; }
+extern "C" void *nmmo_info_ptr(nmmo_handle *h) { return h->prm.info; }
+extern "C" void *nmmo_info_valid_ptr(nmmo_handle *h) { return h->prm.info_valid; }
+extern "C" void *nmmo_episode_done_ptr(nmmo_handle *h) { return h->prm.episode_done; }
+extern "C" int nmmo_obs_stride(nmmo_handle *h) { return h->prm.L.stride; }
+extern "C" int nmmo_num_envs(nmmo_handle *h) { return h->prm.E; }
+extern "C" int nmmo_num_agents(nmmo_handle *h) { return h->prm.P; }
+
+extern "C" int nmmo_inject_rng(nmmo_handle *h, int env, const uint64_t *keys, const uint32_t *vals, int n) {
+  if (!h || env < 0 || env >= h->prm.E || n < 0 || (n > 0 && (!keys || !vals))) return fail(NM_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  auto &v = h->inj[env];
+  v.clear();
+  for (int i = 0; i < n; i++) v.emplace_back(keys[i], vals[i]);
+  std::sort(v.begin(), v.end());
+  std::vector<uint64_t> K; std::vector<uint32_t> V; std::vector<int32_t> off(h->prm.E + 1, 0);
+  for (int e = 0; e < h->prm.E; e++) {
+    off[e] = (int32_t)K.size();
+    for (auto &kv : h->inj[e]) { K.push_back(kv.first); V.push_back(kv.second); }
+  }
+  off[h->prm.E] = (int32_t)K.size();
+  if (h->d_inj_keys) { cudaFree(h->d_inj_keys); h->d_inj_keys = nullptr; }
+  if (h->d_inj_vals) { cudaFree(h->d_inj_vals); h->d_inj_vals = nullptr; }
+  if (K.empty()) { h->prm.inj_off = nullptr; h->prm.inj_keys = nullptr; h->prm.inj_vals = nullptr; return NM_OK; }
+  CU(cudaMalloc((void **)&h->d_inj_keys, K.size() * sizeof(uint64_t)));
+  CU(cudaMalloc((void **)&h->d_inj_vals, V.size() * sizeof(uint32_t)));
+  CU(cudaMemcpy(h->d_inj_keys, K.data(), K.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_inj_vals, V.data(), V.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_inj_off, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  h->prm.inj_off = h->d_inj_off; h->prm.inj_keys = h->d_inj_keys; h->prm.inj_vals = h->d_inj_vals;
+  return NM_OK;
+}
+
+extern "C" int nmmo_snapshot(nmmo_handle *h, int env, int16_t *ent, int16_t *items, uint8_t *map, int32_t *scalars16) {
+  if (!h || env < 0 || env >= h->prm.E) return fail(NM_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  const NmParams &p = h->prm;
+  if (ent) {
+    std::vector<int16_t> soa((size_t)EA_N * p.R);
+    CU(cudaMemcpy(soa.data(), p.ent + (size_t)env * EA_N * p.R, soa.size() * 2, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < p.R; r++) {
+      bool empty = soa[(size_t)EA_STATUS * p.R + r] == ES_EMPTY;
+      for (int k = 0; k < EA_N; k++) ent[(size_t)r * EA_N + k] = empty ? 0 : soa[(size_t)k * p.R + r];
+    }
+  }
+  if (items) {
+    std::vector<int16_t> soa((size_t)IS_N * p.CAP);
+    CU(cudaMemcpy(soa.data(), p.item + (size_t)env * IS_N * p.CAP, soa.size() * 2, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < p.CAP; i++)
+      for (int k = 0; k < IS_N; k++) items[(size_t)i * IS_N + k] = soa[(size_t)k * p.CAP + i];
+  }
+  if (map) CU(cudaMemcpy(map, p.map + (size_t)env * p.S * p.S, (size_t)p.S * p.S, cudaMemcpyDeviceToHost));
+  if (scalars16) CU(cudaMemcpy(scalars16, p.scalars + (size_t)env * NM_SC_N, sizeof(int32_t) * NM_SC_N, cudaMemcpyDeviceToHost));
+  return NM_OK;
+}
+
+extern "C" int nmmo_stats(nmmo_handle *h, double *sums, double *counts, uint64_t *counters, int clear) {
+  if (!h) return fail(NM_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  double agg[2 * IN_N];
+  CU(cudaMemcpy(agg, h->prm.agg, sizeof(agg), cudaMemcpyDeviceToHost));
+  if (sums) memcpy(sums, agg, sizeof(double) * IN_N);
+  if (counts) memcpy(counts, agg + IN_N, sizeof(double) * IN_N);
+  if (counters) CU(cudaMemcpy(counters, h->prm.counters, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost));
+  if (clear) { CU(cudaMemset(h->prm.agg, 0, sizeof(agg))); CU(cudaMemset(h->prm.counters, 0, sizeof(uint64_t) * 4)); }
+  return NM_OK;
+}

@@ -1,0 +1,149 @@
+// nmmo_device.cuh -- device-side state description and small helpers shared by the kernels.
+//
+// Layout in HBM (one handle = E lock-stepped environments on one GPU), all per-env blocks
+// contiguous and 16-byte aligned so a CTA pulls its environment into shared memory with
+// three cp.async.bulk (TMA 1-D) copies and pushes it back the same way:
+//   ent   int16 [E][EA_N][R]      structure-of-arrays entity table (players rows 0..P-1, NPCs after)
+//   item  int16 [E][IS_N][CAP]    item table (only stored columns; stats derive from type+level)
+//   map   uint8 [E][S*S]          current tile materials
+// plus small per-agent blocks (stats, unique-event bitsets, task state) and the output
+// tensors (obs records, reward, terminated, truncated, mask, episode info).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/nmmo_spec.h"
+
+#define NM_EV_CAP 1024          // per-env per-tick event ring (shared memory)
+#define NM_STEP_THREADS 256
+#define NM_OBS_THREADS 256
+#define NM_SC_N 16              // per-env int32 scalars
+
+enum nm_scalar { SC_TICK = 0, SC_DONE, SC_NEXT_NPC_ID, SC_N_DANGER, SC_MAP_ID, SC_EPISODE, SC_FRESH,
+                 SC_ERROR, SC_NEED_RESET, SC_EXPLICIT_MAP, SC_EXPLICIT_TASKS };
+
+struct NmParams {
+  int32_t cfg[NC_COUNT];
+  double fcfg[NF_COUNT];
+  nm_obs_layout L;
+  int E, P, N, R, S, CAP, n_maps, n_tasks;
+  // state
+  int16_t *ent, *item;
+  uint8_t *map;
+  const uint8_t *maps;
+  int32_t *scalars;            // [E][NM_SC_N]
+  uint64_t *seed;              // [E]
+  int16_t *danger;             // [E][N]
+  int32_t *stats;              // [E][P][ST_N]
+  double *dstats;              // [E][P][DS_N]
+  uint32_t *uniq;              // [E][P][NM_UNIQ_WORDS]
+  int32_t *task_id;            // [E][P]
+  const int32_t *tasks;        // [T][8]
+  const uint16_t *embed;       // [T][task_dim]
+  // rng injection
+  const uint64_t *inj_keys; const uint32_t *inj_vals; const int32_t *inj_off;   // off [E+1]
+  // io
+  const int32_t *actions;      // [E][P][12]
+  uint8_t *obs;                // [E*P][stride]
+  float *rew; uint8_t *term, *trunc, *mask; float *info; uint8_t *info_valid; uint8_t *episode_done;
+  double *agg;                 // [2][IN_N] sums and counts of finished-agent info
+  unsigned long long *counters;// [4] slot-steps, alive-agent-steps, episodes, errors
+  int mode;                    // 0 step (auto-reset finished envs), 1 reset flagged envs only
+  int env_base;                // global env index of env 0 (multi-GPU sharding; seeds derive from it)
+};
+
+// ------------------------------------------------------------------------- rng ------
+__host__ __device__ __forceinline__ uint64_t nm_mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint32_t nm_hash_draw(uint64_t seed, uint32_t tick, uint32_t site,
+                                                         uint32_t idx, uint32_t k) {
+  uint64_t key = nm_rng_key(tick, site, idx, k);
+  return (uint32_t)(nm_mix64(nm_mix64(seed ^ key) + key * 0xD6E8FEB86659FD93ULL) >> 32);
+}
+__device__ __forceinline__ int nm_bounded(uint32_t u, int n) { return (int)(((uint64_t)u * (uint64_t)n) >> 32); }
+
+// ----------------------------------------------------------------- async copies -----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// TMA 1-D bulk copy shared -> global
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------- materials ------
+__device__ __forceinline__ int nm_impassible(int m) { return (NM_IMPASSIBLE_MASK >> m) & 1; }
+__device__ __forceinline__ int nm_iabs(int x) { return x < 0 ? -x : x; }
+__device__ __forceinline__ int nm_linf(int r0, int c0, int r1, int c1) { return max(nm_iabs(r0 - r1), nm_iabs(c0 - c1)); }
+
+// ----------------------------------------------------------------------- items ------
+__device__ __forceinline__ bool it_armor(int t) { return t >= IT_HAT && t <= IT_BOTTOM; }
+__device__ __forceinline__ bool it_weapon(int t) { return t >= IT_SPEAR && t <= IT_WAND; }
+__device__ __forceinline__ bool it_tool(int t) { return t >= IT_ROD && t <= IT_CHISEL; }
+__device__ __forceinline__ bool it_ammo(int t) { return t >= IT_WHETSTONE && t <= IT_RUNES; }
+__device__ __forceinline__ bool it_consumable(int t) { return t == IT_RATION || t == IT_POTION; }
+
+// derived item columns (nmmo/systems/item.py constructors [UPSTREAM])
+__device__ __forceinline__ int item_attack(const int32_t *c, int type, int level, int style) {
+  if (it_weapon(type) && type - IT_SPEAR == style) return c[NC_WEAPON_BASE] + level * c[NC_WEAPON_LEVEL];
+  if (it_ammo(type) && type - IT_WHETSTONE == style) return c[NC_AMMO_BASE] + level * c[NC_AMMO_LEVEL];
+  return 0;
+}
+__device__ __forceinline__ int item_defense(const int32_t *c, int type, int level) {
+  if (it_armor(type)) return c[NC_ARMOR_BASE] + level * c[NC_ARMOR_LEVEL];
+  if (it_tool(type)) return c[NC_TOOL_BASE] + level * c[NC_TOOL_LEVEL];
+  return 0;
+}
+// full 16-column observed item row
+__device__ __forceinline__ void item_obs_row(const int32_t *c, int row, int type, int level, int owner, int qty,
+                                             int equipped, int price, int16_t out[IA_N_OBS]) {
+#pragma unroll
+  for (int k = 0; k < IA_N_OBS; k++) out[k] = 0;
+  out[IA_ID] = (int16_t)(row + 1); out[IA_TYPE] = (int16_t)type; out[IA_OWNER] = (int16_t)owner;
+  out[IA_LEVEL] = (int16_t)level; out[IA_QUANTITY] = (int16_t)qty; out[IA_EQUIPPED] = (int16_t)equipped;
+  out[IA_LISTED_PRICE] = (int16_t)price;
+  int d = item_defense(c, type, level);
+  out[IA_MELEE_DEFENSE] = out[IA_RANGE_DEFENSE] = out[IA_MAGE_DEFENSE] = (int16_t)d;
+  out[IA_MELEE_ATTACK] = (int16_t)item_attack(c, type, level, 0);
+  out[IA_RANGE_ATTACK] = (int16_t)item_attack(c, type, level, 1);
+  out[IA_MAGE_ATTACK] = (int16_t)item_attack(c, type, level, 2);
+  int restore = c[NC_RESTORE_BASE] + level * c[NC_RESTORE_LEVEL];
+  if (type == IT_RATION) out[IA_RESOURCE_RESTORE] = (int16_t)restore;
+  if (type == IT_POTION) out[IA_HEALTH_RESTORE] = (int16_t)restore;
+}
+
+__device__ __forceinline__ int nm_dense_event(int code) {
+  switch (code) {
+    case EV_EAT_FOOD: return 0; case EV_DRINK_WATER: return 1; case EV_GO_FARTHEST: return 2;
+    case EV_SCORE_HIT: return 3; case EV_PLAYER_KILL: return 4; case EV_CONSUME_ITEM: return 5;
+    case EV_GIVE_ITEM: return 6; case EV_DESTROY_ITEM: return 7; case EV_HARVEST_ITEM: return 8;
+    case EV_EQUIP_ITEM: return 9; case EV_LOOT_ITEM: return 10; case EV_GIVE_GOLD: return 11;
+    case EV_LIST_ITEM: return 12; case EV_EARN_GOLD: return 13; case EV_BUY_ITEM: return 14;
+    case EV_LOOT_GOLD: return 15; case EV_LEVEL_UP: return 16;
+  }
+  return -1;
+}
+
+static __constant__ int c_dir_dr[5] = {-1, 1, 0, 0, 0};   // North South East West Stay
+static __constant__ int c_dir_dc[5] = {0, 0, 1, -1, 0};

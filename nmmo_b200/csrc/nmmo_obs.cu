@@ -1,0 +1,329 @@
+// nmmo_obs.cu -- observation + ActionTargets writer (the HBM-bound kernel of the step).
+//
+// Replaces, per agent and per tick, nmmo's Observation.to_gym()/_make_action_targets()
+// [UPSTREAM nmmo/core/observation.py], the RewardWrapper.observation() mask edits
+// (agent_zoo/takeru/reward_wrapper.py:25-37, agent_zoo/neurips23_start_kit/reward_wrapper.py:46-54)
+// and pufferlib's flatten + pad of the nested observation (reinforcement_learning/environment.py:73),
+// writing the flat record the policy reads on-device (agent_zoo/takeru/policy.py:39-64).
+//
+// One CTA per environment.  The entity table (31 observed columns + status), the item table and
+// the tile map are staged into shared memory with TMA bulk copies; the env-global Market block
+// is built once in shared memory; then each warp assembles whole agent records and streams them
+// out with 16-byte st.global.cs stores, 512 contiguous bytes per warp instruction.
+#include "nmmo_device.cuh"
+
+namespace {
+
+struct OCtx {
+  const NmParams *p;
+  const int32_t *c;
+  int R, S, CAP, P, NINV;
+  const int16_t *ent;      // [31][R]
+  const int16_t *status;   // [R]
+  const int16_t *item;     // [IS_N][CAP]
+  const uint8_t *map;
+};
+#define OENT(col, row) o.ent[(col) * o.R + (row)]
+#define OITM(col, row) o.item[(col) * o.CAP + (row)]
+
+__device__ __forceinline__ int o_use_level(const OCtx &o, int row, int type) {
+  switch (type) {
+    case IT_SPEAR: case IT_WHETSTONE: return OENT(EA_MELEE_LEVEL, row);
+    case IT_BOW: case IT_ARROW: return OENT(EA_RANGE_LEVEL, row);
+    case IT_WAND: case IT_RUNES: return OENT(EA_MAGE_LEVEL, row);
+    case IT_ROD: return OENT(EA_FISHING_LEVEL, row);
+    case IT_GLOVES: return OENT(EA_HERBALISM_LEVEL, row);
+    case IT_PICKAXE: return OENT(EA_PROSPECTING_LEVEL, row);
+    case IT_AXE: return OENT(EA_CARVING_LEVEL, row);
+    case IT_CHISEL: return OENT(EA_ALCHEMY_LEVEL, row);
+    default: {
+      int l = 1;
+      for (int col = EA_MELEE_LEVEL; col <= EA_ALCHEMY_LEVEL; col += 2) l = max(l, (int)OENT(col, row));
+      return l;
+    }
+  }
+}
+__device__ __forceinline__ void st16(uint8_t *dst, uint4 v) { __stcs((uint4 *)dst, v); }
+__device__ __forceinline__ uint32_t pack2(int a, int b) { return (uint32_t)(uint16_t)a | ((uint32_t)(uint16_t)b << 16); }
+
+}  // namespace
+
+extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, 2)
+nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int env = blockIdx.x, tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
+  const int32_t *c = prm.cfg;
+  const nm_obs_layout &L = prm.L;
+  const int P = prm.P, R = prm.R, S = prm.S, CAP = prm.CAP, NINV = c[NC_N_INV], vis = c[NC_VISION];
+  const int tick = prm.scalars[(size_t)env * NM_SC_N + SC_TICK];
+
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { uint8_t *q = smem + off; off = (off + bytes + 15) & ~(size_t)15; return q; };
+  const uint32_t ent_bytes = (uint32_t)(EA_N_OBS * R * 2), st_bytes = (uint32_t)(R * 2);
+  const uint32_t item_bytes = (uint32_t)(IS_N * CAP * 2), map_bytes = (uint32_t)(S * S);
+  int16_t *s_ent = (int16_t *)carve(ent_bytes);
+  int16_t *s_status = (int16_t *)carve(st_bytes);
+  int16_t *s_item = (int16_t *)carve(item_bytes);
+  uint8_t *s_map = carve(map_bytes);
+  int16_t *s_mkt = (int16_t *)carve((size_t)L.n_mkt * IA_N_OBS * 2);
+  uint16_t *s_mkt_rows = (uint16_t *)carve((size_t)L.n_mkt * 2);
+  uint16_t *s_inv = (uint16_t *)carve((size_t)P * NINV * 2);
+  int *s_invn = (int *)carve((size_t)P * 4);
+  int *s_scan = (int *)carve(64 * 4);
+  const int stage_bytes = nm_align16(L.m_end);
+  uint8_t *s_stage_all = carve((size_t)NW * stage_bytes);
+  uint16_t *s_vis_all = (uint16_t *)carve((size_t)NW * ((L.n_ent * 2 + 15) & ~15));
+  uint64_t *bar = (uint64_t *)carve(8);
+
+  if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar, ent_bytes + st_bytes + item_bytes + map_bytes);
+    const int16_t *ge = prm.ent + (size_t)env * EA_N * R;
+    bulk_g2s(s_ent, ge, ent_bytes, bar);
+    bulk_g2s(s_status, ge + (size_t)EA_STATUS * R, st_bytes, bar);
+    bulk_g2s(s_item, prm.item + (size_t)env * IS_N * CAP, item_bytes, bar);
+    bulk_g2s(s_map, prm.map + (size_t)env * S * S, map_bytes, bar);
+  }
+  for (int i = tid; i < P; i += T) s_invn[i] = 0;
+  while (!mbar_try_wait(bar, 0)) {}
+  __syncthreads();
+
+  OCtx o;
+  o.p = &prm; o.c = c; o.R = R; o.S = S; o.CAP = CAP; o.P = P; o.NINV = NINV;
+  o.ent = s_ent; o.status = s_status; o.item = s_item; o.map = s_map;
+
+  // ---- inventory lists (row order) and the market list (row order, first n_mkt) -------
+  const int K = (CAP + T - 1) / T;          // consecutive rows per thread
+  int my_listed = 0;
+  for (int k = 0; k < K; k++) {
+    int i = tid * K + k;
+    if (i < CAP && OITM(IS_TYPE, i) != 0) {
+      int owner = OITM(IS_OWNER, i);
+      if (owner > 0) { int slot = atomicAdd(&s_invn[owner - 1], 1); if (slot < NINV) s_inv[(owner - 1) * NINV + slot] = (uint16_t)i; }
+      if (OITM(IS_PRICE, i) > 0) my_listed++;
+    }
+  }
+  // block exclusive scan of my_listed
+  int incl = my_listed;
+  for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = lane < NW ? s_scan[lane] : 0, inc2 = v;
+    for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc2, d); if (lane >= d) inc2 += u; }
+    if (lane < NW) s_scan[32 + lane] = inc2 - v;
+    if (lane == NW - 1) s_scan[63] = inc2;
+  }
+  __syncthreads();
+  const int n_mkt = min(s_scan[63], L.n_mkt);
+  {
+    int pos = s_scan[32 + warp] + incl - my_listed;
+    for (int k = 0; k < K; k++) {
+      int i = tid * K + k;
+      if (i < CAP && OITM(IS_TYPE, i) != 0 && OITM(IS_PRICE, i) > 0) { if (pos < L.n_mkt) s_mkt_rows[pos] = (uint16_t)i; pos++; }
+    }
+  }
+  for (int p = tid; p < P; p += T) {           // sort each inventory list by row (<= 12 entries)
+    int n = min(s_invn[p], NINV);
+    uint16_t *l = s_inv + p * NINV;
+    for (int i = 1; i < n; i++) { uint16_t x = l[i]; int j = i - 1; while (j >= 0 && l[j] > x) { l[j + 1] = l[j]; j--; } l[j + 1] = x; }
+  }
+  __syncthreads();
+  for (int j = tid; j < L.n_mkt; j += T) {     // the Market block, identical for every agent of the env
+    int16_t row[IA_N_OBS];
+    if (j < n_mkt) {
+      int i = s_mkt_rows[j];
+      item_obs_row(c, i, OITM(IS_TYPE, i), OITM(IS_LEVEL, i), OITM(IS_OWNER, i), OITM(IS_QUANTITY, i), OITM(IS_EQUIPPED, i), OITM(IS_PRICE, i), row);
+    } else {
+#pragma unroll
+      for (int k = 0; k < IA_N_OBS; k++) row[k] = 0;
+    }
+    uint4 *dst = (uint4 *)(s_mkt + j * IA_N_OBS);
+    dst[0] = make_uint4(pack2(row[0], row[1]), pack2(row[2], row[3]), pack2(row[4], row[5]), pack2(row[6], row[7]));
+    dst[1] = make_uint4(pack2(row[8], row[9]), pack2(row[10], row[11]), pack2(row[12], row[13]), pack2(row[14], row[15]));
+  }
+  __syncthreads();
+
+  // ---- per-agent records: one warp per agent -------------------------------------------
+  uint8_t *stage = s_stage_all + (size_t)warp * stage_bytes;
+  int8_t *m = (int8_t *)stage;
+  uint16_t *s_vis = s_vis_all + (size_t)warp * (((L.n_ent * 2 + 15) & ~15) / 2);
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  const int wrapper = c[NC_WRAPPER];
+  for (int p = warp; p < P; p += NW) {
+    const size_t a = (size_t)env * P + p;
+    uint8_t *rec = prm.obs + a * L.stride;
+    if (s_status[p] != ES_ALIVE) {           // dead or absent agents get the zero pad record
+      for (int k = lane; k < L.stride / 16; k += 32) st16(rec + k * 16, zero4);
+      continue;
+    }
+    const int r0 = OENT(EA_ROW, p), c0 = OENT(EA_COL, p), my_id = OENT(EA_ID, p), my_gold = OENT(EA_GOLD, p);
+    // visible entities: table rows inside the window, in table order, first n_ent
+    int n_vis = 0;
+    for (int base = 0; base < R; base += 32) {
+      int row = base + lane;
+      bool in = row < R && s_status[row] == ES_ALIVE && nm_iabs(OENT(EA_ROW, row) - r0) <= vis && nm_iabs(OENT(EA_COL, row) - c0) <= vis;
+      unsigned bm = __ballot_sync(0xffffffffu, in);
+      if (in) { int idx = n_vis + __popc(bm & ((1u << lane) - 1)); if (idx < L.n_ent) s_vis[idx] = (uint16_t)row; }
+      n_vis += __popc(bm);
+    }
+    n_vis = min(n_vis, L.n_ent);
+    const int n_inv = min(s_invn[p], NINV);
+    const uint16_t *inv = s_inv + p * NINV;
+    for (int k = lane; k < stage_bytes / 16; k += 32) ((uint4 *)stage)[k] = zero4;
+    __syncwarp();
+    // ---- ActionTargets ----
+    if (lane < 3) m[L.m_style + lane] = 1;
+    {
+      bool any = false;
+      bool immune = OENT(EA_TIME_ALIVE, p) < c[NC_SPAWN_IMMUNITY];
+      for (int i = lane; i < n_vis; i += 32) {
+        int row = s_vis[i], id = OENT(EA_ID, row);
+        bool same = OENT(EA_ROW, row) == r0 && OENT(EA_COL, row) == c0;
+        bool ok = nm_linf(OENT(EA_ROW, row), OENT(EA_COL, row), r0, c0) <= c[NC_REACH] && id != my_id && !(immune && id > 0);
+        m[L.m_target + i] = ok; any |= ok;
+        bool give = n_inv > 0 && same && OENT(EA_NPC_TYPE, row) == 0 && id != my_id;
+        m[L.m_give_target + i] = give; m[L.m_gold_target + i] = give;
+      }
+      any = __any_sync(0xffffffffu, any);
+      if (lane == 0) { m[L.m_target + L.n_ent] = any ? 0 : 1; m[L.m_give_target + L.n_ent] = 1; m[L.m_gold_target + L.n_ent] = 1; }
+    }
+    {
+      bool full = n_inv >= NINV;
+      // does a market listing match an ammo stack I own?
+      auto ammo_match = [&](int j) -> bool {
+        int type = s_mkt[j * IA_N_OBS + IA_TYPE], level = s_mkt[j * IA_N_OBS + IA_LEVEL];
+        if (!it_ammo(type) || s_mkt[j * IA_N_OBS + IA_OWNER] == my_id) return false;
+        for (int i = 0; i < n_inv; i++) if (OITM(IS_TYPE, inv[i]) == type && OITM(IS_LEVEL, inv[i]) == level) return true;
+        return false;
+      };
+      bool any_ammo = false;
+      if (full) { for (int j = lane; j < n_mkt; j += 32) any_ammo |= ammo_match(j); any_ammo = __any_sync(0xffffffffu, any_ammo); }
+      if (lane == 0) m[L.m_buy + L.n_mkt] = 1;
+      if (!(full && !any_ammo))
+        for (int j = lane; j < n_mkt; j += 32) {
+          bool ok = s_mkt[j * IA_N_OBS + IA_OWNER] != my_id && s_mkt[j * IA_N_OBS + IA_LISTED_PRICE] <= my_gold;
+          if (full) ok = ok && ammo_match(j);
+          m[L.m_buy + j] = ok;
+        }
+    }
+    if (lane < n_inv) {
+      int i = inv[lane];
+      bool eq = OITM(IS_EQUIPPED, i) != 0, listed = OITM(IS_PRICE, i) != 0;
+      m[L.m_destroy + lane] = !eq;
+      m[L.m_give_item + lane] = !eq && !listed;
+      m[L.m_sell_item + lane] = !eq && !listed;
+      m[L.m_use + lane] = !listed && OITM(IS_LEVEL, i) <= o_use_level(o, p, OITM(IS_TYPE, i));
+    }
+    if (lane == 0) { m[L.m_destroy + L.n_inv] = 1; m[L.m_give_item + L.n_inv] = 1; m[L.m_sell_item + L.n_inv] = 1; m[L.m_use + L.n_inv] = 1; }
+    for (int g = lane; g < L.n_price; g += 32) { m[L.m_gold_price + g] = (g == 0 || g < my_gold) ? 1 : 0; m[L.m_sell_price + g] = 1; }
+    if (lane < 5) m[L.m_move + lane] = !nm_impassible(s_map[(r0 + c_dir_dr[lane]) * S + c0 + c_dir_dc[lane]]);
+    __syncwarp();
+    // RewardWrapper.observation hooks
+    if (wrapper == NW_TAKERU && c[NC_DISABLE_GIVE]) {
+      for (int i = lane; i < L.n_inv; i += 32) m[L.m_give_item + i] = 0;
+      for (int i = lane; i < L.n_ent; i += 32) { m[L.m_give_target + i] = 0; m[L.m_gold_target + i] = 0; }
+      for (int g = 1 + lane; g < L.n_price; g += 32) m[L.m_gold_price + g] = 0;
+    } else if (wrapper == NW_START_KIT) {
+      if (lane == 0) m[L.m_sell_price + prm.stats[a * ST_N + ST_PREV_PRICE]] = 0;
+    }
+    __syncwarp();
+    for (int k = lane; k < stage_bytes / 16; k += 32) st16(rec + k * 16, ((const uint4 *)stage)[k]);
+    // ---- AgentId, CurrentTick ----
+    if (lane == 0) st16(rec + L.o_ids, make_uint4(pack2(my_id, tick), 0, 0, 0));
+    // ---- Entity rows ----
+    {
+      const int n_chunks = nm_align16(L.n_ent * EA_N_OBS * 2) / 16, n_el = n_vis * EA_N_OBS;
+      for (int k = lane; k < n_chunks; k += 32) {
+        int e0 = k * 8;
+        uint4 v = zero4;
+        if (e0 < n_el) {
+          int vals[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            int e = e0 + j, row = e / EA_N_OBS, col = e - row * EA_N_OBS;
+            vals[j] = e < n_el ? (int)OENT(col, s_vis[row]) : 0;
+          }
+          v = make_uint4(pack2(vals[0], vals[1]), pack2(vals[2], vals[3]), pack2(vals[4], vals[5]), pack2(vals[6], vals[7]));
+        }
+        st16(rec + L.o_entity + k * 16, v);
+      }
+    }
+    // ---- Inventory rows ----
+    for (int k = lane; k < L.n_inv * 2; k += 32) {
+      int slot = k >> 1;
+      uint4 v = zero4;
+      if (slot < n_inv) {
+        int i = inv[slot];
+        int16_t row[IA_N_OBS];
+        item_obs_row(c, i, OITM(IS_TYPE, i), OITM(IS_LEVEL, i), OITM(IS_OWNER, i), OITM(IS_QUANTITY, i), OITM(IS_EQUIPPED, i), OITM(IS_PRICE, i), row);
+        int h = (k & 1) * 8;
+        v = make_uint4(pack2(row[h], row[h + 1]), pack2(row[h + 2], row[h + 3]), pack2(row[h + 4], row[h + 5]), pack2(row[h + 6], row[h + 7]));
+      }
+      st16(rec + L.o_inventory + k * 16, v);
+    }
+    // ---- Market block ----
+    for (int k = lane; k < L.n_mkt * 2; k += 32) st16(rec + L.o_market + k * 16, ((const uint4 *)s_mkt)[k]);
+    // ---- Task embedding ----
+    {
+      const uint4 *src = (const uint4 *)(prm.embed + (size_t)prm.task_id[a] * L.task_dim);
+      for (int k = lane; k < L.task_dim * 2 / 16; k += 32) st16(rec + L.o_task + k * 16, __ldg(src + k));
+    }
+    // ---- Tile window ----
+    {
+      const int n_el = L.win * L.win * 3, n_chunks = nm_align16(n_el * 2) / 16;
+      for (int k = lane; k < n_chunks; k += 32) {
+        int vals[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          int e = k * 8 + j;
+          int w = e / 3, comp = e - w * 3;
+          int dr = w / L.win - vis, dc = w % L.win - vis;
+          int v = comp == 0 ? r0 + dr : comp == 1 ? c0 + dc : (e < n_el ? (int)s_map[(r0 + dr) * S + c0 + dc] : 0);
+          vals[j] = e < n_el ? v : 0;
+        }
+        st16(rec + L.o_tile + k * 16, make_uint4(pack2(vals[0], vals[1]), pack2(vals[2], vals[3]), pack2(vals[4], vals[5]), pack2(vals[6], vals[7])));
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ============================================================= action sampler kernel ===
+// uniform-random valid action per head from the ActionTargets masks (BASELINE.json config 2:
+// "uniform-random valid actions ... counter-based RNG keyed (seed, env, tick, agent, head)")
+extern "C" __global__ void nmmo_sample_kernel(const __grid_constant__ NmParams prm, uint64_t seed, int32_t *out) {
+  const nm_obs_layout &L = prm.L;
+  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)prm.E * prm.P * AC_N;
+  if (gid >= total) return;
+  int h = (int)(gid % AC_N);
+  long long a = gid / AC_N;
+  int env = (int)(a / prm.P), p = (int)(a % prm.P);
+  int off, len;
+  switch (h) {
+    case AC_ATTACK_STYLE: off = L.m_style; len = 3; break;
+    case AC_ATTACK_TARGET: off = L.m_target; len = L.n_ent + 1; break;
+    case AC_BUY_ITEM: off = L.m_buy; len = L.n_mkt + 1; break;
+    case AC_DESTROY_ITEM: off = L.m_destroy; len = L.n_inv + 1; break;
+    case AC_GIVE_ITEM: off = L.m_give_item; len = L.n_inv + 1; break;
+    case AC_GIVE_TARGET: off = L.m_give_target; len = L.n_ent + 1; break;
+    case AC_GOLD_PRICE: off = L.m_gold_price; len = L.n_price; break;
+    case AC_GOLD_TARGET: off = L.m_gold_target; len = L.n_ent + 1; break;
+    case AC_MOVE_DIR: off = L.m_move; len = NM_DIR_N; break;
+    case AC_SELL_ITEM: off = L.m_sell_item; len = L.n_inv + 1; break;
+    case AC_SELL_PRICE: off = L.m_sell_price; len = L.n_price; break;
+    default: off = L.m_use; len = L.n_inv + 1; break;
+  }
+  const int8_t *m = (const int8_t *)(prm.obs + (size_t)a * L.stride) + off;
+  int cnt = 0;
+  for (int i = 0; i < len; i++) cnt += m[i] != 0;
+  int pick = 0;
+  if (cnt > 0) {
+    int tick = prm.scalars[(size_t)env * NM_SC_N + SC_TICK];
+    int j = nm_bounded(nm_hash_draw(seed + (uint64_t)(prm.env_base + env), (uint32_t)tick, RS_ACTION, (uint32_t)p, (uint32_t)h), cnt);
+    for (int i = 0; i < len; i++) if (m[i] && j-- == 0) { pick = i; break; }
+  }
+  out[gid] = pick;
+}

@@ -1,0 +1,1247 @@
+// nmmo_step.cu -- one CTA steps one environment: the whole Realm.step + reward/stat wrapper.
+//
+// What it replaces in the reference (all per-env, per-agent Python today):
+//   nmmo.Env.step  (call site reinforcement_learning/stat_wrapper.py:64)   -> phases 0..13
+//   BaseStatWrapper.step / _process_stats_and_early_stop (stat_wrapper.py:57-185),
+//   process_event_log (:216-288), count_unique_events (:295-310)           -> phases 14..15
+//   agent_zoo/{takeru,neurips23_start_kit}/reward_wrapper.py reward hooks  -> phase 15
+//
+// Execution model.  The environment's tables are pulled into shared memory by three TMA bulk
+// copies, every phase runs out of shared memory, and the tables are pushed back with bulk
+// stores.  Phases whose reference semantics are order-free across agents (validation, NPC
+// decide, resource update, Use, Destroy, Sell, cull, respawn, event folding, rewards) run one
+// thread per entity.  Phases the reference executes in entity-id order (harvest drops, Buy,
+// Give, Attack, Move with one-entity-per-tile) are resolved by warp 0 in id order: candidates
+// are found 32 at a time with a ballot and the elected lane applies them, so an idle entity
+// costs nothing.
+#include "nmmo_device.cuh"
+
+namespace {
+
+enum { A_USE = 0, A_DESTROY, A_SELL_ITEM, A_SELL_PRICE, A_BUY, A_GIVE_ITEM, A_GIVE_TARGET, A_GOLD_AMT,
+       A_GOLD_TARGET, A_ATT_STYLE, A_ATT_TARGET, A_MOVE, A_N };
+
+struct Ctx {
+  const NmParams *p;
+  const int32_t *c;
+  int env, P, N, R, S, CAP, NINV;
+  int16_t *ent, *item;
+  uint8_t *map;
+  uint32_t *occ, *used, *fresh;
+  uint16_t *inv;
+  uint8_t *invn;
+  int16_t *act;
+  int8_t *npc_move;
+  int16_t *npc_att;
+  uint2 *ev;
+  int *sc;            // shared scalars: [0] nev, [1] overflow, [2] n_danger, [3] next_npc_id, [4] npc_count
+  int *duniq;
+  uint64_t seed;
+  int tick;
+  int inj_lo, inj_hi;
+};
+#define ENT(col, row) ctx.ent[(col) * ctx.R + (row)]
+#define ITM(col, row) ctx.item[(col) * ctx.CAP + (row)]
+
+__device__ uint32_t draw(const Ctx &ctx, uint32_t site, uint32_t idx, uint32_t k) {
+  if (ctx.inj_hi > ctx.inj_lo) {
+    uint64_t key = nm_rng_key((uint32_t)ctx.tick, site, idx, k);
+    int lo = ctx.inj_lo, hi = ctx.inj_hi - 1;
+    while (lo <= hi) {
+      int mid = (lo + hi) >> 1;
+      uint64_t kk = ctx.p->inj_keys[mid];
+      if (kk == key) return ctx.p->inj_vals[mid];
+      if (kk < key) lo = mid + 1; else hi = mid - 1;
+    }
+  }
+  return nm_hash_draw(ctx.seed, (uint32_t)ctx.tick, site, idx, k);
+}
+
+// ------------------------------------------------------------------ event ring ------
+__device__ void emit(const Ctx &ctx, int prow, int code, int type, int level, int number, int gold, int target) {
+  int i = atomicAdd(&ctx.sc[0], 1);
+  if (i >= NM_EV_CAP) { ctx.sc[1] = 1; return; }
+  uint32_t w0 = (uint32_t)prow | ((uint32_t)nm_dense_event(code) << 8) | ((uint32_t)type << 16) |
+                ((uint32_t)(level & 15) << 24) | (target > 0 ? (1u << 28) : 0u) | (target < 0 ? (1u << 29) : 0u);
+  uint32_t w1 = (uint32_t)(uint16_t)number | ((uint32_t)(uint16_t)gold << 16);
+  ctx.ev[i] = make_uint2(w0, w1);
+}
+
+// ----------------------------------------------------------- item / inventory -------
+__device__ __forceinline__ bool row_used(const Ctx &ctx, int row) { return (ctx.used[row >> 5] >> (row & 31)) & 1u; }
+__device__ int item_alloc(const Ctx &ctx) {          // lowest free row; sequential phases only
+  int words = (ctx.CAP + 31) >> 5;
+  for (int w = 0; w < words; w++) {
+    uint32_t freebits = ~ctx.used[w];
+    if (freebits) {
+      int row = (w << 5) + __ffs(freebits) - 1;
+      if (row >= ctx.CAP) return -1;
+      ctx.used[w] |= 1u << (row & 31);
+      ctx.fresh[w] |= 1u << (row & 31);
+      return row;
+    }
+  }
+  return -1;
+}
+__device__ void inv_remove(const Ctx &ctx, int owner_row, int row) {
+  int n = ctx.invn[owner_row];
+  uint16_t *l = ctx.inv + owner_row * ctx.NINV;
+  for (int i = 0; i < n; i++)
+    if (l[i] == row) { l[i] = l[n - 1]; ctx.invn[owner_row] = (uint8_t)(n - 1); return; }
+}
+__device__ void inv_add(const Ctx &ctx, int owner_row, int row) {
+  int n = ctx.invn[owner_row];
+  if (n < ctx.NINV) { ctx.inv[owner_row * ctx.NINV + n] = (uint16_t)row; ctx.invn[owner_row] = (uint8_t)(n + 1); }
+}
+__device__ int find_stack(const Ctx &ctx, int owner_row, int type, int level, int exclude) {
+  int n = ctx.invn[owner_row];
+  const uint16_t *l = ctx.inv + owner_row * ctx.NINV;
+  for (int i = 0; i < n; i++) {
+    int r = l[i];
+    if (r != exclude && ITM(IS_TYPE, r) == type && ITM(IS_LEVEL, r) == level) return r;
+  }
+  return -1;
+}
+__device__ int equip_col(int type) {
+  if (type == IT_HAT) return EA_EQ_HAT;
+  if (type == IT_TOP) return EA_EQ_TOP;
+  if (type == IT_BOTTOM) return EA_EQ_BOTTOM;
+  if (it_weapon(type) || it_tool(type)) return EA_EQ_HELD;
+  if (it_ammo(type)) return EA_EQ_AMMO;
+  return -1;
+}
+// frees the row; the owner's list and equipment slot are fixed up (owner_row < 0: no owner)
+__device__ void item_destroy(const Ctx &ctx, int row) {
+  int owner = ITM(IS_OWNER, row);
+  if (owner > 0) {
+    int orow = owner - 1;
+    if (ITM(IS_EQUIPPED, row)) {
+      int col = equip_col(ITM(IS_TYPE, row));
+      if (col >= 0 && ENT(col, orow) == row + 1) ENT(col, orow) = 0;
+    }
+    inv_remove(ctx, orow, row);
+  }
+#pragma unroll
+  for (int k = 0; k < IS_N; k++) ITM(k, row) = 0;
+  atomicAnd(&ctx.used[row >> 5], ~(1u << (row & 31)));
+}
+// move an existing row into new_owner's inventory (ammo merges into an existing stack)
+__device__ void inv_receive_existing(const Ctx &ctx, int new_owner_row, int row) {
+  int type = ITM(IS_TYPE, row);
+  int old_owner = ITM(IS_OWNER, row);
+  if (it_ammo(type)) {
+    int st = find_stack(ctx, new_owner_row, type, ITM(IS_LEVEL, row), row);
+    if (st >= 0) { ITM(IS_QUANTITY, st) = (int16_t)(ITM(IS_QUANTITY, st) + ITM(IS_QUANTITY, row)); item_destroy(ctx, row); return; }
+  }
+  if (old_owner > 0) inv_remove(ctx, old_owner - 1, row);
+  ITM(IS_OWNER, row) = (int16_t)(new_owner_row + 1);
+  inv_add(ctx, new_owner_row, row);
+}
+__device__ void inv_receive_new(const Ctx &ctx, int owner_row, int type, int level, int qty) {
+  if (it_ammo(type)) {
+    int st = find_stack(ctx, owner_row, type, level, -1);
+    if (st >= 0) { ITM(IS_QUANTITY, st) = (int16_t)(ITM(IS_QUANTITY, st) + qty); return; }
+  }
+  int row = item_alloc(ctx);
+  if (row < 0) return;
+  ITM(IS_TYPE, row) = (int16_t)type; ITM(IS_LEVEL, row) = (int16_t)level; ITM(IS_OWNER, row) = (int16_t)(owner_row + 1);
+  ITM(IS_QUANTITY, row) = (int16_t)qty; ITM(IS_EQUIPPED, row) = 0; ITM(IS_PRICE, row) = 0; ITM(IS_LIST_TICK, row) = 0;
+  inv_add(ctx, owner_row, row);
+}
+// item argument of a validated action: must still be the object the agent saw
+__device__ int valid_item_ref(const Ctx &ctx, int item_id, int owner) {
+  if (item_id <= 0 || item_id > ctx.CAP) return -1;
+  int row = item_id - 1;
+  if (!row_used(ctx, row) || ((ctx.fresh[row >> 5] >> (row & 31)) & 1u)) return -1;
+  if (owner && ITM(IS_OWNER, row) != owner) return -1;
+  return row;
+}
+
+// -------------------------------------------------------------------- entities ------
+__device__ __forceinline__ bool ent_alive(const Ctx &ctx, int row) {
+  return row >= 0 && ENT(EA_STATUS, row) == ES_ALIVE && ENT(EA_HEALTH, row) > 0;
+}
+__device__ int level_at_exp(const Ctx &ctx, int exp) {
+  int lmax = ctx.c[NC_LEVEL_MAX];
+  if (exp >= ctx.c[NC_EXP_THRESH0 + lmax - 1]) return lmax;
+  int lvl = 0;
+  while (lvl < lmax && exp >= ctx.c[NC_EXP_THRESH0 + lvl]) lvl++;
+  return lvl;
+}
+__device__ void add_xp(const Ctx &ctx, int row, int level_col, int skill_id, int xp) {
+  int lmax = ctx.c[NC_LEVEL_MAX];
+  int nexp = min(ENT(level_col + 1, row) + xp, ctx.c[NC_EXP_THRESH0 + lmax - 1]);
+  ENT(level_col + 1, row) = (int16_t)nexp;
+  int nl = level_at_exp(ctx, nexp);
+  if (nl > ENT(level_col, row)) {
+    ENT(level_col, row) = (int16_t)nl;
+    if (row < ctx.P) emit(ctx, row, EV_LEVEL_UP, skill_id, nl, 0, 0, 0);
+  }
+}
+__device__ int attack_level(const Ctx &ctx, int row) {
+  return max(ENT(EA_MELEE_LEVEL, row), max(ENT(EA_RANGE_LEVEL, row), ENT(EA_MAGE_LEVEL, row)));
+}
+__device__ int use_level(const Ctx &ctx, int row, int type) {
+  switch (type) {
+    case IT_SPEAR: case IT_WHETSTONE: return ENT(EA_MELEE_LEVEL, row);
+    case IT_BOW: case IT_ARROW: return ENT(EA_RANGE_LEVEL, row);
+    case IT_WAND: case IT_RUNES: return ENT(EA_MAGE_LEVEL, row);
+    case IT_ROD: return ENT(EA_FISHING_LEVEL, row);
+    case IT_GLOVES: return ENT(EA_HERBALISM_LEVEL, row);
+    case IT_PICKAXE: return ENT(EA_PROSPECTING_LEVEL, row);
+    case IT_AXE: return ENT(EA_CARVING_LEVEL, row);
+    case IT_CHISEL: return ENT(EA_ALCHEMY_LEVEL, row);
+    default: {
+      int l = 1;
+      for (int col = EA_MELEE_LEVEL; col <= EA_ALCHEMY_LEVEL; col += 2) l = max(l, (int)ENT(col, row));
+      return l;
+    }
+  }
+}
+__device__ __forceinline__ int tile_at(const Ctx &ctx, int r, int c) { return ctx.map[r * ctx.S + c]; }
+__device__ __forceinline__ bool occ_get(const Ctx &ctx, int r, int c) { int i = r * ctx.S + c; return (ctx.occ[i >> 5] >> (i & 31)) & 1u; }
+__device__ __forceinline__ void occ_set(const Ctx &ctx, int r, int c) { int i = r * ctx.S + c; atomicOr(&ctx.occ[i >> 5], 1u << (i & 31)); }
+__device__ __forceinline__ void occ_clr(const Ctx &ctx, int r, int c) { int i = r * ctx.S + c; atomicAnd(&ctx.occ[i >> 5], ~(1u << (i & 31))); }
+
+// ------------------------------------------------------------------ harvesting ------
+__device__ void process_drops(const Ctx &ctx, int prow, int matl, int level_col, int skill_id) {
+  int tool_type = 0, ammo = 0, weapon = 0, consumable = 0;
+  switch (matl) {
+    case MT_FISH: tool_type = IT_ROD; consumable = IT_RATION; break;
+    case MT_HERB: tool_type = IT_GLOVES; consumable = IT_POTION; break;
+    case MT_ORE: tool_type = IT_PICKAXE; ammo = IT_WHETSTONE; weapon = IT_WAND; break;
+    case MT_TREE: tool_type = IT_AXE; ammo = IT_ARROW; weapon = IT_SPEAR; break;
+    case MT_CRYSTAL: tool_type = IT_CHISEL; ammo = IT_RUNES; weapon = IT_BOW; break;
+  }
+  int level = 1;
+  int held = ENT(EA_EQ_HELD, prow);
+  if (held && ITM(IS_TYPE, held - 1) == tool_type) level = min(1 + ITM(IS_LEVEL, held - 1), ctx.c[NC_LEVEL_MAX]);
+  int first = consumable ? consumable : ammo;
+  if (ctx.invn[prow] < ctx.NINV) {
+    inv_receive_new(ctx, prow, first, level, 1);
+    emit(ctx, prow, EV_HARVEST_ITEM, first, level, 1, 0, 0);
+  }
+  if (weapon) {
+    uint32_t u = draw(ctx, RS_HARVEST, (uint32_t)prow, (uint32_t)skill_id);
+    if (u < (uint32_t)ctx.c[NC_WEAPON_DROP_THR] && ctx.invn[prow] < ctx.NINV) {
+      inv_receive_new(ctx, prow, weapon, level, 1);
+      emit(ctx, prow, EV_HARVEST_ITEM, weapon, level, 1, 0, 0);
+    }
+  }
+  add_xp(ctx, prow, level_col, skill_id, consumable ? ctx.c[NC_XP_CONSUMABLE] : ctx.c[NC_XP_AMMO]);
+}
+__device__ bool tile_harvest(const Ctx &ctx, int r, int c, int matl) {
+  int i = r * ctx.S + c;
+  if (ctx.map[i] != matl) return false;
+  ctx.map[i] = (uint8_t)(matl - 1);
+  return true;
+}
+// the id-ordered part of Player.update: anything that depletes a tile or allocates an item
+__device__ void player_harvest(const Ctx &ctx, int p) {
+  int r = ENT(EA_ROW, p), c = ENT(EA_COL, p);
+  if (tile_harvest(ctx, r, c, MT_FOILAGE)) {
+    ENT(EA_FOOD, p) = (int16_t)min(ctx.c[NC_RES_BASE], ENT(EA_FOOD, p) + ctx.c[NC_RES_HARVEST_RESTORE]);
+    emit(ctx, p, EV_EAT_FOOD, 0, 0, 0, 0, 0);
+  }
+  bool fish = false;
+  fish |= tile_harvest(ctx, r - 1, c, MT_FISH);
+  fish |= tile_harvest(ctx, r + 1, c, MT_FISH);
+  fish |= tile_harvest(ctx, r, c - 1, MT_FISH);
+  fish |= tile_harvest(ctx, r, c + 1, MT_FISH);
+  if (fish) process_drops(ctx, p, MT_FISH, EA_FISHING_LEVEL, SK_FISHING);
+  if (tile_harvest(ctx, r, c, MT_HERB)) process_drops(ctx, p, MT_HERB, EA_HERBALISM_LEVEL, SK_HERBALISM);
+  if (tile_harvest(ctx, r, c, MT_ORE)) process_drops(ctx, p, MT_ORE, EA_PROSPECTING_LEVEL, SK_PROSPECTING);
+  if (tile_harvest(ctx, r, c, MT_TREE)) process_drops(ctx, p, MT_TREE, EA_CARVING_LEVEL, SK_CARVING);
+  if (tile_harvest(ctx, r, c, MT_CRYSTAL)) process_drops(ctx, p, MT_CRYSTAL, EA_ALCHEMY_LEVEL, SK_ALCHEMY);
+}
+
+// ---------------------------------------------------------------------- npc ai ------
+__device__ bool valid_target(const Ctx &ctx, int row, int targ_id, int rng) {
+  if (targ_id <= 0 || targ_id > ctx.P) return false;      // NPCs only ever track players
+  int t = targ_id - 1;
+  if (!ent_alive(ctx, t)) return false;
+  return nm_linf(ENT(EA_ROW, row), ENT(EA_COL, row), ENT(EA_ROW, t), ENT(EA_COL, t)) <= rng;
+}
+// first player met by the reference's ring scan (nmmo/systems/ai/utils.py closestTarget)
+__device__ int closest_target(const Ctx &ctx, int row, int rng) {
+  int sr = ENT(EA_ROW, row), sc = ENT(EA_COL, row);
+  int best = 0x7fffffff, best_id = 0;
+  for (int p = 0; p < ctx.P; p++) {
+    if (!ent_alive(ctx, p)) continue;
+    int dr = ENT(EA_ROW, p) - sr, dc = ENT(EA_COL, p) - sc;
+    int d = max(nm_iabs(dr), nm_iabs(dc));
+    if (d > rng) continue;
+    int rk = 0x7fffffff;
+    if (dc == -d) rk = min(rk, (dr + d) * 4 + 0);
+    if (dc == d) rk = min(rk, (dr + d) * 4 + 1);
+    if (dr == -d) rk = min(rk, (dc + d) * 4 + 2);
+    if (dr == d) rk = min(rk, (dc + d) * 4 + 3);
+    rk += d * 1024;
+    if (rk < best) { best = rk; best_id = p + 1; }
+  }
+  return best_id;
+}
+// A* with the reference's 100-expansion budget; per-thread hash map + binary heap in local memory
+__device__ int astar_dir(const Ctx &ctx, int sr, int sc, int gr, int gc) {
+  const int HN = 512, CUTOFF = 100;
+  uint16_t hk[HN]; uint8_t hcost[HN]; int8_t hback[HN];
+  uint32_t heap[4 * CUTOFF + 12];
+  if (sr == gr && sc == gc) return -1;
+  for (int i = 0; i < HN; i++) hk[i] = 0;
+  auto slot_of = [&](int r, int c, bool insert) -> int {
+    uint16_t key = (uint16_t)(((r << 8) | c) + 1);
+    int h = (int)((key * 40503u) >> 7) & (HN - 1);
+    while (hk[h] != 0 && hk[h] != key) h = (h + 1) & (HN - 1);
+    if (hk[h] == 0) { if (!insert) return -1; hk[h] = key; hcost[h] = 255; hback[h] = -1; }
+    return h;
+  };
+  int hn = 0;
+  auto push = [&](uint32_t x) {
+    int i = hn++;
+    heap[i] = x;
+    while (i > 0) { int par = (i - 1) >> 1; if (heap[i] >= heap[par]) break; uint32_t t = heap[i]; heap[i] = heap[par]; heap[par] = t; i = par; }
+  };
+  auto pop = [&]() -> uint32_t {
+    uint32_t top = heap[0];
+    heap[0] = heap[--hn];
+    int i = 0;
+    for (;;) {
+      int l = 2 * i + 1, r = l + 1, m = i;
+      if (l < hn && heap[l] < heap[m]) m = l;
+      if (r < hn && heap[r] < heap[m]) m = r;
+      if (m == i) break;
+      uint32_t t = heap[i]; heap[i] = heap[m]; heap[m] = t; i = m;
+    }
+    return top;
+  };
+  const int adr[4] = {-1, 1, 0, 0}, adc[4] = {0, 0, -1, 1};
+  push((uint32_t)((sr << 8) | sc));
+  { int s = slot_of(sr, sc, true); hcost[s] = 0; }
+  int goal_r = gr, goal_c = gc, close_r = sr, close_c = sc;
+  int close_h = nm_iabs(sr - gr) + nm_iabs(sc - gc), close_cost = close_h;
+  int cutoff = CUTOFF;
+  while (hn > 0) {
+    cutoff--;
+    if (cutoff <= 0) {
+      int g = slot_of(gr, gc, false);
+      if (!(g >= 0 && hback[g] >= 0)) { goal_r = close_r; goal_c = close_c; }
+      break;
+    }
+    uint32_t cur = pop();
+    int cr = (cur >> 8) & 255, cc = cur & 255;
+    if (cr == gr && cc == gc) break;
+    int ccost = hcost[slot_of(cr, cc, false)];
+    for (int k = 0; k < 4; k++) {
+      int nr = cr + adr[k], nc = cc + adc[k];
+      if (nr < 0 || nc < 0 || nr >= ctx.S || nc >= ctx.S) continue;
+      if (nm_impassible(tile_at(ctx, nr, nc))) continue;
+      int ncost = ccost + 1;
+      int s = slot_of(nr, nc, true);
+      if (hcost[s] == 255 || ncost < hcost[s]) {
+        hcost[s] = (uint8_t)ncost;
+        int h = nm_linf(gr, gc, nr, nc);
+        int pri = ncost + h;
+        if (h < close_h || (h == close_h && pri < close_cost)) { close_r = nr; close_c = nc; close_h = h; close_cost = pri; }
+        push(((uint32_t)pri << 16) | (uint32_t)((nr << 8) | nc));
+        hback[s] = (int8_t)k;
+      }
+    }
+  }
+  int r = goal_r, c = goal_c;
+  for (;;) {
+    int s = slot_of(r, c, false);
+    if (s < 0 || hback[s] < 0) break;
+    int pr = r - adr[hback[s]], pc = c - adc[hback[s]];
+    if (pr == sr && pc == sc) break;
+    r = pr; c = pc;
+  }
+  int dr = r - sr, dc = c - sc;
+  if (dr == -1 && dc == 0) return 0;
+  if (dr == 1 && dc == 0) return 1;
+  if (dr == 0 && dc == 1) return 2;
+  if (dr == 0 && dc == -1) return 3;
+  return -1;
+}
+__device__ void npc_decide(const Ctx &ctx, int row) {
+  int vis = ctx.c[NC_NPC_VISION];
+  int n = row - ctx.P;
+  uint32_t k = 0;
+  ctx.npc_move[n] = -1;
+  ctx.npc_att[n] = 0;
+  int attacker = valid_target(ctx, row, ENT(EA_ATTACKER_ID, row), vis) ? ENT(EA_ATTACKER_ID, row) : 0;
+  int target = ENT(EA_NPC_TARGET, row);
+  if (!valid_target(ctx, row, target, vis)) target = 0;
+  bool hunt = false;
+  int type = ENT(EA_NPC_TYPE, row);
+  if (type == 2) { if (attacker) { target = attacker; hunt = true; } }
+  else if (type == 3) { if (!target) target = closest_target(ctx, row, vis); if (target) hunt = true; }
+  ENT(EA_NPC_TARGET, row) = (int16_t)target;
+  int r = ENT(EA_ROW, row), c = ENT(EA_COL, row);
+  if (!hunt) {
+    int start = nm_bounded(draw(ctx, RS_NPC_DECIDE, (uint32_t)row, k++), 4);
+    int pick = start;
+    for (int i = 0; i < 4; i++) {
+      int d = (start + i) & 3;
+      if (!nm_impassible(tile_at(ctx, r + c_dir_dr[d], c + c_dir_dc[d]))) { pick = d; break; }
+    }
+    ctx.npc_move[n] = (int8_t)pick;
+    return;
+  }
+  int t = target - 1;
+  int tr = ENT(EA_ROW, t), tc = ENT(EA_COL, t);
+  int dist = nm_linf(r, c, tr, tc);
+  if (dist == 0) ctx.npc_move[n] = (int8_t)nm_bounded(draw(ctx, RS_NPC_DECIDE, (uint32_t)row, k++), 4);
+  else if (dist > 1) ctx.npc_move[n] = (int8_t)astar_dir(ctx, r, c, tr, tc);
+  if (dist <= ctx.c[NC_REACH]) ctx.npc_att[n] = (int16_t)(t + 1);
+}
+
+// --------------------------------------------------------------------- actions ------
+__device__ void act_use(const Ctx &ctx, int p, int item_id) {
+  int row = valid_item_ref(ctx, item_id, p + 1);
+  if (row < 0) return;
+  int type = ITM(IS_TYPE, row), level = ITM(IS_LEVEL, row);
+  if (ITM(IS_PRICE, row) > 0 || level > use_level(ctx, p, type)) return;
+  if (it_consumable(type)) {
+    emit(ctx, p, EV_CONSUME_ITEM, type, level, ITM(IS_QUANTITY, row), 0, 0);
+    int restore = ctx.c[NC_RESTORE_BASE] + level * ctx.c[NC_RESTORE_LEVEL];
+    int base = ctx.c[NC_RES_BASE];
+    if (type == IT_RATION) {
+      ENT(EA_FOOD, p) = (int16_t)min(base, ENT(EA_FOOD, p) + restore);
+      ENT(EA_WATER, p) = (int16_t)min(base, ENT(EA_WATER, p) + restore);
+    } else ENT(EA_HEALTH, p) = (int16_t)min(base, ENT(EA_HEALTH, p) + restore);
+    item_destroy(ctx, row);
+    return;
+  }
+  int col = equip_col(type);
+  if (col < 0) return;
+  if (ITM(IS_EQUIPPED, row)) { ITM(IS_EQUIPPED, row) = 0; ENT(col, p) = 0; return; }
+  int cur = ENT(col, p);
+  if (cur) ITM(IS_EQUIPPED, cur - 1) = 0;
+  ITM(IS_EQUIPPED, row) = 1; ENT(col, p) = (int16_t)(row + 1);
+  emit(ctx, p, EV_EQUIP_ITEM, type, level, ITM(IS_QUANTITY, row), 0, 0);
+}
+__device__ void act_destroy(const Ctx &ctx, int p, int item_id) {
+  int row = valid_item_ref(ctx, item_id, p + 1);
+  if (row < 0 || ITM(IS_EQUIPPED, row)) return;
+  emit(ctx, p, EV_DESTROY_ITEM, ITM(IS_TYPE, row), ITM(IS_LEVEL, row), ITM(IS_QUANTITY, row), 0, 0);
+  item_destroy(ctx, row);
+}
+__device__ void act_sell(const Ctx &ctx, int p, int item_id, int price) {
+  int row = valid_item_ref(ctx, item_id, p + 1);
+  if (row < 0 || ITM(IS_EQUIPPED, row) || ITM(IS_PRICE, row)) return;
+  ITM(IS_PRICE, row) = (int16_t)price; ITM(IS_LIST_TICK, row) = (int16_t)ctx.tick;
+  emit(ctx, p, EV_LIST_ITEM, ITM(IS_TYPE, row), ITM(IS_LEVEL, row), ITM(IS_QUANTITY, row), price, 0);
+}
+__device__ void act_buy(const Ctx &ctx, int p, int item_id) {
+  int row = valid_item_ref(ctx, item_id, 0);
+  if (row < 0) return;
+  int owner = ITM(IS_OWNER, row), price = ITM(IS_PRICE, row);
+  if (owner == 0 || price == 0) return;
+  if (ENT(EA_GOLD, p) < price || owner == p + 1) return;
+  int type = ITM(IS_TYPE, row), level = ITM(IS_LEVEL, row), qty = ITM(IS_QUANTITY, row);
+  if (ctx.invn[p] >= ctx.NINV && !(it_ammo(type) && find_stack(ctx, p, type, level, -1) >= 0)) return;
+  ITM(IS_PRICE, row) = 0; ITM(IS_LIST_TICK, row) = 0;
+  inv_receive_existing(ctx, p, row);
+  ENT(EA_GOLD, p) = (int16_t)(ENT(EA_GOLD, p) - price);
+  ENT(EA_GOLD, owner - 1) = (int16_t)min(32767, ENT(EA_GOLD, owner - 1) + price);
+  emit(ctx, p, EV_BUY_ITEM, type, level, qty, price, 0);
+  emit(ctx, owner - 1, EV_EARN_GOLD, 0, 0, 0, price, 0);
+}
+__device__ void act_give(const Ctx &ctx, int p, int item_id, int target_row1) {
+  int row = valid_item_ref(ctx, item_id, p + 1);
+  if (row < 0 || target_row1 <= 0) return;
+  int t = target_row1 - 1;
+  if (!ent_alive(ctx, t) || t == p) return;
+  if (ITM(IS_EQUIPPED, row) || ITM(IS_PRICE, row)) return;
+  if (ENT(EA_ROW, p) != ENT(EA_ROW, t) || ENT(EA_COL, p) != ENT(EA_COL, t)) return;
+  int type = ITM(IS_TYPE, row), level = ITM(IS_LEVEL, row);
+  if (ctx.invn[t] >= ctx.NINV && !(it_ammo(type) && find_stack(ctx, t, type, level, -1) >= 0)) return;
+  emit(ctx, p, EV_GIVE_ITEM, type, level, ITM(IS_QUANTITY, row), 0, 0);
+  inv_receive_existing(ctx, t, row);
+}
+__device__ void act_give_gold(const Ctx &ctx, int p, int amount, int target_row1) {
+  if (target_row1 <= 0) return;
+  int t = target_row1 - 1;
+  if (!ent_alive(ctx, t) || t == p) return;
+  if (ENT(EA_ROW, p) != ENT(EA_ROW, t) || ENT(EA_COL, p) != ENT(EA_COL, t)) return;
+  if (!(amount > 0 && ENT(EA_GOLD, p) > 0)) return;
+  amount = min(amount, (int)ENT(EA_GOLD, p));
+  ENT(EA_GOLD, p) = (int16_t)(ENT(EA_GOLD, p) - amount);
+  ENT(EA_GOLD, t) = (int16_t)min(32767, ENT(EA_GOLD, t) + amount);
+  emit(ctx, p, EV_GIVE_GOLD, 0, 0, 0, amount, 0);
+}
+__device__ void act_attack(const Ctx &ctx, int a, int style, int target_row1) {
+  const int32_t *c = ctx.c;
+  int t = target_row1 - 1;
+  if (t < 0 || t == a) return;
+  bool a_player = a < ctx.P, b_player = t < ctx.P;
+  if (a_player && b_player && ENT(EA_TIME_ALIVE, t) < c[NC_SPAWN_IMMUNITY]) return;
+  if (!ent_alive(ctx, t)) return;
+  if (nm_linf(ENT(EA_ROW, a), ENT(EA_COL, a), ENT(EA_ROW, t), ENT(EA_COL, t)) > c[NC_REACH]) return;
+  int a_id = ENT(EA_ID, a), b_id = ENT(EA_ID, t);
+  ENT(EA_ATTACKER_ID, t) = (int16_t)a_id;
+  int ex0 = ENT(EA_MELEE_EXP, t), ex1 = ENT(EA_RANGE_EXP, t), ex2 = ENT(EA_MAGE_EXP, t);
+  int num = 1, den = 1;
+  if (!(ex0 == ex1 && ex1 == ex2)) {
+    int idx = 0, best = ex0;
+    if (ex1 > best) { best = ex1; idx = 1; }
+    if (ex2 > best) { best = ex2; idx = 2; }
+    int weak = idx == 0 ? 2 : (idx == 1 ? 0 : 1);
+    if (style == weak) { num = c[NC_WEAK_NUM]; den = c[NC_WEAK_DEN]; }
+  }
+  int lcol = EA_MELEE_LEVEL + 2 * style;
+  int offense = c[NC_BASE_DAMAGE] + c[NC_LEVEL_DAMAGE] * ENT(lcol, a);
+  int defense = c[NC_BASE_DEFENSE] + c[NC_LEVEL_DEFENSE] * ENT(lcol, t);
+  if (a_player) {
+    for (int s = EA_EQ_HAT; s <= EA_EQ_AMMO; s++) {
+      int it = ENT(s, a);
+      if (it) offense += item_attack(c, ITM(IS_TYPE, it - 1), ITM(IS_LEVEL, it - 1), style);
+    }
+    int am = ENT(EA_EQ_AMMO, a);
+    if (am && item_attack(c, ITM(IS_TYPE, am - 1), ITM(IS_LEVEL, am - 1), style) > 0) {
+      int q = ITM(IS_QUANTITY, am - 1) - 1;
+      ITM(IS_QUANTITY, am - 1) = (int16_t)q;
+      if (q <= 0) item_destroy(ctx, am - 1);
+    }
+  } else offense += ENT(EA_NPC_OFFENSE, a);
+  if (b_player) {
+    for (int s = EA_EQ_HAT; s <= EA_EQ_AMMO; s++) {
+      int it = ENT(s, t);
+      if (it) defense += item_defense(c, ITM(IS_TYPE, it - 1), ITM(IS_LEVEL, it - 1));
+    }
+  } else defense += ENT(EA_NPC_DEFENSE, t);
+  int min_dmg = (c[NC_MINDMG_NUM] * offense) / c[NC_MINDMG_DEN];
+  int dmg = (num * (offense - defense)) / den;
+  dmg = max(min_dmg, dmg);
+  dmg = min(dmg, (int)ENT(EA_HEALTH, t));
+  if (a_player) emit(ctx, a, EV_SCORE_HIT, SK_MELEE + style, 0, dmg, 0, b_id);
+  ENT(EA_DMG_INFLICTED, a) = (int16_t)min(32767, ENT(EA_DMG_INFLICTED, a) + dmg);
+  if (a_player) add_xp(ctx, a, lcol, SK_MELEE + style, c[NC_XP_COMBAT]);
+  ENT(EA_DMG_RECEIVED, t) = (int16_t)min(32767, ENT(EA_DMG_RECEIVED, t) + dmg);
+  ENT(EA_DAMAGE, t) = (int16_t)dmg;
+  ENT(EA_HEALTH, t) = (int16_t)(ENT(EA_HEALTH, t) - dmg);
+  if (style == 2 && dmg > 0) ENT(EA_FREEZE, t) = (int16_t)c[NC_FREEZE_TIME];
+  ENT(EA_LATEST_COMBAT_TICK, a) = (int16_t)(ctx.tick + 1);
+  ENT(EA_LATEST_COMBAT_TICK, t) = (int16_t)(ctx.tick + 1);
+  if (ENT(EA_HEALTH, t) > 0) return;
+  if (a_player) emit(ctx, a, EV_PLAYER_KILL, 0, attack_level(ctx, t), 0, 0, b_id);
+  int tg = ENT(EA_GOLD, t);
+  if (tg > 0) {
+    ENT(EA_GOLD, a) = (int16_t)min(32767, ENT(EA_GOLD, a) + tg);
+    if (a_player) emit(ctx, a, EV_LOOT_GOLD, 0, 0, 0, tg, b_id);
+    ENT(EA_GOLD, t) = 0;
+  }
+  if (b_player) {
+    // the victim's items in table-row order: unlist, then loot (player killer) or destroy
+    int n = ctx.invn[t];
+    uint16_t rows[16];
+    for (int i = 0; i < n; i++) rows[i] = ctx.inv[t * ctx.NINV + i];
+    for (int i = 1; i < n; i++) { uint16_t x = rows[i]; int j = i - 1; while (j >= 0 && rows[j] > x) { rows[j + 1] = rows[j]; j--; } rows[j + 1] = x; }
+    for (int i = 0; i < n; i++) {
+      int row = rows[i];
+      ITM(IS_PRICE, row) = 0; ITM(IS_LIST_TICK, row) = 0;
+      if (ITM(IS_EQUIPPED, row)) { int col = equip_col(ITM(IS_TYPE, row)); if (col >= 0) ENT(col, t) = 0; ITM(IS_EQUIPPED, row) = 0; }
+      if (a_player && ctx.invn[a] < ctx.NINV) {
+        emit(ctx, a, EV_LOOT_ITEM, ITM(IS_TYPE, row), ITM(IS_LEVEL, row), ITM(IS_QUANTITY, row), 0, b_id);
+        inv_receive_existing(ctx, a, row);
+      } else item_destroy(ctx, row);
+    }
+  } else if (a_player) {
+    int lvl = attack_level(ctx, t);
+    int drops[2] = {ENT(EA_NPC_DROP_ARMOR, t), ENT(EA_NPC_DROP_TOOL, t)};
+    for (int k2 = 0; k2 < 2; k2++)
+      if (ctx.invn[a] < ctx.NINV) {
+        inv_receive_new(ctx, a, drops[k2], lvl, 1);
+        emit(ctx, a, EV_LOOT_ITEM, drops[k2], lvl, 1, 0, b_id);
+      }
+  }
+}
+__device__ void act_move(const Ctx &ctx, int row, int dir, bool use_occ) {
+  if (dir < 0 || dir > 3) return;
+  if (ENT(EA_FREEZE, row) > 0) return;
+  int r = ENT(EA_ROW, row), c = ENT(EA_COL, row);
+  int nr = r + c_dir_dr[dir], nc = c + c_dir_dc[dir];
+  if (nm_impassible(tile_at(ctx, nr, nc))) return;
+  if (use_occ) {
+    if (occ_get(ctx, nr, nc)) return;
+    occ_clr(ctx, r, c); occ_set(ctx, nr, nc);
+  }
+  ENT(EA_ROW, row) = (int16_t)nr; ENT(EA_COL, row) = (int16_t)nc;
+  if (row < ctx.P) {
+    int half = ctx.S / 2;
+    int progress = ctx.c[NC_MAP_CENTER] / 2 - nm_linf(half, half, nr, nc);
+    if (progress > ENT(EA_EXPLORATION, row)) {
+      ENT(EA_EXPLORATION, row) = (int16_t)progress;
+      emit(ctx, row, EV_GO_FARTHEST, 0, 0, progress, 0, 0);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ npc spawning ----
+__device__ int border_dist(const Ctx &ctx, int r, int c) {
+  int b = ctx.c[NC_MAP_BORDER], ce = ctx.c[NC_MAP_CENTER];
+  return min(min(r - b, ce + b - r - 1), min(c - b, ce + b - c - 1));
+}
+__device__ void npc_spawn(const Ctx &ctx) {       // single thread
+  const int32_t *c = ctx.c;
+  int b = c[NC_MAP_BORDER], ce = c[NC_MAP_CENTER];
+  int count = ctx.sc[4];
+  int scan = ctx.P;
+  int16_t *danger = ctx.p->danger + (size_t)ctx.env * ctx.N;
+  for (int att = 0; att < c[NC_NPC_SPAWN_ATTEMPTS]; att++) {
+    if (count >= ctx.N) break;
+    while (scan < ctx.R && ENT(EA_STATUS, scan) == ES_ALIVE) scan++;
+    if (scan >= ctx.R) break;
+    uint32_t k = 0;
+    int r, cc;
+    int nd = ctx.sc[2];
+    if (nd > 0) {
+      int d = danger[nd - 1];
+      int mid = ce / 2, max_off = mid - d;
+      int offset = mid + b + nm_bounded(draw(ctx, RS_NPC_SPAWN, att, k++), 2 * max_off) - max_off;
+      int side = nm_bounded(draw(ctx, RS_NPC_SPAWN, att, k++), 4);
+      if (side == 0) { r = b + d; cc = offset; }
+      else if (side == 1) { r = b + ce - d - 1; cc = offset; }
+      else if (side == 2) { cc = b + d; r = offset; }
+      else { cc = b + ce - d - 1; r = offset; }
+    } else {
+      r = b + nm_bounded(draw(ctx, RS_NPC_SPAWN, att, k++), ce);
+      cc = b + nm_bounded(draw(ctx, RS_NPC_SPAWN, att, k++), ce);
+    }
+    if (nm_impassible(tile_at(ctx, r, cc))) continue;
+    if (!c[NC_ALLOW_OCCUPIED] && occ_get(ctx, r, cc)) continue;
+    int d = border_dist(ctx, r, cc);
+    int type;
+    if (200 * d >= c[NC_NPC_AGGR_PCT] * ce) type = 3;
+    else if (200 * d >= c[NC_NPC_NEUT_PCT] * ce) type = 2;
+    else if (200 * d >= c[NC_NPC_PASS_PCT] * ce) type = 1;
+    else continue;
+    int style = nm_bounded(draw(ctx, RS_NPC_SPAWN, att, k++), 3);
+    int level = (2 * d * (c[NC_NPC_LEVEL_MAX] - c[NC_NPC_LEVEL_MIN])) / ce + c[NC_NPC_LEVEL_MIN];
+    int frac = (int)(draw(ctx, RS_NPC_SPAWN, att, k++) >> 16);
+    int lvl_fp = level * 65536 - frac;
+    int armor = IT_HAT + nm_bounded(draw(ctx, RS_NPC_SPAWN, att, k++), 3);
+    int tool = IT_ROD + nm_bounded(draw(ctx, RS_NPC_SPAWN, att, k++), 5);
+    int row = scan;
+    for (int col = 0; col < EA_N; col++) ENT(col, row) = 0;
+    ENT(EA_ID, row) = (int16_t)ctx.sc[3]; ctx.sc[3]--;
+    ENT(EA_NPC_TYPE, row) = (int16_t)type; ENT(EA_ROW, row) = (int16_t)r; ENT(EA_COL, row) = (int16_t)cc;
+    ENT(EA_GOLD, row) = (int16_t)level;
+    ENT(EA_HEALTH, row) = (int16_t)c[NC_RES_BASE]; ENT(EA_FOOD, row) = (int16_t)c[NC_RES_BASE]; ENT(EA_WATER, row) = (int16_t)c[NC_RES_BASE];
+    for (int s = 0; s < 3; s++) ENT(EA_MELEE_LEVEL + 2 * s, row) = 1;
+    ENT(EA_MELEE_LEVEL + 2 * style, row) = (int16_t)level;
+    ENT(EA_MELEE_EXP + 2 * style, row) = (int16_t)c[NC_EXP_THRESH0 + level - 1];
+    ENT(EA_ITEM_LEVEL, row) = (int16_t)((5LL * lvl_fp) >> 16);
+    ENT(EA_NPC_STYLE, row) = (int16_t)style; ENT(EA_NPC_DANGER, row) = (int16_t)d;
+    ENT(EA_NPC_OFFENSE, row) = (int16_t)(c[NC_NPC_BASE_DAMAGE] + (int)(((int64_t)lvl_fp * c[NC_NPC_LEVEL_DAMAGE]) >> 16));
+    ENT(EA_NPC_DEFENSE, row) = (int16_t)(c[NC_NPC_BASE_DEFENSE] + (int)(((int64_t)lvl_fp * c[NC_NPC_LEVEL_DEFENSE]) >> 16));
+    ENT(EA_NPC_DROP_ARMOR, row) = (int16_t)armor; ENT(EA_NPC_DROP_TOOL, row) = (int16_t)tool;
+    ENT(EA_STATUS, row) = ES_ALIVE;
+    occ_set(ctx, r, cc);
+    count++;
+    if (nd > 0) ctx.sc[2] = nd - 1;
+  }
+}
+
+// ------------------------------------------------------------------------ tasks -----
+__device__ double clip01(double x) { return x > 1.0 ? 1.0 : (x < 0.0 ? 0.0 : x); }
+__device__ double eval_predicate(const Ctx &ctx, int p, int pred, int p0, int p1, int p2, int acc0, int acc1) {
+  int vis = ctx.c[NC_VISION];
+  switch (pred) {
+    case TP_TICK_GE: return clip01((double)ctx.tick / (double)p0);
+    case TP_COUNT_EVENT: case TP_SCORE_HIT: return clip01((double)acc0 / (double)p1);
+    case TP_CAN_SEE_TILE: {
+      int r = ENT(EA_ROW, p), c = ENT(EA_COL, p);
+      for (int dr = -vis; dr <= vis; dr++) for (int dc = -vis; dc <= vis; dc++)
+        if (tile_at(ctx, r + dr, c + dc) == p0) return 1.0;
+      return 0.0;
+    }
+    case TP_CAN_SEE_AGENT: case TP_CAN_SEE_GROUP: {
+      // visible = among the first n_ent table rows inside the vision window
+      int lo = p0, hi = pred == TP_CAN_SEE_AGENT ? p0 : p1;
+      int r = ENT(EA_ROW, p), c = ENT(EA_COL, p), seen = 0;
+      for (int row = 0; row < ctx.R && seen < ctx.p->L.n_ent; row++) {
+        if (ENT(EA_STATUS, row) != ES_ALIVE) continue;
+        if (nm_iabs(ENT(EA_ROW, row) - r) > vis || nm_iabs(ENT(EA_COL, row) - c) > vis) continue;
+        seen++;
+        int id = ENT(EA_ID, row);
+        if (id >= lo && id <= hi) return 1.0;
+      }
+      return 0.0;
+    }
+    case TP_OCCUPY_TILE: return (ENT(EA_ROW, p) == p0 && ENT(EA_COL, p) == p1) ? 1.0 : 0.0;
+    case TP_ATTAIN_SKILL:
+      if (p1 <= 1) return 1.0;
+      return clip01((double)(ENT(EA_MELEE_LEVEL + 2 * (p0 - 1), p) - 1) / (double)(p1 - 1));
+    case TP_GAIN_EXPERIENCE: return clip01((double)min((int)ENT(EA_MELEE_EXP + 2 * (p0 - 1), p), p1) / (double)p1);
+    case TP_EQUIP_ITEM: {
+      int k = 0;
+      for (int i = 0; i < ctx.invn[p]; i++) { int r = ctx.inv[p * ctx.NINV + i];
+        if (ITM(IS_TYPE, r) == p0 && ITM(IS_LEVEL, r) >= p1 && ITM(IS_EQUIPPED, r)) k++; }
+      return clip01((double)k);
+    }
+    case TP_HOARD_GOLD: return clip01((double)ENT(EA_GOLD, p) / (double)p0);
+    case TP_EARN_GOLD: case TP_SPEND_GOLD: return clip01((double)acc0 / (double)p0);
+    case TP_MAKE_PROFIT: return clip01((double)(acc0 - acc1) / (double)p0);
+    case TP_INVENTORY_SPACE_GE: return (ctx.NINV - ctx.invn[p] >= p0) ? 1.0 : 0.0;
+    case TP_OWN_ITEM: {
+      int s = 0;
+      for (int i = 0; i < ctx.invn[p]; i++) { int r = ctx.inv[p * ctx.NINV + i];
+        if (ITM(IS_TYPE, r) == p0 && ITM(IS_LEVEL, r) >= p1) s += ITM(IS_QUANTITY, r); }
+      return clip01((double)s / (double)p2);
+    }
+    case TP_CONSUME_ITEM: case TP_HARVEST_ITEM: case TP_LIST_ITEM: case TP_BUY_ITEM: case TP_DEFEAT_ENTITY:
+      return clip01((double)acc0 / (double)p2);
+    case TP_FULLY_ARMED: {
+      int need[5] = {IT_SPEAR + (p0 - 1), IT_WHETSTONE + (p0 - 1), IT_HAT, IT_TOP, IT_BOTTOM}, k = 0;
+      for (int j = 0; j < 5; j++)
+        for (int i = 0; i < ctx.invn[p]; i++) { int r = ctx.inv[p * ctx.NINV + i];
+          if (ITM(IS_TYPE, r) == need[j] && ITM(IS_LEVEL, r) >= p1 && ITM(IS_EQUIPPED, r)) { k++; break; } }
+      return k == 5 ? 1.0 : 0.0;
+    }
+    case TP_STAY_ALIVE: return ENT(EA_HEALTH, p) > 0 ? 1.0 : 0.0;
+    case TP_DISTANCE_TRAVELED:
+      return clip01((double)nm_linf(ENT(EA_ROW, p), ENT(EA_COL, p), ENT(EA_SPAWN_ROW, p), ENT(EA_SPAWN_COL, p)) / (double)p0);
+    case TP_ALL_DEAD: return ENT(EA_HEALTH, p) > 0 ? 0.0 : 1.0;
+    case TP_ALL_MEMBERS_WITHIN_RANGE: return 1.0;
+  }
+  return 0.0;
+}
+
+// fold one event into the agent's accumulators (process_event_log / count_unique_events /
+// event-driven predicates), order-free
+__device__ void fold_event(const Ctx &ctx, uint2 e) {
+  int agent = e.x & 255, de = (e.x >> 8) & 255, type = (e.x >> 16) & 255, level = (e.x >> 24) & 15;
+  bool tpos = (e.x >> 28) & 1, tneg = (e.x >> 29) & 1;
+  int number = (int)(int16_t)(e.y & 0xFFFF), gold = (int)(int16_t)(e.y >> 16);
+  size_t a = (size_t)ctx.env * ctx.P + agent;
+  int32_t *st = ctx.p->stats + a * ST_N;
+  atomicAdd(&st[ST_EVT0 + de], 1);
+  int cls = it_armor(type) ? 0 : it_weapon(type) ? 1 : it_tool(type) ? 2 : it_ammo(type) ? 3 : it_consumable(type) ? 4 : -1;
+  if (de == 9 && cls >= 0 && cls < 4) atomicOr(&st[ST_EQUIP_FLAGS], 1 << cls);
+  if (de == 8 && cls == 1) atomicOr(&st[ST_EQUIP_FLAGS], 1 << 4);
+  if (de == 2) atomicMax(&st[ST_MAX_PROGRESS], number);
+  if (de == 13) atomicAdd(&st[ST_EARNED_GOLD], gold);
+  if (de == 3) atomicMax(&st[ST_MAX_DAMAGE], number);
+  if ((de == 8 || de == 10 || de == 14) && cls >= 0) atomicMax(&st[ST_MAXLVL_ARMOR + cls], level);
+  if (de == 4) { if (tpos) atomicAdd(&st[ST_AGENT_KILLS], 1); else if (tneg) atomicAdd(&st[ST_NPC_KILLS], 1); }
+  // unique (event, type, level)
+  int bit = (de * IT_N + type) * NM_UNIQ_LEVELS + min(level, NM_UNIQ_LEVELS - 1);
+  uint32_t m = 1u << (bit & 31);
+  uint32_t old = atomicOr(&ctx.p->uniq[a * NM_UNIQ_WORDS + (bit >> 5)], m);
+  if (!(old & m) || de == 4 || de == 13) atomicAdd(&ctx.duniq[agent], 1);
+  // event-driven predicate accumulators
+  const int32_t *t = ctx.p->tasks + (size_t)ctx.p->task_id[a] * NM_TASK_COLS;
+  int pred = t[0], p0 = t[1], p1 = t[2];
+  switch (pred) {
+    case TP_COUNT_EVENT: if (nm_dense_event(p0) == de) atomicAdd(&st[ST_TASK_ACC0], 1); break;
+    case TP_SCORE_HIT: if (de == 3 && type == p0) atomicAdd(&st[ST_TASK_ACC0], 1); break;
+    case TP_EARN_GOLD: if (de == 13) atomicAdd(&st[ST_TASK_ACC0], gold); break;
+    case TP_SPEND_GOLD: if (de == 14) atomicAdd(&st[ST_TASK_ACC0], gold); break;
+    case TP_MAKE_PROFIT: if (de == 13) atomicAdd(&st[ST_TASK_ACC0], gold); if (de == 14) atomicAdd(&st[ST_TASK_ACC1], gold); break;
+    case TP_CONSUME_ITEM: if (de == 5 && type == p0 && level >= p1) atomicAdd(&st[ST_TASK_ACC0], number); break;
+    case TP_HARVEST_ITEM: if (de == 8 && type == p0 && level >= p1) atomicAdd(&st[ST_TASK_ACC0], number); break;
+    case TP_LIST_ITEM: if (de == 12 && type == p0 && level >= p1) atomicAdd(&st[ST_TASK_ACC0], number); break;
+    case TP_BUY_ITEM: if (de == 14 && type == p0 && level >= p1) atomicAdd(&st[ST_TASK_ACC0], number); break;
+    case TP_DEFEAT_ENTITY: if (de == 4 && (p0 ? tpos : tneg) && level >= p1) atomicAdd(&st[ST_TASK_ACC0], 1); break;
+    default: break;
+  }
+}
+
+// episode-end info record (stat_wrapper.py:132-185, :216-288)
+__device__ void write_info(const Ctx &ctx, int p, bool terminated, double cum_reward, double max_progress,
+                           int reward_signals, int completed) {
+  size_t a = (size_t)ctx.env * ctx.P + p;
+  float *o = ctx.p->info + a * IN_N;
+  const int32_t *st = ctx.p->stats + a * ST_N;
+  float v[IN_N];
+#pragma unroll
+  for (int i = 0; i < IN_N; i++) v[i] = 0.0f;
+  v[IN_LENGTH] = (float)ctx.tick;
+  v[IN_RETURN] = (float)cum_reward;
+  if (terminated) {
+    v[IN_COD_ATTACKED] = ENT(EA_DAMAGE, p) > 0 ? 1.0f : 0.0f;
+    v[IN_COD_STARVED] = ENT(EA_FOOD, p) == 0 ? 1.0f : 0.0f;
+    v[IN_COD_DEHYDRATED] = ENT(EA_WATER, p) == 0 ? 1.0f : 0.0f;
+  }
+  v[IN_TASK_COMPLETED] = completed ? 1.0f : 0.0f;
+  v[IN_TASK_2_REWARD_SIGNAL] = reward_signals >= 2 ? 1.0f : 0.0f;
+  v[IN_TASK_0P2_MAX_PROGRESS] = max_progress >= 0.2 ? 1.0f : 0.0f;
+  v[IN_CURR_MAX_PROGRESS] = (float)max_progress;
+  v[IN_CURR_REWARD_SIGNALS] = (float)reward_signals;
+  if (ctx.c[NC_EVAL_MODE]) v[IN_RETURN] = (float)max_progress;
+  v[IN_MAX_COMBAT_LEVEL] = (float)attack_level(ctx, p);
+  v[IN_MAX_HARVEST_AMMO] = (float)max((int)ENT(EA_PROSPECTING_LEVEL, p), max((int)ENT(EA_CARVING_LEVEL, p), (int)ENT(EA_ALCHEMY_LEVEL, p)));
+  v[IN_MAX_HARVEST_CONSUM] = (float)max((int)ENT(EA_FISHING_LEVEL, p), (int)ENT(EA_HERBALISM_LEVEL, p));
+  v[IN_MAX_PROGRESS_TO_CENTER] = (float)__ldcg(&st[ST_MAX_PROGRESS]);
+  v[IN_EARNED_GOLD] = (float)__ldcg(&st[ST_EARNED_GOLD]);
+  v[IN_MAX_DAMAGE] = (float)__ldcg(&st[ST_MAX_DAMAGE]);
+  for (int k = 0; k < 5; k++) { int l = __ldcg(&st[ST_MAXLVL_ARMOR + k]); v[IN_MAXLVL_ARMOR + k] = l >= 0 ? (float)l : __int_as_float(0x7fc00000); }
+  v[IN_AGENT_KILLS] = (float)__ldcg(&st[ST_AGENT_KILLS]);
+  v[IN_NPC_KILLS] = (float)__ldcg(&st[ST_NPC_KILLS]);
+  v[IN_UNIQUE_EVENTS] = (float)__ldcg(&st[ST_UNIQ_CURR]);
+  v[IN_EV_EAT_FOOD] = __ldcg(&st[ST_EVT0 + 0]) > 0; v[IN_EV_DRINK_WATER] = __ldcg(&st[ST_EVT0 + 1]) > 0;
+  v[IN_EV_SCORE_HIT] = __ldcg(&st[ST_EVT0 + 3]) > 0; v[IN_EV_PLAYER_KILL] = __ldcg(&st[ST_EVT0 + 4]) > 0;
+  v[IN_EV_CONSUME_ITEM] = __ldcg(&st[ST_EVT0 + 5]) > 0; v[IN_EV_HARVEST_ITEM] = __ldcg(&st[ST_EVT0 + 8]) > 0;
+  v[IN_EV_LIST_ITEM] = __ldcg(&st[ST_EVT0 + 12]) > 0; v[IN_EV_BUY_ITEM] = __ldcg(&st[ST_EVT0 + 14]) > 0;
+  int fl = __ldcg(&st[ST_EQUIP_FLAGS]);
+  for (int k = 0; k < 4; k++) v[IN_EQUIP_ARMOR + k] = (float)((fl >> k) & 1);
+  v[IN_HARVEST_WEAPON] = (float)((fl >> 4) & 1);
+  v[IN_TASK_ID] = (float)ctx.p->task_id[a];
+  for (int i = 0; i < IN_N; i++) {
+    o[i] = v[i];
+    if (v[i] == v[i]) { atomicAdd(&ctx.p->agg[i], (double)v[i]); atomicAdd(&ctx.p->agg[IN_N + i], 1.0); }
+  }
+  ctx.p->info_valid[a] = 1;
+}
+
+// ------------------------------------------------------------------------ reset -----
+__device__ void reset_env(const NmParams &P_, int env, uint64_t seed, bool explicit_map, bool explicit_tasks,
+                          int *s_slot /* >= 2*P ints of shared memory */) {
+  const int32_t *c = P_.cfg;
+  int tid = threadIdx.x, T = blockDim.x;
+  int P = P_.P, R = P_.R, S = P_.S;
+  int32_t *sc = P_.scalars + (size_t)env * NM_SC_N;
+  // injected draws are keyed by tick 0 here
+  Ctx ctx;
+  ctx.p = &P_; ctx.c = c; ctx.env = env; ctx.seed = seed; ctx.tick = 0;
+  ctx.inj_lo = P_.inj_off ? P_.inj_off[env] : 0; ctx.inj_hi = P_.inj_off ? P_.inj_off[env + 1] : 0;
+  int map_id = explicit_map ? sc[SC_MAP_ID] : nm_bounded(draw(ctx, RS_MAP, 0, 0), P_.n_maps);
+  // map copy, table clears
+  {
+    const uint4 *src = (const uint4 *)(P_.maps + (size_t)map_id * S * S);
+    uint4 *dst = (uint4 *)(P_.map + (size_t)env * S * S);
+    for (int i = tid; i < S * S / 16; i += T) dst[i] = src[i];
+    uint4 z = make_uint4(0, 0, 0, 0);
+    uint4 *e4 = (uint4 *)(P_.ent + (size_t)env * EA_N * R);
+    for (int i = tid; i < EA_N * R * 2 / 16; i += T) e4[i] = z;
+    uint4 *i4 = (uint4 *)(P_.item + (size_t)env * IS_N * P_.CAP);
+    for (int i = tid; i < IS_N * P_.CAP * 2 / 16; i += T) i4[i] = z;
+    uint32_t *u = P_.uniq + (size_t)env * P * NM_UNIQ_WORDS;
+    for (int i = tid; i < P * NM_UNIQ_WORDS; i += T) u[i] = 0;
+    int32_t *st = P_.stats + (size_t)env * P * ST_N;
+    for (int i = tid; i < P * ST_N; i += T) { int k = i % ST_N; st[i] = (k >= ST_MAXLVL_ARMOR && k <= ST_MAXLVL_CONSUMABLE) ? -1 : 0; }
+    double *ds = P_.dstats + (size_t)env * P * DS_N;
+    for (int i = tid; i < P * DS_N; i += T) ds[i] = 0.0;
+  }
+  int *slot = s_slot, *resil = s_slot + P;
+  if (tid == 0) {
+    for (int i = 0; i < P; i++) { slot[i] = i; resil[i] = i < c[NC_RES_RESILIENT_N] ? 1 : 0; }
+    for (int i = P - 1; i >= 1; i--) {
+      int j = nm_bounded(draw(ctx, RS_SPAWN_PERM, (uint32_t)i, 0), i + 1);
+      int t = slot[i]; slot[i] = slot[j]; slot[j] = t;
+    }
+    for (int i = P - 1; i >= 1; i--) {
+      int j = nm_bounded(draw(ctx, RS_RESILIENT, (uint32_t)i, 0), i + 1);
+      int t = resil[i]; resil[i] = resil[j]; resil[j] = t;
+    }
+  }
+  __syncthreads();      // also orders the table clears before the row writes below
+  int16_t *ent = P_.ent + (size_t)env * EA_N * R;
+  int b = c[NC_MAP_BORDER], ce = c[NC_MAP_CENTER];
+  for (int p = tid; p < P; p += T) {
+    int k = (int)(((long long)slot[p] * (4 * ce)) / P);
+    int side = k / ce, off = k % ce, r, cc;
+    if (side == 0) { r = b; cc = b + off; }
+    else if (side == 1) { r = b + off; cc = b + ce; }
+    else if (side == 2) { r = b + ce; cc = b + ce - off; }
+    else { r = b + ce - off; cc = b; }
+#define GENT(col) ent[(col) * R + p]
+    GENT(EA_ID) = (int16_t)(p + 1); GENT(EA_ROW) = (int16_t)r; GENT(EA_COL) = (int16_t)cc;
+    GENT(EA_GOLD) = (int16_t)c[NC_BASE_GOLD]; GENT(EA_HEALTH) = (int16_t)c[NC_RES_BASE];
+    GENT(EA_FOOD) = (int16_t)c[NC_RES_BASE]; GENT(EA_WATER) = (int16_t)c[NC_RES_BASE];
+    for (int col = EA_MELEE_LEVEL; col <= EA_ALCHEMY_LEVEL; col += 2) GENT(col) = 1;
+    GENT(EA_SPAWN_ROW) = (int16_t)r; GENT(EA_SPAWN_COL) = (int16_t)cc; GENT(EA_RESILIENT) = (int16_t)resil[p];
+    GENT(EA_STATUS) = ES_ALIVE;
+#undef GENT
+    size_t a = (size_t)env * P + p;
+    if (!explicit_tasks) P_.task_id[a] = nm_bounded(draw(ctx, RS_TASK, (uint32_t)p, 0), P_.n_tasks);
+    P_.rew[a] = 0.0f; P_.term[a] = 0; P_.trunc[a] = 0; P_.mask[a] = 1; P_.info_valid[a] = 0;
+  }
+  if (tid == 0) {
+    P_.seed[env] = seed;
+    sc[SC_TICK] = 0; sc[SC_DONE] = 0; sc[SC_NEXT_NPC_ID] = -1; sc[SC_N_DANGER] = 0; sc[SC_MAP_ID] = map_id;
+    sc[SC_FRESH] = 1; sc[SC_NEED_RESET] = 0; sc[SC_EXPLICIT_MAP] = 0; sc[SC_EXPLICIT_TASKS] = 0;
+    P_.episode_done[env] = 0;
+  }
+}
+
+}  // namespace
+
+// ===================================================================== step kernel ====
+extern "C" __global__ void __launch_bounds__(NM_STEP_THREADS, 2)
+nmmo_step_kernel(const __grid_constant__ NmParams prm) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int env = blockIdx.x, tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int32_t *c = prm.cfg;
+  const int P = prm.P, N = prm.N, R = prm.R, S = prm.S, CAP = prm.CAP, NINV = c[NC_N_INV];
+  int32_t *gsc = prm.scalars + (size_t)env * NM_SC_N;
+
+  // ---- reset paths -------------------------------------------------------------------
+  if (prm.mode == 1) {
+    if (!gsc[SC_NEED_RESET]) return;
+    reset_env(prm, env, prm.seed[env], gsc[SC_EXPLICIT_MAP] != 0, gsc[SC_EXPLICIT_TASKS] != 0, (int *)smem);
+    return;
+  }
+  if (gsc[SC_DONE]) {
+    if (tid == 0) { gsc[SC_EPISODE] += 1; atomicAdd(&prm.counters[2], 1ULL); }
+    reset_env(prm, env, nm_mix64(prm.seed[env] + 0x632BE59BD9B4E019ULL), false, false, (int *)smem);
+    return;
+  }
+
+  // ---- shared memory carve-up ---------------------------------------------------------
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { uint8_t *q = smem + off; off = (off + bytes + 15) & ~(size_t)15; return q; };
+  const uint32_t ent_bytes = (uint32_t)(EA_N * R * 2), item_bytes = (uint32_t)(IS_N * CAP * 2), map_bytes = (uint32_t)(S * S);
+  Ctx ctx;
+  ctx.p = &prm; ctx.c = c; ctx.env = env; ctx.P = P; ctx.N = N; ctx.R = R; ctx.S = S; ctx.CAP = CAP; ctx.NINV = NINV;
+  ctx.ent = (int16_t *)carve(ent_bytes);
+  ctx.item = (int16_t *)carve(item_bytes);
+  ctx.map = carve(map_bytes);
+  const int occ_words = (S * S + 31) >> 5, cap_words = (CAP + 31) >> 5;
+  ctx.occ = (uint32_t *)carve(occ_words * 4);
+  ctx.used = (uint32_t *)carve(cap_words * 4);
+  ctx.fresh = (uint32_t *)carve(cap_words * 4);
+  ctx.inv = (uint16_t *)carve((size_t)P * NINV * 2);
+  ctx.invn = carve(P);
+  ctx.act = (int16_t *)carve((size_t)A_N * P * 2);
+  ctx.npc_move = (int8_t *)carve(N);
+  ctx.npc_att = (int16_t *)carve((size_t)N * 2);
+  ctx.ev = (uint2 *)carve(NM_EV_CAP * 8);
+  ctx.duniq = (int *)carve((size_t)P * 4);
+  int *s_list = (int *)carve((size_t)P * 4);
+  ctx.sc = (int *)carve(16 * 4);
+  uint64_t *bar = (uint64_t *)carve(8);
+  ctx.seed = prm.seed[env];
+  ctx.tick = gsc[SC_TICK];
+  ctx.inj_lo = prm.inj_off ? prm.inj_off[env] : 0;
+  ctx.inj_hi = prm.inj_off ? prm.inj_off[env + 1] : 0;
+
+  // ---- load: three bulk copies on one mbarrier ----------------------------------------
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar, ent_bytes + item_bytes + map_bytes);
+    bulk_g2s(ctx.ent, prm.ent + (size_t)env * EA_N * R, ent_bytes, bar);
+    bulk_g2s(ctx.item, prm.item + (size_t)env * IS_N * CAP, item_bytes, bar);
+    bulk_g2s(ctx.map, prm.map + (size_t)env * S * S, map_bytes, bar);
+  }
+  for (int i = tid; i < occ_words; i += T) ctx.occ[i] = 0;
+  for (int i = tid; i < cap_words; i += T) { ctx.used[i] = 0; ctx.fresh[i] = 0; }
+  for (int i = tid; i < P; i += T) { ctx.invn[i] = 0; ctx.duniq[i] = 0; }
+  if (tid < 16) ctx.sc[tid] = 0;
+  if (tid == 0) { ctx.sc[2] = gsc[SC_N_DANGER]; ctx.sc[3] = gsc[SC_NEXT_NPC_ID]; }
+  while (!mbar_try_wait(bar, 0)) {}
+  __syncthreads();
+
+  // ---- phase 0: bookkeeping rebuilt from the tables -----------------------------------
+  for (int p = tid; p < P; p += T) if (ENT(EA_STATUS, p) == ES_DEAD_THIS_TICK) ENT(EA_STATUS, p) = ES_EMPTY;
+  __syncthreads();
+  for (int r = tid; r < R; r += T) if (ENT(EA_STATUS, r) == ES_ALIVE) occ_set(ctx, ENT(EA_ROW, r), ENT(EA_COL, r));
+  for (int i = tid; i < CAP; i += T)
+    if (ITM(IS_TYPE, i) != 0) {
+      atomicOr(&ctx.used[i >> 5], 1u << (i & 31));
+      int owner = ITM(IS_OWNER, i);
+      if (owner > 0) {
+        // per-owner list; slot order is irrelevant to the engine (obs re-sorts by row)
+        unsigned int *w = (unsigned int *)(ctx.invn + ((owner - 1) & ~3));
+        int sh = ((owner - 1) & 3) * 8;
+        unsigned int old = atomicAdd(w, 1u << sh);
+        int slot = (old >> sh) & 255;
+        ctx.inv[(owner - 1) * NINV + slot] = (uint16_t)i;
+      }
+    }
+  // ---- validate player actions against the observation they were chosen on ------------
+  for (int p = tid; p < P; p += T) {
+    int16_t v[A_N];
+#pragma unroll
+    for (int k = 0; k < A_N; k++) v[k] = 0;
+    v[A_MOVE] = -1;
+    if (ent_alive(ctx, p)) {
+      const int32_t *x = prm.actions + ((size_t)env * P + p) * AC_N;
+      const uint8_t *rec = prm.obs + ((size_t)env * P + p) * prm.L.stride;
+      const nm_obs_layout &L = prm.L;
+      auto ent_id = [&](int idx) -> int { return (idx >= 0 && idx < L.n_ent) ? (int)*(const int16_t *)(rec + L.o_entity + idx * (EA_N_OBS * 2)) : 0; };
+      auto inv_id = [&](int idx) -> int { return (idx >= 0 && idx < L.n_inv) ? (int)*(const int16_t *)(rec + L.o_inventory + idx * (IA_N_OBS * 2)) : 0; };
+      auto mkt_id = [&](int idx) -> int { return (idx >= 0 && idx < L.n_mkt) ? (int)*(const int16_t *)(rec + L.o_market + idx * (IA_N_OBS * 2)) : 0; };
+      auto ent_row1 = [&](int id) -> int {
+        if (id > 0) return id <= P ? id : 0;
+        if (id < 0) for (int r = P; r < R; r++) if (ENT(EA_STATUS, r) == ES_ALIVE && ENT(EA_ID, r) == id) return r + 1;
+        return 0;
+      };
+      int a_use = x[AC_USE_ITEM], a_des = x[AC_DESTROY_ITEM], a_si = x[AC_SELL_ITEM], a_sp = x[AC_SELL_PRICE];
+      int a_buy = x[AC_BUY_ITEM], a_gi = x[AC_GIVE_ITEM], a_gt = x[AC_GIVE_TARGET], a_gp = x[AC_GOLD_PRICE];
+      int a_gg = x[AC_GOLD_TARGET], a_as = x[AC_ATTACK_STYLE], a_at = x[AC_ATTACK_TARGET], a_mv = x[AC_MOVE_DIR];
+      v[A_USE] = (int16_t)inv_id(a_use);
+      v[A_DESTROY] = (int16_t)inv_id(a_des);
+      if (a_sp >= 0 && a_sp < L.n_price) { int id = inv_id(a_si); if (id) { v[A_SELL_ITEM] = (int16_t)id; v[A_SELL_PRICE] = (int16_t)(a_sp + 1); } }
+      v[A_BUY] = (int16_t)mkt_id(a_buy);
+      { int it = inv_id(a_gi), tg = ent_id(a_gt); if (it && tg > 0) { v[A_GIVE_ITEM] = (int16_t)it; v[A_GIVE_TARGET] = (int16_t)ent_row1(tg); } }
+      if (a_gp >= 0 && a_gp < L.n_price) { int tg = ent_id(a_gg); if (tg > 0) { v[A_GOLD_AMT] = (int16_t)(a_gp + 1); v[A_GOLD_TARGET] = (int16_t)ent_row1(tg); } }
+      if (a_as >= 0 && a_as < 3) { int tg = ent_id(a_at); if (tg) { v[A_ATT_STYLE] = (int16_t)a_as; v[A_ATT_TARGET] = (int16_t)ent_row1(tg); } }
+      if (a_mv >= 0 && a_mv < 4) v[A_MOVE] = (int16_t)a_mv;
+      if (c[NC_WRAPPER] == NW_START_KIT)
+        prm.stats[((size_t)env * P + p) * ST_N + ST_PREV_PRICE] = (a_sp >= 0 && a_sp < L.n_price) ? a_sp : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < A_N; k++) ctx.act[k * P + p] = v[k];
+  }
+  __syncthreads();
+
+  // ---- phase 1: npcs.actions ----------------------------------------------------------
+  for (int r = P + tid; r < R; r += T) {
+    if (ent_alive(ctx, r)) npc_decide(ctx, r);
+    else { ctx.npc_move[r - P] = -1; ctx.npc_att[r - P] = 0; }
+  }
+  __syncthreads();
+
+  // ---- phase 2: players.update (order-free part), npcs.update -------------------------
+  for (int p = tid; p < P; p += T) {
+    bool seq = false;
+    if (ENT(EA_STATUS, p) == ES_ALIVE) {
+      if (ENT(EA_DAMAGE, p) == 0) ENT(EA_ATTACKER_ID, p) = 0;
+      int il = 0;
+      for (int s = EA_EQ_HAT; s <= EA_EQ_AMMO; s++) { int it = ENT(s, p); if (it) il += ITM(IS_LEVEL, it - 1); }
+      ENT(EA_ITEM_LEVEL, p) = (int16_t)il;
+      if (ENT(EA_FREEZE, p) > 0) ENT(EA_FREEZE, p) -= 1;
+      ENT(EA_DAMAGE, p) = 0;
+      ENT(EA_TIME_ALIVE, p) += 1;
+      int hp = ENT(EA_HEALTH, p), org = hp, food = ENT(EA_FOOD, p), water = ENT(EA_WATER, p);
+      if (food > c[NC_RES_REGEN_THRESH] && water > c[NC_RES_REGEN_THRESH]) hp = min(c[NC_RES_BASE], hp + c[NC_RES_HEALTH_RESTORE]);
+      int res = ENT(EA_RESILIENT, p);
+      if (food == 0) { int d = c[NC_RES_STARVATION]; if (res) d /= 2; hp = max(0, hp - d); }
+      if (water == 0) { int d = c[NC_RES_DEHYDRATION]; if (res) d /= 2; hp = max(0, hp - d); }
+      ENT(EA_HEALTH, p) = (int16_t)hp;
+      ENT(EA_HEALTH_RESTORE, p) = (int16_t)(hp - org);
+      int r = ENT(EA_ROW, p), cc = ENT(EA_COL, p);
+      water = max(0, water - c[NC_RES_DEPLETION]);
+      int up = tile_at(ctx, r - 1, cc), dn = tile_at(ctx, r + 1, cc), lf = tile_at(ctx, r, cc - 1), rt = tile_at(ctx, r, cc + 1);
+      if (up == MT_WATER || dn == MT_WATER || lf == MT_WATER || rt == MT_WATER) {
+        water = min(c[NC_RES_BASE], water + c[NC_RES_HARVEST_RESTORE]);
+        emit(ctx, p, EV_DRINK_WATER, 0, 0, 0, 0, 0);
+      }
+      ENT(EA_WATER, p) = (int16_t)water;
+      ENT(EA_FOOD, p) = (int16_t)max(0, food - c[NC_RES_DEPLETION]);
+      int here = tile_at(ctx, r, cc);
+      seq = here == MT_FOILAGE || here == MT_HERB || here == MT_ORE || here == MT_TREE || here == MT_CRYSTAL ||
+            up == MT_FISH || dn == MT_FISH || lf == MT_FISH || rt == MT_FISH;
+    }
+    s_list[p] = seq ? 1 : 0;
+  }
+  for (int r = P + tid; r < R; r += T)
+    if (ENT(EA_STATUS, r) == ES_ALIVE) {
+      if (ENT(EA_DAMAGE, r) == 0) ENT(EA_ATTACKER_ID, r) = 0;
+      if (ENT(EA_FREEZE, r) > 0) ENT(EA_FREEZE, r) -= 1;
+      ENT(EA_DAMAGE, r) = 0;
+      ENT(EA_TIME_ALIVE, r) += 1;
+      if (ENT(EA_HEALTH, r) > 0) ENT(EA_HEALTH, r) = (int16_t)min(c[NC_RES_BASE], ENT(EA_HEALTH, r) + 1);
+    }
+  __syncthreads();
+  // id-ordered part: tile depletion and drops
+  if (warp == 0) {
+    for (int base = 0; base < P; base += 32) {
+      int p = base + lane;
+      unsigned m = __ballot_sync(0xffffffffu, p < P && s_list[p]);
+      while (m) {
+        int l = __ffs(m) - 1; m &= m - 1;
+        if (lane == l) player_harvest(ctx, p);
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: actions in priority order ---------------------------------------------
+  // Use (10): touches only the actor's own rows
+  for (int p = tid; p < P; p += T) if (ent_alive(ctx, p) && ctx.act[A_USE * P + p]) act_use(ctx, p, ctx.act[A_USE * P + p]);
+  __syncthreads();
+  // Buy (20): shuffled order, sequential
+  if (tid == 0) {
+    int nb = 0;
+    for (int p = 0; p < P; p++) if (ent_alive(ctx, p) && ctx.act[A_BUY * P + p]) s_list[nb++] = p;
+    for (int i = nb - 1; i >= 1; i--) {
+      int j = nm_bounded(draw(ctx, RS_BUY_SHUFFLE, (uint32_t)i, 0), i + 1);
+      int t = s_list[i]; s_list[i] = s_list[j]; s_list[j] = t;
+    }
+    for (int i = 0; i < nb; i++) { int p = s_list[i]; if (ent_alive(ctx, p)) act_buy(ctx, p, ctx.act[A_BUY * P + p]); }
+    // Give / GiveGold (30)
+    for (int p = 0; p < P; p++) if (ctx.act[A_GIVE_ITEM * P + p] && ent_alive(ctx, p)) act_give(ctx, p, ctx.act[A_GIVE_ITEM * P + p], ctx.act[A_GIVE_TARGET * P + p]);
+    for (int p = 0; p < P; p++) if (ctx.act[A_GOLD_AMT * P + p] && ent_alive(ctx, p)) act_give_gold(ctx, p, ctx.act[A_GOLD_AMT * P + p], ctx.act[A_GOLD_TARGET * P + p]);
+  }
+  __syncthreads();
+  // Destroy (40)
+  for (int p = tid; p < P; p += T) if (ent_alive(ctx, p) && ctx.act[A_DESTROY * P + p]) act_destroy(ctx, p, ctx.act[A_DESTROY * P + p]);
+  __syncthreads();
+  // Attack (50) and Move (60): entity-id order, resolved by warp 0 with ballots
+  if (warp == 0) {
+    for (int base = 0; base < R; base += 32) {
+      int r = base + lane;
+      int tgt = 0;
+      if (r < P) tgt = ctx.act[A_ATT_TARGET * P + r]; else if (r < R) tgt = ctx.npc_att[r - P];
+      unsigned m = __ballot_sync(0xffffffffu, tgt != 0);
+      while (m) {
+        int l = __ffs(m) - 1; m &= m - 1;
+        if (lane == l && ent_alive(ctx, r)) act_attack(ctx, r, r < P ? (int)ctx.act[A_ATT_STYLE * P + r] : (int)ENT(EA_NPC_STYLE, r), tgt);
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
+  if (c[NC_ALLOW_OCCUPIED]) {
+    for (int r = tid; r < R; r += T) if (ent_alive(ctx, r)) act_move(ctx, r, r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P], false);
+  } else if (warp == 0) {
+    for (int base = 0; base < R; base += 32) {
+      int r = base + lane;
+      int dir = -1;
+      if (r < R && ent_alive(ctx, r)) dir = r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P];
+      unsigned m = __ballot_sync(0xffffffffu, dir >= 0 && dir <= 3);
+      while (m) {
+        int l = __ffs(m) - 1; m &= m - 1;
+        if (lane == l) act_move(ctx, r, dir, true);
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
+  // Sell (70)
+  for (int p = tid; p < P; p += T) if (ent_alive(ctx, p) && ctx.act[A_SELL_ITEM * P + p]) act_sell(ctx, p, ctx.act[A_SELL_ITEM * P + p], ctx.act[A_SELL_PRICE * P + p]);
+  __syncthreads();
+
+  // ---- phase 4: cull ------------------------------------------------------------------
+  for (int p = tid; p < P; p += T)
+    if (ENT(EA_STATUS, p) == ES_ALIVE && ENT(EA_HEALTH, p) <= 0) {
+      ENT(EA_STATUS, p) = ES_DEAD_THIS_TICK;
+      occ_clr(ctx, ENT(EA_ROW, p), ENT(EA_COL, p));
+      while (ctx.invn[p] > 0) item_destroy(ctx, ctx.inv[p * NINV + ctx.invn[p] - 1]);
+    }
+  if (warp == 0) {
+    int16_t *danger = prm.danger + (size_t)env * N;
+    int nd = ctx.sc[2], alive = 0;
+    for (int base = P; base < R; base += 32) {
+      int r = base + lane;
+      bool live = r < R && ENT(EA_STATUS, r) == ES_ALIVE;
+      bool dead = live && ENT(EA_HEALTH, r) <= 0;
+      unsigned m = __ballot_sync(0xffffffffu, dead);
+      if (dead) {
+        int idx = nd + __popc(m & ((1u << lane) - 1));
+        if (idx < N) danger[idx] = ENT(EA_NPC_DANGER, r);
+        ENT(EA_STATUS, r) = ES_EMPTY;
+        occ_clr(ctx, ENT(EA_ROW, r), ENT(EA_COL, r));
+      }
+      nd = min(N, nd + __popc(m));
+      alive += __popc(__ballot_sync(0xffffffffu, live && !dead));
+    }
+    if (lane == 0) { ctx.sc[2] = nd; ctx.sc[4] = alive; }
+  }
+  __syncthreads();
+  // ---- phase 5: npcs.spawn (sequential attempts) --------------------------------------
+  if (tid == 0 && ctx.sc[4] < N) { __threadfence_block(); npc_spawn(ctx); }
+  __syncthreads();
+
+  // ---- phase 6: tick += 1, map.step, exchange.step ------------------------------------
+  ctx.tick += 1;
+  {
+    const uint32_t *m32 = (const uint32_t *)ctx.map;
+    for (int w = tid; w < S * S / 4; w += T) {
+      uint32_t word = m32[w];
+      for (int b = 0; b < 4; b++) {
+        int m = (word >> (8 * b)) & 255;
+        if (!((NM_DEPLETED_MASK >> m) & 1)) continue;
+        int thr_idx = m == MT_SCRUB ? NC_RESPAWN_FOILAGE : m == MT_SLAG ? NC_RESPAWN_ORE : m == MT_STUMP ? NC_RESPAWN_TREE
+                    : m == MT_FRAGMENT ? NC_RESPAWN_CRYSTAL : m == MT_WEEDS ? NC_RESPAWN_HERB : NC_RESPAWN_FISH;
+        int i = w * 4 + b;
+        if (draw(ctx, RS_RESPAWN, (uint32_t)i, 0) < (uint32_t)c[thr_idx]) ctx.map[i] = (uint8_t)(m + 1);
+      }
+    }
+  }
+  for (int i = tid; i < CAP; i += T)
+    if (ITM(IS_TYPE, i) != 0 && ITM(IS_PRICE, i) > 0 && ctx.tick - ITM(IS_LIST_TICK, i) > c[NC_LISTING_DURATION]) {
+      ITM(IS_PRICE, i) = 0; ITM(IS_LIST_TICK, i) = 0;
+    }
+  __syncthreads();
+
+  // ---- write the tables back while the wrapper part runs ------------------------------
+  fence_async_smem();
+  __syncthreads();
+  if (tid == 0) {
+    bulk_s2g(prm.ent + (size_t)env * EA_N * R, ctx.ent, ent_bytes);
+    bulk_s2g(prm.item + (size_t)env * IS_N * CAP, ctx.item, item_bytes);
+    bulk_s2g(prm.map + (size_t)env * S * S, ctx.map, map_bytes);
+    bulk_commit();
+  }
+
+  // ---- phase 7: fold the tick's events ------------------------------------------------
+  int nev = min(ctx.sc[0], NM_EV_CAP);
+  for (int i = tid; i < nev; i += T) fold_event(ctx, ctx.ev[i]);
+  __syncthreads();
+
+  // ---- phase 8: rewards, done flags, stat wrapper --------------------------------------
+  int st_me = tid < P ? (int)ENT(EA_STATUS, tid) : ES_EMPTY;
+  int n_alive = __syncthreads_count(st_me == ES_ALIVE);
+  int n_dead = __syncthreads_count(st_me == ES_DEAD_THIS_TICK);
+  int n_current = n_alive + n_dead;
+  bool horizon = ctx.tick >= c[NC_HORIZON];
+  if (horizon) n_current = 0;
+  bool env_done = n_current <= c[NC_EARLY_STOP_N] || n_alive == 0;
+  for (int p = tid; p < P; p += T) {
+    size_t a = (size_t)env * P + p;
+    int st = ENT(EA_STATUS, p);
+    float rew = 0.0f; uint8_t term = 0, trunc = 0, mask = 0;
+    prm.info_valid[a] = 0;
+    if (st != ES_EMPTY) {
+      mask = 1;
+      bool terminated = st == ES_DEAD_THIS_TICK;
+      bool truncated = horizon && !terminated;
+      int32_t *sta = prm.stats + a * ST_N;
+      double *ds = prm.dstats + a * DS_N;
+      double reward;
+      int completed = sta[ST_TASK_DONE], signals = sta[ST_REWARD_SIGNALS];
+      if (terminated) reward = -1.0;
+      else {
+        double diff = 0.0;
+        if (!completed) {
+          const int32_t *t = prm.tasks + (size_t)prm.task_id[a] * NM_TASK_COLS;
+          int acc0 = __ldcg(&sta[ST_TASK_ACC0]), acc1 = __ldcg(&sta[ST_TASK_ACC1]);
+          double v = eval_predicate(ctx, p, t[0], t[1], t[2], t[3], acc0, acc1);
+          if (t[7] == 1) v = v * eval_predicate(ctx, p, t[5], t[6], 0, 0, 0, 0);
+          v = clip01(v);
+          diff = v - ds[DS_PROGRESS];
+          ds[DS_PROGRESS] = v;
+          if (v >= 1.0) { completed = ctx.tick; sta[ST_TASK_DONE] = completed; }
+        }
+        reward = diff;
+        if (reward > 0) { signals++; sta[ST_REWARD_SIGNALS] = signals; }
+        if (ds[DS_PROGRESS] > ds[DS_MAX_PROGRESS]) ds[DS_MAX_PROGRESS] = ds[DS_PROGRESS];
+      }
+      if (env_done && !terminated) truncated = true;
+      int uprev = sta[ST_UNIQ_CURR], ucurr = uprev + ctx.duniq[p];
+      sta[ST_UNIQ_PREV] = uprev; sta[ST_UNIQ_CURR] = ucurr;
+      if (!(terminated || truncated)) ds[DS_CUM_REWARD] += reward;
+      else write_info(ctx, p, terminated, ds[DS_CUM_REWARD], ds[DS_MAX_PROGRESS], signals, completed);
+      if (c[NC_USE_CUSTOM_REWARD]) {
+        double explore = 0.0;
+        if (prm.fcfg[NF_EXPLORE_W] > 0 && ucurr > uprev) explore = (double)min(c[NC_CLIP_UNIQUE], ucurr - uprev) * prm.fcfg[NF_EXPLORE_W];
+        if (c[NC_WRAPPER] == NW_TAKERU) { if (!(terminated || truncated)) reward += explore; }
+        else if (c[NC_WRAPPER] == NW_START_KIT) {
+          double heal = 0.0;
+          if (prm.fcfg[NF_HEAL_W] > 0 && st == ES_ALIVE && ENT(EA_HEALTH_RESTORE, p) > 0) heal = prm.fcfg[NF_HEAL_W];
+          reward += heal + explore;
+        }
+      } else if (terminated) reward = 0.0;
+      rew = (float)reward; term = terminated; trunc = truncated;
+    }
+    prm.rew[a] = rew; prm.term[a] = term; prm.trunc[a] = trunc; prm.mask[a] = mask;
+  }
+  if (tid == 0) {
+    gsc[SC_TICK] = ctx.tick; gsc[SC_DONE] = env_done ? 1 : 0; gsc[SC_N_DANGER] = ctx.sc[2]; gsc[SC_NEXT_NPC_ID] = ctx.sc[3];
+    gsc[SC_FRESH] = 0;
+    if (ctx.sc[1]) { gsc[SC_ERROR] |= 1; atomicAdd(&prm.counters[3], 1ULL); }
+    prm.episode_done[env] = env_done ? 1 : 0;
+    atomicAdd(&prm.counters[0], (unsigned long long)P);
+    atomicAdd(&prm.counters[1], (unsigned long long)(n_alive + n_dead));
+    bulk_wait_all();
+  }
+}
