@@ -95,8 +95,21 @@ int nmmo_snapshot(nmmo_handle *h, int env, int16_t *ent, int16_t *items, uint8_t
 
 /* Episode statistics of finished agents since the last clear: sums[IN_N], counts[IN_N] (means
  * are sums/counts, clean_pufferl.py:381-390), counters[4] = slot-steps, agent-steps (mask
- * sum), finished episodes, event-ring overflows.  Plain sums so ranks can all-reduce them. */
+ * sum), finished episodes, event-ring overflows, bytes moved by the observation kernel, 3 spare
+ * (counters has 8 entries).  Plain sums so ranks can all-reduce them. */
 int nmmo_stats(nmmo_handle *h, double *sums, double *counts, uint64_t *counters, int clear);
+
+/* Per-kernel device timing (CUDA events recorded on the launching stream around the step kernel
+ * and the observation kernel): enable, run steps, read the mean milliseconds per launch. */
+int nmmo_timing(nmmo_handle *h, int enable);
+int nmmo_timing_read(nmmo_handle *h, double *step_ms, double *obs_ms, int *n_launches);
+
+/* Observation writer mode: 0 (default) stores only the bytes of each record that can differ from
+ * what HBM already holds (records persist across ticks); 1 rewrites all bytes of all records. */
+int nmmo_set_obs_full(nmmo_handle *h, int full);
+
+/* Development aid: per-phase SM-clock profile of the step kernel (32 counters). */
+int nmmo_profile(nmmo_handle *h, int enable, unsigned long long *out32);
 
 const char *nmmo_last_error(void);
 

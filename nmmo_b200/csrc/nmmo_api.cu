@@ -27,11 +27,14 @@ struct nmmo_handle {
   size_t step_smem, obs_smem;
   std::vector<void *> allocs;
   int32_t *d_actions;             // staging for the host-buffer path
-  int32_t *h_actions_pinned; float *h_rew; uint8_t *h_flags;
   // injected rng (host mirror, rebuilt on change)
   std::vector<std::vector<std::pair<uint64_t, uint32_t>>> inj;
   uint64_t *d_inj_keys; uint32_t *d_inj_vals; int32_t *d_inj_off;
   uint8_t *d_env_mask;
+  // optional per-kernel timing (CUDA events on the launching stream)
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;    // triples: before step kernel, between, after obs kernel
+  size_t ev_used = 0;
 };
 
 static size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -43,6 +46,7 @@ static size_t step_smem_bytes(const NmParams &p) {
   s += a16((size_t)((p.S * p.S + 31) / 32) * 4); s += 2 * a16((size_t)((p.CAP + 31) / 32) * 4);
   s += a16((size_t)p.P * NINV * 2); s += a16(p.P); s += a16((size_t)12 * p.P * 2);
   s += a16(p.N); s += a16((size_t)p.N * 2); s += a16(NM_EV_CAP * 8); s += a16((size_t)p.P * 4) * 2; s += a16(64); s += 16;
+  s += a16(1024); s += a16((size_t)p.P * 16); s += a16((size_t)p.P * 8); s += 2 * a16((size_t)p.R * 4);
   return s + 128;
 }
 static size_t obs_smem_bytes(const NmParams &p) {
@@ -114,16 +118,13 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   DA(p.obs, E * P * p.L.stride);
   DA(p.rew, E * P); DA(p.term, E * P); DA(p.trunc, E * P); DA(p.mask, E * P);
   DA(p.info, E * P * IN_N); DA(p.info_valid, E * P); DA(p.episode_done, E);
-  DA(p.agg, 2 * IN_N); DA(p.counters, 4);
+  DA(p.agg, 2 * IN_N); DA(p.counters, 8); DA(p.obs_meta, E * P);
   DA(h->d_actions, E * P * AC_N);
   DA(h->d_inj_off, E + 1);
   DA(h->d_env_mask, E);
   h->d_inj_keys = nullptr; h->d_inj_vals = nullptr;
   p.inj_off = nullptr; p.inj_keys = nullptr; p.inj_vals = nullptr;
   h->inj.resize(E);
-  CU(cudaMallocHost((void **)&h->h_actions_pinned, E * P * AC_N * sizeof(int32_t)));
-  CU(cudaMallocHost((void **)&h->h_rew, E * P * sizeof(float)));
-  CU(cudaMallocHost((void **)&h->h_flags, E * P * 3));
   // every env starts "done" so that a step before any reset resets from seed 0
   std::vector<int32_t> sc(E * NM_SC_N, 0);
   for (size_t e = 0; e < E; e++) sc[e * NM_SC_N + SC_DONE] = 1;
@@ -139,7 +140,7 @@ extern "C" int nmmo_destroy(nmmo_handle *h) {
   for (void *q : h->allocs) cudaFree(q);
   if (h->d_inj_keys) cudaFree(h->d_inj_keys);
   if (h->d_inj_vals) cudaFree(h->d_inj_vals);
-  cudaFreeHost(h->h_actions_pinned); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_flags);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
   return NM_OK;
 }
@@ -147,10 +148,21 @@ extern "C" int nmmo_destroy(nmmo_handle *h) {
 static int launch_step(nmmo_handle *h, int mode, cudaStream_t st) {
   NmParams prm = h->prm;
   prm.mode = mode;
+  cudaEvent_t *e3 = nullptr;
+  if (h->timing && mode == 0) {
+    if (h->ev_used + 3 > h->ev.size()) {
+      for (int i = 0; i < 3; i++) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->ev.push_back(e); }
+    }
+    e3 = &h->ev[h->ev_used];
+    h->ev_used += 3;
+    CU(cudaEventRecord(e3[0], st));
+  }
   nmmo_step_kernel<<<prm.E, NM_STEP_THREADS, h->step_smem, st>>>(prm);
   CU(cudaGetLastError());
+  if (e3) CU(cudaEventRecord(e3[1], st));
   nmmo_obs_kernel<<<prm.E, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
   CU(cudaGetLastError());
+  if (e3) CU(cudaEventRecord(e3[2], st));
   return NM_OK;
 }
 
@@ -208,21 +220,17 @@ extern "C" int nmmo_step_host(nmmo_handle *h, const int32_t *actions_host, float
   cudaStream_t st = (cudaStream_t)stream;
   NmParams &p = h->prm;
   size_t n = (size_t)p.E * p.P;
-  memcpy(h->h_actions_pinned, actions_host, n * AC_N * sizeof(int32_t));
-  CU(cudaMemcpyAsync(h->d_actions, h->h_actions_pinned, n * AC_N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  // the caller's buffers are used directly (pinned memory makes the copies asynchronous)
+  CU(cudaMemcpyAsync(h->d_actions, actions_host, n * AC_N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   p.actions = h->d_actions;
   int rc = launch_step(h, 0, st);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(h->h_rew, p.rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(h->h_flags, p.term, n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(h->h_flags + n, p.trunc, n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(h->h_flags + 2 * n, p.mask, n, cudaMemcpyDeviceToHost, st));
+  if (rew_out) CU(cudaMemcpyAsync(rew_out, p.rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (term_out) CU(cudaMemcpyAsync(term_out, p.term, n, cudaMemcpyDeviceToHost, st));
+  if (trunc_out) CU(cudaMemcpyAsync(trunc_out, p.trunc, n, cudaMemcpyDeviceToHost, st));
+  if (mask_out) CU(cudaMemcpyAsync(mask_out, p.mask, n, cudaMemcpyDeviceToHost, st));
   if (obs_out) CU(cudaMemcpyAsync(obs_out, p.obs, n * p.L.stride, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  if (rew_out) memcpy(rew_out, h->h_rew, n * sizeof(float));
-  if (term_out) memcpy(term_out, h->h_flags, n);
-  if (trunc_out) memcpy(trunc_out, h->h_flags + n, n);
-  if (mask_out) memcpy(mask_out, h->h_flags + 2 * n, n);
   return NM_OK;
 }
 
@@ -230,10 +238,11 @@ extern "C" int nmmo_sample_actions(nmmo_handle *h, uint64_t seed, int32_t *actio
   if (!h || !actions_dev) return fail(NM_ERR_ARG, "null argument");
   CU(cudaSetDevice(h->device));
   NmParams prm = h->prm;
-  long long total = (long long)prm.E * prm.P * AC_N;
-  int threads = 256;
-  int blocks = (int)((total + threads - 1) / threads);
-  nmmo_sample_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(prm, seed, actions_dev);
+  int threads = 256, NW = threads / 32;
+  long long n_agents = (long long)prm.E * prm.P;
+  int blocks = (int)std::min<long long>((n_agents + NW - 1) / NW, 148LL * 8 * 4);
+  size_t smem = (size_t)NW * a16(prm.L.m_end);
+  nmmo_sample_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>(prm, seed, actions_dev);
   CU(cudaGetLastError());
   return NM_OK;
 }
@@ -308,7 +317,54 @@ extern "C" int nmmo_stats(nmmo_handle *h, double *sums, double *counts, uint64_t
   CU(cudaMemcpy(agg, h->prm.agg, sizeof(agg), cudaMemcpyDeviceToHost));
   if (sums) memcpy(sums, agg, sizeof(double) * IN_N);
   if (counts) memcpy(counts, agg + IN_N, sizeof(double) * IN_N);
-  if (counters) CU(cudaMemcpy(counters, h->prm.counters, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost));
-  if (clear) { CU(cudaMemset(h->prm.agg, 0, sizeof(agg))); CU(cudaMemset(h->prm.counters, 0, sizeof(uint64_t) * 4)); }
+  if (counters) CU(cudaMemcpy(counters, h->prm.counters, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost));
+  if (clear) { CU(cudaMemset(h->prm.agg, 0, sizeof(agg))); CU(cudaMemset(h->prm.counters, 0, sizeof(uint64_t) * 8)); }
+  return NM_OK;
+}
+
+// per-kernel timing: enable, run steps, then read the mean durations of the two kernels
+extern "C" int nmmo_timing(nmmo_handle *h, int enable) {
+  if (!h) return fail(NM_ERR_ARG, "null handle");
+  h->timing = enable != 0;
+  h->ev_used = 0;
+  return NM_OK;
+}
+extern "C" int nmmo_timing_read(nmmo_handle *h, double *step_ms, double *obs_ms, int *n_launches) {
+  if (!h) return fail(NM_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  double a = 0, b = 0;
+  int n = (int)(h->ev_used / 3);
+  for (int i = 0; i < n; i++) {
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev[3 * i], h->ev[3 * i + 1])); a += ms;
+    CU(cudaEventElapsedTime(&ms, h->ev[3 * i + 1], h->ev[3 * i + 2])); b += ms;
+  }
+  if (step_ms) *step_ms = n ? a / n : 0;
+  if (obs_ms) *obs_ms = n ? b / n : 0;
+  if (n_launches) *n_launches = n;
+  h->ev_used = 0;
+  return NM_OK;
+}
+
+// per-phase clock profile of the step kernel (development aid): enable allocates/clears the
+// accumulators, read copies 32 counters (SM clock cycles summed over CTAs) to the host
+extern "C" int nmmo_profile(nmmo_handle *h, int enable, unsigned long long *out32) {
+  if (!h) return fail(NM_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  if (out32 && h->prm.prof) CU(cudaMemcpy(out32, h->prm.prof, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (enable) {
+    if (!h->prm.prof) { int rc = dalloc(h, &h->prm.prof, 32); if (rc) return rc; }
+    CU(cudaMemset(h->prm.prof, 0, 32 * sizeof(unsigned long long)));
+  } else h->prm.prof = nullptr;
+  return NM_OK;
+}
+
+// 1 = the observation kernel rewrites every byte of every record each tick (dense mode, the
+// HBM-roofline configuration); 0 (default) = only bytes that can differ from the record in HBM
+extern "C" int nmmo_set_obs_full(nmmo_handle *h, int full) {
+  if (!h) return fail(NM_ERR_ARG, "null handle");
+  h->prm.obs_full = full != 0;
   return NM_OK;
 }

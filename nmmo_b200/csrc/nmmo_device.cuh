@@ -17,6 +17,8 @@
 #define NM_STEP_THREADS 256
 #define NM_OBS_THREADS 256
 #define NM_SC_N 16              // per-env int32 scalars
+#define OM_NONZERO (1u << 16)
+#define OM_TASK (1u << 17)
 
 enum nm_scalar { SC_TICK = 0, SC_DONE, SC_NEXT_NPC_ID, SC_N_DANGER, SC_MAP_ID, SC_EPISODE, SC_FRESH,
                  SC_ERROR, SC_NEED_RESET, SC_EXPLICIT_MAP, SC_EXPLICIT_TASKS };
@@ -46,7 +48,10 @@ struct NmParams {
   uint8_t *obs;                // [E*P][stride]
   float *rew; uint8_t *term, *trunc, *mask; float *info; uint8_t *info_valid; uint8_t *episode_done;
   double *agg;                 // [2][IN_N] sums and counts of finished-agent info
-  unsigned long long *counters;// [4] slot-steps, alive-agent-steps, episodes, errors
+  unsigned long long *counters;// [8] slot-steps, alive-agent-steps, episodes, errors, obs-kernel bytes
+  uint32_t *obs_meta;          // [E*P] what each obs record currently holds (incremental writer)
+  int obs_full;                // 1 = rewrite every byte of every record each tick
+  unsigned long long *prof;    // optional [32] per-phase clock accumulators (NULL = off)
   int mode;                    // 0 step (auto-reset finished envs), 1 reset flagged envs only
   int env_base;                // global env index of env 0 (multi-GPU sharding; seeds derive from it)
 };
@@ -58,10 +63,20 @@ __host__ __device__ __forceinline__ uint64_t nm_mix64(uint64_t z) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
   return z ^ (z >> 31);
 }
+__host__ __device__ __forceinline__ uint64_t nm_hash64(uint64_t seed, uint32_t tick, uint32_t site,
+                                                      uint32_t idx, uint32_t k) {
+  uint64_t key = nm_rng_key(tick, site, idx, k);
+  return nm_mix64(nm_mix64(seed ^ key) + key * 0xD6E8FEB86659FD93ULL);
+}
 __host__ __device__ __forceinline__ uint32_t nm_hash_draw(uint64_t seed, uint32_t tick, uint32_t site,
                                                          uint32_t idx, uint32_t k) {
-  uint64_t key = nm_rng_key(tick, site, idx, k);
-  return (uint32_t)(nm_mix64(nm_mix64(seed ^ key) + key * 0xD6E8FEB86659FD93ULL) >> 32);
+  return (uint32_t)(nm_hash64(seed, tick, site, idx, k) >> 32);
+}
+// action sampler: one 64-bit hash per agent, murmur3 fmix32 per head
+__host__ __device__ __forceinline__ uint32_t nm_action_draw(uint64_t base, int head) {
+  uint32_t x = (uint32_t)base + (uint32_t)(base >> 32) * (uint32_t)(2 * head + 1);
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
 }
 __device__ __forceinline__ int nm_bounded(uint32_t u, int n) { return (int)(((uint64_t)u * (uint64_t)n) >> 32); }
 

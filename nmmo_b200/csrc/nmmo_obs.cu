@@ -151,13 +151,27 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   uint16_t *s_vis = s_vis_all + (size_t)warp * (((L.n_ent * 2 + 15) & ~15) / 2);
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
   const int wrapper = c[NC_WRAPPER];
+  long long n_stored = 0;                     // 16-byte chunks stored by this warp
   for (int p = warp; p < P; p += NW) {
     const size_t a = (size_t)env * P + p;
     uint8_t *rec = prm.obs + a * L.stride;
+    // The record lives in HBM across ticks, so only bytes that can differ from last tick's
+    // record are stored.  meta remembers what the record currently holds: rows of Entity /
+    // Inventory / Market that are non-zero, whether the Task block is in place, whether the
+    // record is non-zero at all.  obs_full = 1 rewrites every byte (roofline / A-B mode).
+    const uint32_t meta = prm.obs_meta[a];
     if (s_status[p] != ES_ALIVE) {           // dead or absent agents get the zero pad record
-      for (int k = lane; k < L.stride / 16; k += 32) st16(rec + k * 16, zero4);
+      if ((meta & OM_NONZERO) || prm.obs_full) {
+        for (int k = lane; k < L.stride / 16; k += 32) st16(rec + k * 16, zero4);
+        n_stored += L.stride / 16;
+        if (lane == 0) prm.obs_meta[a] = 0;
+      }
       continue;
     }
+    const int pv = prm.obs_full ? L.n_ent : (int)(meta & 255u);
+    const int pi = prm.obs_full ? L.n_inv : (int)((meta >> 8) & 31u);
+    const int pm = prm.obs_full ? L.n_mkt : (int)((meta >> 18) & 1023u);
+    const bool task_ok = !prm.obs_full && (meta & OM_TASK);
     const int r0 = OENT(EA_ROW, p), c0 = OENT(EA_COL, p), my_id = OENT(EA_ID, p), my_gold = OENT(EA_GOLD, p);
     // visible entities: table rows inside the window, in table order, first n_ent
     int n_vis = 0;
@@ -230,11 +244,14 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     }
     __syncwarp();
     for (int k = lane; k < stage_bytes / 16; k += 32) st16(rec + k * 16, ((const uint4 *)stage)[k]);
+    n_stored += stage_bytes / 16 + 1;
     // ---- AgentId, CurrentTick ----
     if (lane == 0) st16(rec + L.o_ids, make_uint4(pack2(my_id, tick), 0, 0, 0));
     // ---- Entity rows ----
     {
-      const int n_chunks = nm_align16(L.n_ent * EA_N_OBS * 2) / 16, n_el = n_vis * EA_N_OBS;
+      const int n_el = n_vis * EA_N_OBS;
+      const int n_chunks = min(nm_align16(L.n_ent * EA_N_OBS * 2) / 16, (max(n_vis, pv) * EA_N_OBS * 2 + 15) / 16);
+      n_stored += n_chunks;
       for (int k = lane; k < n_chunks; k += 32) {
         int e0 = k * 8;
         uint4 v = zero4;
@@ -251,7 +268,8 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
       }
     }
     // ---- Inventory rows ----
-    for (int k = lane; k < L.n_inv * 2; k += 32) {
+    n_stored += max(n_inv, pi) * 2;
+    for (int k = lane; k < max(n_inv, pi) * 2; k += 32) {
       int slot = k >> 1;
       uint4 v = zero4;
       if (slot < n_inv) {
@@ -264,66 +282,122 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
       st16(rec + L.o_inventory + k * 16, v);
     }
     // ---- Market block ----
-    for (int k = lane; k < L.n_mkt * 2; k += 32) st16(rec + L.o_market + k * 16, ((const uint4 *)s_mkt)[k]);
-    // ---- Task embedding ----
-    {
+    n_stored += max(n_mkt, pm) * 2;
+    for (int k = lane; k < max(n_mkt, pm) * 2; k += 32) st16(rec + L.o_market + k * 16, ((const uint4 *)s_mkt)[k]);
+    // ---- Task embedding (constant within an episode) ----
+    if (!task_ok) {
+      n_stored += L.task_dim * 2 / 16;
       const uint4 *src = (const uint4 *)(prm.embed + (size_t)prm.task_id[a] * L.task_dim);
       for (int k = lane; k < L.task_dim * 2 / 16; k += 32) st16(rec + L.o_task + k * 16, __ldg(src + k));
     }
     // ---- Tile window ----
+    // a lane owns 8 consecutive tiles = 24 int16 = three 16-byte stores
     {
-      const int n_el = L.win * L.win * 3, n_chunks = nm_align16(n_el * 2) / 16;
-      for (int k = lane; k < n_chunks; k += 32) {
-        int vals[8];
+      const int n_tiles = L.win * L.win, n_groups = (n_tiles + 7) / 8;
+      n_stored += nm_align16(n_tiles * 6) / 16;
+      for (int g = lane; g < n_groups; g += 32) {
+        int w = g * 8;
+        int dr = w / L.win, dc = w - dr * L.win;
+        int v[24];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          int e = k * 8 + j;
-          int w = e / 3, comp = e - w * 3;
-          int dr = w / L.win - vis, dc = w % L.win - vis;
-          int v = comp == 0 ? r0 + dr : comp == 1 ? c0 + dc : (e < n_el ? (int)s_map[(r0 + dr) * S + c0 + dc] : 0);
-          vals[j] = e < n_el ? v : 0;
+        for (int t = 0; t < 8; t++) {
+          bool ok = w + t < n_tiles;
+          int rr = r0 + dr - vis, cc = c0 + dc - vis;
+          v[3 * t] = ok ? rr : 0; v[3 * t + 1] = ok ? cc : 0; v[3 * t + 2] = ok ? (int)s_map[rr * S + cc] : 0;
+          if (++dc == L.win) { dc = 0; dr++; }
         }
-        st16(rec + L.o_tile + k * 16, make_uint4(pack2(vals[0], vals[1]), pack2(vals[2], vals[3]), pack2(vals[4], vals[5]), pack2(vals[6], vals[7])));
+        uint8_t *dst = rec + L.o_tile + g * 48;
+        const int last = nm_align16(n_tiles * 6);      // bytes of the section incl. alignment pad
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+          if (g * 48 + q * 16 < last)
+            st16(dst + q * 16, make_uint4(pack2(v[8 * q], v[8 * q + 1]), pack2(v[8 * q + 2], v[8 * q + 3]),
+                                          pack2(v[8 * q + 4], v[8 * q + 5]), pack2(v[8 * q + 6], v[8 * q + 7])));
       }
     }
+    if (lane == 0) prm.obs_meta[a] = (uint32_t)n_vis | ((uint32_t)n_inv << 8) | OM_NONZERO | OM_TASK | ((uint32_t)n_mkt << 18);
     __syncwarp();
   }
+  // bytes this CTA stored (+ the state it pulled in): the kernel's physical traffic estimate
+  if (lane == 0) atomicAdd(&prm.counters[4], (unsigned long long)n_stored * 16ULL + (warp == 0 ? (unsigned long long)(ent_bytes + st_bytes + item_bytes + map_bytes) : 0ULL));
 }
 
 // ============================================================= action sampler kernel ===
 // uniform-random valid action per head from the ActionTargets masks (BASELINE.json config 2:
-// "uniform-random valid actions ... counter-based RNG keyed (seed, env, tick, agent, head)")
-extern "C" __global__ void nmmo_sample_kernel(const __grid_constant__ NmParams prm, uint64_t seed, int32_t *out) {
+// "uniform-random valid actions ... counter-based RNG keyed (seed, env, tick, agent, head)").
+// One warp per agent: the 946 mask bytes are pulled with 16-byte loads into shared memory,
+// then each head is counted and selected with ballots over its mask slice.
+extern "C" __global__ void __launch_bounds__(256)
+nmmo_sample_kernel(const __grid_constant__ NmParams prm, uint64_t seed, int32_t *out) {
+  extern __shared__ __align__(128) uint8_t smem[];
   const nm_obs_layout &L = prm.L;
-  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)prm.E * prm.P * AC_N;
-  if (gid >= total) return;
-  int h = (int)(gid % AC_N);
-  long long a = gid / AC_N;
-  int env = (int)(a / prm.P), p = (int)(a % prm.P);
-  int off, len;
-  switch (h) {
-    case AC_ATTACK_STYLE: off = L.m_style; len = 3; break;
-    case AC_ATTACK_TARGET: off = L.m_target; len = L.n_ent + 1; break;
-    case AC_BUY_ITEM: off = L.m_buy; len = L.n_mkt + 1; break;
-    case AC_DESTROY_ITEM: off = L.m_destroy; len = L.n_inv + 1; break;
-    case AC_GIVE_ITEM: off = L.m_give_item; len = L.n_inv + 1; break;
-    case AC_GIVE_TARGET: off = L.m_give_target; len = L.n_ent + 1; break;
-    case AC_GOLD_PRICE: off = L.m_gold_price; len = L.n_price; break;
-    case AC_GOLD_TARGET: off = L.m_gold_target; len = L.n_ent + 1; break;
-    case AC_MOVE_DIR: off = L.m_move; len = NM_DIR_N; break;
-    case AC_SELL_ITEM: off = L.m_sell_item; len = L.n_inv + 1; break;
-    case AC_SELL_PRICE: off = L.m_sell_price; len = L.n_price; break;
-    default: off = L.m_use; len = L.n_inv + 1; break;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+  const int stage_bytes = nm_align16(L.m_end);
+  uint8_t *stage = smem + (size_t)warp * stage_bytes;
+  const long long n_agents = (long long)prm.E * prm.P;
+  const int off[AC_N] = {L.m_style, L.m_target, L.m_buy, L.m_destroy, L.m_give_item, L.m_give_target,
+                         L.m_gold_price, L.m_gold_target, L.m_move, L.m_sell_item, L.m_sell_price, L.m_use};
+  const int len[AC_N] = {3, L.n_ent + 1, L.n_mkt + 1, L.n_inv + 1, L.n_inv + 1, L.n_ent + 1, L.n_price,
+                         L.n_ent + 1, NM_DIR_N, L.n_inv + 1, L.n_price, L.n_inv + 1};
+  const uint32_t *stage32 = (const uint32_t *)stage;
+  for (long long a = (long long)blockIdx.x * NW + warp; a < n_agents; a += (long long)gridDim.x * NW) {
+    if (!prm.mask[a]) {                       // absent agent: zero record, every head picks 0
+      if (lane < AC_N) out[a * AC_N + lane] = 0;
+      continue;
+    }
+    const uint4 *src = (const uint4 *)(prm.obs + (size_t)a * L.stride);
+    for (int k = lane; k < stage_bytes / 16; k += 32) ((uint4 *)stage)[k] = __ldcs(src + k);
+    __syncwarp();
+    const int env = (int)(a / prm.P), p = (int)(a % prm.P);
+    const int tick = prm.scalars[(size_t)env * NM_SC_N + SC_TICK];
+    // one 64-bit draw per agent, a cheap per-head finaliser on top (nm_action_draw, spec)
+    const uint64_t base64 = nm_hash64(seed + (uint64_t)(prm.env_base + env), (uint32_t)tick, RS_ACTION, (uint32_t)p, 0);
+    int my_pick = 0;
+#pragma unroll
+    for (int h = 0; h < AC_N; h++) {
+      // mask bytes are 0/1: count them a 32-bit word at a time, clipped to the head's byte range
+      const int o0 = off[h], o1 = off[h] + len[h];
+      const int w0 = o0 >> 2, w1 = (o1 + 3) >> 2;
+      int total = 0;
+      for (int wb = w0; wb < w1; wb += 32) {
+        int w = wb + lane;
+        uint32_t y = 0;
+        if (w < w1) {
+          int lo = max(o0 - 4 * w, 0), hi = min(o1 - 4 * w, 4);
+          uint32_t bm = (hi >= 4 ? 0xffffffffu : ((1u << (8 * hi)) - 1u)) & ~((1u << (8 * lo)) - 1u);
+          y = stage32[w] & 0x01010101u & bm;
+        }
+        total += __reduce_add_sync(0xffffffffu, __popc(y));
+      }
+      int pick = 0;
+      if (total > 0) {
+        int jj = nm_bounded(nm_action_draw(base64, h), total);
+        for (int wb = w0; wb < w1; wb += 32) {
+          int w = wb + lane;
+          uint32_t y = 0;
+          if (w < w1) {
+            int lo = max(o0 - 4 * w, 0), hi = min(o1 - 4 * w, 4);
+            uint32_t bm = (hi >= 4 ? 0xffffffffu : ((1u << (8 * hi)) - 1u)) & ~((1u << (8 * lo)) - 1u);
+            y = stage32[w] & 0x01010101u & bm;
+          }
+          int cnt = __popc(y), incl = cnt;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+          int tot = __shfl_sync(0xffffffffu, incl, 31);
+          if (jj < tot) {
+            bool mine = jj >= incl - cnt && jj < incl;
+            int idx = 0;
+            if (mine) idx = 4 * w + (int)(__fns(y, 0, jj - (incl - cnt) + 1) >> 3) - o0;
+            unsigned who = __ballot_sync(0xffffffffu, mine);
+            pick = __shfl_sync(0xffffffffu, idx, __ffs(who) - 1);
+            break;
+          }
+          jj -= tot;
+        }
+      }
+      if (lane == h) my_pick = pick;
+    }
+    if (lane < AC_N) out[a * AC_N + lane] = my_pick;
+    __syncwarp();
   }
-  const int8_t *m = (const int8_t *)(prm.obs + (size_t)a * L.stride) + off;
-  int cnt = 0;
-  for (int i = 0; i < len; i++) cnt += m[i] != 0;
-  int pick = 0;
-  if (cnt > 0) {
-    int tick = prm.scalars[(size_t)env * NM_SC_N + SC_TICK];
-    int j = nm_bounded(nm_hash_draw(seed + (uint64_t)(prm.env_base + env), (uint32_t)tick, RS_ACTION, (uint32_t)p, (uint32_t)h), cnt);
-    for (int i = 0; i < len; i++) if (m[i] && j-- == 0) { pick = i; break; }
-  }
-  out[gid] = pick;
 }

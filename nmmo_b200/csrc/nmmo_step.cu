@@ -36,6 +36,9 @@ struct Ctx {
   uint2 *ev;
   int *sc;            // shared scalars: [0] nev, [1] overflow, [2] n_danger, [3] next_npc_id, [4] npc_count
   int *duniq;
+  unsigned short *npc_hash;   // open-addressing map NPC id -> row+1 (512 slots)
+  int *task;                  // [P][4] pred, p0, p1, spare: the agent's task row for event folding
+  int *acc;                   // [P][2] event-driven predicate accumulators
   uint64_t seed;
   int tick;
   int inj_lo, inj_hi;
@@ -265,6 +268,16 @@ __device__ bool valid_target(const Ctx &ctx, int row, int targ_id, int rng) {
 // first player met by the reference's ring scan (nmmo/systems/ai/utils.py closestTarget)
 __device__ int closest_target(const Ctx &ctx, int row, int rng) {
   int sr = ENT(EA_ROW, row), sc = ENT(EA_COL, row);
+  {   // nothing but me inside the window? (11-bit row slices of the occupancy bitmap)
+    unsigned any = 0;
+    for (int rr = sr - rng; rr <= sr + rng; rr++) {
+      int i0 = rr * ctx.S + sc - rng;
+      unsigned bits = __funnelshift_r(ctx.occ[i0 >> 5], ctx.occ[(i0 >> 5) + 1], i0 & 31) & ((1u << (2 * rng + 1)) - 1);
+      if (rr == sr && !ctx.c[NC_ALLOW_OCCUPIED]) bits &= ~(1u << rng);
+      any |= bits;
+    }
+    if (!any) return 0;
+  }
   int best = 0x7fffffff, best_id = 0;
   for (int p = 0; p < ctx.P; p++) {
     if (!ent_alive(ctx, p)) continue;
@@ -470,16 +483,13 @@ __device__ void act_give_gold(const Ctx &ctx, int p, int amount, int target_row1
   ENT(EA_GOLD, t) = (int16_t)min(32767, ENT(EA_GOLD, t) + amount);
   emit(ctx, p, EV_GIVE_GOLD, 0, 0, 0, amount, 0);
 }
-__device__ void act_attack(const Ctx &ctx, int a, int style, int target_row1) {
+// pure part of combat.attack / Attack.call: validity and damage, no side effects
+__device__ bool attack_compute(const Ctx &ctx, int a, int style, int t, int &dmg, bool &ammo_out) {
   const int32_t *c = ctx.c;
-  int t = target_row1 - 1;
-  if (t < 0 || t == a) return;
   bool a_player = a < ctx.P, b_player = t < ctx.P;
-  if (a_player && b_player && ENT(EA_TIME_ALIVE, t) < c[NC_SPAWN_IMMUNITY]) return;
-  if (!ent_alive(ctx, t)) return;
-  if (nm_linf(ENT(EA_ROW, a), ENT(EA_COL, a), ENT(EA_ROW, t), ENT(EA_COL, t)) > c[NC_REACH]) return;
-  int a_id = ENT(EA_ID, a), b_id = ENT(EA_ID, t);
-  ENT(EA_ATTACKER_ID, t) = (int16_t)a_id;
+  if (a_player && b_player && ENT(EA_TIME_ALIVE, t) < c[NC_SPAWN_IMMUNITY]) return false;
+  if (!ent_alive(ctx, t)) return false;
+  if (nm_linf(ENT(EA_ROW, a), ENT(EA_COL, a), ENT(EA_ROW, t), ENT(EA_COL, t)) > c[NC_REACH]) return false;
   int ex0 = ENT(EA_MELEE_EXP, t), ex1 = ENT(EA_RANGE_EXP, t), ex2 = ENT(EA_MAGE_EXP, t);
   int num = 1, den = 1;
   if (!(ex0 == ex1 && ex1 == ex2)) {
@@ -492,17 +502,14 @@ __device__ void act_attack(const Ctx &ctx, int a, int style, int target_row1) {
   int lcol = EA_MELEE_LEVEL + 2 * style;
   int offense = c[NC_BASE_DAMAGE] + c[NC_LEVEL_DAMAGE] * ENT(lcol, a);
   int defense = c[NC_BASE_DEFENSE] + c[NC_LEVEL_DEFENSE] * ENT(lcol, t);
+  ammo_out = false;
   if (a_player) {
     for (int s = EA_EQ_HAT; s <= EA_EQ_AMMO; s++) {
       int it = ENT(s, a);
       if (it) offense += item_attack(c, ITM(IS_TYPE, it - 1), ITM(IS_LEVEL, it - 1), style);
     }
     int am = ENT(EA_EQ_AMMO, a);
-    if (am && item_attack(c, ITM(IS_TYPE, am - 1), ITM(IS_LEVEL, am - 1), style) > 0) {
-      int q = ITM(IS_QUANTITY, am - 1) - 1;
-      ITM(IS_QUANTITY, am - 1) = (int16_t)q;
-      if (q <= 0) item_destroy(ctx, am - 1);
-    }
+    if (am && item_attack(c, ITM(IS_TYPE, am - 1), ITM(IS_LEVEL, am - 1), style) > 0) ammo_out = ITM(IS_QUANTITY, am - 1) - 1 <= 0;
   } else offense += ENT(EA_NPC_OFFENSE, a);
   if (b_player) {
     for (int s = EA_EQ_HAT; s <= EA_EQ_AMMO; s++) {
@@ -511,9 +518,26 @@ __device__ void act_attack(const Ctx &ctx, int a, int style, int target_row1) {
     }
   } else defense += ENT(EA_NPC_DEFENSE, t);
   int min_dmg = (c[NC_MINDMG_NUM] * offense) / c[NC_MINDMG_DEN];
-  int dmg = (num * (offense - defense)) / den;
+  dmg = (num * (offense - defense)) / den;
   dmg = max(min_dmg, dmg);
   dmg = min(dmg, (int)ENT(EA_HEALTH, t));
+  return true;
+}
+// side effects of one attack whose damage is known (attacker a, target row t)
+__device__ void attack_apply(const Ctx &ctx, int a, int style, int t, int dmg) {
+  const int32_t *c = ctx.c;
+  bool a_player = a < ctx.P, b_player = t < ctx.P;
+  int a_id = ENT(EA_ID, a), b_id = ENT(EA_ID, t);
+  int lcol = EA_MELEE_LEVEL + 2 * style;
+  ENT(EA_ATTACKER_ID, t) = (int16_t)a_id;
+  if (a_player) {
+    int am = ENT(EA_EQ_AMMO, a);
+    if (am && item_attack(c, ITM(IS_TYPE, am - 1), ITM(IS_LEVEL, am - 1), style) > 0) {
+      int q = ITM(IS_QUANTITY, am - 1) - 1;
+      ITM(IS_QUANTITY, am - 1) = (int16_t)q;
+      if (q <= 0) item_destroy(ctx, am - 1);
+    }
+  }
   if (a_player) emit(ctx, a, EV_SCORE_HIT, SK_MELEE + style, 0, dmg, 0, b_id);
   ENT(EA_DMG_INFLICTED, a) = (int16_t)min(32767, ENT(EA_DMG_INFLICTED, a) + dmg);
   if (a_player) add_xp(ctx, a, lcol, SK_MELEE + style, c[NC_XP_COMBAT]);
@@ -731,26 +755,26 @@ __device__ void fold_event(const Ctx &ctx, uint2 e) {
   uint32_t old = atomicOr(&ctx.p->uniq[a * NM_UNIQ_WORDS + (bit >> 5)], m);
   if (!(old & m) || de == 4 || de == 13) atomicAdd(&ctx.duniq[agent], 1);
   // event-driven predicate accumulators
-  const int32_t *t = ctx.p->tasks + (size_t)ctx.p->task_id[a] * NM_TASK_COLS;
-  int pred = t[0], p0 = t[1], p1 = t[2];
+  int pred = ctx.task[agent * 4], p0 = ctx.task[agent * 4 + 1], p1 = ctx.task[agent * 4 + 2];
+  int *acc = ctx.acc + agent * 2;
   switch (pred) {
-    case TP_COUNT_EVENT: if (nm_dense_event(p0) == de) atomicAdd(&st[ST_TASK_ACC0], 1); break;
-    case TP_SCORE_HIT: if (de == 3 && type == p0) atomicAdd(&st[ST_TASK_ACC0], 1); break;
-    case TP_EARN_GOLD: if (de == 13) atomicAdd(&st[ST_TASK_ACC0], gold); break;
-    case TP_SPEND_GOLD: if (de == 14) atomicAdd(&st[ST_TASK_ACC0], gold); break;
-    case TP_MAKE_PROFIT: if (de == 13) atomicAdd(&st[ST_TASK_ACC0], gold); if (de == 14) atomicAdd(&st[ST_TASK_ACC1], gold); break;
-    case TP_CONSUME_ITEM: if (de == 5 && type == p0 && level >= p1) atomicAdd(&st[ST_TASK_ACC0], number); break;
-    case TP_HARVEST_ITEM: if (de == 8 && type == p0 && level >= p1) atomicAdd(&st[ST_TASK_ACC0], number); break;
-    case TP_LIST_ITEM: if (de == 12 && type == p0 && level >= p1) atomicAdd(&st[ST_TASK_ACC0], number); break;
-    case TP_BUY_ITEM: if (de == 14 && type == p0 && level >= p1) atomicAdd(&st[ST_TASK_ACC0], number); break;
-    case TP_DEFEAT_ENTITY: if (de == 4 && (p0 ? tpos : tneg) && level >= p1) atomicAdd(&st[ST_TASK_ACC0], 1); break;
+    case TP_COUNT_EVENT: if (nm_dense_event(p0) == de) atomicAdd(&acc[0], 1); break;
+    case TP_SCORE_HIT: if (de == 3 && type == p0) atomicAdd(&acc[0], 1); break;
+    case TP_EARN_GOLD: if (de == 13) atomicAdd(&acc[0], gold); break;
+    case TP_SPEND_GOLD: if (de == 14) atomicAdd(&acc[0], gold); break;
+    case TP_MAKE_PROFIT: if (de == 13) atomicAdd(&acc[0], gold); if (de == 14) atomicAdd(&acc[1], gold); break;
+    case TP_CONSUME_ITEM: if (de == 5 && type == p0 && level >= p1) atomicAdd(&acc[0], number); break;
+    case TP_HARVEST_ITEM: if (de == 8 && type == p0 && level >= p1) atomicAdd(&acc[0], number); break;
+    case TP_LIST_ITEM: if (de == 12 && type == p0 && level >= p1) atomicAdd(&acc[0], number); break;
+    case TP_BUY_ITEM: if (de == 14 && type == p0 && level >= p1) atomicAdd(&acc[0], number); break;
+    case TP_DEFEAT_ENTITY: if (de == 4 && (p0 ? tpos : tneg) && level >= p1) atomicAdd(&acc[0], 1); break;
     default: break;
   }
 }
 
 // episode-end info record (stat_wrapper.py:132-185, :216-288)
 __device__ void write_info(const Ctx &ctx, int p, bool terminated, double cum_reward, double max_progress,
-                           int reward_signals, int completed) {
+                           int reward_signals, int completed, int unique_events) {
   size_t a = (size_t)ctx.env * ctx.P + p;
   float *o = ctx.p->info + a * IN_N;
   const int32_t *st = ctx.p->stats + a * ST_N;
@@ -779,7 +803,7 @@ __device__ void write_info(const Ctx &ctx, int p, bool terminated, double cum_re
   for (int k = 0; k < 5; k++) { int l = __ldcg(&st[ST_MAXLVL_ARMOR + k]); v[IN_MAXLVL_ARMOR + k] = l >= 0 ? (float)l : __int_as_float(0x7fc00000); }
   v[IN_AGENT_KILLS] = (float)__ldcg(&st[ST_AGENT_KILLS]);
   v[IN_NPC_KILLS] = (float)__ldcg(&st[ST_NPC_KILLS]);
-  v[IN_UNIQUE_EVENTS] = (float)__ldcg(&st[ST_UNIQ_CURR]);
+  v[IN_UNIQUE_EVENTS] = (float)unique_events;
   v[IN_EV_EAT_FOOD] = __ldcg(&st[ST_EVT0 + 0]) > 0; v[IN_EV_DRINK_WATER] = __ldcg(&st[ST_EVT0 + 1]) > 0;
   v[IN_EV_SCORE_HIT] = __ldcg(&st[ST_EVT0 + 3]) > 0; v[IN_EV_PLAYER_KILL] = __ldcg(&st[ST_EVT0 + 4]) > 0;
   v[IN_EV_CONSUME_ITEM] = __ldcg(&st[ST_EVT0 + 5]) > 0; v[IN_EV_HARVEST_ITEM] = __ldcg(&st[ST_EVT0 + 8]) > 0;
@@ -857,6 +881,7 @@ __device__ void reset_env(const NmParams &P_, int env, uint64_t seed, bool expli
     size_t a = (size_t)env * P + p;
     if (!explicit_tasks) P_.task_id[a] = nm_bounded(draw(ctx, RS_TASK, (uint32_t)p, 0), P_.n_tasks);
     P_.rew[a] = 0.0f; P_.term[a] = 0; P_.trunc[a] = 0; P_.mask[a] = 1; P_.info_valid[a] = 0;
+    P_.obs_meta[a] &= ~OM_TASK;        // new episode, new task embedding
   }
   if (tid == 0) {
     P_.seed[env] = seed;
@@ -910,6 +935,11 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   ctx.ev = (uint2 *)carve(NM_EV_CAP * 8);
   ctx.duniq = (int *)carve((size_t)P * 4);
   int *s_list = (int *)carve((size_t)P * 4);
+  ctx.npc_hash = (unsigned short *)carve(512 * 2);
+  ctx.task = (int *)carve((size_t)P * 16);
+  ctx.acc = (int *)carve((size_t)P * 8);
+  uint32_t *s_att = (uint32_t *)carve((size_t)R * 4);
+  int *s_first = (int *)carve((size_t)R * 4);
   ctx.sc = (int *)carve(16 * 4);
   uint64_t *bar = (uint64_t *)carve(8);
   ctx.seed = prm.seed[env];
@@ -917,6 +947,25 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   ctx.inj_lo = prm.inj_off ? prm.inj_off[env] : 0;
   ctx.inj_hi = prm.inj_off ? prm.inj_off[env + 1] : 0;
 
+  // per-player wrapper state: issued now, consumed at the end of the step
+  const size_t my_a = (size_t)env * P + (tid < P ? tid : 0);
+  int32_t *my_sta = prm.stats + my_a * ST_N;
+  double *my_ds = prm.dstats + my_a * DS_N;
+  int my_task_id = 0, my_t[NM_TASK_COLS] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int my_done = 0, my_signals = 0, my_uniq = 0, my_acc0 = 0, my_acc1 = 0;
+  double my_cum = 0.0, my_prog = 0.0, my_maxprog = 0.0;
+  if (tid < P) {
+    my_task_id = prm.task_id[my_a];
+    const int4 *tr = (const int4 *)(prm.tasks + (size_t)my_task_id * NM_TASK_COLS);
+    int4 t0 = __ldg(tr), t1 = __ldg(tr + 1);
+    my_t[0] = t0.x; my_t[1] = t0.y; my_t[2] = t0.z; my_t[3] = t0.w; my_t[4] = t1.x; my_t[5] = t1.y; my_t[6] = t1.z; my_t[7] = t1.w;
+    my_done = my_sta[ST_TASK_DONE]; my_signals = my_sta[ST_REWARD_SIGNALS]; my_uniq = my_sta[ST_UNIQ_CURR];
+    my_acc0 = my_sta[ST_TASK_ACC0]; my_acc1 = my_sta[ST_TASK_ACC1];
+    my_cum = my_ds[DS_CUM_REWARD]; my_prog = my_ds[DS_PROGRESS]; my_maxprog = my_ds[DS_MAX_PROGRESS];
+  }
+  long long t_prev = clock64();
+  int ph = 0;
+#define PHASE() do { if (prm.prof && tid == 0) { long long t_ = clock64(); atomicAdd(&prm.prof[ph], (unsigned long long)(t_ - t_prev)); t_prev = t_; } ph++; } while (0)
   // ---- load: three bulk copies on one mbarrier ----------------------------------------
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -932,13 +981,24 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   for (int i = tid; i < occ_words; i += T) ctx.occ[i] = 0;
   for (int i = tid; i < cap_words; i += T) { ctx.used[i] = 0; ctx.fresh[i] = 0; }
   for (int i = tid; i < P; i += T) { ctx.invn[i] = 0; ctx.duniq[i] = 0; }
+  for (int i = tid; i < 256; i += T) ((uint32_t *)ctx.npc_hash)[i] = 0;
+  if (tid < P) {
+    ctx.task[tid * 4] = my_t[0]; ctx.task[tid * 4 + 1] = my_t[1]; ctx.task[tid * 4 + 2] = my_t[2]; ctx.task[tid * 4 + 3] = 0;
+    ctx.acc[tid * 2] = my_acc0; ctx.acc[tid * 2 + 1] = my_acc1;
+  }
   if (tid < 16) ctx.sc[tid] = 0;
   if (tid == 0) { ctx.sc[2] = gsc[SC_N_DANGER]; ctx.sc[3] = gsc[SC_NEXT_NPC_ID]; }
   while (!mbar_try_wait(bar, 0)) {}
   __syncthreads();
 
+  PHASE();
   // ---- phase 0: bookkeeping rebuilt from the tables -----------------------------------
   for (int p = tid; p < P; p += T) if (ENT(EA_STATUS, p) == ES_DEAD_THIS_TICK) ENT(EA_STATUS, p) = ES_EMPTY;
+  for (int r = P + tid; r < R; r += T)
+    if (ENT(EA_STATUS, r) == ES_ALIVE) {
+      unsigned h = (((unsigned)(-(int)ENT(EA_ID, r))) * 40503u >> 4) & 511u;
+      while (atomicCAS(&ctx.npc_hash[h], (unsigned short)0, (unsigned short)(r + 1)) != 0) h = (h + 1) & 511u;
+    }
   __syncthreads();
   for (int r = tid; r < R; r += T) if (ENT(EA_STATUS, r) == ES_ALIVE) occ_set(ctx, ENT(EA_ROW, r), ENT(EA_COL, r));
   for (int i = tid; i < CAP; i += T)
@@ -969,7 +1029,15 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       auto mkt_id = [&](int idx) -> int { return (idx >= 0 && idx < L.n_mkt) ? (int)*(const int16_t *)(rec + L.o_market + idx * (IA_N_OBS * 2)) : 0; };
       auto ent_row1 = [&](int id) -> int {
         if (id > 0) return id <= P ? id : 0;
-        if (id < 0) for (int r = P; r < R; r++) if (ENT(EA_STATUS, r) == ES_ALIVE && ENT(EA_ID, r) == id) return r + 1;
+        if (id < 0) {
+          unsigned h = (((unsigned)(-id)) * 40503u >> 4) & 511u;
+          for (int probe = 0; probe < 512; probe++) {
+            int r1 = ctx.npc_hash[h];
+            if (r1 == 0) return 0;
+            if (ENT(EA_ID, r1 - 1) == id) return r1;
+            h = (h + 1) & 511u;
+          }
+        }
         return 0;
       };
       int a_use = x[AC_USE_ITEM], a_des = x[AC_DESTROY_ITEM], a_si = x[AC_SELL_ITEM], a_sp = x[AC_SELL_PRICE];
@@ -991,6 +1059,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   }
   __syncthreads();
 
+  PHASE();
   // ---- phase 1: npcs.actions ----------------------------------------------------------
   for (int r = P + tid; r < R; r += T) {
     if (ent_alive(ctx, r)) npc_decide(ctx, r);
@@ -998,6 +1067,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   }
   __syncthreads();
 
+  PHASE();
   // ---- phase 2: players.update (order-free part), npcs.update -------------------------
   for (int p = tid; p < P; p += T) {
     bool seq = false;
@@ -1040,6 +1110,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       if (ENT(EA_HEALTH, r) > 0) ENT(EA_HEALTH, r) = (int16_t)min(c[NC_RES_BASE], ENT(EA_HEALTH, r) + 1);
     }
   __syncthreads();
+  PHASE();
   // id-ordered part: tile depletion and drops
   if (warp == 0) {
     for (int base = 0; base < P; base += 32) {
@@ -1054,62 +1125,144 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   }
   __syncthreads();
 
+  PHASE();
   // ---- phase 3: actions in priority order ---------------------------------------------
   // Use (10): touches only the actor's own rows
   for (int p = tid; p < P; p += T) if (ent_alive(ctx, p) && ctx.act[A_USE * P + p]) act_use(ctx, p, ctx.act[A_USE * P + p]);
   __syncthreads();
-  // Buy (20): shuffled order, sequential
-  if (tid == 0) {
-    int nb = 0;
-    for (int p = 0; p < P; p++) if (ent_alive(ctx, p) && ctx.act[A_BUY * P + p]) s_list[nb++] = p;
-    for (int i = nb - 1; i >= 1; i--) {
-      int j = nm_bounded(draw(ctx, RS_BUY_SHUFFLE, (uint32_t)i, 0), i + 1);
-      int t = s_list[i]; s_list[i] = s_list[j]; s_list[j] = t;
-    }
-    for (int i = 0; i < nb; i++) { int p = s_list[i]; if (ent_alive(ctx, p)) act_buy(ctx, p, ctx.act[A_BUY * P + p]); }
-    // Give / GiveGold (30)
-    for (int p = 0; p < P; p++) if (ctx.act[A_GIVE_ITEM * P + p] && ent_alive(ctx, p)) act_give(ctx, p, ctx.act[A_GIVE_ITEM * P + p], ctx.act[A_GIVE_TARGET * P + p]);
-    for (int p = 0; p < P; p++) if (ctx.act[A_GOLD_AMT * P + p] && ent_alive(ctx, p)) act_give_gold(ctx, p, ctx.act[A_GOLD_AMT * P + p], ctx.act[A_GOLD_TARGET * P + p]);
-  }
-  __syncthreads();
-  // Destroy (40)
-  for (int p = tid; p < P; p += T) if (ent_alive(ctx, p) && ctx.act[A_DESTROY * P + p]) act_destroy(ctx, p, ctx.act[A_DESTROY * P + p]);
-  __syncthreads();
-  // Attack (50) and Move (60): entity-id order, resolved by warp 0 with ballots
-  if (warp == 0) {
-    for (int base = 0; base < R; base += 32) {
-      int r = base + lane;
-      int tgt = 0;
-      if (r < P) tgt = ctx.act[A_ATT_TARGET * P + r]; else if (r < R) tgt = ctx.npc_att[r - P];
-      unsigned m = __ballot_sync(0xffffffffu, tgt != 0);
-      while (m) {
-        int l = __ffs(m) - 1; m &= m - 1;
-        if (lane == l && ent_alive(ctx, r)) act_attack(ctx, r, r < P ? (int)ctx.act[A_ATT_STYLE * P + r] : (int)ENT(EA_NPC_STYLE, r), tgt);
-        __syncwarp();
+  PHASE();
+  // Buy (20): shuffled order.  Buyers are compacted in id order by the whole block, then
+  // shuffled and executed by one thread (a handful per tick); Give / GiveGold (30) likewise
+  {
+    bool mine = tid < P && ctx.act[A_BUY * P + tid] && ent_alive(ctx, tid);
+    unsigned bm = __ballot_sync(0xffffffffu, mine);
+    if (lane == 0) ctx.sc[8 + warp] = __popc(bm);
+    bool give = tid < P && (ctx.act[A_GIVE_ITEM * P + tid] || ctx.act[A_GOLD_AMT * P + tid]);
+    int any_give = __syncthreads_or(give);
+    int base = 0, nb = 0;
+    for (int w2 = 0; w2 < (T >> 5); w2++) { int cw = ctx.sc[8 + w2]; if (w2 < warp) base += cw; nb += cw; }
+    if (mine) s_list[base + __popc(bm & ((1u << lane) - 1))] = tid;
+    __syncthreads();
+    if (tid == 0 && (nb > 0 || any_give)) {
+      for (int i = nb - 1; i >= 1; i--) {
+        int j = nm_bounded(draw(ctx, RS_BUY_SHUFFLE, (uint32_t)i, 0), i + 1);
+        int t = s_list[i]; s_list[i] = s_list[j]; s_list[j] = t;
+      }
+      for (int i = 0; i < nb; i++) { int p = s_list[i]; if (ent_alive(ctx, p)) act_buy(ctx, p, ctx.act[A_BUY * P + p]); }
+      if (any_give) {
+        for (int p = 0; p < P; p++) if (ctx.act[A_GIVE_ITEM * P + p] && ent_alive(ctx, p)) act_give(ctx, p, ctx.act[A_GIVE_ITEM * P + p], ctx.act[A_GIVE_TARGET * P + p]);
+        for (int p = 0; p < P; p++) if (ctx.act[A_GOLD_AMT * P + p] && ent_alive(ctx, p)) act_give_gold(ctx, p, ctx.act[A_GOLD_AMT * P + p], ctx.act[A_GOLD_TARGET * P + p]);
       }
     }
   }
   __syncthreads();
+  PHASE();
+  // Destroy (40)
+  for (int p = tid; p < P; p += T) if (ent_alive(ctx, p) && ctx.act[A_DESTROY * P + p]) act_destroy(ctx, p, ctx.act[A_DESTROY * P + p]);
+  __syncthreads();
+  PHASE();
+  // Attack (50): the reference executes attacks in entity-id order.  Two attacks commute unless
+  // they share an entity (as attacker or target) or touch the item allocator (a kill, or the
+  // last unit of ammunition).  Warp 0 therefore runs rounds: every pending attack registers its
+  // index on both entities with atomicMin; an attack that holds the minimum on both is "ready";
+  // ready attacks without allocator effects are applied in parallel, one per lane; an attack with
+  // allocator effects is applied only when it is the lowest pending index, i.e. in exact
+  // sequential position.  The lowest pending attack is always ready, so every round progresses.
+  if (warp == 0) {
+    const uint32_t DONE = 0xffffffffu;
+    int na = 0;
+    for (int base = 0; base < R; base += 32) {
+      int r = base + lane;
+      int tgt = 0;
+      if (r < P) tgt = ctx.act[A_ATT_TARGET * P + r]; else if (r < R) tgt = ctx.npc_att[r - P];
+      bool has = tgt != 0 && tgt - 1 != r && ent_alive(ctx, r);
+      unsigned m = __ballot_sync(0xffffffffu, has);
+      if (has) s_att[na + __popc(m & ((1u << lane) - 1))] = ((uint32_t)r << 16) | (uint32_t)(tgt - 1);
+      na += __popc(m);
+    }
+    for (int r = lane; r < R; r += 32) s_first[r] = 0x7fffffff;
+    __syncwarp();
+    int remaining = na;
+    while (remaining > 0) {
+      int mylow = 0x7fffffff;
+      for (int i = lane; i < na; i += 32) {
+        uint32_t x = s_att[i];
+        if (x == DONE) continue;
+        if (i < mylow) mylow = i;
+        atomicMin(&s_first[x >> 16], i);
+        atomicMin(&s_first[x & 0xffff], i);
+      }
+      int lowest = __reduce_min_sync(0xffffffffu, mylow);
+      __syncwarp();
+      int ndone = 0;
+      for (int i = lane; i < na; i += 32) {
+        uint32_t x = s_att[i];
+        if (x == DONE) continue;
+        int a = x >> 16, t = x & 0xffff;
+        if (s_first[a] != i || s_first[t] != i) continue;
+        bool done = true;
+        if (ent_alive(ctx, a)) {
+          int style = a < P ? (int)ctx.act[A_ATT_STYLE * P + a] : (int)ENT(EA_NPC_STYLE, a);
+          int dmg; bool ammo_out;
+          if (attack_compute(ctx, a, style, t, dmg, ammo_out)) {
+            bool heavy = ammo_out || dmg >= ENT(EA_HEALTH, t);
+            if (!heavy || i == lowest) attack_apply(ctx, a, style, t, dmg);
+            else done = false;
+          }
+        }
+        if (done) { s_att[i] = DONE; ndone++; }
+      }
+      __syncwarp();
+      for (int r = lane; r < R; r += 32) s_first[r] = 0x7fffffff;
+      remaining -= __reduce_add_sync(0xffffffffu, ndone);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  PHASE();
+  // Move (60): with one entity per tile the reference resolves moves in entity-id order.  Warp 0
+  // takes 32 entities at a time; a mover whose source and destination tiles are touched by no
+  // other mover of the chunk cannot interact with them, so all such movers commit together
+  // against the occupancy bitmap; the rare interacting movers are replayed in lane (= id) order.
   if (c[NC_ALLOW_OCCUPIED]) {
     for (int r = tid; r < R; r += T) if (ent_alive(ctx, r)) act_move(ctx, r, r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P], false);
   } else if (warp == 0) {
     for (int base = 0; base < R; base += 32) {
       int r = base + lane;
-      int dir = -1;
+      int dir = -1, src = -1, dst = -2;
       if (r < R && ent_alive(ctx, r)) dir = r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P];
-      unsigned m = __ballot_sync(0xffffffffu, dir >= 0 && dir <= 3);
-      while (m) {
-        int l = __ffs(m) - 1; m &= m - 1;
+      bool want = dir >= 0 && dir <= 3 && ENT(EA_FREEZE, r) == 0;
+      if (want) {
+        int rr = ENT(EA_ROW, r), cc = ENT(EA_COL, r);
+        int nr = rr + c_dir_dr[dir], nc = cc + c_dir_dc[dir];
+        src = rr * S + cc; dst = nr * S + nc;
+        want = !nm_impassible(ctx.map[dst]);
+      }
+      unsigned wm = __ballot_sync(0xffffffffu, want);
+      if (!wm) continue;
+      bool conflict = false;
+      for (unsigned mm = wm; mm;) {
+        int j = __ffs(mm) - 1; mm &= mm - 1;
+        int dj = __shfl_sync(0xffffffffu, dst, j), sj = __shfl_sync(0xffffffffu, src, j);
+        if (j != lane && want && (dst == dj || dst == sj || src == dj)) conflict = true;
+      }
+      if (want && !conflict) act_move(ctx, r, dir, true);
+      unsigned cm = __ballot_sync(0xffffffffu, want && conflict);
+      while (cm) {
+        int l = __ffs(cm) - 1; cm &= cm - 1;
         if (lane == l) act_move(ctx, r, dir, true);
         __syncwarp();
       }
+      __syncwarp();
     }
   }
   __syncthreads();
+  PHASE();
   // Sell (70)
   for (int p = tid; p < P; p += T) if (ent_alive(ctx, p) && ctx.act[A_SELL_ITEM * P + p]) act_sell(ctx, p, ctx.act[A_SELL_ITEM * P + p], ctx.act[A_SELL_PRICE * P + p]);
   __syncthreads();
 
+  PHASE();
   // ---- phase 4: cull ------------------------------------------------------------------
   for (int p = tid; p < P; p += T)
     if (ENT(EA_STATUS, p) == ES_ALIVE && ENT(EA_HEALTH, p) <= 0) {
@@ -1137,10 +1290,12 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     if (lane == 0) { ctx.sc[2] = nd; ctx.sc[4] = alive; }
   }
   __syncthreads();
+  PHASE();
   // ---- phase 5: npcs.spawn (sequential attempts) --------------------------------------
   if (tid == 0 && ctx.sc[4] < N) { __threadfence_block(); npc_spawn(ctx); }
   __syncthreads();
 
+  PHASE();
   // ---- phase 6: tick += 1, map.step, exchange.step ------------------------------------
   ctx.tick += 1;
   {
@@ -1163,6 +1318,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     }
   __syncthreads();
 
+  PHASE();
   // ---- write the tables back while the wrapper part runs ------------------------------
   fence_async_smem();
   __syncthreads();
@@ -1173,11 +1329,13 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     bulk_commit();
   }
 
+  PHASE();
   // ---- phase 7: fold the tick's events ------------------------------------------------
   int nev = min(ctx.sc[0], NM_EV_CAP);
   for (int i = tid; i < nev; i += T) fold_event(ctx, ctx.ev[i]);
   __syncthreads();
 
+  PHASE();
   // ---- phase 8: rewards, done flags, stat wrapper --------------------------------------
   int st_me = tid < P ? (int)ENT(EA_STATUS, tid) : ES_EMPTY;
   int n_alive = __syncthreads_count(st_me == ES_ALIVE);
@@ -1186,41 +1344,43 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   bool horizon = ctx.tick >= c[NC_HORIZON];
   if (horizon) n_current = 0;
   bool env_done = n_current <= c[NC_EARLY_STOP_N] || n_alive == 0;
-  for (int p = tid; p < P; p += T) {
-    size_t a = (size_t)env * P + p;
-    int st = ENT(EA_STATUS, p);
+  if (tid < P) {       // P <= blockDim: one thread per player, state prefetched at kernel start
+    const int p = tid;
+    const size_t a = my_a;
+    int st = st_me;
     float rew = 0.0f; uint8_t term = 0, trunc = 0, mask = 0;
     prm.info_valid[a] = 0;
     if (st != ES_EMPTY) {
       mask = 1;
       bool terminated = st == ES_DEAD_THIS_TICK;
       bool truncated = horizon && !terminated;
-      int32_t *sta = prm.stats + a * ST_N;
-      double *ds = prm.dstats + a * DS_N;
       double reward;
-      int completed = sta[ST_TASK_DONE], signals = sta[ST_REWARD_SIGNALS];
+      int completed = my_done, signals = my_signals;
+      int acc0 = ctx.acc[p * 2], acc1 = ctx.acc[p * 2 + 1];
+      if (acc0 != my_acc0) my_sta[ST_TASK_ACC0] = acc0;
+      if (acc1 != my_acc1) my_sta[ST_TASK_ACC1] = acc1;
       if (terminated) reward = -1.0;
       else {
         double diff = 0.0;
         if (!completed) {
-          const int32_t *t = prm.tasks + (size_t)prm.task_id[a] * NM_TASK_COLS;
-          int acc0 = __ldcg(&sta[ST_TASK_ACC0]), acc1 = __ldcg(&sta[ST_TASK_ACC1]);
-          double v = eval_predicate(ctx, p, t[0], t[1], t[2], t[3], acc0, acc1);
-          if (t[7] == 1) v = v * eval_predicate(ctx, p, t[5], t[6], 0, 0, 0, 0);
+          double v = eval_predicate(ctx, p, my_t[0], my_t[1], my_t[2], my_t[3], acc0, acc1);
+          if (my_t[7] == 1) v = v * eval_predicate(ctx, p, my_t[5], my_t[6], 0, 0, 0, 0);
           v = clip01(v);
-          diff = v - ds[DS_PROGRESS];
-          ds[DS_PROGRESS] = v;
-          if (v >= 1.0) { completed = ctx.tick; sta[ST_TASK_DONE] = completed; }
+          diff = v - my_prog;
+          if (v != my_prog) my_ds[DS_PROGRESS] = v;
+          my_prog = v;
+          if (v >= 1.0) { completed = ctx.tick; my_sta[ST_TASK_DONE] = completed; }
         }
         reward = diff;
-        if (reward > 0) { signals++; sta[ST_REWARD_SIGNALS] = signals; }
-        if (ds[DS_PROGRESS] > ds[DS_MAX_PROGRESS]) ds[DS_MAX_PROGRESS] = ds[DS_PROGRESS];
+        if (reward > 0) { signals++; my_sta[ST_REWARD_SIGNALS] = signals; }
+        if (my_prog > my_maxprog) { my_maxprog = my_prog; my_ds[DS_MAX_PROGRESS] = my_maxprog; }
       }
       if (env_done && !terminated) truncated = true;
-      int uprev = sta[ST_UNIQ_CURR], ucurr = uprev + ctx.duniq[p];
-      sta[ST_UNIQ_PREV] = uprev; sta[ST_UNIQ_CURR] = ucurr;
-      if (!(terminated || truncated)) ds[DS_CUM_REWARD] += reward;
-      else write_info(ctx, p, terminated, ds[DS_CUM_REWARD], ds[DS_MAX_PROGRESS], signals, completed);
+      int uprev = my_uniq, ucurr = uprev + ctx.duniq[p];
+      my_sta[ST_UNIQ_PREV] = uprev;
+      if (ucurr != uprev) my_sta[ST_UNIQ_CURR] = ucurr;
+      if (!(terminated || truncated)) { if (reward != 0.0) my_ds[DS_CUM_REWARD] = my_cum + reward; }
+      else write_info(ctx, p, terminated, my_cum, my_maxprog, signals, completed, ucurr);
       if (c[NC_USE_CUSTOM_REWARD]) {
         double explore = 0.0;
         if (prm.fcfg[NF_EXPLORE_W] > 0 && ucurr > uprev) explore = (double)min(c[NC_CLIP_UNIQUE], ucurr - uprev) * prm.fcfg[NF_EXPLORE_W];
@@ -1235,6 +1395,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     }
     prm.rew[a] = rew; prm.term[a] = term; prm.trunc[a] = trunc; prm.mask[a] = mask;
   }
+  PHASE();
   if (tid == 0) {
     gsc[SC_TICK] = ctx.tick; gsc[SC_DONE] = env_done ? 1 : 0; gsc[SC_N_DANGER] = ctx.sc[2]; gsc[SC_NEXT_NPC_ID] = ctx.sc[3];
     gsc[SC_FRESH] = 0;
@@ -1244,4 +1405,5 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     atomicAdd(&prm.counters[1], (unsigned long long)(n_alive + n_dead));
     bulk_wait_all();
   }
+  PHASE();
 }

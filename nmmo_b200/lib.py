@@ -20,7 +20,8 @@ EXPORTS = [
     "nmmo_create", "nmmo_destroy", "nmmo_reset", "nmmo_step", "nmmo_step_host", "nmmo_sample_actions",
     "nmmo_obs_ptr", "nmmo_reward_ptr", "nmmo_terminated_ptr", "nmmo_truncated_ptr", "nmmo_mask_ptr",
     "nmmo_info_ptr", "nmmo_info_valid_ptr", "nmmo_episode_done_ptr", "nmmo_obs_stride", "nmmo_num_envs",
-    "nmmo_num_agents", "nmmo_inject_rng", "nmmo_snapshot", "nmmo_stats", "nmmo_last_error",
+    "nmmo_num_agents", "nmmo_inject_rng", "nmmo_snapshot", "nmmo_stats", "nmmo_timing", "nmmo_timing_read", "nmmo_profile", "nmmo_set_obs_full",
+    "nmmo_last_error",
 ]
 
 
@@ -68,6 +69,14 @@ def load(build_if_missing: bool = True):
     L.nmmo_snapshot.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.nmmo_stats.restype = C.c_int
     L.nmmo_stats.argtypes = [vp, vp, vp, vp, C.c_int]
+    L.nmmo_timing.restype = C.c_int
+    L.nmmo_timing.argtypes = [vp, C.c_int]
+    L.nmmo_timing_read.restype = C.c_int
+    L.nmmo_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.nmmo_set_obs_full.restype = C.c_int
+    L.nmmo_set_obs_full.argtypes = [vp, C.c_int]
+    L.nmmo_profile.restype = C.c_int
+    L.nmmo_profile.argtypes = [vp, C.c_int, vp]
     L.nmmo_last_error.restype = C.c_char_p
     _lib = L
     return L
@@ -169,9 +178,14 @@ class Simulator:
         self._check(self.L.nmmo_step(self.h, C.c_void_p(a.data_ptr()), self._stream()))
 
     def step_host(self, actions: np.ndarray, want_obs: bool = False):
+        """Host-buffer call: actions int32 [E,P,12] in host memory (pinned = async copies)."""
         a = np.ascontiguousarray(actions, np.int32).reshape(self.E, self.P, 12)
         n = self.E * self.P
-        rew = np.empty(n, np.float32); term = np.empty(n, np.uint8); trunc = np.empty(n, np.uint8); mask = np.empty(n, np.uint8)
+        if getattr(self, "_host_out", None) is None:
+            t = self.torch
+            self._host_out = (t.empty(n, dtype=t.float32).pin_memory(), t.empty(n, dtype=t.uint8).pin_memory(),
+                              t.empty(n, dtype=t.uint8).pin_memory(), t.empty(n, dtype=t.uint8).pin_memory())
+        rew, term, trunc, mask = (x.numpy() for x in self._host_out)
         obs = np.empty((n, self.stride), np.uint8) if want_obs else None
         self._check(self.L.nmmo_step_host(self.h, _p(a), _p(rew), _p(term), _p(trunc), _p(mask), _p(obs), self._stream()))
         return rew, term, trunc, mask, obs
@@ -195,6 +209,22 @@ class Simulator:
 
     def stats(self, clear: bool = False):
         sums = np.zeros(SPEC["IN_N"], np.float64); counts = np.zeros(SPEC["IN_N"], np.float64)
-        counters = np.zeros(4, np.uint64)
+        counters = np.zeros(8, np.uint64)
         self._check(self.L.nmmo_stats(self.h, _p(sums), _p(counts), _p(counters), int(clear)))
         return sums, counts, counters
+
+    def timing(self, enable: bool):
+        self._check(self.L.nmmo_timing(self.h, int(enable)))
+
+    def timing_read(self):
+        a, b, n = C.c_double(), C.c_double(), C.c_int()
+        self._check(self.L.nmmo_timing_read(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
+    def profile(self, enable: bool):
+        out = np.zeros(32, np.uint64)
+        self._check(self.L.nmmo_profile(self.h, int(enable), _p(out)))
+        return out
+
+    def set_obs_full(self, full: bool):
+        self._check(self.L.nmmo_set_obs_full(self.h, int(full)))

@@ -162,3 +162,30 @@ class OracleEnv:
         mp = np.zeros((self.Sz, self.Sz), np.uint8)
         lib().oracle_snapshot(self.h, _ptr(ent), _ptr(items), _ptr(mp))
         return ent, items, mp
+
+
+class OracleBatch:
+    """Many sequential CPU envs stepped by an OpenMP loop (CPU baseline for bench.py)."""
+
+    def __init__(self, cfg, fcfg, maps, task_table, task_embed, n_envs, threads=None):
+        import os
+        self.envs = [OracleEnv(cfg, fcfg, maps, task_table, task_embed) for _ in range(n_envs)]
+        self.n = n_envs
+        self.P = self.envs[0].P
+        self.ptrs = (C.c_void_p * n_envs)(*[e.h for e in self.envs])
+        self.actions = np.zeros((n_envs, self.P, 12), np.int32)
+        self.threads = threads or len(os.sched_getaffinity(0))
+        os.environ.setdefault("OMP_NUM_THREADS", str(self.threads))
+
+    def reset(self, seeds):
+        for e, s in zip(self.envs, seeds):
+            e.reset(int(s))
+
+    def sample(self, seed):
+        lib().oracle_sample_many(self.ptrs, self.n, C.c_uint64(int(seed)), _ptr(self.actions))
+
+    def step(self):
+        lib().oracle_step_many(self.ptrs, self.n, _ptr(self.actions))
+
+    def alive(self):
+        return int(sum(int(e.mask.sum()) for e in self.envs))
