@@ -46,7 +46,7 @@ static size_t step_smem_bytes(const NmParams &p) {
   s += a16((size_t)((p.S * p.S + 31) / 32) * 4); s += 2 * a16((size_t)((p.CAP + 31) / 32) * 4);
   s += a16((size_t)p.P * NINV * 2); s += a16(p.P); s += a16((size_t)12 * p.P * 2);
   s += a16(p.N); s += a16((size_t)p.N * 2); s += a16(NM_EV_CAP * 8); s += a16((size_t)p.P * 4) * 2; s += a16(64); s += 16;
-  s += a16(1024); s += a16((size_t)p.P * 16); s += a16((size_t)p.P * 8); s += 2 * a16((size_t)p.R * 4);
+  s += a16(1024); s += a16((size_t)p.P * 16); s += a16((size_t)p.P * 8); s += a16(std::max<size_t>(4096, (size_t)p.R * 8)); s += a16(p.P);
   return s + 128;
 }
 static size_t obs_smem_bytes(const NmParams &p) {
@@ -96,6 +96,7 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   p.n_maps = n_maps; p.n_tasks = n_tasks; p.env_base = env_base;
   if (p.P <= 0 || p.P > NM_STEP_THREADS) { delete h; return fail(NM_ERR_LIMIT, "PLAYER_N must be in 1..256 for the per-env CTA design"); }
   if (p.R % 8 || p.CAP % 8 || (p.S * p.S) % 16) { delete h; return fail(NM_ERR_LIMIT, "P+N and item cap must be multiples of 8, S*S of 16 (bulk copies)"); }
+  if (p.R > 2 * NM_STEP_THREADS) { delete h; return fail(NM_ERR_LIMIT, "P+N must be <= 512 for the per-env CTA design"); }
   if (p.S > 255) { delete h; return fail(NM_ERR_LIMIT, "MAP_SIZE must be <= 255"); }
   if (p.L.n_ent > 255 || p.cfg[NC_N_INV] > 16) { delete h; return fail(NM_ERR_LIMIT, "N_ENT_OBS <= 255, N_INV <= 16"); }
   h->step_smem = step_smem_bytes(p);

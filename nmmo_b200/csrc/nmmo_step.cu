@@ -39,6 +39,8 @@ struct Ctx {
   unsigned short *npc_hash;   // open-addressing map NPC id -> row+1 (512 slots)
   int *task;                  // [P][4] pred, p0, p1, spare: the agent's task row for event folding
   int *acc;                   // [P][2] event-driven predicate accumulators
+  int8_t *slow;               // [P] result of the window-scan predicates (-1 = not requested)
+  const uint32_t *predraw;    // NPC-spawn draws computed in parallel: [attempt][8]
   uint64_t seed;
   int tick;
   int inj_lo, inj_hi;
@@ -295,17 +297,27 @@ __device__ int closest_target(const Ctx &ctx, int row, int rng) {
   return best_id;
 }
 // A* with the reference's 100-expansion budget; per-thread hash map + binary heap in local memory
-__device__ int astar_dir(const Ctx &ctx, int sr, int sc, int gr, int gc) {
-  const int HN = 512, CUTOFF = 100;
+// HN = node-table slots.  The search is first tried with a small table (cheap to clear; enough
+// for the common open-ground chase) and repeated with the full-size table if it fills up; the
+// result is identical either way.  Returns -2 when the table overflowed.
+template <int HN>
+__device__ int astar_dir_t(const Ctx &ctx, int sr, int sc, int gr, int gc) {
+  const int CUTOFF = 100;
   uint16_t hk[HN]; uint8_t hcost[HN]; int8_t hback[HN];
-  uint32_t heap[4 * CUTOFF + 12];
+  uint32_t heap[HN];
   if (sr == gr && sc == gc) return -1;
   for (int i = 0; i < HN; i++) hk[i] = 0;
+  int n_nodes = 0;
+  bool overflow = false;
   auto slot_of = [&](int r, int c, bool insert) -> int {
     uint16_t key = (uint16_t)(((r << 8) | c) + 1);
     int h = (int)((key * 40503u) >> 7) & (HN - 1);
     while (hk[h] != 0 && hk[h] != key) h = (h + 1) & (HN - 1);
-    if (hk[h] == 0) { if (!insert) return -1; hk[h] = key; hcost[h] = 255; hback[h] = -1; }
+    if (hk[h] == 0) {
+      if (!insert) return -1;
+      if (++n_nodes > (HN * 3) / 4) { overflow = true; return -1; }
+      hk[h] = key; hcost[h] = 255; hback[h] = -1;
+    }
     return h;
   };
   int hn = 0;
@@ -350,6 +362,8 @@ __device__ int astar_dir(const Ctx &ctx, int sr, int sc, int gr, int gc) {
       if (nm_impassible(tile_at(ctx, nr, nc))) continue;
       int ncost = ccost + 1;
       int s = slot_of(nr, nc, true);
+      if (overflow) return -2;
+      if (hn >= HN - 1) return -2;
       if (hcost[s] == 255 || ncost < hcost[s]) {
         hcost[s] = (uint8_t)ncost;
         int h = nm_linf(gr, gc, nr, nc);
@@ -374,6 +388,11 @@ __device__ int astar_dir(const Ctx &ctx, int sr, int sc, int gr, int gc) {
   if (dr == 0 && dc == 1) return 2;
   if (dr == 0 && dc == -1) return 3;
   return -1;
+}
+__device__ int astar_dir(const Ctx &ctx, int sr, int sc, int gr, int gc) {
+  int d = astar_dir_t<64>(ctx, sr, sc, gr, gc);
+  if (d == -2) d = astar_dir_t<512>(ctx, sr, sc, gr, gc);
+  return d;
 }
 __device__ void npc_decide(const Ctx &ctx, int row) {
   int vis = ctx.c[NC_NPC_VISION];
@@ -606,31 +625,32 @@ __device__ int border_dist(const Ctx &ctx, int r, int c) {
   int b = ctx.c[NC_MAP_BORDER], ce = ctx.c[NC_MAP_CENTER];
   return min(min(r - b, ce + b - r - 1), min(c - b, ce + b - c - 1));
 }
-__device__ void npc_spawn(const Ctx &ctx) {       // single thread
+// NPCManager.spawn, split: one thread replays the sequential accept/reject logic of the (up to
+// 25) attempts and records the accepted ones; the rows are then filled in by one thread each
+__device__ int npc_spawn_decide(const Ctx &ctx, uint32_t *dec) {       // single thread
   const int32_t *c = ctx.c;
   int b = c[NC_MAP_BORDER], ce = c[NC_MAP_CENTER];
   int count = ctx.sc[4];
-  int scan = ctx.P;
+  int scan = ctx.P, n = 0;
   int16_t *danger = ctx.p->danger + (size_t)ctx.env * ctx.N;
   for (int att = 0; att < c[NC_NPC_SPAWN_ATTEMPTS]; att++) {
     if (count >= ctx.N) break;
     while (scan < ctx.R && ENT(EA_STATUS, scan) == ES_ALIVE) scan++;
     if (scan >= ctx.R) break;
-    uint32_t k = 0;
     int r, cc;
     int nd = ctx.sc[2];
     if (nd > 0) {
       int d = danger[nd - 1];
       int mid = ce / 2, max_off = mid - d;
-      int offset = mid + b + nm_bounded(draw(ctx, RS_NPC_SPAWN, att, k++), 2 * max_off) - max_off;
-      int side = nm_bounded(draw(ctx, RS_NPC_SPAWN, att, k++), 4);
+      int offset = mid + b + nm_bounded(ctx.predraw[att * 8 + 0], 2 * max_off) - max_off;
+      int side = nm_bounded(ctx.predraw[att * 8 + 1], 4);
       if (side == 0) { r = b + d; cc = offset; }
       else if (side == 1) { r = b + ce - d - 1; cc = offset; }
       else if (side == 2) { cc = b + d; r = offset; }
       else { cc = b + ce - d - 1; r = offset; }
     } else {
-      r = b + nm_bounded(draw(ctx, RS_NPC_SPAWN, att, k++), ce);
-      cc = b + nm_bounded(draw(ctx, RS_NPC_SPAWN, att, k++), ce);
+      r = b + nm_bounded(ctx.predraw[att * 8 + 0], ce);
+      cc = b + nm_bounded(ctx.predraw[att * 8 + 1], ce);
     }
     if (nm_impassible(tile_at(ctx, r, cc))) continue;
     if (!c[NC_ALLOW_OCCUPIED] && occ_get(ctx, r, cc)) continue;
@@ -640,31 +660,40 @@ __device__ void npc_spawn(const Ctx &ctx) {       // single thread
     else if (200 * d >= c[NC_NPC_NEUT_PCT] * ce) type = 2;
     else if (200 * d >= c[NC_NPC_PASS_PCT] * ce) type = 1;
     else continue;
-    int style = nm_bounded(draw(ctx, RS_NPC_SPAWN, att, k++), 3);
-    int level = (2 * d * (c[NC_NPC_LEVEL_MAX] - c[NC_NPC_LEVEL_MIN])) / ce + c[NC_NPC_LEVEL_MIN];
-    int frac = (int)(draw(ctx, RS_NPC_SPAWN, att, k++) >> 16);
-    int lvl_fp = level * 65536 - frac;
-    int armor = IT_HAT + nm_bounded(draw(ctx, RS_NPC_SPAWN, att, k++), 3);
-    int tool = IT_ROD + nm_bounded(draw(ctx, RS_NPC_SPAWN, att, k++), 5);
-    int row = scan;
-    for (int col = 0; col < EA_N; col++) ENT(col, row) = 0;
-    ENT(EA_ID, row) = (int16_t)ctx.sc[3]; ctx.sc[3]--;
-    ENT(EA_NPC_TYPE, row) = (int16_t)type; ENT(EA_ROW, row) = (int16_t)r; ENT(EA_COL, row) = (int16_t)cc;
-    ENT(EA_GOLD, row) = (int16_t)level;
-    ENT(EA_HEALTH, row) = (int16_t)c[NC_RES_BASE]; ENT(EA_FOOD, row) = (int16_t)c[NC_RES_BASE]; ENT(EA_WATER, row) = (int16_t)c[NC_RES_BASE];
-    for (int s = 0; s < 3; s++) ENT(EA_MELEE_LEVEL + 2 * s, row) = 1;
-    ENT(EA_MELEE_LEVEL + 2 * style, row) = (int16_t)level;
-    ENT(EA_MELEE_EXP + 2 * style, row) = (int16_t)c[NC_EXP_THRESH0 + level - 1];
-    ENT(EA_ITEM_LEVEL, row) = (int16_t)((5LL * lvl_fp) >> 16);
-    ENT(EA_NPC_STYLE, row) = (int16_t)style; ENT(EA_NPC_DANGER, row) = (int16_t)d;
-    ENT(EA_NPC_OFFENSE, row) = (int16_t)(c[NC_NPC_BASE_DAMAGE] + (int)(((int64_t)lvl_fp * c[NC_NPC_LEVEL_DAMAGE]) >> 16));
-    ENT(EA_NPC_DEFENSE, row) = (int16_t)(c[NC_NPC_BASE_DEFENSE] + (int)(((int64_t)lvl_fp * c[NC_NPC_LEVEL_DEFENSE]) >> 16));
-    ENT(EA_NPC_DROP_ARMOR, row) = (int16_t)armor; ENT(EA_NPC_DROP_TOOL, row) = (int16_t)tool;
-    ENT(EA_STATUS, row) = ES_ALIVE;
+    uint32_t *q = dec + n * 8;
+    q[0] = (uint32_t)scan; q[1] = (uint32_t)r; q[2] = (uint32_t)cc; q[3] = (uint32_t)d; q[4] = (uint32_t)type;
+    q[5] = (uint32_t)att; q[6] = (uint32_t)ctx.sc[3];
+    ctx.sc[3]--;
+    ENT(EA_STATUS, scan) = ES_ALIVE;
     occ_set(ctx, r, cc);
-    count++;
+    count++; n++;
     if (nd > 0) ctx.sc[2] = nd - 1;
   }
+  return n;
+}
+__device__ void npc_spawn_fill(const Ctx &ctx, const uint32_t *q) {
+  const int32_t *c = ctx.c;
+  int ce = c[NC_MAP_CENTER];
+  int row = (int)q[0], r = (int)q[1], cc = (int)q[2], d = (int)q[3], type = (int)q[4], att = (int)q[5];
+  int style = nm_bounded(ctx.predraw[att * 8 + 2], 3);
+  int level = (2 * d * (c[NC_NPC_LEVEL_MAX] - c[NC_NPC_LEVEL_MIN])) / ce + c[NC_NPC_LEVEL_MIN];
+  int frac = (int)(ctx.predraw[att * 8 + 3] >> 16);
+  int lvl_fp = level * 65536 - frac;
+  int armor = IT_HAT + nm_bounded(ctx.predraw[att * 8 + 4], 3);
+  int tool = IT_ROD + nm_bounded(ctx.predraw[att * 8 + 5], 5);
+  for (int col = 0; col < EA_N; col++) if (col != EA_STATUS) ENT(col, row) = 0;
+  ENT(EA_ID, row) = (int16_t)(int)q[6];
+  ENT(EA_NPC_TYPE, row) = (int16_t)type; ENT(EA_ROW, row) = (int16_t)r; ENT(EA_COL, row) = (int16_t)cc;
+  ENT(EA_GOLD, row) = (int16_t)level;
+  ENT(EA_HEALTH, row) = (int16_t)c[NC_RES_BASE]; ENT(EA_FOOD, row) = (int16_t)c[NC_RES_BASE]; ENT(EA_WATER, row) = (int16_t)c[NC_RES_BASE];
+  for (int s = 0; s < 3; s++) ENT(EA_MELEE_LEVEL + 2 * s, row) = 1;
+  ENT(EA_MELEE_LEVEL + 2 * style, row) = (int16_t)level;
+  ENT(EA_MELEE_EXP + 2 * style, row) = (int16_t)c[NC_EXP_THRESH0 + level - 1];
+  ENT(EA_ITEM_LEVEL, row) = (int16_t)((5LL * lvl_fp) >> 16);
+  ENT(EA_NPC_STYLE, row) = (int16_t)style; ENT(EA_NPC_DANGER, row) = (int16_t)d;
+  ENT(EA_NPC_OFFENSE, row) = (int16_t)(c[NC_NPC_BASE_DAMAGE] + (int)(((int64_t)lvl_fp * c[NC_NPC_LEVEL_DAMAGE]) >> 16));
+  ENT(EA_NPC_DEFENSE, row) = (int16_t)(c[NC_NPC_BASE_DEFENSE] + (int)(((int64_t)lvl_fp * c[NC_NPC_LEVEL_DEFENSE]) >> 16));
+  ENT(EA_NPC_DROP_ARMOR, row) = (int16_t)armor; ENT(EA_NPC_DROP_TOOL, row) = (int16_t)tool;
 }
 
 // ------------------------------------------------------------------------ tasks -----
@@ -675,6 +704,7 @@ __device__ double eval_predicate(const Ctx &ctx, int p, int pred, int p0, int p1
     case TP_TICK_GE: return clip01((double)ctx.tick / (double)p0);
     case TP_COUNT_EVENT: case TP_SCORE_HIT: return clip01((double)acc0 / (double)p1);
     case TP_CAN_SEE_TILE: {
+      if (ctx.slow[p] >= 0) return (double)ctx.slow[p];
       int r = ENT(EA_ROW, p), c = ENT(EA_COL, p);
       for (int dr = -vis; dr <= vis; dr++) for (int dc = -vis; dc <= vis; dc++)
         if (tile_at(ctx, r + dr, c + dc) == p0) return 1.0;
@@ -682,6 +712,7 @@ __device__ double eval_predicate(const Ctx &ctx, int p, int pred, int p0, int p1
     }
     case TP_CAN_SEE_AGENT: case TP_CAN_SEE_GROUP: {
       // visible = among the first n_ent table rows inside the vision window
+      if (ctx.slow[p] >= 0) return (double)ctx.slow[p];
       int lo = p0, hi = pred == TP_CAN_SEE_AGENT ? p0 : p1;
       int r = ENT(EA_ROW, p), c = ENT(EA_COL, p), seen = 0;
       for (int row = 0; row < ctx.R && seen < ctx.p->L.n_ent; row++) {
@@ -938,8 +969,13 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   ctx.npc_hash = (unsigned short *)carve(512 * 2);
   ctx.task = (int *)carve((size_t)P * 16);
   ctx.acc = (int *)carve((size_t)P * 8);
-  uint32_t *s_att = (uint32_t *)carve((size_t)R * 4);
-  int *s_first = (int *)carve((size_t)R * 4);
+  // 4 KB scratch reused phase by phase: attack list + registrations, move tile hash,
+  // respawn worklist, NPC-spawn pre-drawn values
+  const size_t scratch_bytes = max((size_t)4096, (size_t)R * 8);
+  uint32_t *s_scratch = (uint32_t *)carve(scratch_bytes);
+  uint32_t *s_att = s_scratch;
+  int *s_first = (int *)(s_scratch + R);
+  ctx.slow = (int8_t *)carve((size_t)P);
   ctx.sc = (int *)carve(16 * 4);
   uint64_t *bar = (uint64_t *)carve(8);
   ctx.seed = prm.seed[env];
@@ -1094,8 +1130,16 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
         emit(ctx, p, EV_DRINK_WATER, 0, 0, 0, 0, 0);
       }
       ENT(EA_WATER, p) = (int16_t)water;
-      ENT(EA_FOOD, p) = (int16_t)max(0, food - c[NC_RES_DEPLETION]);
+      food = max(0, food - c[NC_RES_DEPLETION]);
       int here = tile_at(ctx, r, cc);
+      if (here == MT_FOILAGE && !c[NC_ALLOW_OCCUPIED]) {
+        // with one entity per tile nobody else can eat this tile: no ordering needed
+        ctx.map[r * S + cc] = MT_SCRUB;
+        food = min(c[NC_RES_BASE], food + c[NC_RES_HARVEST_RESTORE]);
+        emit(ctx, p, EV_EAT_FOOD, 0, 0, 0, 0, 0);
+        here = MT_SCRUB;
+      }
+      ENT(EA_FOOD, p) = (int16_t)food;
       seq = here == MT_FOILAGE || here == MT_HERB || here == MT_ORE || here == MT_TREE || here == MT_CRYSTAL ||
             up == MT_FISH || dn == MT_FISH || lf == MT_FISH || rt == MT_FISH;
     }
@@ -1163,97 +1207,119 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   PHASE();
   // Attack (50): the reference executes attacks in entity-id order.  Two attacks commute unless
   // they share an entity (as attacker or target) or touch the item allocator (a kill, or the
-  // last unit of ammunition).  Warp 0 therefore runs rounds: every pending attack registers its
+  // last unit of ammunition).  The block therefore runs rounds: every pending attack registers its
   // index on both entities with atomicMin; an attack that holds the minimum on both is "ready";
-  // ready attacks without allocator effects are applied in parallel, one per lane; an attack with
+  // ready attacks without allocator effects are applied in parallel, one per thread; an attack with
   // allocator effects is applied only when it is the lowest pending index, i.e. in exact
   // sequential position.  The lowest pending attack is always ready, so every round progresses.
-  if (warp == 0) {
+  {
     const uint32_t DONE = 0xffffffffu;
-    int na = 0;
-    for (int base = 0; base < R; base += 32) {
-      int r = base + lane;
-      int tgt = 0;
-      if (r < P) tgt = ctx.act[A_ATT_TARGET * P + r]; else if (r < R) tgt = ctx.npc_att[r - P];
-      bool has = tgt != 0 && tgt - 1 != r && ent_alive(ctx, r);
-      unsigned m = __ballot_sync(0xffffffffu, has);
-      if (has) s_att[na + __popc(m & ((1u << lane) - 1))] = ((uint32_t)r << 16) | (uint32_t)(tgt - 1);
-      na += __popc(m);
+    if (warp == 0) {
+      int na = 0;
+      for (int base = 0; base < R; base += 32) {
+        int r = base + lane;
+        int tgt = 0;
+        if (r < P) tgt = ctx.act[A_ATT_TARGET * P + r]; else if (r < R) tgt = ctx.npc_att[r - P];
+        bool has = tgt != 0 && tgt - 1 != r && ent_alive(ctx, r);
+        unsigned m = __ballot_sync(0xffffffffu, has);
+        if (has) s_att[na + __popc(m & ((1u << lane) - 1))] = ((uint32_t)r << 16) | (uint32_t)(tgt - 1);
+        na += __popc(m);
+      }
+      if (lane == 0) ctx.sc[6] = na;
     }
-    for (int r = lane; r < R; r += 32) s_first[r] = 0x7fffffff;
-    __syncwarp();
-    int remaining = na;
-    while (remaining > 0) {
-      int mylow = 0x7fffffff;
-      for (int i = lane; i < na; i += 32) {
+    __syncthreads();
+    const int na = ctx.sc[6];
+    int pending = na > 0;
+    while (pending) {
+      for (int r = tid; r < R; r += T) s_first[r] = 0x7fffffff;
+      if (tid == 0) ctx.sc[7] = 0x7fffffff;
+      __syncthreads();
+      for (int i = tid; i < na; i += T) {
         uint32_t x = s_att[i];
         if (x == DONE) continue;
-        if (i < mylow) mylow = i;
         atomicMin(&s_first[x >> 16], i);
         atomicMin(&s_first[x & 0xffff], i);
+        atomicMin(&ctx.sc[7], i);
       }
-      int lowest = __reduce_min_sync(0xffffffffu, mylow);
-      __syncwarp();
-      int ndone = 0;
-      for (int i = lane; i < na; i += 32) {
+      __syncthreads();
+      const int lowest = ctx.sc[7];
+      int still = 0;
+      for (int i = tid; i < na; i += T) {
         uint32_t x = s_att[i];
         if (x == DONE) continue;
         int a = x >> 16, t = x & 0xffff;
-        if (s_first[a] != i || s_first[t] != i) continue;
-        bool done = true;
-        if (ent_alive(ctx, a)) {
-          int style = a < P ? (int)ctx.act[A_ATT_STYLE * P + a] : (int)ENT(EA_NPC_STYLE, a);
-          int dmg; bool ammo_out;
-          if (attack_compute(ctx, a, style, t, dmg, ammo_out)) {
-            bool heavy = ammo_out || dmg >= ENT(EA_HEALTH, t);
-            if (!heavy || i == lowest) attack_apply(ctx, a, style, t, dmg);
-            else done = false;
+        bool done = false;
+        if (s_first[a] == i && s_first[t] == i) {
+          done = true;
+          if (ent_alive(ctx, a)) {
+            int style = a < P ? (int)ctx.act[A_ATT_STYLE * P + a] : (int)ENT(EA_NPC_STYLE, a);
+            int dmg; bool ammo_out;
+            if (attack_compute(ctx, a, style, t, dmg, ammo_out)) {
+              bool heavy = ammo_out || dmg >= ENT(EA_HEALTH, t);
+              if (!heavy || i == lowest) attack_apply(ctx, a, style, t, dmg);
+              else done = false;
+            }
           }
         }
-        if (done) { s_att[i] = DONE; ndone++; }
+        if (done) s_att[i] = DONE; else still = 1;
       }
-      __syncwarp();
-      for (int r = lane; r < R; r += 32) s_first[r] = 0x7fffffff;
-      remaining -= __reduce_add_sync(0xffffffffu, ndone);
-      __syncwarp();
+      pending = __syncthreads_or(still);
     }
   }
   __syncthreads();
   PHASE();
-  // Move (60): with one entity per tile the reference resolves moves in entity-id order.  Warp 0
-  // takes 32 entities at a time; a mover whose source and destination tiles are touched by no
-  // other mover of the chunk cannot interact with them, so all such movers commit together
-  // against the occupancy bitmap; the rare interacting movers are replayed in lane (= id) order.
+  // Move (60): with one entity per tile the reference resolves moves in entity-id order.
   if (c[NC_ALLOW_OCCUPIED]) {
     for (int r = tid; r < R; r += T) if (ent_alive(ctx, r)) act_move(ctx, r, r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P], false);
-  } else if (warp == 0) {
-    for (int base = 0; base < R; base += 32) {
-      int r = base + lane;
-      int dir = -1, src = -1, dst = -2;
-      if (r < R && ent_alive(ctx, r)) dir = r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P];
-      bool want = dir >= 0 && dir <= 3 && ENT(EA_FREEZE, r) == 0;
-      if (want) {
-        int rr = ENT(EA_ROW, r), cc = ENT(EA_COL, r);
-        int nr = rr + c_dir_dr[dir], nc = cc + c_dir_dc[dir];
-        src = rr * S + cc; dst = nr * S + nc;
-        want = !nm_impassible(ctx.map[dst]);
+  } else {
+    // every pending mover registers its row index on its source and destination tile (atomicMin
+    // in a 1024-slot tile hash); a mover holding the minimum on both tiles cannot be affected by
+    // any other pending mover, so all such movers commit together; chains resolve in later rounds
+    const uint32_t EMPTY = 0xffffffffu;
+    uint32_t *tbl = s_scratch;
+    auto slot_insert = [&](int key, int idx) {
+      uint32_t v = ((uint32_t)key << 16) | (uint32_t)idx;
+      unsigned h = ((unsigned)key * 40503u >> 3) & 1023u;
+      for (;;) {
+        uint32_t cur = tbl[h];
+        if (cur == EMPTY) { uint32_t old = atomicCAS(&tbl[h], EMPTY, v); if (old == EMPTY) return; cur = old; }
+        if ((cur >> 16) == (uint32_t)key) { atomicMin(&tbl[h], v); return; }
+        h = (h + 1) & 1023u;
       }
-      unsigned wm = __ballot_sync(0xffffffffu, want);
-      if (!wm) continue;
-      bool conflict = false;
-      for (unsigned mm = wm; mm;) {
-        int j = __ffs(mm) - 1; mm &= mm - 1;
-        int dj = __shfl_sync(0xffffffffu, dst, j), sj = __shfl_sync(0xffffffffu, src, j);
-        if (j != lane && want && (dst == dj || dst == sj || src == dj)) conflict = true;
+    };
+    auto slot_min = [&](int key) -> int {
+      unsigned h = ((unsigned)key * 40503u >> 3) & 1023u;
+      for (;;) { uint32_t cur = tbl[h]; if ((cur >> 16) == (uint32_t)key) return (int)(cur & 0xffffu); h = (h + 1) & 1023u; }
+    };
+    int mv_src[2], mv_dst[2], mv_dir[2];
+    bool mv_want[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      int r = tid + k * T;
+      mv_want[k] = false; mv_src[k] = 0; mv_dst[k] = 0; mv_dir[k] = -1;
+      if (r < R && ent_alive(ctx, r)) {
+        int dir = r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P];
+        if (dir >= 0 && dir <= 3 && ENT(EA_FREEZE, r) == 0) {
+          int rr = ENT(EA_ROW, r), cc = ENT(EA_COL, r);
+          int dst = (rr + c_dir_dr[dir]) * S + cc + c_dir_dc[dir];
+          if (!nm_impassible(ctx.map[dst])) { mv_want[k] = true; mv_src[k] = rr * S + cc; mv_dst[k] = dst; mv_dir[k] = dir; }
+        }
       }
-      if (want && !conflict) act_move(ctx, r, dir, true);
-      unsigned cm = __ballot_sync(0xffffffffu, want && conflict);
-      while (cm) {
-        int l = __ffs(cm) - 1; cm &= cm - 1;
-        if (lane == l) act_move(ctx, r, dir, true);
-        __syncwarp();
-      }
-      __syncwarp();
+    }
+    int pending = __syncthreads_or(mv_want[0] || mv_want[1]);
+    while (pending) {
+      for (int i = tid; i < 1024; i += T) tbl[i] = EMPTY;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 2; k++) if (mv_want[k]) { slot_insert(mv_src[k], tid + k * T); slot_insert(mv_dst[k], tid + k * T); }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 2; k++)
+        if (mv_want[k] && slot_min(mv_src[k]) == tid + k * T && slot_min(mv_dst[k]) == tid + k * T) {
+          act_move(ctx, tid + k * T, mv_dir[k], true);
+          mv_want[k] = false;
+        }
+      pending = __syncthreads_or(mv_want[0] || mv_want[1]);
     }
   }
   __syncthreads();
@@ -1292,25 +1358,51 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   __syncthreads();
   PHASE();
   // ---- phase 5: npcs.spawn (sequential attempts) --------------------------------------
-  if (tid == 0 && ctx.sc[4] < N) { __threadfence_block(); npc_spawn(ctx); }
+  if (ctx.sc[4] < N) {       // block-uniform: some NPC slot is free
+    // the draws of every attempt are keyed by (attempt, ordinal): compute them all in parallel
+    const int n_pre = min(c[NC_NPC_SPAWN_ATTEMPTS] * 8, (int)(scratch_bytes / 4));
+    for (int i = tid; i < n_pre; i += T) s_scratch[i] = draw(ctx, RS_NPC_SPAWN, (uint32_t)(i >> 3), (uint32_t)(i & 7));
+    ctx.predraw = s_scratch;
+    uint32_t *dec = s_scratch + 256;
+    __syncthreads();
+    if (tid == 0) ctx.sc[5] = npc_spawn_decide(ctx, dec);
+    __syncthreads();
+    if (tid < ctx.sc[5]) npc_spawn_fill(ctx, dec + tid * 8);
+  }
   __syncthreads();
 
   PHASE();
   // ---- phase 6: tick += 1, map.step, exchange.step ------------------------------------
   ctx.tick += 1;
   {
+    // map.step: every depleted tile draws once.  Depleted tiles are first gathered into a
+    // worklist (the draw is keyed by the tile, so order is free), then hashed by all threads
     const uint32_t *m32 = (const uint32_t *)ctx.map;
-    for (int w = tid; w < S * S / 4; w += T) {
+    uint16_t *wl = (uint16_t *)s_scratch;
+    const int wl_cap = (int)(scratch_bytes / 2);
+    const int n_words = S * S / 4;
+    auto respawn_tile = [&](int i, int m) {
+      int thr_idx = m == MT_SCRUB ? NC_RESPAWN_FOILAGE : m == MT_SLAG ? NC_RESPAWN_ORE : m == MT_STUMP ? NC_RESPAWN_TREE
+                  : m == MT_FRAGMENT ? NC_RESPAWN_CRYSTAL : m == MT_WEEDS ? NC_RESPAWN_HERB : NC_RESPAWN_FISH;
+      if (draw(ctx, RS_RESPAWN, (uint32_t)i, 0) < (uint32_t)c[thr_idx]) ctx.map[i] = (uint8_t)(m + 1);
+    };
+    if (tid == 0) ctx.sc[5] = 0;
+    __syncthreads();
+    for (int w = tid; w < n_words; w += T) {
       uint32_t word = m32[w];
+#pragma unroll
       for (int b = 0; b < 4; b++) {
         int m = (word >> (8 * b)) & 255;
-        if (!((NM_DEPLETED_MASK >> m) & 1)) continue;
-        int thr_idx = m == MT_SCRUB ? NC_RESPAWN_FOILAGE : m == MT_SLAG ? NC_RESPAWN_ORE : m == MT_STUMP ? NC_RESPAWN_TREE
-                    : m == MT_FRAGMENT ? NC_RESPAWN_CRYSTAL : m == MT_WEEDS ? NC_RESPAWN_HERB : NC_RESPAWN_FISH;
-        int i = w * 4 + b;
-        if (draw(ctx, RS_RESPAWN, (uint32_t)i, 0) < (uint32_t)c[thr_idx]) ctx.map[i] = (uint8_t)(m + 1);
+        if ((NM_DEPLETED_MASK >> m) & 1) {
+          int k = atomicAdd(&ctx.sc[5], 1);
+          if (k < wl_cap) wl[k] = (uint16_t)(w * 4 + b);
+          else respawn_tile(w * 4 + b, m);          // worklist full: draw in place
+        }
       }
     }
+    __syncthreads();
+    int n = min(ctx.sc[5], wl_cap);
+    for (int k = tid; k < n; k += T) { int i = wl[k]; respawn_tile(i, ctx.map[i]); }
   }
   for (int i = tid; i < CAP; i += T)
     if (ITM(IS_TYPE, i) != 0 && ITM(IS_PRICE, i) > 0 && ctx.tick - ITM(IS_LIST_TICK, i) > c[NC_LISTING_DURATION]) {
@@ -1338,6 +1430,38 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   PHASE();
   // ---- phase 8: rewards, done flags, stat wrapper --------------------------------------
   int st_me = tid < P ? (int)ENT(EA_STATUS, tid) : ES_EMPTY;
+  // window-scan predicates (CanSeeTile / CanSeeAgent / CanSeeGroup) are evaluated by a whole warp
+  // per requesting agent instead of a 225- or 384-iteration loop in one lane
+  if (tid < P) {
+    bool req = st_me == ES_ALIVE && !my_done && (my_t[0] == TP_CAN_SEE_TILE || my_t[0] == TP_CAN_SEE_AGENT || my_t[0] == TP_CAN_SEE_GROUP);
+    ctx.slow[tid] = req ? (int8_t)-2 : (int8_t)-1;
+  }
+  __syncthreads();
+  for (int p = warp; p < P; p += (T >> 5)) {
+    if (ctx.slow[p] != -2) continue;
+    int pred = ctx.task[p * 4], q0 = ctx.task[p * 4 + 1], q1 = ctx.task[p * 4 + 2];
+    int r = ENT(EA_ROW, p), cc = ENT(EA_COL, p), vis = c[NC_VISION];
+    bool hit = false;
+    if (pred == TP_CAN_SEE_TILE) {
+      int win = 2 * vis + 1;
+      for (int w = lane; w < win * win; w += 32) hit |= tile_at(ctx, r - vis + w / win, cc - vis + w % win) == q0;
+      hit = __any_sync(0xffffffffu, hit);
+    } else {
+      int lo = q0, hi = pred == TP_CAN_SEE_AGENT ? q0 : q1, seen = 0;
+      for (int base = 0; base < R && seen < prm.L.n_ent; base += 32) {
+        int row = base + lane;
+        bool in = row < R && ENT(EA_STATUS, row) == ES_ALIVE && nm_iabs(ENT(EA_ROW, row) - r) <= vis && nm_iabs(ENT(EA_COL, row) - cc) <= vis;
+        unsigned bm = __ballot_sync(0xffffffffu, in);
+        int rank = seen + __popc(bm & ((1u << lane) - 1));
+        int id = in ? (int)ENT(EA_ID, row) : 0;
+        hit |= in && rank < prm.L.n_ent && id >= lo && id <= hi;
+        seen += __popc(bm);
+      }
+      hit = __any_sync(0xffffffffu, hit);
+    }
+    if (lane == 0) ctx.slow[p] = hit ? 1 : 0;
+  }
+  __syncthreads();
   int n_alive = __syncthreads_count(st_me == ES_ALIVE);
   int n_dead = __syncthreads_count(st_me == ES_DEAD_THIS_TICK);
   int n_current = n_alive + n_dead;
