@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the batched Neural MMO step on B200 (BASELINE.json metric).
 
-One "step" = one lock-step tick of every environment on the GPU: the action-sampler kernel
-(uniform-random valid actions from the ActionTargets masks, BASELINE.json config 2), the
-step kernel (Realm.step + reward/stat wrapper) and the observation kernel.  Workload at N=1:
+One "step" = one lock-step tick of every environment on the GPU: the step kernel (Realm.step +
+reward/stat wrapper) and the observation kernel, which also draws the next uniform-random valid
+actions from the ActionTargets masks it has just built (BASELINE.json config 2).  Workload at N=1:
 configs[1] -- 4096 envs x 128 agents, full NeurIPS23 config with the takeru overrides, from
 reset with auto-reset on episode end.  N>1: the same per-GPU workload on every rank (envs
 sharded by global index, no collective in the step; one NCCL all-reduce of the episode-stat
@@ -161,11 +161,13 @@ def run_native(args):
     E, P = args.envs, int(cfg[SPEC["NC_N_PLAYERS"]])
     sim = Simulator(*w[:2], E, *w[2:], device=local_rank, env_base=rank * E)
     seeds = np.arange(E, dtype=np.uint64) + np.uint64(rank * E + args.seed)
-    sim.reset(seeds)
     stream = torch.cuda.current_stream()
 
+    # built-in random policy: the observation kernel writes next tick's uniform-random valid
+    # actions itself (same draws as the stand-alone sampler kernel, tests/test_parity_gpu.py)
+    sim.set_autosample(args.seed, sim.actions)
+
     def tick(seed):
-        sim.sample_actions(seed)
         sim.step()
 
     def barrier():
@@ -174,6 +176,7 @@ def run_native(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sim.reset(seeds)
     for _ in range(args.warmup):
         tick(args.seed)
     sim.stats(clear=True)
@@ -212,8 +215,7 @@ def run_native(args):
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(stream)
     for _ in range(e2e_steps):
-        sim.sample_actions(args.seed)                    # stands in for the policy's sampled actions
-        act_host.copy_(sim.actions, non_blocking=True)   # actions leave the device (clean_pufferl.py:329)
+        act_host.copy_(sim.actions, non_blocking=True)   # the policy's actions leave the device (clean_pufferl.py:329)
         stream.synchronize()
         sim.step_host(act_host.numpy())                  # H2D actions, step, D2H reward/term/trunc/mask
     f1.record(stream)
@@ -270,7 +272,7 @@ def run_native(args):
             "e2e": {"value": world_size * n * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "path": "nmmo_step_host (C ABI, pinned host actions in; reward/term/trunc/mask out; obs stay on device)"},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": 2 * args.steps,
             "clocks": clk,
             "episode_stats": {"finished_agents": float(g_counts[SPEC["IN_LENGTH"]]),
                               "mean_length": float(g_sums[SPEC["IN_LENGTH"]] / max(1.0, g_counts[SPEC["IN_LENGTH"]])),

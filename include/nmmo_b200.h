@@ -71,6 +71,11 @@ int nmmo_step_host(nmmo_handle *h, const int32_t *actions_host, float *rew_out, 
  * keyed (seed, global env, tick, agent, head); writes DEVICE int32 [E][P][12]. */
 int nmmo_sample_actions(nmmo_handle *h, uint64_t seed, int32_t *actions_dev, void *stream);
 
+/* Built-in random policy: with a non-NULL DEVICE buffer int32 [E][P][12], every reset/step also
+ * writes uniform-random valid actions for the new observations into it (identical draws to
+ * nmmo_sample_actions(seed)); NULL switches it off. */
+int nmmo_set_autosample(nmmo_handle *h, uint64_t seed, int32_t *actions_dev_out);
+
 /* Device pointers to the step outputs (valid until nmmo_destroy, rewritten by each step). */
 void *nmmo_obs_ptr(nmmo_handle *h);          /* uint8 [E*P][stride]  flat observation records */
 void *nmmo_reward_ptr(nmmo_handle *h);       /* float [E*P] */

@@ -57,6 +57,7 @@ static size_t obs_smem_bytes(const NmParams &p) {
   s += a16((size_t)p.L.n_mkt * IA_N_OBS * 2); s += a16((size_t)p.L.n_mkt * 2);
   s += a16((size_t)p.P * NINV * 2); s += a16((size_t)p.P * 4); s += a16(64 * 4);
   s += a16((size_t)NW * a16(p.L.m_end)); s += a16((size_t)NW * a16((size_t)p.L.n_ent * 2)); s += 16;
+  s += a16((size_t)NW * 128); s += a16(2 * AC_N * 4); s += a16((size_t)p.R * 4); s += a16(a16(p.L.m_end));
   return s + 128;
 }
 
@@ -367,5 +368,15 @@ extern "C" int nmmo_profile(nmmo_handle *h, int enable, unsigned long long *out3
 extern "C" int nmmo_set_obs_full(nmmo_handle *h, int full) {
   if (!h) return fail(NM_ERR_ARG, "null handle");
   h->prm.obs_full = full != 0;
+  return NM_OK;
+}
+
+// Built-in random policy: when `actions_dev_out` is non-NULL every observation pass also writes
+// uniform-random valid actions (same draws as nmmo_sample_actions with this seed) into it, so a
+// rollout with the random policy needs no sampler launch.  NULL switches it off.
+extern "C" int nmmo_set_autosample(nmmo_handle *h, uint64_t seed, int32_t *actions_dev_out) {
+  if (!h) return fail(NM_ERR_ARG, "null handle");
+  h->prm.sample_out = actions_dev_out;
+  h->prm.sample_seed = seed;
   return NM_OK;
 }

@@ -51,6 +51,8 @@ struct NmParams {
   unsigned long long *counters;// [8] slot-steps, alive-agent-steps, episodes, errors, obs-kernel bytes
   uint32_t *obs_meta;          // [E*P] what each obs record currently holds (incremental writer)
   int obs_full;                // 1 = rewrite every byte of every record each tick
+  int32_t *sample_out;         // optional: the obs kernel also writes uniform-random valid actions here
+  uint64_t sample_seed;
   unsigned long long *prof;    // optional [32] per-phase clock accumulators (NULL = off)
   int mode;                    // 0 step (auto-reset finished envs), 1 reset flagged envs only
   int env_base;                // global env index of env 0 (multi-GPU sharding; seeds derive from it)

@@ -73,9 +73,20 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   const int stage_bytes = nm_align16(L.m_end);
   uint8_t *s_stage_all = carve((size_t)NW * stage_bytes);
   uint16_t *s_vis_all = (uint16_t *)carve((size_t)NW * ((L.n_ent * 2 + 15) & ~15));
+  uint32_t *s_bits_all = (uint32_t *)carve((size_t)NW * 32 * 4);
+  uint32_t *s_pos = (uint32_t *)carve((size_t)R * 4);       // (row+7)<<16 | (col+7) of alive rows
+  uint8_t *s_tmpl = carve(stage_bytes);                      // agent-independent part of the masks
+  int *s_head = (int *)carve(2 * AC_N * 4);
   uint64_t *bar = (uint64_t *)carve(8);
 
   if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (tid < AC_N) {
+    const int off[AC_N] = {L.m_style, L.m_target, L.m_buy, L.m_destroy, L.m_give_item, L.m_give_target,
+                           L.m_gold_price, L.m_gold_target, L.m_move, L.m_sell_item, L.m_sell_price, L.m_use};
+    const int len[AC_N] = {3, L.n_ent + 1, L.n_mkt + 1, L.n_inv + 1, L.n_inv + 1, L.n_ent + 1, L.n_price,
+                           L.n_ent + 1, NM_DIR_N, L.n_inv + 1, L.n_price, L.n_inv + 1};
+    s_head[tid] = off[tid]; s_head[AC_N + tid] = len[tid];
+  }
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(bar, ent_bytes + st_bytes + item_bytes + map_bytes);
@@ -92,6 +103,21 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   OCtx o;
   o.p = &prm; o.c = c; o.R = R; o.S = S; o.CAP = CAP; o.P = P; o.NINV = NINV;
   o.ent = s_ent; o.status = s_status; o.item = s_item; o.map = s_map;
+  const int wrapper = c[NC_WRAPPER];
+  const bool no_give = wrapper == NW_TAKERU && c[NC_DISABLE_GIVE];
+  // one word per table row for the vision-window scan: an empty row can never match
+  for (int r = tid; r < R; r += T)
+    s_pos[r] = s_status[r] == ES_ALIVE ? (((uint32_t)(OENT(EA_ROW, r) + vis) << 16) | (uint32_t)(OENT(EA_COL, r) + vis)) : 0x7fff7fffu;
+  // mask template: entries that do not depend on the agent (Style, Sell.Price, the no-op slots,
+  // GiveGold.Price[0]); per agent it is copied and only the agent-specific entries are touched
+  for (int i = tid; i < stage_bytes; i += T) {
+    uint8_t v = 0;
+    if (i >= L.m_style && i < L.m_style + 3) v = 1;
+    if (i >= L.m_sell_price && i < L.m_sell_price + L.n_price) v = 1;
+    if (i == L.m_buy + L.n_mkt || i == L.m_destroy + L.n_inv || i == L.m_give_item + L.n_inv || i == L.m_sell_item + L.n_inv ||
+        i == L.m_use + L.n_inv || i == L.m_give_target + L.n_ent || i == L.m_gold_target + L.n_ent || i == L.m_gold_price) v = 1;
+    s_tmpl[i] = v;
+  }
 
   // ---- inventory lists (row order) and the market list (row order, first n_mkt) -------
   const int K = (CAP + T - 1) / T;          // consecutive rows per thread
@@ -150,17 +176,20 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   int8_t *m = (int8_t *)stage;
   uint16_t *s_vis = s_vis_all + (size_t)warp * (((L.n_ent * 2 + 15) & ~15) / 2);
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
-  const int wrapper = c[NC_WRAPPER];
   long long n_stored = 0;                     // 16-byte chunks stored by this warp
-  for (int p = warp; p < P; p += NW) {
+  // this warp's agents are p = warp + NW*i: fetch all their meta words with one load
+  uint32_t meta_mine = 0;
+  if (warp + NW * lane < P) meta_mine = prm.obs_meta[(size_t)env * P + warp + NW * lane];
+  for (int p = warp, it = 0; p < P; p += NW, it++) {
     const size_t a = (size_t)env * P + p;
     uint8_t *rec = prm.obs + a * L.stride;
     // The record lives in HBM across ticks, so only bytes that can differ from last tick's
     // record are stored.  meta remembers what the record currently holds: rows of Entity /
     // Inventory / Market that are non-zero, whether the Task block is in place, whether the
     // record is non-zero at all.  obs_full = 1 rewrites every byte (roofline / A-B mode).
-    const uint32_t meta = prm.obs_meta[a];
+    const uint32_t meta = it < 32 ? __shfl_sync(0xffffffffu, meta_mine, it) : prm.obs_meta[a];
     if (s_status[p] != ES_ALIVE) {           // dead or absent agents get the zero pad record
+      if (prm.sample_out && lane < AC_N) prm.sample_out[a * AC_N + lane] = 0;
       if ((meta & OM_NONZERO) || prm.obs_full) {
         for (int k = lane; k < L.stride / 16; k += 32) st16(rec + k * 16, zero4);
         n_stored += L.stride / 16;
@@ -177,18 +206,20 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     int n_vis = 0;
     for (int base = 0; base < R; base += 32) {
       int row = base + lane;
-      bool in = row < R && s_status[row] == ES_ALIVE && nm_iabs(OENT(EA_ROW, row) - r0) <= vis && nm_iabs(OENT(EA_COL, row) - c0) <= vis;
+      uint32_t pos = row < R ? s_pos[row] : 0x7fff7fffu;
+      // |r - r0| <= vis  <=>  0 <= (r + vis) - r0 <= 2*vis, same for the column
+      bool in = (uint32_t)((int)(pos >> 16) - r0) <= (uint32_t)(2 * vis) && (uint32_t)((int)(pos & 0xffffu) - c0) <= (uint32_t)(2 * vis);
       unsigned bm = __ballot_sync(0xffffffffu, in);
+      if (!bm) continue;
       if (in) { int idx = n_vis + __popc(bm & ((1u << lane) - 1)); if (idx < L.n_ent) s_vis[idx] = (uint16_t)row; }
       n_vis += __popc(bm);
     }
     n_vis = min(n_vis, L.n_ent);
     const int n_inv = min(s_invn[p], NINV);
     const uint16_t *inv = s_inv + p * NINV;
-    for (int k = lane; k < stage_bytes / 16; k += 32) ((uint4 *)stage)[k] = zero4;
+    for (int k = lane; k < stage_bytes / 16; k += 32) ((uint4 *)stage)[k] = ((const uint4 *)s_tmpl)[k];
     __syncwarp();
     // ---- ActionTargets ----
-    if (lane < 3) m[L.m_style + lane] = 1;
     {
       bool any = false;
       bool immune = OENT(EA_TIME_ALIVE, p) < c[NC_SPAWN_IMMUNITY];
@@ -197,11 +228,13 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
         bool same = OENT(EA_ROW, row) == r0 && OENT(EA_COL, row) == c0;
         bool ok = nm_linf(OENT(EA_ROW, row), OENT(EA_COL, row), r0, c0) <= c[NC_REACH] && id != my_id && !(immune && id > 0);
         m[L.m_target + i] = ok; any |= ok;
-        bool give = n_inv > 0 && same && OENT(EA_NPC_TYPE, row) == 0 && id != my_id;
-        m[L.m_give_target + i] = give; m[L.m_gold_target + i] = give;
+        if (!no_give) {     // takeru's RewardWrapper.observation zeroes these anyway (reward_wrapper.py:31-35)
+          bool give = n_inv > 0 && same && OENT(EA_NPC_TYPE, row) == 0 && id != my_id;
+          m[L.m_give_target + i] = give; m[L.m_gold_target + i] = give;
+        }
       }
       any = __any_sync(0xffffffffu, any);
-      if (lane == 0) { m[L.m_target + L.n_ent] = any ? 0 : 1; m[L.m_give_target + L.n_ent] = 1; m[L.m_gold_target + L.n_ent] = 1; }
+      if (lane == 0) m[L.m_target + L.n_ent] = any ? 0 : 1;
     }
     {
       bool full = n_inv >= NINV;
@@ -214,7 +247,6 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
       };
       bool any_ammo = false;
       if (full) { for (int j = lane; j < n_mkt; j += 32) any_ammo |= ammo_match(j); any_ammo = __any_sync(0xffffffffu, any_ammo); }
-      if (lane == 0) m[L.m_buy + L.n_mkt] = 1;
       if (!(full && !any_ammo))
         for (int j = lane; j < n_mkt; j += 32) {
           bool ok = s_mkt[j * IA_N_OBS + IA_OWNER] != my_id && s_mkt[j * IA_N_OBS + IA_LISTED_PRICE] <= my_gold;
@@ -226,25 +258,61 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
       int i = inv[lane];
       bool eq = OITM(IS_EQUIPPED, i) != 0, listed = OITM(IS_PRICE, i) != 0;
       m[L.m_destroy + lane] = !eq;
-      m[L.m_give_item + lane] = !eq && !listed;
+      if (!no_give) m[L.m_give_item + lane] = !eq && !listed;
       m[L.m_sell_item + lane] = !eq && !listed;
       m[L.m_use + lane] = !listed && OITM(IS_LEVEL, i) <= o_use_level(o, p, OITM(IS_TYPE, i));
     }
-    if (lane == 0) { m[L.m_destroy + L.n_inv] = 1; m[L.m_give_item + L.n_inv] = 1; m[L.m_sell_item + L.n_inv] = 1; m[L.m_use + L.n_inv] = 1; }
-    for (int g = lane; g < L.n_price; g += 32) { m[L.m_gold_price + g] = (g == 0 || g < my_gold) ? 1 : 0; m[L.m_sell_price + g] = 1; }
+    if (!no_give) for (int g = 1 + lane; g < min(my_gold, L.n_price); g += 32) m[L.m_gold_price + g] = 1;
     if (lane < 5) m[L.m_move + lane] = !nm_impassible(s_map[(r0 + c_dir_dr[lane]) * S + c0 + c_dir_dc[lane]]);
     __syncwarp();
     // RewardWrapper.observation hooks
-    if (wrapper == NW_TAKERU && c[NC_DISABLE_GIVE]) {
-      for (int i = lane; i < L.n_inv; i += 32) m[L.m_give_item + i] = 0;
-      for (int i = lane; i < L.n_ent; i += 32) { m[L.m_give_target + i] = 0; m[L.m_gold_target + i] = 0; }
-      for (int g = 1 + lane; g < L.n_price; g += 32) m[L.m_gold_price + g] = 0;
-    } else if (wrapper == NW_START_KIT) {
+    // (takeru: Give.InventoryItem[:-1], Give.Target[:-1], GiveGold.Target[:-1], GiveGold.Price[1:]
+    //  stay at the template's zeros -- they were never filled in, see no_give above)
+    if (wrapper == NW_START_KIT) {
       if (lane == 0) m[L.m_sell_price + prm.stats[a * ST_N + ST_PREV_PRICE]] = 0;
     }
     __syncwarp();
     for (int k = lane; k < stage_bytes / 16; k += 32) st16(rec + k * 16, ((const uint4 *)stage)[k]);
     n_stored += stage_bytes / 16 + 1;
+    // ---- built-in random policy (optional): uniform over the valid entries of every head ----
+    // The 946 mask bytes become 30 ballot words; lanes 0..11 then each resolve one head with
+    // popc / __fns on those words.  Same draws as nmmo_sample_kernel.
+    if (prm.sample_out) {
+      uint32_t *bits = s_bits_all + warp * 32;
+      const int n_words = (L.m_end + 31) >> 5;
+      for (int wd = 0; wd < n_words; wd++) {
+        int i = wd * 32 + lane;
+        uint32_t b = __ballot_sync(0xffffffffu, i < L.m_end && m[i] != 0);
+        if (lane == wd) bits[wd] = b;
+      }
+      __syncwarp();
+      if (lane < AC_N) {
+        const uint64_t base64 = nm_hash64(prm.sample_seed + (uint64_t)(prm.env_base + env), (uint32_t)tick, RS_ACTION, (uint32_t)p, 0);
+        const int o0 = s_head[lane], o1 = o0 + s_head[AC_N + lane];
+        const int w0 = o0 >> 5, w1 = (o1 - 1) >> 5;
+        auto word_at = [&](int w) -> uint32_t {
+          uint32_t x = bits[w];
+          if (w == w0) x &= 0xffffffffu << (o0 & 31);
+          if (w == w1 && (o1 & 31)) x &= (1u << (o1 & 31)) - 1u;
+          return x;
+        };
+        int total = 0;
+        for (int w = w0; w <= w1; w++) if (bits[w]) total += __popc(word_at(w));
+        int pick = 0;
+        if (total > 0) {
+          int jj = nm_bounded(nm_action_draw(base64, lane), total);
+          for (int w = w0; w <= w1; w++) {
+            if (!bits[w]) continue;
+            uint32_t x = word_at(w);
+            int cnt = __popc(x);
+            if (jj < cnt) { pick = w * 32 + (int)__fns(x, 0, jj + 1) - o0; break; }
+            jj -= cnt;
+          }
+        }
+        prm.sample_out[a * AC_N + lane] = pick;
+      }
+      __syncwarp();
+    }
     // ---- AgentId, CurrentTick ----
     if (lane == 0) st16(rec + L.o_ids, make_uint4(pack2(my_id, tick), 0, 0, 0));
     // ---- Entity rows ----

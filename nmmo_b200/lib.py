@@ -20,7 +20,7 @@ EXPORTS = [
     "nmmo_create", "nmmo_destroy", "nmmo_reset", "nmmo_step", "nmmo_step_host", "nmmo_sample_actions",
     "nmmo_obs_ptr", "nmmo_reward_ptr", "nmmo_terminated_ptr", "nmmo_truncated_ptr", "nmmo_mask_ptr",
     "nmmo_info_ptr", "nmmo_info_valid_ptr", "nmmo_episode_done_ptr", "nmmo_obs_stride", "nmmo_num_envs",
-    "nmmo_num_agents", "nmmo_inject_rng", "nmmo_snapshot", "nmmo_stats", "nmmo_timing", "nmmo_timing_read", "nmmo_profile", "nmmo_set_obs_full",
+    "nmmo_num_agents", "nmmo_inject_rng", "nmmo_snapshot", "nmmo_stats", "nmmo_timing", "nmmo_timing_read", "nmmo_profile", "nmmo_set_obs_full", "nmmo_set_autosample",
     "nmmo_last_error",
 ]
 
@@ -75,6 +75,8 @@ def load(build_if_missing: bool = True):
     L.nmmo_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.nmmo_set_obs_full.restype = C.c_int
     L.nmmo_set_obs_full.argtypes = [vp, C.c_int]
+    L.nmmo_set_autosample.restype = C.c_int
+    L.nmmo_set_autosample.argtypes = [vp, C.c_uint64, vp]
     L.nmmo_profile.restype = C.c_int
     L.nmmo_profile.argtypes = [vp, C.c_int, vp]
     L.nmmo_last_error.restype = C.c_char_p
@@ -228,3 +230,10 @@ class Simulator:
 
     def set_obs_full(self, full: bool):
         self._check(self.L.nmmo_set_obs_full(self.h, int(full)))
+
+    def set_autosample(self, seed, out=None, enable: bool = True):
+        """Built-in random policy: every observation pass also writes uniform-random valid actions
+        into `out` (default self.actions)."""
+        a = self.actions if out is None else out
+        ptr = C.c_void_p(a.data_ptr()) if enable else None
+        self._check(self.L.nmmo_set_autosample(self.h, C.c_uint64(int(seed)), ptr))

@@ -47,3 +47,25 @@ def test_default_config_full_size():
     sim, oracles = _make(world, 3)
     run_parity(sim, oracles, seeds=np.array([1, 2, 3]), ticks=160, check_state_every=32)
     sim.close()
+
+
+def test_autosample_matches_sampler_kernel():
+    import torch
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=80, NC_RES_DEPLETION=1)
+    sim, oracles = _make(world, 3)
+    auto = torch.zeros_like(sim.actions)
+    sim.set_autosample(77, auto)
+    sim.reset(np.arange(3) + 9)
+    for o, s in zip(oracles, np.arange(3) + 9):
+        o.reset(int(s))
+    for t in range(60):
+        sim.sample_actions(77)
+        torch.cuda.synchronize()
+        a = sim.actions.cpu().numpy()
+        assert np.array_equal(a, auto.cpu().numpy()), f"tick {t}: fused sampler differs from the sampler kernel"
+        for e, o in enumerate(oracles):
+            assert np.array_equal(a[e], o.sample_actions(77 + e)), f"tick {t} env {e}: oracle sampler differs"
+            o.step(a[e])
+        sim.step()
+    sim.set_autosample(0, enable=False)
+    sim.close()
