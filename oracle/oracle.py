@@ -52,6 +52,12 @@ def lib():
             getattr(L, name).restype = C.c_int
             getattr(L, name).argtypes = [vp]
         L.oracle_snapshot.argtypes = [vp, vp, vp, vp]
+        L.oracle_env_rewards.restype = C.POINTER(C.c_double)
+        L.oracle_env_rewards.argtypes = [vp]
+        L.oracle_log_count.restype = C.c_int
+        L.oracle_log_count.argtypes = [vp, C.c_int]
+        L.oracle_log_rows.argtypes = [vp, C.c_int, vp]
+        L.oracle_task_state.argtypes = [vp, vp, vp, vp, vp]
         L.oracle_step_many.argtypes = [vp, C.c_int, vp]
         L.oracle_sample_many.argtypes = [vp, C.c_int, C.c_uint64, vp]
         _lib = L
@@ -155,6 +161,24 @@ class OracleEnv:
     @property
     def map_id(self):
         return lib().oracle_map_id(self.h)
+
+    @property
+    def env_rewards(self):
+        return self._arr("oracle_env_rewards", (self.P,), np.float64)
+
+    def log_rows(self, p):
+        """Episode event log of player row p, in the reference's 9-column layout."""
+        n = lib().oracle_log_count(self.h, int(p))
+        out = np.zeros((n, 9), np.int32)
+        if n:
+            lib().oracle_log_rows(self.h, int(p), _ptr(out))
+        return out
+
+    def task_state(self):
+        tid = np.zeros(self.P, np.int32); comp = np.zeros(self.P, np.int32); sig = np.zeros(self.P, np.int32)
+        mp = np.zeros(self.P, np.float64)
+        lib().oracle_task_state(self.h, _ptr(tid), _ptr(comp), _ptr(sig), _ptr(mp))
+        return tid, comp, sig, mp
 
     def snapshot(self):
         ent = np.zeros((self.P + self.N, self.S["EA_N"]), np.int16)
