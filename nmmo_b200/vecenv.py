@@ -1,0 +1,180 @@
+"""Vector-env backend with the pufferlib vectorisation contract, backed by the CUDA simulator.
+
+This is the reference's own plugin seam: ``clean_pufferl.create`` builds
+``vectorization(env_creator, env_kwargs, num_envs, envs_per_worker, envs_per_batch, env_pool,
+mask_agents)`` and then only uses ``async_reset / recv / send / close`` plus a few attributes
+(/root/reference/reinforcement_learning/clean_pufferl.py:106-118,151,158,175,293,357,563;
+selected in /root/reference/train.py:117-125).  ``B200VecEnv`` has that shape, reads the same
+``env_kwargs`` (``{"env": Namespace, "reward_wrapper": Namespace}``, train_helper.py:55) and returns
+CUDA tensors, so the rollout loop can skip its ``.cpu()`` / ``.to(device)`` copies
+(clean_pufferl.py:302-345).  It replaces, in one piece, pufferlib's Serial/Multiprocessing pool,
+``PettingZooPufferEnv``, the RewardWrapper/BaseStatWrapper stack and ``nmmo.Env``.
+"""
+from __future__ import annotations
+
+from argparse import Namespace
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from .config import SPEC, make_config, default_env_args, default_wrapper_args
+from .emulation import UnflattenContext
+from .lib import Simulator
+from .mapgen import generate_maps
+from .tasks import default_curriculum, make_task_table
+
+INFO_NAMES = {
+    "IN_LENGTH": "length", "IN_RETURN": "return",
+    "IN_COD_ATTACKED": "stats/cod/attacked", "IN_COD_STARVED": "stats/cod/starved", "IN_COD_DEHYDRATED": "stats/cod/dehydrated",
+    "IN_TASK_COMPLETED": "stats/task/completed", "IN_TASK_2_REWARD_SIGNAL": "stats/task/pcnt_2_reward_signal",
+    "IN_TASK_0P2_MAX_PROGRESS": "stats/task/pcnt_0p2_max_progress",
+    "IN_MAX_COMBAT_LEVEL": "stats/achieved/max_combat_level", "IN_MAX_HARVEST_AMMO": "stats/achieved/max_harvest_skill_ammo",
+    "IN_MAX_HARVEST_CONSUM": "stats/achieved/max_harvest_skill_consum",
+    "IN_MAX_PROGRESS_TO_CENTER": "stats/achieved/max_progress_to_center", "IN_EARNED_GOLD": "stats/achieved/earned_gold",
+    "IN_MAX_DAMAGE": "stats/achieved/max_damage", "IN_MAXLVL_ARMOR": "stats/achieved/max_armor_level",
+    "IN_MAXLVL_WEAPON": "stats/achieved/max_weapon_level", "IN_MAXLVL_TOOL": "stats/achieved/max_tool_level",
+    "IN_MAXLVL_AMMO": "stats/achieved/max_ammo_level", "IN_MAXLVL_CONSUMABLE": "stats/achieved/max_consumable_level",
+    "IN_AGENT_KILLS": "stats/achieved/agent_kill_count", "IN_NPC_KILLS": "stats/achieved/npc_kill_count",
+    "IN_UNIQUE_EVENTS": "stats/achieved/unique_events",
+    "IN_EV_EAT_FOOD": "stats/event/eat_food", "IN_EV_DRINK_WATER": "stats/event/drink_water",
+    "IN_EV_SCORE_HIT": "stats/event/score_hit", "IN_EV_PLAYER_KILL": "stats/event/player_kill",
+    "IN_EV_CONSUME_ITEM": "stats/event/consume_item", "IN_EV_HARVEST_ITEM": "stats/event/harvest_item",
+    "IN_EV_LIST_ITEM": "stats/event/list_item", "IN_EV_BUY_ITEM": "stats/event/buy_item",
+    "IN_EQUIP_ARMOR": "stats/event/equip_armor", "IN_EQUIP_WEAPON": "stats/event/equip_weapon",
+    "IN_EQUIP_TOOL": "stats/event/equip_tool", "IN_EQUIP_AMMO": "stats/event/equip_ammo",
+    "IN_HARVEST_WEAPON": "stats/event/harvest_weapon",
+}
+
+
+def info_record_to_dict(row: np.ndarray, episode_done: bool = False, stat_prefix: Optional[str] = None) -> Dict:
+    """nm_info float record -> the dict BaseStatWrapper emits (stat_wrapper.py:132-185).  Keys whose
+    record entry is NaN are absent, exactly like the achieved/max_*_level keys of the reference."""
+    info: Dict = {"stats": {}}
+    for col, key in INFO_NAMES.items():
+        v = float(row[SPEC[col]])
+        if v != v:
+            continue
+        if key.startswith("stats/"):
+            info["stats"][key[len("stats/"):]] = v
+        else:
+            info[key] = v
+    info["length"] = int(info["length"])
+    tid = int(row[SPEC["IN_TASK_ID"]])
+    info["curriculum"] = {f"task_{tid}": (float(row[SPEC["IN_CURR_MAX_PROGRESS"]]), int(row[SPEC["IN_CURR_REWARD_SIGNALS"]]))}
+    if episode_done:
+        info["episode_done"] = True
+    if stat_prefix:
+        info = {stat_prefix: info}
+    return info
+
+
+class _Space:
+    def __init__(self, shape, dtype, nvec=None):
+        self.shape, self.dtype, self.nvec = tuple(shape), dtype, nvec
+
+
+class DriverEnv:
+    """What clean_pufferl / the policies read from ``pool.driver_env`` (clean_pufferl.py:151,
+    agent_zoo/takeru/policy.py:27)."""
+
+    def __init__(self, cfg, ctx: UnflattenContext, action_dims):
+        self.unflatten_context = ctx
+        self.obs_sz = ctx.obs_sz
+        self.observation_space = _Space((ctx.obs_sz,), np.uint8)
+        self.action_space = _Space((len(action_dims),), np.int32, nvec=np.asarray(action_dims))
+        self.single_observation_space = self.observation_space
+        self.single_action_space = self.action_space
+        self.possible_agents = list(range(1, int(cfg[SPEC["NC_N_PLAYERS"]]) + 1))
+        self.config = cfg
+
+
+class B200VecEnv:
+    def __init__(self, env_creator=None, env_args=None, env_kwargs: Optional[Dict] = None, num_envs: int = 1,
+                 envs_per_worker: int = 1, envs_per_batch: Optional[int] = None, env_pool: bool = False,
+                 mask_agents: bool = True, agent: str = "takeru", device: int = 0, env_base: int = 0,
+                 maps: Optional[np.ndarray] = None, task_rows=None, map_seed: int = 2023, collect_infos: bool = True):
+        # env_creator / env_args / envs_per_worker / env_pool are accepted for signature
+        # compatibility; all envs of this backend step in lock-step on one GPU
+        env_kwargs = env_kwargs or {}
+        env_ns = env_kwargs.get("env") or default_env_args(resilient_population=0 if agent == "takeru" else 0.2)
+        wrap_ns = env_kwargs.get("reward_wrapper") or default_wrapper_args(agent)
+        if isinstance(env_ns, dict):
+            env_ns = Namespace(**env_ns)
+        if isinstance(wrap_ns, dict):
+            wrap_ns = Namespace(**wrap_ns)
+        self.cfg, self.fcfg = make_config(env_ns, wrap_ns, agent)
+        n_maps = min(int(getattr(env_ns, "num_maps", 64)), 256) if maps is None else len(maps)
+        self.maps = generate_maps(self.cfg, map_seed, n_maps) if maps is None else maps
+        rows = task_rows if task_rows is not None else default_curriculum()
+        self.task_table, self.task_embed = make_task_table(rows, int(self.cfg[SPEC["NC_TASK_DIM"]]), seed=3)
+        self.num_envs = int(num_envs)
+        self.envs_per_batch = self.num_envs if envs_per_batch is None else int(envs_per_batch)
+        if self.envs_per_batch != self.num_envs:
+            raise ValueError("B200VecEnv steps every env in lock-step: envs_per_batch must equal num_envs")
+        self.sim = Simulator(self.cfg, self.fcfg, self.num_envs, self.maps, self.task_table, self.task_embed,
+                             device=device, env_base=env_base)
+        self.agents_per_env = self.sim.P
+        self.stat_prefix = getattr(wrap_ns, "stat_prefix", None)
+        self.collect_infos = collect_infos
+        ctx = UnflattenContext(self.cfg)
+        self.driver_env = DriverEnv(self.cfg, ctx, ctx.layout.action_dims)
+        self.single_observation_space = self.driver_env.observation_space
+        self.single_action_space = self.driver_env.action_space
+        self.mask_agents = mask_agents
+        self.multi_envs = None           # replay path (train_helper.py:133) is out of scope
+        import torch
+        self._torch = torch
+        self.env_id = torch.arange(self.num_envs * self.agents_per_env, device=self.sim.obs.device)
+        self._pending = False
+
+    # ---- pufferlib pool contract -------------------------------------------------------
+    def async_reset(self, seed: int = 0):
+        seeds = np.arange(self.num_envs, dtype=np.uint64) + np.uint64(int(seed) + self.sim_env_base())
+        self.sim.reset(seeds)
+        self._pending = True
+
+    def sim_env_base(self) -> int:
+        return 0
+
+    def recv(self):
+        """-> (obs uint8 [B, obs_sz], reward f32 [B], terminated u8 [B], truncated u8 [B], infos,
+        env_id [B], mask u8 [B]) -- all CUDA tensors except `infos` (list of dicts)."""
+        s = self.sim
+        infos: List[Dict] = []
+        if self.collect_infos:
+            valid = s.info_valid.nonzero().flatten()
+            if valid.numel():
+                rows = s.info[valid].cpu().numpy()
+                done = s.episode_done.cpu().numpy()
+                idx = valid.cpu().numpy()
+                last = {}
+                for k, a in enumerate(idx):
+                    last[a // self.agents_per_env] = k
+                for k, a in enumerate(idx):
+                    e = int(a) // self.agents_per_env
+                    infos.append(info_record_to_dict(rows[k], episode_done=bool(done[e]) and last[e] == k,
+                                                     stat_prefix=self.stat_prefix))
+        self._pending = False
+        return s.obs, s.rewards, s.terminated, s.truncated, infos, self.env_id, s.mask
+
+    def send(self, actions):
+        t = self._torch
+        a = actions if t.is_tensor(actions) else t.as_tensor(np.asarray(actions))
+        a = a.to(device=self.sim.obs.device, dtype=t.int32).reshape(self.num_envs, self.agents_per_env, 12).contiguous()
+        self.sim.step(a)
+        self._pending = True
+
+    def close(self):
+        self.sim.close()
+
+    # ---- extras --------------------------------------------------------------------------
+    def stats(self, clear: bool = False) -> Dict[str, float]:
+        """Means of the finished-agent infos since the last clear (clean_pufferl.py:381-390)."""
+        sums, counts, counters = self.sim.stats(clear)
+        out = {}
+        for col, key in INFO_NAMES.items():
+            n = counts[SPEC[col]]
+            if n > 0:
+                out[key] = sums[SPEC[col]] / n
+        out["agent_steps"] = float(counters[1]); out["slot_steps"] = float(counters[0]); out["episodes"] = float(counters[2])
+        return out

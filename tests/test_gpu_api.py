@@ -1,0 +1,228 @@
+"""GPU: the boundary (C ABI calls, VecEnv contract, per-env view, sharding, injection) and
+size-independent properties at the full BASELINE.json size."""
+import numpy as np
+import pytest
+
+from nmmo_b200.config import SPEC, ObsLayout
+from util import SMALL, build_world, run_parity
+
+pytestmark = pytest.mark.gpu
+S = SPEC
+
+
+def _sim(world, E, **kw):
+    from nmmo_b200.lib import Simulator
+    cfg, fcfg, maps, tab, emb = world
+    return Simulator(cfg, fcfg, E, maps, tab, emb, **kw)
+
+
+def _oracles(world, E):
+    from oracle.oracle import OracleEnv
+    return [OracleEnv(*world) for _ in range(E)]
+
+
+def test_injected_rng_parity():
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=150, NC_RES_DEPLETION=1, NC_SPAWN_IMMUNITY=2)
+    cfg = world[0]
+    sim, oracles = _sim(world, 3), _oracles(world, 3)
+    rng = np.random.default_rng(0)
+    R = int(cfg[S["NC_N_PLAYERS"]] + cfg[S["NC_N_NPCS"]])
+    Sz = int(cfg[S["NC_MAP_SIZE"]])
+    for e, o in enumerate(oracles):
+        keys, vals = [], []
+        for t in range(0, 120):
+            for row in rng.choice(np.arange(int(cfg[S["NC_N_PLAYERS"]]), R), 6, replace=False):   # NPC wander directions
+                keys.append((t << 36) | (S["RS_NPC_DECIDE"] << 32) | (int(row) << 8)); vals.append(int(rng.integers(0, 2 ** 32)))
+            for i in rng.choice(Sz * Sz, 40, replace=False):                                       # tile respawn draws
+                keys.append((t << 36) | (S["RS_RESPAWN"] << 32) | (int(i) << 8)); vals.append(int(rng.integers(0, 2 ** 28)))
+            for att in range(25):                                                                  # NPC spawn draws
+                for k in range(6):
+                    keys.append((t << 36) | (S["RS_NPC_SPAWN"] << 32) | (att << 8) | k); vals.append(int(rng.integers(0, 2 ** 32)))
+        for i in range(1, int(cfg[S["NC_N_PLAYERS"]])):                                            # reset: spawn permutation
+            keys.append((0 << 36) | (S["RS_SPAWN_PERM"] << 32) | (i << 8)); vals.append(int(rng.integers(0, 2 ** 32)))
+        keys = np.array(keys, np.uint64); vals = np.array(vals, np.uint32)
+        o.inject_rng(keys, vals)
+        sim.inject_rng(e, keys, vals)
+    run_parity(sim, oracles, seeds=np.arange(3) + 50, ticks=130)
+    sim.close()
+
+
+def test_explicit_maps_and_tasks():
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=90, NC_RES_DEPLETION=1)
+    cfg, _, maps, tab, _ = world
+    P = int(cfg[S["NC_N_PLAYERS"]])
+    sim, oracles = _sim(world, 3), _oracles(world, 3)
+    map_ids = np.array([3, 0, 2], np.int32)
+    # give every agent of env 0 one task of each predicate family in turn
+    task_ids = np.stack([(np.arange(P) * 7 + 11 * e) % len(tab) for e in range(3)]).astype(np.int32)
+    run_parity(sim, oracles, seeds=np.array([5, 6, 7]), ticks=85, map_ids=map_ids, task_ids=task_ids)
+    assert [o.map_id for o in oracles] == [3, 0, 2]
+    sim.close()
+
+
+def test_every_predicate_family_progresses():
+    # all agents of an env share one task; long-lived agents so event-driven predicates move
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=260, NC_RES_DEPLETION=1, NC_SPAWN_IMMUNITY=2, NC_WEAPON_DROP_THR=1 << 30)
+    cfg, _, _, tab, _ = world
+    P = int(cfg[S["NC_N_PLAYERS"]])
+    preds = sorted(set(tab[:, 0].tolist()))
+    pick = [int(np.flatnonzero(tab[:, 0] == p)[0]) for p in preds]
+    E = len(pick)
+    sim, oracles = _sim(world, E), _oracles(world, E)
+    task_ids = np.repeat(np.array(pick, np.int32)[:, None], P, axis=1)
+    run_parity(sim, oracles, seeds=np.arange(E) + 300, ticks=240, task_ids=task_ids, check_state_every=0)
+    sim.close()
+
+
+def test_env_sharding_invariance():
+    """Global env g gives the same trajectory whichever handle (env_base) hosts it."""
+    import torch
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=60)
+    whole = _sim(world, 4, env_base=0)
+    part = _sim(world, 2, env_base=2)
+    from nmmo_b200.dist import global_seeds
+    whole.reset(global_seeds(9, 0, 4)); part.reset(global_seeds(9, 2, 2))
+    P = whole.P
+    for t in range(70):
+        whole.sample_actions(9); part.sample_actions(9)
+        torch.cuda.synchronize()
+        assert torch.equal(whole.actions[2:], part.actions)
+        assert torch.equal(whole.obs[2 * P:], part.obs) and torch.equal(whole.rewards[2 * P:], part.rewards)
+        whole.step(); part.step()
+    whole.close(); part.close()
+
+
+def test_step_host_equals_device_step():
+    import torch
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=60)
+    a, b = _sim(world, 2), _sim(world, 2)
+    a.reset([1, 2]); b.reset([1, 2])
+    for t in range(40):
+        a.sample_actions(4)
+        torch.cuda.synchronize()
+        acts = a.actions.cpu().numpy()
+        a.step()
+        rew, term, trunc, mask, obs = b.step_host(acts, want_obs=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(rew, a.rewards.cpu().numpy()) and np.array_equal(term, a.terminated.cpu().numpy())
+        assert np.array_equal(trunc, a.truncated.cpu().numpy()) and np.array_equal(mask, a.mask.cpu().numpy())
+        assert np.array_equal(obs, a.obs.cpu().numpy())
+    a.close(); b.close()
+
+
+def test_dense_and_incremental_writers_agree():
+    import torch
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=70, NC_RES_DEPLETION=1)
+    a, b = _sim(world, 3), _sim(world, 3)
+    b.set_obs_full(True)
+    a.reset([7, 8, 9]); b.reset([7, 8, 9])
+    for t in range(90):                                     # crosses an episode boundary (auto-reset)
+        a.sample_actions(2); b.sample_actions(2)
+        torch.cuda.synchronize()
+        assert torch.equal(a.obs, b.obs), f"tick {t}"
+        a.step(); b.step()
+    a.close(); b.close()
+
+
+def test_vecenv_contract():
+    import torch
+    from argparse import Namespace
+    from nmmo_b200.emulation import unpack_batched_obs
+    from nmmo_b200.vecenv import B200VecEnv
+    env_ns = Namespace(num_agents=16, num_npcs=32, max_episode_length=40, maps_path="maps/", map_size=32, num_maps=4,
+                       map_force_generation=False, death_fog_tick=None, task_size=64, spawn_immunity=20,
+                       resilient_population=0, curriculum_file_path=None)
+    wrap_ns = Namespace(eval_mode=False, early_stop_agent_num=0, use_custom_reward=True, explore_bonus_weight=0.01,
+                        clip_unique_event=3, disable_give=True)
+    pool = B200VecEnv(env_kwargs={"env": env_ns, "reward_wrapper": wrap_ns}, num_envs=3, envs_per_worker=1, envs_per_batch=3,
+                      env_pool=False, mask_agents=True, agent="takeru")
+    assert pool.agents_per_env == 16 and pool.single_action_space.shape == (12,)
+    assert pool.single_observation_space.shape == (pool.driver_env.obs_sz,)
+    pool.async_reset(1)
+    returns = []
+    for t in range(120):
+        o, r, d, tr, infos, env_id, mask = pool.recv()
+        B = 3 * 16
+        assert o.is_cuda and o.shape == (B, pool.driver_env.obs_sz) and r.shape == (B,) and mask.shape == (B,)
+        assert len(env_id) == B
+        nested = unpack_batched_obs(o, pool.driver_env.unflatten_context)
+        assert nested["Tile"].shape == (B, 225, 3) and nested["Entity"].shape == (B, 100, 31)
+        for i in infos:
+            assert "return" in i and "length" in i and "stats" in i and "curriculum" in i
+            returns.append(i["return"])
+        pool.sim.sample_actions(3)
+        pool.send(pool.sim.actions.reshape(B, 12))
+    assert len(returns) >= 3 * 16                           # at least one full episode per env (horizon 40)
+    st = pool.stats()
+    assert st["episodes"] >= 3 and "stats/achieved/unique_events" in st
+    pool.close()
+
+
+def test_env_view_matches_oracle():
+    from nmmo_b200.env import EnvView, ACTION_KEYS
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=50)
+    sim = _sim(world, 1)
+    o = _oracles(world, 1)[0]
+    env = EnvView(sim)
+    obs, info = env.reset(seed=13)
+    o.reset(13)
+    assert env.agents == env.possible_agents
+    L = ObsLayout(world[0])
+    for t in range(45):
+        a = o.sample_actions(6)
+        acts = {ag: {} for ag in env.agents}
+        for ag in env.agents:
+            for k, (x, y) in enumerate(ACTION_KEYS):
+                acts[ag].setdefault(x, {})[y] = int(a[ag - 1, k])
+        obs, rew, term, trunc, infos = env.step(acts)
+        o.step(a)
+        assert sorted(obs) == [p + 1 for p in np.flatnonzero(o.mask)]
+        for ag in obs:
+            off, n = L.masks["Move.Direction"]
+            assert np.array_equal(obs[ag]["ActionTargets"]["Move"]["Direction"], o.obs[ag - 1][off:off + n].view(np.int8))
+            assert np.float32(rew[ag]) == o.rewards[ag - 1] and term[ag] == bool(o.terminated[ag - 1])
+        if o.episode_done:
+            assert env.agents == [] and any(i.get("episode_done") for i in infos.values())
+            break
+    sim.close()
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[1] size: 4096 envs x 128 agents.  Size-independent checks: bit-exact
+    replay determinism, a sampled subset of envs bit-exact against the oracle, conservation of the
+    per-tick accounting, no event-ring overflow."""
+    import torch
+    world = build_world()
+    E = 4096
+    sim = _sim(world, E)
+    L = ObsLayout(world[0])
+    seeds = np.arange(E, dtype=np.uint64) + 1
+    sample = [0, 1, 777, 2048, 4095]
+    oracles = _oracles(world, len(sample))
+
+    def rollout(check):
+        sim.reset(seeds)
+        if check:
+            for o, e in zip(oracles, sample):
+                o.reset(int(seeds[e]))
+        digest = []
+        for t in range(48):
+            sim.sample_actions(5)
+            if check:
+                torch.cuda.synchronize()
+                acts = sim.actions.cpu().numpy()
+                for o, e in zip(oracles, sample):
+                    assert np.array_equal(sim.obs[e * 128:(e + 1) * 128].cpu().numpy(), o.obs), f"tick {t} env {e}"
+                    assert np.array_equal(acts[e], o.sample_actions(5 + e))
+                    o.step(acts[e])
+            sim.step()
+            digest.append((int(sim.mask.sum()), float(sim.rewards.double().sum()), int(sim.obs[:, :L.m_end].sum())))
+        return digest
+
+    d1 = rollout(True)
+    sums, counts, counters = sim.stats(clear=True)
+    assert counters[3] == 0, "event ring overflowed"
+    assert counters[0] == 48 * E * 128 and counters[1] == sum(d[0] for d in d1)
+    d2 = rollout(False)
+    assert d1 == d2
+    sim.close()
