@@ -114,23 +114,23 @@ enum nm_ent {
   EA_PROSPECTING_LEVEL, EA_PROSPECTING_EXP, EA_CARVING_LEVEL, EA_CARVING_EXP,
   EA_ALCHEMY_LEVEL, EA_ALCHEMY_EXP,
   EA_N_OBS = 31,
-  /* hidden columns (engine state that is not observed) */
+  /* hidden columns (engine state that is not observed).  A row is either a player or an NPC,
+   * so the NPC-only columns share storage with player-only columns. */
   EA_H0 = 31,
   EA_EXPLORATION = 31,   /* History.exploration (players) */
   EA_SPAWN_ROW, EA_SPAWN_COL,
   EA_HEALTH_RESTORE,     /* Resources.health_restore  start_kit/reward_wrapper.py:69 */
   EA_RESILIENT,
-  EA_DMG_INFLICTED, EA_DMG_RECEIVED,
-  EA_EQ_HAT, EA_EQ_TOP, EA_EQ_BOTTOM, EA_EQ_HELD, EA_EQ_AMMO,  /* item row + 1, 0 = empty */
-  /* NPC-only hidden state (reuses none of the above) */
-  EA_NPC_STYLE,          /* 0 melee 1 range 2 mage */
-  EA_NPC_TARGET,         /* entity id of hunt target, 0 none */
-  EA_NPC_DANGER,         /* spawn distance-from-border d */
-  EA_NPC_OFFENSE, EA_NPC_DEFENSE,
-  EA_NPC_DROP_ARMOR, EA_NPC_DROP_TOOL,   /* item type ids */
+  EA_EQ_HAT, EA_EQ_TOP, EA_EQ_BOTTOM, EA_EQ_HELD, EA_EQ_AMMO,  /* item row + 1, 0 = empty (players) */
+  EA_DMG_INFLICTED, EA_DMG_RECEIVED,                           /* History (players and NPCs) */
   EA_STATUS,             /* 0 empty row, 1 alive, 2 culled this tick (kept for episode stats) */
-  EA_PAD,
-  EA_N = 52
+  EA_N = 44,
+  /* NPC-only hidden state, aliased onto the player-only columns above */
+  EA_NPC_STYLE = EA_EXPLORATION,        /* 0 melee 1 range 2 mage */
+  EA_NPC_TARGET = EA_SPAWN_ROW,         /* entity id of hunt target, 0 none */
+  EA_NPC_DANGER = EA_SPAWN_COL,         /* spawn distance-from-border d */
+  EA_NPC_OFFENSE = EA_HEALTH_RESTORE, EA_NPC_DEFENSE = EA_RESILIENT,
+  EA_NPC_DROP_ARMOR = EA_EQ_HAT, EA_NPC_DROP_TOOL = EA_EQ_TOP   /* item type ids */
 };
 enum nm_status { ES_EMPTY = 0, ES_ALIVE = 1, ES_DEAD_THIS_TICK = 2 };
 

@@ -40,6 +40,8 @@ struct Ctx {
   int *task;                  // [P][4] pred, p0, p1, spare: the agent's task row for event folding
   int *acc;                   // [P][2] event-driven predicate accumulators
   int8_t *slow;               // [P] result of the window-scan predicates (-1 = not requested)
+  const uint32_t *plist;      // alive players at the start of the step: row<<16 | r<<8 | c, ascending row
+  int n_plist;
   const uint32_t *predraw;    // NPC-spawn draws computed in parallel: [attempt][8]
   uint64_t seed;
   int tick;
@@ -281,9 +283,10 @@ __device__ int closest_target(const Ctx &ctx, int row, int rng) {
     if (!any) return 0;
   }
   int best = 0x7fffffff, best_id = 0;
-  for (int p = 0; p < ctx.P; p++) {
-    if (!ent_alive(ctx, p)) continue;
-    int dr = ENT(EA_ROW, p) - sr, dc = ENT(EA_COL, p) - sc;
+  for (int k = 0; k < ctx.n_plist; k++) {
+    uint32_t x = ctx.plist[k];
+    int p = (int)(x >> 16);
+    int dr = (int)((x >> 8) & 255u) - sr, dc = (int)(x & 255u) - sc;
     int d = max(nm_iabs(dr), nm_iabs(dc));
     if (d > rng) continue;
     int rk = 0x7fffffff;
@@ -976,7 +979,8 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   uint32_t *s_att = s_scratch;
   int *s_first = (int *)(s_scratch + R);
   ctx.slow = (int8_t *)carve((size_t)P);
-  ctx.sc = (int *)carve(16 * 4);
+  uint32_t *s_plist = (uint32_t *)carve((size_t)P * 4);
+  ctx.sc = (int *)carve(32 * 4);
   uint64_t *bar = (uint64_t *)carve(8);
   ctx.seed = prm.seed[env];
   ctx.tick = gsc[SC_TICK];
@@ -1022,7 +1026,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     ctx.task[tid * 4] = my_t[0]; ctx.task[tid * 4 + 1] = my_t[1]; ctx.task[tid * 4 + 2] = my_t[2]; ctx.task[tid * 4 + 3] = 0;
     ctx.acc[tid * 2] = my_acc0; ctx.acc[tid * 2 + 1] = my_acc1;
   }
-  if (tid < 16) ctx.sc[tid] = 0;
+  if (tid < 32) ctx.sc[tid] = 0;
   if (tid == 0) { ctx.sc[2] = gsc[SC_N_DANGER]; ctx.sc[3] = gsc[SC_NEXT_NPC_ID]; }
   while (!mbar_try_wait(bar, 0)) {}
   __syncthreads();
@@ -1037,6 +1041,17 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     }
   __syncthreads();
   for (int r = tid; r < R; r += T) if (ENT(EA_STATUS, r) == ES_ALIVE) occ_set(ctx, ENT(EA_ROW, r), ENT(EA_COL, r));
+  if (warp == 0) {       // alive players, ascending id, with packed positions (NPC target scans)
+    int n = 0;
+    for (int base = 0; base < P; base += 32) {
+      int p = base + lane;
+      bool live = p < P && ENT(EA_STATUS, p) == ES_ALIVE;
+      unsigned bm = __ballot_sync(0xffffffffu, live);
+      if (live) s_plist[n + __popc(bm & ((1u << lane) - 1))] = ((uint32_t)p << 16) | ((uint32_t)ENT(EA_ROW, p) << 8) | (uint32_t)ENT(EA_COL, p);
+      n += __popc(bm);
+    }
+    if (lane == 0) ctx.sc[16] = n;
+  }
   for (int i = tid; i < CAP; i += T)
     if (ITM(IS_TYPE, i) != 0) {
       atomicOr(&ctx.used[i >> 5], 1u << (i & 31));
@@ -1097,6 +1112,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
 
   PHASE();
   // ---- phase 1: npcs.actions ----------------------------------------------------------
+  ctx.plist = s_plist; ctx.n_plist = ctx.sc[16];
   for (int r = P + tid; r < R; r += T) {
     if (ent_alive(ctx, r)) npc_decide(ctx, r);
     else { ctx.npc_move[r - P] = -1; ctx.npc_att[r - P] = 0; }
@@ -1390,10 +1406,14 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     __syncthreads();
     for (int w = tid; w < n_words; w += T) {
       uint32_t word = m32[w];
+      // four tiles at a time: any byte equal to a depleted material (3, 6, 8, 10, 12, 14)?
+      uint32_t hit = __vcmpeq4(word, 0x03030303u) | __vcmpeq4(word, 0x06060606u) | __vcmpeq4(word, 0x08080808u) |
+                     __vcmpeq4(word, 0x0a0a0a0au) | __vcmpeq4(word, 0x0c0c0c0cu) | __vcmpeq4(word, 0x0e0e0e0eu);
+      if (!hit) continue;
 #pragma unroll
       for (int b = 0; b < 4; b++) {
         int m = (word >> (8 * b)) & 255;
-        if ((NM_DEPLETED_MASK >> m) & 1) {
+        if ((hit >> (8 * b)) & 1) {
           int k = atomicAdd(&ctx.sc[5], 1);
           if (k < wl_cap) wl[k] = (uint16_t)(w * 4 + b);
           else respawn_tile(w * 4 + b, m);          // worklist full: draw in place

@@ -30,5 +30,5 @@ dep = []
 for e in (0, 1, 2, 3):
     ent, items, mp, sc = sim.snapshot(e)
     dep.append(int(np.isin(mp, (3, 6, 8, 10, 12, 14)).sum()))
-    print("env", e, "tick", sc[0], "depleted tiles", dep[-1], "alive players", int((ent[:128, 50] == 1).sum()), "npcs", int((ent[128:, 50] == 1).sum()),
+    print("env", e, "tick", sc[0], "depleted tiles", dep[-1], "alive players", int((ent[:128, 43] == 1).sum()), "npcs", int((ent[128:, 43] == 1).sum()),
           "items", int((items[:, 0] > 0).sum()))
