@@ -42,22 +42,22 @@ static size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
 static size_t step_smem_bytes(const NmParams &p) {
   size_t s = 0;
   int NINV = p.cfg[NC_N_INV];
-  s += a16((size_t)EA_N * p.R * 2); s += a16((size_t)IS_N * p.CAP * 2); s += a16((size_t)p.S * p.S);
+  s += a16((size_t)EA_N * p.R * 2); s += a16((size_t)IS_N * p.CAP * 2); s += a16((size_t)p.S * p.S / 2);
   s += a16((size_t)((p.S * p.S + 31) / 32) * 4); s += 2 * a16((size_t)((p.CAP + 31) / 32) * 4);
   s += a16((size_t)p.P * NINV * 2); s += a16(p.P); s += a16((size_t)12 * p.P * 2);
   s += a16(p.N); s += a16((size_t)p.N * 2); s += a16(NM_EV_CAP * 8); s += a16((size_t)p.P * 4) * 2; s += a16(64); s += 16;
-  s += a16(1024); s += a16((size_t)p.P * 16); s += a16((size_t)p.P * 8); s += a16(std::max<size_t>(4096, (size_t)p.R * 8)); s += a16(p.P); s += a16((size_t)p.P * 4) + 64;
+  s += a16(1024); s += a16((size_t)p.P * 16); s += a16((size_t)p.P * 8); s += a16(std::max<size_t>(4096, (size_t)p.R * 8)); s += a16((size_t)p.R * 4); s += a16(p.P); s += a16((size_t)p.P * 4) + 64;
   return s + 128;
 }
 static size_t obs_smem_bytes(const NmParams &p) {
   size_t s = 0;
   int NINV = p.cfg[NC_N_INV];
   int NW = NM_OBS_THREADS / 32;
-  s += a16((size_t)EA_N_OBS * p.R * 2); s += a16((size_t)p.R * 2); s += a16((size_t)IS_N * p.CAP * 2); s += a16((size_t)p.S * p.S);
+  s += a16((size_t)EA_N_OBS * p.R * 2); s += a16((size_t)p.R * 2); s += a16((size_t)IS_N * p.CAP * 2); s += a16((size_t)p.S * p.S / 2);
   s += a16((size_t)p.L.n_mkt * IA_N_OBS * 2); s += a16((size_t)p.L.n_mkt * 2);
   s += a16((size_t)p.P * NINV * 2); s += a16((size_t)p.P * 4); s += a16(64 * 4);
   s += a16((size_t)NW * a16(p.L.m_end)); s += a16((size_t)NW * a16((size_t)p.L.n_ent * 2)); s += 16;
-  s += a16((size_t)NW * 128); s += a16(2 * AC_N * 4); s += a16((size_t)p.R * 4); s += a16(a16(p.L.m_end));
+  s += a16((size_t)NW * 128); s += a16((2 * AC_N + 2) * 4); s += a16((size_t)p.P * 4); s += a16((size_t)p.P * 2); s += a16((size_t)p.R * 4); s += a16(a16(p.L.m_end));
   return s + 128;
 }
 
@@ -96,9 +96,10 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   p.E = n_envs; p.P = cfg[NC_N_PLAYERS]; p.N = cfg[NC_N_NPCS]; p.R = p.P + p.N; p.S = cfg[NC_MAP_SIZE]; p.CAP = cfg[NC_ITEM_CAP];
   p.n_maps = n_maps; p.n_tasks = n_tasks; p.env_base = env_base;
   if (p.P <= 0 || p.P > NM_STEP_THREADS) { delete h; return fail(NM_ERR_LIMIT, "PLAYER_N must be in 1..256 for the per-env CTA design"); }
-  if (p.R % 8 || p.CAP % 8 || (p.S * p.S) % 16) { delete h; return fail(NM_ERR_LIMIT, "P+N and item cap must be multiples of 8, S*S of 16 (bulk copies)"); }
+  if (p.R % 8 || p.CAP % 8 || (p.S * p.S) % 32) { delete h; return fail(NM_ERR_LIMIT, "P+N and item cap must be multiples of 8, S*S of 32 (bulk copies)"); }
   if (p.R > 2 * NM_STEP_THREADS) { delete h; return fail(NM_ERR_LIMIT, "P+N must be <= 512 for the per-env CTA design"); }
   if (p.S > 255) { delete h; return fail(NM_ERR_LIMIT, "MAP_SIZE must be <= 255"); }
+  if (p.cfg[NC_NPC_SPAWN_ATTEMPTS] > 32) { delete h; return fail(NM_ERR_LIMIT, "NPC_SPAWN_ATTEMPTS must be <= 32"); }
   if (p.L.n_ent > 255 || p.cfg[NC_N_INV] > 16) { delete h; return fail(NM_ERR_LIMIT, "N_ENT_OBS <= 255, N_INV <= 16"); }
   h->step_smem = step_smem_bytes(p);
   h->obs_smem = obs_smem_bytes(p);
@@ -108,7 +109,7 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   CU(cudaFuncSetAttribute(nmmo_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
   CU(cudaFuncSetAttribute(nmmo_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->obs_smem));
   size_t E = p.E, P = p.P;
-  DA(p.ent, E * EA_N * p.R); DA(p.item, E * IS_N * p.CAP); DA(p.map, E * p.S * p.S);
+  DA(p.ent, E * EA_N * p.R); DA(p.item, E * IS_N * p.CAP); DA(p.map, E * p.S * p.S / 2);
   uint8_t *dmaps; DA(dmaps, (size_t)n_maps * p.S * p.S); p.maps = dmaps;
   CU(cudaMemcpy(dmaps, maps, (size_t)n_maps * p.S * p.S, cudaMemcpyHostToDevice));
   DA(p.scalars, E * NM_SC_N); DA(p.seed, E); DA(p.danger, E * p.N);
@@ -120,7 +121,7 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   DA(p.obs, E * P * p.L.stride);
   DA(p.rew, E * P); DA(p.term, E * P); DA(p.trunc, E * P); DA(p.mask, E * P);
   DA(p.info, E * P * IN_N); DA(p.info_valid, E * P); DA(p.episode_done, E);
-  DA(p.agg, 2 * IN_N); DA(p.counters, 8); DA(p.obs_meta, E * P);
+  DA(p.agg, (size_t)NM_AGG_REP * 2 * IN_N); DA(p.counters, 8); DA(p.obs_meta, E * P);
   DA(h->d_actions, E * P * AC_N);
   DA(h->d_inj_off, E + 1);
   DA(h->d_env_mask, E);
@@ -210,6 +211,7 @@ extern "C" int nmmo_reset(nmmo_handle *h, const uint64_t *seeds, const int32_t *
 
 extern "C" int nmmo_step(nmmo_handle *h, const int32_t *actions_dev, void *stream) {
   if (!h || !actions_dev) return fail(NM_ERR_ARG, "null argument");
+  if ((uintptr_t)actions_dev & 15) return fail(NM_ERR_ARG, "actions must be 16-byte aligned");
   CU(cudaSetDevice(h->device));
   h->prm.actions = actions_dev;
   return launch_step(h, 0, (cudaStream_t)stream);
@@ -306,7 +308,12 @@ extern "C" int nmmo_snapshot(nmmo_handle *h, int env, int16_t *ent, int16_t *ite
     for (int i = 0; i < p.CAP; i++)
       for (int k = 0; k < IS_N; k++) items[(size_t)i * IS_N + k] = soa[(size_t)k * p.CAP + i];
   }
-  if (map) CU(cudaMemcpy(map, p.map + (size_t)env * p.S * p.S, (size_t)p.S * p.S, cudaMemcpyDeviceToHost));
+  if (map) {      // the live map is packed 4 bits per tile; the caller gets one byte per tile
+    size_t nt = (size_t)p.S * p.S;
+    std::vector<uint8_t> packed(nt / 2);
+    CU(cudaMemcpy(packed.data(), p.map + (size_t)env * (nt / 2), nt / 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < nt; i++) map[i] = (packed[i >> 1] >> ((i & 1) * 4)) & 15;
+  }
   if (scalars16) CU(cudaMemcpy(scalars16, p.scalars + (size_t)env * NM_SC_N, sizeof(int32_t) * NM_SC_N, cudaMemcpyDeviceToHost));
   return NM_OK;
 }
@@ -315,12 +322,18 @@ extern "C" int nmmo_stats(nmmo_handle *h, double *sums, double *counts, uint64_t
   if (!h) return fail(NM_ERR_ARG, "null handle");
   CU(cudaSetDevice(h->device));
   CU(cudaDeviceSynchronize());
-  double agg[2 * IN_N];
-  CU(cudaMemcpy(agg, h->prm.agg, sizeof(agg), cudaMemcpyDeviceToHost));
+  std::vector<double> rep((size_t)NM_AGG_REP * 2 * IN_N);
+  CU(cudaMemcpy(rep.data(), h->prm.agg, rep.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  double agg[2 * IN_N] = {0};
+  for (int r = 0; r < NM_AGG_REP; r++)
+    for (int i = 0; i < 2 * IN_N; i++) agg[i] += rep[(size_t)r * 2 * IN_N + i];
+  // slot IN_N + 0 counts finished agents; only the max-level keys can be absent (NaN) and keep their own count
+  for (int i = 1; i < IN_N; i++)
+    if (!(i >= IN_MAXLVL_ARMOR && i <= IN_MAXLVL_CONSUMABLE)) agg[IN_N + i] = agg[IN_N];
   if (sums) memcpy(sums, agg, sizeof(double) * IN_N);
   if (counts) memcpy(counts, agg + IN_N, sizeof(double) * IN_N);
   if (counters) CU(cudaMemcpy(counters, h->prm.counters, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost));
-  if (clear) { CU(cudaMemset(h->prm.agg, 0, sizeof(agg))); CU(cudaMemset(h->prm.counters, 0, sizeof(uint64_t) * 8)); }
+  if (clear) { CU(cudaMemset(h->prm.agg, 0, rep.size() * sizeof(double))); CU(cudaMemset(h->prm.counters, 0, sizeof(uint64_t) * 8)); }
   return NM_OK;
 }
 
@@ -350,15 +363,15 @@ extern "C" int nmmo_timing_read(nmmo_handle *h, double *step_ms, double *obs_ms,
 }
 
 // per-phase clock profile of the step kernel (development aid): enable allocates/clears the
-// accumulators, read copies 32 counters (SM clock cycles summed over CTAs) to the host
+// accumulators, read copies 64 counters (0..31 step kernel, 32..63 observation kernel) (SM clock cycles summed over CTAs) to the host
 extern "C" int nmmo_profile(nmmo_handle *h, int enable, unsigned long long *out32) {
   if (!h) return fail(NM_ERR_ARG, "null handle");
   CU(cudaSetDevice(h->device));
   CU(cudaDeviceSynchronize());
-  if (out32 && h->prm.prof) CU(cudaMemcpy(out32, h->prm.prof, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (out32 && h->prm.prof) CU(cudaMemcpy(out32, h->prm.prof, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   if (enable) {
-    if (!h->prm.prof) { int rc = dalloc(h, &h->prm.prof, 32); if (rc) return rc; }
-    CU(cudaMemset(h->prm.prof, 0, 32 * sizeof(unsigned long long)));
+    if (!h->prm.prof) { int rc = dalloc(h, &h->prm.prof, 64); if (rc) return rc; }
+    CU(cudaMemset(h->prm.prof, 0, 64 * sizeof(unsigned long long)));
   } else h->prm.prof = nullptr;
   return NM_OK;
 }

@@ -5,7 +5,7 @@
 // three cp.async.bulk (TMA 1-D) copies and pushes it back the same way:
 //   ent   int16 [E][EA_N][R]      structure-of-arrays entity table (players rows 0..P-1, NPCs after)
 //   item  int16 [E][IS_N][CAP]    item table (only stored columns; stats derive from type+level)
-//   map   uint8 [E][S*S]          current tile materials
+//   map   uint8 [E][S*S/2]        current tile materials, 4 bits per tile (16 materials)
 // plus small per-agent blocks (stats, unique-event bitsets, task state) and the output
 // tensors (obs records, reward, terminated, truncated, mask, episode info).
 #pragma once
@@ -17,6 +17,7 @@
 #define NM_STEP_THREADS 256
 #define NM_OBS_THREADS 256
 #define NM_SC_N 16              // per-env int32 scalars
+#define NM_AGG_REP 256           // replicas of the finished-agent sums (contention spreading)
 #define OM_NONZERO (1u << 16)
 #define OM_TASK (1u << 17)
 
@@ -47,7 +48,7 @@ struct NmParams {
   const int32_t *actions;      // [E][P][12]
   uint8_t *obs;                // [E*P][stride]
   float *rew; uint8_t *term, *trunc, *mask; float *info; uint8_t *info_valid; uint8_t *episode_done;
-  double *agg;                 // [2][IN_N] sums and counts of finished-agent info
+  double *agg;                 // [NM_AGG_REP][2][IN_N] sums and counts of finished-agent info
   unsigned long long *counters;// [8] slot-steps, alive-agent-steps, episodes, errors, obs-kernel bytes
   uint32_t *obs_meta;          // [E*P] what each obs record currently holds (incremental writer)
   int obs_full;                // 1 = rewrite every byte of every record each tick

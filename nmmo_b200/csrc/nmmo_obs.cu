@@ -21,7 +21,7 @@ struct OCtx {
   const int16_t *ent;      // [31][R]
   const int16_t *status;   // [R]
   const int16_t *item;     // [IS_N][CAP]
-  const uint8_t *map;
+  const uint32_t *map;
 };
 #define OENT(col, row) o.ent[(col) * o.R + (row)]
 #define OITM(col, row) o.item[(col) * o.CAP + (row)]
@@ -60,11 +60,12 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   size_t off = 0;
   auto carve = [&](size_t bytes) { uint8_t *q = smem + off; off = (off + bytes + 15) & ~(size_t)15; return q; };
   const uint32_t ent_bytes = (uint32_t)(EA_N_OBS * R * 2), st_bytes = (uint32_t)(R * 2);
-  const uint32_t item_bytes = (uint32_t)(IS_N * CAP * 2), map_bytes = (uint32_t)(S * S);
+  const uint32_t item_bytes = (uint32_t)(IS_N * CAP * 2), map_bytes = (uint32_t)(S * S / 2);
   int16_t *s_ent = (int16_t *)carve(ent_bytes);
   int16_t *s_status = (int16_t *)carve(st_bytes);
   int16_t *s_item = (int16_t *)carve(item_bytes);
-  uint8_t *s_map = carve(map_bytes);
+  uint32_t *s_map = (uint32_t *)carve(map_bytes);       // 4 bits per tile
+  auto tile = [&](int i) -> int { return (int)((s_map[i >> 3] >> ((i & 7) * 4)) & 15u); };
   int16_t *s_mkt = (int16_t *)carve((size_t)L.n_mkt * IA_N_OBS * 2);
   uint16_t *s_mkt_rows = (uint16_t *)carve((size_t)L.n_mkt * 2);
   uint16_t *s_inv = (uint16_t *)carve((size_t)P * NINV * 2);
@@ -76,9 +77,14 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   uint32_t *s_bits_all = (uint32_t *)carve((size_t)NW * 32 * 4);
   uint32_t *s_pos = (uint32_t *)carve((size_t)R * 4);       // (row+7)<<16 | (col+7) of alive rows
   uint8_t *s_tmpl = carve(stage_bytes);                      // agent-independent part of the masks
-  int *s_head = (int *)carve(2 * AC_N * 4);
+  int *s_head = (int *)carve((2 * AC_N + 2) * 4);       // + work-list length and cursor
+  uint32_t *s_meta = (uint32_t *)carve((size_t)P * 4);
+  uint16_t *s_work = (uint16_t *)carve((size_t)P * 2);
   uint64_t *bar = (uint64_t *)carve(8);
 
+  long long t_prev = clock64();
+  int ph = 32;
+#define OPHASE() do { if (prm.prof && tid == 0) { long long t_ = clock64(); atomicAdd(&prm.prof[ph], (unsigned long long)(t_ - t_prev)); t_prev = t_; } ph++; } while (0)
   if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   if (tid < AC_N) {
     const int off[AC_N] = {L.m_style, L.m_target, L.m_buy, L.m_destroy, L.m_give_item, L.m_give_target,
@@ -94,11 +100,12 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     bulk_g2s(s_ent, ge, ent_bytes, bar);
     bulk_g2s(s_status, ge + (size_t)EA_STATUS * R, st_bytes, bar);
     bulk_g2s(s_item, prm.item + (size_t)env * IS_N * CAP, item_bytes, bar);
-    bulk_g2s(s_map, prm.map + (size_t)env * S * S, map_bytes, bar);
+    bulk_g2s(s_map, prm.map + (size_t)env * map_bytes, map_bytes, bar);
   }
   for (int i = tid; i < P; i += T) s_invn[i] = 0;
   while (!mbar_try_wait(bar, 0)) {}
   __syncthreads();
+  OPHASE();      // 32 load
 
   OCtx o;
   o.p = &prm; o.c = c; o.R = R; o.S = S; o.CAP = CAP; o.P = P; o.NINV = NINV;
@@ -142,6 +149,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     if (lane == NW - 1) s_scan[63] = inc2;
   }
   __syncthreads();
+  OPHASE();      // 33 lists + scan
   const int n_mkt = min(s_scan[63], L.n_mkt);
   {
     int pos = s_scan[32 + warp] + incl - my_listed;
@@ -170,6 +178,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     dst[1] = make_uint4(pack2(row[8], row[9]), pack2(row[10], row[11]), pack2(row[12], row[13]), pack2(row[14], row[15]));
   }
   __syncthreads();
+  OPHASE();      // 34 market rows
 
   // ---- per-agent records: one warp per agent -------------------------------------------
   uint8_t *stage = s_stage_all + (size_t)warp * stage_bytes;
@@ -177,24 +186,49 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   uint16_t *s_vis = s_vis_all + (size_t)warp * (((L.n_ent * 2 + 15) & ~15) / 2);
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
   long long n_stored = 0;                     // 16-byte chunks stored by this warp
-  // this warp's agents are p = warp + NW*i: fetch all their meta words with one load
-  uint32_t meta_mine = 0;
-  if (warp + NW * lane < P) meta_mine = prm.obs_meta[(size_t)env * P + warp + NW * lane];
-  for (int p = warp, it = 0; p < P; p += NW, it++) {
+  // Work list.  Alive agents (a full record each) and agents that died since their record was last
+  // written (one zero fill) are compacted in id order by warp 0; the warps then pull entries off
+  // the list one at a time, so a warp never idles while another still has agents queued.
+  if (warp == 0) {
+    int n = 0;
+    for (int base = 0; base < P; base += 32) {
+      int p = base + lane;
+      uint32_t meta = p < P ? prm.obs_meta[(size_t)env * P + p] : 0u;
+      if (p < P) s_meta[p] = meta;
+      bool alive = p < P && s_status[p] == ES_ALIVE;
+      bool work = alive || (p < P && ((meta & OM_NONZERO) || prm.obs_full));
+      unsigned bm = __ballot_sync(0xffffffffu, work);
+      if (work) s_work[n + __popc(bm & ((1u << lane) - 1))] = (uint16_t)(p | (alive ? 0 : 0x8000));
+      n += __popc(bm);
+    }
+    if (lane == 0) { s_head[2 * AC_N] = n; s_head[2 * AC_N + 1] = 0; }
+  }
+  // absent agents: every head of the built-in policy picks 0 (one coalesced pass over the env)
+  if (prm.sample_out)
+    for (int i = tid; i < P * AC_N; i += T)
+      if (s_status[i / AC_N] != ES_ALIVE) prm.sample_out[(size_t)env * P * AC_N + i] = 0;
+  __syncthreads();
+  OPHASE();      // 35 work list
+  const int n_work = s_head[2 * AC_N];
+  long long w_t0 = clock64();
+  for (;;) {
+    int wi = 0;
+    if (lane == 0) wi = atomicAdd(&s_head[2 * AC_N + 1], 1);
+    wi = __shfl_sync(0xffffffffu, wi, 0);
+    if (wi >= n_work) break;
+    const int went = s_work[wi];
+    const int p = went & 0x7fff;
     const size_t a = (size_t)env * P + p;
     uint8_t *rec = prm.obs + a * L.stride;
     // The record lives in HBM across ticks, so only bytes that can differ from last tick's
     // record are stored.  meta remembers what the record currently holds: rows of Entity /
     // Inventory / Market that are non-zero, whether the Task block is in place, whether the
     // record is non-zero at all.  obs_full = 1 rewrites every byte (roofline / A-B mode).
-    const uint32_t meta = it < 32 ? __shfl_sync(0xffffffffu, meta_mine, it) : prm.obs_meta[a];
-    if (s_status[p] != ES_ALIVE) {           // dead or absent agents get the zero pad record
-      if (prm.sample_out && lane < AC_N) prm.sample_out[a * AC_N + lane] = 0;
-      if ((meta & OM_NONZERO) || prm.obs_full) {
-        for (int k = lane; k < L.stride / 16; k += 32) st16(rec + k * 16, zero4);
-        n_stored += L.stride / 16;
-        if (lane == 0) prm.obs_meta[a] = 0;
-      }
+    const uint32_t meta = s_meta[p];
+    if (went & 0x8000) {                     // dead or absent agents get the zero pad record
+      for (int k = lane; k < L.stride / 16; k += 32) st16(rec + k * 16, zero4);
+      n_stored += L.stride / 16;
+      if (lane == 0) prm.obs_meta[a] = 0;
       continue;
     }
     const int pv = prm.obs_full ? L.n_ent : (int)(meta & 255u);
@@ -263,7 +297,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
       m[L.m_use + lane] = !listed && OITM(IS_LEVEL, i) <= o_use_level(o, p, OITM(IS_TYPE, i));
     }
     if (!no_give) for (int g = 1 + lane; g < min(my_gold, L.n_price); g += 32) m[L.m_gold_price + g] = 1;
-    if (lane < 5) m[L.m_move + lane] = !nm_impassible(s_map[(r0 + c_dir_dr[lane]) * S + c0 + c_dir_dc[lane]]);
+    if (lane < 5) m[L.m_move + lane] = !nm_impassible(tile((r0 + c_dir_dr[lane]) * S + c0 + c_dir_dc[lane]));
     __syncwarp();
     // RewardWrapper.observation hooks
     // (takeru: Give.InventoryItem[:-1], Give.Target[:-1], GiveGold.Target[:-1], GiveGold.Price[1:]
@@ -371,7 +405,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
         for (int t = 0; t < 8; t++) {
           bool ok = w + t < n_tiles;
           int rr = r0 + dr - vis, cc = c0 + dc - vis;
-          v[3 * t] = ok ? rr : 0; v[3 * t + 1] = ok ? cc : 0; v[3 * t + 2] = ok ? (int)s_map[rr * S + cc] : 0;
+          v[3 * t] = ok ? rr : 0; v[3 * t + 1] = ok ? cc : 0; v[3 * t + 2] = ok ? tile(rr * S + cc) : 0;
           if (++dc == L.win) { dc = 0; dr++; }
         }
         uint8_t *dst = rec + L.o_tile + g * 48;
@@ -385,6 +419,12 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     }
     if (lane == 0) prm.obs_meta[a] = (uint32_t)n_vis | ((uint32_t)n_inv << 8) | OM_NONZERO | OM_TASK | ((uint32_t)n_mkt << 18);
     __syncwarp();
+  }
+  if (prm.prof && lane == 0) {
+    long long t_ = clock64();
+    atomicAdd(&prm.prof[40], (unsigned long long)(t_ - w_t0));          // warp-busy cycles in the record loop
+    atomicMax(&prm.prof[41 + (blockIdx.x & 7)], (unsigned long long)(t_ - w_t0));
+    if (tid == 0) { atomicAdd(&prm.prof[36], (unsigned long long)(t_ - t_prev)); atomicAdd(&prm.prof[37], (unsigned long long)n_work); }
   }
   // bytes this CTA stored (+ the state it pulled in): the kernel's physical traffic estimate
   if (lane == 0) atomicAdd(&prm.counters[4], (unsigned long long)n_stored * 16ULL + (warp == 0 ? (unsigned long long)(ent_bytes + st_bytes + item_bytes + map_bytes) : 0ULL));

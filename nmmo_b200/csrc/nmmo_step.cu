@@ -26,7 +26,7 @@ struct Ctx {
   const int32_t *c;
   int env, P, N, R, S, CAP, NINV;
   int16_t *ent, *item;
-  uint8_t *map;
+  uint32_t *map;            // 4-bit materials, 8 tiles per word
   uint32_t *occ, *used, *fresh;
   uint16_t *inv;
   uint8_t *invn;
@@ -205,7 +205,13 @@ __device__ int use_level(const Ctx &ctx, int row, int type) {
     }
   }
 }
-__device__ __forceinline__ int tile_at(const Ctx &ctx, int r, int c) { return ctx.map[r * ctx.S + c]; }
+// the tile map is packed 4 bits per tile (16 materials), tile i in bits 4*(i&7) of word i>>3
+__device__ __forceinline__ int tile_i(const Ctx &ctx, int i) { return (ctx.map[i >> 3] >> ((i & 7) * 4)) & 15; }
+__device__ __forceinline__ int tile_at(const Ctx &ctx, int r, int c) { return tile_i(ctx, r * ctx.S + c); }
+// materials only ever change by one step (harvest: m -> m-1, respawn: m -> m+1) and never leave
+// 0..15, so an atomic add on the word is an exact update of one nibble under concurrent writers
+__device__ __forceinline__ void tile_dec(const Ctx &ctx, int i) { atomicSub(&ctx.map[i >> 3], 1u << ((i & 7) * 4)); }
+__device__ __forceinline__ void tile_inc(const Ctx &ctx, int i) { atomicAdd(&ctx.map[i >> 3], 1u << ((i & 7) * 4)); }
 __device__ __forceinline__ bool occ_get(const Ctx &ctx, int r, int c) { int i = r * ctx.S + c; return (ctx.occ[i >> 5] >> (i & 31)) & 1u; }
 __device__ __forceinline__ void occ_set(const Ctx &ctx, int r, int c) { int i = r * ctx.S + c; atomicOr(&ctx.occ[i >> 5], 1u << (i & 31)); }
 __device__ __forceinline__ void occ_clr(const Ctx &ctx, int r, int c) { int i = r * ctx.S + c; atomicAnd(&ctx.occ[i >> 5], ~(1u << (i & 31))); }
@@ -239,8 +245,8 @@ __device__ void process_drops(const Ctx &ctx, int prow, int matl, int level_col,
 }
 __device__ bool tile_harvest(const Ctx &ctx, int r, int c, int matl) {
   int i = r * ctx.S + c;
-  if (ctx.map[i] != matl) return false;
-  ctx.map[i] = (uint8_t)(matl - 1);
+  if (tile_i(ctx, i) != matl) return false;
+  tile_dec(ctx, i);
   return true;
 }
 // the id-ordered part of Player.update: anything that depletes a tile or allocates an item
@@ -630,20 +636,21 @@ __device__ int border_dist(const Ctx &ctx, int r, int c) {
 }
 // NPCManager.spawn, split: one thread replays the sequential accept/reject logic of the (up to
 // 25) attempts and records the accepted ones; the rows are then filled in by one thread each
-__device__ int npc_spawn_decide(const Ctx &ctx, uint32_t *dec) {       // single thread
+__device__ int npc_spawn_decide(const Ctx &ctx, uint32_t *dec, const int *free_rows, const int *dng) {       // single thread
   const int32_t *c = ctx.c;
   int b = c[NC_MAP_BORDER], ce = c[NC_MAP_CENTER];
   int count = ctx.sc[4];
-  int scan = ctx.P, n = 0;
-  int16_t *danger = ctx.p->danger + (size_t)ctx.env * ctx.N;
-  for (int att = 0; att < c[NC_NPC_SPAWN_ATTEMPTS]; att++) {
+  int n = 0;
+  const int nd0 = ctx.sc[2];
+  int nd = nd0;
+  const int attempts = min(c[NC_NPC_SPAWN_ATTEMPTS], 32);
+  for (int att = 0; att < attempts; att++) {
     if (count >= ctx.N) break;
-    while (scan < ctx.R && ENT(EA_STATUS, scan) == ES_ALIVE) scan++;
-    if (scan >= ctx.R) break;
+    // the n-th accepted spawn takes the n-th free row (the reference scans for the first free slot)
+    int scan = free_rows[n];
     int r, cc;
-    int nd = ctx.sc[2];
     if (nd > 0) {
-      int d = danger[nd - 1];
+      int d = dng[nd0 - nd];
       int mid = ce / 2, max_off = mid - d;
       int offset = mid + b + nm_bounded(ctx.predraw[att * 8 + 0], 2 * max_off) - max_off;
       int side = nm_bounded(ctx.predraw[att * 8 + 1], 4);
@@ -670,8 +677,9 @@ __device__ int npc_spawn_decide(const Ctx &ctx, uint32_t *dec) {       // single
     ENT(EA_STATUS, scan) = ES_ALIVE;
     occ_set(ctx, r, cc);
     count++; n++;
-    if (nd > 0) ctx.sc[2] = nd - 1;
+    if (nd > 0) nd--;
   }
+  ctx.sc[2] = nd;
   return n;
 }
 __device__ void npc_spawn_fill(const Ctx &ctx, const uint32_t *q) {
@@ -846,15 +854,23 @@ __device__ void write_info(const Ctx &ctx, int p, bool terminated, double cum_re
   for (int k = 0; k < 4; k++) v[IN_EQUIP_ARMOR + k] = (float)((fl >> k) & 1);
   v[IN_HARVEST_WEAPON] = (float)((fl >> 4) & 1);
   v[IN_TASK_ID] = (float)ctx.p->task_id[a];
+  // running sums for nmmo_stats(): NM_AGG_REP replicas (picked by env) keep thousands of agents
+  // that finish in the same tick from queueing on 80 addresses; zero terms are skipped, and the
+  // count of a key that cannot be NaN is the count of finished agents (slot 0)
+  double *ag = ctx.p->agg + (size_t)(ctx.env & (NM_AGG_REP - 1)) * (2 * IN_N);
+#pragma unroll
+  for (int i = 0; i < IN_N; i += 4) *(float4 *)(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+#pragma unroll
   for (int i = 0; i < IN_N; i++) {
-    o[i] = v[i];
-    if (v[i] == v[i]) { atomicAdd(&ctx.p->agg[i], (double)v[i]); atomicAdd(&ctx.p->agg[IN_N + i], 1.0); }
+    if (v[i] == v[i] && v[i] != 0.0f) atomicAdd(&ag[i], (double)v[i]);
+    if (i >= IN_MAXLVL_ARMOR && i <= IN_MAXLVL_CONSUMABLE && v[i] == v[i]) atomicAdd(&ag[IN_N + i], 1.0);
   }
+  atomicAdd(&ag[IN_N], 1.0);
   ctx.p->info_valid[a] = 1;
 }
 
 // ------------------------------------------------------------------------ reset -----
-__device__ void reset_env(const NmParams &P_, int env, uint64_t seed, bool explicit_map, bool explicit_tasks,
+__device__ __noinline__ void reset_env(const NmParams &P_, int env, uint64_t seed, bool explicit_map, bool explicit_tasks,
                           int *s_slot /* >= 2*P ints of shared memory */) {
   const int32_t *c = P_.cfg;
   int tid = threadIdx.x, T = blockDim.x;
@@ -867,9 +883,15 @@ __device__ void reset_env(const NmParams &P_, int env, uint64_t seed, bool expli
   int map_id = explicit_map ? sc[SC_MAP_ID] : nm_bounded(draw(ctx, RS_MAP, 0, 0), P_.n_maps);
   // map copy, table clears
   {
-    const uint4 *src = (const uint4 *)(P_.maps + (size_t)map_id * S * S);
-    uint4 *dst = (uint4 *)(P_.map + (size_t)env * S * S);
-    for (int i = tid; i < S * S / 16; i += T) dst[i] = src[i];
+    // source maps are one byte per tile; the live map packs two tiles per byte
+    const uint2 *src = (const uint2 *)(P_.maps + (size_t)map_id * S * S);
+    uint32_t *dst = (uint32_t *)(P_.map + (size_t)env * (S * S / 2));
+    for (int i = tid; i < S * S / 8; i += T) {
+      uint2 b = src[i];
+      uint32_t lo = b.x, hi = b.y;
+      dst[i] = (lo & 15u) | ((lo >> 4) & 0xf0u) | ((lo >> 8) & 0xf00u) | ((lo >> 12) & 0xf000u) |
+               ((hi & 15u) << 16) | (((hi >> 8) & 15u) << 20) | (((hi >> 16) & 15u) << 24) | (((hi >> 24) & 15u) << 28);
+    }
     uint4 z = make_uint4(0, 0, 0, 0);
     uint4 *e4 = (uint4 *)(P_.ent + (size_t)env * EA_N * R);
     for (int i = tid; i < EA_N * R * 2 / 16; i += T) e4[i] = z;
@@ -942,21 +964,16 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     reset_env(prm, env, prm.seed[env], gsc[SC_EXPLICIT_MAP] != 0, gsc[SC_EXPLICIT_TASKS] != 0, (int *)smem);
     return;
   }
-  if (gsc[SC_DONE]) {
-    if (tid == 0) { gsc[SC_EPISODE] += 1; atomicAdd(&prm.counters[2], 1ULL); }
-    reset_env(prm, env, nm_mix64(prm.seed[env] + 0x632BE59BD9B4E019ULL), false, false, (int *)smem);
-    return;
-  }
 
   // ---- shared memory carve-up ---------------------------------------------------------
   size_t off = 0;
   auto carve = [&](size_t bytes) { uint8_t *q = smem + off; off = (off + bytes + 15) & ~(size_t)15; return q; };
-  const uint32_t ent_bytes = (uint32_t)(EA_N * R * 2), item_bytes = (uint32_t)(IS_N * CAP * 2), map_bytes = (uint32_t)(S * S);
+  const uint32_t ent_bytes = (uint32_t)(EA_N * R * 2), item_bytes = (uint32_t)(IS_N * CAP * 2), map_bytes = (uint32_t)(S * S / 2);
   Ctx ctx;
   ctx.p = &prm; ctx.c = c; ctx.env = env; ctx.P = P; ctx.N = N; ctx.R = R; ctx.S = S; ctx.CAP = CAP; ctx.NINV = NINV;
   ctx.ent = (int16_t *)carve(ent_bytes);
   ctx.item = (int16_t *)carve(item_bytes);
-  ctx.map = carve(map_bytes);
+  ctx.map = (uint32_t *)carve(map_bytes);
   const int occ_words = (S * S + 31) >> 5, cap_words = (CAP + 31) >> 5;
   ctx.occ = (uint32_t *)carve(occ_words * 4);
   ctx.used = (uint32_t *)carve(cap_words * 4);
@@ -976,12 +993,26 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   // respawn worklist, NPC-spawn pre-drawn values
   const size_t scratch_bytes = max((size_t)4096, (size_t)R * 8);
   uint32_t *s_scratch = (uint32_t *)carve(scratch_bytes);
+  uint16_t *s_mv = (uint16_t *)carve((size_t)R * 4);        // Move phase: destination + verdict per row
   uint32_t *s_att = s_scratch;
   int *s_first = (int *)(s_scratch + R);
   ctx.slow = (int8_t *)carve((size_t)P);
   uint32_t *s_plist = (uint32_t *)carve((size_t)P * 4);
   ctx.sc = (int *)carve(32 * 4);
   uint64_t *bar = (uint64_t *)carve(8);
+  // ---- load: three bulk copies on one mbarrier, issued before anything else touches HBM ----
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar, ent_bytes + item_bytes + map_bytes);
+    bulk_g2s(ctx.ent, prm.ent + (size_t)env * EA_N * R, ent_bytes, bar);
+    bulk_g2s(ctx.item, prm.item + (size_t)env * IS_N * CAP, item_bytes, bar);
+    bulk_g2s(ctx.map, prm.map + (size_t)env * map_bytes, map_bytes, bar);
+  }
+  const int done_flag = gsc[SC_DONE];      // consumed below, after the other loads are in flight
   ctx.seed = prm.seed[env];
   ctx.tick = gsc[SC_TICK];
   ctx.inj_lo = prm.inj_off ? prm.inj_off[env] : 0;
@@ -1006,18 +1037,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   long long t_prev = clock64();
   int ph = 0;
 #define PHASE() do { if (prm.prof && tid == 0) { long long t_ = clock64(); atomicAdd(&prm.prof[ph], (unsigned long long)(t_ - t_prev)); t_prev = t_; } ph++; } while (0)
-  // ---- load: three bulk copies on one mbarrier ----------------------------------------
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(bar, ent_bytes + item_bytes + map_bytes);
-    bulk_g2s(ctx.ent, prm.ent + (size_t)env * EA_N * R, ent_bytes, bar);
-    bulk_g2s(ctx.item, prm.item + (size_t)env * IS_N * CAP, item_bytes, bar);
-    bulk_g2s(ctx.map, prm.map + (size_t)env * S * S, map_bytes, bar);
-  }
+#define PCOUNT(slot, v) do { if (prm.prof && tid == 0) atomicAdd(&prm.prof[slot], (unsigned long long)(v)); } while (0)
   for (int i = tid; i < occ_words; i += T) ctx.occ[i] = 0;
   for (int i = tid; i < cap_words; i += T) { ctx.used[i] = 0; ctx.fresh[i] = 0; }
   for (int i = tid; i < P; i += T) { ctx.invn[i] = 0; ctx.duniq[i] = 0; }
@@ -1028,6 +1048,51 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   }
   if (tid < 32) ctx.sc[tid] = 0;
   if (tid == 0) { ctx.sc[2] = gsc[SC_N_DANGER]; ctx.sc[3] = gsc[SC_NEXT_NPC_ID]; }
+  if (done_flag) {      // episode over: this launch resets the environment instead of stepping it
+    while (!mbar_try_wait(bar, 0)) {}      // the bulk copies must have landed before shared memory is reused
+    __syncthreads();
+    if (tid == 0) { gsc[SC_EPISODE] += 1; atomicAdd(&prm.counters[2], 1ULL); }
+    reset_env(prm, env, nm_mix64(ctx.seed + 0x632BE59BD9B4E019ULL), false, false, (int *)smem);
+    return;
+  }
+  // Decode the player actions against the observation record they were chosen on (the ids are read
+  // back from the record in HBM).  Only global memory is involved, so these loads overlap the bulk
+  // copies; targets stay entity ids here and become table rows once the tables have landed.
+  int my_prev_price = 0;
+  if (tid < P) {
+    const int p = tid;
+    const int4 *x4 = (const int4 *)(prm.actions + ((size_t)env * P + p) * AC_N);
+    const int16_t *gent = prm.ent + (size_t)env * EA_N * R;
+    const int g_status = gent[EA_STATUS * R + p], g_health = gent[EA_HEALTH * R + p];   // same answer as ent_alive() later
+    int4 xa = x4[0], xb = x4[1], xc = x4[2];
+    if (!(g_status == ES_ALIVE && g_health > 0)) { xa = make_int4(-1, -1, -1, -1); xb = xa; xc = xa; }   // no id reads for the dead
+    const uint8_t *rec = prm.obs + ((size_t)env * P + p) * prm.L.stride;
+    const nm_obs_layout &L = prm.L;
+    auto ent_id = [&](int idx) -> int { return (idx >= 0 && idx < L.n_ent) ? (int)*(const int16_t *)(rec + L.o_entity + idx * (EA_N_OBS * 2)) : 0; };
+    auto inv_id = [&](int idx) -> int { return (idx >= 0 && idx < L.n_inv) ? (int)*(const int16_t *)(rec + L.o_inventory + idx * (IA_N_OBS * 2)) : 0; };
+    auto mkt_id = [&](int idx) -> int { return (idx >= 0 && idx < L.n_mkt) ? (int)*(const int16_t *)(rec + L.o_market + idx * (IA_N_OBS * 2)) : 0; };
+    const int a_as = xa.x, a_at = xa.y, a_buy = xa.z, a_des = xa.w, a_gi = xb.x, a_gt = xb.y, a_gp = xb.z, a_gg = xb.w;
+    const int a_mv = xc.x, a_si = xc.y, a_sp = xc.z, a_use = xc.w;
+    // all eight id reads are independent: issue them together
+    const int i_use = inv_id(a_use), i_des = inv_id(a_des), i_si = inv_id(a_si), i_buy = mkt_id(a_buy), i_gi = inv_id(a_gi);
+    const int t_gt = ent_id(a_gt), t_gg = ent_id(a_gg), t_at = ent_id(a_at);
+    int16_t v[A_N];
+#pragma unroll
+    for (int k = 0; k < A_N; k++) v[k] = 0;
+    v[A_MOVE] = -1;
+    v[A_USE] = (int16_t)i_use;
+    v[A_DESTROY] = (int16_t)i_des;
+    const bool sp_ok = a_sp >= 0 && a_sp < L.n_price;
+    if (sp_ok && i_si) { v[A_SELL_ITEM] = (int16_t)i_si; v[A_SELL_PRICE] = (int16_t)(a_sp + 1); }
+    v[A_BUY] = (int16_t)i_buy;
+    if (i_gi && t_gt > 0) { v[A_GIVE_ITEM] = (int16_t)i_gi; v[A_GIVE_TARGET] = (int16_t)t_gt; }
+    if (a_gp >= 0 && a_gp < L.n_price && t_gg > 0) { v[A_GOLD_AMT] = (int16_t)(a_gp + 1); v[A_GOLD_TARGET] = (int16_t)t_gg; }
+    if (a_as >= 0 && a_as < 3 && t_at) { v[A_ATT_STYLE] = (int16_t)a_as; v[A_ATT_TARGET] = (int16_t)t_at; }
+    if (a_mv >= 0 && a_mv < 4) v[A_MOVE] = (int16_t)a_mv;
+    my_prev_price = sp_ok ? a_sp : 0;
+#pragma unroll
+    for (int k = 0; k < A_N; k++) ctx.act[k * P + p] = v[k];
+  }
   while (!mbar_try_wait(bar, 0)) {}
   __syncthreads();
 
@@ -1052,8 +1117,14 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     }
     if (lane == 0) ctx.sc[16] = n;
   }
-  for (int i = tid; i < CAP; i += T)
-    if (ITM(IS_TYPE, i) != 0) {
+  for (int g = tid; g < CAP / 8; g += T) {      // 8 rows of the type column per 16-byte load
+    const uint4 t8 = ((const uint4 *)(ctx.item + IS_TYPE * CAP))[g];
+    if (!(t8.x | t8.y | t8.z | t8.w)) continue;
+    const uint32_t tw[4] = {t8.x, t8.y, t8.z, t8.w};
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (!((tw[j >> 1] >> ((j & 1) * 16)) & 0xffffu)) continue;
+      const int i = g * 8 + j;
       atomicOr(&ctx.used[i >> 5], 1u << (i & 31));
       int owner = ITM(IS_OWNER, i);
       if (owner > 0) {
@@ -1065,19 +1136,11 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
         ctx.inv[(owner - 1) * NINV + slot] = (uint16_t)i;
       }
     }
-  // ---- validate player actions against the observation they were chosen on ------------
-  for (int p = tid; p < P; p += T) {
-    int16_t v[A_N];
-#pragma unroll
-    for (int k = 0; k < A_N; k++) v[k] = 0;
-    v[A_MOVE] = -1;
+  }
+  // ---- validate: entity ids chosen from the observation -> table rows; dead agents act on nothing
+  if (tid < P) {
+    const int p = tid;
     if (ent_alive(ctx, p)) {
-      const int32_t *x = prm.actions + ((size_t)env * P + p) * AC_N;
-      const uint8_t *rec = prm.obs + ((size_t)env * P + p) * prm.L.stride;
-      const nm_obs_layout &L = prm.L;
-      auto ent_id = [&](int idx) -> int { return (idx >= 0 && idx < L.n_ent) ? (int)*(const int16_t *)(rec + L.o_entity + idx * (EA_N_OBS * 2)) : 0; };
-      auto inv_id = [&](int idx) -> int { return (idx >= 0 && idx < L.n_inv) ? (int)*(const int16_t *)(rec + L.o_inventory + idx * (IA_N_OBS * 2)) : 0; };
-      auto mkt_id = [&](int idx) -> int { return (idx >= 0 && idx < L.n_mkt) ? (int)*(const int16_t *)(rec + L.o_market + idx * (IA_N_OBS * 2)) : 0; };
       auto ent_row1 = [&](int id) -> int {
         if (id > 0) return id <= P ? id : 0;
         if (id < 0) {
@@ -1091,22 +1154,14 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
         }
         return 0;
       };
-      int a_use = x[AC_USE_ITEM], a_des = x[AC_DESTROY_ITEM], a_si = x[AC_SELL_ITEM], a_sp = x[AC_SELL_PRICE];
-      int a_buy = x[AC_BUY_ITEM], a_gi = x[AC_GIVE_ITEM], a_gt = x[AC_GIVE_TARGET], a_gp = x[AC_GOLD_PRICE];
-      int a_gg = x[AC_GOLD_TARGET], a_as = x[AC_ATTACK_STYLE], a_at = x[AC_ATTACK_TARGET], a_mv = x[AC_MOVE_DIR];
-      v[A_USE] = (int16_t)inv_id(a_use);
-      v[A_DESTROY] = (int16_t)inv_id(a_des);
-      if (a_sp >= 0 && a_sp < L.n_price) { int id = inv_id(a_si); if (id) { v[A_SELL_ITEM] = (int16_t)id; v[A_SELL_PRICE] = (int16_t)(a_sp + 1); } }
-      v[A_BUY] = (int16_t)mkt_id(a_buy);
-      { int it = inv_id(a_gi), tg = ent_id(a_gt); if (it && tg > 0) { v[A_GIVE_ITEM] = (int16_t)it; v[A_GIVE_TARGET] = (int16_t)ent_row1(tg); } }
-      if (a_gp >= 0 && a_gp < L.n_price) { int tg = ent_id(a_gg); if (tg > 0) { v[A_GOLD_AMT] = (int16_t)(a_gp + 1); v[A_GOLD_TARGET] = (int16_t)ent_row1(tg); } }
-      if (a_as >= 0 && a_as < 3) { int tg = ent_id(a_at); if (tg) { v[A_ATT_STYLE] = (int16_t)a_as; v[A_ATT_TARGET] = (int16_t)ent_row1(tg); } }
-      if (a_mv >= 0 && a_mv < 4) v[A_MOVE] = (int16_t)a_mv;
-      if (c[NC_WRAPPER] == NW_START_KIT)
-        prm.stats[((size_t)env * P + p) * ST_N + ST_PREV_PRICE] = (a_sp >= 0 && a_sp < L.n_price) ? a_sp : 0;
-    }
+      if (ctx.act[A_GIVE_ITEM * P + p]) ctx.act[A_GIVE_TARGET * P + p] = (int16_t)ent_row1(ctx.act[A_GIVE_TARGET * P + p]);
+      if (ctx.act[A_GOLD_AMT * P + p]) ctx.act[A_GOLD_TARGET * P + p] = (int16_t)ent_row1(ctx.act[A_GOLD_TARGET * P + p]);
+      if (ctx.act[A_ATT_TARGET * P + p]) ctx.act[A_ATT_TARGET * P + p] = (int16_t)ent_row1(ctx.act[A_ATT_TARGET * P + p]);
+      if (c[NC_WRAPPER] == NW_START_KIT) prm.stats[((size_t)env * P + p) * ST_N + ST_PREV_PRICE] = my_prev_price;
+    } else {
 #pragma unroll
-    for (int k = 0; k < A_N; k++) ctx.act[k * P + p] = v[k];
+      for (int k = 0; k < A_N; k++) ctx.act[k * P + p] = k == A_MOVE ? (int16_t)-1 : (int16_t)0;
+    }
   }
   __syncthreads();
 
@@ -1150,7 +1205,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       int here = tile_at(ctx, r, cc);
       if (here == MT_FOILAGE && !c[NC_ALLOW_OCCUPIED]) {
         // with one entity per tile nobody else can eat this tile: no ordering needed
-        ctx.map[r * S + cc] = MT_SCRUB;
+        tile_dec(ctx, r * S + cc);
         food = min(c[NC_RES_BASE], food + c[NC_RES_HARVEST_RESTORE]);
         emit(ctx, p, EV_EAT_FOOD, 0, 0, 0, 0, 0);
         here = MT_SCRUB;
@@ -1246,7 +1301,9 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     __syncthreads();
     const int na = ctx.sc[6];
     int pending = na > 0;
+    PCOUNT(22, na);
     while (pending) {
+      PCOUNT(23, 1);
       for (int r = tid; r < R; r += T) s_first[r] = 0x7fffffff;
       if (tid == 0) ctx.sc[7] = 0x7fffffff;
       __syncthreads();
@@ -1288,55 +1345,103 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   if (c[NC_ALLOW_OCCUPIED]) {
     for (int r = tid; r < R; r += T) if (ent_alive(ctx, r)) act_move(ctx, r, r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P], false);
   } else {
-    // every pending mover registers its row index on its source and destination tile (atomicMin
-    // in a 1024-slot tile hash); a mover holding the minimum on both tiles cannot be affected by
-    // any other pending mover, so all such movers commit together; chains resolve in later rounds
-    const uint32_t EMPTY = 0xffffffffu;
-    uint32_t *tbl = s_scratch;
-    auto slot_insert = [&](int key, int idx) {
-      uint32_t v = ((uint32_t)key << 16) | (uint32_t)idx;
-      unsigned h = ((unsigned)key * 40503u >> 3) & 1023u;
-      for (;;) {
-        uint32_t cur = tbl[h];
-        if (cur == EMPTY) { uint32_t old = atomicCAS(&tbl[h], EMPTY, v); if (old == EMPTY) return; cur = old; }
-        if ((cur >> 16) == (uint32_t)key) { atomicMin(&tbl[h], v); return; }
-        h = (h + 1) & 1023u;
-      }
-    };
-    auto slot_min = [&](int key) -> int {
-      unsigned h = ((unsigned)key * 40503u >> 3) & 1023u;
-      for (;;) { uint32_t cur = tbl[h]; if ((cur >> 16) == (uint32_t)key) return (int)(cur & 0xffffu); h = (h + 1) & 1023u; }
-    };
-    int mv_src[2], mv_dst[2], mv_dir[2];
-    bool mv_want[2];
+    // Sequential semantics: movers act in row order and a move succeeds iff the destination is
+    // unoccupied at that moment.  With one entity per tile a destination d has at most four
+    // claimants (one per neighbouring tile) and at most one occupant o, so every mover can decide
+    // locally, from a position index (tile -> row), whether it is the one claimant that may take d:
+    //   d free at tick start      -> the lowest-row claimant wins, the others find it occupied;
+    //   d held by a mover o       -> claimants below o fail (o is still there); the first claimant
+    //                                above o wins iff o itself moves away;
+    //   d held by a non-mover     -> everybody fails.
+    // The only non-local part is "iff o moves away": a chain of strictly decreasing rows that each
+    // winner walks down.  No rounds, no atomics on the decision path.
+    const uint32_t NONE = 0xffffu, NODEP = 0xfffeu;
+    uint32_t *tbl = s_scratch;                               // 1024-slot position index
+    uint16_t *mvd = s_mv, *res = s_mv + R;                   // intended destination, verdict / dependency
+    for (int i = tid; i < 1024; i += T) tbl[i] = 0;
+    int mv_dir[2];
 #pragma unroll
     for (int k = 0; k < 2; k++) {
       int r = tid + k * T;
-      mv_want[k] = false; mv_src[k] = 0; mv_dst[k] = 0; mv_dir[k] = -1;
-      if (r < R && ent_alive(ctx, r)) {
-        int dir = r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P];
-        if (dir >= 0 && dir <= 3 && ENT(EA_FREEZE, r) == 0) {
-          int rr = ENT(EA_ROW, r), cc = ENT(EA_COL, r);
-          int dst = (rr + c_dir_dr[dir]) * S + cc + c_dir_dc[dir];
-          if (!nm_impassible(ctx.map[dst])) { mv_want[k] = true; mv_src[k] = rr * S + cc; mv_dst[k] = dst; mv_dir[k] = dir; }
+      mv_dir[k] = -1;
+      if (r < R) {
+        uint32_t d = NONE;
+        if (ent_alive(ctx, r)) {
+          int dir = r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P];
+          if (dir >= 0 && dir <= 3 && ENT(EA_FREEZE, r) == 0) {
+            int dst = (ENT(EA_ROW, r) + c_dir_dr[dir]) * S + ENT(EA_COL, r) + c_dir_dc[dir];
+            if (!nm_impassible(tile_i(ctx, dst))) { d = (uint32_t)dst; mv_dir[k] = dir; }
+          }
         }
+        mvd[r] = (uint16_t)d;
       }
     }
-    int pending = __syncthreads_or(mv_want[0] || mv_want[1]);
-    while (pending) {
-      for (int i = tid; i < 1024; i += T) tbl[i] = EMPTY;
-      __syncthreads();
+    __syncthreads();
+    for (int r = tid; r < R; r += T)
+      if (ENT(EA_STATUS, r) == ES_ALIVE) {                   // same set as the occupancy bitmap
+        uint32_t key = (uint32_t)(ENT(EA_ROW, r) * S + ENT(EA_COL, r));
+        uint32_t v = ((key + 1) << 16) | (uint32_t)r;
+        unsigned h = (key * 40503u >> 3) & 1023u;
+        while (atomicCAS(&tbl[h], 0u, v) != 0u) h = (h + 1) & 1023u;
+      }
+    __syncthreads();
+    auto who = [&](int tile) -> int {                        // row of the entity on an occupied tile
+      unsigned h = ((unsigned)tile * 40503u >> 3) & 1023u;
+      for (;;) {
+        uint32_t cur = tbl[h];
+        if ((cur >> 16) == (uint32_t)tile + 1) return (int)(cur & 0xffffu);
+        if (cur == 0) return -1;
+        h = (h + 1) & 1023u;
+      }
+    };
 #pragma unroll
-      for (int k = 0; k < 2; k++) if (mv_want[k]) { slot_insert(mv_src[k], tid + k * T); slot_insert(mv_dst[k], tid + k * T); }
-      __syncthreads();
+    for (int k = 0; k < 2; k++) {
+      const int i = tid + k * T;
+      if (mv_dir[k] < 0) { if (i < R) res[i] = (uint16_t)NONE; continue; }
+      const int d = mvd[i];
+      const int dr_ = d / S, dc_ = d - dr_ * S;
+      int o = occ_get(ctx, dr_, dc_) ? who(d) : -1;
+      uint32_t verdict = NODEP;
+      int lo = -1;                                           // claimants in (lo, i) beat me
+      if (o >= 0) {
+        if (mvd[o] == NONE || o > i) verdict = NONE; else { verdict = (uint32_t)o; lo = o; }
+      }
+      if (verdict != NONE) {
 #pragma unroll
-      for (int k = 0; k < 2; k++)
-        if (mv_want[k] && slot_min(mv_src[k]) == tid + k * T && slot_min(mv_dst[k]) == tid + k * T) {
-          act_move(ctx, tid + k * T, mv_dir[k], true);
-          mv_want[k] = false;
+        for (int q = 0; q < 4; q++) {
+          if (q == mv_dir[k]) continue;                      // that neighbour is my own tile
+          int nr = dr_ - c_dir_dr[q], nc = dc_ - c_dir_dc[q];
+          if (!occ_get(ctx, nr, nc)) continue;
+          int e = who(nr * S + nc);
+          if (e > lo && e < i && mvd[e] == d) { verdict = NONE; break; }
         }
-      pending = __syncthreads_or(mv_want[0] || mv_want[1]);
+      }
+      res[i] = (uint16_t)verdict;
     }
+    __syncthreads();
+    bool mv_ok[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      mv_ok[k] = false;
+      if (mv_dir[k] < 0) continue;
+      int j = tid + k * T;
+      for (;;) {
+        uint32_t v = res[j];
+        if (v == NONE) break;
+        if (v == NODEP) { mv_ok[k] = true; break; }
+        j = (int)v;
+      }
+      if (mv_ok[k]) occ_clr(ctx, ENT(EA_ROW, tid + k * T), ENT(EA_COL, tid + k * T));
+    }
+    { int nmv = __syncthreads_count(mv_dir[0] >= 0) + __syncthreads_count(mv_dir[1] >= 0); PCOUNT(24, nmv); }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+      if (mv_ok[k]) {
+        const int i = tid + k * T, d = mvd[i];
+        occ_set(ctx, d / S, d - (d / S) * S);
+        act_move(ctx, i, mv_dir[k], false);
+      }
   }
   __syncthreads();
   PHASE();
@@ -1352,9 +1457,10 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       occ_clr(ctx, ENT(EA_ROW, p), ENT(EA_COL, p));
       while (ctx.invn[p] > 0) item_destroy(ctx, ctx.inv[p * NINV + ctx.invn[p] - 1]);
     }
+  int *s_free = (int *)s_scratch + 512, *s_dng = (int *)s_scratch + 544;   // spawn inputs (scratch is idle here)
   if (warp == 0) {
     int16_t *danger = prm.danger + (size_t)env * N;
-    int nd = ctx.sc[2], alive = 0;
+    int nd = ctx.sc[2], alive = 0, nfree = 0;
     for (int base = P; base < R; base += 32) {
       int r = base + lane;
       bool live = r < R && ENT(EA_STATUS, r) == ES_ALIVE;
@@ -1367,7 +1473,13 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
         occ_clr(ctx, ENT(EA_ROW, r), ENT(EA_COL, r));
       }
       nd = min(N, nd + __popc(m));
-      alive += __popc(__ballot_sync(0xffffffffu, live && !dead));
+      unsigned am = __ballot_sync(0xffffffffu, live && !dead);
+      alive += __popc(am);
+      // free rows in ascending order (first 32): the rows npcs.spawn will fill
+      bool fr = r < R && !(live && !dead);
+      unsigned fm = __ballot_sync(0xffffffffu, fr);
+      if (fr) { int k = nfree + __popc(fm & ((1u << lane) - 1)); if (k < 32) s_free[k] = r; }
+      nfree += __popc(fm);
     }
     if (lane == 0) { ctx.sc[2] = nd; ctx.sc[4] = alive; }
   }
@@ -1378,10 +1490,11 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     // the draws of every attempt are keyed by (attempt, ordinal): compute them all in parallel
     const int n_pre = min(c[NC_NPC_SPAWN_ATTEMPTS] * 8, (int)(scratch_bytes / 4));
     for (int i = tid; i < n_pre; i += T) s_scratch[i] = draw(ctx, RS_NPC_SPAWN, (uint32_t)(i >> 3), (uint32_t)(i & 7));
+    if (tid < 32) { int k = ctx.sc[2] - 1 - tid; s_dng[tid] = k >= 0 ? (int)prm.danger[(size_t)env * N + k] : 0; }   // top of the danger stack
     ctx.predraw = s_scratch;
     uint32_t *dec = s_scratch + 256;
     __syncthreads();
-    if (tid == 0) ctx.sc[5] = npc_spawn_decide(ctx, dec);
+    if (tid == 0) ctx.sc[5] = npc_spawn_decide(ctx, dec, s_free, s_dng);
     __syncthreads();
     if (tid < ctx.sc[5]) npc_spawn_fill(ctx, dec + tid * 8);
   }
@@ -1393,41 +1506,63 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   {
     // map.step: every depleted tile draws once.  Depleted tiles are first gathered into a
     // worklist (the draw is keyed by the tile, so order is free), then hashed by all threads
-    const uint32_t *m32 = (const uint32_t *)ctx.map;
     uint16_t *wl = (uint16_t *)s_scratch;
     const int wl_cap = (int)(scratch_bytes / 2);
-    const int n_words = S * S / 4;
+    const int n_quads = S * S / 32;        // 16 bytes = 32 tiles per load
     auto respawn_tile = [&](int i, int m) {
       int thr_idx = m == MT_SCRUB ? NC_RESPAWN_FOILAGE : m == MT_SLAG ? NC_RESPAWN_ORE : m == MT_STUMP ? NC_RESPAWN_TREE
                   : m == MT_FRAGMENT ? NC_RESPAWN_CRYSTAL : m == MT_WEEDS ? NC_RESPAWN_HERB : NC_RESPAWN_FISH;
-      if (draw(ctx, RS_RESPAWN, (uint32_t)i, 0) < (uint32_t)c[thr_idx]) ctx.map[i] = (uint8_t)(m + 1);
+      if (draw(ctx, RS_RESPAWN, (uint32_t)i, 0) < (uint32_t)c[thr_idx]) tile_inc(ctx, i);
     };
     if (tid == 0) ctx.sc[5] = 0;
     __syncthreads();
-    for (int w = tid; w < n_words; w += T) {
-      uint32_t word = m32[w];
-      // four tiles at a time: any byte equal to a depleted material (3, 6, 8, 10, 12, 14)?
-      uint32_t hit = __vcmpeq4(word, 0x03030303u) | __vcmpeq4(word, 0x06060606u) | __vcmpeq4(word, 0x08080808u) |
-                     __vcmpeq4(word, 0x0a0a0a0au) | __vcmpeq4(word, 0x0c0c0c0cu) | __vcmpeq4(word, 0x0e0e0e0eu);
-      if (!hit) continue;
+    for (int q0 = 0; q0 < n_quads; q0 += T) {       // block-uniform trip count: the append below is warp-wide
+      const int q = q0 + tid;
+      uint32_t hits[4] = {0, 0, 0, 0};
+      int cnt = 0;
+      if (q < n_quads) {
+        const uint4 v = ((const uint4 *)ctx.map)[q];
+        const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int b = 0; b < 4; b++) {
-        int m = (word >> (8 * b)) & 255;
-        if ((hit >> (8 * b)) & 1) {
-          int k = atomicAdd(&ctx.sc[5], 1);
-          if (k < wl_cap) wl[k] = (uint16_t)(w * 4 + b);
-          else respawn_tile(w * 4 + b, m);          // worklist full: draw in place
+        for (int j = 0; j < 4; j++) {
+          // depleted materials are 3, 6 and the even ones from 8 up: bit-sliced test of all 8 nibbles
+          const uint32_t x = xs[j], x1 = x >> 1, x2 = x >> 2, x3 = x >> 3;
+          hits[j] = ((x3 & ~x) | (~x3 & x1 & (x2 ^ x))) & 0x11111111u;
+          cnt += __popc(hits[j]);
+        }
+      }
+      if (!__any_sync(0xffffffffu, cnt)) continue;
+      // one shared-memory atomic per warp: exclusive scan of the lane counts
+      int incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+      int base = 0;
+      if (lane == 31) base = atomicAdd(&ctx.sc[5], incl);
+      int k = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        uint32_t hit = hits[j];
+        while (hit) {
+          int b = __ffs(hit) - 1; hit &= hit - 1;
+          int i = (q * 4 + j) * 8 + (b >> 2);
+          if (k < wl_cap) wl[k] = (uint16_t)i;
+          else respawn_tile(i, tile_i(ctx, i));          // worklist full: draw in place
+          k++;
         }
       }
     }
     __syncthreads();
     int n = min(ctx.sc[5], wl_cap);
-    for (int k = tid; k < n; k += T) { int i = wl[k]; respawn_tile(i, ctx.map[i]); }
+    for (int k = tid; k < n; k += T) { int i = wl[k]; respawn_tile(i, tile_i(ctx, i)); }
   }
-  for (int i = tid; i < CAP; i += T)
-    if (ITM(IS_TYPE, i) != 0 && ITM(IS_PRICE, i) > 0 && ctx.tick - ITM(IS_LIST_TICK, i) > c[NC_LISTING_DURATION]) {
-      ITM(IS_PRICE, i) = 0; ITM(IS_LIST_TICK, i) = 0;
+  // exchange.step: listings expire; only rows in use are visited (one bitmap word per thread)
+  for (int w = tid; w < cap_words; w += T) {
+    uint32_t bits = ctx.used[w];
+    while (bits) {
+      int i = (w << 5) + __ffs(bits) - 1; bits &= bits - 1;
+      if (ITM(IS_PRICE, i) > 0 && ctx.tick - ITM(IS_LIST_TICK, i) > c[NC_LISTING_DURATION]) { ITM(IS_PRICE, i) = 0; ITM(IS_LIST_TICK, i) = 0; }
     }
+  }
   __syncthreads();
 
   PHASE();
@@ -1437,13 +1572,14 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   if (tid == 0) {
     bulk_s2g(prm.ent + (size_t)env * EA_N * R, ctx.ent, ent_bytes);
     bulk_s2g(prm.item + (size_t)env * IS_N * CAP, ctx.item, item_bytes);
-    bulk_s2g(prm.map + (size_t)env * S * S, ctx.map, map_bytes);
+    bulk_s2g(prm.map + (size_t)env * map_bytes, ctx.map, map_bytes);
     bulk_commit();
   }
 
   PHASE();
   // ---- phase 7: fold the tick's events ------------------------------------------------
   int nev = min(ctx.sc[0], NM_EV_CAP);
+  PCOUNT(26, nev);
   for (int i = tid; i < nev; i += T) fold_event(ctx, ctx.ev[i]);
   __syncthreads();
 
@@ -1457,8 +1593,10 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     ctx.slow[tid] = req ? (int8_t)-2 : (int8_t)-1;
   }
   __syncthreads();
-  for (int p = warp; p < P; p += (T >> 5)) {
-    if (ctx.slow[p] != -2) continue;
+  for (int pb = warp * 32; pb < P; pb += T) {
+    unsigned reqm = __ballot_sync(0xffffffffu, pb + lane < P && ctx.slow[pb + lane] == -2);
+  while (reqm) {
+    const int p = pb + __ffs(reqm) - 1; reqm &= reqm - 1;
     int pred = ctx.task[p * 4], q0 = ctx.task[p * 4 + 1], q1 = ctx.task[p * 4 + 2];
     int r = ENT(EA_ROW, p), cc = ENT(EA_COL, p), vis = c[NC_VISION];
     bool hit = false;
@@ -1481,7 +1619,9 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     }
     if (lane == 0) ctx.slow[p] = hit ? 1 : 0;
   }
+  }
   __syncthreads();
+  PHASE();
   int n_alive = __syncthreads_count(st_me == ES_ALIVE);
   int n_dead = __syncthreads_count(st_me == ES_DEAD_THIS_TICK);
   int n_current = n_alive + n_dead;
@@ -1540,6 +1680,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     prm.rew[a] = rew; prm.term[a] = term; prm.trunc[a] = trunc; prm.mask[a] = mask;
   }
   PHASE();
+  PCOUNT(27, n_alive); PCOUNT(28, n_dead);
   if (tid == 0) {
     gsc[SC_TICK] = ctx.tick; gsc[SC_DONE] = env_done ? 1 : 0; gsc[SC_N_DANGER] = ctx.sc[2]; gsc[SC_NEXT_NPC_ID] = ctx.sc[3];
     gsc[SC_FRESH] = 0;

@@ -224,7 +224,7 @@ class Simulator:
         return a.value, b.value, n.value
 
     def profile(self, enable: bool):
-        out = np.zeros(32, np.uint64)
+        out = np.zeros(64, np.uint64)
         self._check(self.L.nmmo_profile(self.h, int(enable), _p(out)))
         return out
 
