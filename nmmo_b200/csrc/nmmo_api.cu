@@ -53,7 +53,7 @@ static size_t obs_smem_bytes(const NmParams &p) {
   size_t s = 0;
   int NINV = p.cfg[NC_N_INV];
   int NW = NM_OBS_THREADS / 32;
-  s += a16((size_t)EA_N_OBS * p.R * 2); s += a16((size_t)p.R * 2); s += a16((size_t)IS_N * p.CAP * 2); s += a16((size_t)p.S * p.S / 2);
+  s += a16((size_t)EA_N_OBS * p.R * 2); s += a16((size_t)p.R * 2); s += a16((size_t)IS_N * p.ICAP * 2); s += a16((size_t)p.S * p.S / 2);
   s += a16((size_t)p.L.n_mkt * IA_N_OBS * 2); s += a16((size_t)p.L.n_mkt * 2);
   s += a16((size_t)p.P * NINV * 2); s += a16((size_t)p.P * 4); s += a16(64 * 4);
   s += a16((size_t)NW * a16(p.L.m_end)); s += a16((size_t)NW * a16((size_t)p.L.n_ent * 2)); s += 16;
@@ -95,6 +95,7 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   nm_obs_layout_init(p.cfg, &p.L);
   p.E = n_envs; p.P = cfg[NC_N_PLAYERS]; p.N = cfg[NC_N_NPCS]; p.R = p.P + p.N; p.S = cfg[NC_MAP_SIZE]; p.CAP = cfg[NC_ITEM_CAP];
   p.n_maps = n_maps; p.n_tasks = n_tasks; p.env_base = env_base;
+  p.ICAP = std::min(p.CAP, 512);      // item rows kept in shared memory; rows beyond are used in HBM
   if (p.P <= 0 || p.P > NM_STEP_THREADS) { delete h; return fail(NM_ERR_LIMIT, "PLAYER_N must be in 1..256 for the per-env CTA design"); }
   if (p.R % 8 || p.CAP % 8 || (p.S * p.S) % 32) { delete h; return fail(NM_ERR_LIMIT, "P+N and item cap must be multiples of 8, S*S of 32 (bulk copies)"); }
   if (p.R > 2 * NM_STEP_THREADS) { delete h; return fail(NM_ERR_LIMIT, "P+N must be <= 512 for the per-env CTA design"); }
@@ -307,6 +308,10 @@ extern "C" int nmmo_snapshot(nmmo_handle *h, int env, int16_t *ent, int16_t *ite
     CU(cudaMemcpy(soa.data(), p.item + (size_t)env * IS_N * p.CAP, soa.size() * 2, cudaMemcpyDeviceToHost));
     for (int i = 0; i < p.CAP; i++)
       for (int k = 0; k < IS_N; k++) items[(size_t)i * IS_N + k] = soa[(size_t)k * p.CAP + i];
+    int32_t hi = 0;      // rows >= SC_ITEM_HI are free: their bytes in HBM are stale, report them empty
+    CU(cudaMemcpy(&hi, p.scalars + (size_t)env * NM_SC_N + SC_ITEM_HI, sizeof(hi), cudaMemcpyDeviceToHost));
+    for (int i = std::max(hi, 0); i < p.CAP; i++)
+      for (int k = 0; k < IS_N; k++) items[(size_t)i * IS_N + k] = 0;
   }
   if (map) {      // the live map is packed 4 bits per tile; the caller gets one byte per tile
     size_t nt = (size_t)p.S * p.S;

@@ -4,7 +4,8 @@
 // contiguous and 16-byte aligned so a CTA pulls its environment into shared memory with
 // three cp.async.bulk (TMA 1-D) copies and pushes it back the same way:
 //   ent   int16 [E][EA_N][R]      structure-of-arrays entity table (players rows 0..P-1, NPCs after)
-//   item  int16 [E][IS_N][CAP]    item table (only stored columns; stats derive from type+level)
+//   item  int16 [E][IS_N][CAP]    item table (only stored columns; stats derive from type+level);
+//                                 rows >= scalars[SC_ITEM_HI] are free and their content is unspecified
 //   map   uint8 [E][S*S/2]        current tile materials, 4 bits per tile (16 materials)
 // plus small per-agent blocks (stats, unique-event bitsets, task state) and the output
 // tensors (obs records, reward, terminated, truncated, mask, episode info).
@@ -22,13 +23,15 @@
 #define OM_TASK (1u << 17)
 
 enum nm_scalar { SC_TICK = 0, SC_DONE, SC_NEXT_NPC_ID, SC_N_DANGER, SC_MAP_ID, SC_EPISODE, SC_FRESH,
-                 SC_ERROR, SC_NEED_RESET, SC_EXPLICIT_MAP, SC_EXPLICIT_TASKS };
+                 SC_ERROR, SC_NEED_RESET, SC_EXPLICIT_MAP, SC_EXPLICIT_TASKS,
+                 SC_ITEM_HI /* rows >= this are free; multiple of 8 */ };
 
 struct NmParams {
   int32_t cfg[NC_COUNT];
   double fcfg[NF_COUNT];
   nm_obs_layout L;
   int E, P, N, R, S, CAP, n_maps, n_tasks;
+  int ICAP;                    // item rows staged in shared memory (the tail is used in HBM)
   // state
   int16_t *ent, *item;
   uint8_t *map;

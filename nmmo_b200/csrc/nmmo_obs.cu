@@ -17,14 +17,15 @@ namespace {
 struct OCtx {
   const NmParams *p;
   const int32_t *c;
-  int R, S, CAP, P, NINV;
+  int R, S, CAP, ICAP, P, NINV;
   const int16_t *ent;      // [31][R]
   const int16_t *status;   // [R]
-  const int16_t *item;     // [IS_N][CAP]
+  const int16_t *item;     // [IS_N][ICAP] staged prefix of the item table
+  const int16_t *gitem;    // [IS_N][CAP] the table in HBM (rows >= ICAP)
   const uint32_t *map;
 };
 #define OENT(col, row) o.ent[(col) * o.R + (row)]
-#define OITM(col, row) o.item[(col) * o.CAP + (row)]
+#define OITM(col, row) ((row) < o.ICAP ? o.item[(col) * o.ICAP + (row)] : o.gitem[(size_t)(col) * o.CAP + (row)])
 
 __device__ __forceinline__ int o_use_level(const OCtx &o, int row, int type) {
   switch (type) {
@@ -48,19 +49,19 @@ __device__ __forceinline__ uint32_t pack2(int a, int b) { return (uint32_t)(uint
 
 }  // namespace
 
-extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, 2)
+extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, 3)
 nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int env = blockIdx.x, tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
   const int32_t *c = prm.cfg;
   const nm_obs_layout &L = prm.L;
-  const int P = prm.P, R = prm.R, S = prm.S, CAP = prm.CAP, NINV = c[NC_N_INV], vis = c[NC_VISION];
+  const int P = prm.P, R = prm.R, S = prm.S, CAP = prm.CAP, ICAP = prm.ICAP, NINV = c[NC_N_INV], vis = c[NC_VISION];
   const int tick = prm.scalars[(size_t)env * NM_SC_N + SC_TICK];
 
   size_t off = 0;
   auto carve = [&](size_t bytes) { uint8_t *q = smem + off; off = (off + bytes + 15) & ~(size_t)15; return q; };
   const uint32_t ent_bytes = (uint32_t)(EA_N_OBS * R * 2), st_bytes = (uint32_t)(R * 2);
-  const uint32_t item_bytes = (uint32_t)(IS_N * CAP * 2), map_bytes = (uint32_t)(S * S / 2);
+  const uint32_t item_bytes = (uint32_t)(IS_N * ICAP * 2), map_bytes = (uint32_t)(S * S / 2);
   int16_t *s_ent = (int16_t *)carve(ent_bytes);
   int16_t *s_status = (int16_t *)carve(st_bytes);
   int16_t *s_item = (int16_t *)carve(item_bytes);
@@ -80,12 +81,13 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   int *s_head = (int *)carve((2 * AC_N + 2) * 4);       // + work-list length and cursor
   uint32_t *s_meta = (uint32_t *)carve((size_t)P * 4);
   uint16_t *s_work = (uint16_t *)carve((size_t)P * 2);
-  uint64_t *bar = (uint64_t *)carve(8);
+  uint64_t *bar = (uint64_t *)carve(16);
 
   long long t_prev = clock64();
   int ph = 32;
 #define OPHASE() do { if (prm.prof && tid == 0) { long long t_ = clock64(); atomicAdd(&prm.prof[ph], (unsigned long long)(t_ - t_prev)); t_prev = t_; } ph++; } while (0)
-  if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  const int item_hi = prm.scalars[(size_t)env * NM_SC_N + SC_ITEM_HI];     // rows >= item_hi are free
   if (tid < AC_N) {
     const int off[AC_N] = {L.m_style, L.m_target, L.m_buy, L.m_destroy, L.m_give_item, L.m_give_target,
                            L.m_gold_price, L.m_gold_target, L.m_move, L.m_sell_item, L.m_sell_price, L.m_use};
@@ -95,20 +97,25 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   }
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(bar, ent_bytes + st_bytes + item_bytes + map_bytes);
+    mbar_expect_tx(bar, ent_bytes + st_bytes + map_bytes);
     const int16_t *ge = prm.ent + (size_t)env * EA_N * R;
     bulk_g2s(s_ent, ge, ent_bytes, bar);
     bulk_g2s(s_status, ge + (size_t)EA_STATUS * R, st_bytes, bar);
-    bulk_g2s(s_item, prm.item + (size_t)env * IS_N * CAP, item_bytes, bar);
     bulk_g2s(s_map, prm.map + (size_t)env * map_bytes, map_bytes, bar);
+    const uint32_t col_bytes = (uint32_t)min(item_hi, ICAP) * 2;       // only the live prefix of each item column
+    mbar_expect_tx(bar + 1, col_bytes * IS_N);
+    if (col_bytes)
+      for (int k = 0; k < IS_N; k++) bulk_g2s(s_item + k * ICAP, prm.item + ((size_t)env * IS_N + k) * CAP, col_bytes, bar + 1);
   }
-  for (int i = tid; i < P; i += T) s_invn[i] = 0;
+  for (int i = tid; i < P; i += T) { s_invn[i] = 0; s_meta[i] = prm.obs_meta[(size_t)env * P + i]; }
   while (!mbar_try_wait(bar, 0)) {}
+  while (!mbar_try_wait(bar + 1, 0)) {}
   __syncthreads();
   OPHASE();      // 32 load
 
   OCtx o;
-  o.p = &prm; o.c = c; o.R = R; o.S = S; o.CAP = CAP; o.P = P; o.NINV = NINV;
+  o.p = &prm; o.c = c; o.R = R; o.S = S; o.CAP = CAP; o.ICAP = ICAP; o.P = P; o.NINV = NINV;
+  o.gitem = prm.item + (size_t)env * IS_N * CAP;
   o.ent = s_ent; o.status = s_status; o.item = s_item; o.map = s_map;
   const int wrapper = c[NC_WRAPPER];
   const bool no_give = wrapper == NW_TAKERU && c[NC_DISABLE_GIVE];
@@ -127,11 +134,11 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   }
 
   // ---- inventory lists (row order) and the market list (row order, first n_mkt) -------
-  const int K = (CAP + T - 1) / T;          // consecutive rows per thread
+  const int K = (item_hi + T - 1) / T;      // consecutive rows per thread
   int my_listed = 0;
   for (int k = 0; k < K; k++) {
     int i = tid * K + k;
-    if (i < CAP && OITM(IS_TYPE, i) != 0) {
+    if (i < item_hi && OITM(IS_TYPE, i) != 0) {
       int owner = OITM(IS_OWNER, i);
       if (owner > 0) { int slot = atomicAdd(&s_invn[owner - 1], 1); if (slot < NINV) s_inv[(owner - 1) * NINV + slot] = (uint16_t)i; }
       if (OITM(IS_PRICE, i) > 0) my_listed++;
@@ -155,7 +162,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     int pos = s_scan[32 + warp] + incl - my_listed;
     for (int k = 0; k < K; k++) {
       int i = tid * K + k;
-      if (i < CAP && OITM(IS_TYPE, i) != 0 && OITM(IS_PRICE, i) > 0) { if (pos < L.n_mkt) s_mkt_rows[pos] = (uint16_t)i; pos++; }
+      if (i < item_hi && OITM(IS_TYPE, i) != 0 && OITM(IS_PRICE, i) > 0) { if (pos < L.n_mkt) s_mkt_rows[pos] = (uint16_t)i; pos++; }
     }
   }
   for (int p = tid; p < P; p += T) {           // sort each inventory list by row (<= 12 entries)
@@ -193,8 +200,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     int n = 0;
     for (int base = 0; base < P; base += 32) {
       int p = base + lane;
-      uint32_t meta = p < P ? prm.obs_meta[(size_t)env * P + p] : 0u;
-      if (p < P) s_meta[p] = meta;
+      uint32_t meta = p < P ? s_meta[p] : 0u;
       bool alive = p < P && s_status[p] == ES_ALIVE;
       bool work = alive || (p < P && ((meta & OM_NONZERO) || prm.obs_full));
       unsigned bm = __ballot_sync(0xffffffffu, work);
@@ -427,7 +433,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     if (tid == 0) { atomicAdd(&prm.prof[36], (unsigned long long)(t_ - t_prev)); atomicAdd(&prm.prof[37], (unsigned long long)n_work); }
   }
   // bytes this CTA stored (+ the state it pulled in): the kernel's physical traffic estimate
-  if (lane == 0) atomicAdd(&prm.counters[4], (unsigned long long)n_stored * 16ULL + (warp == 0 ? (unsigned long long)(ent_bytes + st_bytes + item_bytes + map_bytes) : 0ULL));
+  if (lane == 0) atomicAdd(&prm.counters[4], (unsigned long long)n_stored * 16ULL + (warp == 0 ? (unsigned long long)(ent_bytes + st_bytes + (uint32_t)(IS_N * 2 * item_hi) + map_bytes) : 0ULL));
 }
 
 // ============================================================= action sampler kernel ===

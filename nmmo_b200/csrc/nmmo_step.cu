@@ -50,18 +50,24 @@ struct Ctx {
 #define ENT(col, row) ctx.ent[(col) * ctx.R + (row)]
 #define ITM(col, row) ctx.item[(col) * ctx.CAP + (row)]
 
-__device__ uint32_t draw(const Ctx &ctx, uint32_t site, uint32_t idx, uint32_t k) {
-  if (ctx.inj_hi > ctx.inj_lo) {
-    uint64_t key = nm_rng_key((uint32_t)ctx.tick, site, idx, k);
-    int lo = ctx.inj_lo, hi = ctx.inj_hi - 1;
+// one out-of-line copy of the draw (hash + injected-value lookup): it is called from ~16 sites and
+// the step kernel is instruction-cache bound, not call bound
+__device__ __forceinline__ uint32_t draw_impl(const uint64_t *inj_keys, const uint32_t *inj_vals, int lo, int hi,
+                                           uint64_t seed, uint32_t tick, uint32_t site, uint32_t idx, uint32_t k) {
+  if (hi > lo) {
+    uint64_t key = nm_rng_key(tick, site, idx, k);
+    hi -= 1;
     while (lo <= hi) {
       int mid = (lo + hi) >> 1;
-      uint64_t kk = ctx.p->inj_keys[mid];
-      if (kk == key) return ctx.p->inj_vals[mid];
+      uint64_t kk = inj_keys[mid];
+      if (kk == key) return inj_vals[mid];
       if (kk < key) lo = mid + 1; else hi = mid - 1;
     }
   }
-  return nm_hash_draw(ctx.seed, (uint32_t)ctx.tick, site, idx, k);
+  return nm_hash_draw(seed, tick, site, idx, k);
+}
+__device__ __forceinline__ uint32_t draw(const Ctx &ctx, uint32_t site, uint32_t idx, uint32_t k) {
+  return draw_impl(ctx.p->inj_keys, ctx.p->inj_vals, ctx.inj_lo, ctx.inj_hi, ctx.seed, (uint32_t)ctx.tick, site, idx, k);
 }
 
 // ------------------------------------------------------------------ event ring ------
@@ -895,8 +901,7 @@ __device__ __noinline__ void reset_env(const NmParams &P_, int env, uint64_t see
     uint4 z = make_uint4(0, 0, 0, 0);
     uint4 *e4 = (uint4 *)(P_.ent + (size_t)env * EA_N * R);
     for (int i = tid; i < EA_N * R * 2 / 16; i += T) e4[i] = z;
-    uint4 *i4 = (uint4 *)(P_.item + (size_t)env * IS_N * P_.CAP);
-    for (int i = tid; i < IS_N * P_.CAP * 2 / 16; i += T) i4[i] = z;
+    // the item table is not cleared: SC_ITEM_HI = 0 below declares every row free
     uint32_t *u = P_.uniq + (size_t)env * P * NM_UNIQ_WORDS;
     for (int i = tid; i < P * NM_UNIQ_WORDS; i += T) u[i] = 0;
     int32_t *st = P_.stats + (size_t)env * P * ST_N;
@@ -942,7 +947,7 @@ __device__ __noinline__ void reset_env(const NmParams &P_, int env, uint64_t see
   if (tid == 0) {
     P_.seed[env] = seed;
     sc[SC_TICK] = 0; sc[SC_DONE] = 0; sc[SC_NEXT_NPC_ID] = -1; sc[SC_N_DANGER] = 0; sc[SC_MAP_ID] = map_id;
-    sc[SC_FRESH] = 1; sc[SC_NEED_RESET] = 0; sc[SC_EXPLICIT_MAP] = 0; sc[SC_EXPLICIT_TASKS] = 0;
+    sc[SC_FRESH] = 1; sc[SC_ITEM_HI] = 0; sc[SC_NEED_RESET] = 0; sc[SC_EXPLICIT_MAP] = 0; sc[SC_EXPLICIT_TASKS] = 0;
     P_.episode_done[env] = 0;
   }
 }
@@ -971,6 +976,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   const uint32_t ent_bytes = (uint32_t)(EA_N * R * 2), item_bytes = (uint32_t)(IS_N * CAP * 2), map_bytes = (uint32_t)(S * S / 2);
   Ctx ctx;
   ctx.p = &prm; ctx.c = c; ctx.env = env; ctx.P = P; ctx.N = N; ctx.R = R; ctx.S = S; ctx.CAP = CAP; ctx.NINV = NINV;
+  int16_t *const gitem = prm.item + (size_t)env * IS_N * CAP;
   ctx.ent = (int16_t *)carve(ent_bytes);
   ctx.item = (int16_t *)carve(item_bytes);
   ctx.map = (uint32_t *)carve(map_bytes);
@@ -999,20 +1005,29 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   ctx.slow = (int8_t *)carve((size_t)P);
   uint32_t *s_plist = (uint32_t *)carve((size_t)P * 4);
   ctx.sc = (int *)carve(32 * 4);
-  uint64_t *bar = (uint64_t *)carve(8);
+  uint64_t *bar = (uint64_t *)carve(16);
   // ---- load: three bulk copies on one mbarrier, issued before anything else touches HBM ----
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(bar, 1); mbar_init(bar + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(bar, ent_bytes + item_bytes + map_bytes);
+    mbar_expect_tx(bar, ent_bytes + map_bytes);
     bulk_g2s(ctx.ent, prm.ent + (size_t)env * EA_N * R, ent_bytes, bar);
-    bulk_g2s(ctx.item, prm.item + (size_t)env * IS_N * CAP, item_bytes, bar);
     bulk_g2s(ctx.map, prm.map + (size_t)env * map_bytes, map_bytes, bar);
   }
   const int done_flag = gsc[SC_DONE];      // consumed below, after the other loads are in flight
+  const int item_hi0 = gsc[SC_ITEM_HI];    // rows >= item_hi0 are free (multiple of 8)
+  if (tid == 0) {
+    // Item rows are allocated lowest-free-first, so live rows crowd the low end of the table: only
+    // the prefix below the high-water mark moves between HBM and shared memory.  Rows above it are
+    // never read before they are allocated (the in-use bitmap is built from the prefix).
+    const uint32_t col_bytes = (uint32_t)item_hi0 * 2;
+    mbar_expect_tx(bar + 1, col_bytes * IS_N);
+    if (col_bytes)
+      for (int k = 0; k < IS_N; k++) bulk_g2s(ctx.item + k * CAP, gitem + (size_t)k * CAP, col_bytes, bar + 1);
+  }
   ctx.seed = prm.seed[env];
   ctx.tick = gsc[SC_TICK];
   ctx.inj_lo = prm.inj_off ? prm.inj_off[env] : 0;
@@ -1050,6 +1065,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   if (tid == 0) { ctx.sc[2] = gsc[SC_N_DANGER]; ctx.sc[3] = gsc[SC_NEXT_NPC_ID]; }
   if (done_flag) {      // episode over: this launch resets the environment instead of stepping it
     while (!mbar_try_wait(bar, 0)) {}      // the bulk copies must have landed before shared memory is reused
+    while (!mbar_try_wait(bar + 1, 0)) {}
     __syncthreads();
     if (tid == 0) { gsc[SC_EPISODE] += 1; atomicAdd(&prm.counters[2], 1ULL); }
     reset_env(prm, env, nm_mix64(ctx.seed + 0x632BE59BD9B4E019ULL), false, false, (int *)smem);
@@ -1094,6 +1110,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     for (int k = 0; k < A_N; k++) ctx.act[k * P + p] = v[k];
   }
   while (!mbar_try_wait(bar, 0)) {}
+  while (!mbar_try_wait(bar + 1, 0)) {}
   __syncthreads();
 
   PHASE();
@@ -1117,7 +1134,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     }
     if (lane == 0) ctx.sc[16] = n;
   }
-  for (int g = tid; g < CAP / 8; g += T) {      // 8 rows of the type column per 16-byte load
+  for (int g = tid; g < item_hi0 / 8; g += T) {      // 8 rows of the type column per 16-byte load
     const uint4 t8 = ((const uint4 *)(ctx.item + IS_TYPE * CAP))[g];
     if (!(t8.x | t8.y | t8.z | t8.w)) continue;
     const uint32_t tw[4] = {t8.x, t8.y, t8.z, t8.w};
@@ -1515,6 +1532,16 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       if (draw(ctx, RS_RESPAWN, (uint32_t)i, 0) < (uint32_t)c[thr_idx]) tile_inc(ctx, i);
     };
     if (tid == 0) ctx.sc[5] = 0;
+    if (warp == 1) {
+      // new high-water mark of the item table: no row is allocated or freed after the cull
+      int hi = 0;
+      for (int w0 = 0; w0 < cap_words; w0 += 32) {
+        uint32_t u = w0 + lane < cap_words ? ctx.used[w0 + lane] : 0u;
+        unsigned nz = __ballot_sync(0xffffffffu, u != 0);
+        if (nz) { int top = 31 - __clz(nz); uint32_t ut = __shfl_sync(0xffffffffu, u, top); hi = ((w0 + top) << 5) + 32 - __clz(ut); }
+      }
+      if (lane == 0) ctx.sc[9] = (hi + 7) & ~7;
+    }
     __syncthreads();
     for (int q0 = 0; q0 < n_quads; q0 += T) {       // block-uniform trip count: the append below is warp-wide
       const int q = q0 + tid;
@@ -1555,6 +1582,12 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     int n = min(ctx.sc[5], wl_cap);
     for (int k = tid; k < n; k += T) { int i = wl[k]; respawn_tile(i, tile_i(ctx, i)); }
   }
+  // rows the table grew over this tick that are not in use must read as empty from now on
+  for (int r = item_hi0 + tid; r < ctx.sc[9]; r += T)
+    if (!row_used(ctx, r)) {
+#pragma unroll
+      for (int k = 0; k < IS_N; k++) ITM(k, r) = 0;
+    }
   // exchange.step: listings expire; only rows in use are visited (one bitmap word per thread)
   for (int w = tid; w < cap_words; w += T) {
     uint32_t bits = ctx.used[w];
@@ -1571,7 +1604,10 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   __syncthreads();
   if (tid == 0) {
     bulk_s2g(prm.ent + (size_t)env * EA_N * R, ctx.ent, ent_bytes);
-    bulk_s2g(prm.item + (size_t)env * IS_N * CAP, ctx.item, item_bytes);
+    const int hi = ctx.sc[9];
+    const uint32_t col_bytes = (uint32_t)hi * 2;
+    if (col_bytes)
+      for (int k = 0; k < IS_N; k++) bulk_s2g(gitem + (size_t)k * CAP, ctx.item + k * CAP, col_bytes);
     bulk_s2g(prm.map + (size_t)env * map_bytes, ctx.map, map_bytes);
     bulk_commit();
   }
@@ -1683,7 +1719,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   PCOUNT(27, n_alive); PCOUNT(28, n_dead);
   if (tid == 0) {
     gsc[SC_TICK] = ctx.tick; gsc[SC_DONE] = env_done ? 1 : 0; gsc[SC_N_DANGER] = ctx.sc[2]; gsc[SC_NEXT_NPC_ID] = ctx.sc[3];
-    gsc[SC_FRESH] = 0;
+    gsc[SC_FRESH] = 0; gsc[SC_ITEM_HI] = ctx.sc[9];
     if (ctx.sc[1]) { gsc[SC_ERROR] |= 1; atomicAdd(&prm.counters[3], 1ULL); }
     prm.episode_done[env] = env_done ? 1 : 0;
     atomicAdd(&prm.counters[0], (unsigned long long)P);
