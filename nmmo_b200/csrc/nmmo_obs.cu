@@ -364,11 +364,14 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
         int e0 = k * 8;
         uint4 v = zero4;
         if (e0 < n_el) {
+          // 8 consecutive int16 of the row-major [n_vis][31] block: at most one row change inside
+          int row = e0 / EA_N_OBS, col = e0 - row * EA_N_OBS;
+          int vr = s_vis[row], vr_next = row + 1 < n_vis ? (int)s_vis[row + 1] : -1;
           int vals[8];
 #pragma unroll
           for (int j = 0; j < 8; j++) {
-            int e = e0 + j, row = e / EA_N_OBS, col = e - row * EA_N_OBS;
-            vals[j] = e < n_el ? (int)OENT(col, s_vis[row]) : 0;
+            vals[j] = vr >= 0 ? (int)OENT(col, vr) : 0;
+            if (++col == EA_N_OBS) { col = 0; vr = vr_next; }
           }
           v = make_uint4(pack2(vals[0], vals[1]), pack2(vals[2], vals[3]), pack2(vals[4], vals[5]), pack2(vals[6], vals[7]));
         }

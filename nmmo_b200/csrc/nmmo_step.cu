@@ -1376,18 +1376,19 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     uint32_t *tbl = s_scratch;                               // 1024-slot position index
     uint16_t *mvd = s_mv, *res = s_mv + R;                   // intended destination, verdict / dependency
     for (int i = tid; i < 1024; i += T) tbl[i] = 0;
-    int mv_dir[2];
+    int mv_dir[2], mv_r[2], mv_c[2];                         // direction and destination (row, col)
 #pragma unroll
     for (int k = 0; k < 2; k++) {
       int r = tid + k * T;
-      mv_dir[k] = -1;
+      mv_dir[k] = -1; mv_r[k] = 0; mv_c[k] = 0;
       if (r < R) {
         uint32_t d = NONE;
         if (ent_alive(ctx, r)) {
           int dir = r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P];
           if (dir >= 0 && dir <= 3 && ENT(EA_FREEZE, r) == 0) {
-            int dst = (ENT(EA_ROW, r) + c_dir_dr[dir]) * S + ENT(EA_COL, r) + c_dir_dc[dir];
-            if (!nm_impassible(tile_i(ctx, dst))) { d = (uint32_t)dst; mv_dir[k] = dir; }
+            int nr = ENT(EA_ROW, r) + c_dir_dr[dir], nc = ENT(EA_COL, r) + c_dir_dc[dir];
+            int dst = nr * S + nc;
+            if (!nm_impassible(tile_i(ctx, dst))) { d = (uint32_t)dst; mv_dir[k] = dir; mv_r[k] = nr; mv_c[k] = nc; }
           }
         }
         mvd[r] = (uint16_t)d;
@@ -1415,8 +1416,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     for (int k = 0; k < 2; k++) {
       const int i = tid + k * T;
       if (mv_dir[k] < 0) { if (i < R) res[i] = (uint16_t)NONE; continue; }
-      const int d = mvd[i];
-      const int dr_ = d / S, dc_ = d - dr_ * S;
+      const int dr_ = mv_r[k], dc_ = mv_c[k], d = dr_ * S + dc_;
       int o = occ_get(ctx, dr_, dc_) ? who(d) : -1;
       uint32_t verdict = NODEP;
       int lo = -1;                                           // claimants in (lo, i) beat me
@@ -1450,14 +1450,12 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       }
       if (mv_ok[k]) occ_clr(ctx, ENT(EA_ROW, tid + k * T), ENT(EA_COL, tid + k * T));
     }
-    { int nmv = __syncthreads_count(mv_dir[0] >= 0) + __syncthreads_count(mv_dir[1] >= 0); PCOUNT(24, nmv); }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 2; k++)
       if (mv_ok[k]) {
-        const int i = tid + k * T, d = mvd[i];
-        occ_set(ctx, d / S, d - (d / S) * S);
-        act_move(ctx, i, mv_dir[k], false);
+        occ_set(ctx, mv_r[k], mv_c[k]);
+        act_move(ctx, tid + k * T, mv_dir[k], false);
       }
   }
   __syncthreads();
