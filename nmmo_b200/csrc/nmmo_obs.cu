@@ -75,7 +75,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   const int stage_bytes = nm_align16(L.m_end);
   uint8_t *s_stage_all = carve((size_t)NW * stage_bytes);
   uint16_t *s_vis_all = (uint16_t *)carve((size_t)NW * ((L.n_ent * 2 + 15) & ~15));
-  uint32_t *s_bits_all = (uint32_t *)carve((size_t)NW * 32 * 4);
+  uint32_t *s_bits_all = (uint32_t *)carve((size_t)NW * 72 * 4);   // per warp: 32 bitmap words + 33 running counts
   uint32_t *s_pos = (uint32_t *)carve((size_t)R * 4);       // (row+7)<<16 | (col+7) of alive rows
   uint8_t *s_tmpl = carve(stage_bytes);                      // agent-independent part of the masks
   int *s_head = (int *)carve((2 * AC_N + 2) * 4);       // + work-list length and cursor
@@ -318,12 +318,31 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     // The 946 mask bytes become 30 ballot words; lanes 0..11 then each resolve one head with
     // popc / __fns on those words.  Same draws as nmmo_sample_kernel.
     if (prm.sample_out) {
-      uint32_t *bits = s_bits_all + warp * 32;
+      uint32_t *bits = s_bits_all + warp * 72;
+      uint32_t *cum = bits + 32;             // cum[w] = set bits in words < w (fast path, n_words <= 32)
+      uint32_t my_word = 0;
       const int n_words = (L.m_end + 31) >> 5;
-      for (int wd = 0; wd < n_words; wd++) {
-        int i = wd * 32 + lane;
-        uint32_t b = __ballot_sync(0xffffffffu, i < L.m_end && m[i] != 0);
-        if (lane == wd) bits[wd] = b;
+      // lane w packs mask bytes [32w, 32w+32) into bitmap word w: two 16-byte loads, one multiply
+      // per four bytes (0/1 bytes -> nibble), no cross-lane traffic; bytes past m_end are template zeros
+      for (int wd = lane; wd < n_words; wd += 32) {
+        uint32_t wb = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int qi = wd * 2 + h;
+          const uint4 v = qi < stage_bytes / 16 ? ((const uint4 *)stage)[qi] : zero4;
+          const uint32_t n0 = ((v.x & 0x01010101u) * 0x01020408u) >> 24, n1 = ((v.y & 0x01010101u) * 0x01020408u) >> 24;
+          const uint32_t n2 = ((v.z & 0x01010101u) * 0x01020408u) >> 24, n3 = ((v.w & 0x01010101u) * 0x01020408u) >> 24;
+          wb |= ((n0 & 15u) | ((n1 & 15u) << 4) | ((n2 & 15u) << 8) | ((n3 & 15u) << 12)) << (16 * h);
+        }
+        bits[wd] = wb;
+        my_word = wb;
+      }
+      if (n_words <= 32) {
+        int pc = __popc(my_word), incl = pc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+        cum[lane] = (uint32_t)(incl - pc);
+        if (lane == 31) cum[32] = (uint32_t)incl;
       }
       __syncwarp();
       if (lane < AC_N) {
@@ -336,9 +355,22 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
           if (w == w1 && (o1 & 31)) x &= (1u << (o1 & 31)) - 1u;
           return x;
         };
+        int pick = 0;
+        if (n_words <= 32) {
+          // rank(x) = set bits below bit x of the bitmap: the head's count and the word holding the
+          // drawn entry come from the running counts, without walking the head's words
+          auto rank = [&](int x) -> int { int w = x >> 5; return (int)cum[w] + ((x & 31) ? __popc(bits[w] & ((1u << (x & 31)) - 1u)) : 0); };
+          const int rk0 = rank(o0), total = rank(o1) - rk0;
+          if (total > 0) {
+            const int t = rk0 + nm_bounded(nm_action_draw(base64, lane), total);
+            int lo = w0, hi = w1;
+            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((int)cum[mid] <= t) lo = mid; else hi = mid - 1; }
+            pick = lo * 32 + (int)__fns(bits[lo], 0, t - (int)cum[lo] + 1) - o0;
+          }
+          prm.sample_out[a * AC_N + lane] = pick;
+        } else {
         int total = 0;
         for (int w = w0; w <= w1; w++) if (bits[w]) total += __popc(word_at(w));
-        int pick = 0;
         if (total > 0) {
           int jj = nm_bounded(nm_action_draw(base64, lane), total);
           for (int w = w0; w <= w1; w++) {
@@ -350,6 +382,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
           }
         }
         prm.sample_out[a * AC_N + lane] = pick;
+        }
       }
       __syncwarp();
     }
