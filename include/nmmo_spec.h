@@ -87,7 +87,8 @@ enum nm_cfg {
   NC_EARLY_STOP_N,       /* early_stop_agent_num  config.yaml:100,138 */
   NC_EVAL_MODE, NC_USE_CUSTOM_REWARD,
   NC_CLIP_UNIQUE,        /* clip_unique_event 3 */
-  NC_DISABLE_GIVE,       /* takeru/reward_wrapper.py:31-35 */
+  NC_DISABLE_GIVE,       /* takeru/reward_wrapper.py:31-35, yaofeng/reward_wrapper.py:72-76 */
+  NC_NO_DANGEROUS_NPC,   /* donot_attack_dangerous_npc  yaofeng/reward_wrapper.py:78-81 */
   NC_ITEM_CAP,           /* item table rows = N_PLAYERS * N_INV */
   NC_COUNT
 };
@@ -96,10 +97,12 @@ enum nm_cfg {
 enum nm_fcfg {
   NF_EXPLORE_W = 0,      /* explore_bonus_weight  config.yaml:105,139 */
   NF_HEAL_W,             /* heal_bonus_weight     config.yaml:104 */
+  /* yaofeng/reward_wrapper.py:20-25, config.yaml:117-123 */
+  NF_HP_W, NF_EXP_W, NF_DEFENSE_W, NF_ATTACK_W, NF_GOLD_W, NF_BONUS_SCALE,
   NF_COUNT
 };
 
-enum nm_wrapper { NW_BASE = 0, NW_TAKERU = 1, NW_START_KIT = 2 };
+enum nm_wrapper { NW_BASE = 0, NW_TAKERU = 1, NW_START_KIT = 2, NW_YAOFENG = 3 };
 
 /* --------------------------------------------------------------- entity table ------- */
 /* Observed columns 0..30: EntityState [UPSTREAM nmmo/entity/entity.py]; the 31 names are
@@ -208,7 +211,8 @@ enum nm_stat {
   ST_REWARD_SIGNALS,                   /* Task.reward_signal_count */
   ST_TASK_DONE,                        /* Task.completed */
   ST_PREV_PRICE,                       /* start_kit/reward_wrapper.py:52,59 */
-  ST_N = 36
+  ST_Y_HP, ST_Y_EXP, ST_Y_DMG_INFLICTED, ST_Y_GOLD,   /* yaofeng/reward_wrapper.py:53-63 previous-tick values */
+  ST_N = 40
 };
 /* double accumulators per agent */
 enum nm_dstat { DS_CUM_REWARD = 0, DS_PROGRESS, DS_MAX_PROGRESS, DS_N };

@@ -46,7 +46,8 @@ def _parse_enums(text: str) -> Dict[str, int]:
 SPEC = _parse_enums(_SPEC.read_text())
 globals().update(SPEC)  # NC_*, EA_*, IA_*, ... as module attributes
 
-WRAPPERS = {"base": SPEC["NW_BASE"], "takeru": SPEC["NW_TAKERU"], "neurips23_start_kit": SPEC["NW_START_KIT"]}
+WRAPPERS = {"base": SPEC["NW_BASE"], "takeru": SPEC["NW_TAKERU"], "neurips23_start_kit": SPEC["NW_START_KIT"],
+            "yaofeng": SPEC["NW_YAOFENG"]}
 
 
 def default_exp_threshold(base_exp: int, max_level: int):
@@ -78,6 +79,9 @@ def default_wrapper_args(agent: str = "takeru", **over) -> Namespace:
         d.update(early_stop_agent_num=0, explore_bonus_weight=0.01, clip_unique_event=3, disable_give=True)
     elif agent == "neurips23_start_kit":
         d.update(heal_bonus_weight=0.03, explore_bonus_weight=0.01, clip_unique_event=3)
+    elif agent == "yaofeng":      # config.yaml:117-125; constructor defaults agent_zoo/yaofeng/reward_wrapper.py:13-29
+        d.update(hp_bonus_weight=0.03, exp_bonus_weight=0.002, defense_bonus_weight=0.04, attack_bonus_weight=0.0,
+                 gold_bonus_weight=0.001, custom_bonus_scale=0.1, disable_give=True, donot_attack_dangerous_npc=True)
     d.update(over)
     return Namespace(**d)
 
@@ -86,7 +90,7 @@ def make_config(env_args: Namespace = None, wrapper_args: Namespace = None, agen
                 **engine_over) -> Tuple[np.ndarray, np.ndarray]:
     """Build (cfg int32, fcfg float64).  ``engine_over`` overrides raw NC_* entries (tests)."""
     if env_args is None:
-        env_args = default_env_args(resilient_population=0 if agent == "takeru" else 0.2)
+        env_args = default_env_args(resilient_population=0 if agent in ("takeru", "yaofeng") else 0.2)
     if wrapper_args is None:
         wrapper_args = default_wrapper_args(agent)
     S = SPEC
@@ -156,6 +160,11 @@ def make_config(env_args: Namespace = None, wrapper_args: Namespace = None, agen
     c[S["NC_ITEM_CAP"]] = P * 12
     f[S["NF_EXPLORE_W"]] = float(getattr(wrapper_args, "explore_bonus_weight", 0.0))
     f[S["NF_HEAL_W"]] = float(getattr(wrapper_args, "heal_bonus_weight", 0.0))
+    c[S["NC_NO_DANGEROUS_NPC"]] = int(bool(getattr(wrapper_args, "donot_attack_dangerous_npc", False)))
+    for key, arg, dflt in (("NF_HP_W", "hp_bonus_weight", 0.0), ("NF_EXP_W", "exp_bonus_weight", 0.0),
+                           ("NF_DEFENSE_W", "defense_bonus_weight", 0.0), ("NF_ATTACK_W", "attack_bonus_weight", 0.0),
+                           ("NF_GOLD_W", "gold_bonus_weight", 0.0), ("NF_BONUS_SCALE", "custom_bonus_scale", 1.0)):
+        f[S[key]] = float(getattr(wrapper_args, arg, dflt))
     for k, v in engine_over.items():
         c[S[k]] = v
     c[S["NC_MAP_SIZE"]] = c[S["NC_MAP_CENTER"]] + 2 * c[S["NC_MAP_BORDER"]]

@@ -118,7 +118,8 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   o.gitem = prm.item + (size_t)env * IS_N * CAP;
   o.ent = s_ent; o.status = s_status; o.item = s_item; o.map = s_map;
   const int wrapper = c[NC_WRAPPER];
-  const bool no_give = wrapper == NW_TAKERU && c[NC_DISABLE_GIVE];
+  const bool no_give = (wrapper == NW_TAKERU || wrapper == NW_YAOFENG) && c[NC_DISABLE_GIVE];
+  const bool no_danger = wrapper == NW_YAOFENG && c[NC_NO_DANGEROUS_NPC];      // yaofeng/reward_wrapper.py:78-81
   // one word per table row for the vision-window scan: an empty row can never match
   for (int r = tid; r < R; r += T)
     s_pos[r] = s_status[r] == ES_ALIVE ? (((uint32_t)(OENT(EA_ROW, r) + vis) << 16) | (uint32_t)(OENT(EA_COL, r) + vis)) : 0x7fff7fffu;
@@ -267,7 +268,9 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
         int row = s_vis[i], id = OENT(EA_ID, row);
         bool same = OENT(EA_ROW, row) == r0 && OENT(EA_COL, row) == c0;
         bool ok = nm_linf(OENT(EA_ROW, row), OENT(EA_COL, row), r0, c0) <= c[NC_REACH] && id != my_id && !(immune && id > 0);
-        m[L.m_target + i] = ok; any |= ok;
+        any |= ok;                                   // the no-op entry is the engine's, before the wrapper edit
+        if (no_danger && OENT(EA_NPC_TYPE, row) > 1) ok = false;
+        m[L.m_target + i] = ok;
         if (!no_give) {     // takeru's RewardWrapper.observation zeroes these anyway (reward_wrapper.py:31-35)
           bool give = n_inv > 0 && same && OENT(EA_NPC_TYPE, row) == 0 && id != my_id;
           m[L.m_give_target + i] = give; m[L.m_gold_target + i] = give;

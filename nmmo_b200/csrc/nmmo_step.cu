@@ -905,7 +905,7 @@ __device__ __noinline__ void reset_env(const NmParams &P_, int env, uint64_t see
     uint32_t *u = P_.uniq + (size_t)env * P * NM_UNIQ_WORDS;
     for (int i = tid; i < P * NM_UNIQ_WORDS; i += T) u[i] = 0;
     int32_t *st = P_.stats + (size_t)env * P * ST_N;
-    for (int i = tid; i < P * ST_N; i += T) { int k = i % ST_N; st[i] = (k >= ST_MAXLVL_ARMOR && k <= ST_MAXLVL_CONSUMABLE) ? -1 : 0; }
+    for (int i = tid; i < P * ST_N; i += T) { int k = i % ST_N; st[i] = (k >= ST_MAXLVL_ARMOR && k <= ST_MAXLVL_CONSUMABLE) ? -1 : (k == ST_Y_HP ? 100 : 0); }
     double *ds = P_.dstats + (size_t)env * P * DS_N;
     for (int i = tid; i < P * DS_N; i += T) ds[i] = 0.0;
   }
@@ -1707,6 +1707,26 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
           double heal = 0.0;
           if (prm.fcfg[NF_HEAL_W] > 0 && st == ES_ALIVE && ENT(EA_HEALTH_RESTORE, p) > 0) heal = prm.fcfg[NF_HEAL_W];
           reward += heal + explore;
+        } else if (c[NC_WRAPPER] == NW_YAOFENG) {
+          // yaofeng/reward_wrapper.py:85-129: deltas of hp / best skill exp / damage inflicted / gold since the
+          // agent's previous tick plus the equipment defense term, in the reference's operation order
+          // (explicit round-to-nearest multiplies and adds: no fused multiply-add)
+          if (!(terminated || truncated)) {
+            const int hp = ENT(EA_HEALTH, p), gold = ENT(EA_GOLD, p), dmg = ENT(EA_DMG_INFLICTED, p);
+            int cur_exp = 0;
+            for (int col = EA_MELEE_EXP; col <= EA_ALCHEMY_EXP; col += 2) cur_exp = max(cur_exp, (int)ENT(col, p));
+            int def3 = 0;
+            for (int s2 = EA_EQ_HAT; s2 <= EA_EQ_AMMO; s2++) { int it = ENT(s2, p); if (it) def3 += 3 * item_defense(c, ITM(IS_TYPE, it - 1), ITM(IS_LEVEL, it - 1)); }
+            const double hp_bonus = __dmul_rn((double)(hp - my_sta[ST_Y_HP]), prm.fcfg[NF_HP_W]);
+            const double exp_bonus = __dmul_rn((double)(cur_exp - my_sta[ST_Y_EXP]), prm.fcfg[NF_EXP_W]);
+            const double defense_bonus = __dmul_rn(prm.fcfg[NF_DEFENSE_W], __ddiv_rn((double)def3, 45.0));
+            const double attack_bonus = __dmul_rn((double)(dmg - my_sta[ST_Y_DMG_INFLICTED]), prm.fcfg[NF_ATTACK_W]);
+            const double gold_bonus = __dmul_rn((double)(gold - my_sta[ST_Y_GOLD]), prm.fcfg[NF_GOLD_W]);
+            my_sta[ST_Y_HP] = hp; my_sta[ST_Y_EXP] = cur_exp; my_sta[ST_Y_DMG_INFLICTED] = dmg; my_sta[ST_Y_GOLD] = gold;
+            double sum = __dadd_rn(hp_bonus, exp_bonus);
+            sum = __dadd_rn(sum, defense_bonus); sum = __dadd_rn(sum, attack_bonus); sum = __dadd_rn(sum, gold_bonus);
+            reward = __dadd_rn(reward, __dmul_rn(sum, prm.fcfg[NF_BONUS_SCALE]));
+          }
         }
       } else if (terminated) reward = 0.0;
       rew = (float)reward; term = terminated; trunc = truncated;

@@ -6,6 +6,7 @@ What is pinned.  The reference's stat / reward wrapper stack
                                                 process_event_log, count_unique_events
     agent_zoo/takeru/reward_wrapper.py          RewardWrapper.observation / reward_terminated_truncated_info
     agent_zoo/neurips23_start_kit/reward_wrapper.py   same + RewardWrapper.action
+    agent_zoo/yaofeng/reward_wrapper.py         same (hp / exp / defense / attack / gold bonuses, dangerous-NPC mask)
 is imported UNMODIFIED from /root/reference (only the missing third-party modules pettingzoo and
 nmmo are replaced by minimal stubs: a BaseParallelWrapper that stores `env`, the EventCode
 constants, the item class lists) and driven through whole episodes by a fake `nmmo.Env` that
@@ -81,6 +82,10 @@ def install_stubs():
     sys.modules["pettingzoo.utils.wrappers.base_parallel"].BaseParallelWrapper = BaseParallelWrapper
     nmmo = mod("nmmo"); lib = mod("nmmo.lib"); ec = mod("nmmo.lib.event_code"); systems = mod("nmmo.systems"); item = mod("nmmo.systems.item")
     nmmo.lib = lib; lib.event_code = ec; nmmo.systems = systems; systems.item = item
+    entity = mod("nmmo.entity"); ent_entity = mod("nmmo.entity.entity"); nmmo.entity = entity; entity.entity = ent_entity
+    # EntityState.State.attr_name_to_col (yaofeng/reward_wrapper.py:7): observed column order of include/nmmo_spec.h
+    cols = {k[3:].lower(): v for k, v in SPEC.items() if k.startswith("EA_") and isinstance(v, int) and v < SPEC["EA_N_OBS"] and k != "EA_N_OBS"}
+    ent_entity.EntityState = type("EntityState", (), {"State": type("State", (), {"attr_name_to_col": cols})})
     ec.EventCode = type("EventCode", (), {k[3:]: v for k, v in SPEC.items() if k.startswith("EV_")})
 
     def cls(name):
@@ -108,6 +113,12 @@ class FakePlayer:
         for name in ("prospecting", "carving", "alchemy", "fishing", "herbalism"):
             setattr(self, name + "_level", _Val(row[S["EA_" + name.upper() + "_LEVEL"]]))
         self.resources = Namespace(health_restore=int(row[S["EA_HEALTH_RESTORE"]]))
+        # read by agent_zoo/yaofeng/reward_wrapper.py:88-121
+        self.health = _Val(row[S["EA_HEALTH"]]); self.gold = _Val(row[S["EA_GOLD"]])
+        for name in ("melee", "range", "mage", "fishing", "herbalism", "prospecting", "carving", "alchemy"):
+            setattr(self, name + "_exp", _Val(row[S["EA_" + name.upper() + "_EXP"]]))
+        self.history = Namespace(damage_received=int(row[S["EA_DMG_RECEIVED"]]), damage_inflicted=int(row[S["EA_DMG_INFLICTED"]]))
+        self.inventory = None      # filled in by FakeEnv._sync (needs the item table)
 
 
 class FakePlayers(dict):
@@ -158,11 +169,29 @@ class FakeEnv:
             out.setdefault(a, {})[b] = rec[o:o + n].copy().view(np.int8)
         return out
 
+    def _obs(self, p):
+        """The parts of the engine observation the wrappers read: ActionTargets and the Entity block."""
+        rec = self.raw.obs[p]
+        ent = rec[self.L.o_entity:self.L.o_entity + self.L.n_ent * 62].copy().view(np.int16).reshape(self.L.n_ent, 31)
+        return {"ActionTargets": self._masks(p), "Entity": ent}
+
     def _sync(self):
         ent, _, _ = self.oracle.snapshot()
         st = ent[:self.P, SPEC["EA_STATUS"]]
         self.realm.tick = self.oracle.tick
+        ent, items, _ = self.oracle.snapshot()
         self.realm.players = FakePlayers({p + 1: FakePlayer(ent[p]) for p in range(self.P) if st[p] == 1})
+        for a, pl in self.realm.players.items():      # Equipment.{melee,range,mage}_defense: sums over equipped items
+            d = 0
+            for col in ("EA_EQ_HAT", "EA_EQ_TOP", "EA_EQ_BOTTOM", "EA_EQ_HELD", "EA_EQ_AMMO"):
+                it = int(ent[a - 1][SPEC[col]])
+                if it:
+                    typ, lvl = int(items[it - 1][SPEC["IS_TYPE"]]), int(items[it - 1][SPEC["IS_LEVEL"]])
+                    if SPEC["IT_HAT"] <= typ <= SPEC["IT_BOTTOM"]:
+                        d += int(self.cfg[SPEC["NC_ARMOR_BASE"]]) + lvl * int(self.cfg[SPEC["NC_ARMOR_LEVEL"]])
+                    elif SPEC["IT_ROD"] <= typ <= SPEC["IT_CHISEL"]:
+                        d += int(self.cfg[SPEC["NC_TOOL_BASE"]]) + lvl * int(self.cfg[SPEC["NC_TOOL_LEVEL"]])
+            pl.inventory = Namespace(equipment=Namespace(melee_defense=d, range_defense=d, mage_defense=d))
         self.realm.players.dead_this_tick = {p + 1: FakePlayer(ent[p]) for p in range(self.P) if st[p] == 2}
         tid, comp, sig, mp = self.oracle.task_state()
         self.agent_task_map = {p + 1: [FakeTask(comp[p], sig[p], mp[p], tid[p])] for p in range(self.P)}
@@ -171,7 +200,7 @@ class FakeEnv:
     def reset(self, **kw):
         st = self._sync()
         self.agents = [p + 1 for p in range(self.P) if st[p] == 1]
-        return {a: {"ActionTargets": self._masks(a - 1)} for a in self.agents}, {a: {} for a in self.agents}
+        return {a: self._obs(a - 1) for a in self.agents}, {a: {} for a in self.agents}
 
     def step(self, action):
         flat = self.actions[self.t]
@@ -184,7 +213,7 @@ class FakeEnv:
         horizon = self.realm.tick >= int(self.cfg[SPEC["NC_HORIZON"]])
         current = [p + 1 for p in range(self.P) if st[p] in (1, 2)]
         env_rew = self.oracle.env_rewards
-        obs = {a: {"ActionTargets": self._masks(a - 1)} for a in current}
+        obs = {a: self._obs(a - 1) for a in current}
         rewards = {a: float(env_rew[a - 1]) for a in current}
         terms = {a: bool(st[a - 1] == 2) for a in current}
         truncs = {a: bool(horizon and st[a - 1] == 1) for a in current}
@@ -223,7 +252,7 @@ def run_case(name, agent, ticks, seed, wrapper_over=None, **engine_over):
     T = len(actions)
     # pass 2: the reference wrapper on top of the replayed trajectory
     oracle.reset(seed); raw.reset(seed)
-    if agent in ("takeru", "neurips23_start_kit"):
+    if agent in ("takeru", "neurips23_start_kit", "yaofeng"):
         # the module file itself, unmodified; loaded by path because the package __init__ also
         # imports the policy (pufferlib), which is irrelevant here
         import importlib.util
@@ -288,6 +317,9 @@ def main():
     run_case("start_kit_small", "neurips23_start_kit", 140, 5, NC_HORIZON=100, NC_RES_DEPLETION=2, NC_SPAWN_IMMUNITY=3)
     run_case("takeru_eval_nocustom", "takeru", 90, 7, wrapper_over={"eval_mode": True, "use_custom_reward": False, "early_stop_agent_num": 4},
              NC_HORIZON=80, NC_RES_DEPLETION=3)
+    # slow starvation + fast item drops: combat, equipment (defense bonus), gold and exp all move
+    run_case("yaofeng_small", "yaofeng", 200, 9, wrapper_over={"attack_bonus_weight": 0.005, "early_stop_agent_num": 2},
+             NC_HORIZON=180, NC_RES_DEPLETION=1, NC_SPAWN_IMMUNITY=3, NC_WEAPON_DROP_THR=1 << 30)
 
 
 if __name__ == "__main__":

@@ -42,6 +42,16 @@ def test_allow_occupied_start_kit():
     sim.close()
 
 
+def test_yaofeng_wrapper():
+    # agent_zoo/yaofeng/reward_wrapper.py on the device: bonus terms and the dangerous-NPC target mask
+    world = build_world(agent="yaofeng", task_dim=64, wrapper_over={"attack_bonus_weight": 0.005, "early_stop_agent_num": 2},
+                        **SMALL, NC_HORIZON=200, NC_RES_DEPLETION=1, NC_SPAWN_IMMUNITY=3, NC_WEAPON_DROP_THR=1 << 30)
+    sim, oracles = _make(world, 4)
+    stats = run_parity(sim, oracles, seeds=np.arange(4) + 21, ticks=220)
+    assert stats["infos"] > 0
+    sim.close()
+
+
 def test_default_config_full_size():
     world = build_world()
     sim, oracles = _make(world, 3)

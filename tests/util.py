@@ -12,7 +12,7 @@ SMALL = dict(NC_N_PLAYERS=16, NC_N_NPCS=32, NC_MAP_CENTER=32)
 
 def build_world(agent="takeru", n_maps=4, map_seed=7, task_dim=None, env_over=None, wrapper_over=None, **engine_over):
     from nmmo_b200.config import default_env_args, default_wrapper_args
-    env_args = default_env_args(resilient_population=0 if agent == "takeru" else 0.2, **(env_over or {}))
+    env_args = default_env_args(resilient_population=0 if agent in ("takeru", "yaofeng") else 0.2, **(env_over or {}))
     if task_dim is not None:
         env_args.task_size = task_dim
     wrap = default_wrapper_args(agent, **(wrapper_over or {}))
