@@ -113,10 +113,42 @@ int nmmo_timing_read(nmmo_handle *h, double *step_ms, double *obs_ms, int *n_lau
  * what HBM already holds (records persist across ticks); 1 rewrites all bytes of all records. */
 int nmmo_set_obs_full(nmmo_handle *h, int full);
 
-/* Development aid: per-phase SM-clock profile of the step kernel (32 counters). */
-int nmmo_profile(nmmo_handle *h, int enable, unsigned long long *out32);
+/* Development aid: per-phase SM-clock profiles (64 counters: 0..31 step kernel, 32..63 observation kernel). */
+int nmmo_profile(nmmo_handle *h, int enable, unsigned long long *out64);
 
 const char *nmmo_last_error(void);
+
+/* ------------------------------------------------------------------ rollout storage + GAE ----
+ * Device-resident replacement of the trainer-side rollout arrays.
+ * Replaces: clean_pufferl.py:183-197 (the batch_size + 1 row arrays), :329-346 (masked append of
+ * one recv() and `sort_keys.extend((env_id, step))`), :413-414 (sort by (env_id, step)) and
+ * :424-436 (the GAE loop).  All data pointers are DEVICE pointers; nothing is copied to the host. */
+typedef struct nmmo_rollout nmmo_rollout;
+enum nm_rollout_buffer {     /* nmmo_rollout_buffer(which): rows = batch_size + 1 */
+  NM_RB_OBS = 0,             /* uint8 [rows][obs_stride] */
+  NM_RB_ACTIONS,             /* int32 [rows][12] */
+  NM_RB_LOGPROBS, NM_RB_REWARDS, NM_RB_DONES, NM_RB_VALUES,   /* float32 [rows] */
+  NM_RB_SLOT, NM_RB_STEP,    /* int32 [rows]: the sort key (env_id of the agent slot, step) */
+  NM_RB_IDXS,                /* int32 [rows]: sample indices sorted by (slot, step)  (clean_pufferl.py:413) */
+  NM_RB_ADVANTAGES           /* float32 [rows]: advantages[t] for t < ptr - 1, in sorted order (:424-436) */
+};
+int nmmo_rollout_create(int device, int batch_size, int n_slots, int obs_stride, nmmo_rollout **out);
+int nmmo_rollout_destroy(nmmo_rollout *r);
+/* ptr = 0, sort keys cleared (clean_pufferl.py:278, :414). */
+int nmmo_rollout_reset(nmmo_rollout *r, void *stream);
+/* Append the rows i of one step with mask[i] != 0 (and learner_mask[i] != 0 when given), in slot
+ * order, up to the capacity (`indices = where(...)[: batch_size - ptr + 1]`, clean_pufferl.py:333-348).
+ * obs uint8 [n_slots][obs_stride], actions int32 [n_slots][12], logprob/value/reward/done float32 [n_slots],
+ * masks uint8 [n_slots]; `step` is the loop counter of clean_pufferl.py:281. */
+int nmmo_rollout_store(nmmo_rollout *r, const uint8_t *obs, const int32_t *actions, const float *logprob,
+                       const float *value, const float *reward, const float *done, const uint8_t *mask,
+                       const uint8_t *learner_mask, int step, void *stream);
+/* Rows stored so far (synchronises `stream`). */
+int nmmo_rollout_ptr(nmmo_rollout *r, void *stream, int *ptr_out);
+/* Sorted order + advantages of the stored rows; float32 arithmetic of the reference in its order. */
+int nmmo_rollout_gae(nmmo_rollout *r, double gamma, double gae_lambda, void *stream);
+void *nmmo_rollout_buffer(nmmo_rollout *r, int which);
+const char *nmmo_rollout_last_error(void);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@
 // unity build: the kernels live in their own files but compile into this translation unit
 #include "nmmo_step.cu"
 #include "nmmo_obs.cu"
+#include "nmmo_rollout.cu"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }

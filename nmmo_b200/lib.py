@@ -22,6 +22,8 @@ EXPORTS = [
     "nmmo_info_ptr", "nmmo_info_valid_ptr", "nmmo_episode_done_ptr", "nmmo_obs_stride", "nmmo_num_envs",
     "nmmo_num_agents", "nmmo_inject_rng", "nmmo_snapshot", "nmmo_stats", "nmmo_timing", "nmmo_timing_read", "nmmo_profile", "nmmo_set_obs_full", "nmmo_set_autosample",
     "nmmo_last_error",
+    "nmmo_rollout_create", "nmmo_rollout_destroy", "nmmo_rollout_reset", "nmmo_rollout_store", "nmmo_rollout_ptr",
+    "nmmo_rollout_gae", "nmmo_rollout_buffer", "nmmo_rollout_last_error",
 ]
 
 
@@ -80,6 +82,20 @@ def load(build_if_missing: bool = True):
     L.nmmo_profile.restype = C.c_int
     L.nmmo_profile.argtypes = [vp, C.c_int, vp]
     L.nmmo_last_error.restype = C.c_char_p
+    L.nmmo_rollout_create.restype = C.c_int
+    L.nmmo_rollout_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.nmmo_rollout_destroy.argtypes = [vp]
+    L.nmmo_rollout_reset.restype = C.c_int
+    L.nmmo_rollout_reset.argtypes = [vp, vp]
+    L.nmmo_rollout_store.restype = C.c_int
+    L.nmmo_rollout_store.argtypes = [vp] + [vp] * 8 + [C.c_int, vp]
+    L.nmmo_rollout_ptr.restype = C.c_int
+    L.nmmo_rollout_ptr.argtypes = [vp, vp, C.POINTER(C.c_int)]
+    L.nmmo_rollout_gae.restype = C.c_int
+    L.nmmo_rollout_gae.argtypes = [vp, C.c_double, C.c_double, vp]
+    L.nmmo_rollout_buffer.restype = vp
+    L.nmmo_rollout_buffer.argtypes = [vp, C.c_int]
+    L.nmmo_rollout_last_error.restype = C.c_char_p
     _lib = L
     return L
 
