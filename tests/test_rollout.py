@@ -125,3 +125,43 @@ def test_rollout_from_simulator_records():
         sim.step()
     assert stored == 601
     roll.close(); sim.close()
+
+
+@pytest.mark.gpu
+def test_device_evaluate_loop():
+    """clean_pufferl.evaluate's loop body on the device (nmmo_b200/evaluate.py): policy reads obs and masks on the
+    GPU, the batch is stored and sorted there, the reference's counters come out right."""
+    import sys
+    import torch
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "examples"))
+    from argparse import Namespace
+    from device_rollout import SmallPolicy
+    from nmmo_b200.evaluate import evaluate
+    from nmmo_b200.rollout import DeviceRollout
+    from nmmo_b200.vecenv import B200VecEnv
+    env_ns = Namespace(num_agents=16, num_npcs=32, max_episode_length=64, maps_path="maps/", map_size=32, num_maps=4,
+                       map_force_generation=False, death_fog_tick=None, task_size=64, spawn_immunity=3, resilient_population=0,
+                       curriculum_file_path=None)
+    pool = B200VecEnv(env_kwargs={"env": env_ns}, num_envs=8, agent="takeru")
+    torch.manual_seed(0)
+    policy = SmallPolicy(pool.driver_env, hidden=32).cuda()
+    n = 8 * 16
+    roll = DeviceRollout(700, n, pool.driver_env.obs_sz)
+    pool.async_reset(3)
+    res = evaluate(pool, policy, roll)
+    assert roll.ptr == 701 and res.global_steps == res.steps * n and 701 <= res.agent_steps <= res.global_steps
+    # keys are (slot, step) with step ascending per slot; the sorted order groups slots
+    idxs, adv = roll.gae(0.99, 0.95)
+    torch.cuda.synchronize()
+    slot = roll.slot[:701][idxs[:701].long()].cpu().numpy(); st = roll.step[:701][idxs[:701].long()].cpu().numpy()
+    key = slot.astype(np.int64) * 100000 + st
+    assert np.all(np.diff(key) > 0), "sorted by (slot, step), no duplicates"
+    assert torch.isfinite(adv[:700]).all()
+    # stored actions were valid under the stored masks
+    from nmmo_b200.emulation import unpack_batched_obs
+    x = unpack_batched_obs(roll.obs[:701], pool.driver_env.unflatten_context)
+    for k, path in enumerate(pool.driver_env.unflatten_context.layout.masks):
+        a, b = path.split(".")
+        m = x["ActionTargets"][a][b]
+        assert bool((m[torch.arange(701, device="cuda"), roll.actions[:701, k].long()] == 1).all()), path
+    pool.close(); roll.close()
