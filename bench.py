@@ -247,6 +247,17 @@ def run_native(args):
         # bytes the observation kernel has to move per launch: the env state it reads plus the record
         # bytes that can differ from the record already in HBM, counted by the kernel itself
         obs_bytes_launch = float(g_counters[4]) / max(1, world_size * args.steps)
+        # DRAM traffic of the same kernels from the committed ncu --set full captures (profiles/<tag>_traffic.json,
+        # written by tools/summarize_ncu.py from the .ncu-rep of tools/ncu_round.sh); null when none is committed
+        traffic, traffic_dense, traffic_src = None, None, None
+        try:
+            tf = sorted((ROOT / "profiles").glob("*_traffic.json"))[-1]
+            tj = json.loads(tf.read_text())
+            traffic = tj.get("tick40:nmmo_obs_kernel", {}).get("dram_bytes")
+            traffic_dense = tj.get("dense:nmmo_obs_kernel", {}).get("dram_bytes")
+            traffic_src = f"profiles/{tf.name} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum; incremental capture taken at tick ~40)"
+        except Exception:  # noqa: BLE001
+            pass
         obs_gbs = obs_bytes_launch / (obs_ms * 1e-3) / 1e9
         dense_gbs = n * b_obs / (obs_ms_dense * 1e-3) / 1e9
         line = {
@@ -262,11 +273,11 @@ def run_native(args):
             "alive_fraction": float(g_counters[1]) / max(1.0, float(g_counters[0])),
             "kernels_ms": {"step_kernel": step_ms, "obs_kernel": obs_ms, "launches_timed": n_timed},
             "roofline": {"bound": "hbm", "kernel": "nmmo_obs_kernel", "achieved": obs_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": obs_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": obs_gbs / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "alg_bytes_per_launch": obs_bytes_launch,
                          "note": "incremental writer: algorithmic bytes = env state read + record bytes that changed (counted in-kernel)",
                          "dense_mode": {"achieved": dense_gbs, "frac": dense_gbs / peak, "ms": obs_ms_dense,
-                                        "alg_bytes_per_launch": n * b_obs,
+                                        "alg_bytes_per_launch": n * b_obs, "traffic": traffic_dense,
                                         "what": "same kernel with obs_full=1: all 25 KB of all records rewritten every tick"},
                          "dense_equivalent_gbs": n * b_obs / (obs_ms * 1e-3) / 1e9},
             "e2e": {"value": world_size * n * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
