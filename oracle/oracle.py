@@ -60,6 +60,7 @@ def lib():
         L.oracle_task_state.argtypes = [vp, vp, vp, vp, vp]
         L.oracle_step_many.argtypes = [vp, C.c_int, vp]
         L.oracle_sample_many.argtypes = [vp, C.c_int, C.c_uint64, vp]
+        L.oracle_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -199,7 +200,7 @@ class OracleBatch:
         self.ptrs = (C.c_void_p * n_envs)(*[e.h for e in self.envs])
         self.actions = np.zeros((n_envs, self.P, 12), np.int32)
         self.threads = threads or len(os.sched_getaffinity(0))
-        os.environ.setdefault("OMP_NUM_THREADS", str(self.threads))
+        lib().oracle_set_threads(int(self.threads))      # not the environment: torchrun exports OMP_NUM_THREADS=1
 
     def reset(self, seeds):
         for e, s in zip(self.envs, seeds):
