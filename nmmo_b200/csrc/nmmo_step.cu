@@ -1321,20 +1321,26 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     PCOUNT(22, na);
     while (pending) {
       PCOUNT(23, 1);
+      long long ta0 = clock64();
       for (int r = tid; r < R; r += T) s_first[r] = 0x7fffffff;
       if (tid == 0) ctx.sc[7] = 0x7fffffff;
       __syncthreads();
-      for (int i = tid; i < na; i += T) {
+      long long ta1 = clock64();
+      int my_low = 0x7fffffff;
+      for (int i = lane * (T >> 5) + warp; i < na; i += T) {
         uint32_t x = s_att[i];
         if (x == DONE) continue;
         atomicMin(&s_first[x >> 16], i);
         atomicMin(&s_first[x & 0xffff], i);
-        atomicMin(&ctx.sc[7], i);
+        my_low = min(my_low, i);
       }
+      my_low = __reduce_min_sync(0xffffffffu, my_low);       // one shared-memory atomic per warp, not per attack
+      if (lane == 0 && my_low != 0x7fffffff) atomicMin(&ctx.sc[7], my_low);
       __syncthreads();
+      long long ta2 = clock64();
       const int lowest = ctx.sc[7];
       int still = 0;
-      for (int i = tid; i < na; i += T) {
+      for (int i = lane * (T >> 5) + warp; i < na; i += T) {
         uint32_t x = s_att[i];
         if (x == DONE) continue;
         int a = x >> 16, t = x & 0xffff;
@@ -1354,6 +1360,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
         if (done) s_att[i] = DONE; else still = 1;
       }
       pending = __syncthreads_or(still);
+      PCOUNT(44, ta1 - ta0); PCOUNT(45, ta2 - ta1); PCOUNT(46, clock64() - ta2);
     }
   }
   __syncthreads();
@@ -1622,15 +1629,23 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   int st_me = tid < P ? (int)ENT(EA_STATUS, tid) : ES_EMPTY;
   // window-scan predicates (CanSeeTile / CanSeeAgent / CanSeeGroup) are evaluated by a whole warp
   // per requesting agent instead of a 225- or 384-iteration loop in one lane
-  if (tid < P) {
-    bool req = st_me == ES_ALIVE && !my_done && (my_t[0] == TP_CAN_SEE_TILE || my_t[0] == TP_CAN_SEE_AGENT || my_t[0] == TP_CAN_SEE_GROUP);
-    ctx.slow[tid] = req ? (int8_t)-2 : (int8_t)-1;
+  // requesting agents are gathered into a list (s_list is idle here) that all warps share out
+  if (tid == 0) ctx.sc[18] = 0;
+  __syncthreads();
+  {
+    bool req = tid < P && st_me == ES_ALIVE && !my_done && (my_t[0] == TP_CAN_SEE_TILE || my_t[0] == TP_CAN_SEE_AGENT || my_t[0] == TP_CAN_SEE_GROUP);
+    if (tid < P) ctx.slow[tid] = (int8_t)-1;
+    unsigned rm = __ballot_sync(0xffffffffu, req);
+    int wbase = 0;
+    if (lane == 0 && rm) wbase = atomicAdd(&ctx.sc[18], __popc(rm));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (req) s_list[wbase + __popc(rm & ((1u << lane) - 1))] = tid;
   }
   __syncthreads();
-  for (int pb = warp * 32; pb < P; pb += T) {
-    unsigned reqm = __ballot_sync(0xffffffffu, pb + lane < P && ctx.slow[pb + lane] == -2);
-  while (reqm) {
-    const int p = pb + __ffs(reqm) - 1; reqm &= reqm - 1;
+  {
+  const int n_req = ctx.sc[18];
+  for (int qi = warp; qi < n_req; qi += (T >> 5)) {
+    const int p = s_list[qi];
     int pred = ctx.task[p * 4], q0 = ctx.task[p * 4 + 1], q1 = ctx.task[p * 4 + 2];
     int r = ENT(EA_ROW, p), cc = ENT(EA_COL, p), vis = c[NC_VISION];
     bool hit = false;

@@ -33,6 +33,7 @@ for n, v in zip(NAMES, out):
 print("total cycles/env-tick", tot / (E * ticks))
 print("obs kernel (warp 0 timeline): load %.0f, lists %.0f, market %.0f, worklist %.0f, records(warp0) %.0f; work items %.2f; mean warp busy in record loop %.0f cycles" % (
     *(raw[32:37] / (E * ticks)), raw[37] / (E * ticks), raw[40] / (E * ticks * 8)))
+print("attack round parts (cycles/env-tick): clear %.0f, register %.0f, apply %.0f" % tuple(raw[44:47] / (E * ticks)))
 dep = []
 for e in (0, 1, 2, 3):
     ent, items, mp, sc = sim.snapshot(e)
