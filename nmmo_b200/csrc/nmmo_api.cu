@@ -96,7 +96,11 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   nm_obs_layout_init(p.cfg, &p.L);
   p.E = n_envs; p.P = cfg[NC_N_PLAYERS]; p.N = cfg[NC_N_NPCS]; p.R = p.P + p.N; p.S = cfg[NC_MAP_SIZE]; p.CAP = cfg[NC_ITEM_CAP];
   p.n_maps = n_maps; p.n_tasks = n_tasks; p.env_base = env_base;
-  p.ICAP = std::min(p.CAP, 512);      // item rows kept in shared memory; rows beyond are used in HBM
+  p.ICAP = std::min(p.CAP, 512);      // item rows the observation kernel keeps in shared memory; rows beyond are read in HBM
+  if (const char *ov = getenv("NMMO_B200_ICAP")) {      // test hook: force the HBM tail path with a tiny staged prefix
+    int v = atoi(ov);
+    if (v >= 8 && v % 8 == 0) p.ICAP = std::min(p.CAP, v);
+  }
   if (p.P <= 0 || p.P > NM_STEP_THREADS) { delete h; return fail(NM_ERR_LIMIT, "PLAYER_N must be in 1..256 for the per-env CTA design"); }
   if (p.R % 8 || p.CAP % 8 || (p.S * p.S) % 32) { delete h; return fail(NM_ERR_LIMIT, "P+N and item cap must be multiples of 8, S*S of 32 (bulk copies)"); }
   if (p.R > 2 * NM_STEP_THREADS) { delete h; return fail(NM_ERR_LIMIT, "P+N must be <= 512 for the per-env CTA design"); }

@@ -52,6 +52,66 @@ def test_yaofeng_wrapper():
     sim.close()
 
 
+def _dims(cfg):
+    from nmmo_b200.config import ObsLayout
+    return np.array(ObsLayout(cfg).action_dims)
+
+
+def test_adversarial_actions():
+    # actions ignore the masks: every head uniform over [-2, width + 2) -- invalid targets, items the agent does
+    # not own, out-of-range and negative indices.  Validation must reject exactly what the oracle rejects.
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=120, NC_RES_DEPLETION=1, NC_SPAWN_IMMUNITY=2, NC_WEAPON_DROP_THR=1 << 30)
+    sim, oracles = _make(world, 4)
+    dims = _dims(world[0])
+    rng = np.random.default_rng(5)
+
+    def act(t, obs):
+        return rng.integers(-2, dims[None, None, :] + 2, size=(4, sim.P, 12))
+
+    stats = run_parity(sim, oracles, seeds=np.arange(4) + 31, ticks=125, action_fn=act)
+    assert stats["episodes_done"] >= 1
+    sim.close()
+
+
+def test_collision_heavy_moves():
+    # config 5 in miniature: a 16x16 arena packed with 24 players and 48 NPCs that (almost) always move --
+    # long follow-the-leader chains, four-way contention for one tile, swaps
+    world = build_world(task_dim=64, NC_N_PLAYERS=24, NC_N_NPCS=48, NC_MAP_CENTER=16, NC_HORIZON=90, NC_RES_DEPLETION=1,
+                        NC_SPAWN_IMMUNITY=200)
+    sim, oracles = _make(world, 6)
+    L_move = 8
+    rng = np.random.default_rng(9)
+
+    def act(t, obs):
+        a = np.zeros((6, sim.P, 12), np.int64)
+        a[:, :, L_move] = rng.integers(0, 4, size=(6, sim.P))
+        a[:, :, L_move][rng.random((6, sim.P)) < 0.1] = 4
+        a[:, :, 1] = 100            # Attack.Target no-op (N_ENT_OBS)
+        return a
+
+    run_parity(sim, oracles, seeds=np.arange(6) + 77, ticks=95, action_fn=act, check_state_every=8)
+    sim.close()
+
+
+def test_item_heavy_with_tiny_staged_prefix(monkeypatch):
+    # every harvest drops a weapon too, nobody starves: inventories fill up, items are used, sold, bought and
+    # destroyed; NMMO_B200_ICAP=8 makes the observation kernel read all but 8 item rows from HBM
+    monkeypatch.setenv("NMMO_B200_ICAP", "8")
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=260, NC_RES_DEPLETION=0, NC_SPAWN_IMMUNITY=3,
+                        NC_WEAPON_DROP_THR=-1, NC_NPC_AGGR_PCT=200, NC_NPC_NEUT_PCT=200)     # passive NPCs only
+    sim, oracles = _make(world, 3)
+    peak = []
+
+    def watch(t, sim_, oracles_):
+        if t % 10 == 0:
+            peak.append(int((oracles_[0].snapshot()[1][:, 0] > 0).sum()))
+
+    stats = run_parity(sim, oracles, seeds=np.arange(3) + 41, ticks=270, on_tick=watch)
+    assert max(peak) > 8, f"the item table must outgrow the staged prefix (peak live rows {max(peak)})"
+    assert stats["infos"] > 0
+    sim.close()
+
+
 def test_default_config_full_size():
     world = build_world()
     sim, oracles = _make(world, 3)
