@@ -176,6 +176,7 @@ def run_native(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    n_slots_step = E * P
     sim.reset(seeds)
     for _ in range(args.warmup):
         tick(args.seed)
@@ -196,6 +197,23 @@ def run_native(args):
     step_ms, obs_ms, n_timed = sim.timing_read()
     sim.timing(False)
     sums, counts, counters = sim.stats(clear=False)
+    # ---- steady state: keep going so that several episodes per env are in the average ----
+    steady = None
+    if args.steady_steps > 0:
+        _, _, c0 = sim.stats(clear=False)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(args.steady_steps):
+            tick(args.seed)
+        g1.record(stream)
+        torch.cuda.synchronize()
+        _, _, c1 = sim.stats(clear=False)
+        ms_s = g0.elapsed_time(g1)
+        steady = {"ticks": args.steady_steps, "ms_per_step": ms_s / args.steady_steps,
+                  "value_per_gpu": n_slots_step * args.steady_steps / (ms_s * 1e-3),
+                  "alive_fraction": float(c1[1] - c0[1]) / max(1.0, float(c1[0] - c0[0])),
+                  "episodes_finished": float(c1[2] - c0[2]),
+                  "what": f"the next {args.steady_steps} ticks after the timed window (envs are at different points of their episodes)"}
     # ---- dense-writer reference point: every byte of every record rewritten each tick ----
     sim.set_obs_full(True)
     for _ in range(2):
@@ -208,21 +226,41 @@ def run_native(args):
     sim.set_obs_full(False)
     tick(args.seed)
     # ---- end-to-end through the host-buffer C ABI call ----------------------------------
+    # The caller's inputs (actions) start in pinned HOST memory and its results (reward, terminated, truncated,
+    # mask) end there, every step, through nmmo_step_host.  To feed it the very actions of the device-resident run,
+    # the run is replayed twice from the same reset (it is deterministic): pass A tapes the actions of the last
+    # `e2e_steps` ticks of the window into pinned memory (untimed); pass B advances to the same tick on the device
+    # and then takes the timed host-buffer steps from the tape.  The built-in policy stays on during pass B (writing
+    # to a scratch tensor) so the kernels do the same work as in the device-timed region.
     n = E * P
-    act_host = torch.empty((E, P, 12), dtype=torch.int32).pin_memory()
-    e2e_steps = max(4, min(args.steps, 64))
+    e2e_steps = max(4, min(args.steps, 32))
+    pre = args.warmup + args.steps - e2e_steps
+    tape = torch.empty((e2e_steps, E, P, 12), dtype=torch.int32).pin_memory()
+    sim.set_autosample(args.seed, sim.actions)
+    sim.reset(seeds)
+    for _ in range(pre):
+        tick(args.seed)
+    for k in range(e2e_steps):
+        tape[k].copy_(sim.actions)
+        tick(args.seed)
+    torch.cuda.synchronize()
+    sim.reset(seeds)
+    for _ in range(pre):
+        tick(args.seed)
+    scratch = torch.zeros_like(sim.actions)
+    torch.cuda.synchronize()
+    sim.set_autosample(args.seed, scratch)
+    tape_np = tape.numpy()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(stream)
-    for _ in range(e2e_steps):
-        act_host.copy_(sim.actions, non_blocking=True)   # the policy's actions leave the device (clean_pufferl.py:329)
-        stream.synchronize()
-        sim.step_host(act_host.numpy())                  # H2D actions, step, D2H reward/term/trunc/mask
+    for k in range(e2e_steps):
+        sim.step_host(tape_np[k])                        # H2D actions, step, D2H reward/term/trunc/mask
     f1.record(stream)
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     h2d = n * 12 * 4
-    d2h = n * 12 * 4 + n * (4 + 3)
+    d2h = n * (4 + 3)
     # ---- reduce over ranks --------------------------------------------------------------
     t = torch.tensor([ms_total, ms_e2e, step_ms, obs_ms, obs_ms_dense], dtype=torch.float64, device="cuda")
     agg = torch.tensor(np.concatenate([sums, counts, counters.astype(np.float64)]), dtype=torch.float64, device="cuda")
@@ -282,7 +320,9 @@ def run_native(args):
                          "dense_equivalent_gbs": n * b_obs / (obs_ms * 1e-3) / 1e9},
             "e2e": {"value": world_size * n * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "path": "nmmo_step_host (C ABI, pinned host actions in; reward/term/trunc/mask out; obs stay on device)"},
+                    "path": "nmmo_step_host (C ABI): actions from pinned host memory in, reward/term/trunc/mask to pinned host memory out, every "
+                            "step; observations stay on the device where the policy reads them; actions = tape of the device-resident run"},
+            "steady_state": steady,
             "gpu_launches": 2 * args.steps,
             "clocks": clk,
             "episode_stats": {"finished_agents": float(g_counts[SPEC["IN_LENGTH"]]),
@@ -312,6 +352,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--ref-envs", type=int, default=0, help="envs of the CPU sample (default 4 x cores)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--steady-steps", type=int, default=768, help="extra ticks after the timed window for the steady-state figure (0 = off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
