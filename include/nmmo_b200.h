@@ -73,7 +73,8 @@ int nmmo_sample_actions(nmmo_handle *h, uint64_t seed, int32_t *actions_dev, voi
 
 /* Built-in random policy: with a non-NULL DEVICE buffer int32 [E][P][12], every reset/step also
  * writes uniform-random valid actions for the new observations into it (identical draws to
- * nmmo_sample_actions(seed)); NULL switches it off. */
+ * nmmo_sample_actions(seed)); NULL switches it off.  Rows of absent agents are zeroed once, when the
+ * agent leaves: hand in a zero-initialised buffer (or enable it before a reset). */
 int nmmo_set_autosample(nmmo_handle *h, uint64_t seed, int32_t *actions_dev_out);
 
 /* Device pointers to the step outputs (valid until nmmo_destroy, rewritten by each step). */

@@ -172,15 +172,10 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     for (int i = 1; i < n; i++) { uint16_t x = l[i]; int j = i - 1; while (j >= 0 && l[j] > x) { l[j + 1] = l[j]; j--; } l[j + 1] = x; }
   }
   __syncthreads();
-  for (int j = tid; j < L.n_mkt; j += T) {     // the Market block, identical for every agent of the env
-    int16_t row[IA_N_OBS];
-    if (j < n_mkt) {
-      int i = s_mkt_rows[j];
-      item_obs_row(c, i, OITM(IS_TYPE, i), OITM(IS_LEVEL, i), OITM(IS_OWNER, i), OITM(IS_QUANTITY, i), OITM(IS_EQUIPPED, i), OITM(IS_PRICE, i), row);
-    } else {
-#pragma unroll
-      for (int k = 0; k < IA_N_OBS; k++) row[k] = 0;
-    }
+  for (int j = tid; j < n_mkt; j += T) {       // the Market block, identical for every agent of the env
+    int16_t row[IA_N_OBS];                      // (rows past n_mkt are zeros and are written as such, not staged)
+    int i = s_mkt_rows[j];
+    item_obs_row(c, i, OITM(IS_TYPE, i), OITM(IS_LEVEL, i), OITM(IS_OWNER, i), OITM(IS_QUANTITY, i), OITM(IS_EQUIPPED, i), OITM(IS_PRICE, i), row);
     uint4 *dst = (uint4 *)(s_mkt + j * IA_N_OBS);
     dst[0] = make_uint4(pack2(row[0], row[1]), pack2(row[2], row[3]), pack2(row[4], row[5]), pack2(row[6], row[7]));
     dst[1] = make_uint4(pack2(row[8], row[9]), pack2(row[10], row[11]), pack2(row[12], row[13]), pack2(row[14], row[15]));
@@ -210,10 +205,6 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     }
     if (lane == 0) { s_head[2 * AC_N] = n; s_head[2 * AC_N + 1] = 0; }
   }
-  // absent agents: every head of the built-in policy picks 0 (one coalesced pass over the env)
-  if (prm.sample_out)
-    for (int i = tid; i < P * AC_N; i += T)
-      if (s_status[i / AC_N] != ES_ALIVE) prm.sample_out[(size_t)env * P * AC_N + i] = 0;
   __syncthreads();
   OPHASE();      // 35 work list
   const int n_work = s_head[2 * AC_N];
@@ -233,6 +224,9 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     // record is non-zero at all.  obs_full = 1 rewrites every byte (roofline / A-B mode).
     const uint32_t meta = s_meta[p];
     if (went & 0x8000) {                     // dead or absent agents get the zero pad record
+      // ... and every head of the built-in policy picks 0: written once, when the agent leaves (the action
+      // buffer must start zeroed, which nmmo_set_autosample's caller guarantees)
+      if (prm.sample_out && lane < AC_N) prm.sample_out[a * AC_N + lane] = 0;
       for (int k = lane; k < L.stride / 16; k += 32) st16(rec + k * 16, zero4);
       n_stored += L.stride / 16;
       if (lane == 0) prm.obs_meta[a] = 0;
@@ -430,7 +424,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     }
     // ---- Market block ----
     n_stored += max(n_mkt, pm) * 2;
-    for (int k = lane; k < max(n_mkt, pm) * 2; k += 32) st16(rec + L.o_market + k * 16, ((const uint4 *)s_mkt)[k]);
+    for (int k = lane; k < max(n_mkt, pm) * 2; k += 32) st16(rec + L.o_market + k * 16, k < n_mkt * 2 ? ((const uint4 *)s_mkt)[k] : zero4);
     // ---- Task embedding (constant within an episode) ----
     if (!task_ok) {
       n_stored += L.task_dim * 2 / 16;
