@@ -119,6 +119,17 @@ def test_default_config_full_size():
     sim.close()
 
 
+def test_full_size_whole_episode():
+    # config 1 of BASELINE.json as one lock-stepped env pair: default engine config (128 agents, 256 NPCs, 160x160
+    # map, horizon 1024) with the start-kit wrapper, run until the episode ends (early stop at 8 agents) and on
+    # through the automatic reset
+    world = build_world(agent="neurips23_start_kit")
+    sim, oracles = _make(world, 2)
+    stats = run_parity(sim, oracles, seeds=np.array([1, 7]), ticks=400, check_state_every=50)
+    assert stats["episodes_done"] >= 2 and stats["infos"] >= 2 * 120
+    sim.close()
+
+
 def test_autosample_matches_sampler_kernel():
     import torch
     world = build_world(task_dim=64, **SMALL, NC_HORIZON=80, NC_RES_DEPLETION=1)
