@@ -101,9 +101,9 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
     int v = atoi(ov);
     if (v >= 8 && v % 8 == 0) p.ICAP = std::min(p.CAP, v);
   }
-  if (p.P <= 0 || p.P > NM_STEP_THREADS) { delete h; return fail(NM_ERR_LIMIT, "PLAYER_N must be in 1..256 for the per-env CTA design"); }
+  if (p.P <= 0 || p.P > NM_STEP_THREADS) { delete h; return fail(NM_ERR_LIMIT, "PLAYER_N must be in 1..256 (256 threads per environment)"); }
   if (p.R % 8 || p.CAP % 8 || (p.S * p.S) % 32) { delete h; return fail(NM_ERR_LIMIT, "P+N and item cap must be multiples of 8, S*S of 32 (bulk copies)"); }
-  if (p.R > 2 * NM_STEP_THREADS) { delete h; return fail(NM_ERR_LIMIT, "P+N must be <= 512 for the per-env CTA design"); }
+  if (p.R > 2 * NM_STEP_THREADS) { delete h; return fail(NM_ERR_LIMIT, "P+N must be <= 512 (256 threads per environment)"); }
   if (p.S > 255) { delete h; return fail(NM_ERR_LIMIT, "MAP_SIZE must be <= 255"); }
   if (p.cfg[NC_NPC_SPAWN_ATTEMPTS] > 32) { delete h; return fail(NM_ERR_LIMIT, "NPC_SPAWN_ATTEMPTS must be <= 32"); }
   if (p.L.n_ent > 255 || p.cfg[NC_N_INV] > 16) { delete h; return fail(NM_ERR_LIMIT, "N_ENT_OBS <= 255, N_INV <= 16"); }
@@ -112,7 +112,11 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   int max_smem = 0;
   CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   if ((int)h->step_smem > max_smem || (int)h->obs_smem > max_smem) { delete h; return fail(NM_ERR_LIMIT, "environment does not fit in shared memory"); }
-  CU(cudaFuncSetAttribute(nmmo_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
+  // the step kernel runs two environments per CTA (they walk the code together) when both fit
+  p.half_smem = (int)((h->step_smem + 127) & ~(size_t)127);
+  p.envs_per_cta = 2 * p.half_smem <= max_smem ? 2 : 1;
+  if (const char *ov = getenv("NMMO_B200_ENVS_PER_CTA")) { if (atoi(ov) == 1) p.envs_per_cta = 1; }      // test hook
+  CU(cudaFuncSetAttribute(nmmo_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.envs_per_cta * p.half_smem));
   CU(cudaFuncSetAttribute(nmmo_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->obs_smem));
   size_t E = p.E, P = p.P;
   DA(p.ent, E * EA_N * p.R); DA(p.item, E * IS_N * p.CAP); DA(p.map, E * p.S * p.S / 2);
@@ -166,7 +170,8 @@ static int launch_step(nmmo_handle *h, int mode, cudaStream_t st) {
     h->ev_used += 3;
     CU(cudaEventRecord(e3[0], st));
   }
-  nmmo_step_kernel<<<prm.E, NM_STEP_THREADS, h->step_smem, st>>>(prm);
+  const int epc = h->prm.envs_per_cta;
+  nmmo_step_kernel<<<(prm.E + epc - 1) / epc, epc * NM_STEP_THREADS, (size_t)epc * prm.half_smem, st>>>(prm);
   CU(cudaGetLastError());
   if (e3) CU(cudaEventRecord(e3[1], st));
   nmmo_obs_kernel<<<prm.E, NM_OBS_THREADS, h->obs_smem, st>>>(prm);

@@ -58,6 +58,8 @@ struct NmParams {
   int32_t *sample_out;         // optional: the obs kernel also writes uniform-random valid actions here
   uint64_t sample_seed;
   unsigned long long *prof;    // optional [32] per-phase clock accumulators (NULL = off)
+  int half_smem;               // step kernel: dynamic shared memory of one environment
+  int envs_per_cta;            // step kernel: 2 when two environments fit in one CTA's shared memory, else 1
   int mode;                    // 0 step (auto-reset finished envs), 1 reset flagged envs only
   int env_base;                // global env index of env 0 (multi-GPU sharding; seeds derive from it)
 };

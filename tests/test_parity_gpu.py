@@ -119,6 +119,16 @@ def test_default_config_full_size():
     sim.close()
 
 
+def test_one_env_per_cta_fallback(monkeypatch):
+    # configurations whose tables do not fit twice in a CTA's shared memory run one environment per CTA
+    monkeypatch.setenv("NMMO_B200_ENVS_PER_CTA", "1")
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=60)
+    sim, oracles = _make(world, 5)
+    stats = run_parity(sim, oracles, seeds=np.arange(5) + 3, ticks=130)
+    assert stats["episodes_done"] >= 5
+    sim.close()
+
+
 def test_full_size_whole_episode():
     # config 1 of BASELINE.json as one lock-stepped env pair: default engine config (128 agents, 256 NPCs, 160x160
     # map, horizon 1024) with the start-kit wrapper, run until the episode ends (early stop at 8 agents) and on
