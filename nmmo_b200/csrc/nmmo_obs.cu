@@ -208,6 +208,16 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   __syncthreads();
   OPHASE();      // 35 work list
   const int n_work = s_head[2 * AC_N];
+  // Tile window, fast path (window at least 8 wide, at most 32 groups of 8 tiles): lane g owns tiles 8g..8g+7 of
+  // the row-major window, which lie in at most two window rows.  Where they lie does not depend on the agent.
+  const int tw_tiles = L.win * L.win, tw_groups = (tw_tiles + 7) / 8;
+  const bool tw_fast = L.win >= 8 && tw_groups <= 32;
+  const int tw_dr = (lane * 8) / L.win, tw_dc = (lane * 8) - tw_dr * L.win;
+  const int tw_first = min(8, L.win - tw_dc);             // tiles of the group in its first window row
+  auto fetch8 = [&](int i) -> uint32_t {                    // the 8 nibbles of tiles i..i+7
+    const int w = i >> 3, sh = (i & 7) * 4;
+    return __funnelshift_r(s_map[w], s_map[w + 1], sh);
+  };
   long long w_t0 = clock64();
   for (;;) {
     int wi = 0;
@@ -434,8 +444,33 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     // ---- Tile window ----
     // a lane owns 8 consecutive tiles = 24 int16 = three 16-byte stores
     {
-      const int n_tiles = L.win * L.win, n_groups = (n_tiles + 7) / 8;
+      const int n_tiles = tw_tiles, n_groups = tw_groups;
       n_stored += nm_align16(n_tiles * 6) / 16;
+      if (tw_fast) {
+        if (lane < n_groups) {
+          const int w = lane * 8;
+          const int rrA = r0 + tw_dr - vis, ccA = c0 + tw_dc - vis;
+          // materials of the 8 tiles in order: the rest of window row tw_dr, then the start of the next one
+          const uint32_t a8 = fetch8(rrA * S + ccA), b8 = fetch8((rrA + 1) * S + c0 - vis);
+          const uint32_t mats = tw_first >= 8 ? a8 : ((a8 & ((1u << (4 * tw_first)) - 1u)) | (b8 << (4 * tw_first)));
+          int v[24];
+#pragma unroll
+          for (int t = 0; t < 8; t++) {
+            const bool ok = w + t < n_tiles;
+            const int nx = t >= tw_first ? 1 : 0;          // in the next window row?
+            v[3 * t] = ok ? rrA + nx : 0;
+            v[3 * t + 1] = ok ? ccA + t - nx * L.win : 0;
+            v[3 * t + 2] = ok ? (int)((mats >> (4 * t)) & 15u) : 0;
+          }
+          uint8_t *dst = rec + L.o_tile + lane * 48;
+          const int last = nm_align16(n_tiles * 6);
+#pragma unroll
+          for (int q = 0; q < 3; q++)
+            if (lane * 48 + q * 16 < last)
+              st16(dst + q * 16, make_uint4(pack2(v[8 * q], v[8 * q + 1]), pack2(v[8 * q + 2], v[8 * q + 3]),
+                                            pack2(v[8 * q + 4], v[8 * q + 5]), pack2(v[8 * q + 6], v[8 * q + 7])));
+        }
+      } else
       for (int g = lane; g < n_groups; g += 32) {
         int w = g * 8;
         int dr = w / L.win, dc = w - dr * L.win;
