@@ -239,7 +239,10 @@ enum nm_info {
 /* Closed predicate vocabulary (nmmo/task/base_predicates.py [UPSTREAM]); the names are the
  * ones the reference imports: curriculum_generation/manual_curriculum.py:8-29,
  * neurips23_evaluation/heldout_evaluation_task.py:7-20, syllabus_wrapper.py:58-70.
- * A task row is int32[8]: {pred, p0, p1, p2, p3, pred2, q0, combine}. */
+ * A task row is int32[12]: {pred, p0, p1, p2, p3, pred2, q0, combine, q1, q2, wa, wb}.
+ * combine = 0: pred alone; 1: pred * pred2 (manual_curriculum.py:201-202 `InventorySpaceGE * TickGE`);
+ * 2: (wa/1000) * pred + (wb/1000) * pred2 (manual_curriculum.py:119-122 `0.3 * EquipItem + 0.7 * GainExperience`).
+ * pred2 takes (q0, q1, q2) and must be a state predicate (no event accumulator, no window scan). */
 enum nm_pred {
   TP_NONE = 0, TP_TICK_GE, TP_COUNT_EVENT, TP_CAN_SEE_TILE, TP_CAN_SEE_AGENT, TP_OCCUPY_TILE,
   TP_ATTAIN_SKILL, TP_GAIN_EXPERIENCE, TP_EQUIP_ITEM, TP_SCORE_HIT, TP_HOARD_GOLD, TP_EARN_GOLD,
@@ -247,7 +250,7 @@ enum nm_pred {
   TP_HARVEST_ITEM, TP_LIST_ITEM, TP_BUY_ITEM, TP_DEFEAT_ENTITY, TP_FULLY_ARMED, TP_STAY_ALIVE,
   TP_DISTANCE_TRAVELED, TP_ALL_DEAD, TP_ALL_MEMBERS_WITHIN_RANGE, TP_CAN_SEE_GROUP, TP_N
 };
-#define NM_TASK_COLS 8
+#define NM_TASK_COLS 12
 
 /* ------------------------------------------------------------------------ rng ------- */
 /* Draw sites.  A draw is addressed by (env seed, tick, site, idx, k) so that a parallel

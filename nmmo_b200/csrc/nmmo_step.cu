@@ -1063,13 +1063,14 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   const size_t my_a = (size_t)env * P + (tid < P ? tid : 0);
   int32_t *my_sta = prm.stats + my_a * ST_N;
   double *my_ds = prm.dstats + my_a * DS_N;
-  int my_task_id = 0, my_t[NM_TASK_COLS] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int my_task_id = 0, my_t[NM_TASK_COLS] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   int my_done = 0, my_signals = 0, my_uniq = 0, my_acc0 = 0, my_acc1 = 0;
   double my_cum = 0.0, my_prog = 0.0, my_maxprog = 0.0;
   if (tid < P) {
     my_task_id = prm.task_id[my_a];
     const int4 *tr = (const int4 *)(prm.tasks + (size_t)my_task_id * NM_TASK_COLS);
-    int4 t0 = __ldg(tr), t1 = __ldg(tr + 1);
+    int4 t0 = __ldg(tr), t1 = __ldg(tr + 1), t2 = __ldg(tr + 2);
+    my_t[8] = t2.x; my_t[9] = t2.y; my_t[10] = t2.z; my_t[11] = t2.w;
     my_t[0] = t0.x; my_t[1] = t0.y; my_t[2] = t0.z; my_t[3] = t0.w; my_t[4] = t1.x; my_t[5] = t1.y; my_t[6] = t1.z; my_t[7] = t1.w;
     my_done = my_sta[ST_TASK_DONE]; my_signals = my_sta[ST_REWARD_SIGNALS]; my_uniq = my_sta[ST_UNIQ_CURR];
     my_acc0 = my_sta[ST_TASK_ACC0]; my_acc1 = my_sta[ST_TASK_ACC1];
@@ -1724,7 +1725,10 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
         double diff = 0.0;
         if (!completed) {
           double v = eval_predicate(ctx, p, my_t[0], my_t[1], my_t[2], my_t[3], acc0, acc1);
-          if (my_t[7] == 1) v = v * eval_predicate(ctx, p, my_t[5], my_t[6], 0, 0, 0, 0);
+          if (my_t[7] == 1) v = v * eval_predicate(ctx, p, my_t[5], my_t[6], my_t[8], my_t[9], 0, 0);
+          else if (my_t[7] == 2)      // (wa/1000) * a + (wb/1000) * b, each operation rounded like the reference's Python floats
+            v = __dadd_rn(__dmul_rn(__ddiv_rn((double)my_t[10], 1000.0), v),
+                          __dmul_rn(__ddiv_rn((double)my_t[11], 1000.0), eval_predicate(ctx, p, my_t[5], my_t[6], my_t[8], my_t[9], 0, 0)));
           v = clip01(v);
           diff = v - my_prog;
           if (v != my_prog) my_ds[DS_PROGRESS] = v;

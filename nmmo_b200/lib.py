@@ -132,9 +132,11 @@ class Simulator:
         assert maps.ndim == 3 and maps.shape[1:] == (S, S), "maps must be uint8 [n_maps, S, S]"
         assert task_table.shape[1] == SPEC["NM_TASK_COLS"]
         assert task_embed.shape == (task_table.shape[0], int(cfg[SPEC["NC_TASK_DIM"]]))
-        bad = task_table[(task_table[:, 7] != 0) & (task_table[:, 5] != SPEC["TP_TICK_GE"])]
-        if len(bad):
-            raise NmmoError("combined tasks support `pred * TickGE` only")
+        from .tasks import PRED, STATE_PREDICATES
+        ok2 = np.array([PRED[n] for n in STATE_PREDICATES])
+        bad = task_table[(task_table[:, 7] != 0) & ~np.isin(task_table[:, 5], ok2)]
+        if len(bad) or (~np.isin(task_table[:, 7], (0, 1, 2))).any():
+            raise NmmoError("combined tasks: combine must be 0/1/2 and the second predicate a state predicate")
         self.device = int(device)
         self.E = int(n_envs)
         self.P = int(cfg[SPEC["NC_N_PLAYERS"]]); self.N = int(cfg[SPEC["NC_N_NPCS"]])

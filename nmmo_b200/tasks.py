@@ -3,11 +3,13 @@
 The reference assigns every agent one task drawn from a curriculum of ``TaskSpec`` objects
 (/root/reference/reinforcement_learning/environment.py:48-49; ``nmmo.task.task_spec``), whose
 ``eval_fn`` are Python callables from ``nmmo.task.base_predicates``.  Arbitrary callables cannot
-run on the device, so a task here is a row ``int32[8] = {pred, p0, p1, p2, p3, pred2, q0, combine}``
+run on the device, so a task here is a row ``int32[12] = {pred, p0, p1, p2, p3, pred2, q0, combine, q1, q2, wa, wb}``
 over the predicate names the reference imports
 (curriculum_generation/manual_curriculum.py:8-29, neurips23_evaluation/heldout_evaluation_task.py:7-20,
-syllabus_wrapper.py:58-70).  ``combine = 1`` is the product form ``a * TickGE`` used at
-manual_curriculum.py:119-122.  Each task also carries a ``task_dim`` fp16 embedding (the
+syllabus_wrapper.py:58-70).  ``combine = 1`` is the product form ``a * b`` (manual_curriculum.py:201-202,
+``InventorySpaceGE * TickGE``), ``combine = 2`` the weighted sum ``wa/1000 * a + wb/1000 * b``
+(manual_curriculum.py:119-122, ``0.3 * EquipItem + 0.7 * GainExperience``); ``b`` takes ``(q0, q1, q2)`` and must
+be a state predicate.  Each task also carries a ``task_dim`` fp16 embedding (the
 reference's come from an LLM, curriculum_generation/task_encoder.py:87; here they are seeded
 synthetic vectors because the curriculum pickle is missing from the reference,
 .MISSING_LARGE_BLOBS:1).
@@ -27,8 +29,21 @@ PRED = {k[3:]: v for k, v in SPEC.items() if k.startswith("TP_")}
 NCOL = SPEC["NM_TASK_COLS"]
 
 
-def task_row(pred: str, p0=0, p1=0, p2=0, p3=0, pred2: str = "NONE", q0=0, combine=0) -> List[int]:
-    return [PRED[pred], int(p0), int(p1), int(p2), int(p3), PRED[pred2], int(q0), int(combine)]
+STATE_PREDICATES = ("TICK_GE", "ATTAIN_SKILL", "GAIN_EXPERIENCE", "EQUIP_ITEM", "HOARD_GOLD", "INVENTORY_SPACE_GE", "OWN_ITEM",
+                    "FULLY_ARMED", "STAY_ALIVE", "DISTANCE_TRAVELED", "OCCUPY_TILE", "ALL_DEAD", "ALL_MEMBERS_WITHIN_RANGE")
+
+
+def task_row(pred: str, p0=0, p1=0, p2=0, p3=0, pred2: str = "NONE", q0=0, combine=0, q1=0, q2=0, wa=0, wb=0) -> List[int]:
+    if combine and pred2 not in STATE_PREDICATES:
+        raise ValueError(f"the second predicate of a combined task must be a state predicate, not {pred2}")
+    return [PRED[pred], int(p0), int(p1), int(p2), int(p3), PRED[pred2], int(q0), int(combine), int(q1), int(q2), int(wa), int(wb)]
+
+
+def practice_skill_with_tool(skill: str, exp: int) -> List[int]:
+    """manual_curriculum.py:112-122: 0.3 * EquipItem(tool of the skill, level 1) + 0.7 * GainExperience(skill, exp)."""
+    tool = {"MELEE": "SPEAR", "RANGE": "BOW", "MAGE": "WAND", "FISHING": "ROD", "HERBALISM": "GLOVES", "PROSPECTING": "PICKAXE",
+            "CARVING": "AXE", "ALCHEMY": "CHISEL"}[skill]      # TOOL_FOR_SKILL, manual_curriculum.py:40-51
+    return task_row("EQUIP_ITEM", ITEM[tool], 1, pred2="GAIN_EXPERIENCE", q0=SKILL[skill], q1=exp, combine=2, wa=300, wb=700)
 
 
 def create_basic_tasks(unit_count: int) -> List[List[int]]:
@@ -84,6 +99,8 @@ def default_curriculum() -> List[List[int]]:
     rows.append(task_row("CAN_SEE_AGENT", 1))
     rows.append(task_row("CAN_SEE_GROUP", 1, 8))
     rows.append(task_row("ALL_MEMBERS_WITHIN_RANGE", 5, pred2="TICK_GE", q0=100, combine=1))
+    for skill in ("MELEE", "FISHING", "PROSPECTING"):
+        rows.append(practice_skill_with_tool(skill, 30))
     return rows
 
 

@@ -74,6 +74,27 @@ def test_every_predicate_family_progresses():
     sim.close()
 
 
+def test_combined_tasks_product_and_weighted_sum():
+    # manual_curriculum.py:119-122 `0.3 * EquipItem + 0.7 * GainExperience` and :201-202 `InventorySpaceGE * TickGE`
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=300, NC_RES_DEPLETION=0, NC_SPAWN_IMMUNITY=3, NC_WEAPON_DROP_THR=-1,
+                        NC_NPC_AGGR_PCT=200, NC_NPC_NEUT_PCT=200)
+    cfg, _, _, tab, _ = world
+    P = int(cfg[S["NC_N_PLAYERS"]])
+    pick = np.flatnonzero(tab[:, 7] != 0)
+    assert (tab[pick, 7] == 2).sum() >= 3 and (tab[pick, 7] == 1).sum() >= 1
+    E = len(pick)
+    sim, oracles = _sim(world, E), _oracles(world, E)
+    task_ids = np.repeat(pick.astype(np.int32)[:, None], P, axis=1)
+    moved = []
+
+    def watch(t, sim_, oracles_):
+        moved.append(float(np.abs(sim_.rewards.cpu().numpy()).sum()))
+
+    run_parity(sim, oracles, seeds=np.arange(E) + 500, ticks=280, task_ids=task_ids, check_state_every=0, on_tick=watch)
+    assert sum(m > 0 for m in moved) > 10, "the combined tasks must make progress (rewards move)"
+    sim.close()
+
+
 def test_env_sharding_invariance():
     """Global env g gives the same trajectory whichever handle (env_base) hosts it."""
     import torch

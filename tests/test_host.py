@@ -77,7 +77,15 @@ def test_unpack_batched_obs_views_oracle_record():
 def test_task_table_is_device_evaluable():
     tab, emb = make_task_table(default_curriculum(), 64)
     assert tab.shape[1] == SPEC["NM_TASK_COLS"] and emb.dtype == np.uint16 and emb.shape == (tab.shape[0], 64)
-    assert ((tab[:, 7] == 0) | (tab[:, 5] == SPEC["TP_TICK_GE"])).all()
+    from nmmo_b200.tasks import PRED, STATE_PREDICATES, practice_skill_with_tool, task_row
+    state = [PRED[n] for n in STATE_PREDICATES]
+    assert np.isin(tab[:, 7], (0, 1, 2)).all() and np.isin(tab[tab[:, 7] != 0][:, 5], state).all()
+    # manual_curriculum.py:119-122: 0.3 * EquipItem(tool) + 0.7 * GainExperience(skill, exp)
+    row = practice_skill_with_tool("FISHING", 30)
+    assert row[0] == SPEC["TP_EQUIP_ITEM"] and row[1] == SPEC["IT_ROD"] and row[5] == SPEC["TP_GAIN_EXPERIENCE"]
+    assert row[6] == SPEC["SK_FISHING"] and row[8] == 30 and row[7] == 2 and (row[10], row[11]) == (300, 700)
+    with pytest.raises(ValueError):
+        task_row("TICK_GE", 10, pred2="COUNT_EVENT", q0=1, combine=1)       # event-driven second predicate
     assert (tab[:, 0] > 0).all() and (tab[:, 0] < SPEC["TP_N"]).all()
 
 
