@@ -47,7 +47,8 @@ SPEC = _parse_enums(_SPEC.read_text())
 globals().update(SPEC)  # NC_*, EA_*, IA_*, ... as module attributes
 
 WRAPPERS = {"base": SPEC["NW_BASE"], "takeru": SPEC["NW_TAKERU"], "neurips23_start_kit": SPEC["NW_START_KIT"],
-            "yaofeng": SPEC["NW_YAOFENG"]}
+            "yaofeng": SPEC["NW_YAOFENG"],
+            "hybrid": SPEC["NW_YAOFENG"]}      # agent_zoo/hybrid.py: takeru's policy with yaofeng's RewardWrapper
 
 
 def default_exp_threshold(base_exp: int, max_level: int):
@@ -79,7 +80,7 @@ def default_wrapper_args(agent: str = "takeru", **over) -> Namespace:
         d.update(early_stop_agent_num=0, explore_bonus_weight=0.01, clip_unique_event=3, disable_give=True)
     elif agent == "neurips23_start_kit":
         d.update(heal_bonus_weight=0.03, explore_bonus_weight=0.01, clip_unique_event=3)
-    elif agent == "yaofeng":      # config.yaml:117-125; constructor defaults agent_zoo/yaofeng/reward_wrapper.py:13-29
+    elif agent in ("yaofeng", "hybrid"):      # config.yaml:117-125, :151-159; constructor defaults agent_zoo/yaofeng/reward_wrapper.py:13-29
         d.update(hp_bonus_weight=0.03, exp_bonus_weight=0.002, defense_bonus_weight=0.04, attack_bonus_weight=0.0,
                  gold_bonus_weight=0.001, custom_bonus_scale=0.1, disable_give=True, donot_attack_dangerous_npc=True)
     d.update(over)
@@ -90,7 +91,7 @@ def make_config(env_args: Namespace = None, wrapper_args: Namespace = None, agen
                 **engine_over) -> Tuple[np.ndarray, np.ndarray]:
     """Build (cfg int32, fcfg float64).  ``engine_over`` overrides raw NC_* entries (tests)."""
     if env_args is None:
-        env_args = default_env_args(resilient_population=0 if agent in ("takeru", "yaofeng") else 0.2)
+        env_args = default_env_args(resilient_population=0 if agent in ("takeru", "yaofeng", "hybrid") else 0.2)
     if wrapper_args is None:
         wrapper_args = default_wrapper_args(agent)
     S = SPEC

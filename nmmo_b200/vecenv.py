@@ -96,7 +96,7 @@ class B200VecEnv:
         # env_creator / env_args / envs_per_worker / env_pool are accepted for signature
         # compatibility; all envs of this backend step in lock-step on one GPU
         env_kwargs = env_kwargs or {}
-        env_ns = env_kwargs.get("env") or default_env_args(resilient_population=0 if agent in ("takeru", "yaofeng") else 0.2)
+        env_ns = env_kwargs.get("env") or default_env_args(resilient_population=0 if agent in ("takeru", "yaofeng", "hybrid") else 0.2)
         wrap_ns = env_kwargs.get("reward_wrapper") or default_wrapper_args(agent)
         if isinstance(env_ns, dict):
             env_ns = Namespace(**env_ns)

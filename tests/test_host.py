@@ -32,6 +32,13 @@ def test_config_mirrors_reference_defaults():
     assert cfg3[SPEC["NC_N_PLAYERS"]] == 64 and cfg3[SPEC["NC_SPAWN_IMMUNITY"]] == 5 and cfg3[SPEC["NC_ITEM_CAP"]] == 64 * 12
 
 
+def test_hybrid_agent_uses_yaofeng_wrapper():
+    a, fa = make_config(agent="hybrid")
+    b, fb = make_config(agent="yaofeng")
+    assert np.array_equal(a, b) and np.array_equal(fa, fb) and a[SPEC["NC_WRAPPER"]] == SPEC["NW_YAOFENG"]      # agent_zoo/hybrid.py:4
+    assert fa[SPEC["NF_HP_W"]] == 0.03 and fa[SPEC["NF_BONUS_SCALE"]] == 0.1 and a[SPEC["NC_NO_DANGEROUS_NPC"]] == 1   # config.yaml:151-159
+
+
 def test_layout_matches_survey_accounting():
     cfg, _ = make_config(agent="takeru")
     L = ObsLayout(cfg)
