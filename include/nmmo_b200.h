@@ -99,6 +99,12 @@ int nmmo_inject_rng(nmmo_handle *h, int env, const uint64_t *keys, const uint32_
  * items[CAP][IS_N], uint8 map[S*S]; also the tick, map id and error flags. */
 int nmmo_snapshot(nmmo_handle *h, int env, int16_t *ent, int16_t *items, uint8_t *map, int32_t *scalars16);
 
+/* Task state of one env's agents, what the reference reads from `env.agent_task_map[id][0]`
+ * (stat_wrapper.py:155-159): task_id int32 [P], completed int32 [P] (tick of completion, 0 = not yet),
+ * reward_signal_count int32 [P], max_progress float64 [P].  Any pointer may be NULL. */
+int nmmo_task_state(nmmo_handle *h, int env, int32_t *task_id, int32_t *completed, int32_t *reward_signals,
+                    double *max_progress);
+
 /* Episode statistics of finished agents since the last clear: sums[IN_N], counts[IN_N] (means
  * are sums/counts, clean_pufferl.py:381-390), counters[4] = slot-steps, agent-steps (mask
  * sum), finished episodes, event-ring overflows, bytes moved by the observation kernel, 3 spare

@@ -333,6 +333,26 @@ extern "C" int nmmo_snapshot(nmmo_handle *h, int env, int16_t *ent, int16_t *ite
   return NM_OK;
 }
 
+extern "C" int nmmo_task_state(nmmo_handle *h, int env, int32_t *task_id, int32_t *completed, int32_t *reward_signals,
+                               double *max_progress) {
+  if (!h || env < 0 || env >= h->prm.E) return fail(NM_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  const NmParams &p = h->prm;
+  const size_t P = p.P;
+  std::vector<int32_t> st(P * ST_N);
+  std::vector<double> ds(P * DS_N);
+  CU(cudaMemcpy(st.data(), p.stats + (size_t)env * P * ST_N, st.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(ds.data(), p.dstats + (size_t)env * P * DS_N, ds.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  if (task_id) CU(cudaMemcpy(task_id, p.task_id + (size_t)env * P, P * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (size_t a = 0; a < P; a++) {
+    if (completed) completed[a] = st[a * ST_N + ST_TASK_DONE];
+    if (reward_signals) reward_signals[a] = st[a * ST_N + ST_REWARD_SIGNALS];
+    if (max_progress) max_progress[a] = ds[a * DS_N + DS_MAX_PROGRESS];
+  }
+  return NM_OK;
+}
+
 extern "C" int nmmo_stats(nmmo_handle *h, double *sums, double *counts, uint64_t *counters, int clear) {
   if (!h) return fail(NM_ERR_ARG, "null handle");
   CU(cudaSetDevice(h->device));

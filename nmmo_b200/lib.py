@@ -20,7 +20,7 @@ EXPORTS = [
     "nmmo_create", "nmmo_destroy", "nmmo_reset", "nmmo_step", "nmmo_step_host", "nmmo_sample_actions",
     "nmmo_obs_ptr", "nmmo_reward_ptr", "nmmo_terminated_ptr", "nmmo_truncated_ptr", "nmmo_mask_ptr",
     "nmmo_info_ptr", "nmmo_info_valid_ptr", "nmmo_episode_done_ptr", "nmmo_obs_stride", "nmmo_num_envs",
-    "nmmo_num_agents", "nmmo_inject_rng", "nmmo_snapshot", "nmmo_stats", "nmmo_timing", "nmmo_timing_read", "nmmo_profile", "nmmo_set_obs_full", "nmmo_set_autosample",
+    "nmmo_num_agents", "nmmo_inject_rng", "nmmo_snapshot", "nmmo_task_state", "nmmo_stats", "nmmo_timing", "nmmo_timing_read", "nmmo_profile", "nmmo_set_obs_full", "nmmo_set_autosample",
     "nmmo_last_error",
     "nmmo_rollout_create", "nmmo_rollout_destroy", "nmmo_rollout_reset", "nmmo_rollout_store", "nmmo_rollout_ptr",
     "nmmo_rollout_gae", "nmmo_rollout_buffer", "nmmo_rollout_last_error",
@@ -69,6 +69,8 @@ def load(build_if_missing: bool = True):
     L.nmmo_inject_rng.argtypes = [vp, C.c_int, vp, vp, C.c_int]
     L.nmmo_snapshot.restype = C.c_int
     L.nmmo_snapshot.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    L.nmmo_task_state.restype = C.c_int
+    L.nmmo_task_state.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.nmmo_stats.restype = C.c_int
     L.nmmo_stats.argtypes = [vp, vp, vp, vp, C.c_int]
     L.nmmo_timing.restype = C.c_int
@@ -226,6 +228,13 @@ class Simulator:
         sc = np.zeros(16, np.int32)
         self._check(self.L.nmmo_snapshot(self.h, int(env), _p(ent), _p(items), _p(mp), _p(sc)))
         return ent, items, mp, sc
+
+    def task_state(self, env: int):
+        """(task_id, completed tick, reward_signal_count, max_progress) of one env's agents (stat_wrapper.py:155-159)."""
+        tid = np.zeros(self.P, np.int32); comp = np.zeros(self.P, np.int32); sig = np.zeros(self.P, np.int32)
+        mp = np.zeros(self.P, np.float64)
+        self._check(self.L.nmmo_task_state(self.h, int(env), _p(tid), _p(comp), _p(sig), _p(mp)))
+        return tid, comp, sig, mp
 
     def stats(self, clear: bool = False):
         sums = np.zeros(SPEC["IN_N"], np.float64); counts = np.zeros(SPEC["IN_N"], np.float64)

@@ -202,6 +202,20 @@ def test_env_view_matches_oracle():
             off, n = L.masks["Move.Direction"]
             assert np.array_equal(obs[ag]["ActionTargets"]["Move"]["Direction"], o.obs[ag - 1][off:off + n].view(np.int8))
             assert np.float32(rew[ag]) == o.rewards[ag - 1] and term[ag] == bool(o.terminated[ag - 1])
+        # the secondary boundary of SURVEY.md 8(b): realm.tick / realm.players / dead_this_tick / agent_task_map / config
+        realm = env.realm
+        oe, _, _ = o.snapshot()
+        assert realm.tick == o.tick and env.config.COMBAT_SPAWN_IMMUNITY == int(world[0][S["NC_SPAWN_IMMUNITY"]])
+        assert sorted(realm.players) == [p + 1 for p in range(env.P) if oe[p, S["EA_STATUS"]] == 1]
+        assert sorted(realm.players.dead_this_tick) == [p + 1 for p in range(env.P) if oe[p, S["EA_STATUS"]] == 2]
+        for ag, pl in realm.players.items():
+            assert pl.health.val == oe[ag - 1, S["EA_HEALTH"]] and pl.food.val == oe[ag - 1, S["EA_FOOD"]] and pl.gold.val == oe[ag - 1, S["EA_GOLD"]]
+            assert pl.history.damage_inflicted == oe[ag - 1, S["EA_DMG_INFLICTED"]] and pl.fishing_exp.val == oe[ag - 1, S["EA_FISHING_EXP"]]
+        tid, comp, sig, mp = o.task_state()
+        tmap = env.agent_task_map
+        for p in range(env.P):
+            tk = tmap[p + 1][0]
+            assert tk.spec_name == f"task_{tid[p]}" and tk.completed == bool(comp[p]) and tk.reward_signal_count == sig[p] and tk._max_progress == mp[p]
         if o.episode_done:
             assert env.agents == [] and any(i.get("episode_done") for i in infos.values())
             break
