@@ -119,6 +119,31 @@ def test_default_config_full_size():
     sim.close()
 
 
+@pytest.mark.parametrize("P,N,center,E,over", [
+    (8, 16, 24, 7, dict(NC_RES_DEPLETION=1, NC_SPAWN_IMMUNITY=1)),                      # tiny, odd env count
+    (40, 120, 48, 5, dict(NC_RES_DEPLETION=2, NC_NPC_SPAWN_ATTEMPTS=32)),              # more NPCs than threads / 2
+    (104, 296, 96, 3, dict(NC_RES_DEPLETION=3, NC_SPAWN_IMMUNITY=5)),                  # R = 400: second row per thread used
+    (256, 256, 128, 2, dict(NC_RES_DEPLETION=4)),                                      # the player limit (one thread per player)
+    (64, 64, 32, 4, dict(NC_RES_DEPLETION=1, NC_REACH=5, NC_VISION=7, NC_NPC_VISION=7, NC_LISTING_DURATION=1)),
+])
+def test_shape_sweep(P, N, center, E, over):
+    # shapes away from the default: thread/row mappings, bitmap word counts, hash-table loads, odd E
+    world = build_world(task_dim=64, NC_N_PLAYERS=P, NC_N_NPCS=N, NC_MAP_CENTER=center, NC_HORIZON=70, **over)
+    sim, oracles = _make(world, E)
+    stats = run_parity(sim, oracles, seeds=np.arange(E) + 1000 + P, ticks=80, check_state_every=20)
+    assert stats["infos"] > 0
+    sim.close()
+
+
+def test_many_seeds_rich():
+    # breadth over seeds: 48 small envs with long-lived agents (items, market, combat, level-ups, kills)
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=150, NC_RES_DEPLETION=1, NC_SPAWN_IMMUNITY=2, NC_WEAPON_DROP_THR=1 << 29)
+    sim, oracles = _make(world, 48)
+    stats = run_parity(sim, oracles, seeds=np.arange(48) * 7919 + 17, ticks=160, check_state_every=40)
+    assert stats["episodes_done"] >= 48
+    sim.close()
+
+
 def test_one_env_per_cta_fallback(monkeypatch):
     # configurations whose tables do not fit twice in a CTA's shared memory run one environment per CTA
     monkeypatch.setenv("NMMO_B200_ENVS_PER_CTA", "1")
