@@ -1329,7 +1329,18 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   // sequential position.  The lowest pending attack is always ready, so every round progresses.
   {
     const uint32_t DONE = 0xffffffffu;
-    if (warp == 0) {
+    // pending attacks in attacker-row order (= the reference's execution order).  Every thread looks at its own
+    // rows first: most ticks of a quiet environment have no attack at all and skip the ordered build.
+    bool mine_any = false;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int r = tid + k * T;
+      int tgt = 0;
+      if (r < P) tgt = ctx.act[A_ATT_TARGET * P + r]; else if (r < R) tgt = ctx.npc_att[r - P];
+      mine_any |= tgt != 0 && tgt - 1 != r && ent_alive(ctx, r);
+    }
+    if (tid == 0) ctx.sc[6] = 0;
+    if (half_or(mine_any, half) && warp == 0) {
       int na = 0;
       for (int base = 0; base < R; base += 32) {
         int r = base + lane;
