@@ -234,8 +234,9 @@ def run_native(args):
     # to a scratch tensor) so the kernels do the same work as in the device-timed region.
     n = E * P
     e2e_steps = max(4, min(args.steps, 32))
-    pre = args.warmup + args.steps - e2e_steps
-    tape = torch.empty((e2e_steps, E, P, 12), dtype=torch.int32).pin_memory()
+    e2e_warm = 3                                           # untimed host-buffer steps (first-use costs: pinned result buffers)
+    pre = max(0, args.warmup + args.steps - e2e_steps - e2e_warm)
+    tape = torch.empty((e2e_warm + e2e_steps, E, P, 12), dtype=torch.int16).pin_memory()      # int16: nmmo_step_host_i16
     sim.set_autosample(args.seed, sim.actions)
     sim.reset(seeds)
     # (the first ticks after a reset, when nearly every agent is still alive, are timed on the way: this is the
@@ -256,8 +257,8 @@ def run_native(args):
              "what": "the first ticks after reset (nearly all agents alive)"} if early_n > 0 else None
     for _ in range(pre - early_n):
         tick(args.seed)
-    for k in range(e2e_steps):
-        tape[k].copy_(sim.actions)
+    for k in range(e2e_warm + e2e_steps):
+        tape[k].copy_(sim.actions.to(torch.int16))      # narrowed on the device, like a GPU policy would
         tick(args.seed)
     torch.cuda.synchronize()
     sim.reset(seeds)
@@ -267,15 +268,17 @@ def run_native(args):
     torch.cuda.synchronize()
     sim.set_autosample(args.seed, scratch)
     tape_np = tape.numpy()
+    for k in range(e2e_warm):
+        sim.step_host(tape_np[k])
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(stream)
-    for k in range(e2e_steps):
+    for k in range(e2e_warm, e2e_warm + e2e_steps):
         sim.step_host(tape_np[k])                        # H2D actions, step, D2H reward/term/trunc/mask
     f1.record(stream)
     barrier()
     ms_e2e = f0.elapsed_time(f1)
-    h2d = n * 12 * 4
+    h2d = n * 12 * 2
     d2h = n * (4 + 3)
     # ---- reduce over ranks --------------------------------------------------------------
     t = torch.tensor([ms_total, ms_e2e, step_ms, obs_ms, obs_ms_dense], dtype=torch.float64, device="cuda")
@@ -336,7 +339,7 @@ def run_native(args):
                          "dense_equivalent_gbs": n * b_obs / (obs_ms * 1e-3) / 1e9},
             "e2e": {"value": world_size * n * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "path": "nmmo_step_host (C ABI): actions from pinned host memory in, reward/term/trunc/mask to pinned host memory out, every "
+                    "path": "nmmo_step_host_i16 (C ABI): int16 actions from pinned host memory in, reward/term/trunc/mask to pinned host memory out, every "
                             "step; observations stay on the device where the policy reads them; actions = tape of the device-resident run"},
             "steady_state": steady, "early_window": early,
             "gpu_launches": 2 * args.steps,

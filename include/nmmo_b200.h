@@ -66,6 +66,11 @@ int nmmo_step(nmmo_handle *h, const int32_t *actions_dev, void *stream);
  * E*P*stride bytes.  Synchronises `stream` before returning. */
 int nmmo_step_host(nmmo_handle *h, const int32_t *actions_host, float *rew_out, uint8_t *term_out,
                    uint8_t *trunc_out, uint8_t *mask_out, uint8_t *obs_out, void *stream);
+/* The same with int16 actions (every head is narrower than 32768 entries): half the bytes over the
+ * host link, which is what bounds this call.  A caller whose policy runs on the GPU narrows there
+ * (`actions.to(torch.int16).cpu()`) before the copy the reference makes at clean_pufferl.py:329. */
+int nmmo_step_host_i16(nmmo_handle *h, const int16_t *actions_host, float *rew_out, uint8_t *term_out,
+                       uint8_t *trunc_out, uint8_t *mask_out, uint8_t *obs_out, void *stream);
 
 /* Uniform-random valid actions from the current ActionTargets masks (BASELINE.json config 2),
  * keyed (seed, global env, tick, agent, head); writes DEVICE int32 [E][P][12]. */

@@ -28,6 +28,7 @@ struct nmmo_handle {
   size_t step_smem, obs_smem;
   std::vector<void *> allocs;
   int32_t *d_actions;             // staging for the host-buffer path
+  int16_t *d_actions16;           // ... and for its int16 variant
   // injected rng (host mirror, rebuilt on change)
   std::vector<std::vector<std::pair<uint64_t, uint32_t>>> inj;
   uint64_t *d_inj_keys; uint32_t *d_inj_vals; int32_t *d_inj_off;
@@ -133,6 +134,7 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   DA(p.info, E * P * IN_N); DA(p.info_valid, E * P); DA(p.episode_done, E);
   DA(p.agg, (size_t)NM_AGG_REP * 2 * IN_N); DA(p.counters, 8); DA(p.obs_meta, E * P);
   DA(h->d_actions, E * P * AC_N);
+  DA(h->d_actions16, E * P * AC_N);
   DA(h->d_inj_off, E + 1);
   DA(h->d_env_mask, E);
   h->d_inj_keys = nullptr; h->d_inj_vals = nullptr;
@@ -247,6 +249,48 @@ extern "C" int nmmo_step_host(nmmo_handle *h, const int32_t *actions_host, float
   if (obs_out) CU(cudaMemcpyAsync(obs_out, p.obs, n * p.L.stride, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return NM_OK;
+}
+
+__global__ void nmmo_widen_actions_kernel(const int16_t *src, int32_t *dst, size_t n8) {
+  // 8 actions per thread: one 16-byte load, two 16-byte stores
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = ((const uint4 *)src)[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    int4 lo, hi;
+    lo.x = (int16_t)(w[0] & 0xffffu); lo.y = (int16_t)(w[0] >> 16); lo.z = (int16_t)(w[1] & 0xffffu); lo.w = (int16_t)(w[1] >> 16);
+    hi.x = (int16_t)(w[2] & 0xffffu); hi.y = (int16_t)(w[2] >> 16); hi.z = (int16_t)(w[3] & 0xffffu); hi.w = (int16_t)(w[3] >> 16);
+    ((int4 *)dst)[2 * i] = lo; ((int4 *)dst)[2 * i + 1] = hi;
+  }
+}
+
+static int finish_step_host(nmmo_handle *h, float *rew_out, uint8_t *term_out, uint8_t *trunc_out, uint8_t *mask_out,
+                            uint8_t *obs_out, cudaStream_t st) {
+  NmParams &p = h->prm;
+  size_t n = (size_t)p.E * p.P;
+  p.actions = h->d_actions;
+  int rc = launch_step(h, 0, st);
+  if (rc) return rc;
+  if (rew_out) CU(cudaMemcpyAsync(rew_out, p.rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (term_out) CU(cudaMemcpyAsync(term_out, p.term, n, cudaMemcpyDeviceToHost, st));
+  if (trunc_out) CU(cudaMemcpyAsync(trunc_out, p.trunc, n, cudaMemcpyDeviceToHost, st));
+  if (mask_out) CU(cudaMemcpyAsync(mask_out, p.mask, n, cudaMemcpyDeviceToHost, st));
+  if (obs_out) CU(cudaMemcpyAsync(obs_out, p.obs, n * p.L.stride, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return NM_OK;
+}
+
+extern "C" int nmmo_step_host_i16(nmmo_handle *h, const int16_t *actions_host, float *rew_out, uint8_t *term_out,
+                                  uint8_t *trunc_out, uint8_t *mask_out, uint8_t *obs_out, void *stream) {
+  if (!h || !actions_host) return fail(NM_ERR_ARG, "null argument");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t n12 = (size_t)h->prm.E * h->prm.P * AC_N;
+  CU(cudaMemcpyAsync(h->d_actions16, actions_host, n12 * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+  size_t n8 = n12 / 8;      // P * 12 is a multiple of 8 for every supported P (P+N and the item cap are)
+  if (n12 % 8) return fail(NM_ERR_LIMIT, "E * P * 12 must be a multiple of 8 for the int16 action path");
+  nmmo_widen_actions_kernel<<<(unsigned)std::min<size_t>((n8 + 255) / 256, 148 * 8), 256, 0, st>>>(h->d_actions16, h->d_actions, n8);
+  CU(cudaGetLastError());
+  return finish_step_host(h, rew_out, term_out, trunc_out, mask_out, obs_out, st);
 }
 
 extern "C" int nmmo_sample_actions(nmmo_handle *h, uint64_t seed, int32_t *actions_dev, void *stream) {

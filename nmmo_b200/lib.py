@@ -17,7 +17,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "_build" / "libnmmo_b200.so"
 _lib = None
 
 EXPORTS = [
-    "nmmo_create", "nmmo_destroy", "nmmo_reset", "nmmo_step", "nmmo_step_host", "nmmo_sample_actions",
+    "nmmo_create", "nmmo_destroy", "nmmo_reset", "nmmo_step", "nmmo_step_host", "nmmo_step_host_i16", "nmmo_sample_actions",
     "nmmo_obs_ptr", "nmmo_reward_ptr", "nmmo_terminated_ptr", "nmmo_truncated_ptr", "nmmo_mask_ptr",
     "nmmo_info_ptr", "nmmo_info_valid_ptr", "nmmo_episode_done_ptr", "nmmo_obs_stride", "nmmo_num_envs",
     "nmmo_num_agents", "nmmo_inject_rng", "nmmo_snapshot", "nmmo_task_state", "nmmo_stats", "nmmo_timing", "nmmo_timing_read", "nmmo_profile", "nmmo_set_obs_full", "nmmo_set_autosample",
@@ -56,6 +56,8 @@ def load(build_if_missing: bool = True):
     L.nmmo_step.argtypes = [vp, vp, vp]
     L.nmmo_step_host.restype = C.c_int
     L.nmmo_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.nmmo_step_host_i16.restype = C.c_int
+    L.nmmo_step_host_i16.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.nmmo_sample_actions.restype = C.c_int
     L.nmmo_sample_actions.argtypes = [vp, C.c_uint64, vp, vp]
     for n in ("nmmo_obs_ptr", "nmmo_reward_ptr", "nmmo_terminated_ptr", "nmmo_truncated_ptr", "nmmo_mask_ptr",
@@ -200,8 +202,10 @@ class Simulator:
         self._check(self.L.nmmo_step(self.h, C.c_void_p(a.data_ptr()), self._stream()))
 
     def step_host(self, actions: np.ndarray, want_obs: bool = False):
-        """Host-buffer call: actions int32 [E,P,12] in host memory (pinned = async copies)."""
-        a = np.ascontiguousarray(actions, np.int32).reshape(self.E, self.P, 12)
+        """Host-buffer call: actions int32 (or int16: half the bytes over the host link) [E,P,12] in host memory
+        (pinned = async copies)."""
+        i16 = getattr(actions, "dtype", None) == np.int16
+        a = np.ascontiguousarray(actions, np.int16 if i16 else np.int32).reshape(self.E, self.P, 12)
         n = self.E * self.P
         if getattr(self, "_host_out", None) is None:
             t = self.torch
@@ -209,7 +213,8 @@ class Simulator:
                               t.empty(n, dtype=t.uint8).pin_memory(), t.empty(n, dtype=t.uint8).pin_memory())
         rew, term, trunc, mask = (x.numpy() for x in self._host_out)
         obs = np.empty((n, self.stride), np.uint8) if want_obs else None
-        self._check(self.L.nmmo_step_host(self.h, _p(a), _p(rew), _p(term), _p(trunc), _p(mask), _p(obs), self._stream()))
+        fn = self.L.nmmo_step_host_i16 if i16 else self.L.nmmo_step_host
+        self._check(fn(self.h, _p(a), _p(rew), _p(term), _p(trunc), _p(mask), _p(obs), self._stream()))
         return rew, term, trunc, mask, obs
 
     def sample_actions(self, seed: int, out=None):

@@ -116,19 +116,20 @@ def test_env_sharding_invariance():
 def test_step_host_equals_device_step():
     import torch
     world = build_world(task_dim=64, **SMALL, NC_HORIZON=60)
-    a, b = _sim(world, 2), _sim(world, 2)
-    a.reset([1, 2]); b.reset([1, 2])
+    a, b, c = _sim(world, 2), _sim(world, 2), _sim(world, 2)
+    a.reset([1, 2]); b.reset([1, 2]); c.reset([1, 2])
     for t in range(40):
         a.sample_actions(4)
         torch.cuda.synchronize()
         acts = a.actions.cpu().numpy()
         a.step()
-        rew, term, trunc, mask, obs = b.step_host(acts, want_obs=True)
-        torch.cuda.synchronize()
-        assert np.array_equal(rew, a.rewards.cpu().numpy()) and np.array_equal(term, a.terminated.cpu().numpy())
-        assert np.array_equal(trunc, a.truncated.cpu().numpy()) and np.array_equal(mask, a.mask.cpu().numpy())
-        assert np.array_equal(obs, a.obs.cpu().numpy())
-    a.close(); b.close()
+        for other, host_acts in ((b, acts), (c, acts.astype(np.int16))):      # int32 and int16 host-buffer calls
+            rew, term, trunc, mask, obs = other.step_host(host_acts, want_obs=True)
+            torch.cuda.synchronize()
+            assert np.array_equal(rew, a.rewards.cpu().numpy()) and np.array_equal(term, a.terminated.cpu().numpy())
+            assert np.array_equal(trunc, a.truncated.cpu().numpy()) and np.array_equal(mask, a.mask.cpu().numpy())
+            assert np.array_equal(obs, a.obs.cpu().numpy())
+    a.close(); b.close(); c.close()
 
 
 def test_dense_and_incremental_writers_agree():
