@@ -2,14 +2,16 @@
 //
 // Replaces, per agent and per tick, nmmo's Observation.to_gym()/_make_action_targets()
 // [UPSTREAM nmmo/core/observation.py], the RewardWrapper.observation() mask edits
-// (agent_zoo/takeru/reward_wrapper.py:25-37, agent_zoo/neurips23_start_kit/reward_wrapper.py:46-54)
+// (agent_zoo/takeru/reward_wrapper.py:25-37, agent_zoo/neurips23_start_kit/reward_wrapper.py:46-54,
+// agent_zoo/yaofeng/reward_wrapper.py:65-83)
 // and pufferlib's flatten + pad of the nested observation (reinforcement_learning/environment.py:73),
 // writing the flat record the policy reads on-device (agent_zoo/takeru/policy.py:39-64).
 //
-// One CTA per environment.  The entity table (31 observed columns + status), the item table and
-// the tile map are staged into shared memory with TMA bulk copies; the env-global Market block
-// is built once in shared memory; then each warp assembles whole agent records and streams them
-// out with 16-byte st.global.cs stores, 512 contiguous bytes per warp instruction.
+// One CTA per environment, three CTAs per SM.  The entity table (31 observed columns + status), the
+// live prefix of the item table and the 4-bit tile map are staged into shared memory with TMA bulk
+// copies; the env-global Market block is built once in shared memory; the agents that need a record
+// are compacted into a work list the warps pull from; each warp assembles whole agent records and
+// streams them out with 16-byte st.global.cs stores, 512 contiguous bytes per warp instruction.
 #include "nmmo_device.cuh"
 
 namespace {

@@ -5,16 +5,16 @@
 //   nmmo.Env.step  (call site reinforcement_learning/stat_wrapper.py:64)   -> phases 0..13
 //   BaseStatWrapper.step / _process_stats_and_early_stop (stat_wrapper.py:57-185),
 //   process_event_log (:216-288), count_unique_events (:295-310)           -> phases 14..15
-//   agent_zoo/{takeru,neurips23_start_kit}/reward_wrapper.py reward hooks  -> phase 15
+//   agent_zoo/{takeru,neurips23_start_kit,yaofeng}/reward_wrapper.py reward hooks  -> phase 15
 //
-// Execution model.  The environment's tables are pulled into shared memory by three TMA bulk
-// copies, every phase runs out of shared memory, and the tables are pushed back with bulk
-// stores.  Phases whose reference semantics are order-free across agents (validation, NPC
-// decide, resource update, Use, Destroy, Sell, cull, respawn, event folding, rewards) run one
-// thread per entity.  Phases the reference executes in entity-id order (harvest drops, Buy,
-// Give, Attack, Move with one-entity-per-tile) are resolved by warp 0 in id order: candidates
-// are found 32 at a time with a ballot and the elected lane applies them, so an idle entity
-// costs nothing.
+// Execution model.  The environment's tables (entity table, 4-bit tile map, the live prefix of the
+// item table) are pulled into shared memory by TMA bulk copies, every phase runs out of shared
+// memory, and the tables are pushed back with bulk stores.  Phases whose reference semantics are
+// order-free across agents (validation, NPC decide, resource update, Use, Destroy, Sell, cull,
+// respawn, event folding, rewards) run one thread per entity.  Phases the reference executes in
+// entity-id order keep that order exactly: harvest drops and Buy / Give by ballot-compacted
+// sequential sections, Attack by rounds over entity-disjoint attacks, Move by a local decision per
+// mover from a position index (see the comments at each phase).
 #include "nmmo_device.cuh"
 
 namespace {
