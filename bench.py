@@ -155,7 +155,19 @@ def run_native(args):
         raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local_rank)
     if world_size > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL writes its version banner to stdout when the communicator is created; stdout carries exactly one
+        # JSON line, so the communicator is created (init + one barrier) with fd 1 pointed at stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     w = world(args.agent)
     cfg = w[0]
     E, P = args.envs, int(cfg[SPEC["NC_N_PLAYERS"]])
