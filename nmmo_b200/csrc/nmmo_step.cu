@@ -1576,8 +1576,9 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       if (draw(ctx, RS_RESPAWN, (uint32_t)i, 0) < (uint32_t)c[thr_idx]) tile_inc(ctx, i);
     };
     if (tid == 0) ctx.sc[5] = 0;
-    if (warp == 1) {
-      // new high-water mark of the item table: no row is allocated or freed after the cull
+    HSYNC();
+    if (warp == (T >> 5) - 1) {      // the last warp has one scan pass fewer than warp 0: it also finds the
+      // new high-water mark of the item table (no row is allocated or freed after the cull)
       int hi = 0;
       for (int w0 = 0; w0 < cap_words; w0 += 32) {
         uint32_t u = w0 + lane < cap_words ? ctx.used[w0 + lane] : 0u;
@@ -1586,7 +1587,6 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       }
       if (lane == 0) ctx.sc[9] = (hi + 7) & ~7;
     }
-    HSYNC();
     for (int q0 = 0; q0 < n_quads; q0 += T) {       // block-uniform trip count: the append below is warp-wide
       const int q = q0 + tid;
       uint32_t hits[4] = {0, 0, 0, 0};
