@@ -117,8 +117,13 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   p.half_smem = (int)((h->step_smem + 127) & ~(size_t)127);
   p.envs_per_cta = 2 * p.half_smem <= max_smem ? 2 : 1;
   if (const char *ov = getenv("NMMO_B200_ENVS_PER_CTA")) { if (atoi(ov) == 1) p.envs_per_cta = 1; }      // test hook
-  CU(cudaFuncSetAttribute(nmmo_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.envs_per_cta * p.half_smem));
-  CU(cudaFuncSetAttribute(nmmo_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->obs_smem));
+  {   // the opt-in limit is a property of the kernel, not of the handle: several handles of different shapes may
+      // be alive in one process, so it only ever grows (per device)
+    static int step_attr[64] = {0}, obs_attr[64] = {0};
+    const int need_step = p.envs_per_cta * p.half_smem, need_obs = (int)h->obs_smem, d = device & 63;
+    if (need_step > step_attr[d]) { CU(cudaFuncSetAttribute(nmmo_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_step)); step_attr[d] = need_step; }
+    if (need_obs > obs_attr[d]) { CU(cudaFuncSetAttribute(nmmo_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_obs)); obs_attr[d] = need_obs; }
+  }
   size_t E = p.E, P = p.P;
   DA(p.ent, E * EA_N * p.R); DA(p.item, E * IS_N * p.CAP); DA(p.map, E * p.S * p.S / 2);
   uint8_t *dmaps; DA(dmaps, (size_t)n_maps * p.S * p.S); p.maps = dmaps;

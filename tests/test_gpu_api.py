@@ -113,6 +113,20 @@ def test_env_sharding_invariance():
     whole.close(); part.close()
 
 
+def test_handles_of_different_shapes_coexist():
+    # the kernels' dynamic shared-memory opt-in is process-wide: creating a small handle must not break a big one
+    import torch
+    big = _sim(build_world(task_dim=64, NC_N_PLAYERS=64, NC_N_NPCS=128, NC_MAP_CENTER=64, NC_HORIZON=30), 2)
+    big.reset([1, 2])
+    small = _sim(build_world(task_dim=64, **SMALL, NC_HORIZON=30), 2)
+    small.reset([3, 4])
+    for _ in range(5):
+        big.sample_actions(1); big.step(); small.sample_actions(1); small.step()
+    torch.cuda.synchronize()
+    assert int(big.mask.sum()) > 0 and int(small.mask.sum()) > 0
+    big.close(); small.close()
+
+
 def test_step_host_equals_device_step():
     import torch
     world = build_world(task_dim=64, **SMALL, NC_HORIZON=60)
