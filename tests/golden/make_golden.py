@@ -317,6 +317,11 @@ def main():
     run_case("start_kit_small", "neurips23_start_kit", 140, 5, NC_HORIZON=100, NC_RES_DEPLETION=2, NC_SPAWN_IMMUNITY=3)
     run_case("takeru_eval_nocustom", "takeru", 90, 7, wrapper_over={"eval_mode": True, "use_custom_reward": False, "early_stop_agent_num": 4},
              NC_HORIZON=80, NC_RES_DEPLETION=3)
+    run_case("start_kit_nocustom_prefix", "neurips23_start_kit", 80, 11, wrapper_over={"use_custom_reward": False, "early_stop_agent_num": 12},
+             NC_HORIZON=70, NC_RES_DEPLETION=3)
+    run_case("yaofeng_eval", "yaofeng", 120, 13, wrapper_over={"eval_mode": True, "early_stop_agent_num": 0, "donot_attack_dangerous_npc": False,
+                                                               "disable_give": False, "custom_bonus_scale": 1.0},
+             NC_HORIZON=100, NC_RES_DEPLETION=2, NC_SPAWN_IMMUNITY=2)
     # slow starvation + fast item drops: combat, equipment (defense bonus), gold and exp all move
     run_case("yaofeng_small", "yaofeng", 200, 9, wrapper_over={"attack_bonus_weight": 0.005, "early_stop_agent_num": 2},
              NC_HORIZON=180, NC_RES_DEPLETION=1, NC_SPAWN_IMMUNITY=3, NC_WEAPON_DROP_THR=1 << 30)
