@@ -1587,40 +1587,41 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       }
       if (lane == 0) ctx.sc[9] = (hi + 7) & ~7;
     }
-    for (int q0 = 0; q0 < n_quads; q0 += T) {       // block-uniform trip count: the append below is warp-wide
-      const int q = q0 + tid;
-      uint32_t hits[4] = {0, 0, 0, 0};
-      int cnt = 0;
-      if (q < n_quads) {
-        const uint4 v = ((const uint4 *)ctx.map)[q];
-        const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          // depleted materials are 3, 6 and the even ones from 8 up: bit-sliced test of all 8 nibbles
-          const uint32_t x = xs[j], x1 = x >> 1, x2 = x >> 2, x3 = x >> 3;
-          hits[j] = ((x3 & ~x) | (~x3 & x1 & (x2 ^ x))) & 0x11111111u;
-          cnt += __popc(hits[j]);
-        }
-      }
-      if (!__any_sync(0xffffffffu, cnt)) continue;
-      // one shared-memory atomic per warp: exclusive scan of the lane counts
+    // depleted materials are 3, 6 and the even ones from 8 up: bit-sliced test of all 8 nibbles of a word
+    auto hits_of = [](uint32_t x) -> uint32_t {
+      const uint32_t x1 = x >> 1, x2 = x >> 2, x3 = x >> 3;
+      return ((x3 & ~x) | (~x3 & x1 & (x2 ^ x))) & 0x11111111u;
+    };
+    // pass 1 counts this thread's hits over all its quads, one scan + one shared-memory atomic per warp reserves
+    // the worklist slots, pass 2 re-tests the same words (cheaper than keeping the masks) and fills them in
+    int cnt = 0;
+    for (int q = tid; q < n_quads; q += T) {
+      const uint4 v = ((const uint4 *)ctx.map)[q];
+      cnt += __popc(hits_of(v.x)) + __popc(hits_of(v.y)) + __popc(hits_of(v.z)) + __popc(hits_of(v.w));
+    }
+    if (__any_sync(0xffffffffu, cnt)) {
       int incl = cnt;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
       int base = 0;
       if (lane == 31) base = atomicAdd(&ctx.sc[5], incl);
       int k = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+      if (cnt)
+        for (int q = tid; q < n_quads; q += T) {
+          const uint4 v = ((const uint4 *)ctx.map)[q];
+          const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        uint32_t hit = hits[j];
-        while (hit) {
-          int b = __ffs(hit) - 1; hit &= hit - 1;
-          int i = (q * 4 + j) * 8 + (b >> 2);
-          if (k < wl_cap) wl[k] = (uint16_t)i;
-          else respawn_tile(i, tile_i(ctx, i));          // worklist full: draw in place
-          k++;
+          for (int j = 0; j < 4; j++) {
+            uint32_t hit = hits_of(xs[j]);
+            while (hit) {
+              int b = __ffs(hit) - 1; hit &= hit - 1;
+              int i = (q * 4 + j) * 8 + (b >> 2);
+              if (k < wl_cap) wl[k] = (uint16_t)i;
+              else respawn_tile(i, tile_i(ctx, i));          // worklist full: draw in place
+              k++;
+            }
+          }
         }
-      }
     }
     HSYNC();
     int n = min(ctx.sc[5], wl_cap);
