@@ -48,7 +48,7 @@ static size_t step_smem_bytes(const NmParams &p) {
   s += a16((size_t)((p.S * p.S + 31) / 32) * 4); s += 2 * a16((size_t)((p.CAP + 31) / 32) * 4);
   s += a16((size_t)p.P * NINV * 2); s += a16(p.P); s += a16((size_t)12 * p.P * 2);
   s += a16(p.N); s += a16((size_t)p.N * 2); s += a16(NM_EV_CAP * 8); s += a16((size_t)p.P * 4) * 2; s += a16(64); s += 16;
-  s += a16(1024); s += a16((size_t)p.P * 16); s += a16((size_t)p.P * 8); s += a16(std::max<size_t>(4096, (size_t)p.R * 8)); s += a16((size_t)p.R * 4); s += a16(p.P); s += a16((size_t)p.P * 4) + 64;
+  s += a16(1024); s += a16((size_t)p.P * 16); s += a16((size_t)p.P * 8); s += a16(std::max<size_t>(4096, (size_t)p.R * 8)); s += a16((size_t)p.R * 4); s += a16(NM_DEPL_CAP * 2); s += a16(p.P); s += a16((size_t)p.P * 4) + 64;
   return s + 128;
 }
 static size_t obs_smem_bytes(const NmParams &p) {
@@ -116,6 +116,7 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   // the step kernel runs two environments per CTA (they walk the code together) when both fit
   p.half_smem = (int)((h->step_smem + 127) & ~(size_t)127);
   p.envs_per_cta = 2 * p.half_smem <= max_smem ? 2 : 1;
+  if (getenv("NMMO_B200_NO_DEPL_LIST")) p.no_depl_list = 1;      // test hook
   if (const char *ov = getenv("NMMO_B200_ENVS_PER_CTA")) { if (atoi(ov) == 1) p.envs_per_cta = 1; }      // test hook
   {   // the opt-in limit is a property of the kernel, not of the handle: several handles of different shapes may
       // be alive in one process, so it only ever grows (per device)
@@ -128,7 +129,7 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   DA(p.ent, E * EA_N * p.R); DA(p.item, E * IS_N * p.CAP); DA(p.map, E * p.S * p.S / 2);
   uint8_t *dmaps; DA(dmaps, (size_t)n_maps * p.S * p.S); p.maps = dmaps;
   CU(cudaMemcpy(dmaps, maps, (size_t)n_maps * p.S * p.S, cudaMemcpyHostToDevice));
-  DA(p.scalars, E * NM_SC_N); DA(p.seed, E); DA(p.danger, E * p.N);
+  DA(p.scalars, E * NM_SC_N); DA(p.seed, E); DA(p.danger, E * p.N); DA(p.depl, E * NM_DEPL_CAP);
   DA(p.stats, E * P * ST_N); DA(p.dstats, E * P * DS_N); DA(p.uniq, E * P * NM_UNIQ_WORDS); DA(p.task_id, E * P);
   int32_t *dtasks; DA(dtasks, (size_t)n_tasks * NM_TASK_COLS); p.tasks = dtasks;
   CU(cudaMemcpy(dtasks, tasks, sizeof(int32_t) * n_tasks * NM_TASK_COLS, cudaMemcpyHostToDevice));

@@ -18,13 +18,15 @@
 #define NM_STEP_THREADS 256
 #define NM_OBS_THREADS 256
 #define NM_SC_N 16              // per-env int32 scalars
+#define NM_DEPL_CAP 1024         // per-env list of depleted tiles kept across ticks (falls back to a map scan beyond)
 #define NM_AGG_REP 256           // replicas of the finished-agent sums (contention spreading)
 #define OM_NONZERO (1u << 16)
 #define OM_TASK (1u << 17)
 
 enum nm_scalar { SC_TICK = 0, SC_DONE, SC_NEXT_NPC_ID, SC_N_DANGER, SC_MAP_ID, SC_EPISODE, SC_FRESH,
                  SC_ERROR, SC_NEED_RESET, SC_EXPLICIT_MAP, SC_EXPLICIT_TASKS,
-                 SC_ITEM_HI /* rows >= this are free; multiple of 8 */ };
+                 SC_ITEM_HI /* rows >= this are free; multiple of 8 */,
+                 SC_N_DEPL /* entries of the depleted-tile list; -1 = unknown, rebuild it from a map scan */ };
 
 struct NmParams {
   int32_t cfg[NC_COUNT];
@@ -39,6 +41,7 @@ struct NmParams {
   int32_t *scalars;            // [E][NM_SC_N]
   uint64_t *seed;              // [E]
   int16_t *danger;             // [E][N]
+  uint16_t *depl;              // [E][NM_DEPL_CAP] tile indices of the depleted tiles (unordered)
   int32_t *stats;              // [E][P][ST_N]
   double *dstats;              // [E][P][DS_N]
   uint32_t *uniq;              // [E][P][NM_UNIQ_WORDS]
@@ -59,6 +62,7 @@ struct NmParams {
   uint64_t sample_seed;
   unsigned long long *prof;    // optional [32] per-phase clock accumulators (NULL = off)
   int half_smem;               // step kernel: dynamic shared memory of one environment
+  int no_depl_list;            // test hook: never trust the depleted-tile list (always rebuild it from a map scan)
   int envs_per_cta;            // step kernel: 2 when two environments fit in one CTA's shared memory, else 1
   int mode;                    // 0 step (auto-reset finished envs), 1 reset flagged envs only
   int env_base;                // global env index of env 0 (multi-GPU sharding; seeds derive from it)

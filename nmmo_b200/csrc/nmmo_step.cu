@@ -28,6 +28,7 @@ struct Ctx {
   int env, P, N, R, S, CAP, NINV;
   int16_t *ent, *item;
   uint32_t *map;            // 4-bit materials, 8 tiles per word
+  uint16_t *dlist;          // depleted tiles known at the start of the tick + the ones harvested during it (sc[17] = count)
   uint32_t *occ, *used, *fresh;
   uint16_t *inv;
   uint8_t *invn;
@@ -217,7 +218,11 @@ __device__ __forceinline__ int tile_i(const Ctx &ctx, int i) { return (ctx.map[i
 __device__ __forceinline__ int tile_at(const Ctx &ctx, int r, int c) { return tile_i(ctx, r * ctx.S + c); }
 // materials only ever change by one step (harvest: m -> m-1, respawn: m -> m+1) and never leave
 // 0..15, so an atomic add on the word is an exact update of one nibble under concurrent writers
-__device__ __forceinline__ void tile_dec(const Ctx &ctx, int i) { atomicSub(&ctx.map[i >> 3], 1u << ((i & 7) * 4)); }
+__device__ __forceinline__ void tile_dec(const Ctx &ctx, int i) {      // harvest: the tile joins the depleted list
+  atomicSub(&ctx.map[i >> 3], 1u << ((i & 7) * 4));
+  const int k = atomicAdd(&ctx.sc[17], 1);
+  if (k < NM_DEPL_CAP) ctx.dlist[k] = (uint16_t)i;
+}
 __device__ __forceinline__ void tile_inc(const Ctx &ctx, int i) { atomicAdd(&ctx.map[i >> 3], 1u << ((i & 7) * 4)); }
 __device__ __forceinline__ bool occ_get(const Ctx &ctx, int r, int c) { int i = r * ctx.S + c; return (ctx.occ[i >> 5] >> (i & 31)) & 1u; }
 __device__ __forceinline__ void occ_set(const Ctx &ctx, int r, int c) { int i = r * ctx.S + c; atomicOr(&ctx.occ[i >> 5], 1u << (i & 31)); }
@@ -950,7 +955,7 @@ __device__ __noinline__ void reset_env(const NmParams &P_, int env, uint64_t see
   if (tid == 0) {
     P_.seed[env] = seed;
     sc[SC_TICK] = 0; sc[SC_DONE] = 0; sc[SC_NEXT_NPC_ID] = -1; sc[SC_N_DANGER] = 0; sc[SC_MAP_ID] = map_id;
-    sc[SC_FRESH] = 1; sc[SC_ITEM_HI] = 0; sc[SC_NEED_RESET] = 0; sc[SC_EXPLICIT_MAP] = 0; sc[SC_EXPLICIT_TASKS] = 0;
+    sc[SC_FRESH] = 1; sc[SC_ITEM_HI] = 0; sc[SC_N_DEPL] = 0; sc[SC_NEED_RESET] = 0; sc[SC_EXPLICIT_MAP] = 0; sc[SC_EXPLICIT_TASKS] = 0;
     P_.episode_done[env] = 0;
   }
 }
@@ -1026,6 +1031,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   const size_t scratch_bytes = max((size_t)4096, (size_t)R * 8);
   uint32_t *s_scratch = (uint32_t *)carve(scratch_bytes);
   uint16_t *s_mv = (uint16_t *)carve((size_t)R * 4);        // Move phase: destination + verdict per row
+  ctx.dlist = (uint16_t *)carve(NM_DEPL_CAP * 2);
   uint32_t *s_att = s_scratch;
   int *s_first = (int *)(s_scratch + R);
   ctx.slow = (int8_t *)carve((size_t)P);
@@ -1045,12 +1051,15 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   }
   const int done_flag = gsc[SC_DONE];      // consumed below, after the other loads are in flight
   const int item_hi0 = gsc[SC_ITEM_HI];    // rows >= item_hi0 are free (multiple of 8)
+  const int n_depl0 = gsc[SC_N_DEPL];      // depleted tiles listed in prm.depl (-1: list unknown)
   if (tid == 0) {
     // Item rows are allocated lowest-free-first, so live rows crowd the low end of the table: only
     // the prefix below the high-water mark moves between HBM and shared memory.  Rows above it are
     // never read before they are allocated (the in-use bitmap is built from the prefix).
     const uint32_t col_bytes = (uint32_t)item_hi0 * 2;
-    mbar_expect_tx(bar + 1, col_bytes * IS_N);
+    const uint32_t dl_bytes = n_depl0 > 0 ? (uint32_t)((n_depl0 * 2 + 15) & ~15) : 0u;
+    mbar_expect_tx(bar + 1, col_bytes * IS_N + dl_bytes);
+    if (dl_bytes) bulk_g2s(ctx.dlist, prm.depl + (size_t)env * NM_DEPL_CAP, dl_bytes, bar + 1);
     if (col_bytes)
       for (int k = 0; k < IS_N; k++) bulk_g2s(ctx.item + k * CAP, gitem + (size_t)k * CAP, col_bytes, bar + 1);
   }
@@ -1089,7 +1098,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     ctx.acc[tid * 2] = my_acc0; ctx.acc[tid * 2 + 1] = my_acc1;
   }
   if (tid < 32) ctx.sc[tid] = 0;
-  if (tid == 0) { ctx.sc[2] = gsc[SC_N_DANGER]; ctx.sc[3] = gsc[SC_NEXT_NPC_ID]; }
+  if (tid == 0) { ctx.sc[2] = gsc[SC_N_DANGER]; ctx.sc[3] = gsc[SC_NEXT_NPC_ID]; ctx.sc[17] = max(n_depl0, 0); }
   if (done_flag) {      // episode over: this launch resets the environment instead of stepping it
     while (!mbar_try_wait(bar, 0)) {}      // the bulk copies must have landed before shared memory is reused
     while (!mbar_try_wait(bar + 1, 0)) {}
@@ -1575,7 +1584,10 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
                   : m == MT_FRAGMENT ? NC_RESPAWN_CRYSTAL : m == MT_WEEDS ? NC_RESPAWN_HERB : NC_RESPAWN_FISH;
       if (draw(ctx, RS_RESPAWN, (uint32_t)i, 0) < (uint32_t)c[thr_idx]) tile_inc(ctx, i);
     };
-    if (tid == 0) ctx.sc[5] = 0;
+    // The depleted tiles are known: the list carried over from last tick plus this tick's harvests (tile_dec).
+    // Only when the list is unknown (first use after an overflow) is the map scanned to rebuild it.
+    const bool list_ok = !prm.no_depl_list && n_depl0 >= 0 && ctx.sc[17] <= NM_DEPL_CAP;
+    if (tid == 0) { ctx.sc[5] = 0; ctx.sc[19] = 0; }
     HSYNC();
     if (warp == (T >> 5) - 1) {      // the last warp has one scan pass fewer than warp 0: it also finds the
       // new high-water mark of the item table (no row is allocated or freed after the cull)
@@ -1587,6 +1599,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       }
       if (lane == 0) ctx.sc[9] = (hi + 7) & ~7;
     }
+    if (!list_ok) {
     // depleted materials are 3, 6 and the even ones from 8 up: bit-sliced test of all 8 nibbles of a word
     auto hits_of = [](uint32_t x) -> uint32_t {
       const uint32_t x1 = x >> 1, x2 = x >> 2, x3 = x >> 3;
@@ -1623,9 +1636,35 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
           }
         }
     }
+    }
     HSYNC();
-    int n = min(ctx.sc[5], wl_cap);
-    for (int k = tid; k < n; k += T) { int i = wl[k]; respawn_tile(i, tile_i(ctx, i)); }
+    const uint16_t *src = list_ok ? ctx.dlist : wl;
+    uint16_t *dst = list_ok ? wl : ctx.dlist;
+    const int n_src = list_ok ? ctx.sc[17] : min(ctx.sc[5], wl_cap), dst_cap = list_ok ? wl_cap : NM_DEPL_CAP;
+    // one draw per depleted tile; the tiles that stay depleted form next tick's list
+    for (int k0 = 0; k0 < n_src; k0 += T) {
+      const int k = k0 + tid;
+      bool stays = false;
+      int i = 0;
+      if (k < n_src) {
+        i = src[k];
+        const int m = tile_i(ctx, i);
+        const int thr_idx = m == MT_SCRUB ? NC_RESPAWN_FOILAGE : m == MT_SLAG ? NC_RESPAWN_ORE : m == MT_STUMP ? NC_RESPAWN_TREE
+                          : m == MT_FRAGMENT ? NC_RESPAWN_CRYSTAL : m == MT_WEEDS ? NC_RESPAWN_HERB : NC_RESPAWN_FISH;
+        if (draw(ctx, RS_RESPAWN, (uint32_t)i, 0) < (uint32_t)c[thr_idx]) tile_inc(ctx, i); else stays = true;
+      }
+      const unsigned sm = __ballot_sync(0xffffffffu, stays);
+      int base = 0;
+      if (lane == 0 && sm) base = atomicAdd(&ctx.sc[19], __popc(sm));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (stays) { const int pos = base + __popc(sm & ((1u << lane) - 1)); if (pos < dst_cap) dst[pos] = (uint16_t)i; }
+    }
+    HSYNC();
+    if (tid == 0) {
+      const bool scan_overflow = !list_ok && ctx.sc[5] > wl_cap;      // tiles beyond the worklist drew in place and are not listed
+      ctx.sc[21] = (ctx.sc[19] <= NM_DEPL_CAP && !scan_overflow) ? ctx.sc[19] : -1;
+      ctx.sc[22] = list_ok ? 0 : 1;                                    // which buffer holds the new list: worklist scratch / dlist
+    }
   }
   // rows the table grew over this tick that are not in use must read as empty from now on
   for (int r = item_hi0 + tid; r < ctx.sc[9]; r += T)
@@ -1654,6 +1693,8 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     if (col_bytes)
       for (int k = 0; k < IS_N; k++) bulk_s2g(gitem + (size_t)k * CAP, ctx.item + k * CAP, col_bytes);
     bulk_s2g(prm.map + (size_t)env * map_bytes, ctx.map, map_bytes);
+    if (ctx.sc[21] > 0)
+      bulk_s2g(prm.depl + (size_t)env * NM_DEPL_CAP, ctx.sc[22] ? (const void *)ctx.dlist : (const void *)s_scratch, (uint32_t)((ctx.sc[21] * 2 + 15) & ~15));
     bulk_commit();
   }
 
@@ -1795,7 +1836,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   PCOUNT(27, n_alive); PCOUNT(28, n_dead);
   if (tid == 0) {
     gsc[SC_TICK] = ctx.tick; gsc[SC_DONE] = env_done ? 1 : 0; gsc[SC_N_DANGER] = ctx.sc[2]; gsc[SC_NEXT_NPC_ID] = ctx.sc[3];
-    gsc[SC_FRESH] = 0; gsc[SC_ITEM_HI] = ctx.sc[9];
+    gsc[SC_FRESH] = 0; gsc[SC_ITEM_HI] = ctx.sc[9]; gsc[SC_N_DEPL] = prm.no_depl_list ? -1 : ctx.sc[21];
     if (ctx.sc[1]) { gsc[SC_ERROR] |= 1; atomicAdd(&prm.counters[3], 1ULL); }
     prm.episode_done[env] = env_done ? 1 : 0;
     atomicAdd(&prm.counters[0], (unsigned long long)P);

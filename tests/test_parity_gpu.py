@@ -144,6 +144,15 @@ def test_many_seeds_rich():
     sim.close()
 
 
+def test_respawn_scan_fallback(monkeypatch):
+    # the depleted-tile list is distrusted every tick: respawn rebuilds it from the bit-sliced map scan
+    monkeypatch.setenv("NMMO_B200_NO_DEPL_LIST", "1")
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=120, NC_RES_DEPLETION=1)
+    sim, oracles = _make(world, 4)
+    run_parity(sim, oracles, seeds=np.arange(4) + 61, ticks=130, check_state_every=10)
+    sim.close()
+
+
 def test_one_env_per_cta_fallback(monkeypatch):
     # configurations whose tables do not fit twice in a CTA's shared memory run one environment per CTA
     monkeypatch.setenv("NMMO_B200_ENVS_PER_CTA", "1")
