@@ -84,10 +84,16 @@ class EnvView:
 
         return {p + 1: pick(nested, p) for p in range(self.P) if present[p]}
 
-    def reset(self, seed=0, **kw):
+    def reset(self, seed=0, new_task=None, **kw):
+        """``new_task`` = row of the task table every agent of this env gets for the episode: the task swap
+        SyllabusTaskWrapper.reset does through ``make_task_fn`` (/root/reference/syllabus_wrapper.py:129-150).
+        Without it the tasks are drawn from the table as on every other reset."""
         mask = np.zeros(self.sim.E, np.uint8); mask[self.k] = 1
         seeds = np.zeros(self.sim.E, np.uint64); seeds[self.k] = seed
-        self.sim.reset(seeds, env_mask=mask)
+        task_ids = None
+        if new_task is not None:
+            task_ids = np.zeros((self.sim.E, self.P), np.int32); task_ids[self.k] = int(new_task)
+        self.sim.reset(seeds, task_ids=task_ids, env_mask=mask)
         present = self._slice(self.sim.mask).astype(bool)
         self.agents = [p + 1 for p in range(self.P) if present[p]]
         return self._obs(present), {a: {} for a in self.agents}

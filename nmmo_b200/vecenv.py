@@ -126,11 +126,25 @@ class B200VecEnv:
         self._torch = torch
         self.env_id = torch.arange(self.num_envs * self.agents_per_env, device=self.sim.obs.device)
         self._pending = False
+        self.last_info_slots = []
 
     # ---- pufferlib pool contract -------------------------------------------------------
     def async_reset(self, seed: int = 0):
         seeds = np.arange(self.num_envs, dtype=np.uint64) + np.uint64(int(seed) + self.sim_env_base())
         self.sim.reset(seeds)
+        self._pending = True
+
+    def reset_envs(self, env_indices, seeds, new_tasks=None):
+        """Reset some envs, optionally assigning each a task (one table row for all of its agents): the
+        curriculum hook of /root/reference/syllabus_wrapper.py:129-150 for a batch of envs."""
+        E, P = self.num_envs, self.agents_per_env
+        mask = np.zeros(E, np.uint8); sd = np.zeros(E, np.uint64)
+        mask[np.asarray(env_indices)] = 1; sd[np.asarray(env_indices)] = np.asarray(seeds, np.uint64)
+        task_ids = None
+        if new_tasks is not None:
+            task_ids = np.zeros((E, P), np.int32)
+            task_ids[np.asarray(env_indices)] = np.asarray(new_tasks, np.int32).reshape(-1, 1)
+        self.sim.reset(sd, task_ids=task_ids, env_mask=mask)
         self._pending = True
 
     def sim_env_base(self) -> int:
@@ -141,12 +155,14 @@ class B200VecEnv:
         env_id [B], mask u8 [B]) -- all CUDA tensors except `infos` (list of dicts)."""
         s = self.sim
         infos: List[Dict] = []
+        self.last_info_slots = []        # flat agent slot (env * agents_per_env + agent) of each entry of `infos`
         if self.collect_infos:
             valid = s.info_valid.nonzero().flatten()
             if valid.numel():
                 rows = s.info[valid].cpu().numpy()
                 done = s.episode_done.cpu().numpy()
                 idx = valid.cpu().numpy()
+                self.last_info_slots = idx
                 last = {}
                 for k, a in enumerate(idx):
                     last[a // self.agents_per_env] = k

@@ -194,6 +194,31 @@ def test_vecenv_contract():
     pool.close()
 
 
+def test_task_swap_at_reset():
+    """Syllabus hook (/root/reference/syllabus_wrapper.py:129-150): reset(new_task=k) gives every agent of the
+    env table row k; other envs keep their tasks; the record's Task block is the row's embedding."""
+    from nmmo_b200.env import EnvView
+    from nmmo_b200.vecenv import B200VecEnv
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=50)
+    cfg, fcfg, maps, tab, emb = world
+    sim = _sim(world, 3)
+    sim.reset(np.arange(3, dtype=np.uint64))
+    before = [sim.task_state(e)[0].copy() for e in range(3)]
+    view = EnvView(sim, 1)
+    k = len(tab) - 1
+    obs, _ = view.reset(seed=9, new_task=k)
+    assert (sim.task_state(1)[0] == k).all()
+    assert (sim.task_state(0)[0] == before[0]).all() and (sim.task_state(2)[0] == before[2]).all()
+    for a, o in obs.items():
+        assert (np.asarray(o["Task"]).view(np.uint16) == emb[k]).all()
+    assert {t[0].spec_name for t in view.agent_task_map.values()} == {f"task_{k}"}
+    view.reset(seed=10)                                  # without new_task the tasks are drawn again
+    assert len(set(sim.task_state(1)[0].tolist())) > 1
+    with pytest.raises(RuntimeError):
+        view.reset(seed=1, new_task=len(tab))
+    sim.close()
+
+
 def test_env_view_matches_oracle():
     from nmmo_b200.env import EnvView, ACTION_KEYS
     world = build_world(task_dim=64, **SMALL, NC_HORIZON=50)
