@@ -1430,25 +1430,26 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     uint32_t *tbl = s_scratch;                               // 1024-slot position index
     uint16_t *mvd = s_mv, *res = s_mv + R;                   // intended destination, verdict / dependency
     for (int i = tid; i < 1024; i += T) tbl[i] = 0;
-    int mv_dir[2], mv_r[2], mv_c[2];                         // direction and destination (row, col)
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-      int r = tid + k * T;
-      mv_dir[k] = -1; mv_r[k] = 0; mv_c[k] = 0;
-      if (r < R) {
-        uint32_t d = NONE;
-        if (ent_alive(ctx, r)) {
-          int dir = r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P];
-          if (dir >= 0 && dir <= 3 && ENT(EA_FREEZE, r) == 0) {
-            int nr = ENT(EA_ROW, r) + c_dir_dr[dir], nc = ENT(EA_COL, r) + c_dir_dc[dir];
-            int dst = nr * S + nc;
-            if (!nm_impassible(tile_i(ctx, dst))) { d = (uint32_t)dst; mv_dir[k] = dir; mv_r[k] = nr; mv_c[k] = nc; }
-          }
+    // Every pass is a rolled loop over the rows (two per thread at the full size): the phase's cost is the code
+    // it walks, not its arithmetic, so the per-row state lives in shared memory instead of unrolled registers.
+    // The validated direction replaces the requested one in act / npc_move (-1 = stays).
+    auto dir_of = [&](int r) -> int { return r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P]; };
+#pragma unroll 1
+    for (int r = tid; r < R; r += T) {
+      uint32_t d = NONE;
+      int keep = -1;
+      if (ent_alive(ctx, r)) {
+        int dir = dir_of(r);
+        if (dir >= 0 && dir <= 3 && ENT(EA_FREEZE, r) == 0) {
+          int dst = (ENT(EA_ROW, r) + c_dir_dr[dir]) * S + ENT(EA_COL, r) + c_dir_dc[dir];
+          if (!nm_impassible(tile_i(ctx, dst))) { d = (uint32_t)dst; keep = dir; }
         }
-        mvd[r] = (uint16_t)d;
       }
+      mvd[r] = (uint16_t)d;
+      if (r < P) ctx.act[A_MOVE * P + r] = (int16_t)keep; else ctx.npc_move[r - P] = (int8_t)keep;
     }
     HSYNC();
+#pragma unroll 1
     for (int r = tid; r < R; r += T)
       if (ENT(EA_STATUS, r) == ES_ALIVE) {                   // same set as the occupancy bitmap
         uint32_t key = (uint32_t)(ENT(EA_ROW, r) * S + ENT(EA_COL, r));
@@ -1466,11 +1467,11 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
         h = (h + 1) & 1023u;
       }
     };
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-      const int i = tid + k * T;
-      if (mv_dir[k] < 0) { if (i < R) res[i] = (uint16_t)NONE; continue; }
-      const int dr_ = mv_r[k], dc_ = mv_c[k], d = dr_ * S + dc_;
+#pragma unroll 1
+    for (int i = tid; i < R; i += T) {
+      const int dir = dir_of(i);
+      if (dir < 0) { res[i] = (uint16_t)NONE; continue; }
+      const int dr_ = ENT(EA_ROW, i) + c_dir_dr[dir], dc_ = ENT(EA_COL, i) + c_dir_dc[dir], d = dr_ * S + dc_;
       int o = occ_get(ctx, dr_, dc_) ? who(d) : -1;
       uint32_t verdict = NODEP;
       int lo = -1;                                           // claimants in (lo, i) beat me
@@ -1478,9 +1479,9 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
         if (mvd[o] == NONE || o > i) verdict = NONE; else { verdict = (uint32_t)o; lo = o; }
       }
       if (verdict != NONE) {
-#pragma unroll
+#pragma unroll 1
         for (int q = 0; q < 4; q++) {
-          if (q == mv_dir[k]) continue;                      // that neighbour is my own tile
+          if (q == dir) continue;                            // that neighbour is my own tile
           int nr = dr_ - c_dir_dr[q], nc = dc_ - c_dir_dc[q];
           if (!occ_get(ctx, nr, nc)) continue;
           int e = who(nr * S + nc);
@@ -1490,26 +1491,29 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       res[i] = (uint16_t)verdict;
     }
     HSYNC();
-    bool mv_ok[2];
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-      mv_ok[k] = false;
-      if (mv_dir[k] < 0) continue;
-      int j = tid + k * T;
-      for (;;) {
-        uint32_t v = res[j];
-        if (v == NONE) break;
-        if (v == NODEP) { mv_ok[k] = true; break; }
-        j = (int)v;
+    // mvd is not read any more: it now holds "this row moves" (the chain walk only reads res)
+#pragma unroll 1
+    for (int i = tid; i < R; i += T) {
+      bool ok = false;
+      if (dir_of(i) >= 0) {
+        int j = i;
+        for (;;) {
+          uint32_t v = res[j];
+          if (v == NONE) break;
+          if (v == NODEP) { ok = true; break; }
+          j = (int)v;
+        }
+        if (ok) occ_clr(ctx, ENT(EA_ROW, i), ENT(EA_COL, i));
       }
-      if (mv_ok[k]) occ_clr(ctx, ENT(EA_ROW, tid + k * T), ENT(EA_COL, tid + k * T));
+      mvd[i] = ok ? 1 : 0;
     }
     HSYNC();
-#pragma unroll
-    for (int k = 0; k < 2; k++)
-      if (mv_ok[k]) {
-        occ_set(ctx, mv_r[k], mv_c[k]);
-        act_move(ctx, tid + k * T, mv_dir[k], false);
+#pragma unroll 1
+    for (int i = tid; i < R; i += T)
+      if (mvd[i]) {
+        const int dir = dir_of(i);
+        occ_set(ctx, ENT(EA_ROW, i) + c_dir_dr[dir], ENT(EA_COL, i) + c_dir_dc[dir]);
+        act_move(ctx, i, dir, false);
       }
   }
   HSYNC();
