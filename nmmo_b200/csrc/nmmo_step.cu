@@ -59,6 +59,7 @@ __device__ __forceinline__ uint32_t draw_impl(const uint64_t *inj_keys, const ui
   if (hi > lo) {
     uint64_t key = nm_rng_key(tick, site, idx, k);
     hi -= 1;
+    #pragma unroll 1
     while (lo <= hi) {
       int mid = (lo + hi) >> 1;
       uint64_t kk = inj_keys[mid];
@@ -86,6 +87,7 @@ __device__ void emit(const Ctx &ctx, int prow, int code, int type, int level, in
 __device__ __forceinline__ bool row_used(const Ctx &ctx, int row) { return (ctx.used[row >> 5] >> (row & 31)) & 1u; }
 __device__ int item_alloc(const Ctx &ctx) {          // lowest free row; sequential phases only
   int words = (ctx.CAP + 31) >> 5;
+  #pragma unroll 1
   for (int w = 0; w < words; w++) {
     uint32_t freebits = ~ctx.used[w];
     if (freebits) {
@@ -101,6 +103,7 @@ __device__ int item_alloc(const Ctx &ctx) {          // lowest free row; sequent
 __device__ void inv_remove(const Ctx &ctx, int owner_row, int row) {
   int n = ctx.invn[owner_row];
   uint16_t *l = ctx.inv + owner_row * ctx.NINV;
+  #pragma unroll 1
   for (int i = 0; i < n; i++)
     if (l[i] == row) { l[i] = l[n - 1]; ctx.invn[owner_row] = (uint8_t)(n - 1); return; }
 }
@@ -111,6 +114,7 @@ __device__ void inv_add(const Ctx &ctx, int owner_row, int row) {
 __device__ int find_stack(const Ctx &ctx, int owner_row, int type, int level, int exclude) {
   int n = ctx.invn[owner_row];
   const uint16_t *l = ctx.inv + owner_row * ctx.NINV;
+  #pragma unroll 1
   for (int i = 0; i < n; i++) {
     int r = l[i];
     if (r != exclude && ITM(IS_TYPE, r) == type && ITM(IS_LEVEL, r) == level) return r;
@@ -180,6 +184,7 @@ __device__ int level_at_exp(const Ctx &ctx, int exp) {
   int lmax = ctx.c[NC_LEVEL_MAX];
   if (exp >= ctx.c[NC_EXP_THRESH0 + lmax - 1]) return lmax;
   int lvl = 0;
+  #pragma unroll 1
   while (lvl < lmax && exp >= ctx.c[NC_EXP_THRESH0 + lvl]) lvl++;
   return lvl;
 }
@@ -333,7 +338,7 @@ __device__ int astar_dir_t(const Ctx &ctx, int sr, int sc, int gr, int gc) {
   auto slot_of = [&](int r, int c, bool insert) -> int {
     uint16_t key = (uint16_t)(((r << 8) | c) + 1);
     int h = (int)((key * 40503u) >> 7) & (HN - 1);
-    while (hk[h] != 0 && hk[h] != key) h = (h + 1) & (HN - 1);
+        while (hk[h] != 0 && hk[h] != key) h = (h + 1) & (HN - 1);
     if (hk[h] == 0) {
       if (!insert) return -1;
       if (++n_nodes > (HN * 3) / 4) { overflow = true; return -1; }
@@ -377,7 +382,7 @@ __device__ int astar_dir_t(const Ctx &ctx, int sr, int sc, int gr, int gc) {
     int cr = (cur >> 8) & 255, cc = cur & 255;
     if (cr == gr && cc == gc) break;
     int ccost = hcost[slot_of(cr, cc, false)];
-    for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < 4; k++) {
       int nr = cr + adr[k], nc = cc + adc[k];
       if (nr < 0 || nc < 0 || nr >= ctx.S || nc >= ctx.S) continue;
       if (nm_impassible(tile_at(ctx, nr, nc))) continue;
@@ -599,8 +604,11 @@ __device__ void attack_apply(const Ctx &ctx, int a, int style, int t, int dmg) {
     // the victim's items in table-row order: unlist, then loot (player killer) or destroy
     int n = ctx.invn[t];
     uint16_t rows[16];
+    #pragma unroll 1
     for (int i = 0; i < n; i++) rows[i] = ctx.inv[t * ctx.NINV + i];
+    #pragma unroll 1
     for (int i = 1; i < n; i++) { uint16_t x = rows[i]; int j = i - 1; while (j >= 0 && rows[j] > x) { rows[j + 1] = rows[j]; j--; } rows[j + 1] = x; }
+    #pragma unroll 1
     for (int i = 0; i < n; i++) {
       int row = rows[i];
       ITM(IS_PRICE, row) = 0; ITM(IS_LIST_TICK, row) = 0;
@@ -656,6 +664,7 @@ __device__ int npc_spawn_decide(const Ctx &ctx, uint32_t *dec, const int *free_r
   const int nd0 = ctx.sc[2];
   int nd = nd0;
   const int attempts = min(c[NC_NPC_SPAWN_ATTEMPTS], 32);
+  #pragma unroll 1
   for (int att = 0; att < attempts; att++) {
     if (count >= ctx.N) break;
     // the n-th accepted spawn takes the n-th free row (the reference scans for the first free slot)
@@ -729,6 +738,7 @@ __device__ double eval_predicate(const Ctx &ctx, int p, int pred, int p0, int p1
     case TP_CAN_SEE_TILE: {
       if (ctx.slow[p] >= 0) return (double)ctx.slow[p];
       int r = ENT(EA_ROW, p), c = ENT(EA_COL, p);
+      #pragma unroll 1
       for (int dr = -vis; dr <= vis; dr++) for (int dc = -vis; dc <= vis; dc++)
         if (tile_at(ctx, r + dr, c + dc) == p0) return 1.0;
       return 0.0;
@@ -738,6 +748,7 @@ __device__ double eval_predicate(const Ctx &ctx, int p, int pred, int p0, int p1
       if (ctx.slow[p] >= 0) return (double)ctx.slow[p];
       int lo = p0, hi = pred == TP_CAN_SEE_AGENT ? p0 : p1;
       int r = ENT(EA_ROW, p), c = ENT(EA_COL, p), seen = 0;
+      #pragma unroll 1
       for (int row = 0; row < ctx.R && seen < ctx.p->L.n_ent; row++) {
         if (ENT(EA_STATUS, row) != ES_ALIVE) continue;
         if (nm_iabs(ENT(EA_ROW, row) - r) > vis || nm_iabs(ENT(EA_COL, row) - c) > vis) continue;
@@ -754,6 +765,7 @@ __device__ double eval_predicate(const Ctx &ctx, int p, int pred, int p0, int p1
     case TP_GAIN_EXPERIENCE: return clip01((double)min((int)ENT(EA_MELEE_EXP + 2 * (p0 - 1), p), p1) / (double)p1);
     case TP_EQUIP_ITEM: {
       int k = 0;
+      #pragma unroll 1
       for (int i = 0; i < ctx.invn[p]; i++) { int r = ctx.inv[p * ctx.NINV + i];
         if (ITM(IS_TYPE, r) == p0 && ITM(IS_LEVEL, r) >= p1 && ITM(IS_EQUIPPED, r)) k++; }
       return clip01((double)k);
@@ -764,6 +776,7 @@ __device__ double eval_predicate(const Ctx &ctx, int p, int pred, int p0, int p1
     case TP_INVENTORY_SPACE_GE: return (ctx.NINV - ctx.invn[p] >= p0) ? 1.0 : 0.0;
     case TP_OWN_ITEM: {
       int s = 0;
+      #pragma unroll 1
       for (int i = 0; i < ctx.invn[p]; i++) { int r = ctx.inv[p * ctx.NINV + i];
         if (ITM(IS_TYPE, r) == p0 && ITM(IS_LEVEL, r) >= p1) s += ITM(IS_QUANTITY, r); }
       return clip01((double)s / (double)p2);
@@ -772,7 +785,9 @@ __device__ double eval_predicate(const Ctx &ctx, int p, int pred, int p0, int p1
       return clip01((double)acc0 / (double)p2);
     case TP_FULLY_ARMED: {
       int need[5] = {IT_SPEAR + (p0 - 1), IT_WHETSTONE + (p0 - 1), IT_HAT, IT_TOP, IT_BOTTOM}, k = 0;
+      #pragma unroll 1
       for (int j = 0; j < 5; j++)
+        #pragma unroll 1
         for (int i = 0; i < ctx.invn[p]; i++) { int r = ctx.inv[p * ctx.NINV + i];
           if (ITM(IS_TYPE, r) == need[j] && ITM(IS_LEVEL, r) >= p1 && ITM(IS_EQUIPPED, r)) { k++; break; } }
       return k == 5 ? 1.0 : 0.0;
@@ -899,6 +914,7 @@ __device__ __noinline__ void reset_env(const NmParams &P_, int env, uint64_t see
     // source maps are one byte per tile; the live map packs two tiles per byte
     const uint2 *src = (const uint2 *)(P_.maps + (size_t)map_id * S * S);
     uint32_t *dst = (uint32_t *)(P_.map + (size_t)env * (S * S / 2));
+    #pragma unroll 1
     for (int i = tid; i < S * S / 8; i += T) {
       uint2 b = src[i];
       uint32_t lo = b.x, hi = b.y;
@@ -907,13 +923,17 @@ __device__ __noinline__ void reset_env(const NmParams &P_, int env, uint64_t see
     }
     uint4 z = make_uint4(0, 0, 0, 0);
     uint4 *e4 = (uint4 *)(P_.ent + (size_t)env * EA_N * R);
+    #pragma unroll 1
     for (int i = tid; i < EA_N * R * 2 / 16; i += T) e4[i] = z;
     // the item table is not cleared: SC_ITEM_HI = 0 below declares every row free
     uint32_t *u = P_.uniq + (size_t)env * P * NM_UNIQ_WORDS;
+    #pragma unroll 1
     for (int i = tid; i < P * NM_UNIQ_WORDS; i += T) u[i] = 0;
     int32_t *st = P_.stats + (size_t)env * P * ST_N;
+    #pragma unroll 1
     for (int i = tid; i < P * ST_N; i += T) { int k = i % ST_N; st[i] = (k >= ST_MAXLVL_ARMOR && k <= ST_MAXLVL_CONSUMABLE) ? -1 : (k == ST_Y_HP ? 100 : 0); }
     double *ds = P_.dstats + (size_t)env * P * DS_N;
+    #pragma unroll 1
     for (int i = tid; i < P * DS_N; i += T) ds[i] = 0.0;
   }
   int *slot = s_slot, *resil = s_slot + P;
@@ -932,6 +952,7 @@ __device__ __noinline__ void reset_env(const NmParams &P_, int env, uint64_t see
   asm volatile("bar.sync %0, %1;" ::"r"(1 + half_id), "r"(NM_STEP_THREADS) : "memory");      // also orders the table clears before the row writes below
   int16_t *ent = P_.ent + (size_t)env * EA_N * R;
   int b = c[NC_MAP_BORDER], ce = c[NC_MAP_CENTER];
+  #pragma unroll 1
   for (int p = tid; p < P; p += T) {
     int k = (int)(((long long)slot[p] * (4 * ce)) / P);
     int side = k / ce, off = k % ce, r, cc;
@@ -1089,9 +1110,13 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   int ph = 0;
 #define PHASE() do { if (prm.prof && tid == 0) { long long t_ = clock64(); atomicAdd(&prm.prof[ph], (unsigned long long)(t_ - t_prev)); t_prev = t_; } ph++; } while (0)
 #define PCOUNT(slot, v) do { if (prm.prof && tid == 0) atomicAdd(&prm.prof[slot], (unsigned long long)(v)); } while (0)
+  #pragma unroll 1
   for (int i = tid; i < occ_words; i += T) ctx.occ[i] = 0;
+  #pragma unroll 1
   for (int i = tid; i < cap_words; i += T) { ctx.used[i] = 0; ctx.fresh[i] = 0; }
+  #pragma unroll 1
   for (int i = tid; i < P; i += T) { ctx.invn[i] = 0; ctx.duniq[i] = 0; }
+  #pragma unroll 1
   for (int i = tid; i < 256; i += T) ((uint32_t *)ctx.npc_hash)[i] = 0;
   if (tid < P) {
     ctx.task[tid * 4] = my_t[0]; ctx.task[tid * 4 + 1] = my_t[1]; ctx.task[tid * 4 + 2] = my_t[2]; ctx.task[tid * 4 + 3] = 0;
@@ -1151,16 +1176,21 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
 
   PHASE();
   // ---- phase 0: bookkeeping rebuilt from the tables -----------------------------------
+  #pragma unroll 1
   for (int p = tid; p < P; p += T) if (ENT(EA_STATUS, p) == ES_DEAD_THIS_TICK) ENT(EA_STATUS, p) = ES_EMPTY;
+  #pragma unroll 1
   for (int r = P + tid; r < R; r += T)
     if (ENT(EA_STATUS, r) == ES_ALIVE) {
       unsigned h = (((unsigned)(-(int)ENT(EA_ID, r))) * 40503u >> 4) & 511u;
+      #pragma unroll 1
       while (atomicCAS(&ctx.npc_hash[h], (unsigned short)0, (unsigned short)(r + 1)) != 0) h = (h + 1) & 511u;
     }
   HSYNC();
+  #pragma unroll 1
   for (int r = tid; r < R; r += T) if (ENT(EA_STATUS, r) == ES_ALIVE) occ_set(ctx, ENT(EA_ROW, r), ENT(EA_COL, r));
   if (warp == 0) {       // alive players, ascending id, with packed positions (NPC target scans)
     int n = 0;
+    #pragma unroll 1
     for (int base = 0; base < P; base += 32) {
       int p = base + lane;
       bool live = p < P && ENT(EA_STATUS, p) == ES_ALIVE;
@@ -1170,6 +1200,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     }
     if (lane == 0) ctx.sc[16] = n;
   }
+  #pragma unroll 1
   for (int g = tid; g < item_hi0 / 8; g += T) {      // 8 rows of the type column per 16-byte load
     const uint4 t8 = ((const uint4 *)(ctx.item + IS_TYPE * CAP))[g];
     if (!(t8.x | t8.y | t8.z | t8.w)) continue;
@@ -1198,6 +1229,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
         if (id > 0) return id <= P ? id : 0;
         if (id < 0) {
           unsigned h = (((unsigned)(-id)) * 40503u >> 4) & 511u;
+          #pragma unroll 1
           for (int probe = 0; probe < 512; probe++) {
             int r1 = ctx.npc_hash[h];
             if (r1 == 0) return 0;
@@ -1221,6 +1253,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   PHASE();
   // ---- phase 1: npcs.actions ----------------------------------------------------------
   ctx.plist = s_plist; ctx.n_plist = ctx.sc[16];
+  #pragma unroll 1
   for (int r = P + tid; r < R; r += T) {
     if (ent_alive(ctx, r)) npc_decide(ctx, r);
     else { ctx.npc_move[r - P] = -1; ctx.npc_att[r - P] = 0; }
@@ -1229,11 +1262,13 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
 
   PHASE();
   // ---- phase 2: players.update (order-free part), npcs.update -------------------------
+  #pragma unroll 1
   for (int p = tid; p < P; p += T) {
     bool seq = false;
     if (ENT(EA_STATUS, p) == ES_ALIVE) {
       if (ENT(EA_DAMAGE, p) == 0) ENT(EA_ATTACKER_ID, p) = 0;
       int il = 0;
+      #pragma unroll 1
       for (int s = EA_EQ_HAT; s <= EA_EQ_AMMO; s++) { int it = ENT(s, p); if (it) il += ITM(IS_LEVEL, it - 1); }
       ENT(EA_ITEM_LEVEL, p) = (int16_t)il;
       if (ENT(EA_FREEZE, p) > 0) ENT(EA_FREEZE, p) -= 1;
@@ -1269,6 +1304,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     }
     s_list[p] = seq ? 1 : 0;
   }
+  #pragma unroll 1
   for (int r = P + tid; r < R; r += T)
     if (ENT(EA_STATUS, r) == ES_ALIVE) {
       if (ENT(EA_DAMAGE, r) == 0) ENT(EA_ATTACKER_ID, r) = 0;
@@ -1281,9 +1317,11 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   PHASE();
   // id-ordered part: tile depletion and drops
   if (warp == 0) {
+    #pragma unroll 1
     for (int base = 0; base < P; base += 32) {
       int p = base + lane;
       unsigned m = __ballot_sync(0xffffffffu, p < P && s_list[p]);
+      #pragma unroll 1
       while (m) {
         int l = __ffs(m) - 1; m &= m - 1;
         if (lane == l) player_harvest(ctx, p);
@@ -1296,6 +1334,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   PHASE();
   // ---- phase 3: actions in priority order ---------------------------------------------
   // Use (10): touches only the actor's own rows
+  #pragma unroll 1
   for (int p = tid; p < P; p += T) if (ent_alive(ctx, p) && ctx.act[A_USE * P + p]) act_use(ctx, p, ctx.act[A_USE * P + p]);
   HSYNC();
   PHASE();
@@ -1308,17 +1347,22 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     bool give = tid < P && (ctx.act[A_GIVE_ITEM * P + tid] || ctx.act[A_GOLD_AMT * P + tid]);
     int any_give = half_or(give, half);
     int base = 0, nb = 0;
+    #pragma unroll 1
     for (int w2 = 0; w2 < (T >> 5); w2++) { int cw = ctx.sc[8 + w2]; if (w2 < warp) base += cw; nb += cw; }
     if (mine) s_list[base + __popc(bm & ((1u << lane) - 1))] = tid;
     HSYNC();
     if (tid == 0 && (nb > 0 || any_give)) {
+      #pragma unroll 1
       for (int i = nb - 1; i >= 1; i--) {
         int j = nm_bounded(draw(ctx, RS_BUY_SHUFFLE, (uint32_t)i, 0), i + 1);
         int t = s_list[i]; s_list[i] = s_list[j]; s_list[j] = t;
       }
+      #pragma unroll 1
       for (int i = 0; i < nb; i++) { int p = s_list[i]; if (ent_alive(ctx, p)) act_buy(ctx, p, ctx.act[A_BUY * P + p]); }
       if (any_give) {
+        #pragma unroll 1
         for (int p = 0; p < P; p++) if (ctx.act[A_GIVE_ITEM * P + p] && ent_alive(ctx, p)) act_give(ctx, p, ctx.act[A_GIVE_ITEM * P + p], ctx.act[A_GIVE_TARGET * P + p]);
+        #pragma unroll 1
         for (int p = 0; p < P; p++) if (ctx.act[A_GOLD_AMT * P + p] && ent_alive(ctx, p)) act_give_gold(ctx, p, ctx.act[A_GOLD_AMT * P + p], ctx.act[A_GOLD_TARGET * P + p]);
       }
     }
@@ -1326,6 +1370,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   HSYNC();
   PHASE();
   // Destroy (40)
+  #pragma unroll 1
   for (int p = tid; p < P; p += T) if (ent_alive(ctx, p) && ctx.act[A_DESTROY * P + p]) act_destroy(ctx, p, ctx.act[A_DESTROY * P + p]);
   HSYNC();
   PHASE();
@@ -1351,6 +1396,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     if (tid == 0) ctx.sc[6] = 0;
     if (half_or(mine_any, half) && warp == 0) {
       int na = 0;
+      #pragma unroll 1
       for (int base = 0; base < R; base += 32) {
         int r = base + lane;
         int tgt = 0;
@@ -1366,14 +1412,17 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     const int na = ctx.sc[6];
     int pending = na > 0;
     PCOUNT(22, na);
+    #pragma unroll 1
     while (pending) {
       PCOUNT(23, 1);
       long long ta0 = clock64();
+      #pragma unroll 1
       for (int r = tid; r < R; r += T) s_first[r] = 0x7fffffff;
       if (tid == 0) ctx.sc[7] = 0x7fffffff;
       HSYNC();
       long long ta1 = clock64();
       int my_low = 0x7fffffff;
+      #pragma unroll 1
       for (int i = lane * (T >> 5) + warp; i < na; i += T) {
         uint32_t x = s_att[i];
         if (x == DONE) continue;
@@ -1387,6 +1436,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       long long ta2 = clock64();
       const int lowest = ctx.sc[7];
       int still = 0;
+      #pragma unroll 1
       for (int i = lane * (T >> 5) + warp; i < na; i += T) {
         uint32_t x = s_att[i];
         if (x == DONE) continue;
@@ -1414,6 +1464,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   PHASE();
   // Move (60): with one entity per tile the reference resolves moves in entity-id order.
   if (c[NC_ALLOW_OCCUPIED]) {
+    #pragma unroll 1
     for (int r = tid; r < R; r += T) if (ent_alive(ctx, r)) act_move(ctx, r, r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P], false);
   } else {
     // Sequential semantics: movers act in row order and a move succeeds iff the destination is
@@ -1429,27 +1480,27 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     const uint32_t NONE = 0xffffu, NODEP = 0xfffeu;
     uint32_t *tbl = s_scratch;                               // 1024-slot position index
     uint16_t *mvd = s_mv, *res = s_mv + R;                   // intended destination, verdict / dependency
+    #pragma unroll 1
     for (int i = tid; i < 1024; i += T) tbl[i] = 0;
-    // Every pass is a rolled loop over the rows (two per thread at the full size): the phase's cost is the code
-    // it walks, not its arithmetic, so the per-row state lives in shared memory instead of unrolled registers.
-    // The validated direction replaces the requested one in act / npc_move (-1 = stays).
-    auto dir_of = [&](int r) -> int { return r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P]; };
-#pragma unroll 1
-    for (int r = tid; r < R; r += T) {
-      uint32_t d = NONE;
-      int keep = -1;
-      if (ent_alive(ctx, r)) {
-        int dir = dir_of(r);
-        if (dir >= 0 && dir <= 3 && ENT(EA_FREEZE, r) == 0) {
-          int dst = (ENT(EA_ROW, r) + c_dir_dr[dir]) * S + ENT(EA_COL, r) + c_dir_dc[dir];
-          if (!nm_impassible(tile_i(ctx, dst))) { d = (uint32_t)dst; keep = dir; }
+    int mv_dir[2], mv_r[2], mv_c[2];                         // direction and destination (row, col)
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      int r = tid + k * T;
+      mv_dir[k] = -1; mv_r[k] = 0; mv_c[k] = 0;
+      if (r < R) {
+        uint32_t d = NONE;
+        if (ent_alive(ctx, r)) {
+          int dir = r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P];
+          if (dir >= 0 && dir <= 3 && ENT(EA_FREEZE, r) == 0) {
+            int nr = ENT(EA_ROW, r) + c_dir_dr[dir], nc = ENT(EA_COL, r) + c_dir_dc[dir];
+            int dst = nr * S + nc;
+            if (!nm_impassible(tile_i(ctx, dst))) { d = (uint32_t)dst; mv_dir[k] = dir; mv_r[k] = nr; mv_c[k] = nc; }
+          }
         }
+        mvd[r] = (uint16_t)d;
       }
-      mvd[r] = (uint16_t)d;
-      if (r < P) ctx.act[A_MOVE * P + r] = (int16_t)keep; else ctx.npc_move[r - P] = (int8_t)keep;
     }
     HSYNC();
-#pragma unroll 1
     for (int r = tid; r < R; r += T)
       if (ENT(EA_STATUS, r) == ES_ALIVE) {                   // same set as the occupancy bitmap
         uint32_t key = (uint32_t)(ENT(EA_ROW, r) * S + ENT(EA_COL, r));
@@ -1467,11 +1518,11 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
         h = (h + 1) & 1023u;
       }
     };
-#pragma unroll 1
-    for (int i = tid; i < R; i += T) {
-      const int dir = dir_of(i);
-      if (dir < 0) { res[i] = (uint16_t)NONE; continue; }
-      const int dr_ = ENT(EA_ROW, i) + c_dir_dr[dir], dc_ = ENT(EA_COL, i) + c_dir_dc[dir], d = dr_ * S + dc_;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int i = tid + k * T;
+      if (mv_dir[k] < 0) { if (i < R) res[i] = (uint16_t)NONE; continue; }
+      const int dr_ = mv_r[k], dc_ = mv_c[k], d = dr_ * S + dc_;
       int o = occ_get(ctx, dr_, dc_) ? who(d) : -1;
       uint32_t verdict = NODEP;
       int lo = -1;                                           // claimants in (lo, i) beat me
@@ -1479,9 +1530,9 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
         if (mvd[o] == NONE || o > i) verdict = NONE; else { verdict = (uint32_t)o; lo = o; }
       }
       if (verdict != NONE) {
-#pragma unroll 1
+#pragma unroll
         for (int q = 0; q < 4; q++) {
-          if (q == dir) continue;                            // that neighbour is my own tile
+          if (q == mv_dir[k]) continue;                      // that neighbour is my own tile
           int nr = dr_ - c_dir_dr[q], nc = dc_ - c_dir_dc[q];
           if (!occ_get(ctx, nr, nc)) continue;
           int e = who(nr * S + nc);
@@ -1491,49 +1542,50 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       res[i] = (uint16_t)verdict;
     }
     HSYNC();
-    // mvd is not read any more: it now holds "this row moves" (the chain walk only reads res)
-#pragma unroll 1
-    for (int i = tid; i < R; i += T) {
-      bool ok = false;
-      if (dir_of(i) >= 0) {
-        int j = i;
-        for (;;) {
-          uint32_t v = res[j];
-          if (v == NONE) break;
-          if (v == NODEP) { ok = true; break; }
-          j = (int)v;
-        }
-        if (ok) occ_clr(ctx, ENT(EA_ROW, i), ENT(EA_COL, i));
+    bool mv_ok[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      mv_ok[k] = false;
+      if (mv_dir[k] < 0) continue;
+      int j = tid + k * T;
+      for (;;) {
+        uint32_t v = res[j];
+        if (v == NONE) break;
+        if (v == NODEP) { mv_ok[k] = true; break; }
+        j = (int)v;
       }
-      mvd[i] = ok ? 1 : 0;
+      if (mv_ok[k]) occ_clr(ctx, ENT(EA_ROW, tid + k * T), ENT(EA_COL, tid + k * T));
     }
     HSYNC();
-#pragma unroll 1
-    for (int i = tid; i < R; i += T)
-      if (mvd[i]) {
-        const int dir = dir_of(i);
-        occ_set(ctx, ENT(EA_ROW, i) + c_dir_dr[dir], ENT(EA_COL, i) + c_dir_dc[dir]);
-        act_move(ctx, i, dir, false);
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+      if (mv_ok[k]) {
+        occ_set(ctx, mv_r[k], mv_c[k]);
+        act_move(ctx, tid + k * T, mv_dir[k], false);
       }
   }
   HSYNC();
   PHASE();
   // Sell (70)
+  #pragma unroll 1
   for (int p = tid; p < P; p += T) if (ent_alive(ctx, p) && ctx.act[A_SELL_ITEM * P + p]) act_sell(ctx, p, ctx.act[A_SELL_ITEM * P + p], ctx.act[A_SELL_PRICE * P + p]);
   HSYNC();
 
   PHASE();
   // ---- phase 4: cull ------------------------------------------------------------------
+  #pragma unroll 1
   for (int p = tid; p < P; p += T)
     if (ENT(EA_STATUS, p) == ES_ALIVE && ENT(EA_HEALTH, p) <= 0) {
       ENT(EA_STATUS, p) = ES_DEAD_THIS_TICK;
       occ_clr(ctx, ENT(EA_ROW, p), ENT(EA_COL, p));
+      #pragma unroll 1
       while (ctx.invn[p] > 0) item_destroy(ctx, ctx.inv[p * NINV + ctx.invn[p] - 1]);
     }
   int *s_free = (int *)s_scratch + 512, *s_dng = (int *)s_scratch + 544;   // spawn inputs (scratch is idle here)
   if (warp == 0) {
     int16_t *danger = prm.danger + (size_t)env * N;
     int nd = ctx.sc[2], alive = 0, nfree = 0;
+    #pragma unroll 1
     for (int base = P; base < R; base += 32) {
       int r = base + lane;
       bool live = r < R && ENT(EA_STATUS, r) == ES_ALIVE;
@@ -1596,6 +1648,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     if (warp == (T >> 5) - 1) {      // the last warp has one scan pass fewer than warp 0: it also finds the
       // new high-water mark of the item table (no row is allocated or freed after the cull)
       int hi = 0;
+      #pragma unroll 1
       for (int w0 = 0; w0 < cap_words; w0 += 32) {
         uint32_t u = w0 + lane < cap_words ? ctx.used[w0 + lane] : 0u;
         unsigned nz = __ballot_sync(0xffffffffu, u != 0);
@@ -1612,6 +1665,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     // pass 1 counts this thread's hits over all its quads, one scan + one shared-memory atomic per warp reserves
     // the worklist slots, pass 2 re-tests the same words (cheaper than keeping the masks) and fills them in
     int cnt = 0;
+    #pragma unroll 1
     for (int q = tid; q < n_quads; q += T) {
       const uint4 v = ((const uint4 *)ctx.map)[q];
       cnt += __popc(hits_of(v.x)) + __popc(hits_of(v.y)) + __popc(hits_of(v.z)) + __popc(hits_of(v.w));
@@ -1624,12 +1678,14 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       if (lane == 31) base = atomicAdd(&ctx.sc[5], incl);
       int k = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
       if (cnt)
+        #pragma unroll 1
         for (int q = tid; q < n_quads; q += T) {
           const uint4 v = ((const uint4 *)ctx.map)[q];
           const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             uint32_t hit = hits_of(xs[j]);
+            #pragma unroll 1
             while (hit) {
               int b = __ffs(hit) - 1; hit &= hit - 1;
               int i = (q * 4 + j) * 8 + (b >> 2);
@@ -1646,6 +1702,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     uint16_t *dst = list_ok ? wl : ctx.dlist;
     const int n_src = list_ok ? ctx.sc[17] : min(ctx.sc[5], wl_cap), dst_cap = list_ok ? wl_cap : NM_DEPL_CAP;
     // one draw per depleted tile; the tiles that stay depleted form next tick's list
+    #pragma unroll 1
     for (int k0 = 0; k0 < n_src; k0 += T) {
       const int k = k0 + tid;
       bool stays = false;
@@ -1671,14 +1728,17 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     }
   }
   // rows the table grew over this tick that are not in use must read as empty from now on
+  #pragma unroll 1
   for (int r = item_hi0 + tid; r < ctx.sc[9]; r += T)
     if (!row_used(ctx, r)) {
 #pragma unroll
       for (int k = 0; k < IS_N; k++) ITM(k, r) = 0;
     }
   // exchange.step: listings expire; only rows in use are visited (one bitmap word per thread)
+  #pragma unroll 1
   for (int w = tid; w < cap_words; w += T) {
     uint32_t bits = ctx.used[w];
+    #pragma unroll 1
     while (bits) {
       int i = (w << 5) + __ffs(bits) - 1; bits &= bits - 1;
       if (ITM(IS_PRICE, i) > 0 && ctx.tick - ITM(IS_LIST_TICK, i) > c[NC_LISTING_DURATION]) { ITM(IS_PRICE, i) = 0; ITM(IS_LIST_TICK, i) = 0; }
@@ -1706,6 +1766,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   // ---- phase 7: fold the tick's events ------------------------------------------------
   int nev = min(ctx.sc[0], NM_EV_CAP);
   PCOUNT(26, nev);
+  #pragma unroll 1
   for (int i = tid; i < nev; i += T) fold_event(ctx, ctx.ev[i]);
   HSYNC();
 
@@ -1729,6 +1790,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   HSYNC();
   {
   const int n_req = ctx.sc[18];
+  #pragma unroll 1
   for (int qi = warp; qi < n_req; qi += (T >> 5)) {
     const int p = s_list[qi];
     int pred = ctx.task[p * 4], q0 = ctx.task[p * 4 + 1], q1 = ctx.task[p * 4 + 2];
@@ -1736,10 +1798,12 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     bool hit = false;
     if (pred == TP_CAN_SEE_TILE) {
       int win = 2 * vis + 1;
+      #pragma unroll 1
       for (int w = lane; w < win * win; w += 32) hit |= tile_at(ctx, r - vis + w / win, cc - vis + w % win) == q0;
       hit = __any_sync(0xffffffffu, hit);
     } else {
       int lo = q0, hi = pred == TP_CAN_SEE_AGENT ? q0 : q1, seen = 0;
+      #pragma unroll 1
       for (int base = 0; base < R && seen < prm.L.n_ent; base += 32) {
         int row = base + lane;
         bool in = row < R && ENT(EA_STATUS, row) == ES_ALIVE && nm_iabs(ENT(EA_ROW, row) - r) <= vis && nm_iabs(ENT(EA_COL, row) - cc) <= vis;
@@ -1817,8 +1881,10 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
           if (!(terminated || truncated)) {
             const int hp = ENT(EA_HEALTH, p), gold = ENT(EA_GOLD, p), dmg = ENT(EA_DMG_INFLICTED, p);
             int cur_exp = 0;
+            #pragma unroll 1
             for (int col = EA_MELEE_EXP; col <= EA_ALCHEMY_EXP; col += 2) cur_exp = max(cur_exp, (int)ENT(col, p));
             int def3 = 0;
+            #pragma unroll 1
             for (int s2 = EA_EQ_HAT; s2 <= EA_EQ_AMMO; s2++) { int it = ENT(s2, p); if (it) def3 += 3 * item_defense(c, ITM(IS_TYPE, it - 1), ITM(IS_LEVEL, it - 1)); }
             const double hp_bonus = __dmul_rn((double)(hp - my_sta[ST_Y_HP]), prm.fcfg[NF_HP_W]);
             const double exp_bonus = __dmul_rn((double)(cur_exp - my_sta[ST_Y_EXP]), prm.fcfg[NF_EXP_W]);
