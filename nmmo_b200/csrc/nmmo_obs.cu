@@ -109,6 +109,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     if (col_bytes)
       for (int k = 0; k < IS_N; k++) bulk_g2s(s_item + k * ICAP, prm.item + ((size_t)env * IS_N + k) * CAP, col_bytes, bar + 1);
   }
+  #pragma unroll 1
   for (int i = tid; i < P; i += T) { s_invn[i] = 0; s_meta[i] = prm.obs_meta[(size_t)env * P + i]; }
   while (!mbar_try_wait(bar, 0)) {}
   while (!mbar_try_wait(bar + 1, 0)) {}
@@ -123,10 +124,12 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   const bool no_give = (wrapper == NW_TAKERU || wrapper == NW_YAOFENG) && c[NC_DISABLE_GIVE];
   const bool no_danger = wrapper == NW_YAOFENG && c[NC_NO_DANGEROUS_NPC];      // yaofeng/reward_wrapper.py:78-81
   // one word per table row for the vision-window scan: an empty row can never match
+  #pragma unroll 1
   for (int r = tid; r < R; r += T)
     s_pos[r] = s_status[r] == ES_ALIVE ? (((uint32_t)(OENT(EA_ROW, r) + vis) << 16) | (uint32_t)(OENT(EA_COL, r) + vis)) : 0x7fff7fffu;
   // mask template: entries that do not depend on the agent (Style, Sell.Price, the no-op slots,
   // GiveGold.Price[0]); per agent it is copied and only the agent-specific entries are touched
+  #pragma unroll 1
   for (int i = tid; i < stage_bytes; i += T) {
     uint8_t v = 0;
     if (i >= L.m_style && i < L.m_style + 3) v = 1;
@@ -168,12 +171,14 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
       if (i < item_hi && OITM(IS_TYPE, i) != 0 && OITM(IS_PRICE, i) > 0) { if (pos < L.n_mkt) s_mkt_rows[pos] = (uint16_t)i; pos++; }
     }
   }
+  #pragma unroll 1
   for (int p = tid; p < P; p += T) {           // sort each inventory list by row (<= 12 entries)
     int n = min(s_invn[p], NINV);
     uint16_t *l = s_inv + p * NINV;
     for (int i = 1; i < n; i++) { uint16_t x = l[i]; int j = i - 1; while (j >= 0 && l[j] > x) { l[j + 1] = l[j]; j--; } l[j + 1] = x; }
   }
   __syncthreads();
+  #pragma unroll 1
   for (int j = tid; j < n_mkt; j += T) {       // the Market block, identical for every agent of the env
     int16_t row[IA_N_OBS];                      // (rows past n_mkt are zeros and are written as such, not staged)
     int i = s_mkt_rows[j];
@@ -196,6 +201,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   // the list one at a time, so a warp never idles while another still has agents queued.
   if (warp == 0) {
     int n = 0;
+    #pragma unroll 1
     for (int base = 0; base < P; base += 32) {
       int p = base + lane;
       uint32_t meta = p < P ? s_meta[p] : 0u;
@@ -251,6 +257,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     const int r0 = OENT(EA_ROW, p), c0 = OENT(EA_COL, p), my_id = OENT(EA_ID, p), my_gold = OENT(EA_GOLD, p);
     // visible entities: table rows inside the window, in table order, first n_ent
     int n_vis = 0;
+    #pragma unroll 1
     for (int base = 0; base < R; base += 32) {
       int row = base + lane;
       uint32_t pos = row < R ? s_pos[row] : 0x7fff7fffu;
@@ -264,12 +271,14 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     n_vis = min(n_vis, L.n_ent);
     const int n_inv = min(s_invn[p], NINV);
     const uint16_t *inv = s_inv + p * NINV;
+    #pragma unroll 1
     for (int k = lane; k < stage_bytes / 16; k += 32) ((uint4 *)stage)[k] = ((const uint4 *)s_tmpl)[k];
     __syncwarp();
     // ---- ActionTargets ----
     {
       bool any = false;
       bool immune = OENT(EA_TIME_ALIVE, p) < c[NC_SPAWN_IMMUNITY];
+      #pragma unroll 1
       for (int i = lane; i < n_vis; i += 32) {
         int row = s_vis[i], id = OENT(EA_ID, row);
         bool same = OENT(EA_ROW, row) == r0 && OENT(EA_COL, row) == c0;
@@ -297,6 +306,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
       bool any_ammo = false;
       if (full) { for (int j = lane; j < n_mkt; j += 32) any_ammo |= ammo_match(j); any_ammo = __any_sync(0xffffffffu, any_ammo); }
       if (!(full && !any_ammo))
+        #pragma unroll 1
         for (int j = lane; j < n_mkt; j += 32) {
           bool ok = s_mkt[j * IA_N_OBS + IA_OWNER] != my_id && s_mkt[j * IA_N_OBS + IA_LISTED_PRICE] <= my_gold;
           if (full) ok = ok && ammo_match(j);
@@ -321,6 +331,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
       if (lane == 0) m[L.m_sell_price + prm.stats[a * ST_N + ST_PREV_PRICE]] = 0;
     }
     __syncwarp();
+    #pragma unroll 1
     for (int k = lane; k < stage_bytes / 16; k += 32) st16(rec + k * 16, ((const uint4 *)stage)[k]);
     n_stored += stage_bytes / 16 + 1;
     // ---- built-in random policy (optional): uniform over the valid entries of every head ----
@@ -333,6 +344,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
       const int n_words = (L.m_end + 31) >> 5;
       // lane w packs mask bytes [32w, 32w+32) into bitmap word w: two 16-byte loads, one multiply
       // per four bytes (0/1 bytes -> nibble), no cross-lane traffic; bytes past m_end are template zeros
+      #pragma unroll 1
       for (int wd = lane; wd < n_words; wd += 32) {
         uint32_t wb = 0;
 #pragma unroll
@@ -402,6 +414,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
       const int n_el = n_vis * EA_N_OBS;
       const int n_chunks = min(nm_align16(L.n_ent * EA_N_OBS * 2) / 16, (max(n_vis, pv) * EA_N_OBS * 2 + 15) / 16);
       n_stored += n_chunks;
+      #pragma unroll 1
       for (int k = lane; k < n_chunks; k += 32) {
         int e0 = k * 8;
         uint4 v = zero4;
@@ -422,6 +435,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     }
     // ---- Inventory rows ----
     n_stored += max(n_inv, pi) * 2;
+    #pragma unroll 1
     for (int k = lane; k < max(n_inv, pi) * 2; k += 32) {
       int slot = k >> 1;
       uint4 v = zero4;
@@ -473,6 +487,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
                                             pack2(v[8 * q + 4], v[8 * q + 5]), pack2(v[8 * q + 6], v[8 * q + 7])));
         }
       } else
+      #pragma unroll 1
       for (int g = lane; g < n_groups; g += 32) {
         int w = g * 8;
         int dr = w / L.win, dc = w - dr * L.win;
