@@ -25,6 +25,8 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 struct nmmo_handle {
   NmParams prm;
   int device;
+  cudaStream_t copy_stream = nullptr;      // host-buffer path: results go home underneath the observation kernel
+  cudaEvent_t ev_step_done = nullptr, ev_copy_done = nullptr;
   size_t step_smem, obs_smem;
   std::vector<void *> allocs;
   int32_t *d_actions;             // staging for the host-buffer path
@@ -162,11 +164,12 @@ extern "C" int nmmo_destroy(nmmo_handle *h) {
   if (h->d_inj_keys) cudaFree(h->d_inj_keys);
   if (h->d_inj_vals) cudaFree(h->d_inj_vals);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  if (h->copy_stream) { cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->ev_step_done); cudaEventDestroy(h->ev_copy_done); }
   delete h;
   return NM_OK;
 }
 
-static int launch_step(nmmo_handle *h, int mode, cudaStream_t st) {
+static int launch_step(nmmo_handle *h, int mode, cudaStream_t st, cudaEvent_t after_step = nullptr) {
   NmParams prm = h->prm;
   prm.mode = mode;
   cudaEvent_t *e3 = nullptr;
@@ -182,6 +185,7 @@ static int launch_step(nmmo_handle *h, int mode, cudaStream_t st) {
   nmmo_step_kernel<<<(prm.E + epc - 1) / epc, epc * NM_STEP_THREADS, (size_t)epc * prm.half_smem, st>>>(prm);
   CU(cudaGetLastError());
   if (e3) CU(cudaEventRecord(e3[1], st));
+  if (after_step) CU(cudaEventRecord(after_step, st));      // rewards / flags / mask are final here
   nmmo_obs_kernel<<<prm.E, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
   CU(cudaGetLastError());
   if (e3) CU(cudaEventRecord(e3[2], st));
@@ -236,6 +240,9 @@ extern "C" int nmmo_step(nmmo_handle *h, const int32_t *actions_dev, void *strea
   return launch_step(h, 0, (cudaStream_t)stream);
 }
 
+static int finish_step_host(nmmo_handle *h, float *rew_out, uint8_t *term_out, uint8_t *trunc_out, uint8_t *mask_out,
+                            uint8_t *obs_out, cudaStream_t st);
+
 extern "C" int nmmo_step_host(nmmo_handle *h, const int32_t *actions_host, float *rew_out, uint8_t *term_out,
                               uint8_t *trunc_out, uint8_t *mask_out, uint8_t *obs_out, void *stream) {
   if (!h || !actions_host) return fail(NM_ERR_ARG, "null argument");
@@ -245,16 +252,7 @@ extern "C" int nmmo_step_host(nmmo_handle *h, const int32_t *actions_host, float
   size_t n = (size_t)p.E * p.P;
   // the caller's buffers are used directly (pinned memory makes the copies asynchronous)
   CU(cudaMemcpyAsync(h->d_actions, actions_host, n * AC_N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  p.actions = h->d_actions;
-  int rc = launch_step(h, 0, st);
-  if (rc) return rc;
-  if (rew_out) CU(cudaMemcpyAsync(rew_out, p.rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (term_out) CU(cudaMemcpyAsync(term_out, p.term, n, cudaMemcpyDeviceToHost, st));
-  if (trunc_out) CU(cudaMemcpyAsync(trunc_out, p.trunc, n, cudaMemcpyDeviceToHost, st));
-  if (mask_out) CU(cudaMemcpyAsync(mask_out, p.mask, n, cudaMemcpyDeviceToHost, st));
-  if (obs_out) CU(cudaMemcpyAsync(obs_out, p.obs, n * p.L.stride, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  return NM_OK;
+  return finish_step_host(h, rew_out, term_out, trunc_out, mask_out, obs_out, st);
 }
 
 __global__ void nmmo_widen_actions_kernel(const int16_t *src, int32_t *dst, size_t n8) {
@@ -274,13 +272,24 @@ static int finish_step_host(nmmo_handle *h, float *rew_out, uint8_t *term_out, u
   NmParams &p = h->prm;
   size_t n = (size_t)p.E * p.P;
   p.actions = h->d_actions;
-  int rc = launch_step(h, 0, st);
+  // The step kernel writes reward / terminated / truncated / mask; the observation kernel only reads them.
+  // Their way back to the host therefore runs on a side stream underneath the observation kernel.
+  if (!h->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_step_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_copy_done, cudaEventDisableTiming));
+  }
+  int rc = launch_step(h, 0, st, h->ev_step_done);
   if (rc) return rc;
-  if (rew_out) CU(cudaMemcpyAsync(rew_out, p.rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (term_out) CU(cudaMemcpyAsync(term_out, p.term, n, cudaMemcpyDeviceToHost, st));
-  if (trunc_out) CU(cudaMemcpyAsync(trunc_out, p.trunc, n, cudaMemcpyDeviceToHost, st));
-  if (mask_out) CU(cudaMemcpyAsync(mask_out, p.mask, n, cudaMemcpyDeviceToHost, st));
+  cudaStream_t cs = h->copy_stream;
+  CU(cudaStreamWaitEvent(cs, h->ev_step_done, 0));
+  if (rew_out) CU(cudaMemcpyAsync(rew_out, p.rew, n * sizeof(float), cudaMemcpyDeviceToHost, cs));
+  if (term_out) CU(cudaMemcpyAsync(term_out, p.term, n, cudaMemcpyDeviceToHost, cs));
+  if (trunc_out) CU(cudaMemcpyAsync(trunc_out, p.trunc, n, cudaMemcpyDeviceToHost, cs));
+  if (mask_out) CU(cudaMemcpyAsync(mask_out, p.mask, n, cudaMemcpyDeviceToHost, cs));
+  CU(cudaEventRecord(h->ev_copy_done, cs));
   if (obs_out) CU(cudaMemcpyAsync(obs_out, p.obs, n * p.L.stride, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamWaitEvent(st, h->ev_copy_done, 0));
   CU(cudaStreamSynchronize(st));
   return NM_OK;
 }
