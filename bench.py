@@ -146,7 +146,7 @@ def run_reference(args):
 def run_native(args):
     import torch
     import torch.distributed as dist
-    from nmmo_b200.lib import Simulator
+    from nmmo_b200.lib import Simulator, pack_actions_u8
 
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -248,7 +248,7 @@ def run_native(args):
     e2e_steps = max(4, min(args.steps, 32))
     e2e_warm = 3                                           # untimed host-buffer steps (first-use costs: pinned result buffers)
     pre = max(0, args.warmup + args.steps - e2e_steps - e2e_warm)
-    tape = torch.empty((e2e_warm + e2e_steps, E, P, 12), dtype=torch.int16).pin_memory()      # int16: nmmo_step_host_i16
+    tape = torch.empty((e2e_warm + e2e_steps, E, P, 12), dtype=torch.uint8).pin_memory()      # 12 bytes per agent: nmmo_step_host_u8
     sim.set_autosample(args.seed, sim.actions)
     sim.reset(seeds)
     # (the first ticks after a reset, when nearly every agent is still alive, are timed on the way: this is the
@@ -270,7 +270,7 @@ def run_native(args):
     for _ in range(pre - early_n):
         tick(args.seed)
     for k in range(e2e_warm + e2e_steps):
-        tape[k].copy_(sim.actions.to(torch.int16))      # narrowed on the device, like a GPU policy would
+        tape[k].copy_(pack_actions_u8(sim.actions))      # packed on the device, like a GPU policy would
         tick(args.seed)
     torch.cuda.synchronize()
     sim.reset(seeds)
@@ -290,7 +290,7 @@ def run_native(args):
     f1.record(stream)
     barrier()
     ms_e2e = f0.elapsed_time(f1)
-    h2d = n * 12 * 2
+    h2d = n * 12
     d2h = n * (4 + 3)
     # ---- reduce over ranks --------------------------------------------------------------
     t = torch.tensor([ms_total, ms_e2e, step_ms, obs_ms, obs_ms_dense], dtype=torch.float64, device="cuda")
@@ -351,7 +351,7 @@ def run_native(args):
                          "dense_equivalent_gbs": n * b_obs / (obs_ms * 1e-3) / 1e9},
             "e2e": {"value": world_size * n * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "path": "nmmo_step_host_i16 (C ABI): int16 actions from pinned host memory in, reward/term/trunc/mask to pinned host memory out, every "
+                    "path": "nmmo_step_host_u8 (C ABI): one byte per action head from pinned host memory in, reward/term/trunc/mask to pinned host memory out, every "
                             "step; observations stay on the device where the policy reads them; actions = tape of the device-resident run"},
             "steady_state": steady, "early_window": early,
             "gpu_launches": 2 * args.steps,

@@ -72,6 +72,14 @@ int nmmo_step_host(nmmo_handle *h, const int32_t *actions_host, float *rew_out, 
 int nmmo_step_host_i16(nmmo_handle *h, const int16_t *actions_host, float *rew_out, uint8_t *term_out,
                        uint8_t *trunc_out, uint8_t *mask_out, uint8_t *obs_out, void *stream);
 
+/* The same with one byte per head: byte k of an agent's 12 bytes = index of head k (all heads but one have
+ * at most 256 entries: 3 styles, N_ent+1 targets, N_inv+1 items, 99 prices, 5 directions); the wide head,
+ * Buy.MarketItem (head 2, N_mkt+1 entries), keeps bits 8.. of its index in bits 2..7 of byte 0, above the
+ * two bits of Attack.Style.  A quarter of the int32 bytes over the host link.  An index outside its head
+ * is a no-op for that head, as in the other variants.  NM_ERR_LIMIT if a head does not fit. */
+int nmmo_step_host_u8(nmmo_handle *h, const uint8_t *actions_host, float *rew_out, uint8_t *term_out,
+                      uint8_t *trunc_out, uint8_t *mask_out, uint8_t *obs_out, void *stream);
+
 /* Uniform-random valid actions from the current ActionTargets masks (BASELINE.json config 2),
  * keyed (seed, global env, tick, agent, head); writes DEVICE int32 [E][P][12]. */
 int nmmo_sample_actions(nmmo_handle *h, uint64_t seed, int32_t *actions_dev, void *stream);

@@ -308,6 +308,33 @@ extern "C" int nmmo_step_host_i16(nmmo_handle *h, const int16_t *actions_host, f
   return finish_step_host(h, rew_out, term_out, trunc_out, mask_out, obs_out, st);
 }
 
+__global__ void nmmo_unpack_actions_u8_kernel(const uint32_t *src, int4 *dst, size_t n_agents) {
+  // one agent per thread: 12 bytes in, 12 int32 out; bits 2..7 of byte 0 are bits 8.. of head 2 (Buy.MarketItem)
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_agents; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t a = src[3 * i], b = src[3 * i + 1], c2 = src[3 * i + 2];
+    const int b0 = (int)(a & 0xffu);
+    dst[3 * i] = make_int4(b0 & 3, (int)((a >> 8) & 0xffu), (int)((a >> 16) & 0xffu) | ((b0 >> 2) << 8), (int)(a >> 24));
+    dst[3 * i + 1] = make_int4((int)(b & 0xffu), (int)((b >> 8) & 0xffu), (int)((b >> 16) & 0xffu), (int)(b >> 24));
+    dst[3 * i + 2] = make_int4((int)(c2 & 0xffu), (int)((c2 >> 8) & 0xffu), (int)((c2 >> 16) & 0xffu), (int)(c2 >> 24));
+  }
+}
+
+extern "C" int nmmo_step_host_u8(nmmo_handle *h, const uint8_t *actions_host, float *rew_out, uint8_t *term_out,
+                                 uint8_t *trunc_out, uint8_t *mask_out, uint8_t *obs_out, void *stream) {
+  if (!h || !actions_host) return fail(NM_ERR_ARG, "null argument");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const nm_obs_layout &L = h->prm.L;
+  if (L.n_ent + 1 > 256 || L.n_price > 256 || L.n_inv + 1 > 256 || L.n_mkt + 1 > (1 << 14))
+    return fail(NM_ERR_LIMIT, "an action head is too wide for the packed byte format");
+  size_t n = (size_t)h->prm.E * h->prm.P;
+  CU(cudaMemcpyAsync(h->d_actions16, actions_host, n * AC_N, cudaMemcpyHostToDevice, st));
+  nmmo_unpack_actions_u8_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(
+      (const uint32_t *)h->d_actions16, (int4 *)h->d_actions, n);
+  CU(cudaGetLastError());
+  return finish_step_host(h, rew_out, term_out, trunc_out, mask_out, obs_out, st);
+}
+
 extern "C" int nmmo_sample_actions(nmmo_handle *h, uint64_t seed, int32_t *actions_dev, void *stream) {
   if (!h || !actions_dev) return fail(NM_ERR_ARG, "null argument");
   CU(cudaSetDevice(h->device));

@@ -17,7 +17,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "_build" / "libnmmo_b200.so"
 _lib = None
 
 EXPORTS = [
-    "nmmo_create", "nmmo_destroy", "nmmo_reset", "nmmo_step", "nmmo_step_host", "nmmo_step_host_i16", "nmmo_sample_actions",
+    "nmmo_create", "nmmo_destroy", "nmmo_reset", "nmmo_step", "nmmo_step_host", "nmmo_step_host_i16", "nmmo_step_host_u8", "nmmo_sample_actions",
     "nmmo_obs_ptr", "nmmo_reward_ptr", "nmmo_terminated_ptr", "nmmo_truncated_ptr", "nmmo_mask_ptr",
     "nmmo_info_ptr", "nmmo_info_valid_ptr", "nmmo_episode_done_ptr", "nmmo_obs_stride", "nmmo_num_envs",
     "nmmo_num_agents", "nmmo_inject_rng", "nmmo_snapshot", "nmmo_task_state", "nmmo_stats", "nmmo_timing", "nmmo_timing_read", "nmmo_profile", "nmmo_set_obs_full", "nmmo_set_autosample",
@@ -58,6 +58,8 @@ def load(build_if_missing: bool = True):
     L.nmmo_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.nmmo_step_host_i16.restype = C.c_int
     L.nmmo_step_host_i16.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.nmmo_step_host_u8.restype = C.c_int
+    L.nmmo_step_host_u8.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.nmmo_sample_actions.restype = C.c_int
     L.nmmo_sample_actions.argtypes = [vp, C.c_uint64, vp, vp]
     for n in ("nmmo_obs_ptr", "nmmo_reward_ptr", "nmmo_terminated_ptr", "nmmo_truncated_ptr", "nmmo_mask_ptr",
@@ -115,6 +117,28 @@ class _DevView:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
                                          "version": 2, "strides": None}
         self._owner = owner
+
+
+def pack_actions_u8(actions, out=None):
+    """int actions [..., 12] -> the 12-byte-per-agent format of nmmo_step_host_u8 (include/nmmo_b200.h): byte k = head
+    k's index, bits 8.. of Buy.MarketItem (head 2) in bits 2..7 of byte 0.  Works on numpy arrays and torch tensors
+    (pack on the device before the copy to the host)."""
+    if hasattr(actions, "numpy") and not isinstance(actions, np.ndarray):      # torch tensor
+        import torch
+        a = actions.to(torch.int32)
+        lo = (a & 0xff)
+        lo[..., 0] = (a[..., 0] & 3) | (((a[..., 2] >> 8) & 0x3f) << 2)
+        res = lo.to(torch.uint8)
+        if out is not None:
+            out.copy_(res); return out
+        return res
+    a = np.asarray(actions).astype(np.int32)
+    lo = a & 0xff
+    lo[..., 0] = (a[..., 0] & 3) | (((a[..., 2] >> 8) & 0x3f) << 2)
+    res = lo.astype(np.uint8)
+    if out is not None:
+        out[...] = res; return out
+    return res
 
 
 class Simulator:
@@ -202,10 +226,11 @@ class Simulator:
         self._check(self.L.nmmo_step(self.h, C.c_void_p(a.data_ptr()), self._stream()))
 
     def step_host(self, actions: np.ndarray, want_obs: bool = False):
-        """Host-buffer call: actions int32 (or int16: half the bytes over the host link) [E,P,12] in host memory
-        (pinned = async copies)."""
-        i16 = getattr(actions, "dtype", None) == np.int16
-        a = np.ascontiguousarray(actions, np.int16 if i16 else np.int32).reshape(self.E, self.P, 12)
+        """Host-buffer call: actions [E,P,12] in host memory (pinned = async copies) as int32, int16 (half the
+        bytes over the host link) or uint8 packed by ``pack_actions_u8`` (a quarter)."""
+        dt = getattr(actions, "dtype", None)
+        i16, u8 = dt == np.int16, dt == np.uint8
+        a = np.ascontiguousarray(actions, np.uint8 if u8 else (np.int16 if i16 else np.int32)).reshape(self.E, self.P, 12)
         n = self.E * self.P
         if getattr(self, "_host_out", None) is None:
             t = self.torch
@@ -213,7 +238,7 @@ class Simulator:
                               t.empty(n, dtype=t.uint8).pin_memory(), t.empty(n, dtype=t.uint8).pin_memory())
         rew, term, trunc, mask = (x.numpy() for x in self._host_out)
         obs = np.empty((n, self.stride), np.uint8) if want_obs else None
-        fn = self.L.nmmo_step_host_i16 if i16 else self.L.nmmo_step_host
+        fn = self.L.nmmo_step_host_u8 if u8 else (self.L.nmmo_step_host_i16 if i16 else self.L.nmmo_step_host)
         self._check(fn(self.h, _p(a), _p(rew), _p(term), _p(trunc), _p(mask), _p(obs), self._stream()))
         return rew, term, trunc, mask, obs
 

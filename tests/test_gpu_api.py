@@ -130,20 +130,27 @@ def test_handles_of_different_shapes_coexist():
 def test_step_host_equals_device_step():
     import torch
     world = build_world(task_dim=64, **SMALL, NC_HORIZON=60)
-    a, b, c = _sim(world, 2), _sim(world, 2), _sim(world, 2)
-    a.reset([1, 2]); b.reset([1, 2]); c.reset([1, 2])
+    from nmmo_b200.lib import pack_actions_u8
+    a, b, c, d = _sim(world, 2), _sim(world, 2), _sim(world, 2), _sim(world, 2)
+    a.reset([1, 2]); b.reset([1, 2]); c.reset([1, 2]); d.reset([1, 2])
     for t in range(40):
         a.sample_actions(4)
         torch.cuda.synchronize()
         acts = a.actions.cpu().numpy()
         a.step()
-        for other, host_acts in ((b, acts), (c, acts.astype(np.int16))):      # int32 and int16 host-buffer calls
+        packed = pack_actions_u8(acts)
+        assert packed.dtype == np.uint8 and np.array_equal(packed, pack_actions_u8(a.actions).cpu().numpy())
+        for other, host_acts in ((b, acts), (c, acts.astype(np.int16)), (d, packed)):      # int32, int16 and byte-packed calls
             rew, term, trunc, mask, obs = other.step_host(host_acts, want_obs=True)
             torch.cuda.synchronize()
             assert np.array_equal(rew, a.rewards.cpu().numpy()) and np.array_equal(term, a.terminated.cpu().numpy())
             assert np.array_equal(trunc, a.truncated.cpu().numpy()) and np.array_equal(mask, a.mask.cpu().numpy())
             assert np.array_equal(obs, a.obs.cpu().numpy())
-    a.close(); b.close(); c.close()
+    # the wide head (Buy.MarketItem) survives the packing, negative entries stay no-ops
+    wide = np.zeros((1, 1, 12), np.int32); wide[0, 0, 2] = 300; wide[0, 0, 0] = 2; wide[0, 0, 8] = -1
+    pk = pack_actions_u8(wide)
+    assert pk[0, 0, 0] == (2 | (1 << 2)) and pk[0, 0, 2] == 300 - 256 and pk[0, 0, 8] == 255
+    a.close(); b.close(); c.close(); d.close()
 
 
 def test_dense_and_incremental_writers_agree():
