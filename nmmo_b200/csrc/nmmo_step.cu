@@ -1248,6 +1248,17 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       for (int k = 0; k < A_N; k++) ctx.act[k * P + p] = k == A_MOVE ? (int16_t)-1 : (int16_t)0;
     }
   }
+  {   // which item-action phases have anything to do this tick: the others are skipped together with their barriers
+    int bits = 0;
+    if (tid < P) {
+      const int p = tid;
+      bits = (ctx.act[A_USE * P + p] ? 1 : 0) | (ctx.act[A_BUY * P + p] ? 2 : 0) |
+             ((ctx.act[A_GIVE_ITEM * P + p] || ctx.act[A_GOLD_AMT * P + p]) ? 4 : 0) | (ctx.act[A_DESTROY * P + p] ? 8 : 0) |
+             (ctx.act[A_SELL_ITEM * P + p] ? 16 : 0);
+    }
+    bits = __reduce_or_sync(0xffffffffu, bits);
+    if (lane == 0 && bits) atomicOr(&ctx.sc[23], bits);
+  }
   HSYNC();
 
   PHASE();
@@ -1303,6 +1314,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
             up == MT_FISH || dn == MT_FISH || lf == MT_FISH || rt == MT_FISH;
     }
     s_list[p] = seq ? 1 : 0;
+    if (seq) atomicOr(&ctx.sc[23], 32);
   }
   #pragma unroll 1
   for (int r = P + tid; r < R; r += T)
@@ -1315,7 +1327,9 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     }
   HSYNC();
   PHASE();
+  const int todo = ctx.sc[23];      // env-uniform: bit per phase that has work (Use, Buy, Give, Destroy, Sell, harvest)
   // id-ordered part: tile depletion and drops
+  if (todo & 32) {
   if (warp == 0) {
     #pragma unroll 1
     for (int base = 0; base < P; base += 32) {
@@ -1330,17 +1344,20 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     }
   }
   HSYNC();
+  }
 
   PHASE();
   // ---- phase 3: actions in priority order ---------------------------------------------
   // Use (10): touches only the actor's own rows
+  if (todo & 1) {
   #pragma unroll 1
   for (int p = tid; p < P; p += T) if (ent_alive(ctx, p) && ctx.act[A_USE * P + p]) act_use(ctx, p, ctx.act[A_USE * P + p]);
   HSYNC();
+  }
   PHASE();
   // Buy (20): shuffled order.  Buyers are compacted in id order by the whole block, then
   // shuffled and executed by one thread (a handful per tick); Give / GiveGold (30) likewise
-  {
+  if (todo & 6) {
     bool mine = tid < P && ctx.act[A_BUY * P + tid] && ent_alive(ctx, tid);
     unsigned bm = __ballot_sync(0xffffffffu, mine);
     if (lane == 0) ctx.sc[8 + warp] = __popc(bm);
@@ -1366,13 +1383,15 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
         for (int p = 0; p < P; p++) if (ctx.act[A_GOLD_AMT * P + p] && ent_alive(ctx, p)) act_give_gold(ctx, p, ctx.act[A_GOLD_AMT * P + p], ctx.act[A_GOLD_TARGET * P + p]);
       }
     }
+    HSYNC();
   }
-  HSYNC();
   PHASE();
   // Destroy (40)
+  if (todo & 8) {
   #pragma unroll 1
   for (int p = tid; p < P; p += T) if (ent_alive(ctx, p) && ctx.act[A_DESTROY * P + p]) act_destroy(ctx, p, ctx.act[A_DESTROY * P + p]);
   HSYNC();
+  }
   PHASE();
   // Attack (50): the reference executes attacks in entity-id order.  Two attacks commute unless
   // they share an entity (as attacker or target) or touch the item allocator (a kill, or the
@@ -1567,9 +1586,11 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   HSYNC();
   PHASE();
   // Sell (70)
+  if (todo & 16) {
   #pragma unroll 1
   for (int p = tid; p < P; p += T) if (ent_alive(ctx, p) && ctx.act[A_SELL_ITEM * P + p]) act_sell(ctx, p, ctx.act[A_SELL_ITEM * P + p], ctx.act[A_SELL_PRICE * P + p]);
   HSYNC();
+  }
 
   PHASE();
   // ---- phase 4: cull ------------------------------------------------------------------
