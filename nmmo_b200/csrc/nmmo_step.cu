@@ -1722,6 +1722,15 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     const uint16_t *src = list_ok ? ctx.dlist : wl;
     uint16_t *dst = list_ok ? wl : ctx.dlist;
     const int n_src = list_ok ? ctx.sc[17] : min(ctx.sc[5], wl_cap), dst_cap = list_ok ? wl_cap : NM_DEPL_CAP;
+    // Fold the tick's events here (nothing emits after the spawn): the last threads fold while the first ones
+    // walk the depleted tiles below, and the fold's global atomics -- one returns a value -- are in flight
+    // underneath the walk.  The barriers that follow order them before the reward phase reads the counters.
+    {
+      const int nev = min(ctx.sc[0], NM_EV_CAP);
+      PCOUNT(26, nev);
+      #pragma unroll 1
+      for (int i = T - 1 - tid; i < nev; i += T) fold_event(ctx, ctx.ev[i]);
+    }
     // one draw per depleted tile; the tiles that stay depleted form next tick's list
     #pragma unroll 1
     for (int k0 = 0; k0 < n_src; k0 += T) {
@@ -1784,12 +1793,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   }
 
   PHASE();
-  // ---- phase 7: fold the tick's events ------------------------------------------------
-  int nev = min(ctx.sc[0], NM_EV_CAP);
-  PCOUNT(26, nev);
-  #pragma unroll 1
-  for (int i = tid; i < nev; i += T) fold_event(ctx, ctx.ev[i]);
-  HSYNC();
+  // ---- phase 7: (the tick's events were folded before phase 6) --------------------------
 
   PHASE();
   // ---- phase 8: rewards, done flags, stat wrapper --------------------------------------
