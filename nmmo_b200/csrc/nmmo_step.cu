@@ -1603,31 +1603,49 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       while (ctx.invn[p] > 0) item_destroy(ctx, ctx.inv[p * NINV + ctx.invn[p] - 1]);
     }
   int *s_free = (int *)s_scratch + 512, *s_dng = (int *)s_scratch + 544;   // spawn inputs (scratch is idle here)
-  if (warp == 0) {
-    int16_t *danger = prm.danger + (size_t)env * N;
-    int nd = ctx.sc[2], alive = 0, nfree = 0;
+  {
+    // NPC cull: every warp classifies 32-row chunks (dead now / still alive / free afterwards) and publishes the
+    // three counts; after one barrier each chunk knows how many dead and free rows precede it, which gives the
+    // danger-stack slot of every dead NPC (stack order = row order) and the ascending list of free rows.
+    int *s_cnt = (int *)s_scratch + 600;                     // one packed count per chunk (<= 16 chunks)
+    const int n_chunks = (N + 31) >> 5;
+    auto classify = [&](int r, bool &dead, bool &stays, bool &fr) {
+      const bool live = r < R && ENT(EA_STATUS, r) == ES_ALIVE;
+      dead = live && ENT(EA_HEALTH, r) <= 0;
+      stays = live && !dead;
+      fr = r < R && !stays;
+    };
     #pragma unroll 1
-    for (int base = P; base < R; base += 32) {
-      int r = base + lane;
-      bool live = r < R && ENT(EA_STATUS, r) == ES_ALIVE;
-      bool dead = live && ENT(EA_HEALTH, r) <= 0;
-      unsigned m = __ballot_sync(0xffffffffu, dead);
+    for (int ch = warp; ch < n_chunks; ch += (T >> 5)) {
+      bool dead, stays, fr;
+      classify(P + ch * 32 + lane, dead, stays, fr);
+      const unsigned m = __ballot_sync(0xffffffffu, dead), am = __ballot_sync(0xffffffffu, stays), fm = __ballot_sync(0xffffffffu, fr);
+      if (lane == 0) s_cnt[ch] = __popc(m) | (__popc(am) << 8) | (__popc(fm) << 16);
+    }
+    const int nd0 = ctx.sc[2];                               // read before the barrier: warp 0 replaces it below
+    HSYNC();
+    int16_t *danger = prm.danger + (size_t)env * N;
+    #pragma unroll 1
+    for (int ch = warp; ch < n_chunks; ch += (T >> 5)) {
+      const int mine = lane < n_chunks ? s_cnt[lane] : 0;
+      const int before = lane < ch ? mine : 0;
+      const int dead_before = __reduce_add_sync(0xffffffffu, before & 255), free_before = __reduce_add_sync(0xffffffffu, (before >> 16) & 255);
+      const int r = P + ch * 32 + lane;
+      bool dead, stays, fr;
+      classify(r, dead, stays, fr);
+      const unsigned m = __ballot_sync(0xffffffffu, dead), fm = __ballot_sync(0xffffffffu, fr), lt = (1u << lane) - 1u;
+      if (fr) { const int k = free_before + __popc(fm & lt); if (k < 32) s_free[k] = r; }      // the rows npcs.spawn will fill
       if (dead) {
-        int idx = nd + __popc(m & ((1u << lane) - 1));
+        const int idx = nd0 + dead_before + __popc(m & lt);
         if (idx < N) danger[idx] = ENT(EA_NPC_DANGER, r);
         ENT(EA_STATUS, r) = ES_EMPTY;
         occ_clr(ctx, ENT(EA_ROW, r), ENT(EA_COL, r));
       }
-      nd = min(N, nd + __popc(m));
-      unsigned am = __ballot_sync(0xffffffffu, live && !dead);
-      alive += __popc(am);
-      // free rows in ascending order (first 32): the rows npcs.spawn will fill
-      bool fr = r < R && !(live && !dead);
-      unsigned fm = __ballot_sync(0xffffffffu, fr);
-      if (fr) { int k = nfree + __popc(fm & ((1u << lane) - 1)); if (k < 32) s_free[k] = r; }
-      nfree += __popc(fm);
+      if (ch == 0) {
+        const int tot_dead = __reduce_add_sync(0xffffffffu, mine & 255), tot_alive = __reduce_add_sync(0xffffffffu, (mine >> 8) & 255);
+        if (lane == 0) { ctx.sc[2] = min(N, nd0 + tot_dead); ctx.sc[4] = tot_alive; }
+      }
     }
-    if (lane == 0) { ctx.sc[2] = nd; ctx.sc[4] = alive; }
   }
   HSYNC();
   PHASE();
