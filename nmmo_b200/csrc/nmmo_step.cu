@@ -1413,19 +1413,30 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       mine_any |= tgt != 0 && tgt - 1 != r && ent_alive(ctx, r);
     }
     if (tid == 0) ctx.sc[6] = 0;
-    if (half_or(mine_any, half) && warp == 0) {
-      int na = 0;
-      #pragma unroll 1
-      for (int base = 0; base < R; base += 32) {
-        int r = base + lane;
+    if (half_or(mine_any, half)) {
+      // ordered build by all warps: per-chunk counts, one barrier, each chunk writes at its prefix
+      int *s_cnt = (int *)s_mv;                              // the Move scratch is idle here
+      const int n_chunks = (R + 31) >> 5;
+      auto pending_target = [&](int r) -> int {
         int tgt = 0;
         if (r < P) tgt = ctx.act[A_ATT_TARGET * P + r]; else if (r < R) tgt = ctx.npc_att[r - P];
-        bool has = tgt != 0 && tgt - 1 != r && ent_alive(ctx, r);
-        unsigned m = __ballot_sync(0xffffffffu, has);
-        if (has) s_att[na + __popc(m & ((1u << lane) - 1))] = ((uint32_t)r << 16) | (uint32_t)(tgt - 1);
-        na += __popc(m);
+        return (tgt != 0 && tgt - 1 != r && ent_alive(ctx, r)) ? tgt : 0;
+      };
+      #pragma unroll 1
+      for (int ch = warp; ch < n_chunks; ch += (T >> 5)) {
+        const unsigned m = __ballot_sync(0xffffffffu, pending_target(ch * 32 + lane) != 0);
+        if (lane == 0) s_cnt[ch] = __popc(m);
       }
-      if (lane == 0) ctx.sc[6] = na;
+      HSYNC();
+      #pragma unroll 1
+      for (int ch = warp; ch < n_chunks; ch += (T >> 5)) {
+        const int mine = lane < n_chunks ? s_cnt[lane] : 0;
+        const int before = __reduce_add_sync(0xffffffffu, lane < ch ? mine : 0);
+        const int r = ch * 32 + lane, tgt = pending_target(r);
+        const unsigned m = __ballot_sync(0xffffffffu, tgt != 0);
+        if (tgt) s_att[before + __popc(m & ((1u << lane) - 1))] = ((uint32_t)r << 16) | (uint32_t)(tgt - 1);
+        if (ch == 0) { const int tot = __reduce_add_sync(0xffffffffu, mine); if (lane == 0) ctx.sc[6] = tot; }
+      }
     }
     HSYNC();
     const int na = ctx.sc[6];
