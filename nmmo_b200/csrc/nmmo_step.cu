@@ -1053,6 +1053,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   uint32_t *s_scratch = (uint32_t *)carve(scratch_bytes);
   uint16_t *s_mv = (uint16_t *)carve((size_t)R * 4);        // Move phase: destination + verdict per row
   ctx.dlist = (uint16_t *)carve(NM_DEPL_CAP * 2);
+  uint32_t *s_tbl = (uint32_t *)carve(1024 * 4);           // Move phase: position index (tile -> row), 1024 slots
   uint32_t *s_att = s_scratch;
   int *s_first = (int *)(s_scratch + R);
   ctx.slow = (int8_t *)carve((size_t)P);
@@ -1118,6 +1119,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   for (int i = tid; i < P; i += T) { ctx.invn[i] = 0; ctx.duniq[i] = 0; }
   #pragma unroll 1
   for (int i = tid; i < 256; i += T) ((uint32_t *)ctx.npc_hash)[i] = 0;
+  for (int i = tid; i < 1024; i += T) s_tbl[i] = 0;
   if (tid < P) {
     ctx.task[tid * 4] = my_t[0]; ctx.task[tid * 4 + 1] = my_t[1]; ctx.task[tid * 4 + 2] = my_t[2]; ctx.task[tid * 4 + 3] = 0;
     ctx.acc[tid * 2] = my_acc0; ctx.acc[tid * 2 + 1] = my_acc1;
@@ -1508,10 +1510,8 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     // The only non-local part is "iff o moves away": a chain of strictly decreasing rows that each
     // winner walks down.  No rounds, no atomics on the decision path.
     const uint32_t NONE = 0xffffu, NODEP = 0xfffeu;
-    uint32_t *tbl = s_scratch;                               // 1024-slot position index
+    uint32_t *tbl = s_tbl;                                   // 1024-slot position index, zeroed at the start of the tick
     uint16_t *mvd = s_mv, *res = s_mv + R;                   // intended destination, verdict / dependency
-    #pragma unroll 1
-    for (int i = tid; i < 1024; i += T) tbl[i] = 0;
     int mv_dir[2], mv_r[2], mv_c[2];                         // direction and destination (row, col)
 #pragma unroll
     for (int k = 0; k < 2; k++) {
@@ -1528,16 +1528,14 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
           }
         }
         mvd[r] = (uint16_t)d;
+        if (ENT(EA_STATUS, r) == ES_ALIVE) {                 // position index: same set as the occupancy bitmap
+          uint32_t key = (uint32_t)(ENT(EA_ROW, r) * S + ENT(EA_COL, r));
+          uint32_t v = ((key + 1) << 16) | (uint32_t)r;
+          unsigned h = (key * 40503u >> 3) & 1023u;
+          while (atomicCAS(&tbl[h], 0u, v) != 0u) h = (h + 1) & 1023u;
+        }
       }
     }
-    HSYNC();
-    for (int r = tid; r < R; r += T)
-      if (ENT(EA_STATUS, r) == ES_ALIVE) {                   // same set as the occupancy bitmap
-        uint32_t key = (uint32_t)(ENT(EA_ROW, r) * S + ENT(EA_COL, r));
-        uint32_t v = ((key + 1) << 16) | (uint32_t)r;
-        unsigned h = (key * 40503u >> 3) & 1023u;
-        while (atomicCAS(&tbl[h], 0u, v) != 0u) h = (h + 1) & 1023u;
-      }
     HSYNC();
     auto who = [&](int tile) -> int {                        // row of the entity on an occupied tile
       unsigned h = ((unsigned)tile * 40503u >> 3) & 1023u;
@@ -1553,19 +1551,24 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       const int i = tid + k * T;
       if (mv_dir[k] < 0) { if (i < R) res[i] = (uint16_t)NONE; continue; }
       const int dr_ = mv_r[k], dc_ = mv_c[k], d = dr_ * S + dc_;
-      int o = occ_get(ctx, dr_, dc_) ? who(d) : -1;
+      // occupancy of the destination and of its other three neighbours first (five independent loads, no branches):
+      // on a sparse map nearly every mask is empty and no index look-up happens at all
+      const bool od = occ_get(ctx, dr_, dc_);
+      unsigned nb = 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (q != mv_dir[k] && occ_get(ctx, dr_ - c_dir_dr[q], dc_ - c_dir_dc[q])) nb |= 1u << q;      // q == my direction: my own tile
+      int o = od ? who(d) : -1;
       uint32_t verdict = NODEP;
       int lo = -1;                                           // claimants in (lo, i) beat me
       if (o >= 0) {
         if (mvd[o] == NONE || o > i) verdict = NONE; else { verdict = (uint32_t)o; lo = o; }
       }
       if (verdict != NONE) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          if (q == mv_dir[k]) continue;                      // that neighbour is my own tile
-          int nr = dr_ - c_dir_dr[q], nc = dc_ - c_dir_dc[q];
-          if (!occ_get(ctx, nr, nc)) continue;
-          int e = who(nr * S + nc);
+        #pragma unroll 1
+        while (nb) {
+          const int q = __ffs(nb) - 1; nb &= nb - 1;
+          int e = who((dr_ - c_dir_dr[q]) * S + dc_ - c_dir_dc[q]);
           if (e > lo && e < i && mvd[e] == d) { verdict = NONE; break; }
         }
       }
