@@ -15,6 +15,12 @@
 // entity-id order keep that order exactly: harvest drops and Buy / Give by ballot-compacted
 // sequential sections, Attack by rounds over entity-disjoint attacks, Move by a local decision per
 // mover from a position index (see the comments at each phase).
+//
+// What the kernel's time follows: the code an environment walks per tick and the number of
+// barrier-delimited segments on its critical path, not the bytes it moves.  Hence: short per-row loops are
+// kept rolled (#pragma unroll 1; nvcc would unroll them four times for one or two trips), phases nobody asked
+// for are skipped together with their barriers (`todo` mask), and row walks with ballots are spread over all
+// warps with per-chunk counts and one barrier instead of being done by warp 0 alone.
 #include "nmmo_device.cuh"
 
 namespace {
@@ -984,7 +990,7 @@ __device__ __noinline__ void reset_env(const NmParams &P_, int env, uint64_t see
 }  // namespace
 
 // Barriers over one environment's 256 threads (named barrier 1 + half).  Two environments share a CTA
-// so that they walk the kernel's code together; they only wait for each other at NM_ALIGN() points.
+// so that they walk the kernel's code together (one instruction fetch serves both); they never wait for each other.
 #define HSYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(NM_STEP_THREADS) : "memory")
 __device__ __forceinline__ int half_or(int pred, int half) {
   int r;
