@@ -738,9 +738,12 @@ __device__ void npc_spawn_fill(const Ctx &ctx, const uint32_t *q) {
 __device__ double clip01(double x) { return x > 1.0 ? 1.0 : (x < 0.0 ? 0.0 : x); }
 __device__ double eval_predicate(const Ctx &ctx, int p, int pred, int p0, int p1, int p2, int acc0, int acc1) {
   int vis = ctx.c[NC_VISION];
+  // Ratio predicates only pick (num, den) here; the one f64 division sits behind the switch, and is skipped when
+  // the clipped result is known without it (nothing counted yet, or the goal already reached).
+  int num = 0, den = 1;
   switch (pred) {
-    case TP_TICK_GE: return clip01((double)ctx.tick / (double)p0);
-    case TP_COUNT_EVENT: case TP_SCORE_HIT: return clip01((double)acc0 / (double)p1);
+    case TP_TICK_GE: num = ctx.tick; den = p0; break;
+    case TP_COUNT_EVENT: case TP_SCORE_HIT: num = acc0; den = p1; break;
     case TP_CAN_SEE_TILE: {
       if (ctx.slow[p] >= 0) return (double)ctx.slow[p];
       int r = ENT(EA_ROW, p), c = ENT(EA_COL, p);
@@ -767,28 +770,28 @@ __device__ double eval_predicate(const Ctx &ctx, int p, int pred, int p0, int p1
     case TP_OCCUPY_TILE: return (ENT(EA_ROW, p) == p0 && ENT(EA_COL, p) == p1) ? 1.0 : 0.0;
     case TP_ATTAIN_SKILL:
       if (p1 <= 1) return 1.0;
-      return clip01((double)(ENT(EA_MELEE_LEVEL + 2 * (p0 - 1), p) - 1) / (double)(p1 - 1));
-    case TP_GAIN_EXPERIENCE: return clip01((double)min((int)ENT(EA_MELEE_EXP + 2 * (p0 - 1), p), p1) / (double)p1);
+      num = ENT(EA_MELEE_LEVEL + 2 * (p0 - 1), p) - 1; den = p1 - 1; break;
+    case TP_GAIN_EXPERIENCE: num = min((int)ENT(EA_MELEE_EXP + 2 * (p0 - 1), p), p1); den = p1; break;
     case TP_EQUIP_ITEM: {
       int k = 0;
       #pragma unroll 1
       for (int i = 0; i < ctx.invn[p]; i++) { int r = ctx.inv[p * ctx.NINV + i];
         if (ITM(IS_TYPE, r) == p0 && ITM(IS_LEVEL, r) >= p1 && ITM(IS_EQUIPPED, r)) k++; }
-      return clip01((double)k);
+      num = k; den = 1; break;
     }
-    case TP_HOARD_GOLD: return clip01((double)ENT(EA_GOLD, p) / (double)p0);
-    case TP_EARN_GOLD: case TP_SPEND_GOLD: return clip01((double)acc0 / (double)p0);
-    case TP_MAKE_PROFIT: return clip01((double)(acc0 - acc1) / (double)p0);
+    case TP_HOARD_GOLD: num = ENT(EA_GOLD, p); den = p0; break;
+    case TP_EARN_GOLD: case TP_SPEND_GOLD: num = acc0; den = p0; break;
+    case TP_MAKE_PROFIT: num = acc0 - acc1; den = p0; break;
     case TP_INVENTORY_SPACE_GE: return (ctx.NINV - ctx.invn[p] >= p0) ? 1.0 : 0.0;
     case TP_OWN_ITEM: {
       int s = 0;
       #pragma unroll 1
       for (int i = 0; i < ctx.invn[p]; i++) { int r = ctx.inv[p * ctx.NINV + i];
         if (ITM(IS_TYPE, r) == p0 && ITM(IS_LEVEL, r) >= p1) s += ITM(IS_QUANTITY, r); }
-      return clip01((double)s / (double)p2);
+      num = s; den = p2; break;
     }
     case TP_CONSUME_ITEM: case TP_HARVEST_ITEM: case TP_LIST_ITEM: case TP_BUY_ITEM: case TP_DEFEAT_ENTITY:
-      return clip01((double)acc0 / (double)p2);
+      num = acc0; den = p2; break;
     case TP_FULLY_ARMED: {
       int need[5] = {IT_SPEAR + (p0 - 1), IT_WHETSTONE + (p0 - 1), IT_HAT, IT_TOP, IT_BOTTOM}, k = 0;
       #pragma unroll 1
@@ -800,11 +803,16 @@ __device__ double eval_predicate(const Ctx &ctx, int p, int pred, int p0, int p1
     }
     case TP_STAY_ALIVE: return ENT(EA_HEALTH, p) > 0 ? 1.0 : 0.0;
     case TP_DISTANCE_TRAVELED:
-      return clip01((double)nm_linf(ENT(EA_ROW, p), ENT(EA_COL, p), ENT(EA_SPAWN_ROW, p), ENT(EA_SPAWN_COL, p)) / (double)p0);
+      num = nm_linf(ENT(EA_ROW, p), ENT(EA_COL, p), ENT(EA_SPAWN_ROW, p), ENT(EA_SPAWN_COL, p)); den = p0; break;
     case TP_ALL_DEAD: return ENT(EA_HEALTH, p) > 0 ? 0.0 : 1.0;
     case TP_ALL_MEMBERS_WITHIN_RANGE: return 1.0;
+    default: return 0.0;
   }
-  return 0.0;
+  if (den > 0) {      // same value as the clipped quotient: <= 0 clips to 0.0, >= 1 clips to 1.0
+    if (num <= 0) return 0.0;
+    if (num >= den) return 1.0;
+  }
+  return clip01((double)num / (double)den);
 }
 
 // fold one event into the agent's accumulators (process_event_log / count_unique_events /
