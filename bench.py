@@ -374,8 +374,8 @@ def run_native(args):
         line["roofline_step_kernel"] = {"bound": "hbm", "kernel": "nmmo_step_kernel", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
                                         "frac": step_gbs / peak, "traffic": traffic_step, "traffic_source": traffic_src,
                                         "peak_source": peak_src, "alg_bytes_per_launch": step_alg,
-                                        "note": "latency / instruction-issue bound per-env critical path (42 % of warp stalls at barriers), "
-                                                "not bandwidth bound"}
+                                        "note": "per-env critical path bound by instruction fetch and barrier latency "
+                                                "(DESIGN.md 4.1: 2.0 M instruction-line requests per launch), not by bandwidth"}
         dominant = "roofline_step_kernel" if step_ms >= obs_ms else "roofline_obs_kernel"
         line["roofline"] = dict(line[dominant], dominant_by="mean launch duration in the timed region")
         if world_size == 1 and not args.no_cpu:
