@@ -1458,29 +1458,36 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     const int na = ctx.sc[6];
     int pending = na > 0;
     PCOUNT(22, na);
-    #pragma unroll 1
-    while (pending) {
-      PCOUNT(23, 1);
-      long long ta0 = clock64();
+    if (pending) {
       #pragma unroll 1
       for (int r = tid; r < R; r += T) s_first[r] = 0x7fffffff;
       if (tid == 0) ctx.sc[7] = 0x7fffffff;
       HSYNC();
-      long long ta1 = clock64();
+    }
+    int round = 0;
+    #pragma unroll 1
+    while (pending) {
+      PCOUNT(23, 1);
+      // Registrations carry a round tag that shrinks from round to round, so a later round's values undercut
+      // whatever the earlier ones left behind: nothing is cleared between rounds (na <= 512 < 2^20, < 512 rounds).
+      const int tag = (1023 - round) << 20;
+      round++;
+      long long ta0 = clock64();
+      long long ta1 = ta0;
       int my_low = 0x7fffffff;
       #pragma unroll 1
       for (int i = lane * (T >> 5) + warp; i < na; i += T) {
         uint32_t x = s_att[i];
         if (x == DONE) continue;
-        atomicMin(&s_first[x >> 16], i);
-        atomicMin(&s_first[x & 0xffff], i);
-        my_low = min(my_low, i);
+        atomicMin(&s_first[x >> 16], tag | i);
+        atomicMin(&s_first[x & 0xffff], tag | i);
+        my_low = min(my_low, tag | i);
       }
       my_low = __reduce_min_sync(0xffffffffu, my_low);       // one shared-memory atomic per warp, not per attack
       if (lane == 0 && my_low != 0x7fffffff) atomicMin(&ctx.sc[7], my_low);
       HSYNC();
       long long ta2 = clock64();
-      const int lowest = ctx.sc[7];
+      const int lowest = ctx.sc[7] & 0xfffff;
       int still = 0;
       #pragma unroll 1
       for (int i = lane * (T >> 5) + warp; i < na; i += T) {
@@ -1488,7 +1495,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
         if (x == DONE) continue;
         int a = x >> 16, t = x & 0xffff;
         bool done = false;
-        if (s_first[a] == i && s_first[t] == i) {
+        if (s_first[a] == (tag | i) && s_first[t] == (tag | i)) {
           done = true;
           if (ent_alive(ctx, a)) {
             int style = a < P ? (int)ctx.act[A_ATT_STYLE * P + a] : (int)ENT(EA_NPC_STYLE, a);
