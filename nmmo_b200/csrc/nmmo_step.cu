@@ -1877,7 +1877,11 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     if (pred == TP_CAN_SEE_TILE) {
       int win = 2 * vis + 1;
       #pragma unroll 1
-      for (int w = lane; w < win * win; w += 32) hit |= tile_at(ctx, r - vis + w / win, cc - vis + w % win) == q0;
+      for (int w = lane, dr = lane / win, dc = lane % win; w < win * win; w += 32) {      // (dr, dc) advance without dividing
+        hit |= tile_at(ctx, r - vis + dr, cc - vis + dc) == q0;
+        dr += 32 / win; dc += 32 % win;
+        if (dc >= win) { dc -= win; dr++; }
+      }
       hit = __any_sync(0xffffffffu, hit);
     } else {
       int lo = q0, hi = pred == TP_CAN_SEE_AGENT ? q0 : q1, seen = 0;
