@@ -127,3 +127,25 @@ def test_no_cpu_fallback_without_gpu():
     assert rc == -2 and b"no CPU fallback" in L.nmmo_last_error()
     with pytest.raises(lib.NmmoError):
         lib.Simulator(cfg, fcfg, 2, maps, tab, emb)
+
+
+def test_pack_actions_u8_layout():
+    """12 bytes per agent for nmmo_step_host_u8 (include/nmmo_b200.h): byte k = head k, the high bits of the one wide
+    head (Buy.MarketItem, head 2) in bits 2..7 of byte 0; numpy and torch packers agree."""
+    import torch
+    from nmmo_b200.lib import pack_actions_u8
+    rng = np.random.default_rng(0)
+    dims = ObsLayout(make_config()[0]).action_dims
+    a = np.stack([rng.integers(0, n, size=(5, 7)) for n in dims], -1).astype(np.int32)
+    a[0, 0] = -1                                            # "no action" entries stay out of range after packing
+    pk = pack_actions_u8(a)
+    assert pk.dtype == np.uint8 and pk.shape == a.shape
+    back = pk.astype(np.int32)
+    buy = back[..., 2] | ((back[..., 0] >> 2) << 8)
+    style = back[..., 0] & 3
+    ok = a[..., 2] >= 0
+    assert np.array_equal(buy[ok], a[..., 2][ok]) and np.array_equal(style[1:], a[1:, :, 0])
+    for k in (1, 3, 4, 5, 6, 7, 8, 9, 10, 11):
+        assert np.array_equal(back[1:, :, k], a[1:, :, k])
+    assert buy[0, 0] >= dims[2] and style[0, 0] == 3 and (back[0, 0, 1:] == 255).all()
+    assert np.array_equal(pack_actions_u8(torch.from_numpy(a)).numpy(), pk)
