@@ -61,7 +61,7 @@ static size_t obs_smem_bytes(const NmParams &p) {
   s += a16((size_t)p.L.n_mkt * IA_N_OBS * 2); s += a16((size_t)p.L.n_mkt * 2);
   s += a16((size_t)p.P * NINV * 2); s += a16((size_t)p.P * 4); s += a16(64 * 4);
   s += a16((size_t)NW * a16(p.L.m_end)); s += a16((size_t)NW * a16((size_t)p.L.n_ent * 2)); s += 16;
-  s += a16((size_t)NW * 72 * 4); s += a16((2 * AC_N + 2) * 4); s += a16((size_t)p.P * 4); s += a16((size_t)p.P * 2); s += a16((size_t)p.R * 4); s += a16(a16(p.L.m_end));
+  s += a16((size_t)NW * 72 * 4); s += a16((2 * AC_N + 2) * 4); s += a16((size_t)p.P * 4); s += a16((size_t)p.P * 2); s += a16((size_t)((p.R + 31) & ~31) * 4); s += a16(a16(p.L.m_end));
   return s + 128;
 }
 

@@ -78,7 +78,8 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   uint8_t *s_stage_all = carve((size_t)NW * stage_bytes);
   uint16_t *s_vis_all = (uint16_t *)carve((size_t)NW * ((L.n_ent * 2 + 15) & ~15));
   uint32_t *s_bits_all = (uint32_t *)carve((size_t)NW * 72 * 4);   // per warp: 32 bitmap words + 33 running counts
-  uint32_t *s_pos = (uint32_t *)carve((size_t)R * 4);       // (row+7)<<16 | (col+7) of alive rows
+  const int R32 = (R + 31) & ~31;
+  uint32_t *s_pos = (uint32_t *)carve((size_t)R32 * 4);     // (row+7)<<16 | (col+7) of alive rows, padded to whole warps
   uint8_t *s_tmpl = carve(stage_bytes);                      // agent-independent part of the masks
   int *s_head = (int *)carve((2 * AC_N + 2) * 4);       // + work-list length and cursor
   uint32_t *s_meta = (uint32_t *)carve((size_t)P * 4);
@@ -125,8 +126,8 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   const bool no_danger = wrapper == NW_YAOFENG && c[NC_NO_DANGEROUS_NPC];      // yaofeng/reward_wrapper.py:78-81
   // one word per table row for the vision-window scan: an empty row can never match
   #pragma unroll 1
-  for (int r = tid; r < R; r += T)
-    s_pos[r] = s_status[r] == ES_ALIVE ? (((uint32_t)(OENT(EA_ROW, r) + vis) << 16) | (uint32_t)(OENT(EA_COL, r) + vis)) : 0x7fff7fffu;
+  for (int r = tid; r < R32; r += T)
+    s_pos[r] = (r < R && s_status[r] == ES_ALIVE) ? (((uint32_t)(OENT(EA_ROW, r) + vis) << 16) | (uint32_t)(OENT(EA_COL, r) + vis)) : 0x7fff7fffu;
   // mask template: entries that do not depend on the agent (Style, Sell.Price, the no-op slots,
   // GiveGold.Price[0]); per agent it is copied and only the agent-specific entries are touched
   #pragma unroll 1
@@ -260,7 +261,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     #pragma unroll 1
     for (int base = 0; base < R; base += 32) {
       int row = base + lane;
-      uint32_t pos = row < R ? s_pos[row] : 0x7fff7fffu;
+      const uint32_t pos = s_pos[row];                       // padded: rows >= R hold the never-matching word
       // |r - r0| <= vis  <=>  0 <= (r + vis) - r0 <= 2*vis, same for the column
       bool in = (uint32_t)((int)(pos >> 16) - r0) <= (uint32_t)(2 * vis) && (uint32_t)((int)(pos & 0xffffu) - c0) <= (uint32_t)(2 * vis);
       unsigned bm = __ballot_sync(0xffffffffu, in);
