@@ -1458,44 +1458,48 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     const int na = ctx.sc[6];
     int pending = na > 0;
     PCOUNT(22, na);
+    // Rounds with one barrier each.  Registrations carry a round tag that shrinks from round to round, so a later
+    // round's values undercut whatever earlier rounds left behind and nothing is ever cleared; and a round registers
+    // its leftovers for the next round into the *other* of two registration arrays while its own is still being
+    // checked (na <= 512 < 2^20 attacks, fewer than 512 rounds).
+    int *s_first2 = (int *)s_mv;                             // second registration array (the Move scratch is idle)
     if (pending) {
       #pragma unroll 1
-      for (int r = tid; r < R; r += T) s_first[r] = 0x7fffffff;
-      if (tid == 0) ctx.sc[7] = 0x7fffffff;
+      for (int r = tid; r < R; r += T) { s_first[r] = 0x7fffffff; s_first2[r] = 0x7fffffff; }
+      if (tid == 0) { ctx.sc[7] = 0x7fffffff; ctx.sc[24] = 0x7fffffff; }
+      HSYNC();
+      // round 0 registers everything
+      int my_low = 0x7fffffff;
+      const int tag0 = 1023 << 20;
+      #pragma unroll 1
+      for (int i = lane * (T >> 5) + warp; i < na; i += T) {
+        uint32_t x = s_att[i];
+        atomicMin(&s_first[x >> 16], tag0 | i);
+        atomicMin(&s_first[x & 0xffff], tag0 | i);
+        my_low = min(my_low, tag0 | i);
+      }
+      my_low = __reduce_min_sync(0xffffffffu, my_low);       // one shared-memory atomic per warp, not per attack
+      if (lane == 0 && my_low != 0x7fffffff) atomicMin(&ctx.sc[7], my_low);
       HSYNC();
     }
     int round = 0;
     #pragma unroll 1
     while (pending) {
       PCOUNT(23, 1);
-      // Registrations carry a round tag that shrinks from round to round, so a later round's values undercut
-      // whatever the earlier ones left behind: nothing is cleared between rounds (na <= 512 < 2^20, < 512 rounds).
-      const int tag = (1023 - round) << 20;
+      int *cur = (round & 1) ? s_first2 : s_first, *nxt = (round & 1) ? s_first : s_first2;
+      int *low_cur = &ctx.sc[(round & 1) ? 24 : 7], *low_nxt = &ctx.sc[(round & 1) ? 7 : 24];
+      const int tag = (1023 - round) << 20, tag_n = (1022 - round) << 20;
       round++;
-      long long ta0 = clock64();
-      long long ta1 = ta0;
-      int my_low = 0x7fffffff;
-      #pragma unroll 1
-      for (int i = lane * (T >> 5) + warp; i < na; i += T) {
-        uint32_t x = s_att[i];
-        if (x == DONE) continue;
-        atomicMin(&s_first[x >> 16], tag | i);
-        atomicMin(&s_first[x & 0xffff], tag | i);
-        my_low = min(my_low, tag | i);
-      }
-      my_low = __reduce_min_sync(0xffffffffu, my_low);       // one shared-memory atomic per warp, not per attack
-      if (lane == 0 && my_low != 0x7fffffff) atomicMin(&ctx.sc[7], my_low);
-      HSYNC();
       long long ta2 = clock64();
-      const int lowest = ctx.sc[7] & 0xfffff;
-      int still = 0;
+      const int lowest = *low_cur & 0xfffff;
+      int still = 0, my_low = 0x7fffffff;
       #pragma unroll 1
       for (int i = lane * (T >> 5) + warp; i < na; i += T) {
         uint32_t x = s_att[i];
         if (x == DONE) continue;
         int a = x >> 16, t = x & 0xffff;
         bool done = false;
-        if (s_first[a] == (tag | i) && s_first[t] == (tag | i)) {
+        if (cur[a] == (tag | i) && cur[t] == (tag | i)) {
           done = true;
           if (ent_alive(ctx, a)) {
             int style = a < P ? (int)ctx.act[A_ATT_STYLE * P + a] : (int)ENT(EA_NPC_STYLE, a);
@@ -1507,10 +1511,18 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
             }
           }
         }
-        if (done) s_att[i] = DONE; else still = 1;
+        if (done) s_att[i] = DONE;
+        else {      // still pending: register for the next round right away
+          still = 1;
+          atomicMin(&nxt[a], tag_n | i);
+          atomicMin(&nxt[t], tag_n | i);
+          my_low = min(my_low, tag_n | i);
+        }
       }
+      my_low = __reduce_min_sync(0xffffffffu, my_low);
+      if (lane == 0 && my_low != 0x7fffffff) atomicMin(low_nxt, my_low);
       pending = half_or(still, half);
-      PCOUNT(44, ta1 - ta0); PCOUNT(45, ta2 - ta1); PCOUNT(46, clock64() - ta2);
+      PCOUNT(46, clock64() - ta2);
     }
   }
   HSYNC();
