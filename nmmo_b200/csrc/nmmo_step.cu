@@ -1064,7 +1064,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   // 4 KB scratch reused phase by phase: attack list + registrations, move tile hash,
   // respawn worklist, NPC-spawn pre-drawn values
   const size_t scratch_bytes = max((size_t)4096, (size_t)R * 8);
-  uint32_t *s_scratch = (uint32_t *)carve(scratch_bytes);
+  uint32_t *s_scratch = (uint32_t *)carve(scratch_bytes + 64);      // + 16 per-chunk counts behind the two attack arrays
   uint16_t *s_mv = (uint16_t *)carve((size_t)R * 4);        // Move phase: destination + verdict per row
   ctx.dlist = (uint16_t *)carve(NM_DEPL_CAP * 2);
   uint32_t *s_tbl = (uint32_t *)carve(1024 * 4);           // Move phase: position index (tile -> row), 1024 slots
@@ -1428,10 +1428,12 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       if (r < P) tgt = ctx.act[A_ATT_TARGET * P + r]; else if (r < R) tgt = ctx.npc_att[r - P];
       mine_any |= tgt != 0 && tgt - 1 != r && ent_alive(ctx, r);
     }
+    int *s_first2 = (int *)s_mv;                             // second registration array (the Move scratch is idle)
     if (tid == 0) ctx.sc[6] = 0;
     if (half_or(mine_any, half)) {
-      // ordered build by all warps: per-chunk counts, one barrier, each chunk writes at its prefix
-      int *s_cnt = (int *)s_mv;                              // the Move scratch is idle here
+      // ordered build by all warps: per-chunk counts, one barrier, each chunk writes at its prefix -- and registers
+      // its attacks for round 0 in the same pass (the registration arrays are reset in the counting pass)
+      int *s_cnt = (int *)s_scratch + 2 * R;
       const int n_chunks = (R + 31) >> 5;
       auto pending_target = [&](int r) -> int {
         int tgt = 0;
@@ -1439,18 +1441,29 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
         return (tgt != 0 && tgt - 1 != r && ent_alive(ctx, r)) ? tgt : 0;
       };
       #pragma unroll 1
+      for (int r = tid; r < R; r += T) { s_first[r] = 0x7fffffff; s_first2[r] = 0x7fffffff; }
+      if (tid == 0) { ctx.sc[7] = 0x7fffffff; ctx.sc[24] = 0x7fffffff; }
+      #pragma unroll 1
       for (int ch = warp; ch < n_chunks; ch += (T >> 5)) {
         const unsigned m = __ballot_sync(0xffffffffu, pending_target(ch * 32 + lane) != 0);
         if (lane == 0) s_cnt[ch] = __popc(m);
       }
       HSYNC();
+      const int tag0 = 1023 << 20;
       #pragma unroll 1
       for (int ch = warp; ch < n_chunks; ch += (T >> 5)) {
         const int mine = lane < n_chunks ? s_cnt[lane] : 0;
         const int before = __reduce_add_sync(0xffffffffu, lane < ch ? mine : 0);
         const int r = ch * 32 + lane, tgt = pending_target(r);
         const unsigned m = __ballot_sync(0xffffffffu, tgt != 0);
-        if (tgt) s_att[before + __popc(m & ((1u << lane) - 1))] = ((uint32_t)r << 16) | (uint32_t)(tgt - 1);
+        if (tgt) {
+          const int i = before + __popc(m & ((1u << lane) - 1));
+          s_att[i] = ((uint32_t)r << 16) | (uint32_t)(tgt - 1);
+          atomicMin(&s_first[r], tag0 | i);
+          atomicMin(&s_first[tgt - 1], tag0 | i);
+        }
+        // the lowest pending index of the chunk is its first attack; chunk 0 .. the first non-empty chunk holds index 0
+        if (m && lane == 0) atomicMin(&ctx.sc[7], tag0 | before);
         if (ch == 0) { const int tot = __reduce_add_sync(0xffffffffu, mine); if (lane == 0) ctx.sc[6] = tot; }
       }
     }
@@ -1462,26 +1475,6 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     // round's values undercut whatever earlier rounds left behind and nothing is ever cleared; and a round registers
     // its leftovers for the next round into the *other* of two registration arrays while its own is still being
     // checked (na <= 512 < 2^20 attacks, fewer than 512 rounds).
-    int *s_first2 = (int *)s_mv;                             // second registration array (the Move scratch is idle)
-    if (pending) {
-      #pragma unroll 1
-      for (int r = tid; r < R; r += T) { s_first[r] = 0x7fffffff; s_first2[r] = 0x7fffffff; }
-      if (tid == 0) { ctx.sc[7] = 0x7fffffff; ctx.sc[24] = 0x7fffffff; }
-      HSYNC();
-      // round 0 registers everything
-      int my_low = 0x7fffffff;
-      const int tag0 = 1023 << 20;
-      #pragma unroll 1
-      for (int i = lane * (T >> 5) + warp; i < na; i += T) {
-        uint32_t x = s_att[i];
-        atomicMin(&s_first[x >> 16], tag0 | i);
-        atomicMin(&s_first[x & 0xffff], tag0 | i);
-        my_low = min(my_low, tag0 | i);
-      }
-      my_low = __reduce_min_sync(0xffffffffu, my_low);       // one shared-memory atomic per warp, not per attack
-      if (lane == 0 && my_low != 0x7fffffff) atomicMin(&ctx.sc[7], my_low);
-      HSYNC();
-    }
     int round = 0;
     #pragma unroll 1
     while (pending) {
