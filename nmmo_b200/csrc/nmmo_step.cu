@@ -1192,18 +1192,21 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
 
   PHASE();
   // ---- phase 0: bookkeeping rebuilt from the tables -----------------------------------
+  // one pass over the rows: last tick's dead players become empty slots, alive entities enter the occupancy bitmap,
+  // alive NPCs the id -> row hash (read by the validation below, after the barrier)
   #pragma unroll 1
-  for (int p = tid; p < P; p += T) if (ENT(EA_STATUS, p) == ES_DEAD_THIS_TICK) ENT(EA_STATUS, p) = ES_EMPTY;
-  #pragma unroll 1
-  for (int r = P + tid; r < R; r += T)
-    if (ENT(EA_STATUS, r) == ES_ALIVE) {
-      unsigned h = (((unsigned)(-(int)ENT(EA_ID, r))) * 40503u >> 4) & 511u;
-      #pragma unroll 1
-      while (atomicCAS(&ctx.npc_hash[h], (unsigned short)0, (unsigned short)(r + 1)) != 0) h = (h + 1) & 511u;
+  for (int r = tid; r < R; r += T) {
+    const int st = ENT(EA_STATUS, r);
+    if (st == ES_DEAD_THIS_TICK && r < P) ENT(EA_STATUS, r) = ES_EMPTY;
+    if (st == ES_ALIVE) {
+      occ_set(ctx, ENT(EA_ROW, r), ENT(EA_COL, r));
+      if (r >= P) {
+        unsigned h = (((unsigned)(-(int)ENT(EA_ID, r))) * 40503u >> 4) & 511u;
+        #pragma unroll 1
+        while (atomicCAS(&ctx.npc_hash[h], (unsigned short)0, (unsigned short)(r + 1)) != 0) h = (h + 1) & 511u;
+      }
     }
-  HSYNC();
-  #pragma unroll 1
-  for (int r = tid; r < R; r += T) if (ENT(EA_STATUS, r) == ES_ALIVE) occ_set(ctx, ENT(EA_ROW, r), ENT(EA_COL, r));
+  }
   if (warp == 0) {       // alive players, ascending id, with packed positions (NPC target scans)
     int n = 0;
     #pragma unroll 1
@@ -1237,6 +1240,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       }
     }
   }
+  HSYNC();
   // ---- validate: entity ids chosen from the observation -> table rows; dead agents act on nothing
   if (tid < P) {
     const int p = tid;
