@@ -1695,6 +1695,17 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   PHASE();
   // ---- phase 5: npcs.spawn (sequential attempts) --------------------------------------
   const bool my_spawn = ctx.sc[4] < N;        // env-uniform: some NPC slot is free
+  if (warp == (T >> 5) - 1) {      // the last warp has no part in the spawn draws: it finds the new high-water mark
+    // of the item table meanwhile (no row is allocated or freed after the cull); read by the write-back
+    int hi = 0;
+    #pragma unroll 1
+    for (int w0 = 0; w0 < cap_words; w0 += 32) {
+      uint32_t u = w0 + lane < cap_words ? ctx.used[w0 + lane] : 0u;
+      unsigned nz = __ballot_sync(0xffffffffu, u != 0);
+      if (nz) { int top = 31 - __clz(nz); uint32_t ut = __shfl_sync(0xffffffffu, u, top); hi = ((w0 + top) << 5) + 32 - __clz(ut); }
+    }
+    if (lane == 0) ctx.sc[9] = (hi + 7) & ~7;
+  }
   if (my_spawn) {
     // the draws of every attempt are keyed by (attempt, ordinal): compute them all in parallel
     const int n_pre = min(c[NC_NPC_SPAWN_ATTEMPTS] * 8, (int)(scratch_bytes / 4));
@@ -1726,19 +1737,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     // The depleted tiles are known: the list carried over from last tick plus this tick's harvests (tile_dec).
     // Only when the list is unknown (first use after an overflow) is the map scanned to rebuild it.
     const bool list_ok = !prm.no_depl_list && n_depl0 >= 0 && ctx.sc[17] <= NM_DEPL_CAP;
-    if (tid == 0) { ctx.sc[5] = 0; ctx.sc[19] = 0; }
-    HSYNC();
-    if (warp == (T >> 5) - 1) {      // the last warp has one scan pass fewer than warp 0: it also finds the
-      // new high-water mark of the item table (no row is allocated or freed after the cull)
-      int hi = 0;
-      #pragma unroll 1
-      for (int w0 = 0; w0 < cap_words; w0 += 32) {
-        uint32_t u = w0 + lane < cap_words ? ctx.used[w0 + lane] : 0u;
-        unsigned nz = __ballot_sync(0xffffffffu, u != 0);
-        if (nz) { int top = 31 - __clz(nz); uint32_t ut = __shfl_sync(0xffffffffu, u, top); hi = ((w0 + top) << 5) + 32 - __clz(ut); }
-      }
-      if (lane == 0) ctx.sc[9] = (hi + 7) & ~7;
-    }
+    // sc[19] (survivors) and sc[20] (scan hits) are still zero from the start of the tick: no set-up barrier
     if (!list_ok) {
     // depleted materials are 3, 6 and the even ones from 8 up: bit-sliced test of all 8 nibbles of a word
     auto hits_of = [](uint32_t x) -> uint32_t {
@@ -1758,7 +1757,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
       int base = 0;
-      if (lane == 31) base = atomicAdd(&ctx.sc[5], incl);
+      if (lane == 31) base = atomicAdd(&ctx.sc[20], incl);
       int k = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
       if (cnt)
         #pragma unroll 1
@@ -1779,11 +1778,11 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
           }
         }
     }
-    }
     HSYNC();
+    }
     const uint16_t *src = list_ok ? ctx.dlist : wl;
     uint16_t *dst = list_ok ? wl : ctx.dlist;
-    const int n_src = list_ok ? ctx.sc[17] : min(ctx.sc[5], wl_cap), dst_cap = list_ok ? wl_cap : NM_DEPL_CAP;
+    const int n_src = list_ok ? ctx.sc[17] : min(ctx.sc[20], wl_cap), dst_cap = list_ok ? wl_cap : NM_DEPL_CAP;
     // Fold the tick's events here (nothing emits after the spawn): the last threads fold while the first ones
     // walk the depleted tiles below, and the fold's global atomics -- one returns a value -- are in flight
     // underneath the walk.  The barriers that follow order them before the reward phase reads the counters.
@@ -1814,7 +1813,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     }
     HSYNC();
     if (tid == 0) {
-      const bool scan_overflow = !list_ok && ctx.sc[5] > wl_cap;      // tiles beyond the worklist drew in place and are not listed
+      const bool scan_overflow = !list_ok && ctx.sc[20] > wl_cap;      // tiles beyond the worklist drew in place and are not listed
       ctx.sc[21] = (ctx.sc[19] <= NM_DEPL_CAP && !scan_overflow) ? ctx.sc[19] : -1;
       ctx.sc[22] = list_ok ? 0 : 1;                                    // which buffer holds the new list: worklist scratch / dlist
     }
