@@ -69,7 +69,6 @@ def main():
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
         print(f"rollout {k}: {res.steps} steps, {res.agent_steps} agent steps ({res.agent_steps / dt:,.0f}/s), "
               f"{res.global_steps} slot steps, mean advantage {adv[:a.batch].mean().item():+.4f}")
-        pool.send(torch.zeros((a.envs, pool.agents_per_env, 12), dtype=torch.int32, device="cuda"))
     pool.close(); roll.close()
 
 

@@ -36,7 +36,7 @@ enum nm_err { NM_OK = 0, NM_ERR_ARG = -1, NM_ERR_CUDA = -2, NM_ERR_LIMIT = -3, N
  * cfg / fcfg: the vectors of nmmo_spec.h (built by nmmo_b200/config.py from the same
  * env / reward_wrapper namespaces).  maps: uint8 [n_maps][S][S] host memory (the reference loads
  * them from PATH_MAPS, environment.py:41).  tasks / task_embed: the curriculum
- * (environment.py:49) as int32 [n_tasks][8] predicate rows + fp16 [n_tasks][task_dim].
+ * (environment.py:49) as int32 [n_tasks][NM_TASK_COLS] predicate rows (nmmo_spec.h: 12 columns) + fp16 [n_tasks][task_dim].
  * env_base: global index of this handle's env 0 (env sharding across GPUs). */
 int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, int n_fcfg, int n_envs, int device,
                 int env_base, const uint8_t *maps, int n_maps, const int32_t *tasks,

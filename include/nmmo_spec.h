@@ -90,6 +90,12 @@ enum nm_cfg {
   NC_DISABLE_GIVE,       /* takeru/reward_wrapper.py:31-35, yaofeng/reward_wrapper.py:72-76 */
   NC_NO_DANGEROUS_NPC,   /* donot_attack_dangerous_npc  yaofeng/reward_wrapper.py:78-81 */
   NC_ITEM_CAP,           /* item table rows = N_PLAYERS * N_INV */
+  /* stress workload knobs (BASELINE.json configs[4]; no counterpart in the reference's Config: it only scales
+   * PLAYER_N / NPC_N / MAP_CENTER, config.yaml:76-80) */
+  NC_SPAWN_PATCH,        /* 0 = players spawn on the border ring; k > 0 = all players spawn inside a k x k patch
+                            centred on the map ("clustered spawn"), k * k >= PLAYER_N */
+  NC_SAMPLE_MOVE_PCT,    /* built-in action sampler only: percent probability that the Move head picks a valid
+                            direction other than Stay (0 = uniform over the valid entries, config 2) */
   NC_COUNT
 };
 

@@ -43,6 +43,32 @@ struct nmmo_handle {
 
 static size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+// big family: shared memory and per-env HBM workspace of nmmo_step_big_kernel (same carve order as step_body<VBig>)
+static size_t step_big_smem_bytes(const NmParams &p) {
+  size_t s = 0;
+  int NINV = p.cfg[NC_N_INV];
+  s += a16((size_t)((p.S * p.S + 31) / 32) * 4); s += 2 * a16((size_t)((p.CAP + 31) / 32) * 4);
+  s += a16((size_t)p.P * NINV * 2); s += a16(p.P);
+  s += a16(p.N); s += a16((size_t)p.N * 2); s += a16((size_t)p.P * 4) * 2;
+  s += a16((size_t)VBig::kNpcHash * 2);
+  s += a16(std::max<size_t>(4096, (size_t)p.R * 8) + 32 * VBig::kChunkIters * 4); s += a16((size_t)p.R * (sizeof(VBig::tile_t) + 2));
+  s += a16((size_t)VBig::kTblSlots * 4); s += a16(p.P); s += a16((size_t)p.P * 4); s += a16(32 * 4); s += 16;
+  return s + 128;
+}
+static size_t step_big_ws_bytes(const NmParams &p) {
+  return a16((size_t)12 * p.P * 2) + a16((size_t)VBig::kEvCap * 8) + a16((size_t)p.P * 16) + a16((size_t)p.P * 8) + 128;
+}
+static size_t obs_big_smem_bytes(const NmParams &p) {
+  size_t s = 0;
+  int NINV = p.cfg[NC_N_INV];
+  int NW = NM_OBS_THREADS / 32, AP = std::min(p.P, NM_BIG_OBS_AGENTS);
+  s += a16((size_t)p.L.n_mkt * IA_N_OBS * 2); s += a16((size_t)p.L.n_mkt * 2);
+  s += a16((size_t)AP * NINV * 2); s += a16((size_t)AP * 4); s += a16(64 * 4);
+  s += a16((size_t)NW * a16(p.L.m_end)); s += a16((size_t)NW * a16((size_t)p.L.n_ent * 2)); s += 16;
+  s += a16((size_t)NW * 72 * 4); s += a16((2 * AC_N + 2) * 4); s += a16((size_t)AP * 4); s += a16((size_t)AP * 2); s += a16((size_t)((p.R + 31) & ~31) * 4); s += a16(a16(p.L.m_end));
+  return s + 128;
+}
+
 static size_t step_smem_bytes(const NmParams &p) {
   size_t s = 0;
   int NINV = p.cfg[NC_N_INV];
@@ -50,7 +76,7 @@ static size_t step_smem_bytes(const NmParams &p) {
   s += a16((size_t)((p.S * p.S + 31) / 32) * 4); s += 2 * a16((size_t)((p.CAP + 31) / 32) * 4);
   s += a16((size_t)p.P * NINV * 2); s += a16(p.P); s += a16((size_t)12 * p.P * 2);
   s += a16(p.N); s += a16((size_t)p.N * 2); s += a16(NM_EV_CAP * 8); s += a16((size_t)p.P * 4) * 2; s += a16(64); s += 16;
-  s += a16(1024); s += a16((size_t)p.P * 16); s += a16((size_t)p.P * 8); s += a16(std::max<size_t>(4096, (size_t)p.R * 8) + 64); s += a16((size_t)p.R * 4); s += a16(NM_DEPL_CAP * 2); s += 4096; s += a16(p.P); s += a16((size_t)p.P * 4) + 64;
+  s += a16(1024); s += a16((size_t)p.P * 16); s += a16((size_t)p.P * 8); s += a16(std::max<size_t>(4096, (size_t)p.R * 8) + 128); s += a16((size_t)p.R * 4); s += a16(NM_DEPL_CAP * 2); s += 4096; s += a16(p.P); s += a16((size_t)p.P * 4) + 64;
   return s + 128;
 }
 static size_t obs_smem_bytes(const NmParams &p) {
@@ -91,6 +117,10 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   if (device < 0 || device >= ndev) return fail(NM_ERR_ARG, "bad device index");
   CU(cudaSetDevice(device));
   nmmo_handle *h = new nmmo_handle();
+  struct Guard {      // any early return below frees what was allocated so far
+    nmmo_handle *h; bool armed = true;
+    ~Guard() { if (armed) { for (void *q : h->allocs) cudaFree(q); delete h; } }
+  } guard{h};
   h->device = device;
   NmParams &p = h->prm;
   memset(&p, 0, sizeof(p));
@@ -104,34 +134,55 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
     int v = atoi(ov);
     if (v >= 8 && v % 8 == 0) p.ICAP = std::min(p.CAP, v);
   }
-  if (p.P <= 0 || p.P > NM_STEP_THREADS) { delete h; return fail(NM_ERR_LIMIT, "PLAYER_N must be in 1..256 (256 threads per environment)"); }
-  if (p.R % 8 || p.CAP % 8 || (p.S * p.S) % 32) { delete h; return fail(NM_ERR_LIMIT, "P+N and item cap must be multiples of 8, S*S of 32 (bulk copies)"); }
-  if (p.R > 2 * NM_STEP_THREADS) { delete h; return fail(NM_ERR_LIMIT, "P+N must be <= 512 (256 threads per environment)"); }
-  if (p.S > 255) { delete h; return fail(NM_ERR_LIMIT, "MAP_SIZE must be <= 255"); }
-  if (p.cfg[NC_NPC_SPAWN_ATTEMPTS] > 32) { delete h; return fail(NM_ERR_LIMIT, "NPC_SPAWN_ATTEMPTS must be <= 32"); }
-  if (p.L.n_ent > 255 || p.cfg[NC_N_INV] > 16) { delete h; return fail(NM_ERR_LIMIT, "N_ENT_OBS <= 255, N_INV <= 16"); }
-  h->step_smem = step_smem_bytes(p);
-  h->obs_smem = obs_smem_bytes(p);
+  // Two kernel families (csrc/nmmo_step.cu): environments of up to 256 players / 512 entities / 255^2 tiles run out of
+  // shared memory, 256 threads each; larger ones (BASELINE.json configs[4]: 1024 players, 2048 NPCs, 544^2 tiles) keep
+  // their tables in HBM / L2 and get 1024 threads
+  p.big = (p.P > NM_STEP_THREADS || p.R > 2 * NM_STEP_THREADS || p.S > 255) ? 1 : 0;
+  if (const char *ov = getenv("NMMO_B200_FORCE_BIG")) { if (atoi(ov) == 1) p.big = 1; }      // test hook: big family on a small env
+  if (p.P <= 0 || p.P > NM_BIG_THREADS) { return fail(NM_ERR_LIMIT, "PLAYER_N must be in 1..1024"); }
+  if (p.R % 8 || p.CAP % 8 || (p.S * p.S) % 32) { return fail(NM_ERR_LIMIT, "P+N and item cap must be multiples of 8, S*S of 32 (bulk copies)"); }
+  if (p.R > VBig::kRowsPerThread * NM_BIG_THREADS) { return fail(NM_ERR_LIMIT, "P+N must be <= 3072"); }
+  if (p.S > 1023) { return fail(NM_ERR_LIMIT, "MAP_SIZE must be <= 1023"); }
+  if (p.N > VBig::kNpcHash / 2) { return fail(NM_ERR_LIMIT, "NPC_N must be <= 2048"); }
+  if (p.cfg[NC_NPC_SPAWN_ATTEMPTS] > 32) { return fail(NM_ERR_LIMIT, "NPC_SPAWN_ATTEMPTS must be <= 32"); }
+  if (p.L.n_ent > 255 || p.cfg[NC_N_INV] > 16) { return fail(NM_ERR_LIMIT, "N_ENT_OBS <= 255, N_INV <= 16"); }
+  if (p.cfg[NC_SPAWN_PATCH] > 0 && (p.cfg[NC_SPAWN_PATCH] * p.cfg[NC_SPAWN_PATCH] < p.P || p.cfg[NC_SPAWN_PATCH] > p.cfg[NC_MAP_CENTER]))
+    return fail(NM_ERR_ARG, "SPAWN_PATCH^2 must hold PLAYER_N players and fit inside the map centre");
+  if (p.cfg[NC_SPAWN_PATCH] == 0 && !p.cfg[NC_ALLOW_OCCUPIED] && p.P > 4 * p.cfg[NC_MAP_CENTER])
+    return fail(NM_ERR_ARG, "border-ring spawn with one entity per tile needs PLAYER_N <= 4 * MAP_CENTER");
+  h->step_smem = p.big ? step_big_smem_bytes(p) : step_smem_bytes(p);
+  h->obs_smem = p.big ? obs_big_smem_bytes(p) : obs_smem_bytes(p);
   int max_smem = 0;
   CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  if ((int)h->step_smem > max_smem || (int)h->obs_smem > max_smem) { delete h; return fail(NM_ERR_LIMIT, "environment does not fit in shared memory"); }
-  // the step kernel runs two environments per CTA (they walk the code together) when both fit
+  if ((int)h->step_smem > max_smem || (int)h->obs_smem > max_smem) { return fail(NM_ERR_LIMIT, "environment does not fit in shared memory"); }
+  // the small step kernel runs two environments per CTA (they walk the code together) when both fit
   p.half_smem = (int)((h->step_smem + 127) & ~(size_t)127);
-  p.envs_per_cta = 2 * p.half_smem <= max_smem ? 2 : 1;
+  p.envs_per_cta = (!p.big && 2 * p.half_smem <= max_smem) ? 2 : 1;
   if (getenv("NMMO_B200_NO_DEPL_LIST")) p.no_depl_list = 1;      // test hook
   if (const char *ov = getenv("NMMO_B200_ENVS_PER_CTA")) { if (atoi(ov) == 1) p.envs_per_cta = 1; }      // test hook
   {   // the opt-in limit is a property of the kernel, not of the handle: several handles of different shapes may
       // be alive in one process, so it only ever grows (per device)
-    static int step_attr[64] = {0}, obs_attr[64] = {0};
-    const int need_step = p.envs_per_cta * p.half_smem, need_obs = (int)h->obs_smem, d = device & 63;
-    if (need_step > step_attr[d]) { CU(cudaFuncSetAttribute(nmmo_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_step)); step_attr[d] = need_step; }
-    if (need_obs > obs_attr[d]) { CU(cudaFuncSetAttribute(nmmo_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_obs)); obs_attr[d] = need_obs; }
+    static int step_attr[2][64] = {{0}}, obs_attr[2][64] = {{0}};
+    const int need_step = p.envs_per_cta * p.half_smem, need_obs = (int)h->obs_smem, d = device & 63, b = p.big;
+    if (need_step > step_attr[b][d]) {
+      if (b) CU(cudaFuncSetAttribute(nmmo_step_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_step));
+      else CU(cudaFuncSetAttribute(nmmo_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_step));
+      step_attr[b][d] = need_step;
+    }
+    if (need_obs > obs_attr[b][d]) {
+      if (b) CU(cudaFuncSetAttribute(nmmo_obs_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_obs));
+      else CU(cudaFuncSetAttribute(nmmo_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_obs));
+      obs_attr[b][d] = need_obs;
+    }
   }
   size_t E = p.E, P = p.P;
-  DA(p.ent, E * EA_N * p.R); DA(p.item, E * IS_N * p.CAP); DA(p.map, E * p.S * p.S / 2);
+  const size_t ent_i16 = p.big ? (size_t)NM_BIG_ENT_STRIDE * p.R : (size_t)EA_N * p.R;      // int16 per env
+  DA(p.ent, E * ent_i16); DA(p.item, E * IS_N * p.CAP); DA(p.map, E * p.S * p.S / 2);
+  if (p.big) { p.ws_bytes = step_big_ws_bytes(p); DA(p.ws, E * p.ws_bytes); }
   uint8_t *dmaps; DA(dmaps, (size_t)n_maps * p.S * p.S); p.maps = dmaps;
   CU(cudaMemcpy(dmaps, maps, (size_t)n_maps * p.S * p.S, cudaMemcpyHostToDevice));
-  DA(p.scalars, E * NM_SC_N); DA(p.seed, E); DA(p.danger, E * p.N); DA(p.depl, E * NM_DEPL_CAP);
+  DA(p.scalars, E * NM_SC_N); DA(p.seed, E); DA(p.danger, E * p.N);
+  { uint8_t *dl; DA(dl, p.big ? E * VBig::kDeplCap * sizeof(VBig::tile_t) : E * VSmall::kDeplCap * sizeof(VSmall::tile_t)); p.depl = dl; }
   DA(p.stats, E * P * ST_N); DA(p.dstats, E * P * DS_N); DA(p.uniq, E * P * NM_UNIQ_WORDS); DA(p.task_id, E * P);
   int32_t *dtasks; DA(dtasks, (size_t)n_tasks * NM_TASK_COLS); p.tasks = dtasks;
   CU(cudaMemcpy(dtasks, tasks, sizeof(int32_t) * n_tasks * NM_TASK_COLS, cudaMemcpyHostToDevice));
@@ -152,6 +203,7 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   std::vector<int32_t> sc(E * NM_SC_N, 0);
   for (size_t e = 0; e < E; e++) sc[e * NM_SC_N + SC_DONE] = 1;
   CU(cudaMemcpy(p.scalars, sc.data(), sizeof(int32_t) * sc.size(), cudaMemcpyHostToDevice));
+  guard.armed = false;
   *out = h;
   return NM_OK;
 }
@@ -182,11 +234,15 @@ static int launch_step(nmmo_handle *h, int mode, cudaStream_t st, cudaEvent_t af
     CU(cudaEventRecord(e3[0], st));
   }
   const int epc = h->prm.envs_per_cta;
-  nmmo_step_kernel<<<(prm.E + epc - 1) / epc, epc * NM_STEP_THREADS, (size_t)epc * prm.half_smem, st>>>(prm);
+  if (prm.big) nmmo_step_big_kernel<<<prm.E, NM_BIG_THREADS, (size_t)prm.half_smem, st>>>(prm);
+  else nmmo_step_kernel<<<(prm.E + epc - 1) / epc, epc * NM_STEP_THREADS, (size_t)epc * prm.half_smem, st>>>(prm);
   CU(cudaGetLastError());
   if (e3) CU(cudaEventRecord(e3[1], st));
   if (after_step) CU(cudaEventRecord(after_step, st));      // rewards / flags / mask are final here
-  nmmo_obs_kernel<<<prm.E, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
+  if (prm.big) {
+    const int ap = std::min(prm.P, NM_BIG_OBS_AGENTS), parts = (prm.P + ap - 1) / ap;
+    nmmo_obs_big_kernel<<<prm.E * parts, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
+  } else nmmo_obs_kernel<<<prm.E, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
   CU(cudaGetLastError());
   if (e3) CU(cudaEventRecord(e3[2], st));
   return NM_OK;
@@ -199,6 +255,14 @@ extern "C" int nmmo_reset(nmmo_handle *h, const uint64_t *seeds, const int32_t *
   cudaStream_t st = (cudaStream_t)stream;
   NmParams &p = h->prm;
   size_t E = p.E, P = p.P;
+  // validate everything before any device state is touched: an NM_ERR_ARG return leaves the handle as it was
+  for (size_t e = 0; e < E; e++) {
+    if (env_mask && !env_mask[e]) continue;
+    if (map_ids && (map_ids[e] < 0 || map_ids[e] >= p.n_maps)) return fail(NM_ERR_ARG, "map id out of range");
+    if (task_ids)
+      for (size_t a = 0; a < P; a++)
+        if (task_ids[e * P + a] < 0 || task_ids[e * P + a] >= p.n_tasks) return fail(NM_ERR_ARG, "task id out of range");
+  }
   CU(cudaStreamSynchronize(st));
   std::vector<int32_t> sc(E * NM_SC_N);
   CU(cudaMemcpy(sc.data(), p.scalars, sizeof(int32_t) * sc.size(), cudaMemcpyDeviceToHost));
@@ -209,21 +273,17 @@ extern "C" int nmmo_reset(nmmo_handle *h, const uint64_t *seeds, const int32_t *
     int32_t *s = &sc[e * NM_SC_N];
     s[SC_NEED_RESET] = 1; s[SC_EPISODE] = 0; s[SC_ERROR] = 0;
     s[SC_EXPLICIT_MAP] = map_ids ? 1 : 0;
-    if (map_ids) {
-      if (map_ids[e] < 0 || map_ids[e] >= p.n_maps) return fail(NM_ERR_ARG, "map id out of range");
-      s[SC_MAP_ID] = map_ids[e];
-    }
+    if (map_ids) s[SC_MAP_ID] = map_ids[e];
     s[SC_EXPLICIT_TASKS] = task_ids ? 1 : 0;
     sd[e] = seeds[e];
   }
-  CU(cudaMemcpy(p.scalars, sc.data(), sizeof(int32_t) * sc.size(), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(p.seed, sd.data(), sizeof(uint64_t) * E, cudaMemcpyHostToDevice));
+  // uploads are stream-ordered on `st` with the reset launch below (the host vectors outlive the final synchronize)
+  CU(cudaMemcpyAsync(p.scalars, sc.data(), sizeof(int32_t) * sc.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(p.seed, sd.data(), sizeof(uint64_t) * E, cudaMemcpyHostToDevice, st));
   if (task_ids) {
     for (size_t e = 0; e < E; e++) {
       if (env_mask && !env_mask[e]) continue;
-      for (size_t a = 0; a < P; a++)
-        if (task_ids[e * P + a] < 0 || task_ids[e * P + a] >= p.n_tasks) return fail(NM_ERR_ARG, "task id out of range");
-      CU(cudaMemcpy(p.task_id + e * P, task_ids + e * P, sizeof(int32_t) * P, cudaMemcpyHostToDevice));
+      CU(cudaMemcpyAsync(p.task_id + e * P, task_ids + e * P, sizeof(int32_t) * P, cudaMemcpyHostToDevice, st));
     }
   }
   int rc = launch_step(h, 1, st);
@@ -392,11 +452,13 @@ extern "C" int nmmo_snapshot(nmmo_handle *h, int env, int16_t *ent, int16_t *ite
   CU(cudaDeviceSynchronize());
   const NmParams &p = h->prm;
   if (ent) {
-    std::vector<int16_t> soa((size_t)EA_N * p.R);
-    CU(cudaMemcpy(soa.data(), p.ent + (size_t)env * EA_N * p.R, soa.size() * 2, cudaMemcpyDeviceToHost));
+    const size_t ent_i16 = p.big ? (size_t)NM_BIG_ENT_STRIDE * p.R : (size_t)EA_N * p.R;
+    std::vector<int16_t> soa(ent_i16);
+    CU(cudaMemcpy(soa.data(), p.ent + (size_t)env * ent_i16, soa.size() * 2, cudaMemcpyDeviceToHost));
+    auto at = [&](int k, int r) -> int16_t { return p.big ? soa[(size_t)VBig::ent_idx(k, r, p.R)] : soa[(size_t)VSmall::ent_idx(k, r, p.R)]; };
     for (int r = 0; r < p.R; r++) {
-      bool empty = soa[(size_t)EA_STATUS * p.R + r] == ES_EMPTY;
-      for (int k = 0; k < EA_N; k++) ent[(size_t)r * EA_N + k] = empty ? 0 : soa[(size_t)k * p.R + r];
+      bool empty = at(EA_STATUS, r) == ES_EMPTY;
+      for (int k = 0; k < EA_N; k++) ent[(size_t)r * EA_N + k] = empty ? 0 : at(k, r);
     }
   }
   if (items) {

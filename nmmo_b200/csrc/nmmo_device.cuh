@@ -20,6 +20,12 @@
 #define NM_SC_N 16              // per-env int32 scalars
 #define NM_DEPL_CAP 1024         // per-env list of depleted tiles kept across ticks (falls back to a map scan beyond)
 #define NM_AGG_REP 256           // replicas of the finished-agent sums (contention spreading)
+// big family (nmmo_step_big_kernel / nmmo_obs_big_kernel: up to 1024 players, 3072 entities, 1023^2 tiles per env)
+#define NM_BIG_THREADS 1024
+#define NM_BIG_EV_CAP 4096
+#define NM_BIG_DEPL_CAP 4096
+#define NM_BIG_ENT_STRIDE 48     // int16 per row of the row-major entity table (EA_N = 44, padded to 96 bytes)
+#define NM_BIG_OBS_AGENTS 128    // agents per CTA of the big observation kernel
 #define OM_NONZERO (1u << 16)
 #define OM_TASK (1u << 17)
 
@@ -41,12 +47,14 @@ struct NmParams {
   int32_t *scalars;            // [E][NM_SC_N]
   uint64_t *seed;              // [E]
   int16_t *danger;             // [E][N]
-  uint16_t *depl;              // [E][NM_DEPL_CAP] tile indices of the depleted tiles (unordered)
+  void *depl;                  // [E][depleted-list capacity] tile indices of the depleted tiles (unordered; uint16 small / uint32 big)
+  uint8_t *ws; size_t ws_bytes;// big family: per-env workspace for the step kernel's rarely touched arrays
+  int big;                     // 1 = big family (row-major entity table, tables used in place)
   int32_t *stats;              // [E][P][ST_N]
   double *dstats;              // [E][P][DS_N]
   uint32_t *uniq;              // [E][P][NM_UNIQ_WORDS]
   int32_t *task_id;            // [E][P]
-  const int32_t *tasks;        // [T][8]
+  const int32_t *tasks;        // [T][NM_TASK_COLS]
   const uint16_t *embed;       // [T][task_dim]
   // rng injection
   const uint64_t *inj_keys; const uint32_t *inj_vals; const int32_t *inj_off;   // off [E+1]

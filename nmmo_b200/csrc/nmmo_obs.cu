@@ -7,14 +7,26 @@
 // and pufferlib's flatten + pad of the nested observation (reinforcement_learning/environment.py:73),
 // writing the flat record the policy reads on-device (agent_zoo/takeru/policy.py:39-64).
 //
-// One CTA per environment, three CTAs per SM.  The entity table (31 observed columns + status), the
-// live prefix of the item table and the 4-bit tile map are staged into shared memory with TMA bulk
-// copies; the env-global Market block is built once in shared memory; the agents that need a record
+// Small family (nmmo_obs_kernel): one CTA per environment, three CTAs per SM.  The entity table (31 observed
+// columns + status), the live prefix of the item table and the 4-bit tile map are staged into shared memory with
+// TMA bulk copies; the env-global Market block is built once in shared memory; the agents that need a record
 // are compacted into a work list the warps pull from; each warp assembles whole agent records and
 // streams them out with 16-byte st.global.cs stores, 512 contiguous bytes per warp instruction.
+// Big family (nmmo_obs_big_kernel, up to 1024 agents per env): NM_BIG_OBS_AGENTS agents per CTA, several CTAs per
+// environment; the tables are read where they live (row-major entity table: an observed row is the first 62 bytes
+// of its table row), only the per-row position words, the Market block and the per-agent lists are in shared memory.
 #include "nmmo_device.cuh"
 
 namespace {
+
+struct OSmall {
+  static constexpr bool kStage = true;
+  static __device__ __forceinline__ int ent_idx(int col, int row, int R) { return col * R + row; }
+};
+struct OBig {
+  static constexpr bool kStage = false;
+  static __device__ __forceinline__ int ent_idx(int col, int row, int) { return row * NM_BIG_ENT_STRIDE + col; }
+};
 
 struct OCtx {
   const NmParams *p;
@@ -26,9 +38,10 @@ struct OCtx {
   const int16_t *gitem;    // [IS_N][CAP] the table in HBM (rows >= ICAP)
   const uint32_t *map;
 };
-#define OENT(col, row) o.ent[(col) * o.R + (row)]
+#define OENT(col, row) o.ent[V::ent_idx((col), (row), o.R)]
 #define OITM(col, row) ((row) < o.ICAP ? o.item[(col) * o.ICAP + (row)] : o.gitem[(size_t)(col) * o.CAP + (row)])
 
+template <class V>
 __device__ __forceinline__ int o_use_level(const OCtx &o, int row, int type) {
   switch (type) {
     case IT_SPEAR: case IT_WHETSTONE: return OENT(EA_MELEE_LEVEL, row);
@@ -51,10 +64,15 @@ __device__ __forceinline__ uint32_t pack2(int a, int b) { return (uint32_t)(uint
 
 }  // namespace
 
-extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, 3)
-nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
+template <class V>
+__device__ __forceinline__ void obs_body(const NmParams &prm) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int env = blockIdx.x, tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
+  // small: one CTA per env, all of its agents; big: AP agents per CTA, parts CTAs per env
+  const int AP = V::kStage ? prm.P : min(prm.P, NM_BIG_OBS_AGENTS);
+  const int parts = V::kStage ? 1 : (prm.P + AP - 1) / AP;
+  const int env = V::kStage ? (int)blockIdx.x : (int)blockIdx.x / parts;
+  const int p_lo = V::kStage ? 0 : ((int)blockIdx.x % parts) * AP, p_hi = min(prm.P, p_lo + AP);
   const int32_t *c = prm.cfg;
   const nm_obs_layout &L = prm.L;
   const int P = prm.P, R = prm.R, S = prm.S, CAP = prm.CAP, ICAP = prm.ICAP, NINV = c[NC_N_INV], vis = c[NC_VISION];
@@ -64,15 +82,18 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   auto carve = [&](size_t bytes) { uint8_t *q = smem + off; off = (off + bytes + 15) & ~(size_t)15; return q; };
   const uint32_t ent_bytes = (uint32_t)(EA_N_OBS * R * 2), st_bytes = (uint32_t)(R * 2);
   const uint32_t item_bytes = (uint32_t)(IS_N * ICAP * 2), map_bytes = (uint32_t)(S * S / 2);
-  int16_t *s_ent = (int16_t *)carve(ent_bytes);
-  int16_t *s_status = (int16_t *)carve(st_bytes);
-  int16_t *s_item = (int16_t *)carve(item_bytes);
-  uint32_t *s_map = (uint32_t *)carve(map_bytes);       // 4 bits per tile
+  const int16_t *const g_ent = prm.ent + (size_t)env * (V::kStage ? (size_t)EA_N * R : (size_t)NM_BIG_ENT_STRIDE * R);
+  int16_t *s_ent = V::kStage ? (int16_t *)carve(ent_bytes) : nullptr;
+  int16_t *s_status = V::kStage ? (int16_t *)carve(st_bytes) : nullptr;
+  int16_t *s_item = V::kStage ? (int16_t *)carve(item_bytes) : nullptr;
+  const uint32_t *s_map = V::kStage ? (const uint32_t *)carve(map_bytes)        // 4 bits per tile
+                                    : (const uint32_t *)(prm.map + (size_t)env * map_bytes);
   auto tile = [&](int i) -> int { return (int)((s_map[i >> 3] >> ((i & 7) * 4)) & 15u); };
+  auto status_of = [&](int r) -> int { return V::kStage ? (int)s_status[r] : (int)g_ent[V::ent_idx(EA_STATUS, r, R)]; };
   int16_t *s_mkt = (int16_t *)carve((size_t)L.n_mkt * IA_N_OBS * 2);
   uint16_t *s_mkt_rows = (uint16_t *)carve((size_t)L.n_mkt * 2);
-  uint16_t *s_inv = (uint16_t *)carve((size_t)P * NINV * 2);
-  int *s_invn = (int *)carve((size_t)P * 4);
+  uint16_t *s_inv = (uint16_t *)carve((size_t)AP * NINV * 2);      // indexed by p - p_lo
+  int *s_invn = (int *)carve((size_t)AP * 4);
   int *s_scan = (int *)carve(64 * 4);
   const int stage_bytes = nm_align16(L.m_end);
   uint8_t *s_stage_all = carve((size_t)NW * stage_bytes);
@@ -82,14 +103,14 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   uint32_t *s_pos = (uint32_t *)carve((size_t)R32 * 4);     // (row+7)<<16 | (col+7) of alive rows, padded to whole warps
   uint8_t *s_tmpl = carve(stage_bytes);                      // agent-independent part of the masks
   int *s_head = (int *)carve((2 * AC_N + 2) * 4);       // + work-list length and cursor
-  uint32_t *s_meta = (uint32_t *)carve((size_t)P * 4);
-  uint16_t *s_work = (uint16_t *)carve((size_t)P * 2);
+  uint32_t *s_meta = (uint32_t *)carve((size_t)AP * 4);
+  uint16_t *s_work = (uint16_t *)carve((size_t)AP * 2);
   uint64_t *bar = (uint64_t *)carve(16);
 
   long long t_prev = clock64();
   int ph = 32;
 #define OPHASE() do { if (prm.prof && tid == 0) { long long t_ = clock64(); atomicAdd(&prm.prof[ph], (unsigned long long)(t_ - t_prev)); t_prev = t_; } ph++; } while (0)
-  if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (V::kStage && tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   const int item_hi = prm.scalars[(size_t)env * NM_SC_N + SC_ITEM_HI];     // rows >= item_hi are free
   if (tid < AC_N) {
     const int off[AC_N] = {L.m_style, L.m_target, L.m_buy, L.m_destroy, L.m_give_item, L.m_give_target,
@@ -99,35 +120,37 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     s_head[tid] = off[tid]; s_head[AC_N + tid] = len[tid];
   }
   __syncthreads();
-  if (tid == 0) {
+  if (V::kStage && tid == 0) {
     mbar_expect_tx(bar, ent_bytes + st_bytes + map_bytes);
-    const int16_t *ge = prm.ent + (size_t)env * EA_N * R;
+    const int16_t *ge = g_ent;
     bulk_g2s(s_ent, ge, ent_bytes, bar);
     bulk_g2s(s_status, ge + (size_t)EA_STATUS * R, st_bytes, bar);
-    bulk_g2s(s_map, prm.map + (size_t)env * map_bytes, map_bytes, bar);
+    bulk_g2s((void *)s_map, prm.map + (size_t)env * map_bytes, map_bytes, bar);
     const uint32_t col_bytes = (uint32_t)min(item_hi, ICAP) * 2;       // only the live prefix of each item column
     mbar_expect_tx(bar + 1, col_bytes * IS_N);
     if (col_bytes)
       for (int k = 0; k < IS_N; k++) bulk_g2s(s_item + k * ICAP, prm.item + ((size_t)env * IS_N + k) * CAP, col_bytes, bar + 1);
   }
   #pragma unroll 1
-  for (int i = tid; i < P; i += T) { s_invn[i] = 0; s_meta[i] = prm.obs_meta[(size_t)env * P + i]; }
-  while (!mbar_try_wait(bar, 0)) {}
-  while (!mbar_try_wait(bar + 1, 0)) {}
+  for (int i = tid; i < p_hi - p_lo; i += T) { s_invn[i] = 0; s_meta[i] = prm.obs_meta[(size_t)env * P + p_lo + i]; }
+  if (V::kStage) {
+    while (!mbar_try_wait(bar, 0)) {}
+    while (!mbar_try_wait(bar + 1, 0)) {}
+  }
   __syncthreads();
   OPHASE();      // 32 load
 
   OCtx o;
   o.p = &prm; o.c = c; o.R = R; o.S = S; o.CAP = CAP; o.ICAP = ICAP; o.P = P; o.NINV = NINV;
   o.gitem = prm.item + (size_t)env * IS_N * CAP;
-  o.ent = s_ent; o.status = s_status; o.item = s_item; o.map = s_map;
+  o.ent = V::kStage ? s_ent : g_ent; o.status = s_status; o.item = s_item; o.map = s_map;
   const int wrapper = c[NC_WRAPPER];
   const bool no_give = (wrapper == NW_TAKERU || wrapper == NW_YAOFENG) && c[NC_DISABLE_GIVE];
   const bool no_danger = wrapper == NW_YAOFENG && c[NC_NO_DANGEROUS_NPC];      // yaofeng/reward_wrapper.py:78-81
   // one word per table row for the vision-window scan: an empty row can never match
   #pragma unroll 1
   for (int r = tid; r < R32; r += T)
-    s_pos[r] = (r < R && s_status[r] == ES_ALIVE) ? (((uint32_t)(OENT(EA_ROW, r) + vis) << 16) | (uint32_t)(OENT(EA_COL, r) + vis)) : 0x7fff7fffu;
+    s_pos[r] = (r < R && status_of(r) == ES_ALIVE) ? (((uint32_t)(OENT(EA_ROW, r) + vis) << 16) | (uint32_t)(OENT(EA_COL, r) + vis)) : 0x7fff7fffu;
   // mask template: entries that do not depend on the agent (Style, Sell.Price, the no-op slots,
   // GiveGold.Price[0]); per agent it is copied and only the agent-specific entries are touched
   #pragma unroll 1
@@ -147,7 +170,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     int i = tid * K + k;
     if (i < item_hi && OITM(IS_TYPE, i) != 0) {
       int owner = OITM(IS_OWNER, i);
-      if (owner > 0) { int slot = atomicAdd(&s_invn[owner - 1], 1); if (slot < NINV) s_inv[(owner - 1) * NINV + slot] = (uint16_t)i; }
+      if (owner > p_lo && owner <= p_hi) { int slot = atomicAdd(&s_invn[owner - 1 - p_lo], 1); if (slot < NINV) s_inv[(owner - 1 - p_lo) * NINV + slot] = (uint16_t)i; }
       if (OITM(IS_PRICE, i) > 0) my_listed++;
     }
   }
@@ -173,7 +196,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     }
   }
   #pragma unroll 1
-  for (int p = tid; p < P; p += T) {           // sort each inventory list by row (<= 12 entries)
+  for (int p = tid; p < p_hi - p_lo; p += T) {           // sort each inventory list by row (<= 12 entries)
     int n = min(s_invn[p], NINV);
     uint16_t *l = s_inv + p * NINV;
     for (int i = 1; i < n; i++) { uint16_t x = l[i]; int j = i - 1; while (j >= 0 && l[j] > x) { l[j + 1] = l[j]; j--; } l[j + 1] = x; }
@@ -203,11 +226,11 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
   if (warp == 0) {
     int n = 0;
     #pragma unroll 1
-    for (int base = 0; base < P; base += 32) {
+    for (int base = p_lo; base < p_hi; base += 32) {
       int p = base + lane;
-      uint32_t meta = p < P ? s_meta[p] : 0u;
-      bool alive = p < P && s_status[p] == ES_ALIVE;
-      bool work = alive || (p < P && ((meta & OM_NONZERO) || prm.obs_full));
+      uint32_t meta = p < p_hi ? s_meta[p - p_lo] : 0u;
+      bool alive = p < p_hi && status_of(p) == ES_ALIVE;
+      bool work = alive || (p < p_hi && ((meta & OM_NONZERO) || prm.obs_full));
       unsigned bm = __ballot_sync(0xffffffffu, work);
       if (work) s_work[n + __popc(bm & ((1u << lane) - 1))] = (uint16_t)(p | (alive ? 0 : 0x8000));
       n += __popc(bm);
@@ -241,7 +264,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     // record are stored.  meta remembers what the record currently holds: rows of Entity /
     // Inventory / Market that are non-zero, whether the Task block is in place, whether the
     // record is non-zero at all.  obs_full = 1 rewrites every byte (roofline / A-B mode).
-    const uint32_t meta = s_meta[p];
+    const uint32_t meta = s_meta[p - p_lo];
     if (went & 0x8000) {                     // dead or absent agents get the zero pad record
       // ... and every head of the built-in policy picks 0: written once, when the agent leaves (the action
       // buffer must start zeroed, which nmmo_set_autosample's caller guarantees)
@@ -270,8 +293,8 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
       n_vis += __popc(bm);
     }
     n_vis = min(n_vis, L.n_ent);
-    const int n_inv = min(s_invn[p], NINV);
-    const uint16_t *inv = s_inv + p * NINV;
+    const int n_inv = min(s_invn[p - p_lo], NINV);
+    const uint16_t *inv = s_inv + (p - p_lo) * NINV;
     #pragma unroll 1
     for (int k = lane; k < stage_bytes / 16; k += 32) ((uint4 *)stage)[k] = ((const uint4 *)s_tmpl)[k];
     __syncwarp();
@@ -320,7 +343,7 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
       m[L.m_destroy + lane] = !eq;
       if (!no_give) m[L.m_give_item + lane] = !eq && !listed;
       m[L.m_sell_item + lane] = !eq && !listed;
-      m[L.m_use + lane] = !listed && OITM(IS_LEVEL, i) <= o_use_level(o, p, OITM(IS_TYPE, i));
+      m[L.m_use + lane] = !listed && OITM(IS_LEVEL, i) <= o_use_level<V>(o, p, OITM(IS_TYPE, i));
     }
     if (!no_give) for (int g = 1 + lane; g < min(my_gold, L.n_price); g += 32) m[L.m_gold_price + g] = 1;
     if (lane < 5) m[L.m_move + lane] = !nm_impassible(tile((r0 + c_dir_dr[lane]) * S + c0 + c_dir_dc[lane]));
@@ -369,7 +392,15 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
       __syncwarp();
       if (lane < AC_N) {
         const uint64_t base64 = nm_hash64(prm.sample_seed + (uint64_t)(prm.env_base + env), (uint32_t)tick, RS_ACTION, (uint32_t)p, 0);
-        const int o0 = s_head[lane], o1 = o0 + s_head[AC_N + lane];
+        const int o0 = s_head[lane];
+        int o1 = o0 + s_head[AC_N + lane];
+        bool stay = false;
+        if (lane == AC_MOVE_DIR && c[NC_SAMPLE_MOVE_PCT] > 0) {
+          // Move-biased workload (BASELINE.json configs[4]): with the given probability a valid direction other
+          // than Stay (the head then covers the four directions only), else Stay
+          const int nv = (m[o0] != 0) + (m[o0 + 1] != 0) + (m[o0 + 2] != 0) + (m[o0 + 3] != 0);
+          if (nv > 0) { if (nm_bounded(nm_action_draw(base64, AC_N), 100) < c[NC_SAMPLE_MOVE_PCT]) o1 = o0 + 4; else stay = true; }
+        }
         const int w0 = o0 >> 5, w1 = (o1 - 1) >> 5;
         auto word_at = [&](int w) -> uint32_t {
           uint32_t x = bits[w];
@@ -383,7 +414,8 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
           // drawn entry come from the running counts, without walking the head's words
           auto rank = [&](int x) -> int { int w = x >> 5; return (int)cum[w] + ((x & 31) ? __popc(bits[w] & ((1u << (x & 31)) - 1u)) : 0); };
           const int rk0 = rank(o0), total = rank(o1) - rk0;
-          if (total > 0) {
+          if (stay) pick = 4;
+          else if (total > 0) {
             const int t = rk0 + nm_bounded(nm_action_draw(base64, lane), total);
             int lo = w0, hi = w1;
             while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((int)cum[mid] <= t) lo = mid; else hi = mid - 1; }
@@ -393,7 +425,8 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
         } else {
         int total = 0;
         for (int w = w0; w <= w1; w++) if (bits[w]) total += __popc(word_at(w));
-        if (total > 0) {
+        if (stay) pick = 4;
+        else if (total > 0) {
           int jj = nm_bounded(nm_action_draw(base64, lane), total);
           for (int w = w0; w <= w1; w++) {
             if (!bits[w]) continue;
@@ -519,8 +552,14 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
     if (tid == 0) { atomicAdd(&prm.prof[36], (unsigned long long)(t_ - t_prev)); atomicAdd(&prm.prof[37], (unsigned long long)n_work); }
   }
   // bytes this CTA stored (+ the state it pulled in): the kernel's physical traffic estimate
-  if (lane == 0) atomicAdd(&prm.counters[4], (unsigned long long)n_stored * 16ULL + (warp == 0 ? (unsigned long long)(ent_bytes + st_bytes + (uint32_t)(IS_N * 2 * item_hi) + map_bytes) : 0ULL));
+  if (lane == 0) atomicAdd(&prm.counters[4], (unsigned long long)n_stored * 16ULL + ((warp == 0 && p_lo == 0) ? (unsigned long long)(ent_bytes + st_bytes + (uint32_t)(IS_N * 2 * item_hi) + map_bytes) : 0ULL));
 }
+
+extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, 3)
+nmmo_obs_kernel(const __grid_constant__ NmParams prm) { obs_body<OSmall>(prm); }
+
+extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, 3)
+nmmo_obs_big_kernel(const __grid_constant__ NmParams prm) { obs_body<OBig>(prm); }
 
 // ============================================================= action sampler kernel ===
 // uniform-random valid action per head from the ActionTargets masks (BASELINE.json config 2:
@@ -529,11 +568,11 @@ nmmo_obs_kernel(const __grid_constant__ NmParams prm) {
 // then each head is counted and selected with ballots over its mask slice.
 extern "C" __global__ void __launch_bounds__(256)
 nmmo_sample_kernel(const __grid_constant__ NmParams prm, uint64_t seed, int32_t *out) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem_sampler[];
   const nm_obs_layout &L = prm.L;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
   const int stage_bytes = nm_align16(L.m_end);
-  uint8_t *stage = smem + (size_t)warp * stage_bytes;
+  uint8_t *stage = smem_sampler + (size_t)warp * stage_bytes;
   const long long n_agents = (long long)prm.E * prm.P;
   const int off[AC_N] = {L.m_style, L.m_target, L.m_buy, L.m_destroy, L.m_give_item, L.m_give_target,
                          L.m_gold_price, L.m_gold_target, L.m_move, L.m_sell_item, L.m_sell_price, L.m_use};
@@ -556,7 +595,15 @@ nmmo_sample_kernel(const __grid_constant__ NmParams prm, uint64_t seed, int32_t 
 #pragma unroll
     for (int h = 0; h < AC_N; h++) {
       // mask bytes are 0/1: count them a 32-bit word at a time, clipped to the head's byte range
-      const int o0 = off[h], o1 = off[h] + len[h];
+      const int o0 = off[h];
+      int o1 = off[h] + len[h];
+      if (h == AC_MOVE_DIR && prm.cfg[NC_SAMPLE_MOVE_PCT] > 0) {      // Move-biased workload, see the observation kernel
+        const int nv = (stage[o0] != 0) + (stage[o0 + 1] != 0) + (stage[o0 + 2] != 0) + (stage[o0 + 3] != 0);
+        if (nv > 0) {
+          if (nm_bounded(nm_action_draw(base64, AC_N), 100) < prm.cfg[NC_SAMPLE_MOVE_PCT]) o1 = o0 + 4;
+          else { if (lane == h) my_pick = 4; continue; }
+        }
+      }
       const int w0 = o0 >> 2, w1 = (o1 + 3) >> 2;
       int total = 0;
       for (int wb = w0; wb < w1; wb += 32) {

@@ -1,5 +1,12 @@
-// nmmo_step.cu -- 256 threads step one environment (two environments per CTA): the whole Realm.step +
-// reward/stat wrapper.
+// nmmo_step.cu -- one thread group steps one environment: the whole Realm.step + reward/stat wrapper.
+//
+// Two instantiations of the same phases (struct VSmall / VBig below):
+//   nmmo_step_kernel      256 threads per environment, two environments per CTA, every table in shared memory
+//                         (PLAYER_N <= 256, P + N <= 512, map <= 255^2: BASELINE.json configs 1-4);
+//   nmmo_step_big_kernel  1024 threads per environment, one environment per CTA; the entity table (row-major), the
+//                         item table and the tile map stay in HBM / L2 and only the hot indices (occupancy bitmap,
+//                         position index, attack lists, inventories) live in shared memory
+//                         (PLAYER_N <= 1024, P + N <= 3072, map <= 1023^2: configs[4], 1024 agents per env).
 //
 // What it replaces in the reference (all per-env, per-agent Python today):
 //   nmmo.Env.step  (call site reinforcement_learning/stat_wrapper.py:64)   -> phases 0..13
@@ -25,16 +32,43 @@
 
 namespace {
 
+// ---- the two kernel families -------------------------------------------------------------------------------------
+struct VSmall {
+  static constexpr int kThreads = NM_STEP_THREADS;      // per environment
+  static constexpr int kRowsPerThread = 2;              // P + N <= 2 * kThreads
+  static constexpr int kChunkIters = 1;                 // 32-row chunks per lane in the per-chunk prefix sums (<= 32 chunks)
+  static constexpr int kEvCap = NM_EV_CAP, kDeplCap = NM_DEPL_CAP, kNpcHash = 512, kTblSlots = 1024;
+  static constexpr bool kGlobalTables = false;          // tables are staged in shared memory by TMA bulk copies
+  typedef uint16_t tile_t;                              // a tile index r * S + c
+  // structure-of-arrays entity table: column-major inside the env (bank-conflict-free per-thread column access)
+  static __host__ __device__ __forceinline__ int ent_idx(int col, int row, int R) { return col * R + row; }
+};
+struct VBig {
+  static constexpr int kThreads = NM_BIG_THREADS;
+  static constexpr int kRowsPerThread = 3;
+  static constexpr int kChunkIters = 3;                 // <= 96 chunks
+  static constexpr int kEvCap = NM_BIG_EV_CAP, kDeplCap = NM_BIG_DEPL_CAP, kNpcHash = 4096, kTblSlots = 8192;
+  static constexpr bool kGlobalTables = true;           // tables are used where they live (HBM, served from L2)
+  typedef uint32_t tile_t;
+  // row-major entity table, NM_BIG_ENT_STRIDE int16 per row: the columns of one entity share L2 sectors, and the
+  // 31 observed columns are the first 62 bytes of the row, which is what the observation kernel copies out
+  static __host__ __device__ __forceinline__ int ent_idx(int col, int row, int) { return row * NM_BIG_ENT_STRIDE + col; }
+};
+// attack registrations: (round tag << kIdxBits) | index of the attack in the ordered list (< 4096 attacks per env)
+constexpr int kIdxBits = 12;
+
 enum { A_USE = 0, A_DESTROY, A_SELL_ITEM, A_SELL_PRICE, A_BUY, A_GIVE_ITEM, A_GIVE_TARGET, A_GOLD_AMT,
        A_GOLD_TARGET, A_ATT_STYLE, A_ATT_TARGET, A_MOVE, A_N };
 
+template <class V>
 struct Ctx {
+  typedef typename V::tile_t tile_t;
   const NmParams *p;
   const int32_t *c;
   int env, P, N, R, S, CAP, NINV;
   int16_t *ent, *item;
   uint32_t *map;            // 4-bit materials, 8 tiles per word
-  uint16_t *dlist;          // depleted tiles known at the start of the tick + the ones harvested during it (sc[17] = count)
+  tile_t *dlist;            // depleted tiles known at the start of the tick + the ones harvested during it (sc[17] = count)
   uint32_t *occ, *used, *fresh;
   uint16_t *inv;
   uint8_t *invn;
@@ -48,14 +82,14 @@ struct Ctx {
   int *task;                  // [P][4] pred, p0, p1, spare: the agent's task row for event folding
   int *acc;                   // [P][2] event-driven predicate accumulators
   int8_t *slow;               // [P] result of the window-scan predicates (-1 = not requested)
-  const uint32_t *plist;      // alive players at the start of the step: row<<16 | r<<8 | c, ascending row
+  const uint32_t *plist;      // alive players at the start of the step: row<<20 | r<<10 | c, ascending row
   int n_plist;
   const uint32_t *predraw;    // NPC-spawn draws computed in parallel: [attempt][8]
   uint64_t seed;
   int tick;
   int inj_lo, inj_hi;
 };
-#define ENT(col, row) ctx.ent[(col) * ctx.R + (row)]
+#define ENT(col, row) ctx.ent[V::ent_idx((col), (row), ctx.R)]
 #define ITM(col, row) ctx.item[(col) * ctx.CAP + (row)]
 
 // one out-of-line copy of the draw (hash + injected-value lookup): it is called from ~16 sites and
@@ -75,23 +109,28 @@ __device__ __forceinline__ uint32_t draw_impl(const uint64_t *inj_keys, const ui
   }
   return nm_hash_draw(seed, tick, site, idx, k);
 }
-__device__ __forceinline__ uint32_t draw(const Ctx &ctx, uint32_t site, uint32_t idx, uint32_t k) {
+template <class V>
+__device__ __forceinline__ uint32_t draw(const Ctx<V> &ctx, uint32_t site, uint32_t idx, uint32_t k) {
   return draw_impl(ctx.p->inj_keys, ctx.p->inj_vals, ctx.inj_lo, ctx.inj_hi, ctx.seed, (uint32_t)ctx.tick, site, idx, k);
 }
 
 // ------------------------------------------------------------------ event ring ------
-__device__ void emit(const Ctx &ctx, int prow, int code, int type, int level, int number, int gold, int target) {
+template <class V>
+__device__ void emit(const Ctx<V> &ctx, int prow, int code, int type, int level, int number, int gold, int target) {
   int i = atomicAdd(&ctx.sc[0], 1);
-  if (i >= NM_EV_CAP) { ctx.sc[1] = 1; return; }
-  uint32_t w0 = (uint32_t)prow | ((uint32_t)nm_dense_event(code) << 8) | ((uint32_t)type << 16) |
-                ((uint32_t)(level & 15) << 24) | (target > 0 ? (1u << 28) : 0u) | (target < 0 ? (1u << 29) : 0u);
+  if (i >= V::kEvCap) { ctx.sc[1] = 1; return; }
+  // agent 16 bits | dense event 5 | item type / skill 5 | level 4 | target sign 2
+  uint32_t w0 = (uint32_t)prow | ((uint32_t)nm_dense_event(code) << 16) | ((uint32_t)type << 21) |
+                ((uint32_t)(level & 15) << 26) | (target > 0 ? (1u << 30) : 0u) | (target < 0 ? (1u << 31) : 0u);
   uint32_t w1 = (uint32_t)(uint16_t)number | ((uint32_t)(uint16_t)gold << 16);
   ctx.ev[i] = make_uint2(w0, w1);
 }
 
 // ----------------------------------------------------------- item / inventory -------
-__device__ __forceinline__ bool row_used(const Ctx &ctx, int row) { return (ctx.used[row >> 5] >> (row & 31)) & 1u; }
-__device__ int item_alloc(const Ctx &ctx) {          // lowest free row; sequential phases only
+template <class V>
+__device__ __forceinline__ bool row_used(const Ctx<V> &ctx, int row) { return (ctx.used[row >> 5] >> (row & 31)) & 1u; }
+template <class V>
+__device__ int item_alloc(const Ctx<V> &ctx) {          // lowest free row; sequential phases only
   int words = (ctx.CAP + 31) >> 5;
   #pragma unroll 1
   for (int w = 0; w < words; w++) {
@@ -106,18 +145,21 @@ __device__ int item_alloc(const Ctx &ctx) {          // lowest free row; sequent
   }
   return -1;
 }
-__device__ void inv_remove(const Ctx &ctx, int owner_row, int row) {
+template <class V>
+__device__ void inv_remove(const Ctx<V> &ctx, int owner_row, int row) {
   int n = ctx.invn[owner_row];
   uint16_t *l = ctx.inv + owner_row * ctx.NINV;
   #pragma unroll 1
   for (int i = 0; i < n; i++)
     if (l[i] == row) { l[i] = l[n - 1]; ctx.invn[owner_row] = (uint8_t)(n - 1); return; }
 }
-__device__ void inv_add(const Ctx &ctx, int owner_row, int row) {
+template <class V>
+__device__ void inv_add(const Ctx<V> &ctx, int owner_row, int row) {
   int n = ctx.invn[owner_row];
   if (n < ctx.NINV) { ctx.inv[owner_row * ctx.NINV + n] = (uint16_t)row; ctx.invn[owner_row] = (uint8_t)(n + 1); }
 }
-__device__ int find_stack(const Ctx &ctx, int owner_row, int type, int level, int exclude) {
+template <class V>
+__device__ int find_stack(const Ctx<V> &ctx, int owner_row, int type, int level, int exclude) {
   int n = ctx.invn[owner_row];
   const uint16_t *l = ctx.inv + owner_row * ctx.NINV;
   #pragma unroll 1
@@ -136,7 +178,8 @@ __device__ int equip_col(int type) {
   return -1;
 }
 // frees the row; the owner's list and equipment slot are fixed up (owner_row < 0: no owner)
-__device__ void item_destroy(const Ctx &ctx, int row) {
+template <class V>
+__device__ void item_destroy(const Ctx<V> &ctx, int row) {
   int owner = ITM(IS_OWNER, row);
   if (owner > 0) {
     int orow = owner - 1;
@@ -151,7 +194,8 @@ __device__ void item_destroy(const Ctx &ctx, int row) {
   atomicAnd(&ctx.used[row >> 5], ~(1u << (row & 31)));
 }
 // move an existing row into new_owner's inventory (ammo merges into an existing stack)
-__device__ void inv_receive_existing(const Ctx &ctx, int new_owner_row, int row) {
+template <class V>
+__device__ void inv_receive_existing(const Ctx<V> &ctx, int new_owner_row, int row) {
   int type = ITM(IS_TYPE, row);
   int old_owner = ITM(IS_OWNER, row);
   if (it_ammo(type)) {
@@ -162,7 +206,8 @@ __device__ void inv_receive_existing(const Ctx &ctx, int new_owner_row, int row)
   ITM(IS_OWNER, row) = (int16_t)(new_owner_row + 1);
   inv_add(ctx, new_owner_row, row);
 }
-__device__ void inv_receive_new(const Ctx &ctx, int owner_row, int type, int level, int qty) {
+template <class V>
+__device__ void inv_receive_new(const Ctx<V> &ctx, int owner_row, int type, int level, int qty) {
   if (it_ammo(type)) {
     int st = find_stack(ctx, owner_row, type, level, -1);
     if (st >= 0) { ITM(IS_QUANTITY, st) = (int16_t)(ITM(IS_QUANTITY, st) + qty); return; }
@@ -174,7 +219,8 @@ __device__ void inv_receive_new(const Ctx &ctx, int owner_row, int type, int lev
   inv_add(ctx, owner_row, row);
 }
 // item argument of a validated action: must still be the object the agent saw
-__device__ int valid_item_ref(const Ctx &ctx, int item_id, int owner) {
+template <class V>
+__device__ int valid_item_ref(const Ctx<V> &ctx, int item_id, int owner) {
   if (item_id <= 0 || item_id > ctx.CAP) return -1;
   int row = item_id - 1;
   if (!row_used(ctx, row) || ((ctx.fresh[row >> 5] >> (row & 31)) & 1u)) return -1;
@@ -183,10 +229,12 @@ __device__ int valid_item_ref(const Ctx &ctx, int item_id, int owner) {
 }
 
 // -------------------------------------------------------------------- entities ------
-__device__ __forceinline__ bool ent_alive(const Ctx &ctx, int row) {
+template <class V>
+__device__ __forceinline__ bool ent_alive(const Ctx<V> &ctx, int row) {
   return row >= 0 && ENT(EA_STATUS, row) == ES_ALIVE && ENT(EA_HEALTH, row) > 0;
 }
-__device__ int level_at_exp(const Ctx &ctx, int exp) {
+template <class V>
+__device__ int level_at_exp(const Ctx<V> &ctx, int exp) {
   int lmax = ctx.c[NC_LEVEL_MAX];
   if (exp >= ctx.c[NC_EXP_THRESH0 + lmax - 1]) return lmax;
   int lvl = 0;
@@ -194,7 +242,8 @@ __device__ int level_at_exp(const Ctx &ctx, int exp) {
   while (lvl < lmax && exp >= ctx.c[NC_EXP_THRESH0 + lvl]) lvl++;
   return lvl;
 }
-__device__ void add_xp(const Ctx &ctx, int row, int level_col, int skill_id, int xp) {
+template <class V>
+__device__ void add_xp(const Ctx<V> &ctx, int row, int level_col, int skill_id, int xp) {
   int lmax = ctx.c[NC_LEVEL_MAX];
   int nexp = min(ENT(level_col + 1, row) + xp, ctx.c[NC_EXP_THRESH0 + lmax - 1]);
   ENT(level_col + 1, row) = (int16_t)nexp;
@@ -204,10 +253,12 @@ __device__ void add_xp(const Ctx &ctx, int row, int level_col, int skill_id, int
     if (row < ctx.P) emit(ctx, row, EV_LEVEL_UP, skill_id, nl, 0, 0, 0);
   }
 }
-__device__ int attack_level(const Ctx &ctx, int row) {
+template <class V>
+__device__ int attack_level(const Ctx<V> &ctx, int row) {
   return max(ENT(EA_MELEE_LEVEL, row), max(ENT(EA_RANGE_LEVEL, row), ENT(EA_MAGE_LEVEL, row)));
 }
-__device__ int use_level(const Ctx &ctx, int row, int type) {
+template <class V>
+__device__ int use_level(const Ctx<V> &ctx, int row, int type) {
   switch (type) {
     case IT_SPEAR: case IT_WHETSTONE: return ENT(EA_MELEE_LEVEL, row);
     case IT_BOW: case IT_ARROW: return ENT(EA_RANGE_LEVEL, row);
@@ -225,22 +276,30 @@ __device__ int use_level(const Ctx &ctx, int row, int type) {
   }
 }
 // the tile map is packed 4 bits per tile (16 materials), tile i in bits 4*(i&7) of word i>>3
-__device__ __forceinline__ int tile_i(const Ctx &ctx, int i) { return (ctx.map[i >> 3] >> ((i & 7) * 4)) & 15; }
-__device__ __forceinline__ int tile_at(const Ctx &ctx, int r, int c) { return tile_i(ctx, r * ctx.S + c); }
+template <class V>
+__device__ __forceinline__ int tile_i(const Ctx<V> &ctx, int i) { return (ctx.map[i >> 3] >> ((i & 7) * 4)) & 15; }
+template <class V>
+__device__ __forceinline__ int tile_at(const Ctx<V> &ctx, int r, int c) { return tile_i(ctx, r * ctx.S + c); }
 // materials only ever change by one step (harvest: m -> m-1, respawn: m -> m+1) and never leave
 // 0..15, so an atomic add on the word is an exact update of one nibble under concurrent writers
-__device__ __forceinline__ void tile_dec(const Ctx &ctx, int i) {      // harvest: the tile joins the depleted list
+template <class V>
+__device__ __forceinline__ void tile_dec(const Ctx<V> &ctx, int i) {      // harvest: the tile joins the depleted list
   atomicSub(&ctx.map[i >> 3], 1u << ((i & 7) * 4));
   const int k = atomicAdd(&ctx.sc[17], 1);
-  if (k < NM_DEPL_CAP) ctx.dlist[k] = (uint16_t)i;
+  if (k < V::kDeplCap) ctx.dlist[k] = (typename V::tile_t)i;
 }
-__device__ __forceinline__ void tile_inc(const Ctx &ctx, int i) { atomicAdd(&ctx.map[i >> 3], 1u << ((i & 7) * 4)); }
-__device__ __forceinline__ bool occ_get(const Ctx &ctx, int r, int c) { int i = r * ctx.S + c; return (ctx.occ[i >> 5] >> (i & 31)) & 1u; }
-__device__ __forceinline__ void occ_set(const Ctx &ctx, int r, int c) { int i = r * ctx.S + c; atomicOr(&ctx.occ[i >> 5], 1u << (i & 31)); }
-__device__ __forceinline__ void occ_clr(const Ctx &ctx, int r, int c) { int i = r * ctx.S + c; atomicAnd(&ctx.occ[i >> 5], ~(1u << (i & 31))); }
+template <class V>
+__device__ __forceinline__ void tile_inc(const Ctx<V> &ctx, int i) { atomicAdd(&ctx.map[i >> 3], 1u << ((i & 7) * 4)); }
+template <class V>
+__device__ __forceinline__ bool occ_get(const Ctx<V> &ctx, int r, int c) { int i = r * ctx.S + c; return (ctx.occ[i >> 5] >> (i & 31)) & 1u; }
+template <class V>
+__device__ __forceinline__ void occ_set(const Ctx<V> &ctx, int r, int c) { int i = r * ctx.S + c; atomicOr(&ctx.occ[i >> 5], 1u << (i & 31)); }
+template <class V>
+__device__ __forceinline__ void occ_clr(const Ctx<V> &ctx, int r, int c) { int i = r * ctx.S + c; atomicAnd(&ctx.occ[i >> 5], ~(1u << (i & 31))); }
 
 // ------------------------------------------------------------------ harvesting ------
-__device__ void process_drops(const Ctx &ctx, int prow, int matl, int level_col, int skill_id) {
+template <class V>
+__device__ void process_drops(const Ctx<V> &ctx, int prow, int matl, int level_col, int skill_id) {
   int tool_type = 0, ammo = 0, weapon = 0, consumable = 0;
   switch (matl) {
     case MT_FISH: tool_type = IT_ROD; consumable = IT_RATION; break;
@@ -266,14 +325,16 @@ __device__ void process_drops(const Ctx &ctx, int prow, int matl, int level_col,
   }
   add_xp(ctx, prow, level_col, skill_id, consumable ? ctx.c[NC_XP_CONSUMABLE] : ctx.c[NC_XP_AMMO]);
 }
-__device__ bool tile_harvest(const Ctx &ctx, int r, int c, int matl) {
+template <class V>
+__device__ bool tile_harvest(const Ctx<V> &ctx, int r, int c, int matl) {
   int i = r * ctx.S + c;
   if (tile_i(ctx, i) != matl) return false;
   tile_dec(ctx, i);
   return true;
 }
 // the id-ordered part of Player.update: anything that depletes a tile or allocates an item
-__device__ void player_harvest(const Ctx &ctx, int p) {
+template <class V>
+__device__ void player_harvest(const Ctx<V> &ctx, int p) {
   int r = ENT(EA_ROW, p), c = ENT(EA_COL, p);
   if (tile_harvest(ctx, r, c, MT_FOILAGE)) {
     ENT(EA_FOOD, p) = (int16_t)min(ctx.c[NC_RES_BASE], ENT(EA_FOOD, p) + ctx.c[NC_RES_HARVEST_RESTORE]);
@@ -292,14 +353,16 @@ __device__ void player_harvest(const Ctx &ctx, int p) {
 }
 
 // ---------------------------------------------------------------------- npc ai ------
-__device__ bool valid_target(const Ctx &ctx, int row, int targ_id, int rng) {
+template <class V>
+__device__ bool valid_target(const Ctx<V> &ctx, int row, int targ_id, int rng) {
   if (targ_id <= 0 || targ_id > ctx.P) return false;      // NPCs only ever track players
   int t = targ_id - 1;
   if (!ent_alive(ctx, t)) return false;
   return nm_linf(ENT(EA_ROW, row), ENT(EA_COL, row), ENT(EA_ROW, t), ENT(EA_COL, t)) <= rng;
 }
 // first player met by the reference's ring scan (nmmo/systems/ai/utils.py closestTarget)
-__device__ int closest_target(const Ctx &ctx, int row, int rng) {
+template <class V>
+__device__ int closest_target(const Ctx<V> &ctx, int row, int rng) {
   int sr = ENT(EA_ROW, row), sc = ENT(EA_COL, row);
   {   // nothing but me inside the window? (11-bit row slices of the occupancy bitmap)
     unsigned any = 0;
@@ -314,8 +377,8 @@ __device__ int closest_target(const Ctx &ctx, int row, int rng) {
   int best = 0x7fffffff, best_id = 0;
   for (int k = 0; k < ctx.n_plist; k++) {
     uint32_t x = ctx.plist[k];
-    int p = (int)(x >> 16);
-    int dr = (int)((x >> 8) & 255u) - sr, dc = (int)(x & 255u) - sc;
+    int p = (int)(x >> 20);
+    int dr = (int)((x >> 10) & 1023u) - sr, dc = (int)(x & 1023u) - sc;
     int d = max(nm_iabs(dr), nm_iabs(dc));
     if (d > rng) continue;
     int rk = 0x7fffffff;
@@ -332,8 +395,8 @@ __device__ int closest_target(const Ctx &ctx, int row, int rng) {
 // HN = node-table slots.  The search is first tried with a small table (cheap to clear; enough
 // for the common open-ground chase) and repeated with the full-size table if it fills up; the
 // result is identical either way.  Returns -2 when the table overflowed.
-template <int HN>
-__device__ int astar_dir_t(const Ctx &ctx, int sr, int sc, int gr, int gc) {
+template <class V, int HN>
+__device__ int astar_dir_t(const Ctx<V> &ctx, int sr, int sc, int gr, int gc) {
   const int CUTOFF = 100;
   uint16_t hk[HN]; uint8_t hcost[HN]; int8_t hback[HN];
   uint32_t heap[HN];
@@ -341,8 +404,12 @@ __device__ int astar_dir_t(const Ctx &ctx, int sr, int sc, int gr, int gc) {
   for (int i = 0; i < HN; i++) hk[i] = 0;
   int n_nodes = 0;
   bool overflow = false;
+  // nodes are keyed by their offset from the start tile (+128): the 100-expansion budget keeps the search within
+  // 100 tiles of it, whatever the size of the map; a goal further away than that can never be found in the table
+  const int kr = 128 - sr, kc = 128 - sc;
   auto slot_of = [&](int r, int c, bool insert) -> int {
-    uint16_t key = (uint16_t)(((r << 8) | c) + 1);
+    if ((unsigned)(r + kr) > 255u || (unsigned)(c + kc) > 255u) return -1;
+    uint16_t key = (uint16_t)((((r + kr) << 8) | (c + kc)) + 1);
     int h = (int)((key * 40503u) >> 7) & (HN - 1);
         while (hk[h] != 0 && hk[h] != key) h = (h + 1) & (HN - 1);
     if (hk[h] == 0) {
@@ -372,7 +439,7 @@ __device__ int astar_dir_t(const Ctx &ctx, int sr, int sc, int gr, int gc) {
     return top;
   };
   const int adr[4] = {-1, 1, 0, 0}, adc[4] = {0, 0, -1, 1};
-  push((uint32_t)((sr << 8) | sc));
+  push((uint32_t)((128 << 8) | 128));
   { int s = slot_of(sr, sc, true); hcost[s] = 0; }
   int goal_r = gr, goal_c = gc, close_r = sr, close_c = sc;
   int close_h = nm_iabs(sr - gr) + nm_iabs(sc - gc), close_cost = close_h;
@@ -385,7 +452,7 @@ __device__ int astar_dir_t(const Ctx &ctx, int sr, int sc, int gr, int gc) {
       break;
     }
     uint32_t cur = pop();
-    int cr = (cur >> 8) & 255, cc = cur & 255;
+    int cr = (int)((cur >> 8) & 255) - kr, cc = (int)(cur & 255) - kc;
     if (cr == gr && cc == gc) break;
     int ccost = hcost[slot_of(cr, cc, false)];
         for (int k = 0; k < 4; k++) {
@@ -401,7 +468,7 @@ __device__ int astar_dir_t(const Ctx &ctx, int sr, int sc, int gr, int gc) {
         int h = nm_linf(gr, gc, nr, nc);
         int pri = ncost + h;
         if (h < close_h || (h == close_h && pri < close_cost)) { close_r = nr; close_c = nc; close_h = h; close_cost = pri; }
-        push(((uint32_t)pri << 16) | (uint32_t)((nr << 8) | nc));
+        push(((uint32_t)pri << 16) | (uint32_t)(((nr + kr) << 8) | (nc + kc)));
         hback[s] = (int8_t)k;
       }
     }
@@ -421,12 +488,14 @@ __device__ int astar_dir_t(const Ctx &ctx, int sr, int sc, int gr, int gc) {
   if (dr == 0 && dc == -1) return 3;
   return -1;
 }
-__device__ int astar_dir(const Ctx &ctx, int sr, int sc, int gr, int gc) {
-  int d = astar_dir_t<64>(ctx, sr, sc, gr, gc);
-  if (d == -2) d = astar_dir_t<512>(ctx, sr, sc, gr, gc);
+template <class V>
+__device__ int astar_dir(const Ctx<V> &ctx, int sr, int sc, int gr, int gc) {
+  int d = astar_dir_t<V, 64>(ctx, sr, sc, gr, gc);
+  if (d == -2) d = astar_dir_t<V, 512>(ctx, sr, sc, gr, gc);
   return d;
 }
-__device__ void npc_decide(const Ctx &ctx, int row) {
+template <class V>
+__device__ void npc_decide(const Ctx<V> &ctx, int row) {
   int vis = ctx.c[NC_NPC_VISION];
   int n = row - ctx.P;
   uint32_t k = 0;
@@ -460,7 +529,8 @@ __device__ void npc_decide(const Ctx &ctx, int row) {
 }
 
 // --------------------------------------------------------------------- actions ------
-__device__ void act_use(const Ctx &ctx, int p, int item_id) {
+template <class V>
+__device__ void act_use(const Ctx<V> &ctx, int p, int item_id) {
   int row = valid_item_ref(ctx, item_id, p + 1);
   if (row < 0) return;
   int type = ITM(IS_TYPE, row), level = ITM(IS_LEVEL, row);
@@ -484,19 +554,22 @@ __device__ void act_use(const Ctx &ctx, int p, int item_id) {
   ITM(IS_EQUIPPED, row) = 1; ENT(col, p) = (int16_t)(row + 1);
   emit(ctx, p, EV_EQUIP_ITEM, type, level, ITM(IS_QUANTITY, row), 0, 0);
 }
-__device__ void act_destroy(const Ctx &ctx, int p, int item_id) {
+template <class V>
+__device__ void act_destroy(const Ctx<V> &ctx, int p, int item_id) {
   int row = valid_item_ref(ctx, item_id, p + 1);
   if (row < 0 || ITM(IS_EQUIPPED, row)) return;
   emit(ctx, p, EV_DESTROY_ITEM, ITM(IS_TYPE, row), ITM(IS_LEVEL, row), ITM(IS_QUANTITY, row), 0, 0);
   item_destroy(ctx, row);
 }
-__device__ void act_sell(const Ctx &ctx, int p, int item_id, int price) {
+template <class V>
+__device__ void act_sell(const Ctx<V> &ctx, int p, int item_id, int price) {
   int row = valid_item_ref(ctx, item_id, p + 1);
   if (row < 0 || ITM(IS_EQUIPPED, row) || ITM(IS_PRICE, row)) return;
   ITM(IS_PRICE, row) = (int16_t)price; ITM(IS_LIST_TICK, row) = (int16_t)ctx.tick;
   emit(ctx, p, EV_LIST_ITEM, ITM(IS_TYPE, row), ITM(IS_LEVEL, row), ITM(IS_QUANTITY, row), price, 0);
 }
-__device__ void act_buy(const Ctx &ctx, int p, int item_id) {
+template <class V>
+__device__ void act_buy(const Ctx<V> &ctx, int p, int item_id) {
   int row = valid_item_ref(ctx, item_id, 0);
   if (row < 0) return;
   int owner = ITM(IS_OWNER, row), price = ITM(IS_PRICE, row);
@@ -511,7 +584,8 @@ __device__ void act_buy(const Ctx &ctx, int p, int item_id) {
   emit(ctx, p, EV_BUY_ITEM, type, level, qty, price, 0);
   emit(ctx, owner - 1, EV_EARN_GOLD, 0, 0, 0, price, 0);
 }
-__device__ void act_give(const Ctx &ctx, int p, int item_id, int target_row1) {
+template <class V>
+__device__ void act_give(const Ctx<V> &ctx, int p, int item_id, int target_row1) {
   int row = valid_item_ref(ctx, item_id, p + 1);
   if (row < 0 || target_row1 <= 0) return;
   int t = target_row1 - 1;
@@ -523,7 +597,8 @@ __device__ void act_give(const Ctx &ctx, int p, int item_id, int target_row1) {
   emit(ctx, p, EV_GIVE_ITEM, type, level, ITM(IS_QUANTITY, row), 0, 0);
   inv_receive_existing(ctx, t, row);
 }
-__device__ void act_give_gold(const Ctx &ctx, int p, int amount, int target_row1) {
+template <class V>
+__device__ void act_give_gold(const Ctx<V> &ctx, int p, int amount, int target_row1) {
   if (target_row1 <= 0) return;
   int t = target_row1 - 1;
   if (!ent_alive(ctx, t) || t == p) return;
@@ -535,7 +610,8 @@ __device__ void act_give_gold(const Ctx &ctx, int p, int amount, int target_row1
   emit(ctx, p, EV_GIVE_GOLD, 0, 0, 0, amount, 0);
 }
 // pure part of combat.attack / Attack.call: validity and damage, no side effects
-__device__ bool attack_compute(const Ctx &ctx, int a, int style, int t, int &dmg, bool &ammo_out) {
+template <class V>
+__device__ bool attack_compute(const Ctx<V> &ctx, int a, int style, int t, int &dmg, bool &ammo_out) {
   const int32_t *c = ctx.c;
   bool a_player = a < ctx.P, b_player = t < ctx.P;
   if (a_player && b_player && ENT(EA_TIME_ALIVE, t) < c[NC_SPAWN_IMMUNITY]) return false;
@@ -575,7 +651,8 @@ __device__ bool attack_compute(const Ctx &ctx, int a, int style, int t, int &dmg
   return true;
 }
 // side effects of one attack whose damage is known (attacker a, target row t)
-__device__ void attack_apply(const Ctx &ctx, int a, int style, int t, int dmg) {
+template <class V>
+__device__ void attack_apply(const Ctx<V> &ctx, int a, int style, int t, int dmg) {
   const int32_t *c = ctx.c;
   bool a_player = a < ctx.P, b_player = t < ctx.P;
   int a_id = ENT(EA_ID, a), b_id = ENT(EA_ID, t);
@@ -634,7 +711,8 @@ __device__ void attack_apply(const Ctx &ctx, int a, int style, int t, int dmg) {
       }
   }
 }
-__device__ void act_move(const Ctx &ctx, int row, int dir, bool use_occ) {
+template <class V>
+__device__ void act_move(const Ctx<V> &ctx, int row, int dir, bool use_occ) {
   if (dir < 0 || dir > 3) return;
   if (ENT(EA_FREEZE, row) > 0) return;
   int r = ENT(EA_ROW, row), c = ENT(EA_COL, row);
@@ -656,13 +734,15 @@ __device__ void act_move(const Ctx &ctx, int row, int dir, bool use_occ) {
 }
 
 // ------------------------------------------------------------------ npc spawning ----
-__device__ int border_dist(const Ctx &ctx, int r, int c) {
+template <class V>
+__device__ int border_dist(const Ctx<V> &ctx, int r, int c) {
   int b = ctx.c[NC_MAP_BORDER], ce = ctx.c[NC_MAP_CENTER];
   return min(min(r - b, ce + b - r - 1), min(c - b, ce + b - c - 1));
 }
 // NPCManager.spawn, split: one thread replays the sequential accept/reject logic of the (up to
 // 25) attempts and records the accepted ones; the rows are then filled in by one thread each
-__device__ int npc_spawn_decide(const Ctx &ctx, uint32_t *dec, const int *free_rows, const int *dng) {       // single thread
+template <class V>
+__device__ int npc_spawn_decide(const Ctx<V> &ctx, uint32_t *dec, const int *free_rows, const int *dng) {       // single thread
   const int32_t *c = ctx.c;
   int b = c[NC_MAP_BORDER], ce = c[NC_MAP_CENTER];
   int count = ctx.sc[4];
@@ -709,7 +789,8 @@ __device__ int npc_spawn_decide(const Ctx &ctx, uint32_t *dec, const int *free_r
   ctx.sc[2] = nd;
   return n;
 }
-__device__ void npc_spawn_fill(const Ctx &ctx, const uint32_t *q) {
+template <class V>
+__device__ void npc_spawn_fill(const Ctx<V> &ctx, const uint32_t *q) {
   const int32_t *c = ctx.c;
   int ce = c[NC_MAP_CENTER];
   int row = (int)q[0], r = (int)q[1], cc = (int)q[2], d = (int)q[3], type = (int)q[4], att = (int)q[5];
@@ -736,7 +817,8 @@ __device__ void npc_spawn_fill(const Ctx &ctx, const uint32_t *q) {
 
 // ------------------------------------------------------------------------ tasks -----
 __device__ double clip01(double x) { return x > 1.0 ? 1.0 : (x < 0.0 ? 0.0 : x); }
-__device__ double eval_predicate(const Ctx &ctx, int p, int pred, int p0, int p1, int p2, int acc0, int acc1) {
+template <class V>
+__device__ double eval_predicate(const Ctx<V> &ctx, int p, int pred, int p0, int p1, int p2, int acc0, int acc1) {
   int vis = ctx.c[NC_VISION];
   // Ratio predicates only pick (num, den) here; the one f64 division sits behind the switch, and is skipped when
   // the clipped result is known without it (nothing counted yet, or the goal already reached).
@@ -817,9 +899,10 @@ __device__ double eval_predicate(const Ctx &ctx, int p, int pred, int p0, int p1
 
 // fold one event into the agent's accumulators (process_event_log / count_unique_events /
 // event-driven predicates), order-free
-__device__ void fold_event(const Ctx &ctx, uint2 e) {
-  int agent = e.x & 255, de = (e.x >> 8) & 255, type = (e.x >> 16) & 255, level = (e.x >> 24) & 15;
-  bool tpos = (e.x >> 28) & 1, tneg = (e.x >> 29) & 1;
+template <class V>
+__device__ void fold_event(const Ctx<V> &ctx, uint2 e) {
+  int agent = e.x & 0xffff, de = (e.x >> 16) & 31, type = (e.x >> 21) & 31, level = (e.x >> 26) & 15;
+  bool tpos = (e.x >> 30) & 1, tneg = (e.x >> 31) & 1;
   int number = (int)(int16_t)(e.y & 0xFFFF), gold = (int)(int16_t)(e.y >> 16);
   size_t a = (size_t)ctx.env * ctx.P + agent;
   int32_t *st = ctx.p->stats + a * ST_N;
@@ -856,7 +939,8 @@ __device__ void fold_event(const Ctx &ctx, uint2 e) {
 }
 
 // episode-end info record (stat_wrapper.py:132-185, :216-288)
-__device__ void write_info(const Ctx &ctx, int p, bool terminated, double cum_reward, double max_progress,
+template <class V>
+__device__ void write_info(const Ctx<V> &ctx, int p, bool terminated, double cum_reward, double max_progress,
                            int reward_signals, int completed, int unique_events) {
   size_t a = (size_t)ctx.env * ctx.P + p;
   float *o = ctx.p->info + a * IN_N;
@@ -911,15 +995,16 @@ __device__ void write_info(const Ctx &ctx, int p, bool terminated, double cum_re
 }
 
 // ------------------------------------------------------------------------ reset -----
+template <class V>
 __device__ __noinline__ void reset_env(const NmParams &P_, int env, uint64_t seed, bool explicit_map, bool explicit_tasks,
                           int *s_slot /* >= 2*P ints of shared memory */) {
   const int32_t *c = P_.cfg;
-  int tid = threadIdx.x % NM_STEP_THREADS, T = NM_STEP_THREADS;
-  const int half_id = threadIdx.x / NM_STEP_THREADS;
+  int tid = threadIdx.x % V::kThreads, T = V::kThreads;
+  const int half_id = threadIdx.x / V::kThreads;
   int P = P_.P, R = P_.R, S = P_.S;
   int32_t *sc = P_.scalars + (size_t)env * NM_SC_N;
   // injected draws are keyed by tick 0 here
-  Ctx ctx;
+  Ctx<V> ctx;
   ctx.p = &P_; ctx.c = c; ctx.env = env; ctx.seed = seed; ctx.tick = 0;
   ctx.inj_lo = P_.inj_off ? P_.inj_off[env] : 0; ctx.inj_hi = P_.inj_off ? P_.inj_off[env + 1] : 0;
   int map_id = explicit_map ? sc[SC_MAP_ID] : nm_bounded(draw(ctx, RS_MAP, 0, 0), P_.n_maps);
@@ -936,9 +1021,10 @@ __device__ __noinline__ void reset_env(const NmParams &P_, int env, uint64_t see
                ((hi & 15u) << 16) | (((hi >> 8) & 15u) << 20) | (((hi >> 16) & 15u) << 24) | (((hi >> 24) & 15u) << 28);
     }
     uint4 z = make_uint4(0, 0, 0, 0);
-    uint4 *e4 = (uint4 *)(P_.ent + (size_t)env * EA_N * R);
+    const size_t ent_i16 = V::kGlobalTables ? (size_t)NM_BIG_ENT_STRIDE * R : (size_t)EA_N * R;      // int16 per env
+    uint4 *e4 = (uint4 *)(P_.ent + (size_t)env * ent_i16);
     #pragma unroll 1
-    for (int i = tid; i < EA_N * R * 2 / 16; i += T) e4[i] = z;
+    for (int i = tid; i < (int)(ent_i16 * 2 / 16); i += T) e4[i] = z;
     // the item table is not cleared: SC_ITEM_HI = 0 below declares every row free
     uint32_t *u = P_.uniq + (size_t)env * P * NM_UNIQ_WORDS;
     #pragma unroll 1
@@ -963,8 +1049,9 @@ __device__ __noinline__ void reset_env(const NmParams &P_, int env, uint64_t see
     }
   }
   // barrier over this environment's own 256 threads (the other half of the CTA may be stepping, or gone)
-  asm volatile("bar.sync %0, %1;" ::"r"(1 + half_id), "r"(NM_STEP_THREADS) : "memory");      // also orders the table clears before the row writes below
-  int16_t *ent = P_.ent + (size_t)env * EA_N * R;
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + half_id), "r"(V::kThreads) : "memory");      // also orders the table clears before the row writes below
+  int16_t *ent = P_.ent + (size_t)env * (V::kGlobalTables ? (size_t)NM_BIG_ENT_STRIDE * R : (size_t)EA_N * R);
+  const int patch = c[NC_SPAWN_PATCH];
   int b = c[NC_MAP_BORDER], ce = c[NC_MAP_CENTER];
   #pragma unroll 1
   for (int p = tid; p < P; p += T) {
@@ -974,7 +1061,11 @@ __device__ __noinline__ void reset_env(const NmParams &P_, int env, uint64_t see
     else if (side == 1) { r = b + off; cc = b + ce; }
     else if (side == 2) { r = b + ce; cc = b + ce - off; }
     else { r = b + ce - off; cc = b; }
-#define GENT(col) ent[(col) * R + p]
+    if (patch > 0) {      // stress workload (BASELINE.json configs[4]): shuffled cells of a patch x patch square at the centre
+      const int o = S / 2 - patch / 2, cell = (int)(((long long)slot[p] * patch * patch) / P);
+      r = o + cell / patch; cc = o + cell % patch;
+    }
+#define GENT(col) ent[V::ent_idx((col), p, R)]
     GENT(EA_ID) = (int16_t)(p + 1); GENT(EA_ROW) = (int16_t)r; GENT(EA_COL) = (int16_t)cc;
     GENT(EA_GOLD) = (int16_t)c[NC_BASE_GOLD]; GENT(EA_HEALTH) = (int16_t)c[NC_RES_BASE];
     GENT(EA_FOOD) = (int16_t)c[NC_RES_BASE]; GENT(EA_WATER) = (int16_t)c[NC_RES_BASE];
@@ -997,33 +1088,39 @@ __device__ __noinline__ void reset_env(const NmParams &P_, int env, uint64_t see
 
 }  // namespace
 
-// Barriers over one environment's 256 threads (named barrier 1 + half).  Two environments share a CTA
-// so that they walk the kernel's code together (one instruction fetch serves both); they never wait for each other.
-#define HSYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(NM_STEP_THREADS) : "memory")
-__device__ __forceinline__ int half_or(int pred, int half) {
+// Barriers over one environment's threads (named barrier 1 + half).  In the small family two environments share a
+// CTA so that they walk the kernel's code together (one instruction fetch serves both); they never wait for each other.
+#define HSYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "n"(V::kThreads) : "memory")
+template <int NT>
+__device__ __forceinline__ int half_or_t(int pred, int half) {
   int r;
   asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %1, 0; bar.red.or.pred q, %2, %3, p; selp.s32 %0, 1, 0, q; }"
-               : "=r"(r) : "r"(pred), "r"(1 + half), "r"(NM_STEP_THREADS) : "memory");
+               : "=r"(r) : "r"(pred), "r"(1 + half), "n"(NT) : "memory");
   return r;
 }
-__device__ __forceinline__ int half_count(int pred, int half) {
+template <int NT>
+__device__ __forceinline__ int half_count_t(int pred, int half) {
   int r;
   asm volatile("{ .reg .pred p; setp.ne.s32 p, %1, 0; bar.red.popc.u32 %0, %2, %3, p; }"
-               : "=r"(r) : "r"(pred), "r"(1 + half), "r"(NM_STEP_THREADS) : "memory");
+               : "=r"(r) : "r"(pred), "r"(1 + half), "n"(NT) : "memory");
   return r;
 }
+#define half_or(pred, half) half_or_t<V::kThreads>((pred), (half))
+#define half_count(pred, half) half_count_t<V::kThreads>((pred), (half))
 
 // ===================================================================== step kernel ====
-extern "C" __global__ void __launch_bounds__(2 * NM_STEP_THREADS, 1)
-nmmo_step_kernel(const __grid_constant__ NmParams prm) {
-  // Two environments per CTA, 256 threads and half of the dynamic shared memory each.  They share nothing
-  // and never wait for each other (every barrier below is a named barrier over one half); the point of the
+template <class V>
+__device__ __forceinline__ void step_body(const NmParams &prm) {
+  // Small family: two environments per CTA, 256 threads and half of the dynamic shared memory each.  They share
+  // nothing and never wait for each other (every barrier below is a named barrier over one half); the point of the
   // pairing is that both walk the kernel's 300 KB of code at the same time, so the SM fetches it once
   // (measured: 0.63 -> 0.56 ms against two independent 256-thread CTAs per SM).
+  // Big family: one environment per CTA (half == 0).
+  typedef typename V::tile_t tile_t;
   extern __shared__ __align__(128) uint8_t smem_all[];
-  const int half = threadIdx.x / NM_STEP_THREADS;
+  const int half = threadIdx.x / V::kThreads;
   uint8_t *smem = smem_all + (size_t)half * prm.half_smem;
-  const int env = blockIdx.x * prm.envs_per_cta + half, tid = threadIdx.x % NM_STEP_THREADS, T = NM_STEP_THREADS, lane = tid & 31, warp = tid >> 5;
+  const int env = blockIdx.x * prm.envs_per_cta + half, tid = threadIdx.x % V::kThreads, T = V::kThreads, lane = tid & 31, warp = tid >> 5;
   const int32_t *c = prm.cfg;
   const int P = prm.P, N = prm.N, R = prm.R, S = prm.S, CAP = prm.CAP, NINV = c[NC_N_INV];
   if (env >= prm.E) return;          // odd environment count: the last CTA runs one half (exited threads do not count at barriers)
@@ -1032,42 +1129,56 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   // ---- reset paths -------------------------------------------------------------------
   if (prm.mode == 1) {
     if (!gsc[SC_NEED_RESET]) return;
-    reset_env(prm, env, prm.seed[env], gsc[SC_EXPLICIT_MAP] != 0, gsc[SC_EXPLICIT_TASKS] != 0, (int *)smem);
+    reset_env<V>(prm, env, prm.seed[env], gsc[SC_EXPLICIT_MAP] != 0, gsc[SC_EXPLICIT_TASKS] != 0, (int *)smem);
     return;
   }
 
   // ---- shared memory carve-up ---------------------------------------------------------
-  size_t off = 0;
+  size_t off = 0, goff = 0;
   auto carve = [&](size_t bytes) { uint8_t *q = smem + off; off = (off + bytes + 15) & ~(size_t)15; return q; };
+  // big family: the arrays that are touched a few times per tick live in a per-env workspace in HBM / L2
+  uint8_t *const gws = V::kGlobalTables ? prm.ws + (size_t)env * prm.ws_bytes : nullptr;
+  auto carve_ws = [&](size_t bytes) {
+    if (!V::kGlobalTables) return carve(bytes);
+    uint8_t *q = gws + goff; goff = (goff + bytes + 15) & ~(size_t)15; return q;
+  };
   const uint32_t ent_bytes = (uint32_t)(EA_N * R * 2), item_bytes = (uint32_t)(IS_N * CAP * 2), map_bytes = (uint32_t)(S * S / 2);
-  Ctx ctx;
+  Ctx<V> ctx;
   ctx.p = &prm; ctx.c = c; ctx.env = env; ctx.P = P; ctx.N = N; ctx.R = R; ctx.S = S; ctx.CAP = CAP; ctx.NINV = NINV;
   int16_t *const gitem = prm.item + (size_t)env * IS_N * CAP;
-  ctx.ent = (int16_t *)carve(ent_bytes);
-  ctx.item = (int16_t *)carve(item_bytes);
-  ctx.map = (uint32_t *)carve(map_bytes);
+  if (V::kGlobalTables) {
+    ctx.ent = prm.ent + (size_t)env * NM_BIG_ENT_STRIDE * R;
+    ctx.item = gitem;
+    ctx.map = (uint32_t *)(prm.map + (size_t)env * map_bytes);
+  } else {
+    ctx.ent = (int16_t *)carve(ent_bytes);
+    ctx.item = (int16_t *)carve(item_bytes);
+    ctx.map = (uint32_t *)carve(map_bytes);
+  }
   const int occ_words = (S * S + 31) >> 5, cap_words = (CAP + 31) >> 5;
   ctx.occ = (uint32_t *)carve(occ_words * 4);
   ctx.used = (uint32_t *)carve(cap_words * 4);
   ctx.fresh = (uint32_t *)carve(cap_words * 4);
   ctx.inv = (uint16_t *)carve((size_t)P * NINV * 2);
   ctx.invn = carve(P);
-  ctx.act = (int16_t *)carve((size_t)A_N * P * 2);
+  ctx.act = (int16_t *)carve_ws((size_t)A_N * P * 2);
   ctx.npc_move = (int8_t *)carve(N);
   ctx.npc_att = (int16_t *)carve((size_t)N * 2);
-  ctx.ev = (uint2 *)carve(NM_EV_CAP * 8);
+  ctx.ev = (uint2 *)carve_ws((size_t)V::kEvCap * 8);
   ctx.duniq = (int *)carve((size_t)P * 4);
   int *s_list = (int *)carve((size_t)P * 4);
-  ctx.npc_hash = (unsigned short *)carve(512 * 2);
-  ctx.task = (int *)carve((size_t)P * 16);
-  ctx.acc = (int *)carve((size_t)P * 8);
+  ctx.npc_hash = (unsigned short *)carve((size_t)V::kNpcHash * 2);
+  ctx.task = (int *)carve_ws((size_t)P * 16);
+  ctx.acc = (int *)carve_ws((size_t)P * 8);
   // 4 KB scratch reused phase by phase: attack list + registrations, move tile hash,
   // respawn worklist, NPC-spawn pre-drawn values
   const size_t scratch_bytes = max((size_t)4096, (size_t)R * 8);
-  uint32_t *s_scratch = (uint32_t *)carve(scratch_bytes + 64);      // + 16 per-chunk counts behind the two attack arrays
-  uint16_t *s_mv = (uint16_t *)carve((size_t)R * 4);        // Move phase: destination + verdict per row
-  ctx.dlist = (uint16_t *)carve(NM_DEPL_CAP * 2);
-  uint32_t *s_tbl = (uint32_t *)carve(1024 * 4);           // Move phase: position index (tile -> row), 1024 slots
+  uint32_t *s_scratch = (uint32_t *)carve(scratch_bytes + 32 * V::kChunkIters * 4);      // + the per-chunk counts behind the two attack arrays
+  uint8_t *s_mv = carve((size_t)R * (sizeof(tile_t) + 2));     // Move phase: destination (tile_t) + verdict (u16) per row; >= R * 4 bytes
+  // depleted-tile list: staged in shared memory (small) / used in place in HBM (big)
+  tile_t *const gdepl = (tile_t *)prm.depl + (size_t)env * V::kDeplCap;
+  ctx.dlist = V::kGlobalTables ? gdepl : (tile_t *)carve((size_t)V::kDeplCap * sizeof(tile_t));
+  uint32_t *s_tbl = (uint32_t *)carve((size_t)V::kTblSlots * 4);           // Move phase: position index (tile -> row)
   uint32_t *s_att = s_scratch;
   int *s_first = (int *)(s_scratch + R);
   ctx.slow = (int8_t *)carve((size_t)P);
@@ -1075,6 +1186,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   ctx.sc = (int *)carve(32 * 4);
   uint64_t *bar = (uint64_t *)carve(16);
   // ---- load: three bulk copies on one mbarrier, issued before anything else touches HBM ----
+  if (!V::kGlobalTables) {
   if (tid == 0) {
     mbar_init(bar, 1); mbar_init(bar + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1085,17 +1197,18 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     bulk_g2s(ctx.ent, prm.ent + (size_t)env * EA_N * R, ent_bytes, bar);
     bulk_g2s(ctx.map, prm.map + (size_t)env * map_bytes, map_bytes, bar);
   }
+  }
   const int done_flag = gsc[SC_DONE];      // consumed below, after the other loads are in flight
   const int item_hi0 = gsc[SC_ITEM_HI];    // rows >= item_hi0 are free (multiple of 8)
   const int n_depl0 = gsc[SC_N_DEPL];      // depleted tiles listed in prm.depl (-1: list unknown)
-  if (tid == 0) {
+  if (!V::kGlobalTables && tid == 0) {
     // Item rows are allocated lowest-free-first, so live rows crowd the low end of the table: only
     // the prefix below the high-water mark moves between HBM and shared memory.  Rows above it are
     // never read before they are allocated (the in-use bitmap is built from the prefix).
     const uint32_t col_bytes = (uint32_t)item_hi0 * 2;
-    const uint32_t dl_bytes = n_depl0 > 0 ? (uint32_t)((n_depl0 * 2 + 15) & ~15) : 0u;
+    const uint32_t dl_bytes = n_depl0 > 0 ? (uint32_t)((n_depl0 * (int)sizeof(tile_t) + 15) & ~15) : 0u;
     mbar_expect_tx(bar + 1, col_bytes * IS_N + dl_bytes);
-    if (dl_bytes) bulk_g2s(ctx.dlist, prm.depl + (size_t)env * NM_DEPL_CAP, dl_bytes, bar + 1);
+    if (dl_bytes) bulk_g2s(ctx.dlist, gdepl, dl_bytes, bar + 1);
     if (col_bytes)
       for (int k = 0; k < IS_N; k++) bulk_g2s(ctx.item + k * CAP, gitem + (size_t)k * CAP, col_bytes, bar + 1);
   }
@@ -1132,8 +1245,9 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   #pragma unroll 1
   for (int i = tid; i < P; i += T) { ctx.invn[i] = 0; ctx.duniq[i] = 0; }
   #pragma unroll 1
-  for (int i = tid; i < 256; i += T) ((uint32_t *)ctx.npc_hash)[i] = 0;
-  for (int i = tid; i < 1024; i += T) s_tbl[i] = 0;
+  for (int i = tid; i < V::kNpcHash / 2; i += T) ((uint32_t *)ctx.npc_hash)[i] = 0;
+  #pragma unroll 1
+  for (int i = tid; i < V::kTblSlots; i += T) s_tbl[i] = 0;
   if (tid < P) {
     ctx.task[tid * 4] = my_t[0]; ctx.task[tid * 4 + 1] = my_t[1]; ctx.task[tid * 4 + 2] = my_t[2]; ctx.task[tid * 4 + 3] = 0;
     ctx.acc[tid * 2] = my_acc0; ctx.acc[tid * 2 + 1] = my_acc1;
@@ -1141,11 +1255,13 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   if (tid < 32) ctx.sc[tid] = 0;
   if (tid == 0) { ctx.sc[2] = gsc[SC_N_DANGER]; ctx.sc[3] = gsc[SC_NEXT_NPC_ID]; ctx.sc[17] = max(n_depl0, 0); }
   if (done_flag) {      // episode over: this launch resets the environment instead of stepping it
-    while (!mbar_try_wait(bar, 0)) {}      // the bulk copies must have landed before shared memory is reused
-    while (!mbar_try_wait(bar + 1, 0)) {}
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(NM_STEP_THREADS) : "memory");
+    if (!V::kGlobalTables) {
+      while (!mbar_try_wait(bar, 0)) {}      // the bulk copies must have landed before shared memory is reused
+      while (!mbar_try_wait(bar + 1, 0)) {}
+    }
+    HSYNC();
     if (tid == 0) { gsc[SC_EPISODE] += 1; atomicAdd(&prm.counters[2], 1ULL); }
-    reset_env(prm, env, nm_mix64(ctx.seed + 0x632BE59BD9B4E019ULL), false, false, (int *)smem);
+    reset_env<V>(prm, env, nm_mix64(ctx.seed + 0x632BE59BD9B4E019ULL), false, false, (int *)smem);
     return;
   }
   // Decode the player actions against the observation record they were chosen on (the ids are read
@@ -1155,8 +1271,8 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   if (tid < P) {
     const int p = tid;
     const int4 *x4 = (const int4 *)(prm.actions + ((size_t)env * P + p) * AC_N);
-    const int16_t *gent = prm.ent + (size_t)env * EA_N * R;
-    const int g_status = gent[EA_STATUS * R + p], g_health = gent[EA_HEALTH * R + p];   // same answer as ent_alive() later
+    const int16_t *gent = prm.ent + (size_t)env * (V::kGlobalTables ? (size_t)NM_BIG_ENT_STRIDE * R : (size_t)EA_N * R);
+    const int g_status = gent[V::ent_idx(EA_STATUS, p, R)], g_health = gent[V::ent_idx(EA_HEALTH, p, R)];   // same answer as ent_alive() later
     int4 xa = x4[0], xb = x4[1], xc = x4[2];
     if (!(g_status == ES_ALIVE && g_health > 0)) { xa = make_int4(-1, -1, -1, -1); xb = xa; xc = xa; }   // no id reads for the dead
     const uint8_t *rec = prm.obs + ((size_t)env * P + p) * prm.L.stride;
@@ -1186,8 +1302,10 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
 #pragma unroll
     for (int k = 0; k < A_N; k++) ctx.act[k * P + p] = v[k];
   }
-  while (!mbar_try_wait(bar, 0)) {}
-  while (!mbar_try_wait(bar + 1, 0)) {}
+  if (!V::kGlobalTables) {
+    while (!mbar_try_wait(bar, 0)) {}
+    while (!mbar_try_wait(bar + 1, 0)) {}
+  }
   HSYNC();
 
   PHASE();
@@ -1201,9 +1319,9 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     if (st == ES_ALIVE) {
       occ_set(ctx, ENT(EA_ROW, r), ENT(EA_COL, r));
       if (r >= P) {
-        unsigned h = (((unsigned)(-(int)ENT(EA_ID, r))) * 40503u >> 4) & 511u;
+        unsigned h = (((unsigned)(-(int)ENT(EA_ID, r))) * 40503u >> 4) & (unsigned)(V::kNpcHash - 1);
         #pragma unroll 1
-        while (atomicCAS(&ctx.npc_hash[h], (unsigned short)0, (unsigned short)(r + 1)) != 0) h = (h + 1) & 511u;
+        while (atomicCAS(&ctx.npc_hash[h], (unsigned short)0, (unsigned short)(r + 1)) != 0) h = (h + 1) & (unsigned)(V::kNpcHash - 1);
       }
     }
   }
@@ -1214,7 +1332,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       int p = base + lane;
       bool live = p < P && ENT(EA_STATUS, p) == ES_ALIVE;
       unsigned bm = __ballot_sync(0xffffffffu, live);
-      if (live) s_plist[n + __popc(bm & ((1u << lane) - 1))] = ((uint32_t)p << 16) | ((uint32_t)ENT(EA_ROW, p) << 8) | (uint32_t)ENT(EA_COL, p);
+      if (live) s_plist[n + __popc(bm & ((1u << lane) - 1))] = ((uint32_t)p << 20) | ((uint32_t)ENT(EA_ROW, p) << 10) | (uint32_t)ENT(EA_COL, p);
       n += __popc(bm);
     }
     if (lane == 0) ctx.sc[16] = n;
@@ -1248,13 +1366,13 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       auto ent_row1 = [&](int id) -> int {
         if (id > 0) return id <= P ? id : 0;
         if (id < 0) {
-          unsigned h = (((unsigned)(-id)) * 40503u >> 4) & 511u;
+          unsigned h = (((unsigned)(-id)) * 40503u >> 4) & (unsigned)(V::kNpcHash - 1);
           #pragma unroll 1
-          for (int probe = 0; probe < 512; probe++) {
+          for (int probe = 0; probe < V::kNpcHash; probe++) {
             int r1 = ctx.npc_hash[h];
             if (r1 == 0) return 0;
             if (ENT(EA_ID, r1 - 1) == id) return r1;
-            h = (h + 1) & 511u;
+            h = (h + 1) & (unsigned)(V::kNpcHash - 1);
           }
         }
         return 0;
@@ -1380,12 +1498,13 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   if (todo & 6) {
     bool mine = tid < P && ctx.act[A_BUY * P + tid] && ent_alive(ctx, tid);
     unsigned bm = __ballot_sync(0xffffffffu, mine);
-    if (lane == 0) ctx.sc[8 + warp] = __popc(bm);
+    int *const wcnt = V::kThreads > 256 ? (int *)s_scratch : &ctx.sc[8];      // per-warp buyer counts (the scratch is idle here)
+    if (lane == 0) wcnt[warp] = __popc(bm);
     bool give = tid < P && (ctx.act[A_GIVE_ITEM * P + tid] || ctx.act[A_GOLD_AMT * P + tid]);
     int any_give = half_or(give, half);
     int base = 0, nb = 0;
     #pragma unroll 1
-    for (int w2 = 0; w2 < (T >> 5); w2++) { int cw = ctx.sc[8 + w2]; if (w2 < warp) base += cw; nb += cw; }
+    for (int w2 = 0; w2 < (T >> 5); w2++) { int cw = wcnt[w2]; if (w2 < warp) base += cw; nb += cw; }
     if (mine) s_list[base + __popc(bm & ((1u << lane) - 1))] = tid;
     HSYNC();
     if (tid == 0 && (nb > 0 || any_give)) {
@@ -1426,13 +1545,13 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     // rows first: most ticks of a quiet environment have no attack at all and skip the ordered build.
     bool mine_any = false;
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < V::kRowsPerThread; k++) {
       const int r = tid + k * T;
       int tgt = 0;
       if (r < P) tgt = ctx.act[A_ATT_TARGET * P + r]; else if (r < R) tgt = ctx.npc_att[r - P];
       mine_any |= tgt != 0 && tgt - 1 != r && ent_alive(ctx, r);
     }
-    int *s_first2 = (int *)s_mv;                             // second registration array (the Move scratch is idle)
+    int *s_first2 = (int *)s_mv;                             // second registration array (the Move scratch is idle, >= R * 4 bytes)
     if (tid == 0) ctx.sc[6] = 0;
     if (half_or(mine_any, half)) {
       // ordered build by all warps: per-chunk counts, one barrier, each chunk writes at its prefix -- and registers
@@ -1453,11 +1572,16 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
         if (lane == 0) s_cnt[ch] = __popc(m);
       }
       HSYNC();
-      const int tag0 = 1023 << 20;
+      const int tag0 = ((1 << (31 - kIdxBits)) - 1) << kIdxBits;
       #pragma unroll 1
       for (int ch = warp; ch < n_chunks; ch += (T >> 5)) {
-        const int mine = lane < n_chunks ? s_cnt[lane] : 0;
-        const int before = __reduce_add_sync(0xffffffffu, lane < ch ? mine : 0);
+        int mine = 0, mine_before = 0;      // this lane's share of the per-chunk counts: chunks lane, lane + 32, ...
+#pragma unroll
+        for (int q = 0; q < V::kChunkIters; q++) {
+          const int cq = lane + 32 * q, v = cq < n_chunks ? s_cnt[cq] : 0;
+          mine += v; mine_before += cq < ch ? v : 0;
+        }
+        const int before = __reduce_add_sync(0xffffffffu, mine_before);
         const int r = ch * 32 + lane, tgt = pending_target(r);
         const unsigned m = __ballot_sync(0xffffffffu, tgt != 0);
         if (tgt) {
@@ -1478,17 +1602,17 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     // Rounds with one barrier each.  Registrations carry a round tag that shrinks from round to round, so a later
     // round's values undercut whatever earlier rounds left behind and nothing is ever cleared; and a round registers
     // its leftovers for the next round into the *other* of two registration arrays while its own is still being
-    // checked (na <= 512 < 2^20 attacks, fewer than 512 rounds).
+    // checked (na < 2^kIdxBits attacks, fewer than 2^(31 - kIdxBits) rounds).
     int round = 0;
     #pragma unroll 1
     while (pending) {
       PCOUNT(23, 1);
       int *cur = (round & 1) ? s_first2 : s_first, *nxt = (round & 1) ? s_first : s_first2;
       int *low_cur = &ctx.sc[(round & 1) ? 24 : 7], *low_nxt = &ctx.sc[(round & 1) ? 7 : 24];
-      const int tag = (1023 - round) << 20, tag_n = (1022 - round) << 20;
+      const int tag = ((1 << (31 - kIdxBits)) - 1 - round) << kIdxBits, tag_n = ((1 << (31 - kIdxBits)) - 2 - round) << kIdxBits;
       round++;
       long long ta2 = clock64();
-      const int lowest = *low_cur & 0xfffff;
+      const int lowest = *low_cur & ((1 << kIdxBits) - 1);
       int still = 0, my_low = 0x7fffffff;
       #pragma unroll 1
       for (int i = lane * (T >> 5) + warp; i < na; i += T) {
@@ -1539,45 +1663,49 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     //   d held by a non-mover     -> everybody fails.
     // The only non-local part is "iff o moves away": a chain of strictly decreasing rows that each
     // winner walks down.  No rounds, no atomics on the decision path.
-    const uint32_t NONE = 0xffffu, NODEP = 0xfffeu;
-    uint32_t *tbl = s_tbl;                                   // 1024-slot position index, zeroed at the start of the tick
-    uint16_t *mvd = s_mv, *res = s_mv + R;                   // intended destination, verdict / dependency
-    int mv_dir[2], mv_r[2], mv_c[2];                         // direction and destination (row, col)
+    constexpr int KR = V::kRowsPerThread;
+    constexpr unsigned TM = (unsigned)(V::kTblSlots - 1);
+    const uint32_t NONE = 0xffffu, NODEP = 0xfffeu;          // verdict codes (rows are < 0xfffe)
+    const tile_t NOTILE = (tile_t)~(tile_t)0;                // "does not move"
+    uint32_t *tbl = s_tbl;                                   // position index, zeroed at the start of the tick: (tile + 1) << 12 | row
+    tile_t *mvd = (tile_t *)s_mv;                            // intended destination
+    uint16_t *res = (uint16_t *)(s_mv + (size_t)R * sizeof(tile_t));      // verdict / dependency
+    int mv_dir[KR], mv_r[KR], mv_c[KR];                      // direction and destination (row, col)
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < KR; k++) {
       int r = tid + k * T;
       mv_dir[k] = -1; mv_r[k] = 0; mv_c[k] = 0;
       if (r < R) {
-        uint32_t d = NONE;
+        tile_t d = NOTILE;
         if (ent_alive(ctx, r)) {
           int dir = r < P ? (int)ctx.act[A_MOVE * P + r] : (int)ctx.npc_move[r - P];
           if (dir >= 0 && dir <= 3 && ENT(EA_FREEZE, r) == 0) {
             int nr = ENT(EA_ROW, r) + c_dir_dr[dir], nc = ENT(EA_COL, r) + c_dir_dc[dir];
             int dst = nr * S + nc;
-            if (!nm_impassible(tile_i(ctx, dst))) { d = (uint32_t)dst; mv_dir[k] = dir; mv_r[k] = nr; mv_c[k] = nc; }
+            if (!nm_impassible(tile_i(ctx, dst))) { d = (tile_t)dst; mv_dir[k] = dir; mv_r[k] = nr; mv_c[k] = nc; }
           }
         }
-        mvd[r] = (uint16_t)d;
+        mvd[r] = d;
         if (ENT(EA_STATUS, r) == ES_ALIVE) {                 // position index: same set as the occupancy bitmap
           uint32_t key = (uint32_t)(ENT(EA_ROW, r) * S + ENT(EA_COL, r));
-          uint32_t v = ((key + 1) << 16) | (uint32_t)r;
-          unsigned h = (key * 40503u >> 3) & 1023u;
-          while (atomicCAS(&tbl[h], 0u, v) != 0u) h = (h + 1) & 1023u;
+          uint32_t v = ((key + 1) << 12) | (uint32_t)r;
+          unsigned h = (key * 40503u >> 3) & TM;
+          while (atomicCAS(&tbl[h], 0u, v) != 0u) h = (h + 1) & TM;
         }
       }
     }
     HSYNC();
     auto who = [&](int tile) -> int {                        // row of the entity on an occupied tile
-      unsigned h = ((unsigned)tile * 40503u >> 3) & 1023u;
+      unsigned h = ((unsigned)tile * 40503u >> 3) & TM;
       for (;;) {
         uint32_t cur = tbl[h];
-        if ((cur >> 16) == (uint32_t)tile + 1) return (int)(cur & 0xffffu);
+        if ((cur >> 12) == (uint32_t)tile + 1) return (int)(cur & 0xfffu);
         if (cur == 0) return -1;
-        h = (h + 1) & 1023u;
+        h = (h + 1) & TM;
       }
     };
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < KR; k++) {
       const int i = tid + k * T;
       if (mv_dir[k] < 0) { if (i < R) res[i] = (uint16_t)NONE; continue; }
       const int dr_ = mv_r[k], dc_ = mv_c[k], d = dr_ * S + dc_;
@@ -1592,22 +1720,22 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       uint32_t verdict = NODEP;
       int lo = -1;                                           // claimants in (lo, i) beat me
       if (o >= 0) {
-        if (mvd[o] == NONE || o > i) verdict = NONE; else { verdict = (uint32_t)o; lo = o; }
+        if (mvd[o] == NOTILE || o > i) verdict = NONE; else { verdict = (uint32_t)o; lo = o; }
       }
       if (verdict != NONE) {
         #pragma unroll 1
         while (nb) {
           const int q = __ffs(nb) - 1; nb &= nb - 1;
           int e = who((dr_ - c_dir_dr[q]) * S + dc_ - c_dir_dc[q]);
-          if (e > lo && e < i && mvd[e] == d) { verdict = NONE; break; }
+          if (e > lo && e < i && mvd[e] == (tile_t)d) { verdict = NONE; break; }
         }
       }
       res[i] = (uint16_t)verdict;
     }
     HSYNC();
-    bool mv_ok[2];
+    bool mv_ok[KR];
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < KR; k++) {
       mv_ok[k] = false;
       if (mv_dir[k] < 0) continue;
       int j = tid + k * T;
@@ -1621,7 +1749,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     }
     HSYNC();
 #pragma unroll
-    for (int k = 0; k < 2; k++)
+    for (int k = 0; k < KR; k++)
       if (mv_ok[k]) {
         occ_set(ctx, mv_r[k], mv_c[k]);
         act_move(ctx, tid + k * T, mv_dir[k], false);
@@ -1651,7 +1779,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     // NPC cull: every warp classifies 32-row chunks (dead now / still alive / free afterwards) and publishes the
     // three counts; after one barrier each chunk knows how many dead and free rows precede it, which gives the
     // danger-stack slot of every dead NPC (stack order = row order) and the ascending list of free rows.
-    int *s_cnt = (int *)s_scratch + 600;                     // one packed count per chunk (<= 16 chunks)
+    int *s_cnt = (int *)s_scratch + 600;                     // one packed count per chunk (<= 32 * kChunkIters chunks)
     const int n_chunks = (N + 31) >> 5;
     auto classify = [&](int r, bool &dead, bool &stays, bool &fr) {
       const bool live = r < R && ENT(EA_STATUS, r) == ES_ALIVE;
@@ -1671,9 +1799,14 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     int16_t *danger = prm.danger + (size_t)env * N;
     #pragma unroll 1
     for (int ch = warp; ch < n_chunks; ch += (T >> 5)) {
-      const int mine = lane < n_chunks ? s_cnt[lane] : 0;
-      const int before = lane < ch ? mine : 0;
-      const int dead_before = __reduce_add_sync(0xffffffffu, before & 255), free_before = __reduce_add_sync(0xffffffffu, (before >> 16) & 255);
+      int dead_b = 0, free_b = 0, dead_all = 0, alive_all = 0;      // this lane's share: chunks lane, lane + 32, ...
+#pragma unroll
+      for (int q = 0; q < V::kChunkIters; q++) {
+        const int cq = lane + 32 * q, v = cq < n_chunks ? s_cnt[cq] : 0;
+        dead_all += v & 255; alive_all += (v >> 8) & 255;
+        if (cq < ch) { dead_b += v & 255; free_b += (v >> 16) & 255; }
+      }
+      const int dead_before = __reduce_add_sync(0xffffffffu, dead_b), free_before = __reduce_add_sync(0xffffffffu, free_b);
       const int r = P + ch * 32 + lane;
       bool dead, stays, fr;
       classify(r, dead, stays, fr);
@@ -1686,7 +1819,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
         occ_clr(ctx, ENT(EA_ROW, r), ENT(EA_COL, r));
       }
       if (ch == 0) {
-        const int tot_dead = __reduce_add_sync(0xffffffffu, mine & 255), tot_alive = __reduce_add_sync(0xffffffffu, (mine >> 8) & 255);
+        const int tot_dead = __reduce_add_sync(0xffffffffu, dead_all), tot_alive = __reduce_add_sync(0xffffffffu, alive_all);
         if (lane == 0) { ctx.sc[2] = min(N, nd0 + tot_dead); ctx.sc[4] = tot_alive; }
       }
     }
@@ -1726,8 +1859,8 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
   {
     // map.step: every depleted tile draws once.  Depleted tiles are first gathered into a
     // worklist (the draw is keyed by the tile, so order is free), then hashed by all threads
-    uint16_t *wl = (uint16_t *)s_scratch;
-    const int wl_cap = (int)(scratch_bytes / 2);
+    tile_t *wl = (tile_t *)s_scratch;
+    const int wl_cap = (int)(scratch_bytes / sizeof(tile_t));
     const int n_quads = S * S / 32;        // 16 bytes = 32 tiles per load
     auto respawn_tile = [&](int i, int m) {
       int thr_idx = m == MT_SCRUB ? NC_RESPAWN_FOILAGE : m == MT_SLAG ? NC_RESPAWN_ORE : m == MT_STUMP ? NC_RESPAWN_TREE
@@ -1736,7 +1869,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     };
     // The depleted tiles are known: the list carried over from last tick plus this tick's harvests (tile_dec).
     // Only when the list is unknown (first use after an overflow) is the map scanned to rebuild it.
-    const bool list_ok = !prm.no_depl_list && n_depl0 >= 0 && ctx.sc[17] <= NM_DEPL_CAP;
+    const bool list_ok = !prm.no_depl_list && n_depl0 >= 0 && ctx.sc[17] <= V::kDeplCap;
     // sc[19] (survivors) and sc[20] (scan hits) are still zero from the start of the tick: no set-up barrier
     if (!list_ok) {
     // depleted materials are 3, 6 and the even ones from 8 up: bit-sliced test of all 8 nibbles of a word
@@ -1771,7 +1904,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
             while (hit) {
               int b = __ffs(hit) - 1; hit &= hit - 1;
               int i = (q * 4 + j) * 8 + (b >> 2);
-              if (k < wl_cap) wl[k] = (uint16_t)i;
+              if (k < wl_cap) wl[k] = (tile_t)i;
               else respawn_tile(i, tile_i(ctx, i));          // worklist full: draw in place
               k++;
             }
@@ -1780,14 +1913,14 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     }
     HSYNC();
     }
-    const uint16_t *src = list_ok ? ctx.dlist : wl;
-    uint16_t *dst = list_ok ? wl : ctx.dlist;
-    const int n_src = list_ok ? ctx.sc[17] : min(ctx.sc[20], wl_cap), dst_cap = list_ok ? wl_cap : NM_DEPL_CAP;
+    const tile_t *src = list_ok ? ctx.dlist : wl;
+    tile_t *dst = list_ok ? wl : ctx.dlist;
+    const int n_src = list_ok ? ctx.sc[17] : min(ctx.sc[20], wl_cap), dst_cap = list_ok ? wl_cap : V::kDeplCap;
     // Fold the tick's events here (nothing emits after the spawn): the last threads fold while the first ones
     // walk the depleted tiles below, and the fold's global atomics -- one returns a value -- are in flight
     // underneath the walk.  The barriers that follow order them before the reward phase reads the counters.
     {
-      const int nev = min(ctx.sc[0], NM_EV_CAP);
+      const int nev = min(ctx.sc[0], V::kEvCap);
       PCOUNT(26, nev);
       #pragma unroll 1
       for (int i = T - 1 - tid; i < nev; i += T) fold_event(ctx, ctx.ev[i]);
@@ -1809,12 +1942,12 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       int base = 0;
       if (lane == 0 && sm) base = atomicAdd(&ctx.sc[19], __popc(sm));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (stays) { const int pos = base + __popc(sm & ((1u << lane) - 1)); if (pos < dst_cap) dst[pos] = (uint16_t)i; }
+      if (stays) { const int pos = base + __popc(sm & ((1u << lane) - 1)); if (pos < dst_cap) dst[pos] = (tile_t)i; }
     }
     HSYNC();
     if (tid == 0) {
       const bool scan_overflow = !list_ok && ctx.sc[20] > wl_cap;      // tiles beyond the worklist drew in place and are not listed
-      ctx.sc[21] = (ctx.sc[19] <= NM_DEPL_CAP && !scan_overflow) ? ctx.sc[19] : -1;
+      ctx.sc[21] = (ctx.sc[19] <= min(V::kDeplCap, dst_cap) && !scan_overflow) ? ctx.sc[19] : -1;
       ctx.sc[22] = list_ok ? 0 : 1;                                    // which buffer holds the new list: worklist scratch / dlist
     }
   }
@@ -1839,6 +1972,7 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
 
   PHASE();
   // ---- write the tables back while the wrapper part runs ------------------------------
+  if (!V::kGlobalTables) {
   fence_async_smem();
   HSYNC();
   if (tid == 0) {
@@ -1849,8 +1983,17 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
       for (int k = 0; k < IS_N; k++) bulk_s2g(gitem + (size_t)k * CAP, ctx.item + k * CAP, col_bytes);
     bulk_s2g(prm.map + (size_t)env * map_bytes, ctx.map, map_bytes);
     if (ctx.sc[21] > 0)
-      bulk_s2g(prm.depl + (size_t)env * NM_DEPL_CAP, ctx.sc[22] ? (const void *)ctx.dlist : (const void *)s_scratch, (uint32_t)((ctx.sc[21] * 2 + 15) & ~15));
+      bulk_s2g(gdepl, ctx.sc[22] ? (const void *)ctx.dlist : (const void *)s_scratch, (uint32_t)((ctx.sc[21] * (int)sizeof(tile_t) + 15) & ~15));
     bulk_commit();
+  }
+  } else {
+    // the tables are already where they live; only a list that ended up in the shared-memory worklist moves
+    if (ctx.sc[21] > 0 && !ctx.sc[22]) {
+      const tile_t *wl2 = (const tile_t *)s_scratch;
+      #pragma unroll 1
+      for (int i = tid; i < ctx.sc[21]; i += T) gdepl[i] = wl2[i];
+    }
+    HSYNC();      // the scratch is reused by the reward phase
   }
 
   PHASE();
@@ -2001,7 +2144,15 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) {
     prm.episode_done[env] = env_done ? 1 : 0;
     atomicAdd(&prm.counters[0], (unsigned long long)P);
     atomicAdd(&prm.counters[1], (unsigned long long)(n_alive + n_dead));
-    bulk_wait_all();
+    if (!V::kGlobalTables) bulk_wait_all();
   }
   PHASE();
 }
+#undef half_or
+#undef half_count
+
+extern "C" __global__ void __launch_bounds__(2 * VSmall::kThreads, 1)
+nmmo_step_kernel(const __grid_constant__ NmParams prm) { step_body<VSmall>(prm); }
+
+extern "C" __global__ void __launch_bounds__(VBig::kThreads, 1)
+nmmo_step_big_kernel(const __grid_constant__ NmParams prm) { step_body<VBig>(prm); }

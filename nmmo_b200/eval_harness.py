@@ -124,7 +124,7 @@ class EvalRunner:
             assert len(self.policies) == 1, "PvE mode requires only one policy"
         kw = eval_env_kwargs(mode, **self.env_over)
         pool = B200VecEnv(env_kwargs=kw, num_envs=self.num_envs, agent="neurips23_start_kit", device=self.device,
-                          task_rows=task_rows, collect_infos=True)
+                          task_rows=task_rows, collect_infos="async")
         kernel = create_kernel(pool.agents_per_env, len(self.policies), shuffle_with_seed=seed)
         policy_pool = PolicyPool(self.policies, kernel, self.num_envs, device=pool.sim.obs.device)
         pool.async_reset(seed)
@@ -145,6 +145,7 @@ class EvalRunner:
             with torch.no_grad():
                 actions, _, _ = policy_pool.forwards(o)
             pool.send(actions)
+        # (with collect_infos="async" the records of the last step are handed out by the next call's first recv())
         return infos
 
     def perform_eval(self, mode: str, seed: int, num_eval_episode: int, save_file_prefix: str, task_rows=None,

@@ -1,6 +1,7 @@
 """Device-resident rollout loop: the body of ``clean_pufferl.evaluate`` without host round trips.
 
-Mirrors /root/reference/reinforcement_learning/clean_pufferl.py:279-362 statement by statement:
+Mirrors /root/reference/reinforcement_learning/clean_pufferl.py:279-362 statement by statement
+(including the exit test at the top of the loop, :289, so every stored action is also sent):
 
     o, r, d, t, i, env_id, mask = data.pool.recv()                     :293
     agent_steps_collected += sum(mask); padded_steps_collected += len(mask)   :306-307
@@ -26,18 +27,22 @@ def evaluate(pool, policy, rollout, learner_mask=None, max_steps: int = 1 << 30)
     import torch
     rollout.reset()
     agent_steps = torch.zeros((), dtype=torch.int64, device=rollout.obs.device)
-    padded, step, infos = 0, 0, []
+    padded, step, n_recv, infos = 0, 0, 0, []
     cap = rollout.batch_size + 1
     while step < max_steps:
         step += 1
+        if rollout.ptr >= cap:        # the one host read per step (the reference's `ptr == batch_size + 1` test, :289)
+            break
         o, r, d, t, i, env_id, mask = pool.recv()
+        n_recv += 1
         infos.extend(i)
         agent_steps += mask.sum()
         padded += mask.numel()
         with torch.no_grad():
             actions, logprob, value = policy(o)
         rollout.store(o, value, actions, logprob, r, d.float(), mask, step, learner_mask=learner_mask)
-        if rollout.ptr >= cap:        # the one host read per step (the reference's `ptr == batch_size + 1` test, :282)
-            break
+        # the reference always sends the step's actions and only leaves at the top of the next iteration (:289, :357):
+        # the stored (action, logprob, value) of the last row are the ones the envs execute, and the next call's
+        # first recv() sees fresh outputs
         pool.send(actions)
-    return SimpleNamespace(agent_steps=int(agent_steps.item()), global_steps=padded, steps=step, infos=infos)
+    return SimpleNamespace(agent_steps=int(agent_steps.item()), global_steps=padded, steps=n_recv, infos=infos)

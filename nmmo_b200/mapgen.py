@@ -73,6 +73,11 @@ def generate_map(cfg: np.ndarray, seed: int, index: int) -> np.ndarray:
     m[inner] = FOILAGE
     m[l == ring] = GRASS
     m[l > ring] = VOID
+    kp = int(cfg[SPEC["NC_SPAWN_PATCH"]])
+    if kp > 0:      # clustered spawn (BASELINE.json configs[4]): the spawn patch and a one-tile rim around it are walkable
+        o = half - kp // 2
+        patch = m[o - 1:o + kp + 1, o - 1:o + kp + 1]
+        patch[np.isin(patch, (STONE, WATER, FISH, ORE, CRYSTAL))] = GRASS
     return m
 
 

@@ -105,7 +105,7 @@ def default_curriculum() -> List[List[int]]:
 
 
 def make_task_table(rows: Sequence[Sequence[int]], task_dim: int, seed: int = 0) -> Tuple[np.ndarray, np.ndarray]:
-    """-> (int32[T, 8] specs, uint16[T, task_dim] fp16 bit patterns of the embeddings)."""
+    """-> (int32[T, NM_TASK_COLS = 12] specs, uint16[T, task_dim] fp16 bit patterns of the embeddings)."""
     tab = np.asarray(rows, np.int32).reshape(-1, NCOL)
     rng = np.random.default_rng(seed)
     emb = (rng.standard_normal((tab.shape[0], task_dim)) * 0.5).astype(np.float16)

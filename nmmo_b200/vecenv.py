@@ -92,7 +92,12 @@ class B200VecEnv:
     def __init__(self, env_creator=None, env_args=None, env_kwargs: Optional[Dict] = None, num_envs: int = 1,
                  envs_per_worker: int = 1, envs_per_batch: Optional[int] = None, env_pool: bool = False,
                  mask_agents: bool = True, agent: str = "takeru", device: int = 0, env_base: int = 0,
-                 maps: Optional[np.ndarray] = None, task_rows=None, map_seed: int = 2023, collect_infos: bool = True):
+                 maps: Optional[np.ndarray] = None, task_rows=None, map_seed: int = 2023, collect_infos="async",
+                 task_embed: Optional[np.ndarray] = None, info_cap: int = 16384):
+        """collect_infos: "async" (default) -- finished-agent info records are compacted on the device, copied to
+        pinned host memory on a side stream and handed out by the NEXT recv() (no host sync in the loop; call
+        drain_infos() after the last step); True -- gathered synchronously inside recv() (exact tick, one host sync
+        per step); False -- never (use stats())."""
         # env_creator / env_args / envs_per_worker / env_pool are accepted for signature
         # compatibility; all envs of this backend step in lock-step on one GPU
         env_kwargs = env_kwargs or {}
@@ -103,10 +108,15 @@ class B200VecEnv:
         if isinstance(wrap_ns, dict):
             wrap_ns = Namespace(**wrap_ns)
         self.cfg, self.fcfg = make_config(env_ns, wrap_ns, agent)
-        n_maps = min(int(getattr(env_ns, "num_maps", 64)), 256) if maps is None else len(maps)
+        # num_maps is honoured as given (takeru 1280, yaofeng 1024: config.yaml:131,113); generation costs ~2 ms per map
+        n_maps = max(1, int(getattr(env_ns, "num_maps", 64))) if maps is None else len(maps)
         self.maps = generate_maps(self.cfg, map_seed, n_maps) if maps is None else maps
         rows = task_rows if task_rows is not None else default_curriculum()
         self.task_table, self.task_embed = make_task_table(rows, int(self.cfg[SPEC["NC_TASK_DIM"]]), seed=3)
+        if task_embed is not None:      # real embeddings (e.g. nmmo_b200.curriculum.load_heldout): fp16 bit patterns [T, task_dim]
+            te = np.ascontiguousarray(task_embed)
+            self.task_embed = te.view(np.uint16) if te.dtype == np.float16 else te.astype(np.uint16)
+            assert self.task_embed.shape == (self.task_table.shape[0], int(self.cfg[SPEC["NC_TASK_DIM"]]))
         self.num_envs = int(num_envs)
         self.envs_per_batch = self.num_envs if envs_per_batch is None else int(envs_per_batch)
         if self.envs_per_batch != self.num_envs:
@@ -127,11 +137,18 @@ class B200VecEnv:
         self.env_id = torch.arange(self.num_envs * self.agents_per_env, device=self.sim.obs.device)
         self._pending = False
         self.last_info_slots = []
+        self.env_base = int(env_base)
+        self._info_cap = int(min(info_cap, self.num_envs * self.agents_per_env))
+        self._info_q = None              # in-flight async gather: (event, n, idx, rows, done)
+        self._info_stream = None
 
     # ---- pufferlib pool contract -------------------------------------------------------
     def async_reset(self, seed: int = 0):
-        seeds = np.arange(self.num_envs, dtype=np.uint64) + np.uint64(int(seed) + self.sim_env_base())
-        self.sim.reset(seeds)
+        # seeds derive from the GLOBAL env index: two shards of a job reproduce the
+        # trajectories of one handle holding all the envs
+        from .dist import global_seeds
+        self.sim.reset(global_seeds(int(seed), self.env_base, self.num_envs))
+        self._info_q = None
         self._pending = True
 
     def reset_envs(self, env_indices, seeds, new_tasks=None):
@@ -148,28 +165,87 @@ class B200VecEnv:
         self._pending = True
 
     def sim_env_base(self) -> int:
-        return 0
+        return self.env_base
+
+    def _infos_from(self, idx, rows, done):
+        infos: List[Dict] = []
+        last = {}
+        for k, a in enumerate(idx):
+            last[int(a) // self.agents_per_env] = k
+        for k, a in enumerate(idx):
+            e = int(a) // self.agents_per_env
+            infos.append(info_record_to_dict(rows[k], episode_done=bool(done[e]) and last[e] == k, stat_prefix=self.stat_prefix))
+        return infos
+
+    def _enqueue_infos(self):
+        """Compact this tick's finished-agent records on the device (fixed capacity, no size read-back) and start their
+        copy to pinned host memory on a side stream."""
+        t, s = self._torch, self.sim
+        cap = self._info_cap
+        if self._info_stream is None:
+            self._info_stream = t.cuda.Stream(device=s.obs.device)
+            self._info_host = [(t.empty(1, dtype=t.int64).pin_memory(), t.empty(cap, dtype=t.int64).pin_memory(),
+                                t.empty((cap, s.info.shape[1]), dtype=t.float32).pin_memory(),
+                                t.empty(self.num_envs, dtype=t.uint8).pin_memory()) for _ in range(2)]
+            self._info_flip = 0
+        n_d = s.info_valid.sum(dtype=t.int64).reshape(1)
+        idx_d = t.nonzero_static(s.info_valid, size=cap, fill_value=0).flatten()
+        rows_d = s.info[idx_d]
+        done_d = s.episode_done.clone()
+        ev = t.cuda.Event()
+        cur = t.cuda.current_stream(s.obs.device)
+        self._info_stream.wait_stream(cur)
+        h = self._info_host[self._info_flip]; self._info_flip ^= 1
+        with t.cuda.stream(self._info_stream):
+            h[0].copy_(n_d, non_blocking=True); h[1].copy_(idx_d, non_blocking=True)
+            h[2].copy_(rows_d, non_blocking=True); h[3].copy_(done_d, non_blocking=True)
+            for x in (n_d, idx_d, rows_d, done_d):
+                x.record_stream(self._info_stream)
+            ev.record(self._info_stream)
+        self._info_q = (ev, h, s.info_valid.clone())
+
+    def drain_infos(self):
+        """Infos of the in-flight asynchronous gather (the last step's), if any."""
+        q, self._info_q = self._info_q, None
+        self.last_info_slots = []
+        if q is None:
+            return []
+        ev, h, valid_d = q
+        ev.synchronize()           # recorded a whole tick ago on a side stream: normally already complete
+        n = int(h[0][0])
+        if n > self._info_cap:
+            # more agents finished in one tick than the staging holds (every env truncating at the horizon together):
+            # gather them synchronously.  Their records are still intact: a slot cannot finish again in the tick
+            # that resets its env.
+            idx_d = valid_d.nonzero().flatten()
+            idx, rows = idx_d.cpu().numpy(), self.sim.info[idx_d].cpu().numpy()
+        else:
+            idx, rows = h[1][:n].numpy().copy(), h[2][:n].numpy()
+        self.last_info_slots = idx
+        return self._infos_from(idx, rows, h[3].numpy())
 
     def recv(self):
         """-> (obs uint8 [B, obs_sz], reward f32 [B], terminated u8 [B], truncated u8 [B], infos,
-        env_id [B], mask u8 [B]) -- all CUDA tensors except `infos` (list of dicts)."""
+        env_id [B], mask u8 [B]) -- all CUDA tensors except `infos` (list of dicts).
+
+        The returned tensors are views of the handle's own buffers, and the NEXT step decodes the actions' target
+        indices by reading entity / item ids back from this very observation buffer (csrc/nmmo_step.cu, action decode):
+        treat `obs` as read-only.  A consumer that edits observations in place must work on a copy
+        (`recv_copy=True` at construction is not offered on purpose: 13 GB per tick)."""
         s = self.sim
+        if not self._pending:
+            raise RuntimeError("recv() without a preceding async_reset()/send(): the outputs on the device were already handed out")
         infos: List[Dict] = []
         self.last_info_slots = []        # flat agent slot (env * agents_per_env + agent) of each entry of `infos`
-        if self.collect_infos:
+        if self.collect_infos == "async":
+            infos = self.drain_infos()   # the previous step's records (their copy ran underneath that step)
+            self._enqueue_infos()
+        elif self.collect_infos:
             valid = s.info_valid.nonzero().flatten()
             if valid.numel():
-                rows = s.info[valid].cpu().numpy()
-                done = s.episode_done.cpu().numpy()
                 idx = valid.cpu().numpy()
                 self.last_info_slots = idx
-                last = {}
-                for k, a in enumerate(idx):
-                    last[a // self.agents_per_env] = k
-                for k, a in enumerate(idx):
-                    e = int(a) // self.agents_per_env
-                    infos.append(info_record_to_dict(rows[k], episode_done=bool(done[e]) and last[e] == k,
-                                                     stat_prefix=self.stat_prefix))
+                infos = self._infos_from(idx, s.info[valid].cpu().numpy(), s.episode_done.cpu().numpy())
         self._pending = False
         return s.obs, s.rewards, s.terminated, s.truncated, infos, self.env_id, s.mask
 

@@ -164,4 +164,18 @@ def test_device_evaluate_loop():
         a, b = path.split(".")
         m = x["ActionTargets"][a][b]
         assert bool((m[torch.arange(701, device="cuda"), roll.actions[:701, k].long()] == 1).all()), path
+    # a second call continues where the first stopped: every recv() of a call is followed by a send() of the actions
+    # that were stored for it (clean_pufferl.py:289,357), so its first recv() is a new tick, and recv() refuses to
+    # hand the same outputs out twice
+    calls = []
+    recv0, send0 = pool.recv, pool.send
+    pool.recv = lambda: (calls.append("r"), recv0())[1]
+    pool.send = lambda a: (calls.append("s"), send0(a))[1]
+    res2 = evaluate(pool, policy, roll)
+    pool.recv, pool.send = recv0, send0
+    assert roll.ptr == 701 and res2.steps >= 1
+    assert "".join(calls) == "rs" * res2.steps
+    pool.recv()
+    with pytest.raises(RuntimeError):
+        pool.recv()
     pool.close(); roll.close()

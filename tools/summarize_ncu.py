@@ -5,7 +5,7 @@ from pathlib import Path
 
 tag = sys.argv[1]
 G = Path("gpurun_out"); P = Path("profiles"); P.mkdir(exist_ok=True)
-METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+METRICS = ["gpu__time_duration.sum", "gcc__cache_requests_type_instruction.sum", "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__registers_per_thread",
            "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem", "launch__grid_size", "launch__block_size"]
@@ -30,7 +30,7 @@ def to_bytes(v, unit):
     return float(v) * f
 
 
-lines = [f"# ncu evidence, {tag}", "", "Command: `python bench.py --steps 48 --warmup 3 --no-cpu` (4096 envs x 128 agents, 1 x B200),",
+lines = [f"# ncu evidence, {tag}", "", f"Command: `{sys.argv[2] if len(sys.argv) > 2 else 'python bench.py --gpus 1 --steps 20 --warmup 5'}` (4096 envs x 128 agents, 1 x B200),",
          "`--clock-control none`.  Per-launch times under ncu are cold-cache and serialised: compare shares.", ""]
 # launch list
 rows = [r for r in csv.reader(open(G / f"launches_{tag}.csv")) if len(r) > 5]
@@ -44,7 +44,9 @@ lines += ["## Launch list (gpu__time_duration.sum, first 140 launches)", "", "| 
 for k, v in d.items():
     lines.append(f"| {k[:48]} | {len(v)} | {sum(v)/len(v):.1f} | {100*sum(v)/tot if k.startswith('nmmo') else 0:.1f} % |")
 summary = {}
-for name, title in ((f"prof_{tag}_tick40", "Full capture at tick ~40 (incremental observation writer)"),
+for name, title in ((f"prof_{tag}_alive", "Full capture at tick 12 of the driver's window (ticks 5-25: every agent alive, incremental observation writer)"),
+                    (f"prof_{tag}_tick40", "Full capture at tick ~40 (incremental observation writer)"),
+                    (f"prof_{tag}_c5", "Full capture, config 5 (1024 agents per env), tick 12"),
                     (f"prof_{tag}_dense", "Full capture, dense observation writer (obs_full=1)")):
     rep = G / f"{name}.ncu-rep"
     if not rep.exists():
