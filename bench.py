@@ -41,11 +41,45 @@ METRIC = "agent_steps_per_sec"
 UNIT = "agent-slot-steps/s"
 
 
-def world(agent="takeru", n_maps=64):
-    cfg, fcfg = make_config(agent=agent)
-    maps = generate_maps(cfg, 2023, n_maps)
+NOMINAL_HBM_GBS = 8000.0      # BASELINE.json north_star: "~8 TB/s peak"; reported beside the measured copy peak
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    "config2": dict(envs=4096, engine={}, env={},
+                    what="configs[1]: {E} lockstep envs x {P} agents per GPU, NeurIPS23 config + takeru overrides, "
+                         "synthetic seeded maps, uniform-random valid actions, from reset with auto-reset"),
+    # BASELINE.json configs[4]: 1024 agents per env, NPC_N x8, map centre 512, every agent
+    # spawned inside a 32x32 patch, Move chosen with p = 0.9 (collision-heavy); the big kernel family
+    "config5": dict(envs=512, engine=dict(NC_SPAWN_PATCH=32, NC_SAMPLE_MOVE_PCT=90),
+                    env=dict(num_agents=1024, num_npcs=2048, map_size=512),
+                    what="configs[4] stress: {E} lockstep envs x {P} agents per GPU (NPC_N 2048, 544^2 map), clustered "
+                         "spawn in a 32x32 patch, Move-biased uniform-random valid actions (p = 0.9), from reset"),
+}
+
+
+def world(agent="takeru", n_maps=None, workload="config2"):
+    from nmmo_b200.config import default_env_args, default_wrapper_args
+    wl = WORKLOADS[workload]
+    env_args = default_env_args(resilient_population=0 if agent in ("takeru", "yaofeng", "hybrid") else 0.2, **wl["env"])
+    cfg, fcfg = make_config(env_args, default_wrapper_args(agent), agent, **wl["engine"])
+    maps = generate_maps(cfg, 2023, n_maps or (64 if workload == "config2" else 8))
     tab, emb = make_task_table(default_curriculum(), int(cfg[SPEC["NC_TASK_DIM"]]), seed=3)
     return cfg, fcfg, maps, tab, emb
+
+
+def committed_traffic(regime_keys):
+    """DRAM traffic per launch of the two kernels from the newest committed `ncu --set full` capture whose regime
+    matches the timed window (profiles/<tag>_traffic.json, written by tools/summarize_ncu.py).  -> (dict, source)"""
+    for tf in sorted((ROOT / "profiles").glob("*_traffic.json"), reverse=True):
+        try:
+            tj = json.loads(tf.read_text())
+        except Exception:  # noqa: BLE001
+            continue
+        for key in regime_keys:
+            found = {k.split(":", 1)[1]: v.get("dram_bytes") for k, v in tj.items() if k.startswith(key + ":")}
+            if found:
+                return found, f"profiles/{tf.name} capture '{key}' (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+    return {}, None
 
 
 def alg_bytes_per_slot(cfg):
@@ -58,7 +92,8 @@ def alg_bytes_per_slot(cfg):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    """SM clock + throttle reasons sampled DURING the timed region.  NVML is polled in a thread that is already
+    running when the region starts (a 33 ms window still gets samples); `nvidia-smi -lms` is the fallback."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -99,6 +134,84 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class NvmlSampler(ClockSampler):
+    def __init__(self, index: int):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+        except Exception:  # noqa: BLE001
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        self.samples = []          # (host time, sm MHz, reasons bitmask, power W)
+        self.t0 = self.t1 = None
+        self._run = True
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()       # polling starts now, before the warm-up
+
+    def _poll(self):
+        nv = self.nv
+        while self._run:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((time.perf_counter(), sm, rs, pw))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        self.t0 = time.perf_counter()
+
+    def stop(self):
+        self.t1 = time.perf_counter()
+        time.sleep(0.005)
+        self._run = False
+        nv = self.nv
+        inside = [x for x in self.samples if self.t0 <= x[0] <= self.t1]
+        if not inside and self.samples:      # window shorter than one poll: the nearest sample
+            inside = [min(self.samples, key=lambda x: abs(x[0] - 0.5 * (self.t0 + self.t1)))]
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(n for n, bit in names.items() if any(x[2] & bit for x in inside))
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            mx = None
+        sm = [x[1] for x in inside]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm),
+                "power_w_max": max((x[3] for x in inside), default=None), "source": "NVML polled every ~2 ms, samples inside the timed region"}
+
+
+def make_clock_sampler(index: int):
+    try:
+        return NvmlSampler(index)
+    except Exception:  # noqa: BLE001
+        return ClockSampler(index)
+
+
+def ref_envs_default(requested: int, P: int, stride: int) -> int:
+    """Envs of the CPU arm: the GPU arm's count when the host has the memory for that many oracle envs
+    (each holds its own observation records), else as many as fit in a quarter of the free RAM."""
+    try:
+        import psutil
+        free = psutil.virtual_memory().available
+    except Exception:  # noqa: BLE001
+        free = 16 << 30
+    per_env = P * (stride + 4096) + (4 << 20)
+    return int(max(16, min(requested, (free // 4) // per_env)))
+
+
 def cpu_leg(w, n_envs, ticks, warmup=4, seed=1):
     """The CPU restatement (oracle/, OpenMP over envs) on the host cores."""
     from oracle.oracle import OracleBatch
@@ -125,17 +238,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w = world(args.agent)
+    w = world(args.agent, workload=args.workload)
     cores = len(os.sched_getaffinity(0))
-    n_envs = args.ref_envs or 4 * cores
     P = int(w[0][SPEC["NC_N_PLAYERS"]])
+    gpu_envs = args.envs or WORKLOADS[args.workload]["envs"]
+    n_envs = args.ref_envs or ref_envs_default(gpu_envs, P, ObsLayout(w[0]).stride)
     res = cpu_leg(w, n_envs, args.steps, warmup=args.warmup)
     ms = res["seconds"] / args.steps * 1e3
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16", "data": "synthetic",
-            "config": {"workload": f"configs[1] sampled: {n_envs} envs x {P} agents, takeru config, uniform-random valid actions",
-                       "envs": n_envs, "agents_per_env": P},
+            "config": {"workload": WORKLOADS[args.workload]["what"].format(E=n_envs, P=P) + " -- CPU arm: oracle/nmmo_oracle.c (kind: port; the nmmo engine "
+                                   "is not installable here), all host cores, one env per OpenMP task",
+                       "envs": n_envs, "agents_per_env": P, "same_envs_as_gpu_arm": n_envs == gpu_envs},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "alive_agent_steps_per_s": res["alive_agent_steps_per_s"],
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -168,9 +283,10 @@ def run_native(args):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    w = world(args.agent)
+    w = world(args.agent, workload=args.workload)
     cfg = w[0]
-    E, P = args.envs, int(cfg[SPEC["NC_N_PLAYERS"]])
+    E, P = args.envs or WORKLOADS[args.workload]["envs"], int(cfg[SPEC["NC_N_PLAYERS"]])
+    clocks = make_clock_sampler(local_rank)      # NVML polling runs from here on, through the warm-up
     sim = Simulator(*w[:2], E, *w[2:], device=local_rank, env_base=rank * E)
     seeds = np.arange(E, dtype=np.uint64) + np.uint64(rank * E + args.seed)
     stream = torch.cuda.current_stream()
@@ -194,7 +310,6 @@ def run_native(args):
         tick(args.seed)
     sim.stats(clear=True)
     # ---- device-resident timed region ---------------------------------------------------
-    clocks = ClockSampler(local_rank)
     sim.timing(True)
     barrier()
     clocks.start()
@@ -318,34 +433,34 @@ def run_native(args):
         obs_bytes_launch = float(g_counters[4]) / max(1, world_size * args.steps)
         # DRAM traffic of the same kernels from the committed ncu --set full captures (profiles/<tag>_traffic.json,
         # written by tools/summarize_ncu.py from the .ncu-rep of tools/ncu_round.sh); null when none is committed
-        traffic, traffic_dense, traffic_src = None, None, None
-        try:
-            tf = sorted((ROOT / "profiles").glob("*_traffic.json"))[-1]
-            tj = json.loads(tf.read_text())
-            traffic = tj.get("tick40:nmmo_obs_kernel", {}).get("dram_bytes")
-            traffic_dense = tj.get("dense:nmmo_obs_kernel", {}).get("dram_bytes")
-            traffic_src = f"profiles/{tf.name} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum; incremental capture taken at tick ~40)"
-        except Exception:  # noqa: BLE001
-            pass
+        alive_frac = float(g_counters[1]) / max(1.0, float(g_counters[0]))
+        big = args.workload == "config5"
+        k_step, k_obs = ("nmmo_step_big_kernel", "nmmo_obs_big_kernel") if big else ("nmmo_step_kernel", "nmmo_obs_kernel")
+        # captures are labelled by regime: "alive" = tick 12 of the driver's window (every agent alive), "tick40" = the
+        # mostly-dead regime of long random-action runs, "c5" = config 5; only a capture of the window's regime is quoted
+        regime = ["c5"] if big else (["alive"] if alive_frac > 0.8 else ["tick40"])
+        tr, traffic_src = committed_traffic(regime)
+        traffic = tr.get(k_obs)
+        traffic_dense = committed_traffic(["dense"])[0].get("nmmo_obs_kernel") if not big else None
         obs_gbs = obs_bytes_launch / (obs_ms * 1e-3) / 1e9
         dense_gbs = n * b_obs / (obs_ms_dense * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16", "data": "synthetic",
-            "config": {"workload": f"configs[1]: {E} lockstep envs x {P} agents per GPU, NeurIPS23 config + takeru overrides, "
-                                   "synthetic seeded maps, uniform-random valid actions, from reset with auto-reset",
+            "config": {"workload": WORKLOADS[args.workload]["what"].format(E=E, P=P),
                        "envs_per_gpu": E, "agents_per_env": P, "npcs_per_env": int(cfg[SPEC["NC_N_NPCS"]]),
                        "obs_record_bytes": int(sim.stride), "sharding": f"env-index x{world_size}",
-                       "l2": "working set per tick (13 GB of obs records, 0.36 GB of env state) exceeds the 126 MB L2"},
+                       "l2": "inputs larger than L2: the working set per tick (13 GB of obs records, 0.2-0.4 GB of env state) exceeds the 126 MB L2"},
             "alive_agent_steps_per_s": float(g_counters[1]) / (ms_total * 1e-3),
-            "alive_fraction": float(g_counters[1]) / max(1.0, float(g_counters[0])),
+            "alive_fraction": alive_frac,
             "kernels_ms": {"step_kernel": step_ms, "obs_kernel": obs_ms, "launches_timed": n_timed},
-            "roofline": None, "roofline_obs_kernel": {"bound": "hbm", "kernel": "nmmo_obs_kernel", "achieved": obs_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": obs_gbs / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+            "roofline": None, "roofline_obs_kernel": {"bound": "hbm", "kernel": k_obs, "achieved": obs_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": obs_gbs / peak, "peak_nominal": NOMINAL_HBM_GBS, "frac_nominal": obs_gbs / NOMINAL_HBM_GBS,
+                         "traffic": traffic, "traffic_source": traffic_src, "traffic_regime": regime[0], "peak_source": peak_src,
                          "alg_bytes_per_launch": obs_bytes_launch,
                          "note": "incremental writer: algorithmic bytes = env state read + record bytes that changed (counted in-kernel)",
-                         "dense_mode": {"achieved": dense_gbs, "frac": dense_gbs / peak, "ms": obs_ms_dense,
+                         "dense_mode": {"achieved": dense_gbs, "frac": dense_gbs / peak, "frac_nominal": dense_gbs / NOMINAL_HBM_GBS, "ms": obs_ms_dense,
                                         "alg_bytes_per_launch": n * b_obs, "traffic": traffic_dense,
                                         "what": "same kernel with obs_full=1: all 25 KB of all records rewritten every tick"},
                          "dense_equivalent_gbs": n * b_obs / (obs_ms * 1e-3) / 1e9},
@@ -366,13 +481,10 @@ def run_native(args):
         R_ = P + int(cfg[SPEC["NC_N_NPCS"]]); S_ = int(cfg[SPEC["NC_MAP_SIZE"]])
         step_alg = E * (2 * (SPEC["EA_N"] * R_ * 2 + S_ * S_ // 2) + P * 12 * 4 + P * 7)
         step_gbs = step_alg / (step_ms * 1e-3) / 1e9
-        traffic_step = None
-        try:
-            traffic_step = tj.get("tick40:nmmo_step_kernel", {}).get("dram_bytes")
-        except Exception:  # noqa: BLE001
-            pass
-        line["roofline_step_kernel"] = {"bound": "hbm", "kernel": "nmmo_step_kernel", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
-                                        "frac": step_gbs / peak, "traffic": traffic_step, "traffic_source": traffic_src,
+        traffic_step = tr.get(k_step)
+        line["roofline_step_kernel"] = {"bound": "hbm", "kernel": k_step, "achieved": step_gbs, "peak": peak, "unit": "GB/s",
+                                        "frac": step_gbs / peak, "peak_nominal": NOMINAL_HBM_GBS, "frac_nominal": step_gbs / NOMINAL_HBM_GBS,
+                                        "traffic": traffic_step, "traffic_source": traffic_src, "traffic_regime": regime[0],
                                         "peak_source": peak_src, "alg_bytes_per_launch": step_alg,
                                         "note": "per-env critical path bound by instruction fetch and barrier latency "
                                                 "(DESIGN.md 4.1: 2.0 M instruction-line requests per launch), not by bandwidth"}
@@ -380,7 +492,8 @@ def run_native(args):
         line["roofline"] = dict(line[dominant], dominant_by="mean launch duration in the timed region")
         if world_size == 1 and not args.no_cpu:
             cores = len(os.sched_getaffinity(0))
-            res = cpu_leg(w, n_envs=args.ref_envs or 4 * cores, ticks=min(args.steps, 256), warmup=min(args.warmup, 8))
+            ce = args.ref_envs or (min(1024, ref_envs_default(E, P, sim.stride)) if not big else 32)
+            res = cpu_leg(w, n_envs=ce, ticks=min(args.steps, 64), warmup=min(args.warmup, 8))
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         else:
             line["cpu_baseline"] = None
@@ -396,7 +509,7 @@ def run_rollout(args):
     import torch
     from nmmo_b200.rollout import DeviceRollout
     from argparse import Namespace
-    a = Namespace(batch=args.rollout_batch, envs=args.envs, agents=128, stride=25344, alive=0.5, reps=10, cpu_batch=32768)
+    a = Namespace(batch=args.rollout_batch, envs=args.envs or 4096, agents=128, stride=25344, alive=0.5, reps=10, cpu_batch=32768)
     n = a.envs * a.agents
     dev = torch.device("cuda")
     g = torch.Generator(device=dev); g.manual_seed(1)
@@ -466,7 +579,8 @@ def main():
     ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--envs", type=int, default=0, help="environments per GPU (default: 4096 for config2, 512 for config5)")
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS), help="BASELINE.json configs[1] (default) or configs[4] (1024 agents per env)")
     ap.add_argument("--agent", default="takeru")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--ref-envs", type=int, default=0, help="envs of the CPU sample (default 4 x cores)")
