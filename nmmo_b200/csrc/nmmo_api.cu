@@ -55,6 +55,11 @@ static size_t step_big_smem_bytes(const NmParams &p) {
   s += a16((size_t)VBig::kTblSlots * 4); s += a16(p.P); s += a16((size_t)p.P * 4); s += a16(32 * 4); s += 16;
   return s + 128;
 }
+// observation kernels: cell index (per-cell list ends, rows grouped by cell) and the per-warp row bitmaps
+static size_t obs_cell_bytes(const NmParams &p, int NW) {
+  const int ncx = (p.S + NM_OBS_CELL - 1) / NM_OBS_CELL, R32 = (p.R + 31) & ~31;
+  return a16((size_t)(ncx * ncx + 1) * 4) + a16((size_t)R32 * 2) + a16((size_t)NW * (R32 / 32) * 4);
+}
 static size_t step_big_ws_bytes(const NmParams &p) {
   return a16((size_t)12 * p.P * 2) + a16((size_t)VBig::kEvCap * 8) + a16((size_t)p.P * 16) + a16((size_t)p.P * 8) + 128;
 }
@@ -66,16 +71,17 @@ static size_t obs_big_smem_bytes(const NmParams &p) {
   s += a16((size_t)AP * NINV * 2); s += a16((size_t)AP * 4); s += a16(64 * 4);
   s += a16((size_t)NW * a16(p.L.m_end)); s += a16((size_t)NW * a16((size_t)p.L.n_ent * 2)); s += 16;
   s += a16((size_t)NW * 72 * 4); s += a16((2 * AC_N + 2) * 4); s += a16((size_t)AP * 4); s += a16((size_t)AP * 2); s += a16((size_t)((p.R + 31) & ~31) * 4); s += a16(a16(p.L.m_end));
+  s += obs_cell_bytes(p, NW) + 64 * 4;
   return s + 128;
 }
 
-static size_t step_smem_bytes(const NmParams &p) {
+static size_t step_smem_bytes(const NmParams &p, bool items_in_place = false) {
   size_t s = 0;
   int NINV = p.cfg[NC_N_INV];
-  s += a16((size_t)EA_N * p.R * 2); s += a16((size_t)IS_N * p.CAP * 2); s += a16((size_t)p.S * p.S / 2);
+  s += a16((size_t)EA_N * p.R * 2); s += items_in_place ? 0 : a16((size_t)IS_N * p.CAP * 2); s += a16((size_t)p.S * p.S / 2);
   s += a16((size_t)((p.S * p.S + 31) / 32) * 4); s += 2 * a16((size_t)((p.CAP + 31) / 32) * 4);
   s += a16((size_t)p.P * NINV * 2); s += a16(p.P); s += a16((size_t)12 * p.P * 2);
-  s += a16(p.N); s += a16((size_t)p.N * 2); s += a16(NM_EV_CAP * 8); s += a16((size_t)p.P * 4) * 2; s += a16(64); s += 16;
+  s += a16(p.N); s += a16((size_t)p.N * 2); s += items_in_place ? 0 : a16(NM_EV_CAP * 8); s += a16((size_t)p.P * 4) * 2; s += a16(64); s += 16;
   s += a16(1024); s += a16((size_t)p.P * 16); s += a16((size_t)p.P * 8); s += a16(std::max<size_t>(4096, (size_t)p.R * 8) + 128); s += a16((size_t)p.R * 4); s += a16(NM_DEPL_CAP * 2); s += 4096; s += a16(p.P); s += a16((size_t)p.P * 4) + 64;
   return s + 128;
 }
@@ -88,6 +94,7 @@ static size_t obs_smem_bytes(const NmParams &p) {
   s += a16((size_t)p.P * NINV * 2); s += a16((size_t)p.P * 4); s += a16(64 * 4);
   s += a16((size_t)NW * a16(p.L.m_end)); s += a16((size_t)NW * a16((size_t)p.L.n_ent * 2)); s += 16;
   s += a16((size_t)NW * 72 * 4); s += a16((2 * AC_N + 2) * 4); s += a16((size_t)p.P * 4); s += a16((size_t)p.P * 2); s += a16((size_t)((p.R + 31) & ~31) * 4); s += a16(a16(p.L.m_end));
+  s += obs_cell_bytes(p, NW) + 64 * 4;
   return s + 128;
 }
 
@@ -129,7 +136,7 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   nm_obs_layout_init(p.cfg, &p.L);
   p.E = n_envs; p.P = cfg[NC_N_PLAYERS]; p.N = cfg[NC_N_NPCS]; p.R = p.P + p.N; p.S = cfg[NC_MAP_SIZE]; p.CAP = cfg[NC_ITEM_CAP];
   p.n_maps = n_maps; p.n_tasks = n_tasks; p.env_base = env_base;
-  p.ICAP = std::min(p.CAP, 512);      // item rows the observation kernel keeps in shared memory; rows beyond are read in HBM
+  p.ICAP = std::min(p.CAP, 384);      // item rows the observation kernel keeps in shared memory; rows beyond are read in HBM
   if (const char *ov = getenv("NMMO_B200_ICAP")) {      // test hook: force the HBM tail path with a tiny staged prefix
     int v = atoi(ov);
     if (v >= 8 && v % 8 == 0) p.ICAP = std::min(p.CAP, v);
@@ -158,16 +165,27 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   // the small step kernel runs two environments per CTA (they walk the code together) when both fit
   p.half_smem = (int)((h->step_smem + 127) & ~(size_t)127);
   p.envs_per_cta = (!p.big && 2 * p.half_smem <= max_smem) ? 2 : 1;
+  // three environments per CTA (item table and event ring in place in HBM / L2) when they fit
+  int want3 = 1;
+  if (const char *ov = getenv("NMMO_B200_ENVS_PER_CTA")) want3 = atoi(ov) == 3;      // test hook: 1 / 2 / 3
+  if (!p.big && want3) {
+    const size_t s3 = (step_smem_bytes(p, true) + 127) & ~(size_t)127;
+    if (3 * s3 <= (size_t)max_smem) { p.envs_per_cta = 3; p.half_smem = (int)s3; h->step_smem = s3; }
+  }
   if (getenv("NMMO_B200_NO_DEPL_LIST")) p.no_depl_list = 1;      // test hook
-  if (const char *ov = getenv("NMMO_B200_ENVS_PER_CTA")) { if (atoi(ov) == 1) p.envs_per_cta = 1; }      // test hook
+  if (const char *ov = getenv("NMMO_B200_ENVS_PER_CTA")) {      // test hook
+    if (!p.big && atoi(ov) == 1) { p.envs_per_cta = 1; p.half_smem = (int)((step_smem_bytes(p) + 127) & ~(size_t)127); h->step_smem = p.half_smem; }
+  }
   {   // the opt-in limit is a property of the kernel, not of the handle: several handles of different shapes may
       // be alive in one process, so it only ever grows (per device)
-    static int step_attr[2][64] = {{0}}, obs_attr[2][64] = {{0}};
+    static int step_attr[3][64] = {{0}}, obs_attr[2][64] = {{0}};
     const int need_step = p.envs_per_cta * p.half_smem, need_obs = (int)h->obs_smem, d = device & 63, b = p.big;
-    if (need_step > step_attr[b][d]) {
-      if (b) CU(cudaFuncSetAttribute(nmmo_step_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_step));
+    const int sk = b ? 1 : (p.envs_per_cta == 3 ? 2 : 0);
+    if (need_step > step_attr[sk][d]) {
+      if (sk == 1) CU(cudaFuncSetAttribute(nmmo_step_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_step));
+      else if (sk == 2) CU(cudaFuncSetAttribute(nmmo_step3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_step));
       else CU(cudaFuncSetAttribute(nmmo_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_step));
-      step_attr[b][d] = need_step;
+      step_attr[sk][d] = need_step;
     }
     if (need_obs > obs_attr[b][d]) {
       if (b) CU(cudaFuncSetAttribute(nmmo_obs_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_obs));
@@ -179,6 +197,7 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   const size_t ent_i16 = p.big ? (size_t)NM_BIG_ENT_STRIDE * p.R : (size_t)EA_N * p.R;      // int16 per env
   DA(p.ent, E * ent_i16); DA(p.item, E * IS_N * p.CAP); DA(p.map, E * p.S * p.S / 2);
   if (p.big) { p.ws_bytes = step_big_ws_bytes(p); DA(p.ws, E * p.ws_bytes); }
+  else if (p.envs_per_cta == 3) { p.ws_bytes = a16((size_t)NM_EV_CAP * 8); DA(p.ws, E * p.ws_bytes); }
   uint8_t *dmaps; DA(dmaps, (size_t)n_maps * p.S * p.S); p.maps = dmaps;
   CU(cudaMemcpy(dmaps, maps, (size_t)n_maps * p.S * p.S, cudaMemcpyHostToDevice));
   DA(p.scalars, E * NM_SC_N); DA(p.seed, E); DA(p.danger, E * p.N);
@@ -235,6 +254,7 @@ static int launch_step(nmmo_handle *h, int mode, cudaStream_t st, cudaEvent_t af
   }
   const int epc = h->prm.envs_per_cta;
   if (prm.big) nmmo_step_big_kernel<<<prm.E, NM_BIG_THREADS, (size_t)prm.half_smem, st>>>(prm);
+  else if (epc == 3) nmmo_step3_kernel<<<(prm.E + 2) / 3, 3 * NM_STEP_THREADS, (size_t)3 * prm.half_smem, st>>>(prm);
   else nmmo_step_kernel<<<(prm.E + epc - 1) / epc, epc * NM_STEP_THREADS, (size_t)epc * prm.half_smem, st>>>(prm);
   CU(cudaGetLastError());
   if (e3) CU(cudaEventRecord(e3[1], st));

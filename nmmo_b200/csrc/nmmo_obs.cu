@@ -94,13 +94,20 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   uint16_t *s_mkt_rows = (uint16_t *)carve((size_t)L.n_mkt * 2);
   uint16_t *s_inv = (uint16_t *)carve((size_t)AP * NINV * 2);      // indexed by p - p_lo
   int *s_invn = (int *)carve((size_t)AP * 4);
-  int *s_scan = (int *)carve(64 * 4);
+  int *s_scan = (int *)carve(128 * 4);
   const int stage_bytes = nm_align16(L.m_end);
   uint8_t *s_stage_all = carve((size_t)NW * stage_bytes);
   uint16_t *s_vis_all = (uint16_t *)carve((size_t)NW * ((L.n_ent * 2 + 15) & ~15));
   uint32_t *s_bits_all = (uint32_t *)carve((size_t)NW * 72 * 4);   // per warp: 32 bitmap words + 33 running counts
-  const int R32 = (R + 31) & ~31;
+  const int R32 = (R + 31) & ~31, RW = R32 >> 5;
   uint32_t *s_pos = (uint32_t *)carve((size_t)R32 * 4);     // (row+7)<<16 | (col+7) of alive rows, padded to whole warps
+  // cell index for the vision-window search: alive rows bucketed by NM_OBS_CELL x NM_OBS_CELL-tile cell.  A window
+  // (2 * vision + 1 <= NM_OBS_CELL + 1 tiles wide) overlaps at most 2 x 2 cells, so an agent looks at the handful of rows
+  // listed there instead of at every row of the table.
+  const int ncx = (S + NM_OBS_CELL - 1) / NM_OBS_CELL, n_cells = ncx * ncx;
+  int *s_cend = (int *)carve((size_t)(n_cells + 1) * 4);    // per cell: count, then (after the fill) the end of its row list
+  uint16_t *s_crow = (uint16_t *)carve((size_t)R32 * 2);    // rows grouped by cell
+  uint32_t *s_vbm_all = (uint32_t *)carve((size_t)NW * RW * 4);      // per warp: bitmap of the rows inside the agent's window
   uint8_t *s_tmpl = carve(stage_bytes);                      // agent-independent part of the masks
   int *s_head = (int *)carve((2 * AC_N + 2) * 4);       // + work-list length and cursor
   uint32_t *s_meta = (uint32_t *)carve((size_t)AP * 4);
@@ -133,6 +140,8 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   }
   #pragma unroll 1
   for (int i = tid; i < p_hi - p_lo; i += T) { s_invn[i] = 0; s_meta[i] = prm.obs_meta[(size_t)env * P + p_lo + i]; }
+  #pragma unroll 1
+  for (int i = tid; i <= n_cells; i += T) s_cend[i] = 0;
   if (V::kStage) {
     while (!mbar_try_wait(bar, 0)) {}
     while (!mbar_try_wait(bar + 1, 0)) {}
@@ -148,9 +157,18 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   const bool no_give = (wrapper == NW_TAKERU || wrapper == NW_YAOFENG) && c[NC_DISABLE_GIVE];
   const bool no_danger = wrapper == NW_YAOFENG && c[NC_NO_DANGEROUS_NPC];      // yaofeng/reward_wrapper.py:78-81
   // one word per table row for the vision-window scan: an empty row can never match
+  const bool use_cells = 2 * vis + 1 <= NM_OBS_CELL + 1;      // else (huge vision radius): every row is scanned
   #pragma unroll 1
-  for (int r = tid; r < R32; r += T)
-    s_pos[r] = (r < R && status_of(r) == ES_ALIVE) ? (((uint32_t)(OENT(EA_ROW, r) + vis) << 16) | (uint32_t)(OENT(EA_COL, r) + vis)) : 0x7fff7fffu;
+  for (int r = tid; r < R32; r += T) {
+    const bool live = r < R && status_of(r) == ES_ALIVE;
+    uint32_t pos = 0x7fff7fffu;
+    if (live) {
+      const int er = OENT(EA_ROW, r), ec = OENT(EA_COL, r);
+      pos = ((uint32_t)(er + vis) << 16) | (uint32_t)(ec + vis);
+      if (use_cells) atomicAdd(&s_cend[(er / NM_OBS_CELL) * ncx + ec / NM_OBS_CELL], 1);
+    }
+    s_pos[r] = pos;
+  }
   // mask template: entries that do not depend on the agent (Style, Sell.Price, the no-op slots,
   // GiveGold.Price[0]); per agent it is copied and only the agent-specific entries are touched
   #pragma unroll 1
@@ -174,18 +192,36 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
       if (OITM(IS_PRICE, i) > 0) my_listed++;
     }
   }
-  // block exclusive scan of my_listed
-  int incl = my_listed;
-  for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-  if (lane == 31) s_scan[warp] = incl;
+  // block exclusive scan of my_listed -- and, in the same two barriers, of the per-cell row counts (each thread owns
+  // CK consecutive cells; the counts were completed before the barrier that precedes the item pass... no: they are
+  // complete here because the item pass below them reads nothing of theirs and a barrier follows the s_pos pass)
+  const int CK = (n_cells + T - 1) / T;
+  int my_cells = 0;
+  __syncthreads();                                   // cell counts complete
+  #pragma unroll 1
+  for (int k = 0; k < CK; k++) { const int ci = tid * CK + k; if (ci < n_cells) my_cells += s_cend[ci]; }
+  int incl = my_listed, cincl = my_cells;
+  for (int d = 1; d < 32; d <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, d), cv = __shfl_up_sync(0xffffffffu, cincl, d);
+    if (lane >= d) { incl += v; cincl += cv; }
+  }
+  if (lane == 31) { s_scan[warp] = incl; s_scan[64 + warp] = cincl; }
   __syncthreads();
   if (warp == 0) {
-    int v = lane < NW ? s_scan[lane] : 0, inc2 = v;
-    for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc2, d); if (lane >= d) inc2 += u; }
-    if (lane < NW) s_scan[32 + lane] = inc2 - v;
+    int v = lane < NW ? s_scan[lane] : 0, inc2 = v, cv = lane < NW ? s_scan[64 + lane] : 0, cinc2 = cv;
+    for (int d = 1; d < 32; d <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, inc2, d), cu = __shfl_up_sync(0xffffffffu, cinc2, d);
+      if (lane >= d) { inc2 += u; cinc2 += cu; }
+    }
+    if (lane < NW) { s_scan[32 + lane] = inc2 - v; s_scan[96 + lane] = cinc2 - cv; }
     if (lane == NW - 1) s_scan[63] = inc2;
   }
   __syncthreads();
+  {   // counts -> start offsets (the fill below advances each to the end of its cell's list)
+    int run = s_scan[96 + warp] + cincl - my_cells;
+    #pragma unroll 1
+    for (int k = 0; k < CK; k++) { const int ci = tid * CK + k; if (ci < n_cells) { const int cnt = s_cend[ci]; s_cend[ci] = run; run += cnt; } }
+  }
   OPHASE();      // 33 lists + scan
   const int n_mkt = min(s_scan[63], L.n_mkt);
   {
@@ -202,6 +238,16 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     for (int i = 1; i < n; i++) { uint16_t x = l[i]; int j = i - 1; while (j >= 0 && l[j] > x) { l[j + 1] = l[j]; j--; } l[j + 1] = x; }
   }
   __syncthreads();
+  if (use_cells) {      // fill the per-cell row lists (each cell's cursor ends at the end of its list)
+    #pragma unroll 1
+    for (int r = tid; r < R; r += T) {
+      const uint32_t pos = s_pos[r];
+      if (pos == 0x7fff7fffu) continue;
+      const int er = (int)(pos >> 16) - vis, ec = (int)(pos & 0xffffu) - vis;
+      const int k = atomicAdd(&s_cend[(er / NM_OBS_CELL) * ncx + ec / NM_OBS_CELL], 1);
+      s_crow[k] = (uint16_t)r;
+    }
+  }
   #pragma unroll 1
   for (int j = tid; j < n_mkt; j += T) {       // the Market block, identical for every agent of the env
     int16_t row[IA_N_OBS];                      // (rows past n_mkt are zeros and are written as such, not staged)
@@ -281,16 +327,54 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     const int r0 = OENT(EA_ROW, p), c0 = OENT(EA_COL, p), my_id = OENT(EA_ID, p), my_gold = OENT(EA_GOLD, p);
     // visible entities: table rows inside the window, in table order, first n_ent
     int n_vis = 0;
-    #pragma unroll 1
-    for (int base = 0; base < R; base += 32) {
-      int row = base + lane;
-      const uint32_t pos = s_pos[row];                       // padded: rows >= R hold the never-matching word
-      // |r - r0| <= vis  <=>  0 <= (r + vis) - r0 <= 2*vis, same for the column
-      bool in = (uint32_t)((int)(pos >> 16) - r0) <= (uint32_t)(2 * vis) && (uint32_t)((int)(pos & 0xffffu) - c0) <= (uint32_t)(2 * vis);
-      unsigned bm = __ballot_sync(0xffffffffu, in);
-      if (!bm) continue;
-      if (in) { int idx = n_vis + __popc(bm & ((1u << lane) - 1)); if (idx < L.n_ent) s_vis[idx] = (uint16_t)row; }
-      n_vis += __popc(bm);
+    // |r - r0| <= vis  <=>  0 <= (r + vis) - r0 <= 2*vis, same for the column
+    auto in_window = [&](uint32_t pos) -> bool {
+      return (uint32_t)((int)(pos >> 16) - r0) <= (uint32_t)(2 * vis) && (uint32_t)((int)(pos & 0xffffu) - c0) <= (uint32_t)(2 * vis);
+    };
+    if (use_cells) {
+      // the rows listed in the (at most 2 x 2) cells under the window are tested and marked in a row bitmap; walking the
+      // bitmap then yields them in table order
+      uint32_t *vbm = s_vbm_all + warp * RW;
+      #pragma unroll 1
+      for (int w = lane; w < RW; w += 32) vbm[w] = 0;
+      __syncwarp();
+      const int cr0 = max(r0 - vis, 0) / NM_OBS_CELL, cr1 = min(r0 + vis, S - 1) / NM_OBS_CELL;
+      const int cc0 = max(c0 - vis, 0) / NM_OBS_CELL, cc1 = min(c0 + vis, S - 1) / NM_OBS_CELL;
+      #pragma unroll 1
+      for (int cr = cr0; cr <= cr1; cr++) {                  // the cells of one cell row are adjacent in the list
+        const int ca = cr * ncx + cc0;
+        const int beg = ca ? s_cend[ca - 1] : 0, end = s_cend[cr * ncx + cc1];
+        #pragma unroll 1
+        for (int i = beg + lane; i < end; i += 32) {
+          const int row = s_crow[i];
+          if (in_window(s_pos[row])) atomicOr(&vbm[row >> 5], 1u << (row & 31));
+        }
+      }
+      __syncwarp();
+      #pragma unroll 1
+      for (int w0 = 0; w0 < RW; w0 += 32) {
+        const int w = w0 + lane;
+        uint32_t bits = w < RW ? vbm[w] : 0u;
+        const int pc = __popc(bits);
+        if (!__any_sync(0xffffffffu, pc)) continue;
+        int incl2 = pc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl2, d); if (lane >= d) incl2 += u; }
+        int idx = n_vis + incl2 - pc;
+        #pragma unroll 1
+        while (bits && idx < L.n_ent) { const int b = __ffs(bits) - 1; bits &= bits - 1; s_vis[idx++] = (uint16_t)(w * 32 + b); }
+        n_vis += __shfl_sync(0xffffffffu, incl2, 31);
+      }
+    } else {
+      #pragma unroll 1
+      for (int base = 0; base < R; base += 32) {
+        int row = base + lane;
+        const bool in = in_window(s_pos[row]);               // padded: rows >= R hold the never-matching word
+        unsigned bm = __ballot_sync(0xffffffffu, in);
+        if (!bm) continue;
+        if (in) { int idx = n_vis + __popc(bm & ((1u << lane) - 1)); if (idx < L.n_ent) s_vis[idx] = (uint16_t)row; }
+        n_vis += __popc(bm);
+      }
     }
     n_vis = min(n_vis, L.n_ent);
     const int n_inv = min(s_invn[p - p_lo], NINV);

@@ -39,9 +39,15 @@ struct VSmall {
   static constexpr int kChunkIters = 1;                 // 32-row chunks per lane in the per-chunk prefix sums (<= 32 chunks)
   static constexpr int kEvCap = NM_EV_CAP, kDeplCap = NM_DEPL_CAP, kNpcHash = 512, kTblSlots = 1024;
   static constexpr bool kGlobalTables = false;          // tables are staged in shared memory by TMA bulk copies
+  static constexpr bool kItemsInPlace = false;          // ... including the live prefix of the item table and the event ring
   typedef uint16_t tile_t;                              // a tile index r * S + c
   // structure-of-arrays entity table: column-major inside the env (bank-conflict-free per-thread column access)
   static __host__ __device__ __forceinline__ int ent_idx(int col, int row, int R) { return col * R + row; }
+};
+// Small family, three environments per CTA: the item table and the event ring (30 KB of the 105 KB an environment
+// needs) are used in place in HBM / L2, which lets a third environment walk the code with the other two.
+struct VSmall3 : VSmall {
+  static constexpr bool kItemsInPlace = true;
 };
 struct VBig {
   static constexpr int kThreads = NM_BIG_THREADS;
@@ -49,6 +55,7 @@ struct VBig {
   static constexpr int kChunkIters = 3;                 // <= 96 chunks
   static constexpr int kEvCap = NM_BIG_EV_CAP, kDeplCap = NM_BIG_DEPL_CAP, kNpcHash = 4096, kTblSlots = 8192;
   static constexpr bool kGlobalTables = true;           // tables are used where they live (HBM, served from L2)
+  static constexpr bool kItemsInPlace = true;
   typedef uint32_t tile_t;
   // row-major entity table, NM_BIG_ENT_STRIDE int16 per row: the columns of one entity share L2 sectors, and the
   // 31 observed columns are the first 62 bytes of the row, which is what the observation kernel copies out
@@ -1137,7 +1144,7 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
   size_t off = 0, goff = 0;
   auto carve = [&](size_t bytes) { uint8_t *q = smem + off; off = (off + bytes + 15) & ~(size_t)15; return q; };
   // big family: the arrays that are touched a few times per tick live in a per-env workspace in HBM / L2
-  uint8_t *const gws = V::kGlobalTables ? prm.ws + (size_t)env * prm.ws_bytes : nullptr;
+  uint8_t *const gws = V::kItemsInPlace ? prm.ws + (size_t)env * prm.ws_bytes : nullptr;
   auto carve_ws = [&](size_t bytes) {
     if (!V::kGlobalTables) return carve(bytes);
     uint8_t *q = gws + goff; goff = (goff + bytes + 15) & ~(size_t)15; return q;
@@ -1152,7 +1159,7 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
     ctx.map = (uint32_t *)(prm.map + (size_t)env * map_bytes);
   } else {
     ctx.ent = (int16_t *)carve(ent_bytes);
-    ctx.item = (int16_t *)carve(item_bytes);
+    ctx.item = V::kItemsInPlace ? gitem : (int16_t *)carve(item_bytes);
     ctx.map = (uint32_t *)carve(map_bytes);
   }
   const int occ_words = (S * S + 31) >> 5, cap_words = (CAP + 31) >> 5;
@@ -1164,7 +1171,8 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
   ctx.act = (int16_t *)carve_ws((size_t)A_N * P * 2);
   ctx.npc_move = (int8_t *)carve(N);
   ctx.npc_att = (int16_t *)carve((size_t)N * 2);
-  ctx.ev = (uint2 *)carve_ws((size_t)V::kEvCap * 8);
+  if (V::kItemsInPlace && !V::kGlobalTables) { ctx.ev = (uint2 *)(gws + goff); goff += (size_t)V::kEvCap * 8; }      // (VSmall3: the only workspace array)
+  else ctx.ev = (uint2 *)carve_ws((size_t)V::kEvCap * 8);
   ctx.duniq = (int *)carve((size_t)P * 4);
   int *s_list = (int *)carve((size_t)P * 4);
   ctx.npc_hash = (unsigned short *)carve((size_t)V::kNpcHash * 2);
@@ -1207,9 +1215,9 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
     // never read before they are allocated (the in-use bitmap is built from the prefix).
     const uint32_t col_bytes = (uint32_t)item_hi0 * 2;
     const uint32_t dl_bytes = n_depl0 > 0 ? (uint32_t)((n_depl0 * (int)sizeof(tile_t) + 15) & ~15) : 0u;
-    mbar_expect_tx(bar + 1, col_bytes * IS_N + dl_bytes);
+    mbar_expect_tx(bar + 1, (V::kItemsInPlace ? 0u : col_bytes * IS_N) + dl_bytes);
     if (dl_bytes) bulk_g2s(ctx.dlist, gdepl, dl_bytes, bar + 1);
-    if (col_bytes)
+    if (col_bytes && !V::kItemsInPlace)
       for (int k = 0; k < IS_N; k++) bulk_g2s(ctx.item + k * CAP, gitem + (size_t)k * CAP, col_bytes, bar + 1);
   }
   ctx.seed = prm.seed[env];
@@ -1979,7 +1987,7 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
     bulk_s2g(prm.ent + (size_t)env * EA_N * R, ctx.ent, ent_bytes);
     const int hi = ctx.sc[9];
     const uint32_t col_bytes = (uint32_t)hi * 2;
-    if (col_bytes)
+    if (col_bytes && !V::kItemsInPlace)
       for (int k = 0; k < IS_N; k++) bulk_s2g(gitem + (size_t)k * CAP, ctx.item + k * CAP, col_bytes);
     bulk_s2g(prm.map + (size_t)env * map_bytes, ctx.map, map_bytes);
     if (ctx.sc[21] > 0)
@@ -2153,6 +2161,9 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
 
 extern "C" __global__ void __launch_bounds__(2 * VSmall::kThreads, 1)
 nmmo_step_kernel(const __grid_constant__ NmParams prm) { step_body<VSmall>(prm); }
+
+extern "C" __global__ void __launch_bounds__(3 * VSmall3::kThreads, 1)
+nmmo_step3_kernel(const __grid_constant__ NmParams prm) { step_body<VSmall3>(prm); }
 
 extern "C" __global__ void __launch_bounds__(VBig::kThreads, 1)
 nmmo_step_big_kernel(const __grid_constant__ NmParams prm) { step_body<VBig>(prm); }

@@ -153,10 +153,12 @@ def test_respawn_scan_fallback(monkeypatch):
     sim.close()
 
 
-def test_one_env_per_cta_fallback(monkeypatch):
-    # configurations whose tables do not fit twice in a CTA's shared memory run one environment per CTA
-    monkeypatch.setenv("NMMO_B200_ENVS_PER_CTA", "1")
-    world = build_world(task_dim=64, **SMALL, NC_HORIZON=60)
+@pytest.mark.parametrize("epc", ["1", "2"])
+def test_envs_per_cta_variants(monkeypatch, epc):
+    # the default is three environments per CTA (item table and event ring in place in HBM / L2); configurations whose
+    # tables do not fit that way run two per CTA (everything in shared memory), or one
+    monkeypatch.setenv("NMMO_B200_ENVS_PER_CTA", epc)
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=60, NC_RES_DEPLETION=1, NC_SPAWN_IMMUNITY=3)
     sim, oracles = _make(world, 5)
     stats = run_parity(sim, oracles, seeds=np.arange(5) + 3, ticks=130)
     assert stats["episodes_done"] >= 5
