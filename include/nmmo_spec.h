@@ -94,6 +94,8 @@ enum nm_cfg {
    * PLAYER_N / NPC_N / MAP_CENTER, config.yaml:76-80) */
   NC_SPAWN_PATCH,        /* 0 = players spawn on the border ring; k > 0 = all players spawn inside a k x k patch
                             centred on the map ("clustered spawn"), k * k >= PLAYER_N */
+  NC_TEAM_SIZE,          /* players per team (0 or 1 = every agent is its own team, the AgentTraining game of
+                            environment.py:48); teams are consecutive id ranges, the first member is the leader */
   NC_SAMPLE_MOVE_PCT,    /* built-in action sampler only: percent probability that the Move head picks a valid
                             direction other than Stay (0 = uniform over the valid entries, config 2) */
   NC_COUNT
@@ -245,7 +247,7 @@ enum nm_info {
 /* Closed predicate vocabulary (nmmo/task/base_predicates.py [UPSTREAM]); the names are the
  * ones the reference imports: curriculum_generation/manual_curriculum.py:8-29,
  * neurips23_evaluation/heldout_evaluation_task.py:7-20, syllabus_wrapper.py:58-70.
- * A task row is int32[12]: {pred, p0, p1, p2, p3, pred2, q0, combine, q1, q2, wa, wb}.
+ * A task row is int32[12]: {pred, p0, p1, p2, flags (nm_task_flag), pred2, q0, combine, q1, q2, wa, wb}.
  * combine = 0: pred alone; 1: pred * pred2 (manual_curriculum.py:201-202 `InventorySpaceGE * TickGE`);
  * 2: (wa/1000) * pred + (wb/1000) * pred2 (manual_curriculum.py:119-122 `0.3 * EquipItem + 0.7 * GainExperience`).
  * pred2 takes (q0, q1, q2) and must be a state predicate (no event accumulator, no window scan). */
@@ -257,6 +259,14 @@ enum nm_pred {
   TP_DISTANCE_TRAVELED, TP_ALL_DEAD, TP_ALL_MEMBERS_WITHIN_RANGE, TP_CAN_SEE_GROUP, TP_N
 };
 #define NM_TASK_COLS 12
+/* task flags (row column 4, "p3"): who the subject is and how a target given by name is resolved
+ * (reward_to="team" and the "left_team" / "right_team_leader" ... targets of manual_curriculum.py:158-162,
+ * syllabus_wrapper.py:226-240) */
+enum nm_task_flag {
+  TF_TEAM = 1,              /* reward_to="team": the subject is the assignee's whole team, every member gets the reward */
+  TF_RELATIVE_TARGET = 2    /* p0 = team offset relative to the assignee's team (-1 left, +1 right, 0 own):
+                               CanSeeAgent -> that team's leader, CanSeeGroup / AllDead -> that team (AllDead p1 = 1: its leader) */
+};
 
 /* ------------------------------------------------------------------------ rng ------- */
 /* Draw sites.  A draw is addressed by (env seed, tick, site, idx, k) so that a parallel

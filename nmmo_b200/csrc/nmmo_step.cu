@@ -825,6 +825,98 @@ __device__ void npc_spawn_fill(const Ctx<V> &ctx, const uint32_t *q) {
 // ------------------------------------------------------------------------ tasks -----
 __device__ double clip01(double x) { return x > 1.0 ? 1.0 : (x < 0.0 ? 0.0 : x); }
 template <class V>
+__device__ bool sees_tile(const Ctx<V> &ctx, int p, int matl) {
+  const int vis = ctx.c[NC_VISION], r = ENT(EA_ROW, p), c = ENT(EA_COL, p);
+  #pragma unroll 1
+  for (int dr = -vis; dr <= vis; dr++)
+    #pragma unroll 1
+    for (int dc = -vis; dc <= vis; dc++)
+      if (tile_at(ctx, r + dr, c + dc) == matl) return true;
+  return false;
+}
+// is an entity with id in [lo, hi] among the first n_ent table rows inside p's vision window?
+template <class V>
+__device__ bool sees_ids(const Ctx<V> &ctx, int p, int lo, int hi) {
+  const int vis = ctx.c[NC_VISION], r = ENT(EA_ROW, p), c = ENT(EA_COL, p);
+  int seen = 0;
+  #pragma unroll 1
+  for (int row = 0; row < ctx.R && seen < ctx.p->L.n_ent; row++) {
+    if (ENT(EA_STATUS, row) != ES_ALIVE) continue;
+    if (nm_iabs(ENT(EA_ROW, row) - r) > vis || nm_iabs(ENT(EA_COL, row) - c) > vis) continue;
+    seen++;
+    const int id = ENT(EA_ID, row);
+    if (id >= lo && id <= hi) return true;
+  }
+  return false;
+}
+// Team subjects and named targets (nm_task_flag).  Teams are consecutive id ranges of NC_TEAM_SIZE players; a
+// TF_TEAM task is evaluated over the alive members of the assignee's team (every member holds the same task and
+// computes the same value); TF_RELATIVE_TARGET resolves "left/right team (leader)" from the assignee's team.
+template <class V>
+__device__ double eval_team_predicate(const Ctx<V> &ctx, int p, int pred, int p0, int p1, int p2, int flags, bool &handled) {
+  const int ts = max(1, ctx.c[NC_TEAM_SIZE]), nt = (ctx.P + ts - 1) / ts, team = p / ts;
+  const int m0 = (flags & TF_TEAM) ? team * ts : p, m1 = (flags & TF_TEAM) ? min(ctx.P, m0 + ts) : p + 1;      // subject rows
+  int lo = p0, hi = pred == TP_CAN_SEE_AGENT ? p0 : p1;                                                          // target ids
+  int t0 = m0, t1 = m1;                                                                                          // target rows (AllDead)
+  if (flags & TF_RELATIVE_TARGET) {
+    const int tt = (((team + p0) % nt) + nt) % nt;
+    t0 = tt * ts; t1 = min(ctx.P, t0 + ts);
+    if (pred == TP_CAN_SEE_AGENT || (pred == TP_ALL_DEAD && p1 == 1)) t1 = t0 + 1;                               // the leader
+    lo = t0 + 1; hi = t1;
+  }
+  handled = true;
+  int num = 0, den = 1;
+  switch (pred) {
+    case TP_CAN_SEE_TILE:
+      #pragma unroll 1
+      for (int m = m0; m < m1; m++) if (ent_alive(ctx, m) && sees_tile(ctx, m, p0)) return 1.0;
+      return 0.0;
+    case TP_CAN_SEE_AGENT: case TP_CAN_SEE_GROUP:
+      #pragma unroll 1
+      for (int m = m0; m < m1; m++) if (ent_alive(ctx, m) && sees_ids(ctx, m, lo, hi)) return 1.0;
+      return 0.0;
+    case TP_OCCUPY_TILE:
+      #pragma unroll 1
+      for (int m = m0; m < m1; m++) if (ent_alive(ctx, m) && ENT(EA_ROW, m) == p0 && ENT(EA_COL, m) == p1) return 1.0;
+      return 0.0;
+    case TP_STAY_ALIVE:
+      #pragma unroll 1
+      for (int m = m0; m < m1; m++) if (!ent_alive(ctx, m)) return 0.0;
+      return 1.0;
+    case TP_ALL_DEAD:
+      #pragma unroll 1
+      for (int m = t0; m < t1; m++) num += ent_alive(ctx, m) ? 0 : 1;
+      den = t1 - t0; break;
+    case TP_ALL_MEMBERS_WITHIN_RANGE: {
+      int r0 = 1 << 20, r1 = -1, c0 = 1 << 20, c1 = -1;
+      #pragma unroll 1
+      for (int m = m0; m < m1; m++) if (ent_alive(ctx, m)) {
+        r0 = min(r0, (int)ENT(EA_ROW, m)); r1 = max(r1, (int)ENT(EA_ROW, m)); c0 = min(c0, (int)ENT(EA_COL, m)); c1 = max(c1, (int)ENT(EA_COL, m));
+      }
+      return (r1 - r0 <= p0 && c1 - c0 <= p0) ? 1.0 : 0.0;
+    }
+    case TP_DISTANCE_TRAVELED:
+      #pragma unroll 1
+      for (int m = m0; m < m1; m++) if (ent_alive(ctx, m)) num += nm_linf(ENT(EA_ROW, m), ENT(EA_COL, m), ENT(EA_SPAWN_ROW, m), ENT(EA_SPAWN_COL, m));
+      den = p0; break;
+    case TP_HOARD_GOLD:
+      #pragma unroll 1
+      for (int m = m0; m < m1; m++) if (ent_alive(ctx, m)) num += ENT(EA_GOLD, m);
+      den = p0; break;
+    case TP_COUNT_EVENT: case TP_SCORE_HIT: case TP_EARN_GOLD: case TP_SPEND_GOLD: case TP_MAKE_PROFIT: case TP_CONSUME_ITEM:
+    case TP_HARVEST_ITEM: case TP_LIST_ITEM: case TP_BUY_ITEM: case TP_DEFEAT_ENTITY: {
+      // the event-driven accumulators of every member (each counts its own events for the shared task)
+      #pragma unroll 1
+      for (int m = m0; m < m1; m++) num += ctx.acc[m * 2] - (pred == TP_MAKE_PROFIT ? ctx.acc[m * 2 + 1] : 0);
+      den = (pred == TP_COUNT_EVENT || pred == TP_SCORE_HIT) ? p1 : (pred == TP_EARN_GOLD || pred == TP_SPEND_GOLD || pred == TP_MAKE_PROFIT) ? p0 : p2;
+      break;
+    }
+    default: handled = false; return 0.0;      // evaluated on the agent itself
+  }
+  if (den > 0) { if (num <= 0) return 0.0; if (num >= den) return 1.0; }
+  return clip01((double)num / (double)den);
+}
+template <class V>
 __device__ double eval_predicate(const Ctx<V> &ctx, int p, int pred, int p0, int p1, int p2, int acc0, int acc1) {
   int vis = ctx.c[NC_VISION];
   // Ratio predicates only pick (num, den) here; the one f64 division sits behind the switch, and is skipped when
@@ -902,6 +994,23 @@ __device__ double eval_predicate(const Ctx<V> &ctx, int p, int pred, int p0, int
     if (num >= den) return 1.0;
   }
   return clip01((double)num / (double)den);
+}
+
+// whole value of a flagged task (team subject and/or named target), incl. the second predicate and the combinator
+// (measured: as a real call -- __noinline__ -- its mere presence costs the step kernel 22 %, inlined < 1 %)
+template <class V>
+__device__ __forceinline__ double flagged_task_value(const Ctx<V> &ctx, int p, int4 ta, int4 tb, int4 tc, int acc0, int acc1) {
+  const int flags = tb.x;
+  auto one = [&](int pred, int p0, int p1, int p2, int a0, int a1) -> double {
+    bool handled;
+    const double v = eval_team_predicate(ctx, p, pred, p0, p1, p2, flags, handled);
+    return handled ? v : eval_predicate(ctx, p, pred, p0, p1, p2, a0, a1);
+  };
+  double v = one(ta.x, ta.y, ta.z, ta.w, acc0, acc1);
+  if (tb.w == 1) v = v * one(tb.y, tb.z, tc.x, tc.y, 0, 0);
+  else if (tb.w == 2)
+    v = __dadd_rn(__dmul_rn(__ddiv_rn((double)tc.z, 1000.0), v), __dmul_rn(__ddiv_rn((double)tc.w, 1000.0), one(tb.y, tb.z, tc.x, tc.y, 0, 0)));
+  return v;
 }
 
 // fold one event into the agent's accumulators (process_event_log / count_unique_events /
@@ -1081,7 +1190,8 @@ __device__ __noinline__ void reset_env(const NmParams &P_, int env, uint64_t see
     GENT(EA_STATUS) = ES_ALIVE;
 #undef GENT
     size_t a = (size_t)env * P + p;
-    if (!explicit_tasks) P_.task_id[a] = nm_bounded(draw(ctx, RS_TASK, (uint32_t)p, 0), P_.n_tasks);
+    // one task per team: the draw is keyed by the team leader's row (team size 1: by the agent's own)
+    if (!explicit_tasks) P_.task_id[a] = nm_bounded(draw(ctx, RS_TASK, (uint32_t)(p - p % max(1, c[NC_TEAM_SIZE])), 0), P_.n_tasks);
     P_.rew[a] = 0.0f; P_.term[a] = 0; P_.trunc[a] = 0; P_.mask[a] = 1; P_.info_valid[a] = 0;
     P_.obs_meta[a] &= ~OM_TASK;        // new episode, new task embedding
   }
@@ -2016,7 +2126,7 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
   if (tid == 0) ctx.sc[18] = 0;
   HSYNC();
   {
-    bool req = tid < P && st_me == ES_ALIVE && !my_done && (my_t[0] == TP_CAN_SEE_TILE || my_t[0] == TP_CAN_SEE_AGENT || my_t[0] == TP_CAN_SEE_GROUP);
+    bool req = tid < P && st_me == ES_ALIVE && !my_done && my_t[4] == 0 && (my_t[0] == TP_CAN_SEE_TILE || my_t[0] == TP_CAN_SEE_AGENT || my_t[0] == TP_CAN_SEE_GROUP);
     if (tid < P) ctx.slow[tid] = (int8_t)-1;
     unsigned rm = __ballot_sync(0xffffffffu, req);
     int wbase = 0;
@@ -2086,11 +2196,18 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
       else {
         double diff = 0.0;
         if (!completed) {
-          double v = eval_predicate(ctx, p, my_t[0], my_t[1], my_t[2], my_t[3], acc0, acc1);
+          double v;
+          if (my_t[4]) {
+            // team subject / named target (nm_task_flag): rare; one inlined copy instead of a flag test in every predicate
+            v = flagged_task_value(ctx, p, make_int4(my_t[0], my_t[1], my_t[2], my_t[3]), make_int4(my_t[4], my_t[5], my_t[6], my_t[7]),
+                                   make_int4(my_t[8], my_t[9], my_t[10], my_t[11]), acc0, acc1);
+          } else {
+          v = eval_predicate(ctx, p, my_t[0], my_t[1], my_t[2], my_t[3], acc0, acc1);
           if (my_t[7] == 1) v = v * eval_predicate(ctx, p, my_t[5], my_t[6], my_t[8], my_t[9], 0, 0);
           else if (my_t[7] == 2)      // (wa/1000) * a + (wb/1000) * b, each operation rounded like the reference's Python floats
             v = __dadd_rn(__dmul_rn(__ddiv_rn((double)my_t[10], 1000.0), v),
                           __dmul_rn(__ddiv_rn((double)my_t[11], 1000.0), eval_predicate(ctx, p, my_t[5], my_t[6], my_t[8], my_t[9], 0, 0)));
+          }
           v = clip01(v);
           diff = v - my_prog;
           if (v != my_prog) my_ds[DS_PROGRESS] = v;

@@ -118,13 +118,15 @@ class EvalRunner:
         self._debug = debug
         self.env_over = env_over
 
-    def setup_evaluator(self, mode: str, seed: int, task_rows=None):
+    def setup_evaluator(self, mode: str, seed: int, task_rows=None, curriculum: Optional[str] = None):
         from .vecenv import B200VecEnv
         if mode == "pve":
             assert len(self.policies) == 1, "PvE mode requires only one policy"
         kw = eval_env_kwargs(mode, **self.env_over)
+        if task_rows is None and curriculum is None and int(kw["env"].task_size) == 2048:
+            curriculum = "heldout"       # EVAL_TASK_FILE = heldout_task_with_embedding.pkl, TASK_EMBED_DIM 2048 (evaluate.py:20,52-53)
         pool = B200VecEnv(env_kwargs=kw, num_envs=self.num_envs, agent="neurips23_start_kit", device=self.device,
-                          task_rows=task_rows, collect_infos="async")
+                          task_rows=task_rows, curriculum=curriculum, collect_infos="async")
         kernel = create_kernel(pool.agents_per_env, len(self.policies), shuffle_with_seed=seed)
         policy_pool = PolicyPool(self.policies, kernel, self.num_envs, device=pool.sim.obs.device)
         pool.async_reset(seed)
@@ -149,8 +151,8 @@ class EvalRunner:
         return infos
 
     def perform_eval(self, mode: str, seed: int, num_eval_episode: int, save_file_prefix: str, task_rows=None,
-                     steps_per_call: int = 64, max_calls: int = 1 << 20):
-        pool, policy_pool = self.setup_evaluator(mode, seed, task_rows)
+                     steps_per_call: int = 64, max_calls: int = 1 << 20, curriculum: Optional[str] = None):
+        pool, policy_pool = self.setup_evaluator(mode, seed, task_rows, curriculum)
         eval_results: Dict[str, Dict[str, list]] = {}
         cnt_episode, calls = 0, 0
         try:
@@ -175,7 +177,7 @@ class EvalRunner:
         return eval_results, file_name
 
     def run(self, mode: str, seed: Optional[int] = None, num_episode: Optional[int] = None,
-            save_file_prefix: Optional[str] = None, task_rows=None):
+            save_file_prefix: Optional[str] = None, task_rows=None, curriculum: Optional[str] = None):
         assert mode in ("pve", "pvp"), f"Invalid mode: {mode}"
         num_episode = num_episode or (NUM_PVE_EVAL_EPISODE if mode == "pve" else NUM_PVP_EVAL_EPISODE)
         save_file_prefix = save_file_prefix or ("eval_pve" if mode == "pve" else "eval_pvp")
@@ -183,4 +185,4 @@ class EvalRunner:
             num_episode = 4
         if seed is None:
             seed = random.randint(10000000, 99999999)
-        return self.perform_eval(mode, seed, num_episode, save_file_prefix, task_rows=task_rows)
+        return self.perform_eval(mode, seed, num_episode, save_file_prefix, task_rows=task_rows, curriculum=curriculum)

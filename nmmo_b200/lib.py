@@ -45,7 +45,8 @@ def load(build_if_missing: bool = True):
                 raise NmmoError(f"CUDA extension missing and could not be built: {e}") from e
     if not _LIB_PATH.exists():
         raise NmmoError(f"CUDA extension not found at {_LIB_PATH}; run `python -m nmmo_b200.build`")
-    L = C.CDLL(str(_LIB_PATH))
+    import os
+    L = C.CDLL(os.environ.get("NMMO_B200_LIB", str(_LIB_PATH)))      # (development: A/B builds of the same ABI)
     vp = C.c_void_p
     L.nmmo_create.restype = C.c_int
     L.nmmo_create.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.POINTER(vp)]

@@ -27,6 +27,7 @@ SKILL = {k[3:]: v for k, v in SPEC.items() if k.startswith("SK_")}
 ITEM = {k[3:]: v for k, v in SPEC.items() if k.startswith("IT_")}
 PRED = {k[3:]: v for k, v in SPEC.items() if k.startswith("TP_")}
 NCOL = SPEC["NM_TASK_COLS"]
+TF_TEAM, TF_RELATIVE_TARGET = SPEC["TF_TEAM"], SPEC["TF_RELATIVE_TARGET"]
 
 
 STATE_PREDICATES = ("TICK_GE", "ATTAIN_SKILL", "GAIN_EXPERIENCE", "EQUIP_ITEM", "HOARD_GOLD", "INVENTORY_SPACE_GE", "OWN_ITEM",
@@ -34,6 +35,7 @@ STATE_PREDICATES = ("TICK_GE", "ATTAIN_SKILL", "GAIN_EXPERIENCE", "EQUIP_ITEM", 
 
 
 def task_row(pred: str, p0=0, p1=0, p2=0, p3=0, pred2: str = "NONE", q0=0, combine=0, q1=0, q2=0, wa=0, wb=0) -> List[int]:
+    """p3 = flags (TF_TEAM | TF_RELATIVE_TARGET, include/nmmo_spec.h nm_task_flag)."""
     if combine and pred2 not in STATE_PREDICATES:
         raise ValueError(f"the second predicate of a combined task must be a state predicate, not {pred2}")
     return [PRED[pred], int(p0), int(p1), int(p2), int(p3), PRED[pred2], int(q0), int(combine), int(q1), int(q2), int(wa), int(wb)]

@@ -46,7 +46,8 @@ INFO_NAMES = {
 }
 
 
-def info_record_to_dict(row: np.ndarray, episode_done: bool = False, stat_prefix: Optional[str] = None) -> Dict:
+def info_record_to_dict(row: np.ndarray, episode_done: bool = False, stat_prefix: Optional[str] = None,
+                        task_names: Optional[List[str]] = None) -> Dict:
     """nm_info float record -> the dict BaseStatWrapper emits (stat_wrapper.py:132-185).  Keys whose
     record entry is NaN are absent, exactly like the achieved/max_*_level keys of the reference."""
     info: Dict = {"stats": {}}
@@ -60,7 +61,9 @@ def info_record_to_dict(row: np.ndarray, episode_done: bool = False, stat_prefix
             info[key] = v
     info["length"] = int(info["length"])
     tid = int(row[SPEC["IN_TASK_ID"]])
-    info["curriculum"] = {f"task_{tid}": (float(row[SPEC["IN_CURR_MAX_PROGRESS"]]), int(row[SPEC["IN_CURR_REWARD_SIGNALS"]]))}
+    # curriculum[spec_name] = (max_progress, reward_signal_count), stat_wrapper.py:159
+    name = task_names[tid] if task_names is not None and 0 <= tid < len(task_names) else f"task_{tid}"
+    info["curriculum"] = {name: (float(row[SPEC["IN_CURR_MAX_PROGRESS"]]), int(row[SPEC["IN_CURR_REWARD_SIGNALS"]]))}
     if episode_done:
         info["episode_done"] = True
     if stat_prefix:
@@ -93,7 +96,8 @@ class B200VecEnv:
                  envs_per_worker: int = 1, envs_per_batch: Optional[int] = None, env_pool: bool = False,
                  mask_agents: bool = True, agent: str = "takeru", device: int = 0, env_base: int = 0,
                  maps: Optional[np.ndarray] = None, task_rows=None, map_seed: int = 2023, collect_infos="async",
-                 task_embed: Optional[np.ndarray] = None, info_cap: int = 16384):
+                 task_embed: Optional[np.ndarray] = None, info_cap: int = 16384, curriculum: Optional[str] = None,
+                 task_names: Optional[List[str]] = None):
         """collect_infos: "async" (default) -- finished-agent info records are compacted on the device, copied to
         pinned host memory on a side stream and handed out by the NEXT recv() (no host sync in the loop; call
         drain_infos() after the last step); True -- gathered synchronously inside recv() (exact tick, one host sync
@@ -111,6 +115,15 @@ class B200VecEnv:
         # num_maps is honoured as given (takeru 1280, yaofeng 1024: config.yaml:131,113); generation costs ~2 ms per map
         n_maps = max(1, int(getattr(env_ns, "num_maps", 64))) if maps is None else len(maps)
         self.maps = generate_maps(self.cfg, map_seed, n_maps) if maps is None else maps
+        # curriculum: a table translated from the reference's own spec sources (nmmo_b200/curriculum.py): "heldout" (the 63
+        # evaluation tasks with their real 2048-d embeddings, evaluate.py:20,52), "sample_eval", "manual" (training specs)
+        if curriculum is not None:
+            from .curriculum import load_table
+            tab = load_table(curriculum)
+            task_rows, task_names = tab["rows"], tab["names"]
+            if tab["embed"] is not None and tab["embed"].shape[1] == int(self.cfg[SPEC["NC_TASK_DIM"]]):
+                task_embed = tab["embed"]
+        self.task_names = list(task_names) if task_names is not None else None
         rows = task_rows if task_rows is not None else default_curriculum()
         self.task_table, self.task_embed = make_task_table(rows, int(self.cfg[SPEC["NC_TASK_DIM"]]), seed=3)
         if task_embed is not None:      # real embeddings (e.g. nmmo_b200.curriculum.load_heldout): fp16 bit patterns [T, task_dim]
@@ -174,7 +187,8 @@ class B200VecEnv:
             last[int(a) // self.agents_per_env] = k
         for k, a in enumerate(idx):
             e = int(a) // self.agents_per_env
-            infos.append(info_record_to_dict(rows[k], episode_done=bool(done[e]) and last[e] == k, stat_prefix=self.stat_prefix))
+            infos.append(info_record_to_dict(rows[k], episode_done=bool(done[e]) and last[e] == k, stat_prefix=self.stat_prefix,
+                                             task_names=self.task_names))
         return infos
 
     def _enqueue_infos(self):

@@ -96,3 +96,31 @@ def test_pvp_eval_on_device(tmp_path):
     with pytest.raises(AssertionError):
         EvalRunner({"a": idle_policy, "b": idle_policy}, num_envs=1, num_agents=16, num_npcs=32, horizon=48, map_size=32,
                    task_size=64).setup_evaluator("pve", 1)
+
+
+@pytest.mark.gpu
+def test_pvp_eval_on_the_heldout_tasks(tmp_path):
+    """evaluate.py:20,52: evaluation runs on the 63 held-out tasks (real specs and real 2048-d embeddings, translated
+    by nmmo_b200/curriculum.py); the result file is keyed by the reference's spec names."""
+    from nmmo_b200.curriculum import load_table
+
+    def idle_policy(o):
+        B = o.shape[0]
+        a = torch.zeros((B, 12), dtype=torch.int64, device=o.device)
+        a[:, 8] = 4
+        return a, torch.zeros(B, device=o.device), torch.zeros(B, device=o.device)
+
+    runner = EvalRunner({"idle_a": idle_policy, "idle_b": idle_policy}, save_dir=str(tmp_path), num_envs=4, horizon=40)
+    pool, pp = runner.setup_evaluator("pvp", seed=3)
+    held = load_table("heldout")
+    assert pool.task_names == held["names"] and pool.sim.P == 128
+    o = pool.recv()[0]
+    L = pool.driver_env.unflatten_context.layout
+    tid = pool.sim.task_state(0)[0]
+    task_block = o[:128, L.o_task:L.o_task + 4096].cpu().numpy().view(np.uint16)
+    assert np.array_equal(task_block, held["embed"].view(np.uint16)[tid])      # the policy reads the real embeddings
+    pool.send(torch.zeros((4 * 128, 12), dtype=torch.int32, device="cuda"))
+    pool.close()
+    results, _ = runner.perform_eval("pvp", seed=3, num_eval_episode=4, save_file_prefix="eval_pvp", steps_per_call=16)
+    keys = {k for v in results.values() for k in v if k.startswith("curriculum/")}
+    assert keys and all(k[len("curriculum/"):] in set(held["names"]) for k in keys)

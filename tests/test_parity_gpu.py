@@ -52,6 +52,27 @@ def test_yaofeng_wrapper():
     sim.close()
 
 
+def test_team_tasks_and_named_targets():
+    # reward_to="team" subjects and "left/right team (leader)" targets (nm_task_flag) next to the ordinary curriculum:
+    # teams of 4, one task per team, group predicates evaluated over the alive members
+    from nmmo_b200.tasks import EVENT, TF_RELATIVE_TARGET, TF_TEAM, default_curriculum, make_task_table, task_row
+    T, R = TF_TEAM, TF_RELATIVE_TARGET
+    rows = default_curriculum()[:20] + [
+        task_row("ALL_MEMBERS_WITHIN_RANGE", 5, 0, 0, T, pred2="TICK_GE", q0=40, combine=1), task_row("ALL_DEAD", 1, 0, 0, T | R),
+        task_row("ALL_DEAD", -1, 1, 0, T | R), task_row("STAY_ALIVE", 0, 0, 0, T), task_row("DISTANCE_TRAVELED", 20, 0, 0, T),
+        task_row("COUNT_EVENT", EVENT["DRINK_WATER"], 8, 0, T), task_row("CAN_SEE_GROUP", 1, 0, 0, R), task_row("CAN_SEE_GROUP", -1, 0, 0, T | R),
+        task_row("CAN_SEE_AGENT", 1, 0, 0, R), task_row("CAN_SEE_TILE", 4, 0, 0, T), task_row("HOARD_GOLD", 6, 0, 0, T),
+        task_row("OCCUPY_TILE", 24, 24, 0, T), task_row("EARN_GOLD", 3, 0, 0, T), task_row("ATTAIN_SKILL", 1, 2, 0, T)]
+    cfg, fcfg, maps, _, _ = build_world(task_dim=64, **SMALL, NC_HORIZON=150, NC_RES_DEPLETION=1, NC_SPAWN_IMMUNITY=3, NC_TEAM_SIZE=4)
+    tab, emb = make_task_table(rows, 64, seed=2)
+    sim, oracles = _make((cfg, fcfg, maps, tab, emb), 8)
+    stats = run_parity(sim, oracles, seeds=np.arange(8) + 71, ticks=170)
+    assert stats["infos"] > 0
+    tid = sim.task_state(0)[0]
+    assert all(len(set(tid[t * 4:(t + 1) * 4].tolist())) == 1 for t in range(4))
+    sim.close()
+
+
 def _dims(cfg):
     from nmmo_b200.config import ObsLayout
     return np.array(ObsLayout(cfg).action_dims)
