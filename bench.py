@@ -573,6 +573,85 @@ def run_rollout(args):
 
 
 
+def run_config4(args):
+    """`--what config4` (BASELINE.json configs[3]): the rollout loop of clean_pufferl.evaluate
+    (/root/reference/reinforcement_learning/clean_pufferl.py:287-357) with the takeru policy, observations and masks
+    consumed on the device (no host copy): recv -> policy forward -> rollout store -> send, 4096 envs x 128 agents.
+    Reports the reference's own counters (:361-379): SPS (padded slots / elapsed), agent_SPS (sum(mask) / elapsed),
+    env_sps (agent steps / env time), inference_sps (padded / inference time).  One JSON line."""
+    import torch
+    from nmmo_b200.rollout import DeviceRollout
+    from nmmo_b200.takeru_policy import TakeruPolicy
+    from nmmo_b200.vecenv import B200VecEnv
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
+    E = args.envs or 4096
+    pool = B200VecEnv(num_envs=E, agent="takeru", collect_infos=False, curriculum="heldout")
+    P = pool.agents_per_env
+    n = E * P
+    torch.manual_seed(args.seed)
+    policy = TakeruPolicy(pool.driver_env.unflatten_context, 256, 256, 2048, agents_per_env=P, envs_per_chunk=args.policy_chunk_envs).cuda().eval()
+    batch = min(args.rollout_batch, n)
+    roll = DeviceRollout(batch, n, pool.driver_env.obs_sz)
+    clocks = make_clock_sampler(0)
+    pool.async_reset(args.seed)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(args.seed)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    marks = []
+    agent_steps = torch.zeros((), dtype=torch.int64, device="cuda")
+    padded = 0
+
+    def one_step(k, timed):
+        nonlocal padded
+        e = [ev() for _ in range(4)]
+        o, r, d, t, i, env_id, mask = pool.recv()
+        e[0].record()
+        actions, logprob, value = policy(o, generator=gen)                     # inference (:317-319), on the records in HBM
+        e[1].record()
+        roll.reset()                                                           # (one recv fills the batch at this env count)
+        roll.store(o, value, actions, logprob, r, d.float(), mask, k + 1)      # misc: the batch arrays (:333-348), device to device
+        e[2].record()
+        pool.send(actions)                                                     # env: step + observation kernels (:357, :293)
+        e[3].record()
+        if timed:
+            marks.append(e)
+            agent_steps.add_(mask.sum())
+            padded += mask.numel()
+
+    for k in range(args.warmup):
+        one_step(k, False)
+    torch.cuda.synchronize()
+    clocks.start()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for k in range(args.steps):
+        one_step(args.warmup + k, True)
+    t1.record()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    total = t0.elapsed_time(t1) * 1e-3
+    inf_t = sum(e[0].elapsed_time(e[1]) for e in marks) * 1e-3
+    misc_t = sum(e[1].elapsed_time(e[2]) for e in marks) * 1e-3
+    env_t = sum(e[2].elapsed_time(e[3]) for e in marks) * 1e-3
+    a_steps = int(agent_steps.item())
+    rec_bytes = n * pool.driver_env.obs_sz
+    line = {"metric": "agent_SPS", "value": a_steps / total, "unit": "agent-steps/s (sum of mask, clean_pufferl.py:306,365)",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int16 env / fp32 policy" + (" (TF32 matmul)" if args.tf32 else ""), "data": "synthetic",
+            "config": {"workload": f"configs[3]: clean_pufferl rollout loop with the takeru policy (ReducedModelV2 256/256, random init, no LSTM: "
+                                   f"config.yaml:135-136), {E} envs x {P} agents, observations and masks read on the device, held-out task "
+                                   f"curriculum with its real 2048-d embeddings, rollout batch {batch} rows stored on the device",
+                       "envs": E, "agents_per_env": P, "policy_chunk_envs": args.policy_chunk_envs, "obs_record_bytes": pool.driver_env.obs_sz},
+            "SPS": padded / total, "agent_SPS": a_steps / total, "alive_fraction": a_steps / max(1, padded),
+            "env_sps": a_steps / env_t, "env_sps_padded": padded / env_t, "inference_sps": padded / inf_t,
+            "time_share": {"env": env_t / total, "inference": inf_t / total, "misc_rollout_store": misc_t / total},
+            "ms": {"env": env_t / args.steps * 1e3, "inference": inf_t / args.steps * 1e3, "rollout_store": misc_t / args.steps * 1e3},
+            "host_copies_per_step": 0, "obs_bytes_read_by_policy_per_step": rec_bytes,
+            "gpu_launches": 2 * args.steps, "clocks": clk}
+    print(json.dumps(line))
+    pool.close(); roll.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -585,12 +664,17 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--ref-envs", type=int, default=0, help="envs of the CPU sample (default 4 x cores)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--what", default="step", choices=["step", "rollout"], help="rollout = the device rollout storage / GAE micro-benchmark")
+    ap.add_argument("--what", default="step", choices=["step", "rollout", "config4"],
+                    help="rollout = the device rollout storage / GAE micro-benchmark; config4 = rollout loop with the takeru policy on the device")
+    ap.add_argument("--policy-chunk-envs", type=int, default=512, help="config4: environments per policy forward chunk")
+    ap.add_argument("--tf32", type=int, default=0, help="config4: allow TF32 in the policy's matmuls / convolutions (the reference runs fp32)")
     ap.add_argument("--rollout-batch", type=int, default=131072)
     ap.add_argument("--steady-steps", type=int, default=768, help="extra ticks after the timed window for the steady-state figure (0 = off)")
     args = ap.parse_args()
     if args.what == "rollout":
         run_rollout(args)
+    elif args.what == "config4":
+        run_config4(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

@@ -124,6 +124,11 @@ int nmmo_task_state(nmmo_handle *h, int env, int32_t *task_id, int32_t *complete
  * (counters has 8 entries).  Plain sums so ranks can all-reduce them. */
 int nmmo_stats(nmmo_handle *h, double *sums, double *counts, uint64_t *counters, int clear);
 
+/* Device-side error state (synchronises): NM_ERR_STATE when an environment produced more events in one tick than its
+ * event ring holds (events were dropped: statistics and event-driven task progress of that env are wrong) since the
+ * counters were last cleared.  nmmo_step is asynchronous and cannot report it; the host-buffer calls do. */
+int nmmo_check(nmmo_handle *h);
+
 /* Per-kernel device timing (CUDA events recorded on the launching stream around the step kernel
  * and the observation kernel): enable, run steps, read the mean milliseconds per launch. */
 int nmmo_timing(nmmo_handle *h, int enable);

@@ -27,6 +27,7 @@ struct nmmo_handle {
   int device;
   cudaStream_t copy_stream = nullptr;      // host-buffer path: results go home underneath the observation kernel
   cudaEvent_t ev_step_done = nullptr, ev_copy_done = nullptr;
+  unsigned long long *h_overflow = nullptr;   // pinned: event-ring overflow counter, copied home with the results
   size_t step_smem, obs_smem;
   std::vector<void *> allocs;
   int32_t *d_actions;             // staging for the host-buffer path
@@ -173,6 +174,8 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
     if (3 * s3 <= (size_t)max_smem) { p.envs_per_cta = 3; p.half_smem = (int)s3; h->step_smem = s3; }
   }
   if (getenv("NMMO_B200_NO_DEPL_LIST")) p.no_depl_list = 1;      // test hook
+  p.ev_cap = p.big ? VBig::kEvCap : VSmall::kEvCap;
+  if (const char *ov = getenv("NMMO_B200_EV_CAP")) { int v = atoi(ov); if (v > 0 && v < p.ev_cap) p.ev_cap = v; }      // test hook: provoke overflow
   if (const char *ov = getenv("NMMO_B200_ENVS_PER_CTA")) {      // test hook
     if (!p.big && atoi(ov) == 1) { p.envs_per_cta = 1; p.half_smem = (int)((step_smem_bytes(p) + 127) & ~(size_t)127); h->step_smem = p.half_smem; }
   }
@@ -235,7 +238,7 @@ extern "C" int nmmo_destroy(nmmo_handle *h) {
   if (h->d_inj_keys) cudaFree(h->d_inj_keys);
   if (h->d_inj_vals) cudaFree(h->d_inj_vals);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
-  if (h->copy_stream) { cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->ev_step_done); cudaEventDestroy(h->ev_copy_done); }
+  if (h->copy_stream) { cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->ev_step_done); cudaEventDestroy(h->ev_copy_done); cudaFreeHost(h->h_overflow); }
   delete h;
   return NM_OK;
 }
@@ -358,6 +361,8 @@ static int finish_step_host(nmmo_handle *h, float *rew_out, uint8_t *term_out, u
     CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&h->ev_step_done, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_copy_done, cudaEventDisableTiming));
+    CU(cudaMallocHost((void **)&h->h_overflow, sizeof(unsigned long long)));
+    *h->h_overflow = 0;
   }
   int rc = launch_step(h, 0, st, h->ev_step_done);
   if (rc) return rc;
@@ -367,10 +372,26 @@ static int finish_step_host(nmmo_handle *h, float *rew_out, uint8_t *term_out, u
   if (term_out) CU(cudaMemcpyAsync(term_out, p.term, n, cudaMemcpyDeviceToHost, cs));
   if (trunc_out) CU(cudaMemcpyAsync(trunc_out, p.trunc, n, cudaMemcpyDeviceToHost, cs));
   if (mask_out) CU(cudaMemcpyAsync(mask_out, p.mask, n, cudaMemcpyDeviceToHost, cs));
+  CU(cudaMemcpyAsync(h->h_overflow, p.counters + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, cs));
   CU(cudaEventRecord(h->ev_copy_done, cs));
   if (obs_out) CU(cudaMemcpyAsync(obs_out, p.obs, n * p.L.stride, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamWaitEvent(st, h->ev_copy_done, 0));
   CU(cudaStreamSynchronize(st));
+  if (*h->h_overflow)      // events were dropped: the episode statistics and event-driven task progress of that env are wrong
+    return fail(NM_ERR_STATE, "event ring overflow in " + std::to_string(*h->h_overflow) + " env-tick(s): more events in one tick than the ring holds");
+  return NM_OK;
+}
+
+// Device-side error state (synchronises): NM_ERR_STATE when any environment dropped events (its SC_ERROR bit is set)
+// since the counters were last cleared.  The asynchronous nmmo_step cannot report it; callers poll this at their
+// logging cadence (B200VecEnv.stats does).
+extern "C" int nmmo_check(nmmo_handle *h) {
+  if (!h) return fail(NM_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  unsigned long long n = 0;
+  CU(cudaMemcpy(&n, h->prm.counters + 3, sizeof(n), cudaMemcpyDeviceToHost));
+  if (n) return fail(NM_ERR_STATE, "event ring overflow in " + std::to_string(n) + " env-tick(s): more events in one tick than the ring holds");
   return NM_OK;
 }
 

@@ -50,6 +50,7 @@ struct NmParams {
   int16_t *danger;             // [E][N]
   void *depl;                  // [E][depleted-list capacity] tile indices of the depleted tiles (unordered; uint16 small / uint32 big)
   uint8_t *ws; size_t ws_bytes;// big family: per-env workspace for the step kernel's rarely touched arrays
+  int ev_cap;                  // events an env may emit per tick before the ring overflows (the family's ring size)
   int big;                     // 1 = big family (row-major entity table, tables used in place)
   int32_t *stats;              // [E][P][ST_N]
   double *dstats;              // [E][P][DS_N]

@@ -125,7 +125,7 @@ __device__ __forceinline__ uint32_t draw(const Ctx<V> &ctx, uint32_t site, uint3
 template <class V>
 __device__ void emit(const Ctx<V> &ctx, int prow, int code, int type, int level, int number, int gold, int target) {
   int i = atomicAdd(&ctx.sc[0], 1);
-  if (i >= V::kEvCap) { ctx.sc[1] = 1; return; }
+  if (i >= ctx.p->ev_cap) { ctx.sc[1] = 1; return; }      // ev_cap = V::kEvCap (a test hook can lower it)
   // agent 16 bits | dense event 5 | item type / skill 5 | level 4 | target sign 2
   uint32_t w0 = (uint32_t)prow | ((uint32_t)nm_dense_event(code) << 16) | ((uint32_t)type << 21) |
                 ((uint32_t)(level & 15) << 26) | (target > 0 ? (1u << 30) : 0u) | (target < 0 ? (1u << 31) : 0u);
@@ -1111,8 +1111,11 @@ __device__ void write_info(const Ctx<V> &ctx, int p, bool terminated, double cum
 }
 
 // ------------------------------------------------------------------------ reset -----
+#ifndef NM_RESET_INLINE
+#define NM_RESET_INLINE __noinline__
+#endif
 template <class V>
-__device__ __noinline__ void reset_env(const NmParams &P_, int env, uint64_t seed, bool explicit_map, bool explicit_tasks,
+__device__ NM_RESET_INLINE void reset_env(const NmParams &P_, int env, uint64_t seed, bool explicit_map, bool explicit_tasks,
                           int *s_slot /* >= 2*P ints of shared memory */) {
   const int32_t *c = P_.cfg;
   int tid = threadIdx.x % V::kThreads, T = V::kThreads;
@@ -2038,7 +2041,7 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
     // walk the depleted tiles below, and the fold's global atomics -- one returns a value -- are in flight
     // underneath the walk.  The barriers that follow order them before the reward phase reads the counters.
     {
-      const int nev = min(ctx.sc[0], V::kEvCap);
+      const int nev = min(ctx.sc[0], prm.ev_cap);
       PCOUNT(26, nev);
       #pragma unroll 1
       for (int i = T - 1 - tid; i < nev; i += T) fold_event(ctx, ctx.ev[i]);

@@ -20,7 +20,7 @@ EXPORTS = [
     "nmmo_create", "nmmo_destroy", "nmmo_reset", "nmmo_step", "nmmo_step_host", "nmmo_step_host_i16", "nmmo_step_host_u8", "nmmo_sample_actions",
     "nmmo_obs_ptr", "nmmo_reward_ptr", "nmmo_terminated_ptr", "nmmo_truncated_ptr", "nmmo_mask_ptr",
     "nmmo_info_ptr", "nmmo_info_valid_ptr", "nmmo_episode_done_ptr", "nmmo_obs_stride", "nmmo_num_envs",
-    "nmmo_num_agents", "nmmo_inject_rng", "nmmo_snapshot", "nmmo_task_state", "nmmo_stats", "nmmo_timing", "nmmo_timing_read", "nmmo_profile", "nmmo_set_obs_full", "nmmo_set_autosample",
+    "nmmo_num_agents", "nmmo_inject_rng", "nmmo_snapshot", "nmmo_task_state", "nmmo_stats", "nmmo_check", "nmmo_timing", "nmmo_timing_read", "nmmo_profile", "nmmo_set_obs_full", "nmmo_set_autosample",
     "nmmo_last_error",
     "nmmo_rollout_create", "nmmo_rollout_destroy", "nmmo_rollout_reset", "nmmo_rollout_store", "nmmo_rollout_ptr",
     "nmmo_rollout_gae", "nmmo_rollout_buffer", "nmmo_rollout_last_error",
@@ -78,6 +78,8 @@ def load(build_if_missing: bool = True):
     L.nmmo_task_state.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.nmmo_stats.restype = C.c_int
     L.nmmo_stats.argtypes = [vp, vp, vp, vp, C.c_int]
+    L.nmmo_check.restype = C.c_int
+    L.nmmo_check.argtypes = [vp]
     L.nmmo_timing.restype = C.c_int
     L.nmmo_timing.argtypes = [vp, C.c_int]
     L.nmmo_timing_read.restype = C.c_int
@@ -272,6 +274,10 @@ class Simulator:
         counters = np.zeros(8, np.uint64)
         self._check(self.L.nmmo_stats(self.h, _p(sums), _p(counts), _p(counters), int(clear)))
         return sums, counts, counters
+
+    def check(self):
+        """Raises NmmoError if any environment dropped events (event ring overflow) since the last stats clear."""
+        self._check(self.L.nmmo_check(self.h))
 
     def timing(self, enable: bool):
         self._check(self.L.nmmo_timing(self.h, int(enable)))

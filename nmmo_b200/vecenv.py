@@ -276,6 +276,7 @@ class B200VecEnv:
     # ---- extras --------------------------------------------------------------------------
     def stats(self, clear: bool = False) -> Dict[str, float]:
         """Means of the finished-agent infos since the last clear (clean_pufferl.py:381-390)."""
+        self.sim.check()             # a dropped event makes these means wrong: fail instead of reporting them
         sums, counts, counters = self.sim.stats(clear)
         out = {}
         for col, key in INFO_NAMES.items():

@@ -308,3 +308,21 @@ def test_full_size_properties():
     d2 = rollout(False)
     assert d1 == d2
     sim.close()
+
+
+def test_event_ring_overflow_is_an_error(monkeypatch):
+    """An env that emits more events in a tick than its ring holds drops events; that must not pass silently: the
+    host-buffer step call and nmmo_check / B200VecEnv.stats fail with NM_ERR_STATE (ring shrunk to 4 by a test hook)."""
+    from nmmo_b200.lib import NmmoError
+    monkeypatch.setenv("NMMO_B200_EV_CAP", "4")
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=50)
+    sim = _sim(world, 2)
+    sim.reset(np.arange(2, dtype=np.uint64) + 5)
+    sim.check()
+    acts = np.zeros((2, sim.P, 12), np.int32); acts[:, :, 8] = 1          # everybody moves: GO_FARTHEST / DRINK events
+    with pytest.raises(NmmoError, match="event ring overflow"):
+        for _ in range(6):
+            sim.step_host(acts)
+    with pytest.raises(NmmoError, match="event ring overflow"):
+        sim.check()
+    sim.close()
