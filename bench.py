@@ -62,7 +62,8 @@ def world(agent="takeru", n_maps=None, workload="config2"):
     wl = WORKLOADS[workload]
     env_args = default_env_args(resilient_population=0 if agent in ("takeru", "yaofeng", "hybrid") else 0.2, **wl["env"])
     cfg, fcfg = make_config(env_args, default_wrapper_args(agent), agent, **wl["engine"])
-    maps = generate_maps(cfg, 2023, n_maps or (64 if workload == "config2" else 8))
+    # "fine" terrain: ponds and groves every ~10 tiles (nmmo_b200/mapgen.py), so that a foraging population can survive
+    maps = generate_maps(cfg, 2023, n_maps or (64 if workload == "config2" else 8), terrain="fine")
     tab, emb = make_task_table(default_curriculum(), int(cfg[SPEC["NC_TASK_DIM"]]), seed=3)
     return cfg, fcfg, maps, tab, emb
 
@@ -324,23 +325,49 @@ def run_native(args):
     step_ms, obs_ms, n_timed = sim.timing_read()
     sim.timing(False)
     sums, counts, counters = sim.stats(clear=False)
-    # ---- steady state: keep going so that several episodes per env are in the average ----
+    # ---- survival leg (SURVEY.md 8d "run 1024 ticks from reset so the alive-fraction decay is included"): a whole
+    # episode under the scripted forager policy (nmmo_forage_actions: walk to water / foliage when hungry), whose
+    # population decays like the published trained-policy runs (alive 0.83 / 0.53 / 0.25 / 0.13 at ticks
+    # 32 / 128 / 512 / 1023, time average 0.31) instead of starving by tick ~35 like uniform-random agents do.
     steady = None
     if args.steady_steps > 0:
-        _, _, c0 = sim.stats(clear=False)
+        horizon = int(cfg[SPEC["NC_HORIZON"]])
+        n_ticks = min(args.steady_steps, horizon - 1)
+        sim.set_autosample(0, enable=False)
+        sim.reset(seeds)
+        sim.stats(clear=True)
+        marks = {t: None for t in (32, 128, 512, n_ticks - 1) if t < n_ticks}
+        sim.timing(True)
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(8)]
         g0.record(stream)
-        for _ in range(args.steady_steps):
-            tick(args.seed)
+        for t in range(n_ticks):
+            if t < 8:
+                f_ev[t][0].record(stream)
+            sim.forage_actions(args.seed)
+            if t < 8:
+                f_ev[t][1].record(stream)
+            sim.step()
+            if t in marks:
+                marks[t] = sim.mask.sum(dtype=torch.int64)           # stays on the device until the end
         g1.record(stream)
         torch.cuda.synchronize()
+        s_step_ms, s_obs_ms, _ = sim.timing_read()
+        sim.timing(False)
         _, _, c1 = sim.stats(clear=False)
         ms_s = g0.elapsed_time(g1)
-        steady = {"ticks": args.steady_steps, "ms_per_step": ms_s / args.steady_steps,
-                  "value_per_gpu": n_slots_step * args.steady_steps / (ms_s * 1e-3),
-                  "alive_fraction": float(c1[1] - c0[1]) / max(1.0, float(c1[0] - c0[0])),
-                  "episodes_finished": float(c1[2] - c0[2]),
-                  "what": f"the next {args.steady_steps} ticks after the timed window (envs are at different points of their episodes)"}
+        steady = {"policy": "scripted forager (nmmo_forage_actions), no fighting or trading", "ticks": n_ticks,
+                  "ms_per_step": ms_s / n_ticks, "kernels_ms": {"step_kernel": s_step_ms, "obs_kernel": s_obs_ms,
+                                                                 "forager_policy_kernel_first_ticks": sum(a.elapsed_time(b) for a, b in f_ev) / len(f_ev)},
+                  "value_per_gpu": n_slots_step * n_ticks / (ms_s * 1e-3),
+                  "alive_agent_steps_per_s_per_gpu": float(c1[1]) / (ms_s * 1e-3),
+                  "alive_fraction": float(c1[1]) / max(1.0, float(c1[0])),
+                  "alive_fraction_at_tick": {str(t): float(v.item()) / n_slots_step for t, v in marks.items() if v is not None},
+                  "episodes_finished": float(c1[2]),
+                  "what": f"one episode from reset, {n_ticks} ticks, every env in lock-step; the policy kernel's time is inside ms_per_step"}
+        sim.set_autosample(args.seed, sim.actions)
+        sim.reset(seeds)
+        sim.stats(clear=True)
     # ---- dense-writer reference point: every byte of every record rewritten each tick ----
     sim.set_obs_full(True)
     for _ in range(2):
@@ -468,7 +495,7 @@ def run_native(args):
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "path": "nmmo_step_host_u8 (C ABI): one byte per action head from pinned host memory in, reward/term/trunc/mask to pinned host memory out, every "
                             "step; observations stay on the device where the policy reads them; actions = tape of the device-resident run"},
-            "steady_state": steady, "early_window": early,
+            "survival_episode": steady, "early_window": early,
             "gpu_launches": 2 * args.steps,
             "clocks": clk,
             "episode_stats": {"finished_agents": float(g_counts[SPEC["IN_LENGTH"]]),
@@ -669,7 +696,7 @@ def main():
     ap.add_argument("--policy-chunk-envs", type=int, default=512, help="config4: environments per policy forward chunk")
     ap.add_argument("--tf32", type=int, default=0, help="config4: allow TF32 in the policy's matmuls / convolutions (the reference runs fp32)")
     ap.add_argument("--rollout-batch", type=int, default=131072)
-    ap.add_argument("--steady-steps", type=int, default=768, help="extra ticks after the timed window for the steady-state figure (0 = off)")
+    ap.add_argument("--steady-steps", type=int, default=1023, help="ticks of the survival leg (one episode under the scripted forager policy; 0 = off)")
     args = ap.parse_args()
     if args.what == "rollout":
         run_rollout(args)

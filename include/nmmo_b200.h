@@ -84,6 +84,11 @@ int nmmo_step_host_u8(nmmo_handle *h, const uint8_t *actions_host, float *rew_ou
  * keyed (seed, global env, tick, agent, head); writes DEVICE int32 [E][P][12]. */
 int nmmo_sample_actions(nmmo_handle *h, uint64_t seed, int32_t *actions_dev, void *stream);
 
+/* Scripted survival policy for long benchmark runs (uniform-random agents starve within ~35 ticks): every agent walks
+ * to the nearest water / foliage tile of its observation window when hungry, explores otherwise, never fights or
+ * trades.  Reads only the observation records; writes DEVICE int32 [E][P][12]. */
+int nmmo_forage_actions(nmmo_handle *h, uint64_t seed, int32_t *actions_dev, void *stream);
+
 /* Built-in random policy: with a non-NULL DEVICE buffer int32 [E][P][12], every reset/step also
  * writes uniform-random valid actions for the new observations into it (identical draws to
  * nmmo_sample_actions(seed)); NULL switches it off.  Rows of absent agents are zeroed once, when the

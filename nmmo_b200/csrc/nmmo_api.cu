@@ -449,6 +449,19 @@ extern "C" int nmmo_sample_actions(nmmo_handle *h, uint64_t seed, int32_t *actio
   return NM_OK;
 }
 
+extern "C" int nmmo_forage_actions(nmmo_handle *h, uint64_t seed, int32_t *actions_dev, void *stream) {
+  if (!h || !actions_dev) return fail(NM_ERR_ARG, "null argument");
+  if ((uintptr_t)actions_dev & 15) return fail(NM_ERR_ARG, "actions must be 16-byte aligned");
+  CU(cudaSetDevice(h->device));
+  NmParams prm = h->prm;
+  const int threads = 256, NW = threads / 32;
+  const long long n_agents = (long long)prm.E * prm.P;
+  const int blocks = (int)std::min<long long>((n_agents + NW - 1) / NW, 148LL * 8 * 4);
+  nmmo_forage_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(prm, seed, actions_dev);
+  CU(cudaGetLastError());
+  return NM_OK;
+}
+
 extern "C" void *nmmo_obs_ptr(nmmo_handle *h) { return h->prm.obs; }
 extern "C" void *nmmo_reward_ptr(nmmo_handle *h) { return h->prm.rew; }
 extern "C" void *nmmo_terminated_ptr(nmmo_handle *h) { return h->prm.term; }

@@ -732,3 +732,122 @@ nmmo_sample_kernel(const __grid_constant__ NmParams prm, uint64_t seed, int32_t 
     __syncwarp();
   }
 }
+
+// ============================================================= forager action source ===
+// A scripted survival policy for benchmarking: uniform-random agents starve by tick ~35, so long
+// runs of the random workload step mostly empty slots.  The forager keeps a population alive for the whole horizon:
+// a hungry agent (food or water <= 60) takes the first step of a shortest walkable path, inside its 15x15 tile
+// window, to the resource it is shorter of (water: a tile next to water, food: a foliage tile) -- a breadth-first
+// search over the window by one warp -- or, seeing none, heads for the map centre; a sated agent stays put; nobody
+// fights or trades.  It reads only what a policy reads: the agent's own observation record (tile window, own entity
+// row, Move mask).  tests/forager_ref.py is the numpy restatement it is checked against.
+extern "C" __global__ void __launch_bounds__(256)
+nmmo_forage_kernel(const __grid_constant__ NmParams prm, uint64_t seed, int32_t *out) {
+  __shared__ uint8_t s_dist[8][256], s_first[8][256], s_kind[8][256];
+  const nm_obs_layout &L = prm.L;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+  const long long n_agents = (long long)prm.E * prm.P;
+  const int win = L.win, vis = win >> 1, n_tiles = win * win;
+  uint8_t *dist = s_dist[warp], *first = s_first[warp], *kind = s_kind[warp];      // kind: bit0 walkable, bit1 goal
+  for (long long a = (long long)blockIdx.x * NW + warp; a < n_agents; a += (long long)gridDim.x * NW) {
+    const uint8_t *rec = prm.obs + (size_t)a * L.stride;
+    const int16_t my_id = *(const int16_t *)(rec + L.o_ids);
+    if (!prm.mask[a] || my_id == 0 || n_tiles > 256) {      // absent agent: every head picks 0
+      if (lane < AC_N) out[a * AC_N + lane] = 0;
+      continue;
+    }
+    // own row: the Entity row whose id is AgentId
+    const int16_t *ent = (const int16_t *)(rec + L.o_entity);
+    int food = 0, water = 0, my_r = 0, my_c = 0;
+    {
+      int found = -1;
+      for (int r = lane; r < L.n_ent && found < 0; r += 32) if (ent[r * EA_N_OBS + EA_ID] == my_id) found = r;
+      const unsigned bm = __ballot_sync(0xffffffffu, found >= 0);
+      const int src = bm ? __ffs(bm) - 1 : 0;
+      found = __shfl_sync(0xffffffffu, found, src);
+      if (bm) { food = ent[found * EA_N_OBS + EA_FOOD]; water = ent[found * EA_N_OBS + EA_WATER];
+                my_r = ent[found * EA_N_OBS + EA_ROW]; my_c = ent[found * EA_N_OBS + EA_COL]; }
+    }
+    const int env = (int)(a / prm.P), p = (int)(a % prm.P);
+    const int tick = prm.scalars[(size_t)env * NM_SC_N + SC_TICK];
+    const uint64_t base64 = nm_hash64(seed + (uint64_t)(prm.env_base + env), (uint32_t)tick, RS_ACTION, (uint32_t)p, 1);
+    const bool hungry = min(food, water) <= 60;
+    const int want = water <= food ? MT_WATER : MT_FOILAGE;
+    const int16_t *tl = (const int16_t *)(rec + L.o_tile);
+    int dir = 4;                       // Stay
+    bool decided = !hungry;            // sated: stay where the resources are
+    if (hungry) {
+      // breadth-first search over the window from the centre tile; the first goal tile reached (ties: lowest window
+      // index) gives the first step.  Other entities are ignored (they move).
+      const int centre = vis * win + vis;
+      __syncwarp();
+      for (int w = lane; w < n_tiles; w += 32) {
+        const int m = tl[w * 3 + 2];
+        const bool walk = !nm_impassible(m);
+        bool goal = false;
+        if (want == MT_FOILAGE) goal = m == MT_FOILAGE;
+        else if (walk) {
+          const int r = w / win, c = w % win;
+          goal = (r > 0 && tl[(w - win) * 3 + 2] == MT_WATER) || (r < win - 1 && tl[(w + win) * 3 + 2] == MT_WATER) ||
+                 (c > 0 && tl[(w - 1) * 3 + 2] == MT_WATER) || (c < win - 1 && tl[(w + 1) * 3 + 2] == MT_WATER);
+        }
+        kind[w] = (uint8_t)((walk ? 1 : 0) | (goal ? 2 : 0));
+        dist[w] = w == centre ? 0 : 255;
+        first[w] = 4;
+      }
+      __syncwarp();
+      int hit = (kind[centre] & 2) ? centre : -1;
+      for (int round = 1; round <= 48 && hit < 0; round++) {
+        bool grew = false;
+        int mine = 0x7fffffff;
+        for (int w = lane; w < n_tiles; w += 32) {
+          if (dist[w] != 255 || !(kind[w] & 1)) continue;
+          const int r = w / win, c = w % win;
+          // neighbours in the order North, South, West, East of the tile; stepping from a neighbour onto this tile
+          int from = -1, step = 4;
+          if (r > 0 && dist[w - win] == round - 1) { from = w - win; step = 1; }            // came from the north: moved South
+          else if (r < win - 1 && dist[w + win] == round - 1) { from = w + win; step = 0; }
+          else if (c > 0 && dist[w - 1] == round - 1) { from = w - 1; step = 2; }            // came from the west: moved East
+          else if (c < win - 1 && dist[w + 1] == round - 1) { from = w + 1; step = 3; }
+          if (from < 0) continue;
+          first[w] = round == 1 ? (uint8_t)step : first[from];
+          dist[w] = 254;                 // claimed this round (turned into `round` below, after everybody has looked)
+          grew = true;
+          if (kind[w] & 2) mine = min(mine, w);
+        }
+        __syncwarp();
+        for (int w = lane; w < n_tiles; w += 32) if (dist[w] == 254) dist[w] = (uint8_t)round;
+        __syncwarp();
+        mine = __reduce_min_sync(0xffffffffu, mine);
+        if (mine != 0x7fffffff) hit = mine;
+        if (!__any_sync(0xffffffffu, grew)) break;
+      }
+      if (hit >= 0) { dir = hit == centre ? 4 : (int)first[hit]; decided = true; }
+    }
+    if (lane == 0) {
+      const int8_t *mv = (const int8_t *)(rec + L.m_move);      // North South East West Stay
+      if (!decided) {
+        // nothing reachable in sight: head for the map centre (7 ticks in 8), else / when blocked a seeded random valid direction
+        const int dr = prm.S / 2 - my_r, dc = prm.S / 2 - my_c;
+        if (nm_bounded(nm_action_draw(base64, AC_N), 8) != 0) {
+          const int vdir = dr < 0 ? 0 : 1, hdir = dc > 0 ? 2 : 3;
+          const int f1 = nm_iabs(dr) >= nm_iabs(dc) ? vdir : hdir, f2 = nm_iabs(dr) >= nm_iabs(dc) ? hdir : vdir;
+          if ((f1 < 2 ? dr != 0 : dc != 0) && mv[f1]) { dir = f1; decided = true; }
+          else if ((f2 < 2 ? dr != 0 : dc != 0) && mv[f2]) { dir = f2; decided = true; }
+        }
+        if (!decided) {
+          const int nv = (mv[0] != 0) + (mv[1] != 0) + (mv[2] != 0) + (mv[3] != 0);
+          if (nv > 0) {
+            int j = nm_bounded(nm_action_draw(base64, AC_MOVE_DIR), nv);
+            for (int k = 0; k < 4; k++) if (mv[k] && j-- == 0) { dir = k; break; }
+          }
+        }
+      }
+      int4 *o4 = (int4 *)(out + a * AC_N);
+      // no-op everywhere else: Attack.Target / Give.Target / GiveGold.Target = N_ent, Buy = N_mkt, item heads = N_inv
+      o4[0] = make_int4(0, L.n_ent, L.n_mkt, L.n_inv);
+      o4[1] = make_int4(L.n_inv, L.n_ent, 0, L.n_ent);
+      o4[2] = make_int4(dir, L.n_inv, 0, L.n_inv);
+    }
+  }
+}

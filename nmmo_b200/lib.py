@@ -17,7 +17,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "_build" / "libnmmo_b200.so"
 _lib = None
 
 EXPORTS = [
-    "nmmo_create", "nmmo_destroy", "nmmo_reset", "nmmo_step", "nmmo_step_host", "nmmo_step_host_i16", "nmmo_step_host_u8", "nmmo_sample_actions",
+    "nmmo_create", "nmmo_destroy", "nmmo_reset", "nmmo_step", "nmmo_step_host", "nmmo_step_host_i16", "nmmo_step_host_u8", "nmmo_sample_actions", "nmmo_forage_actions",
     "nmmo_obs_ptr", "nmmo_reward_ptr", "nmmo_terminated_ptr", "nmmo_truncated_ptr", "nmmo_mask_ptr",
     "nmmo_info_ptr", "nmmo_info_valid_ptr", "nmmo_episode_done_ptr", "nmmo_obs_stride", "nmmo_num_envs",
     "nmmo_num_agents", "nmmo_inject_rng", "nmmo_snapshot", "nmmo_task_state", "nmmo_stats", "nmmo_check", "nmmo_timing", "nmmo_timing_read", "nmmo_profile", "nmmo_set_obs_full", "nmmo_set_autosample",
@@ -63,6 +63,8 @@ def load(build_if_missing: bool = True):
     L.nmmo_step_host_u8.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.nmmo_sample_actions.restype = C.c_int
     L.nmmo_sample_actions.argtypes = [vp, C.c_uint64, vp, vp]
+    L.nmmo_forage_actions.restype = C.c_int
+    L.nmmo_forage_actions.argtypes = [vp, C.c_uint64, vp, vp]
     for n in ("nmmo_obs_ptr", "nmmo_reward_ptr", "nmmo_terminated_ptr", "nmmo_truncated_ptr", "nmmo_mask_ptr",
               "nmmo_info_ptr", "nmmo_info_valid_ptr", "nmmo_episode_done_ptr"):
         getattr(L, n).restype = vp
@@ -248,6 +250,12 @@ class Simulator:
     def sample_actions(self, seed: int, out=None):
         a = self.actions if out is None else out
         self._check(self.L.nmmo_sample_actions(self.h, C.c_uint64(int(seed)), C.c_void_p(a.data_ptr()), self._stream()))
+        return a
+
+    def forage_actions(self, seed: int, out=None):
+        """Scripted survival policy (nmmo_forage_actions): walk to the nearest water / foliage when hungry, else explore."""
+        a = self.actions if out is None else out
+        self._check(self.L.nmmo_forage_actions(self.h, C.c_uint64(int(seed)), C.c_void_p(a.data_ptr()), self._stream()))
         return a
 
     def inject_rng(self, env: int, keys, vals):

@@ -37,12 +37,19 @@ def _smooth_noise(rng: np.random.Generator, size: int, cell: int) -> np.ndarray:
     return (a * (1 - tc) + b * tc) * (1 - tr) + (c * (1 - tc) + d * tc) * tr
 
 
-def generate_map(cfg: np.ndarray, seed: int, index: int) -> np.ndarray:
+TERRAIN = {
+    # (lattice cell, amplitude) octaves of the value noise
+    "coarse": ((32, 1.0), (16, 0.5), (8, 0.25), (4, 0.125)),      # broad lakes and ranges (the default of the parity tests)
+    "fine": ((16, 0.4), (8, 1.0), (4, 0.5)),                       # ponds and groves every ~10 tiles, like upstream's frequency
+}
+
+
+def generate_map(cfg: np.ndarray, seed: int, index: int, terrain: str = "coarse") -> np.ndarray:
     S = int(cfg[SPEC["NC_MAP_SIZE"]])
     ce = int(cfg[SPEC["NC_MAP_CENTER"]])
     rng = np.random.default_rng([int(seed) & 0xFFFFFFFF, int(index)])
     val = np.zeros((S, S))
-    for cell, amp in ((32, 1.0), (16, 0.5), (8, 0.25), (4, 0.125)):
+    for cell, amp in TERRAIN[terrain]:
         val += amp * _smooth_noise(rng, S, cell)
     # rank-normalise so the material proportions follow the upstream thresholds exactly
     order = val.ravel().argsort().argsort().reshape(S, S) / float(S * S - 1)
@@ -81,5 +88,5 @@ def generate_map(cfg: np.ndarray, seed: int, index: int) -> np.ndarray:
     return m
 
 
-def generate_maps(cfg: np.ndarray, seed: int, n_maps: int) -> np.ndarray:
-    return np.stack([generate_map(cfg, seed, i) for i in range(n_maps)]).astype(np.uint8)
+def generate_maps(cfg: np.ndarray, seed: int, n_maps: int, terrain: str = "coarse") -> np.ndarray:
+    return np.stack([generate_map(cfg, seed, i, terrain) for i in range(n_maps)]).astype(np.uint8)

@@ -326,3 +326,31 @@ def test_event_ring_overflow_is_an_error(monkeypatch):
     with pytest.raises(NmmoError, match="event ring overflow"):
         sim.check()
     sim.close()
+
+
+def test_forager_policy_matches_numpy_and_keeps_agents_alive():
+    """nmmo_forage_actions (scripted survival policy of the bench's survival leg) against tests/forager_ref.py on the
+    device's own records, tick by tick; and it does what it is for: most agents are still alive when uniform-random
+    agents have long starved."""
+    import torch
+    from forager_ref import forage_actions
+    from nmmo_b200.mapgen import generate_maps
+    cfg, fcfg, maps, tab, emb = build_world(task_dim=64, NC_N_PLAYERS=32, NC_N_NPCS=32, NC_MAP_CENTER=48, NC_HORIZON=200)
+    maps = generate_maps(cfg, 11, 3, terrain="fine")
+    sim = _sim((cfg, fcfg, maps, tab, emb), 3)
+    sim.reset(np.arange(3, dtype=np.uint64) + 2)
+    P = sim.P
+    for t in range(90):
+        sim.forage_actions(7)
+        torch.cuda.synchronize()
+        a = sim.actions.cpu().numpy()
+        obs = sim.obs.cpu().numpy().reshape(3, P, -1); mask = sim.mask.cpu().numpy().reshape(3, P)
+        for e in range(3):
+            tick = int(sim.snapshot(e)[3][0])
+            ref = forage_actions(cfg, obs[e], mask[e], tick, 7, env_global=e)
+            assert np.array_equal(a[e], ref), f"tick {t} env {e}: rows {np.flatnonzero((a[e] != ref).any(1))[:4]}"
+        sim.step()
+    torch.cuda.synchronize()
+    alive = sim.mask.cpu().numpy().reshape(3, P).sum(1)
+    assert (alive >= P // 3).all(), f"foragers alive at tick 90: {alive}"
+    sim.close()
