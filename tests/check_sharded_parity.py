@@ -34,6 +34,10 @@ def main():
     ap.add_argument("--check", type=int, default=8, help="envs per GPU compared with the oracle")
     ap.add_argument("--ticks", type=int, default=256)
     ap.add_argument("--seed", type=int, default=11)
+    ap.add_argument("--policy", default="forage", choices=["forage", "random"],
+                    help="forage: the scripted survival policy (episodes run to the horizon); random: uniform-random valid actions")
+    ap.add_argument("--inject-ticks", type=int, default=1 << 20, help="ticks with injected draws (default: all)")
+    ap.add_argument("--out", default=None, help="also write the JSON line to this file (rank 0)")
     a = ap.parse_args()
     ws, rank, lr = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(lr)
@@ -52,7 +56,7 @@ def main():
     R = P + int(cfg[S["NC_N_NPCS"]]); Sz = int(cfg[S["NC_MAP_SIZE"]])
     for e, o in oracles.items():
         keys, vals = [], []
-        for t in range(0, min(a.ticks, 64)):
+        for t in range(0, min(a.ticks, a.inject_ticks)):
             for row in rng.choice(np.arange(P, R), 8, replace=False):
                 keys.append((t << 36) | (S["RS_NPC_DECIDE"] << 32) | (int(row) << 8)); vals.append(int(rng.integers(0, 2 ** 32)))
             for i in rng.choice(Sz * Sz, 32, replace=False):
@@ -62,38 +66,53 @@ def main():
     sim.reset(seeds)
     for e, o in oracles.items():
         o.reset(int(seeds[e]))
-    bad, t0 = 0, time.perf_counter()
+    bad, t0, episodes, alive_sum = 0, time.perf_counter(), 0, 0
+    pick_d = torch.as_tensor(pick, device="cuda")
     for t in range(a.ticks + 1):
-        torch.cuda.synchronize()
-        obs = sim.obs.view(E, P, -1)
-        for e, o in oracles.items():
-            same = (np.array_equal(obs[e].cpu().numpy(), o.obs) and np.array_equal(sim.rewards.view(E, P)[e].cpu().numpy().view(np.uint32), o.rewards.view(np.uint32))
-                    and np.array_equal(sim.terminated.view(E, P)[e].cpu().numpy(), o.terminated) and np.array_equal(sim.truncated.view(E, P)[e].cpu().numpy(), o.truncated)
-                    and np.array_equal(sim.mask.view(E, P)[e].cpu().numpy(), o.mask))
+        # the sampled envs' outputs come home in one gather per tensor
+        g_obs = sim.obs.view(E, P, -1).index_select(0, pick_d).cpu().numpy()
+        g_rew = sim.rewards.view(E, P).index_select(0, pick_d).cpu().numpy(); g_term = sim.terminated.view(E, P).index_select(0, pick_d).cpu().numpy()
+        g_trunc = sim.truncated.view(E, P).index_select(0, pick_d).cpu().numpy(); g_mask = sim.mask.view(E, P).index_select(0, pick_d).cpu().numpy()
+        g_done = sim.episode_done.index_select(0, pick_d).cpu().numpy()
+        for k, (e, o) in enumerate(oracles.items()):
+            same = (np.array_equal(g_obs[k], o.obs) and np.array_equal(g_rew[k].view(np.uint32), o.rewards.view(np.uint32))
+                    and np.array_equal(g_term[k], o.terminated) and np.array_equal(g_trunc[k], o.truncated)
+                    and np.array_equal(g_mask[k], o.mask) and bool(g_done[k]) == bool(o.episode_done))
             bad += 0 if same else 1
+            episodes += int(o.episode_done)
+            alive_sum += int(o.mask.sum())
         if t == a.ticks:
             break
-        sim.sample_actions(a.seed)
-        torch.cuda.synchronize()
-        acts = sim.actions.cpu().numpy()
-        for e, o in oracles.items():
-            oa = o.sample_actions(a.seed + base + e)
-            bad += 0 if np.array_equal(acts[e], oa) else 1
-            o.step(acts[e])
+        if a.policy == "forage":
+            sim.forage_actions(a.seed)
+        else:
+            sim.sample_actions(a.seed)
+        acts = sim.actions.index_select(0, pick_d).cpu().numpy()
+        for k, (e, o) in enumerate(oracles.items()):
+            if a.policy == "random":
+                bad += 0 if np.array_equal(acts[k], o.sample_actions(a.seed + base + e)) else 1
+            o.step(acts[k])
         sim.step()
     sums, counts, counters = reduce_stats(*sim.stats(), device=torch.device("cuda", lr))
-    tb = torch.tensor([bad], dtype=torch.int64, device="cuda")
+    tb = torch.tensor([bad, episodes, alive_sum], dtype=torch.int64, device="cuda")
     if ws > 1:
         dist.all_reduce(tb)
     if rank == 0:
-        print(json.dumps({"what": "config 3 check: env-sharded run, sampled envs vs CPU oracle, injected draws", "n_gpus": ws,
-                          "envs_total": ws * E, "envs_checked": ws * a.check, "ticks": a.ticks, "mismatches": int(tb.item()),
-                          "slot_steps_all_ranks": float(counters[0]), "finished_agents_all_ranks": float(counts[S["IN_LENGTH"]]),
-                          "seconds": time.perf_counter() - t0}))
+        line = json.dumps({"what": "config 3 check: env-sharded run, sampled envs of every rank vs the CPU oracle every tick (observations, "
+                                   "rewards, flags, masks, episode_done), recorded draws injected into both sides", "n_gpus": ws,
+                           "envs_total": ws * E, "envs_checked": ws * a.check, "ticks": a.ticks, "policy": a.policy,
+                           "injected_ticks": min(a.ticks, a.inject_ticks), "mismatches": int(tb[0].item()),
+                           "episodes_finished_in_checked_envs": int(tb[1].item()),
+                           "mean_alive_fraction_checked": float(tb[2].item()) / max(1, ws * a.check * P * (a.ticks + 1)),
+                           "slot_steps_all_ranks": float(counters[0]), "finished_agents_all_ranks": float(counts[S["IN_LENGTH"]]),
+                           "seconds": time.perf_counter() - t0})
+        print(line)
+        if a.out:
+            Path(a.out).write_text(line + "\n")
     sim.close()
     if ws > 1:
         dist.destroy_process_group()
-    sys.exit(0 if int(tb.item()) == 0 else 1)
+    sys.exit(0 if int(tb[0].item()) == 0 else 1)
 
 
 if __name__ == "__main__":
