@@ -29,6 +29,7 @@ struct nmmo_handle {
   cudaEvent_t ev_step_done = nullptr, ev_copy_done = nullptr;
   unsigned long long *h_overflow = nullptr;   // pinned: event-ring overflow counter, copied home with the results
   size_t step_smem, obs_smem;
+  bool obs_std = false, step_std = false;      // the handle has the reference's default shape: the *_std kernels (compile-time shape and layout)
   std::vector<void *> allocs;
   int32_t *d_actions;             // staging for the host-buffer path
   int16_t *d_actions16;           // ... and for its int16 variant
@@ -192,8 +193,21 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
     }
     if (need_obs > obs_attr[b][d]) {
       if (b) CU(cudaFuncSetAttribute(nmmo_obs_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_obs));
-      else CU(cudaFuncSetAttribute(nmmo_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_obs));
+      else {
+        CU(cudaFuncSetAttribute(nmmo_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_obs));
+        CU(cudaFuncSetAttribute(nmmo_obs_std_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_obs));
+      }
       obs_attr[b][d] = need_obs;
+    }
+    {
+      constexpr nm_obs_layout sl = nm_std_layout();
+      const bool std_shape = !b && memcmp(&p.L, &sl, sizeof(sl)) == 0 && p.P == StdShape::P && p.N == StdShape::N && p.R == StdShape::R &&
+                             p.S == StdShape::S && p.CAP == StdShape::CAP && p.cfg[NC_N_INV] == StdShape::NINV;
+      h->obs_std = std_shape && p.ICAP == StdShape::ICAP && p.cfg[NC_VISION] == StdShape::VIS;
+      h->step_std = std_shape && p.envs_per_cta == 3;
+      if (const char *ov = getenv("NMMO_B200_NO_STD_OBS")) { if (atoi(ov) == 1) h->obs_std = false; }      // test hooks: the generic kernels on the default shape
+      if (const char *ov = getenv("NMMO_B200_NO_STD_STEP")) { if (atoi(ov) == 1) h->step_std = false; }
+      if (h->step_std) CU(cudaFuncSetAttribute(nmmo_step3_std_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_step));
     }
   }
   size_t E = p.E, P = p.P;
@@ -257,6 +271,7 @@ static int launch_step(nmmo_handle *h, int mode, cudaStream_t st, cudaEvent_t af
   }
   const int epc = h->prm.envs_per_cta;
   if (prm.big) nmmo_step_big_kernel<<<prm.E, NM_BIG_THREADS, (size_t)prm.half_smem, st>>>(prm);
+  else if (epc == 3 && h->step_std) nmmo_step3_std_kernel<<<(prm.E + 2) / 3, 3 * NM_STEP_THREADS, (size_t)3 * prm.half_smem, st>>>(prm);
   else if (epc == 3) nmmo_step3_kernel<<<(prm.E + 2) / 3, 3 * NM_STEP_THREADS, (size_t)3 * prm.half_smem, st>>>(prm);
   else nmmo_step_kernel<<<(prm.E + epc - 1) / epc, epc * NM_STEP_THREADS, (size_t)epc * prm.half_smem, st>>>(prm);
   CU(cudaGetLastError());
@@ -265,7 +280,8 @@ static int launch_step(nmmo_handle *h, int mode, cudaStream_t st, cudaEvent_t af
   if (prm.big) {
     const int ap = std::min(prm.P, NM_BIG_OBS_AGENTS), parts = (prm.P + ap - 1) / ap;
     nmmo_obs_big_kernel<<<prm.E * parts, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
-  } else nmmo_obs_kernel<<<prm.E, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
+  } else if (h->obs_std) nmmo_obs_std_kernel<<<prm.E, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
+  else nmmo_obs_kernel<<<prm.E, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
   CU(cudaGetLastError());
   if (e3) CU(cudaEventRecord(e3[2], st));
   return NM_OK;

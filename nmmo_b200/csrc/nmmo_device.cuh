@@ -78,6 +78,40 @@ struct NmParams {
   int env_base;                // global env index of env 0 (multi-GPU sharding; seeds derive from it)
 };
 
+// The reference's default shape (config 2: 128 players, 256 NPCs, 160^2 map, N_ent 100, N_mkt 384, 12 inventory rows,
+// 99 prices, 2048-d task, vision 7) as compile-time constants: with it every record offset, stride and divisor of the
+// kernels folds into immediates.  nmmo_create selects the *_std kernels when the handle has this shape.
+__host__ __device__ constexpr nm_obs_layout nm_std_layout() {
+  nm_obs_layout L{};
+  L.n_ent = 100; L.n_mkt = 384; L.n_inv = 12; L.n_price = 99; L.task_dim = 2048; L.win = 15;
+  int o = 0;
+  L.m_style = o; o += 3;
+  L.m_target = o; o += L.n_ent + 1;
+  L.m_buy = o; o += L.n_mkt + 1;
+  L.m_destroy = o; o += L.n_inv + 1;
+  L.m_give_item = o; o += L.n_inv + 1;
+  L.m_give_target = o; o += L.n_ent + 1;
+  L.m_gold_price = o; o += L.n_price;
+  L.m_gold_target = o; o += L.n_ent + 1;
+  L.m_move = o; o += NM_DIR_N;
+  L.m_sell_item = o; o += L.n_inv + 1;
+  L.m_sell_price = o; o += L.n_price;
+  L.m_use = o; o += L.n_inv + 1;
+  L.m_end = o;
+  L.alg_bytes = o;
+  o = (o + 15) & ~15;
+  L.o_ids = o; o += 4; L.alg_bytes += 4; o = (o + 15) & ~15;
+  L.o_entity = o; o += L.n_ent * EA_N_OBS * 2; L.alg_bytes += L.n_ent * EA_N_OBS * 2; o = (o + 15) & ~15;
+  L.o_inventory = o; o += L.n_inv * IA_N_OBS * 2; L.alg_bytes += L.n_inv * IA_N_OBS * 2; o = (o + 15) & ~15;
+  L.o_market = o; o += L.n_mkt * IA_N_OBS * 2; L.alg_bytes += L.n_mkt * IA_N_OBS * 2; o = (o + 15) & ~15;
+  L.o_task = o; o += L.task_dim * 2; L.alg_bytes += L.task_dim * 2; o = (o + 15) & ~15;
+  L.o_tile = o; o += L.win * L.win * 3 * 2; L.alg_bytes += L.win * L.win * 3 * 2;
+  L.stride = (o + 127) & ~127;
+  return L;
+}
+struct StdShape { static constexpr int P = 128, N = 256, R = 384, S = 160, CAP = 1536, ICAP = 384, NINV = 12, VIS = 7; };
+
+
 // ------------------------------------------------------------------------- rng ------
 __host__ __device__ __forceinline__ uint64_t nm_mix64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ULL;

@@ -21,10 +21,15 @@ namespace {
 
 struct OSmall {
   static constexpr bool kStage = true;
+  static constexpr bool kStd = false;
   static __device__ __forceinline__ int ent_idx(int col, int row, int R) { return col * R + row; }
+};
+struct OStd : OSmall {
+  static constexpr bool kStd = true;
 };
 struct OBig {
   static constexpr bool kStage = false;
+  static constexpr bool kStd = false;
   static __device__ __forceinline__ int ent_idx(int col, int row, int) { return row * NM_BIG_ENT_STRIDE + col; }
 };
 
@@ -69,13 +74,17 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
   // small: one CTA per env, all of its agents; big: AP agents per CTA, parts CTAs per env
-  const int AP = V::kStage ? prm.P : min(prm.P, NM_BIG_OBS_AGENTS);
-  const int parts = V::kStage ? 1 : (prm.P + AP - 1) / AP;
-  const int env = V::kStage ? (int)blockIdx.x : (int)blockIdx.x / parts;
-  const int p_lo = V::kStage ? 0 : ((int)blockIdx.x % parts) * AP, p_hi = min(prm.P, p_lo + AP);
   const int32_t *c = prm.cfg;
-  const nm_obs_layout &L = prm.L;
-  const int P = prm.P, R = prm.R, S = prm.S, CAP = prm.CAP, ICAP = prm.ICAP, NINV = c[NC_N_INV], vis = c[NC_VISION];
+  // record layout and table shape: immediates in the std instantiation, run-time values otherwise
+  constexpr nm_obs_layout kStdL = nm_std_layout();
+  const nm_obs_layout &L = V::kStd ? kStdL : prm.L;
+  const int P = V::kStd ? StdShape::P : prm.P, R = V::kStd ? StdShape::R : prm.R, S = V::kStd ? StdShape::S : prm.S;
+  const int CAP = V::kStd ? StdShape::CAP : prm.CAP, ICAP = V::kStd ? StdShape::ICAP : prm.ICAP;
+  const int NINV = V::kStd ? StdShape::NINV : c[NC_N_INV], vis = V::kStd ? StdShape::VIS : c[NC_VISION];
+  const int AP = V::kStage ? P : min(P, NM_BIG_OBS_AGENTS);
+  const int parts = V::kStage ? 1 : (P + AP - 1) / AP;
+  const int env = V::kStage ? (int)blockIdx.x : (int)blockIdx.x / parts;
+  const int p_lo = V::kStage ? 0 : ((int)blockIdx.x % parts) * AP, p_hi = min(P, p_lo + AP);
   const int tick = prm.scalars[(size_t)env * NM_SC_N + SC_TICK];
 
   size_t off = 0;
@@ -641,6 +650,9 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
 
 extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, 3)
 nmmo_obs_kernel(const __grid_constant__ NmParams prm) { obs_body<OSmall>(prm); }
+
+extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, 3)
+nmmo_obs_std_kernel(const __grid_constant__ NmParams prm) { obs_body<OStd>(prm); }
 
 extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, 3)
 nmmo_obs_big_kernel(const __grid_constant__ NmParams prm) { obs_body<OBig>(prm); }

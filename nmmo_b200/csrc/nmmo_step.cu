@@ -40,6 +40,7 @@ struct VSmall {
   static constexpr int kEvCap = NM_EV_CAP, kDeplCap = NM_DEPL_CAP, kNpcHash = 512, kTblSlots = 1024;
   static constexpr bool kGlobalTables = false;          // tables are staged in shared memory by TMA bulk copies
   static constexpr bool kItemsInPlace = false;          // ... including the live prefix of the item table and the event ring
+  static constexpr bool kStd = false;                   // true: the reference's default shape as compile-time constants
   typedef uint16_t tile_t;                              // a tile index r * S + c
   // structure-of-arrays entity table: column-major inside the env (bank-conflict-free per-thread column access)
   static __host__ __device__ __forceinline__ int ent_idx(int col, int row, int R) { return col * R + row; }
@@ -49,6 +50,10 @@ struct VSmall {
 struct VSmall3 : VSmall {
   static constexpr bool kItemsInPlace = true;
 };
+// ... and with the reference's default shape (128 players, 256 NPCs, 160^2 map, default record layout) folded in
+struct VSmall3Std : VSmall3 {
+  static constexpr bool kStd = true;
+};
 struct VBig {
   static constexpr int kThreads = NM_BIG_THREADS;
   static constexpr int kRowsPerThread = 3;
@@ -56,6 +61,7 @@ struct VBig {
   static constexpr int kEvCap = NM_BIG_EV_CAP, kDeplCap = NM_BIG_DEPL_CAP, kNpcHash = 4096, kTblSlots = 8192;
   static constexpr bool kGlobalTables = true;           // tables are used where they live (HBM, served from L2)
   static constexpr bool kItemsInPlace = true;
+  static constexpr bool kStd = false;
   typedef uint32_t tile_t;
   // row-major entity table, NM_BIG_ENT_STRIDE int16 per row: the columns of one entity share L2 sectors, and the
   // 31 observed columns are the first 62 bytes of the row, which is what the observation kernel copies out
@@ -1242,7 +1248,9 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
   uint8_t *smem = smem_all + (size_t)half * prm.half_smem;
   const int env = blockIdx.x * prm.envs_per_cta + half, tid = threadIdx.x % V::kThreads, T = V::kThreads, lane = tid & 31, warp = tid >> 5;
   const int32_t *c = prm.cfg;
-  const int P = prm.P, N = prm.N, R = prm.R, S = prm.S, CAP = prm.CAP, NINV = c[NC_N_INV];
+  constexpr nm_obs_layout kStdL = nm_std_layout();
+  const int P = V::kStd ? StdShape::P : prm.P, N = V::kStd ? StdShape::N : prm.N, R = V::kStd ? StdShape::R : prm.R;
+  const int S = V::kStd ? StdShape::S : prm.S, CAP = V::kStd ? StdShape::CAP : prm.CAP, NINV = V::kStd ? StdShape::NINV : c[NC_N_INV];
   if (env >= prm.E) return;          // odd environment count: the last CTA runs one half (exited threads do not count at barriers)
   int32_t *gsc = prm.scalars + (size_t)env * NM_SC_N;
 
@@ -1396,8 +1404,8 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
     const int g_status = gent[V::ent_idx(EA_STATUS, p, R)], g_health = gent[V::ent_idx(EA_HEALTH, p, R)];   // same answer as ent_alive() later
     int4 xa = x4[0], xb = x4[1], xc = x4[2];
     if (!(g_status == ES_ALIVE && g_health > 0)) { xa = make_int4(-1, -1, -1, -1); xb = xa; xc = xa; }   // no id reads for the dead
-    const uint8_t *rec = prm.obs + ((size_t)env * P + p) * prm.L.stride;
-    const nm_obs_layout &L = prm.L;
+    const nm_obs_layout &L = V::kStd ? kStdL : prm.L;
+    const uint8_t *rec = prm.obs + ((size_t)env * P + p) * L.stride;
     auto ent_id = [&](int idx) -> int { return (idx >= 0 && idx < L.n_ent) ? (int)*(const int16_t *)(rec + L.o_entity + idx * (EA_N_OBS * 2)) : 0; };
     auto inv_id = [&](int idx) -> int { return (idx >= 0 && idx < L.n_inv) ? (int)*(const int16_t *)(rec + L.o_inventory + idx * (IA_N_OBS * 2)) : 0; };
     auto mkt_id = [&](int idx) -> int { return (idx >= 0 && idx < L.n_mkt) ? (int)*(const int16_t *)(rec + L.o_market + idx * (IA_N_OBS * 2)) : 0; };
@@ -2158,13 +2166,14 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
     } else {
       int lo = q0, hi = pred == TP_CAN_SEE_AGENT ? q0 : q1, seen = 0;
       #pragma unroll 1
-      for (int base = 0; base < R && seen < prm.L.n_ent; base += 32) {
+      const int n_ent_obs = V::kStd ? kStdL.n_ent : prm.L.n_ent;
+      for (int base = 0; base < R && seen < n_ent_obs; base += 32) {
         int row = base + lane;
         bool in = row < R && ENT(EA_STATUS, row) == ES_ALIVE && nm_iabs(ENT(EA_ROW, row) - r) <= vis && nm_iabs(ENT(EA_COL, row) - cc) <= vis;
         unsigned bm = __ballot_sync(0xffffffffu, in);
         int rank = seen + __popc(bm & ((1u << lane) - 1));
         int id = in ? (int)ENT(EA_ID, row) : 0;
-        hit |= in && rank < prm.L.n_ent && id >= lo && id <= hi;
+        hit |= in && rank < n_ent_obs && id >= lo && id <= hi;
         seen += __popc(bm);
       }
       hit = __any_sync(0xffffffffu, hit);
@@ -2284,6 +2293,9 @@ nmmo_step_kernel(const __grid_constant__ NmParams prm) { step_body<VSmall>(prm);
 
 extern "C" __global__ void __launch_bounds__(3 * VSmall3::kThreads, 1)
 nmmo_step3_kernel(const __grid_constant__ NmParams prm) { step_body<VSmall3>(prm); }
+
+extern "C" __global__ void __launch_bounds__(3 * VSmall3Std::kThreads, 1)
+nmmo_step3_std_kernel(const __grid_constant__ NmParams prm) { step_body<VSmall3Std>(prm); }
 
 extern "C" __global__ void __launch_bounds__(VBig::kThreads, 1)
 nmmo_step_big_kernel(const __grid_constant__ NmParams prm) { step_body<VBig>(prm); }
