@@ -289,6 +289,7 @@ def run_native(args):
     E, P = args.envs or WORKLOADS[args.workload]["envs"], int(cfg[SPEC["NC_N_PLAYERS"]])
     clocks = make_clock_sampler(local_rank)      # NVML polling runs from here on, through the warm-up
     sim = Simulator(*w[:2], E, *w[2:], device=local_rank, env_base=rank * E)
+    kernel_names = sim.kernel_names()
     seeds = np.arange(E, dtype=np.uint64) + np.uint64(rank * E + args.seed)
     stream = torch.cuda.current_stream()
 
@@ -462,13 +463,13 @@ def run_native(args):
         # written by tools/summarize_ncu.py from the .ncu-rep of tools/ncu_round.sh); null when none is committed
         alive_frac = float(g_counters[1]) / max(1.0, float(g_counters[0]))
         big = args.workload == "config5"
-        k_step, k_obs = ("nmmo_step_big_kernel", "nmmo_obs_big_kernel") if big else ("nmmo_step_kernel", "nmmo_obs_kernel")
+        k_step, k_obs = kernel_names
         # captures are labelled by regime: "alive" = tick 12 of the driver's window (every agent alive), "tick40" = the
         # mostly-dead regime of long random-action runs, "c5" = config 5; only a capture of the window's regime is quoted
         regime = ["c5"] if big else (["alive"] if alive_frac > 0.8 else ["tick40"])
         tr, traffic_src = committed_traffic(regime)
-        traffic = tr.get(k_obs)
-        traffic_dense = committed_traffic(["dense"])[0].get("nmmo_obs_kernel") if not big else None
+        traffic = tr.get(k_obs)          # only a capture of the very kernel instantiation that was timed is quoted
+        traffic_dense = committed_traffic(["dense"])[0].get(k_obs) if not big else None
         obs_gbs = obs_bytes_launch / (obs_ms * 1e-3) / 1e9
         dense_gbs = n * b_obs / (obs_ms_dense * 1e-3) / 1e9
         line = {

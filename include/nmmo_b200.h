@@ -105,6 +105,10 @@ void *nmmo_info_ptr(nmmo_handle *h);         /* float [E*P][IN_N]  episode-end i
 void *nmmo_info_valid_ptr(nmmo_handle *h);   /* uint8 [E*P] */
 void *nmmo_episode_done_ptr(nmmo_handle *h); /* uint8 [E]    infos[..]["episode_done"], stat_wrapper.py:93-95 */
 int nmmo_obs_stride(nmmo_handle *h);
+/* Names of the kernel instantiations this handle launches per step (family and compile-time shape are chosen by
+ * nmmo_create from the configuration), as a profiler lists them. */
+const char *nmmo_step_kernel_name(nmmo_handle *h);
+const char *nmmo_obs_kernel_name(nmmo_handle *h);
 int nmmo_num_envs(nmmo_handle *h);
 int nmmo_num_agents(nmmo_handle *h);
 

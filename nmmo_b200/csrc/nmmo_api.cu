@@ -29,7 +29,7 @@ struct nmmo_handle {
   cudaEvent_t ev_step_done = nullptr, ev_copy_done = nullptr;
   unsigned long long *h_overflow = nullptr;   // pinned: event-ring overflow counter, copied home with the results
   size_t step_smem, obs_smem;
-  bool obs_std = false, step_std = false;      // the handle has the reference's default shape: the *_std kernels (compile-time shape and layout)
+  bool obs_std = false, step_std = false, big_std = false;      // the handle has the reference's default shape: the *_std kernels (compile-time shape and layout)
   std::vector<void *> allocs;
   int32_t *d_actions;             // staging for the host-buffer path
   int16_t *d_actions16;           // ... and for its int16 variant
@@ -208,6 +208,14 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
       if (const char *ov = getenv("NMMO_B200_NO_STD_OBS")) { if (atoi(ov) == 1) h->obs_std = false; }      // test hooks: the generic kernels on the default shape
       if (const char *ov = getenv("NMMO_B200_NO_STD_STEP")) { if (atoi(ov) == 1) h->step_std = false; }
       if (h->step_std) CU(cudaFuncSetAttribute(nmmo_step3_std_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_step));
+      // big family: the configs[4] shape
+      h->big_std = b && memcmp(&p.L, &sl, sizeof(sl)) == 0 && p.P == StdShape5::P && p.N == StdShape5::N && p.R == StdShape5::R &&
+                   p.S == StdShape5::S && p.CAP == StdShape5::CAP && p.cfg[NC_N_INV] == StdShape5::NINV && p.cfg[NC_VISION] == StdShape5::VIS;
+      if (const char *ov = getenv("NMMO_B200_NO_STD_STEP")) { if (atoi(ov) == 1) h->big_std = false; }
+      if (h->big_std) {
+        CU(cudaFuncSetAttribute(nmmo_step_big_std_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_step));
+        CU(cudaFuncSetAttribute(nmmo_obs_big_std_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_obs));
+      }
     }
   }
   size_t E = p.E, P = p.P;
@@ -270,7 +278,8 @@ static int launch_step(nmmo_handle *h, int mode, cudaStream_t st, cudaEvent_t af
     CU(cudaEventRecord(e3[0], st));
   }
   const int epc = h->prm.envs_per_cta;
-  if (prm.big) nmmo_step_big_kernel<<<prm.E, NM_BIG_THREADS, (size_t)prm.half_smem, st>>>(prm);
+  if (prm.big && h->big_std) nmmo_step_big_std_kernel<<<prm.E, NM_BIG_THREADS, (size_t)prm.half_smem, st>>>(prm);
+  else if (prm.big) nmmo_step_big_kernel<<<prm.E, NM_BIG_THREADS, (size_t)prm.half_smem, st>>>(prm);
   else if (epc == 3 && h->step_std) nmmo_step3_std_kernel<<<(prm.E + 2) / 3, 3 * NM_STEP_THREADS, (size_t)3 * prm.half_smem, st>>>(prm);
   else if (epc == 3) nmmo_step3_kernel<<<(prm.E + 2) / 3, 3 * NM_STEP_THREADS, (size_t)3 * prm.half_smem, st>>>(prm);
   else nmmo_step_kernel<<<(prm.E + epc - 1) / epc, epc * NM_STEP_THREADS, (size_t)epc * prm.half_smem, st>>>(prm);
@@ -279,7 +288,8 @@ static int launch_step(nmmo_handle *h, int mode, cudaStream_t st, cudaEvent_t af
   if (after_step) CU(cudaEventRecord(after_step, st));      // rewards / flags / mask are final here
   if (prm.big) {
     const int ap = std::min(prm.P, NM_BIG_OBS_AGENTS), parts = (prm.P + ap - 1) / ap;
-    nmmo_obs_big_kernel<<<prm.E * parts, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
+    if (h->big_std) nmmo_obs_big_std_kernel<<<prm.E * parts, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
+    else nmmo_obs_big_kernel<<<prm.E * parts, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
   } else if (h->obs_std) nmmo_obs_std_kernel<<<prm.E, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
   else nmmo_obs_kernel<<<prm.E, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
   CU(cudaGetLastError());
@@ -486,6 +496,16 @@ extern "C" void *nmmo_mask_ptr(nmmo_handle *h) { return h->prm.mask; }
 extern "C" void *nmmo_info_ptr(nmmo_handle *h) { return h->prm.info; }
 extern "C" void *nmmo_info_valid_ptr(nmmo_handle *h) { return h->prm.info_valid; }
 extern "C" void *nmmo_episode_done_ptr(nmmo_handle *h) { return h->prm.episode_done; }
+// which instantiation this handle launches (bench / profiling: kernel names as ncu lists them)
+extern "C" const char *nmmo_step_kernel_name(nmmo_handle *h) {
+  if (h->prm.big) return h->big_std ? "nmmo_step_big_std_kernel" : "nmmo_step_big_kernel";
+  if (h->prm.envs_per_cta == 3) return h->step_std ? "nmmo_step3_std_kernel" : "nmmo_step3_kernel";
+  return "nmmo_step_kernel";
+}
+extern "C" const char *nmmo_obs_kernel_name(nmmo_handle *h) {
+  if (h->prm.big) return h->big_std ? "nmmo_obs_big_std_kernel" : "nmmo_obs_big_kernel";
+  return h->obs_std ? "nmmo_obs_std_kernel" : "nmmo_obs_kernel";
+}
 extern "C" int nmmo_obs_stride(nmmo_handle *h) { return h->prm.L.stride; }
 extern "C" int nmmo_num_envs(nmmo_handle *h) { return h->prm.E; }
 extern "C" int nmmo_num_agents(nmmo_handle *h) { return h->prm.P; }

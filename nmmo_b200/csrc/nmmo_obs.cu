@@ -22,6 +22,7 @@ namespace {
 struct OSmall {
   static constexpr bool kStage = true;
   static constexpr bool kStd = false;
+  typedef StdShape Shape;
   static __device__ __forceinline__ int ent_idx(int col, int row, int R) { return col * R + row; }
 };
 struct OStd : OSmall {
@@ -30,6 +31,7 @@ struct OStd : OSmall {
 struct OBig {
   static constexpr bool kStage = false;
   static constexpr bool kStd = false;
+  typedef StdShape5 Shape;
   static __device__ __forceinline__ int ent_idx(int col, int row, int) { return row * NM_BIG_ENT_STRIDE + col; }
 };
 
@@ -69,6 +71,10 @@ __device__ __forceinline__ uint32_t pack2(int a, int b) { return (uint32_t)(uint
 
 }  // namespace
 
+struct OBigStd : OBig {
+  static constexpr bool kStd = true;
+};
+
 template <class V>
 __device__ __forceinline__ void obs_body(const NmParams &prm) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -76,11 +82,13 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   // small: one CTA per env, all of its agents; big: AP agents per CTA, parts CTAs per env
   const int32_t *c = prm.cfg;
   // record layout and table shape: immediates in the std instantiation, run-time values otherwise
+  typedef typename V::Shape SH;
   constexpr nm_obs_layout kStdL = nm_std_layout();
   const nm_obs_layout &L = V::kStd ? kStdL : prm.L;
-  const int P = V::kStd ? StdShape::P : prm.P, R = V::kStd ? StdShape::R : prm.R, S = V::kStd ? StdShape::S : prm.S;
-  const int CAP = V::kStd ? StdShape::CAP : prm.CAP, ICAP = V::kStd ? StdShape::ICAP : prm.ICAP;
-  const int NINV = V::kStd ? StdShape::NINV : c[NC_N_INV], vis = V::kStd ? StdShape::VIS : c[NC_VISION];
+  const int P = V::kStd ? SH::P : prm.P, R = V::kStd ? SH::R : prm.R, S = V::kStd ? SH::S : prm.S;
+  const int CAP = V::kStd ? SH::CAP : prm.CAP;
+  const int ICAP = !V::kStage ? 0 : (V::kStd ? SH::ICAP : prm.ICAP);      // big family: no staged item prefix, every row is read in place
+  const int NINV = V::kStd ? SH::NINV : c[NC_N_INV], vis = V::kStd ? SH::VIS : c[NC_VISION];
   const int AP = V::kStage ? P : min(P, NM_BIG_OBS_AGENTS);
   const int parts = V::kStage ? 1 : (P + AP - 1) / AP;
   const int env = V::kStage ? (int)blockIdx.x : (int)blockIdx.x / parts;
@@ -656,6 +664,9 @@ nmmo_obs_std_kernel(const __grid_constant__ NmParams prm) { obs_body<OStd>(prm);
 
 extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, 3)
 nmmo_obs_big_kernel(const __grid_constant__ NmParams prm) { obs_body<OBig>(prm); }
+
+extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, 3)
+nmmo_obs_big_std_kernel(const __grid_constant__ NmParams prm) { obs_body<OBigStd>(prm); }
 
 // ============================================================= action sampler kernel ===
 // uniform-random valid action per head from the ActionTargets masks (BASELINE.json config 2:

@@ -40,7 +40,8 @@ struct VSmall {
   static constexpr int kEvCap = NM_EV_CAP, kDeplCap = NM_DEPL_CAP, kNpcHash = 512, kTblSlots = 1024;
   static constexpr bool kGlobalTables = false;          // tables are staged in shared memory by TMA bulk copies
   static constexpr bool kItemsInPlace = false;          // ... including the live prefix of the item table and the event ring
-  static constexpr bool kStd = false;                   // true: the reference's default shape as compile-time constants
+  static constexpr bool kStd = false;                   // true: a known shape (Shape) as compile-time constants
+  typedef StdShape Shape;
   typedef uint16_t tile_t;                              // a tile index r * S + c
   // structure-of-arrays entity table: column-major inside the env (bank-conflict-free per-thread column access)
   static __host__ __device__ __forceinline__ int ent_idx(int col, int row, int R) { return col * R + row; }
@@ -62,10 +63,14 @@ struct VBig {
   static constexpr bool kGlobalTables = true;           // tables are used where they live (HBM, served from L2)
   static constexpr bool kItemsInPlace = true;
   static constexpr bool kStd = false;
+  typedef StdShape5 Shape;
   typedef uint32_t tile_t;
   // row-major entity table, NM_BIG_ENT_STRIDE int16 per row: the columns of one entity share L2 sectors, and the
   // 31 observed columns are the first 62 bytes of the row, which is what the observation kernel copies out
   static __host__ __device__ __forceinline__ int ent_idx(int col, int row, int) { return row * NM_BIG_ENT_STRIDE + col; }
+};
+struct VBigStd : VBig {      // the configs[4] shape folded in
+  static constexpr bool kStd = true;
 };
 // attack registrations: (round tag << kIdxBits) | index of the attack in the ordered list (< 4096 attacks per env)
 constexpr int kIdxBits = 12;
@@ -1249,8 +1254,9 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
   const int env = blockIdx.x * prm.envs_per_cta + half, tid = threadIdx.x % V::kThreads, T = V::kThreads, lane = tid & 31, warp = tid >> 5;
   const int32_t *c = prm.cfg;
   constexpr nm_obs_layout kStdL = nm_std_layout();
-  const int P = V::kStd ? StdShape::P : prm.P, N = V::kStd ? StdShape::N : prm.N, R = V::kStd ? StdShape::R : prm.R;
-  const int S = V::kStd ? StdShape::S : prm.S, CAP = V::kStd ? StdShape::CAP : prm.CAP, NINV = V::kStd ? StdShape::NINV : c[NC_N_INV];
+  typedef typename V::Shape SH;
+  const int P = V::kStd ? SH::P : prm.P, N = V::kStd ? SH::N : prm.N, R = V::kStd ? SH::R : prm.R;
+  const int S = V::kStd ? SH::S : prm.S, CAP = V::kStd ? SH::CAP : prm.CAP, NINV = V::kStd ? SH::NINV : c[NC_N_INV];
   if (env >= prm.E) return;          // odd environment count: the last CTA runs one half (exited threads do not count at barriers)
   int32_t *gsc = prm.scalars + (size_t)env * NM_SC_N;
 
@@ -2299,3 +2305,6 @@ nmmo_step3_std_kernel(const __grid_constant__ NmParams prm) { step_body<VSmall3S
 
 extern "C" __global__ void __launch_bounds__(VBig::kThreads, 1)
 nmmo_step_big_kernel(const __grid_constant__ NmParams prm) { step_body<VBig>(prm); }
+
+extern "C" __global__ void __launch_bounds__(VBigStd::kThreads, 1)
+nmmo_step_big_std_kernel(const __grid_constant__ NmParams prm) { step_body<VBigStd>(prm); }

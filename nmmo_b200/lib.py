@@ -20,7 +20,7 @@ EXPORTS = [
     "nmmo_create", "nmmo_destroy", "nmmo_reset", "nmmo_step", "nmmo_step_host", "nmmo_step_host_i16", "nmmo_step_host_u8", "nmmo_sample_actions", "nmmo_forage_actions",
     "nmmo_obs_ptr", "nmmo_reward_ptr", "nmmo_terminated_ptr", "nmmo_truncated_ptr", "nmmo_mask_ptr",
     "nmmo_info_ptr", "nmmo_info_valid_ptr", "nmmo_episode_done_ptr", "nmmo_obs_stride", "nmmo_num_envs",
-    "nmmo_num_agents", "nmmo_inject_rng", "nmmo_snapshot", "nmmo_task_state", "nmmo_stats", "nmmo_check", "nmmo_timing", "nmmo_timing_read", "nmmo_profile", "nmmo_set_obs_full", "nmmo_set_autosample",
+    "nmmo_num_agents", "nmmo_step_kernel_name", "nmmo_obs_kernel_name", "nmmo_inject_rng", "nmmo_snapshot", "nmmo_task_state", "nmmo_stats", "nmmo_check", "nmmo_timing", "nmmo_timing_read", "nmmo_profile", "nmmo_set_obs_full", "nmmo_set_autosample",
     "nmmo_last_error",
     "nmmo_rollout_create", "nmmo_rollout_destroy", "nmmo_rollout_reset", "nmmo_rollout_store", "nmmo_rollout_ptr",
     "nmmo_rollout_gae", "nmmo_rollout_buffer", "nmmo_rollout_last_error",
@@ -71,6 +71,9 @@ def load(build_if_missing: bool = True):
         getattr(L, n).argtypes = [vp]
     for n in ("nmmo_obs_stride", "nmmo_num_envs", "nmmo_num_agents"):
         getattr(L, n).restype = C.c_int
+        getattr(L, n).argtypes = [vp]
+    for n in ("nmmo_step_kernel_name", "nmmo_obs_kernel_name"):
+        getattr(L, n).restype = C.c_char_p
         getattr(L, n).argtypes = [vp]
     L.nmmo_inject_rng.restype = C.c_int
     L.nmmo_inject_rng.argtypes = [vp, C.c_int, vp, vp, C.c_int]
@@ -282,6 +285,10 @@ class Simulator:
         counters = np.zeros(8, np.uint64)
         self._check(self.L.nmmo_stats(self.h, _p(sums), _p(counts), _p(counters), int(clear)))
         return sums, counts, counters
+
+    def kernel_names(self):
+        """(step kernel, observation kernel) instantiations this handle launches."""
+        return self.L.nmmo_step_kernel_name(self.h).decode(), self.L.nmmo_obs_kernel_name(self.h).decode()
 
     def check(self):
         """Raises NmmoError if any environment dropped events (event ring overflow) since the last stats clear."""
