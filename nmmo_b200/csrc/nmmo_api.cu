@@ -201,7 +201,10 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
     }
     {
       constexpr nm_obs_layout sl = nm_std_layout();
-      const bool std_shape = !b && memcmp(&p.L, &sl, sizeof(sl)) == 0 && p.P == StdShape::P && p.N == StdShape::N && p.R == StdShape::R &&
+      bool std_cfg = true;      // the engine defaults the *_std kernels fold in (nm_cfg_std_value)
+      for (int i = 0; i < NC_COUNT; i++)
+        if (nm_cfg_std_value(i) != NM_CFG_RUNTIME && p.cfg[i] != nm_cfg_std_value(i)) std_cfg = false;
+      const bool std_shape = std_cfg && !b && memcmp(&p.L, &sl, sizeof(sl)) == 0 && p.P == StdShape::P && p.N == StdShape::N && p.R == StdShape::R &&
                              p.S == StdShape::S && p.CAP == StdShape::CAP && p.cfg[NC_N_INV] == StdShape::NINV;
       h->obs_std = std_shape && p.ICAP == StdShape::ICAP && p.cfg[NC_VISION] == StdShape::VIS;
       h->step_std = std_shape && p.envs_per_cta == 3;
@@ -209,7 +212,7 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
       if (const char *ov = getenv("NMMO_B200_NO_STD_STEP")) { if (atoi(ov) == 1) h->step_std = false; }
       if (h->step_std) CU(cudaFuncSetAttribute(nmmo_step3_std_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_step));
       // big family: the configs[4] shape
-      h->big_std = b && memcmp(&p.L, &sl, sizeof(sl)) == 0 && p.P == StdShape5::P && p.N == StdShape5::N && p.R == StdShape5::R &&
+      h->big_std = std_cfg && b && memcmp(&p.L, &sl, sizeof(sl)) == 0 && p.P == StdShape5::P && p.N == StdShape5::N && p.R == StdShape5::R &&
                    p.S == StdShape5::S && p.CAP == StdShape5::CAP && p.cfg[NC_N_INV] == StdShape5::NINV && p.cfg[NC_VISION] == StdShape5::VIS;
       if (const char *ov = getenv("NMMO_B200_NO_STD_STEP")) { if (atoi(ov) == 1) h->big_std = false; }
       if (h->big_std) {

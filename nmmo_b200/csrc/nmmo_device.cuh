@@ -114,6 +114,100 @@ struct StdShape { static constexpr int P = 128, N = 256, R = 384, S = 160, CAP =
 struct StdShape5 { static constexpr int P = 1024, N = 2048, R = 3072, S = 544, CAP = 12288, ICAP = 0, NINV = 12, VIS = 7; };
 
 
+// Engine defaults of nmmo.core.config [UPSTREAM] that the reference's Config never overrides (environment.py:14-49 sets
+// PLAYER_N, NPC_N, HORIZON, MAP_*, TASK_EMBED_DIM, RESILIENT_POPULATION, SPAWN_IMMUNITY and the wrapper arguments only),
+// as compile-time constants for the *_std kernel instantiations.  nm_cfg_std_value(i) < 0x7fffffff for every folded
+// index; nmmo_create selects a *_std kernel only when the handle's vector equals this table at every folded index
+// (tests/test_host.py checks the table against nmmo_b200/config.py make_config()).
+#define NM_CFG_RUNTIME 0x7fffffff
+__host__ __device__ constexpr int nm_cfg_std_value(int i) {
+  switch (i) {
+    case NC_MAP_BORDER: return 16;
+    case NC_N_ENT_OBS: return 100;
+    case NC_N_MKT_OBS: return 384;
+    case NC_N_INV: return 12;
+    case NC_N_PRICE: return 99;
+    case NC_VISION: return 7;
+    case NC_TASK_DIM: return 2048;
+    case NC_NPC_VISION: return 5;
+    case NC_RES_BASE: return 100;
+    case NC_RES_DEPLETION: return 5;
+    case NC_RES_STARVATION: return 10;
+    case NC_RES_DEHYDRATION: return 10;
+    case NC_RES_REGEN_THRESH: return 50;
+    case NC_RES_HEALTH_RESTORE: return 10;
+    case NC_RES_HARVEST_RESTORE: return 100;
+    case NC_REACH: return 3;
+    case NC_FREEZE_TIME: return 3;
+    case NC_WEAK_NUM: return 3;
+    case NC_WEAK_DEN: return 2;
+    case NC_MINDMG_NUM: return 1;
+    case NC_MINDMG_DEN: return 4;
+    case NC_LEVEL_MAX: return 10;
+    case NC_XP_COMBAT: return 6;
+    case NC_XP_AMMO: return 15;
+    case NC_XP_CONSUMABLE: return 30;
+    case NC_BASE_DAMAGE: return 10;
+    case NC_LEVEL_DAMAGE: return 5;
+    case NC_BASE_DEFENSE: return 0;
+    case NC_LEVEL_DEFENSE: return 5;
+    case NC_EXP_THRESH0: return 0;
+    case NC_EXP_THRESH0 + 1: return 30;
+    case NC_EXP_THRESH0 + 2: return 72;
+    case NC_EXP_THRESH0 + 3: return 124;
+    case NC_EXP_THRESH0 + 4: return 184;
+    case NC_EXP_THRESH0 + 5: return 251;
+    case NC_EXP_THRESH0 + 6: return 324;
+    case NC_EXP_THRESH0 + 7: return 403;
+    case NC_EXP_THRESH0 + 8: return 488;
+    case NC_EXP_THRESH0 + 9: return 578;
+    case NC_NPC_SPAWN_ATTEMPTS: return 25;
+    case NC_NPC_AGGR_PCT: return 80;
+    case NC_NPC_NEUT_PCT: return 50;
+    case NC_NPC_PASS_PCT: return 0;
+    case NC_NPC_LEVEL_MIN: return 1;
+    case NC_NPC_LEVEL_MAX: return 10;
+    case NC_NPC_BASE_DEFENSE: return 0;
+    case NC_NPC_LEVEL_DEFENSE: return 15;
+    case NC_NPC_BASE_DAMAGE: return 15;
+    case NC_NPC_LEVEL_DAMAGE: return 15;
+    case NC_WEAPON_DROP_THR: return 107374182;
+    case NC_WEAPON_BASE: return 5;
+    case NC_WEAPON_LEVEL: return 5;
+    case NC_AMMO_BASE: return 5;
+    case NC_AMMO_LEVEL: return 10;
+    case NC_TOOL_BASE: return 15;
+    case NC_TOOL_LEVEL: return 0;
+    case NC_ARMOR_BASE: return 0;
+    case NC_ARMOR_LEVEL: return 3;
+    case NC_RESTORE_BASE: return 50;
+    case NC_RESTORE_LEVEL: return 5;
+    case NC_RESPAWN_FOILAGE: return 107374182;
+    case NC_RESPAWN_ORE: return 429496729;
+    case NC_RESPAWN_TREE: return 450971566;
+    case NC_RESPAWN_CRYSTAL: return 429496729;
+    case NC_RESPAWN_HERB: return 85899345;
+    case NC_RESPAWN_FISH: return 85899345;
+    case NC_BASE_GOLD: return 1;
+    case NC_LISTING_DURATION: return 3;
+    default: return NM_CFG_RUNTIME;      // shape entries (PLAYER_N, NPC_N, MAP_CENTER, MAP_SIZE, ITEM_CAP), HORIZON, RESILIENT_N,
+                                         // SPAWN_IMMUNITY, ALLOW_OCCUPIED, the wrapper arguments and the workload knobs stay run-time
+  }
+}
+// The config vector as the kernels see it: c[NC_X] with a literal index folds to the constant in a *_std instantiation
+// (the accessor is inlined, the switch above disappears); c.p[...] is the plain vector for run-time indices.
+template <bool STD>
+struct NmCfg {
+  const int32_t *p;
+  __host__ __device__ __forceinline__ int operator[](int i) const {
+#ifdef NM_NO_CFG_FOLD
+    return p[i];
+#else
+    return (STD && nm_cfg_std_value(i) != NM_CFG_RUNTIME) ? nm_cfg_std_value(i) : p[i];
+#endif
+  }
+};
+
 // ------------------------------------------------------------------------- rng ------
 __host__ __device__ __forceinline__ uint64_t nm_mix64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ULL;
@@ -178,18 +272,21 @@ __device__ __forceinline__ bool it_ammo(int t) { return t >= IT_WHETSTONE && t <
 __device__ __forceinline__ bool it_consumable(int t) { return t == IT_RATION || t == IT_POTION; }
 
 // derived item columns (nmmo/systems/item.py constructors [UPSTREAM])
-__device__ __forceinline__ int item_attack(const int32_t *c, int type, int level, int style) {
+template <class C>
+__device__ __forceinline__ int item_attack(const C &c, int type, int level, int style) {
   if (it_weapon(type) && type - IT_SPEAR == style) return c[NC_WEAPON_BASE] + level * c[NC_WEAPON_LEVEL];
   if (it_ammo(type) && type - IT_WHETSTONE == style) return c[NC_AMMO_BASE] + level * c[NC_AMMO_LEVEL];
   return 0;
 }
-__device__ __forceinline__ int item_defense(const int32_t *c, int type, int level) {
+template <class C>
+__device__ __forceinline__ int item_defense(const C &c, int type, int level) {
   if (it_armor(type)) return c[NC_ARMOR_BASE] + level * c[NC_ARMOR_LEVEL];
   if (it_tool(type)) return c[NC_TOOL_BASE] + level * c[NC_TOOL_LEVEL];
   return 0;
 }
 // full 16-column observed item row
-__device__ __forceinline__ void item_obs_row(const int32_t *c, int row, int type, int level, int owner, int qty,
+template <class C>
+__device__ __forceinline__ void item_obs_row(const C &c, int row, int type, int level, int owner, int qty,
                                              int equipped, int price, int16_t out[IA_N_OBS]) {
 #pragma unroll
   for (int k = 0; k < IA_N_OBS; k++) out[k] = 0;

@@ -80,7 +80,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
   // small: one CTA per env, all of its agents; big: AP agents per CTA, parts CTAs per env
-  const int32_t *c = prm.cfg;
+  const NmCfg<V::kStd> c{prm.cfg};
   // record layout and table shape: immediates in the std instantiation, run-time values otherwise
   typedef typename V::Shape SH;
   constexpr nm_obs_layout kStdL = nm_std_layout();
@@ -167,7 +167,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   OPHASE();      // 32 load
 
   OCtx o;
-  o.p = &prm; o.c = c; o.R = R; o.S = S; o.CAP = CAP; o.ICAP = ICAP; o.P = P; o.NINV = NINV;
+  o.p = &prm; o.c = prm.cfg; o.R = R; o.S = S; o.CAP = CAP; o.ICAP = ICAP; o.P = P; o.NINV = NINV;
   o.gitem = prm.item + (size_t)env * IS_N * CAP;
   o.ent = V::kStage ? s_ent : g_ent; o.status = s_status; o.item = s_item; o.map = s_map;
   const int wrapper = c[NC_WRAPPER];

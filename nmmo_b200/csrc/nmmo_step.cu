@@ -82,7 +82,7 @@ template <class V>
 struct Ctx {
   typedef typename V::tile_t tile_t;
   const NmParams *p;
-  const int32_t *c;
+  NmCfg<V::kStd> c;          // config vector (engine defaults folded in a *_std instantiation)
   int env, P, N, R, S, CAP, NINV;
   int16_t *ent, *item;
   uint32_t *map;            // 4-bit materials, 8 tiles per word
@@ -254,16 +254,16 @@ __device__ __forceinline__ bool ent_alive(const Ctx<V> &ctx, int row) {
 template <class V>
 __device__ int level_at_exp(const Ctx<V> &ctx, int exp) {
   int lmax = ctx.c[NC_LEVEL_MAX];
-  if (exp >= ctx.c[NC_EXP_THRESH0 + lmax - 1]) return lmax;
+  if (exp >= ctx.c.p[NC_EXP_THRESH0 + lmax - 1]) return lmax;
   int lvl = 0;
   #pragma unroll 1
-  while (lvl < lmax && exp >= ctx.c[NC_EXP_THRESH0 + lvl]) lvl++;
+  while (lvl < lmax && exp >= ctx.c.p[NC_EXP_THRESH0 + lvl]) lvl++;
   return lvl;
 }
 template <class V>
 __device__ void add_xp(const Ctx<V> &ctx, int row, int level_col, int skill_id, int xp) {
   int lmax = ctx.c[NC_LEVEL_MAX];
-  int nexp = min(ENT(level_col + 1, row) + xp, ctx.c[NC_EXP_THRESH0 + lmax - 1]);
+  int nexp = min(ENT(level_col + 1, row) + xp, ctx.c.p[NC_EXP_THRESH0 + lmax - 1]);
   ENT(level_col + 1, row) = (int16_t)nexp;
   int nl = level_at_exp(ctx, nexp);
   if (nl > ENT(level_col, row)) {
@@ -630,7 +630,7 @@ __device__ void act_give_gold(const Ctx<V> &ctx, int p, int amount, int target_r
 // pure part of combat.attack / Attack.call: validity and damage, no side effects
 template <class V>
 __device__ bool attack_compute(const Ctx<V> &ctx, int a, int style, int t, int &dmg, bool &ammo_out) {
-  const int32_t *c = ctx.c;
+  const NmCfg<V::kStd> c = ctx.c;
   bool a_player = a < ctx.P, b_player = t < ctx.P;
   if (a_player && b_player && ENT(EA_TIME_ALIVE, t) < c[NC_SPAWN_IMMUNITY]) return false;
   if (!ent_alive(ctx, t)) return false;
@@ -671,7 +671,7 @@ __device__ bool attack_compute(const Ctx<V> &ctx, int a, int style, int t, int &
 // side effects of one attack whose damage is known (attacker a, target row t)
 template <class V>
 __device__ void attack_apply(const Ctx<V> &ctx, int a, int style, int t, int dmg) {
-  const int32_t *c = ctx.c;
+  const NmCfg<V::kStd> c = ctx.c;
   bool a_player = a < ctx.P, b_player = t < ctx.P;
   int a_id = ENT(EA_ID, a), b_id = ENT(EA_ID, t);
   int lcol = EA_MELEE_LEVEL + 2 * style;
@@ -761,7 +761,7 @@ __device__ int border_dist(const Ctx<V> &ctx, int r, int c) {
 // 25) attempts and records the accepted ones; the rows are then filled in by one thread each
 template <class V>
 __device__ int npc_spawn_decide(const Ctx<V> &ctx, uint32_t *dec, const int *free_rows, const int *dng) {       // single thread
-  const int32_t *c = ctx.c;
+  const NmCfg<V::kStd> c = ctx.c;
   int b = c[NC_MAP_BORDER], ce = c[NC_MAP_CENTER];
   int count = ctx.sc[4];
   int n = 0;
@@ -809,7 +809,7 @@ __device__ int npc_spawn_decide(const Ctx<V> &ctx, uint32_t *dec, const int *fre
 }
 template <class V>
 __device__ void npc_spawn_fill(const Ctx<V> &ctx, const uint32_t *q) {
-  const int32_t *c = ctx.c;
+  const NmCfg<V::kStd> c = ctx.c;
   int ce = c[NC_MAP_CENTER];
   int row = (int)q[0], r = (int)q[1], cc = (int)q[2], d = (int)q[3], type = (int)q[4], att = (int)q[5];
   int style = nm_bounded(ctx.predraw[att * 8 + 2], 3);
@@ -825,7 +825,7 @@ __device__ void npc_spawn_fill(const Ctx<V> &ctx, const uint32_t *q) {
   ENT(EA_HEALTH, row) = (int16_t)c[NC_RES_BASE]; ENT(EA_FOOD, row) = (int16_t)c[NC_RES_BASE]; ENT(EA_WATER, row) = (int16_t)c[NC_RES_BASE];
   for (int s = 0; s < 3; s++) ENT(EA_MELEE_LEVEL + 2 * s, row) = 1;
   ENT(EA_MELEE_LEVEL + 2 * style, row) = (int16_t)level;
-  ENT(EA_MELEE_EXP + 2 * style, row) = (int16_t)c[NC_EXP_THRESH0 + level - 1];
+  ENT(EA_MELEE_EXP + 2 * style, row) = (int16_t)c.p[NC_EXP_THRESH0 + level - 1];
   ENT(EA_ITEM_LEVEL, row) = (int16_t)((5LL * lvl_fp) >> 16);
   ENT(EA_NPC_STYLE, row) = (int16_t)style; ENT(EA_NPC_DANGER, row) = (int16_t)d;
   ENT(EA_NPC_OFFENSE, row) = (int16_t)(c[NC_NPC_BASE_DAMAGE] + (int)(((int64_t)lvl_fp * c[NC_NPC_LEVEL_DAMAGE]) >> 16));
@@ -1135,7 +1135,7 @@ __device__ NM_RESET_INLINE void reset_env(const NmParams &P_, int env, uint64_t 
   int32_t *sc = P_.scalars + (size_t)env * NM_SC_N;
   // injected draws are keyed by tick 0 here
   Ctx<V> ctx;
-  ctx.p = &P_; ctx.c = c; ctx.env = env; ctx.seed = seed; ctx.tick = 0;
+  ctx.p = &P_; ctx.c = NmCfg<V::kStd>{c}; ctx.env = env; ctx.seed = seed; ctx.tick = 0;
   ctx.inj_lo = P_.inj_off ? P_.inj_off[env] : 0; ctx.inj_hi = P_.inj_off ? P_.inj_off[env + 1] : 0;
   int map_id = explicit_map ? sc[SC_MAP_ID] : nm_bounded(draw(ctx, RS_MAP, 0, 0), P_.n_maps);
   // map copy, table clears
@@ -1252,7 +1252,7 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
   const int half = threadIdx.x / V::kThreads;
   uint8_t *smem = smem_all + (size_t)half * prm.half_smem;
   const int env = blockIdx.x * prm.envs_per_cta + half, tid = threadIdx.x % V::kThreads, T = V::kThreads, lane = tid & 31, warp = tid >> 5;
-  const int32_t *c = prm.cfg;
+  const NmCfg<V::kStd> c{prm.cfg};
   constexpr nm_obs_layout kStdL = nm_std_layout();
   typedef typename V::Shape SH;
   const int P = V::kStd ? SH::P : prm.P, N = V::kStd ? SH::N : prm.N, R = V::kStd ? SH::R : prm.R;
@@ -2000,7 +2000,7 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
     auto respawn_tile = [&](int i, int m) {
       int thr_idx = m == MT_SCRUB ? NC_RESPAWN_FOILAGE : m == MT_SLAG ? NC_RESPAWN_ORE : m == MT_STUMP ? NC_RESPAWN_TREE
                   : m == MT_FRAGMENT ? NC_RESPAWN_CRYSTAL : m == MT_WEEDS ? NC_RESPAWN_HERB : NC_RESPAWN_FISH;
-      if (draw(ctx, RS_RESPAWN, (uint32_t)i, 0) < (uint32_t)c[thr_idx]) tile_inc(ctx, i);
+      if (draw(ctx, RS_RESPAWN, (uint32_t)i, 0) < (uint32_t)c.p[thr_idx]) tile_inc(ctx, i);
     };
     // The depleted tiles are known: the list carried over from last tick plus this tick's harvests (tile_dec).
     // Only when the list is unknown (first use after an overflow) is the map scanned to rebuild it.
@@ -2071,7 +2071,7 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
         const int m = tile_i(ctx, i);
         const int thr_idx = m == MT_SCRUB ? NC_RESPAWN_FOILAGE : m == MT_SLAG ? NC_RESPAWN_ORE : m == MT_STUMP ? NC_RESPAWN_TREE
                           : m == MT_FRAGMENT ? NC_RESPAWN_CRYSTAL : m == MT_WEEDS ? NC_RESPAWN_HERB : NC_RESPAWN_FISH;
-        if (draw(ctx, RS_RESPAWN, (uint32_t)i, 0) < (uint32_t)c[thr_idx]) tile_inc(ctx, i); else stays = true;
+        if (draw(ctx, RS_RESPAWN, (uint32_t)i, 0) < (uint32_t)c.p[thr_idx]) tile_inc(ctx, i); else stays = true;
       }
       const unsigned sm = __ballot_sync(0xffffffffu, stays);
       int base = 0;

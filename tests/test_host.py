@@ -149,3 +149,26 @@ def test_pack_actions_u8_layout():
         assert np.array_equal(back[1:, :, k], a[1:, :, k])
     assert buy[0, 0] >= dims[2] and style[0, 0] == 3 and (back[0, 0, 1:] == 255).all()
     assert np.array_equal(pack_actions_u8(torch.from_numpy(a)).numpy(), pk)
+
+
+def test_std_cfg_table_matches_the_python_defaults():
+    """nm_cfg_std_value (csrc/nmmo_device.cuh): the engine defaults the *_std kernel instantiations fold to immediates must be
+    the values nmmo_b200/config.py produces; entries the reference's Config or wrappers set stay run-time."""
+    import re
+    from pathlib import Path
+    from nmmo_b200.config import SPEC, make_config
+    text = (Path(__file__).resolve().parent.parent / "nmmo_b200" / "csrc" / "nmmo_device.cuh").read_text()
+    body = text[text.index("constexpr int nm_cfg_std_value"):text.index("default: return NM_CFG_RUNTIME")]
+    table = {}
+    for name, off, val in re.findall(r"case (NC_\w+)(?: \+ (\d+))?: return (-?\d+);", body):
+        table[SPEC[name] + int(off or 0)] = int(val)
+    assert len(table) > 60
+    for agent in ("takeru", "neurips23_start_kit", "yaofeng"):
+        cfg, _ = make_config(agent=agent)
+        for i, v in table.items():
+            assert int(cfg[i]) == v, (agent, i, v, int(cfg[i]))
+    runtime = {"NC_N_PLAYERS", "NC_N_NPCS", "NC_MAP_CENTER", "NC_MAP_SIZE", "NC_ITEM_CAP", "NC_HORIZON", "NC_RES_RESILIENT_N",
+               "NC_SPAWN_IMMUNITY", "NC_ALLOW_OCCUPIED", "NC_WRAPPER", "NC_EARLY_STOP_N", "NC_EVAL_MODE", "NC_USE_CUSTOM_REWARD",
+               "NC_CLIP_UNIQUE", "NC_DISABLE_GIVE", "NC_NO_DANGEROUS_NPC", "NC_SPAWN_PATCH", "NC_TEAM_SIZE", "NC_SAMPLE_MOVE_PCT"}
+    assert not ({SPEC[n] for n in runtime} & set(table)), "an entry the reference sets per run must not be folded"
+    assert set(table) | {SPEC[n] for n in runtime} == set(range(SPEC["NC_COUNT"]))

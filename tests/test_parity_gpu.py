@@ -140,6 +140,18 @@ def test_default_config_full_size():
     sim.close()
 
 
+@pytest.mark.parametrize("over,std", [(dict(), True), (dict(NC_RES_DEPLETION=3, NC_REACH=4), False), (dict(NC_N_ENT_OBS=60), False),
+                                      (dict(NC_SPAWN_IMMUNITY=2, NC_HORIZON=100, NC_EARLY_STOP_N=4), True)])
+def test_default_shape_std_and_generic_kernels(over, std):
+    # the reference's default shape runs the compile-time-shape kernels (engine defaults folded); an engine override or another
+    # record layout on the same shape must fall back to the generic instantiation -- and both must match the oracle
+    world = build_world(**over)
+    sim, oracles = _make(world, 3)
+    assert ("_std" in sim.kernel_names()[0]) == std and ("_std" in sim.kernel_names()[1]) == std, sim.kernel_names()
+    run_parity(sim, oracles, seeds=np.array([5, 6, 7]), ticks=110, check_state_every=36)
+    sim.close()
+
+
 @pytest.mark.parametrize("P,N,center,E,over", [
     (8, 16, 24, 7, dict(NC_RES_DEPLETION=1, NC_SPAWN_IMMUNITY=1)),                      # tiny, odd env count
     (40, 120, 48, 5, dict(NC_RES_DEPLETION=2, NC_NPC_SPAWN_ATTEMPTS=32)),              # more NPCs than threads / 2
