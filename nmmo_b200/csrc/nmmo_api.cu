@@ -73,7 +73,7 @@ static size_t obs_big_smem_bytes(const NmParams &p) {
   s += a16((size_t)AP * NINV * 2); s += a16((size_t)AP * 4); s += a16(64 * 4);
   s += a16((size_t)NW * a16(p.L.m_end)); s += a16((size_t)NW * a16((size_t)p.L.n_ent * 2)); s += 16;
   s += a16((size_t)NW * 72 * 4); s += a16((2 * AC_N + 2) * 4); s += a16((size_t)AP * 4); s += a16((size_t)AP * 2); s += a16((size_t)((p.R + 31) & ~31) * 4); s += a16(a16(p.L.m_end));
-  s += obs_cell_bytes(p, NW) + 64 * 4;
+  s += obs_cell_bytes(p, NW) + 64 * 4 + a16((size_t)AP * 8);
   return s + 128;
 }
 
@@ -96,7 +96,7 @@ static size_t obs_smem_bytes(const NmParams &p) {
   s += a16((size_t)p.P * NINV * 2); s += a16((size_t)p.P * 4); s += a16(64 * 4);
   s += a16((size_t)NW * a16(p.L.m_end)); s += a16((size_t)NW * a16((size_t)p.L.n_ent * 2)); s += 16;
   s += a16((size_t)NW * 72 * 4); s += a16((2 * AC_N + 2) * 4); s += a16((size_t)p.P * 4); s += a16((size_t)p.P * 2); s += a16((size_t)((p.R + 31) & ~31) * 4); s += a16(a16(p.L.m_end));
-  s += obs_cell_bytes(p, NW) + 64 * 4;
+  s += obs_cell_bytes(p, NW) + 64 * 4 + a16((size_t)p.P * 8);
   return s + 128;
 }
 
@@ -138,7 +138,7 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   nm_obs_layout_init(p.cfg, &p.L);
   p.E = n_envs; p.P = cfg[NC_N_PLAYERS]; p.N = cfg[NC_N_NPCS]; p.R = p.P + p.N; p.S = cfg[NC_MAP_SIZE]; p.CAP = cfg[NC_ITEM_CAP];
   p.n_maps = n_maps; p.n_tasks = n_tasks; p.env_base = env_base;
-  p.ICAP = std::min(p.CAP, 384);      // item rows the observation kernel keeps in shared memory; rows beyond are read in HBM
+  p.ICAP = std::min(p.CAP, 256);      // item rows the observation kernel keeps in shared memory; rows beyond are read in HBM
   if (const char *ov = getenv("NMMO_B200_ICAP")) {      // test hook: force the HBM tail path with a tiny staged prefix
     int v = atoi(ov);
     if (v >= 8 && v % 8 == 0) p.ICAP = std::min(p.CAP, v);

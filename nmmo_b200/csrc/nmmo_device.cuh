@@ -109,7 +109,7 @@ __host__ __device__ constexpr nm_obs_layout nm_std_layout() {
   L.stride = (o + 127) & ~127;
   return L;
 }
-struct StdShape { static constexpr int P = 128, N = 256, R = 384, S = 160, CAP = 1536, ICAP = 384, NINV = 12, VIS = 7; };
+struct StdShape { static constexpr int P = 128, N = 256, R = 384, S = 160, CAP = 1536, ICAP = 256, NINV = 12, VIS = 7; };
 // ... and the shape of BASELINE.json configs[4] (1024 players, 2048 NPCs, 544^2 map; same record layout) for the big family
 struct StdShape5 { static constexpr int P = 1024, N = 2048, R = 3072, S = 544, CAP = 12288, ICAP = 0, NINV = 12, VIS = 7; };
 

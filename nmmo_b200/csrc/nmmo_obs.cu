@@ -66,6 +66,15 @@ __device__ __forceinline__ int o_use_level(const OCtx &o, int row, int type) {
     }
   }
 }
+// position of the r-th (0-based) set bit of x (r < popc(x)): five popc steps instead of the software loop behind __fns
+__device__ __forceinline__ int nth_set_bit(uint32_t x, int r) {
+  int pos = 0, c;
+  c = __popc(x & 0xffffu); if (r >= c) { r -= c; pos += 16; x >>= 16; }
+  c = __popc(x & 0xffu);   if (r >= c) { r -= c; pos += 8;  x >>= 8; }
+  c = __popc(x & 0xfu);    if (r >= c) { r -= c; pos += 4;  x >>= 4; }
+  c = __popc(x & 0x3u);    if (r >= c) { r -= c; pos += 2;  x >>= 2; }
+  return pos + ((r >= (int)(x & 1u)) ? 1 : 0);
+}
 __device__ __forceinline__ void st16(uint8_t *dst, uint4 v) { __stcs((uint4 *)dst, v); }
 __device__ __forceinline__ uint32_t pack2(int a, int b) { return (uint32_t)(uint16_t)a | ((uint32_t)(uint16_t)b << 16); }
 
@@ -127,6 +136,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   uint32_t *s_vbm_all = (uint32_t *)carve((size_t)NW * RW * 4);      // per warp: bitmap of the rows inside the agent's window
   uint8_t *s_tmpl = carve(stage_bytes);                      // agent-independent part of the masks
   int *s_head = (int *)carve((2 * AC_N + 2) * 4);       // + work-list length and cursor
+  uint64_t *s_hash = (uint64_t *)carve((size_t)AP * 8);     // built-in policy: one 64-bit draw per agent, computed by one thread each
   uint32_t *s_meta = (uint32_t *)carve((size_t)AP * 4);
   uint16_t *s_work = (uint16_t *)carve((size_t)AP * 2);
   uint64_t *bar = (uint64_t *)carve(16);
@@ -159,6 +169,10 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   for (int i = tid; i < p_hi - p_lo; i += T) { s_invn[i] = 0; s_meta[i] = prm.obs_meta[(size_t)env * P + p_lo + i]; }
   #pragma unroll 1
   for (int i = tid; i <= n_cells; i += T) s_cend[i] = 0;
+  if (prm.sample_out)      // (the whole warp would otherwise compute the same hash for its agent, 128 times per CTA)
+    #pragma unroll 1
+    for (int i = tid; i < p_hi - p_lo; i += T)
+      s_hash[i] = nm_hash64(prm.sample_seed + (uint64_t)(prm.env_base + env), (uint32_t)tick, RS_ACTION, (uint32_t)(p_lo + i), 0);
   if (V::kStage) {
     while (!mbar_try_wait(bar, 0)) {}
     while (!mbar_try_wait(bar + 1, 0)) {}
@@ -348,15 +362,35 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     auto in_window = [&](uint32_t pos) -> bool {
       return (uint32_t)((int)(pos >> 16) - r0) <= (uint32_t)(2 * vis) && (uint32_t)((int)(pos & 0xffffu) - c0) <= (uint32_t)(2 * vis);
     };
+    // the rows listed in the (at most 2 x 2) cells under the window: two contiguous ranges of the cell-ordered row list
+    const int cr0 = max(r0 - vis, 0) / NM_OBS_CELL, cr1 = min(r0 + vis, S - 1) / NM_OBS_CELL;
+    const int cc0 = max(c0 - vis, 0) / NM_OBS_CELL, cc1 = min(c0 + vis, S - 1) / NM_OBS_CELL;
+    int begA = 0, endA = 0, begB = 0, endB = 0;
     if (use_cells) {
-      // the rows listed in the (at most 2 x 2) cells under the window are tested and marked in a row bitmap; walking the
-      // bitmap then yields them in table order
+      const int ca = cr0 * ncx + cc0;
+      begA = ca ? s_cend[ca - 1] : 0; endA = s_cend[cr0 * ncx + cc1];
+      if (cr1 > cr0) { const int cb = cr1 * ncx + cc0; begB = s_cend[cb - 1]; endB = s_cend[cr1 * ncx + cc1]; }
+    }
+    const int nA = endA - begA, n_cand = nA + endB - begB;
+    if (use_cells && n_cand <= 32) {
+      // the common case: one candidate per lane; a hit's place in table order is the number of hits with a smaller row
+      int row = 0x7fffffff;
+      if (lane < n_cand) {
+        const int r = s_crow[lane < nA ? begA + lane : begB + lane - nA];
+        if (in_window(s_pos[r])) row = r;
+      }
+      unsigned hits = __ballot_sync(0xffffffffu, row != 0x7fffffff);
+      n_vis = __popc(hits);
+      int rank = 0;
+      #pragma unroll 1
+      for (unsigned h = hits; h; h &= h - 1) rank += __shfl_sync(0xffffffffu, row, __ffs(h) - 1) < row;
+      if (row != 0x7fffffff && rank < L.n_ent) s_vis[rank] = (uint16_t)row;
+    } else if (use_cells) {
+      // many candidates: they are tested and marked in a row bitmap; walking the bitmap yields them in table order
       uint32_t *vbm = s_vbm_all + warp * RW;
       #pragma unroll 1
       for (int w = lane; w < RW; w += 32) vbm[w] = 0;
       __syncwarp();
-      const int cr0 = max(r0 - vis, 0) / NM_OBS_CELL, cr1 = min(r0 + vis, S - 1) / NM_OBS_CELL;
-      const int cc0 = max(c0 - vis, 0) / NM_OBS_CELL, cc1 = min(c0 + vis, S - 1) / NM_OBS_CELL;
       #pragma unroll 1
       for (int cr = cr0; cr <= cr1; cr++) {                  // the cells of one cell row are adjacent in the list
         const int ca = cr * ncx + cc0;
@@ -492,7 +526,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
       }
       __syncwarp();
       if (lane < AC_N) {
-        const uint64_t base64 = nm_hash64(prm.sample_seed + (uint64_t)(prm.env_base + env), (uint32_t)tick, RS_ACTION, (uint32_t)p, 0);
+        const uint64_t base64 = s_hash[p - p_lo];
         const int o0 = s_head[lane];
         int o1 = o0 + s_head[AC_N + lane];
         bool stay = false;
@@ -520,7 +554,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
             const int t = rk0 + nm_bounded(nm_action_draw(base64, lane), total);
             int lo = w0, hi = w1;
             while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((int)cum[mid] <= t) lo = mid; else hi = mid - 1; }
-            pick = lo * 32 + (int)__fns(bits[lo], 0, t - (int)cum[lo] + 1) - o0;
+            pick = lo * 32 + nth_set_bit(bits[lo], t - (int)cum[lo]) - o0;
           }
           prm.sample_out[a * AC_N + lane] = pick;
         } else {
