@@ -328,10 +328,16 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     return __funnelshift_r(s_map[w], s_map[w + 1], sh);
   };
   long long w_t0 = clock64();
-  for (;;) {
-    int wi = 0;
-    if (lane == 0) wi = atomicAdd(&s_head[2 * AC_N + 1], 1);
-    wi = __shfl_sync(0xffffffffu, wi, 0);
+  // Work items are dealt round-robin when most agents are alive (items of equal cost: no queue traffic) and pulled from a
+  // shared cursor otherwise (a zero fill is much cheaper than a record, so a static deal would leave warps idle)
+  const bool deal = 2 * n_work > AP;
+  #pragma unroll 1
+  for (int it = 0;; it++) {
+    int wi = warp + it * NW;
+    if (!deal) {
+      if (lane == 0) wi = atomicAdd(&s_head[2 * AC_N + 1], 1);
+      wi = __shfl_sync(0xffffffffu, wi, 0);
+    }
     if (wi >= n_work) break;
     const int went = s_work[wi];
     const int p = went & 0x7fff;
