@@ -281,9 +281,11 @@ static int launch_step(nmmo_handle *h, int mode, cudaStream_t st, cudaEvent_t af
     CU(cudaEventRecord(e3[0], st));
   }
   const int epc = h->prm.envs_per_cta;
-  if (prm.big && h->big_std) nmmo_step_big_std_kernel<<<prm.E, NM_BIG_THREADS, (size_t)prm.half_smem, st>>>(prm);
+  // the *_std instantiations have no profile counters and no injected-draw lookup
+  const bool lean_ok = !prm.prof && !prm.inj_off;
+  if (prm.big && h->big_std && lean_ok) nmmo_step_big_std_kernel<<<prm.E, NM_BIG_THREADS, (size_t)prm.half_smem, st>>>(prm);
   else if (prm.big) nmmo_step_big_kernel<<<prm.E, NM_BIG_THREADS, (size_t)prm.half_smem, st>>>(prm);
-  else if (epc == 3 && h->step_std) nmmo_step3_std_kernel<<<(prm.E + 2) / 3, 3 * NM_STEP_THREADS, (size_t)3 * prm.half_smem, st>>>(prm);
+  else if (epc == 3 && h->step_std && lean_ok) nmmo_step3_std_kernel<<<(prm.E + 2) / 3, 3 * NM_STEP_THREADS, (size_t)3 * prm.half_smem, st>>>(prm);
   else if (epc == 3) nmmo_step3_kernel<<<(prm.E + 2) / 3, 3 * NM_STEP_THREADS, (size_t)3 * prm.half_smem, st>>>(prm);
   else nmmo_step_kernel<<<(prm.E + epc - 1) / epc, epc * NM_STEP_THREADS, (size_t)epc * prm.half_smem, st>>>(prm);
   CU(cudaGetLastError());
@@ -291,9 +293,9 @@ static int launch_step(nmmo_handle *h, int mode, cudaStream_t st, cudaEvent_t af
   if (after_step) CU(cudaEventRecord(after_step, st));      // rewards / flags / mask are final here
   if (prm.big) {
     const int ap = std::min(prm.P, NM_BIG_OBS_AGENTS), parts = (prm.P + ap - 1) / ap;
-    if (h->big_std) nmmo_obs_big_std_kernel<<<prm.E * parts, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
+    if (h->big_std && !prm.prof) nmmo_obs_big_std_kernel<<<prm.E * parts, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
     else nmmo_obs_big_kernel<<<prm.E * parts, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
-  } else if (h->obs_std) nmmo_obs_std_kernel<<<prm.E, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
+  } else if (h->obs_std && !prm.prof) nmmo_obs_std_kernel<<<prm.E, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
   else nmmo_obs_kernel<<<prm.E, NM_OBS_THREADS, h->obs_smem, st>>>(prm);
   CU(cudaGetLastError());
   if (e3) CU(cudaEventRecord(e3[2], st));
@@ -501,13 +503,14 @@ extern "C" void *nmmo_info_valid_ptr(nmmo_handle *h) { return h->prm.info_valid;
 extern "C" void *nmmo_episode_done_ptr(nmmo_handle *h) { return h->prm.episode_done; }
 // which instantiation this handle launches (bench / profiling: kernel names as ncu lists them)
 extern "C" const char *nmmo_step_kernel_name(nmmo_handle *h) {
-  if (h->prm.big) return h->big_std ? "nmmo_step_big_std_kernel" : "nmmo_step_big_kernel";
-  if (h->prm.envs_per_cta == 3) return h->step_std ? "nmmo_step3_std_kernel" : "nmmo_step3_kernel";
+  const bool lean_ok = !h->prm.prof && !h->prm.inj_off;      // same rule as launch_step
+  if (h->prm.big) return (h->big_std && lean_ok) ? "nmmo_step_big_std_kernel" : "nmmo_step_big_kernel";
+  if (h->prm.envs_per_cta == 3) return (h->step_std && lean_ok) ? "nmmo_step3_std_kernel" : "nmmo_step3_kernel";
   return "nmmo_step_kernel";
 }
 extern "C" const char *nmmo_obs_kernel_name(nmmo_handle *h) {
-  if (h->prm.big) return h->big_std ? "nmmo_obs_big_std_kernel" : "nmmo_obs_big_kernel";
-  return h->obs_std ? "nmmo_obs_std_kernel" : "nmmo_obs_kernel";
+  if (h->prm.big) return (h->big_std && !h->prm.prof) ? "nmmo_obs_big_std_kernel" : "nmmo_obs_big_kernel";
+  return (h->obs_std && !h->prm.prof) ? "nmmo_obs_std_kernel" : "nmmo_obs_kernel";
 }
 extern "C" int nmmo_obs_stride(nmmo_handle *h) { return h->prm.L.stride; }
 extern "C" int nmmo_num_envs(nmmo_handle *h) { return h->prm.E; }

@@ -188,10 +188,11 @@ __host__ __device__ constexpr int nm_cfg_std_value(int i) {
     case NC_RESPAWN_CRYSTAL: return 429496729;
     case NC_RESPAWN_HERB: return 85899345;
     case NC_RESPAWN_FISH: return 85899345;
+    case NC_ALLOW_OCCUPIED: return 0;      // one entity per tile; the reference's Config never sets it
     case NC_BASE_GOLD: return 1;
     case NC_LISTING_DURATION: return 3;
     default: return NM_CFG_RUNTIME;      // shape entries (PLAYER_N, NPC_N, MAP_CENTER, MAP_SIZE, ITEM_CAP), HORIZON, RESILIENT_N,
-                                         // SPAWN_IMMUNITY, ALLOW_OCCUPIED, the wrapper arguments and the workload knobs stay run-time
+                                         // SPAWN_IMMUNITY, the wrapper arguments and the workload knobs stay run-time
   }
 }
 // The config vector as the kernels see it: c[NC_X] with a literal index folds to the constant in a *_std instantiation

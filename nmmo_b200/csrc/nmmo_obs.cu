@@ -143,7 +143,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
 
   long long t_prev = clock64();
   int ph = 32;
-#define OPHASE() do { if (prm.prof && tid == 0) { long long t_ = clock64(); atomicAdd(&prm.prof[ph], (unsigned long long)(t_ - t_prev)); t_prev = t_; } ph++; } while (0)
+#define OPHASE() do { if (!V::kStd && prm.prof && tid == 0) { long long t_ = clock64(); atomicAdd(&prm.prof[ph], (unsigned long long)(t_ - t_prev)); t_prev = t_; } ph++; } while (0)
   if (V::kStage && tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   const int item_hi = prm.scalars[(size_t)env * NM_SC_N + SC_ITEM_HI];     // rows >= item_hi are free
   if (tid < AC_N) {
@@ -686,7 +686,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     if (lane == 0) prm.obs_meta[a] = (uint32_t)n_vis | ((uint32_t)n_inv << 8) | OM_NONZERO | OM_TASK | ((uint32_t)n_mkt << 18);
     __syncwarp();
   }
-  if (prm.prof && lane == 0) {
+  if (!V::kStd && prm.prof && lane == 0) {
     long long t_ = clock64();
     atomicAdd(&prm.prof[40], (unsigned long long)(t_ - w_t0));          // warp-busy cycles in the record loop
     atomicMax(&prm.prof[41 + (blockIdx.x & 7)], (unsigned long long)(t_ - w_t0));

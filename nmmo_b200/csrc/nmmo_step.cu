@@ -129,6 +129,7 @@ __device__ __forceinline__ uint32_t draw_impl(const uint64_t *inj_keys, const ui
 }
 template <class V>
 __device__ __forceinline__ uint32_t draw(const Ctx<V> &ctx, uint32_t site, uint32_t idx, uint32_t k) {
+  if (V::kStd) return nm_hash_draw(ctx.seed, (uint32_t)ctx.tick, site, idx, k);      // no injected draws in a *_std instantiation
   return draw_impl(ctx.p->inj_keys, ctx.p->inj_vals, ctx.inj_lo, ctx.inj_hi, ctx.seed, (uint32_t)ctx.tick, site, idx, k);
 }
 
@@ -1371,8 +1372,10 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
   }
   long long t_prev = clock64();
   int ph = 0;
-#define PHASE() do { if (prm.prof && tid == 0) { long long t_ = clock64(); atomicAdd(&prm.prof[ph], (unsigned long long)(t_ - t_prev)); t_prev = t_; } ph++; } while (0)
-#define PCOUNT(slot, v) do { if (prm.prof && tid == 0) atomicAdd(&prm.prof[slot], (unsigned long long)(v)); } while (0)
+  // (the *_std instantiations carry neither the per-phase profile counters nor the injected-draw lookup: a handle that
+  //  profiles or injects draws launches the generic instantiation)
+#define PHASE() do { if (!V::kStd && prm.prof && tid == 0) { long long t_ = clock64(); atomicAdd(&prm.prof[ph], (unsigned long long)(t_ - t_prev)); t_prev = t_; } ph++; } while (0)
+#define PCOUNT(slot, v) do { if (!V::kStd && prm.prof && tid == 0) atomicAdd(&prm.prof[slot], (unsigned long long)(v)); } while (0)
   #pragma unroll 1
   for (int i = tid; i < occ_words; i += T) ctx.occ[i] = 0;
   #pragma unroll 1

@@ -168,7 +168,7 @@ def test_std_cfg_table_matches_the_python_defaults():
         for i, v in table.items():
             assert int(cfg[i]) == v, (agent, i, v, int(cfg[i]))
     runtime = {"NC_N_PLAYERS", "NC_N_NPCS", "NC_MAP_CENTER", "NC_MAP_SIZE", "NC_ITEM_CAP", "NC_HORIZON", "NC_RES_RESILIENT_N",
-               "NC_SPAWN_IMMUNITY", "NC_ALLOW_OCCUPIED", "NC_WRAPPER", "NC_EARLY_STOP_N", "NC_EVAL_MODE", "NC_USE_CUSTOM_REWARD",
+               "NC_SPAWN_IMMUNITY", "NC_WRAPPER", "NC_EARLY_STOP_N", "NC_EVAL_MODE", "NC_USE_CUSTOM_REWARD",
                "NC_CLIP_UNIQUE", "NC_DISABLE_GIVE", "NC_NO_DANGEROUS_NPC", "NC_SPAWN_PATCH", "NC_TEAM_SIZE", "NC_SAMPLE_MOVE_PCT"}
     assert not ({SPEC[n] for n in runtime} & set(table)), "an entry the reference sets per run must not be folded"
     assert set(table) | {SPEC[n] for n in runtime} == set(range(SPEC["NC_COUNT"]))
