@@ -561,6 +561,35 @@ def run_rollout(args):
         ms += e0.elapsed_time(e1)
     store_ms = ms / a.reps
     store_bytes = per_call * (2 * a.stride + 2 * (12 * 4 + 4 * 4)) + n * 2
+    # ---- compact storage: Market once per (step, env), Task as the task id (a row is 8 960 of the 25 344 bytes)
+    L = ObsLayout(make_config()[0])
+    embed = torch.randn((128, L.task_dim), device=dev, generator=g).half()
+    tid = torch.randint(0, 128, (n,), dtype=torch.int32, device=dev, generator=g)
+    rc = DeviceRollout(a.batch, n, a.stride, compact=dict(agents_per_env=a.agents, market_off=L.o_market, market_bytes=L.n_mkt * 32,
+                                                          task_off=L.o_task, task_bytes=L.task_dim * 2, ids_off=L.o_ids, max_steps=8,
+                                                          task_embed_ptr=embed.data_ptr()))
+    for _ in range(2):
+        rc.reset(); rc.store(obs, val, actions, lp, rew, done, mask, 1, task_id=tid)
+    torch.cuda.synchronize()
+    ms = 0.0
+    for _ in range(a.reps):
+        rc.reset()
+        e0.record(); rc.store(obs, val, actions, lp, rew, done, mask, 1, task_id=tid); e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+    cstore_ms = ms / a.reps
+    cstore_bytes = per_call * (2 * rc.row_stride + 2 * (12 * 4 + 4 * 4) + 8) + a.envs * 2 * L.n_mkt * 32 + n * 2
+    mb = min(16384, per_call)
+    pick = torch.randperm(per_call, device=dev, generator=g)[:mb].int()
+    out = torch.empty((mb, a.stride), dtype=torch.uint8, device=dev)
+    rc.expand(pick, out=out); torch.cuda.synchronize()
+    ms = 0.0
+    for _ in range(a.reps):
+        e0.record(); rc.expand(pick, out=out); e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+    expand_ms = ms / a.reps
+    rc.close()
     # ---- sort + GAE over a full batch collected over several steps
     r.reset()
     step = 0
@@ -595,6 +624,10 @@ def run_rollout(args):
                       "n_slots": n, "obs_stride": a.stride, "batch_size": a.batch,
                       "append": {"rows_per_call": per_call, "ms": store_ms, "GB/s": store_bytes / store_ms / 1e6, "peak_GB/s": peak,
                                  "frac": store_bytes / store_ms / 1e6 / peak, "alg_bytes": store_bytes},
+                      "append_compact": {"rows_per_call": per_call, "ms": cstore_ms, "row_bytes": a.stride - L.n_mkt * 32 - L.task_dim * 2,
+                                         "GB/s": cstore_bytes / cstore_ms / 1e6, "frac": cstore_bytes / cstore_ms / 1e6 / peak, "alg_bytes": cstore_bytes,
+                                         "batch_bytes_vs_plain": (per_call * (a.stride - L.n_mkt * 32 - L.task_dim * 2) + a.envs * L.n_mkt * 32) / (per_call * a.stride),
+                                         "expand_minibatch": {"rows": mb, "ms": expand_ms, "GB/s": mb * 2 * a.stride / expand_ms / 1e6}},
                       "sort_gae": {"rows": rows, "ms": gae_ms, "samples_per_s": (rows - 1) / gae_ms * 1e3},
                       "cpu_port": {"rows": cb + 1, "seconds": cpu_s, "samples_per_s": cb / cpu_s, "kind": "port (Python loop, like the reference)"}}))
     r.close()
@@ -620,7 +653,7 @@ def run_config4(args):
     torch.manual_seed(args.seed)
     policy = TakeruPolicy(pool.driver_env.unflatten_context, 256, 256, 2048, agents_per_env=P, envs_per_chunk=args.policy_chunk_envs).cuda().eval()
     batch = min(args.rollout_batch, n)
-    roll = DeviceRollout(batch, n, pool.driver_env.obs_sz)
+    roll = DeviceRollout(batch, n, pool.driver_env.obs_sz, compact=DeviceRollout.compact_for(pool.sim, max_steps=4))
     clocks = make_clock_sampler(0)
     pool.async_reset(args.seed)
     gen = torch.Generator(device="cuda"); gen.manual_seed(args.seed)
@@ -637,7 +670,7 @@ def run_config4(args):
         actions, logprob, value = policy(o, generator=gen)                     # inference (:317-319), on the records in HBM
         e[1].record()
         roll.reset()                                                           # (one recv fills the batch at this env count)
-        roll.store(o, value, actions, logprob, r, d.float(), mask, k + 1)      # misc: the batch arrays (:333-348), device to device
+        roll.store(o, value, actions, logprob, r, d.float(), mask, k + 1, task_id=pool.sim.task_id)      # misc: the batch arrays (:333-348), device to device
         e[2].record()
         pool.send(actions)                                                     # env: step + observation kernels (:357, :293)
         e[3].record()
@@ -668,7 +701,7 @@ def run_config4(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "int16 env / fp32 policy" + (" (TF32 matmul)" if args.tf32 else ""), "data": "synthetic",
             "config": {"workload": f"configs[3]: clean_pufferl rollout loop with the takeru policy (ReducedModelV2 256/256, random init, no LSTM: "
                                    f"config.yaml:135-136), {E} envs x {P} agents, observations and masks read on the device, held-out task "
-                                   f"curriculum with its real 2048-d embeddings, rollout batch {batch} rows stored on the device",
+                                   f"curriculum with its real 2048-d embeddings, rollout batch {batch} rows stored on the device (compact: Market once per env-step, Task as id)",
                        "envs": E, "agents_per_env": P, "policy_chunk_envs": args.policy_chunk_envs, "obs_record_bytes": pool.driver_env.obs_sz},
             "SPS": padded / total, "agent_SPS": a_steps / total, "alive_fraction": a_steps / max(1, padded),
             "env_sps": a_steps / env_t, "env_sps_padded": padded / env_t, "inference_sps": padded / inf_t,

@@ -104,6 +104,8 @@ void *nmmo_mask_ptr(nmmo_handle *h);         /* uint8 [E*P]  agent present in th
 void *nmmo_info_ptr(nmmo_handle *h);         /* float [E*P][IN_N]  episode-end info records */
 void *nmmo_info_valid_ptr(nmmo_handle *h);   /* uint8 [E*P] */
 void *nmmo_episode_done_ptr(nmmo_handle *h); /* uint8 [E]    infos[..]["episode_done"], stat_wrapper.py:93-95 */
+void *nmmo_task_id_ptr(nmmo_handle *h);      /* int32 [E*P]  task-table row of every agent slot (this episode) */
+void *nmmo_task_embed_ptr(nmmo_handle *h);   /* fp16  [n_tasks][task_dim]  the task embeddings (the Task block of a record) */
 int nmmo_obs_stride(nmmo_handle *h);
 /* Names of the kernel instantiations this handle launches per step (family and compile-time shape are chosen by
  * nmmo_create from the configuration), as a profiler lists them. */
@@ -164,9 +166,29 @@ enum nm_rollout_buffer {     /* nmmo_rollout_buffer(which): rows = batch_size + 
   NM_RB_LOGPROBS, NM_RB_REWARDS, NM_RB_DONES, NM_RB_VALUES,   /* float32 [rows] */
   NM_RB_SLOT, NM_RB_STEP,    /* int32 [rows]: the sort key (env_id of the agent slot, step) */
   NM_RB_IDXS,                /* int32 [rows]: sample indices sorted by (slot, step)  (clean_pufferl.py:413) */
-  NM_RB_ADVANTAGES           /* float32 [rows]: advantages[t] for t < ptr - 1, in sorted order (:424-436) */
+  NM_RB_ADVANTAGES,          /* float32 [rows]: advantages[t] for t < ptr - 1, in sorted order (:424-436) */
+  /* compact mode only */
+  NM_RB_MARKET,              /* uint8 [max_steps][n_envs][market_bytes]: the Market block of an env in a step, stored once */
+  NM_RB_MARKET_SLOT,         /* int32 [rows]: step_index * n_envs + env of the row's Market block */
+  NM_RB_TASK_ID              /* int32 [rows]: the row's task id (its Task block is the embedding of that task) */
 };
 int nmmo_rollout_create(int device, int batch_size, int n_slots, int obs_stride, nmmo_rollout **out);
+/* Compact storage: the Market block (identical for every agent of an env in a step, 12 KB of the 25 KB record) is stored
+ * once per (step, env) and the Task block (the embedding of the agent's task, 4 KB) as the task id; a row keeps the other
+ * 9 KB.  NM_RB_OBS is then uint8 [rows][obs_stride - market_bytes - task_bytes]; nmmo_rollout_expand re-assembles whole
+ * records, bit-identical to what the plain mode stores.  market_off / task_off: byte offsets of the sections in a record
+ * (nm_obs_layout o_market / o_task); ids_off: offset of the int16 AgentId (o_ids; a record with AgentId 0 is the all-zero
+ * record of an agent that died this tick and expands to zeros); max_steps: store calls between two resets. */
+int nmmo_rollout_create_compact(int device, int batch_size, int n_slots, int obs_stride, int agents_per_env,
+                                int market_off, int market_bytes, int task_off, int task_bytes, int ids_off, int max_steps,
+                                nmmo_rollout **out);
+/* task_id: DEVICE int32 [n_slots] (nmmo_task_id_ptr of the env handle). */
+int nmmo_rollout_store_compact(nmmo_rollout *r, const uint8_t *obs, const int32_t *actions, const float *logprob,
+                               const float *value, const float *reward, const float *done, const uint8_t *mask,
+                               const uint8_t *learner_mask, const int32_t *task_id, int step, void *stream);
+/* out[k] = full record of row idxs[k] (idxs NULL: row k), k < n; task_embed: DEVICE fp16 [n_tasks][task_dim]
+ * (nmmo_task_embed_ptr); out: DEVICE uint8 [n][obs_stride].  The minibatch gather of clean_pufferl.py:439-443. */
+int nmmo_rollout_expand(nmmo_rollout *r, const int32_t *idxs_dev, int n, const uint16_t *task_embed_dev, uint8_t *out_dev, void *stream);
 int nmmo_rollout_destroy(nmmo_rollout *r);
 /* ptr = 0, sort keys cleared (clean_pufferl.py:278, :414). */
 int nmmo_rollout_reset(nmmo_rollout *r, void *stream);

@@ -501,6 +501,8 @@ extern "C" void *nmmo_mask_ptr(nmmo_handle *h) { return h->prm.mask; }
 extern "C" void *nmmo_info_ptr(nmmo_handle *h) { return h->prm.info; }
 extern "C" void *nmmo_info_valid_ptr(nmmo_handle *h) { return h->prm.info_valid; }
 extern "C" void *nmmo_episode_done_ptr(nmmo_handle *h) { return h->prm.episode_done; }
+extern "C" void *nmmo_task_id_ptr(nmmo_handle *h) { return h->prm.task_id; }
+extern "C" void *nmmo_task_embed_ptr(nmmo_handle *h) { return (void *)h->prm.embed; }
 // which instantiation this handle launches (bench / profiling: kernel names as ncu lists them)
 extern "C" const char *nmmo_step_kernel_name(nmmo_handle *h) {
   const bool lean_ok = !h->prm.prof && !h->prm.inj_off;      // same rule as launch_step

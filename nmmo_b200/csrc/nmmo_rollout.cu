@@ -39,6 +39,18 @@ struct RolloutParams {
   int32_t *idxs;           // [cap] sample indices in (slot, step) order
   float *delta, *coef, *adv;       // [cap]
   int32_t *starts;         // [cap] chain start positions
+  // compact mode (nmmo_rollout_create_compact): a row keeps the record without its Market and Task sections.  The Market
+  // block is identical for every agent of an env in a step and is stored once per (step, env); the Task block is the
+  // embedding of the agent's task and is stored as the task id.  nmmo_rollout_expand re-assembles full records.
+  int compact;             // 0 = rows are whole records
+  int agents_per_env, n_envs;
+  int m_off, m_len, t_off, t_len;  // byte ranges of the two sections inside a record (multiples of 16)
+  int ids_off;             // byte offset of the int16 AgentId: 0 there = the all-zero record of an agent that just died
+  int row_stride;          // bytes per stored row (= stride - m_len - t_len in compact mode)
+  int max_steps;           // Market slots: [max_steps][n_envs][m_len]
+  uint8_t *market;
+  int32_t *mslot;          // [cap] row -> step_index * n_envs + env
+  int32_t *task;           // [cap] row -> task id
 };
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
@@ -116,10 +128,79 @@ __global__ void __launch_bounds__(RB) k_store_rows(RolloutParams p, const uint8_
   }
   __syncthreads();
   const int n = s_n, n16 = p.stride >> 4;
-  for (int k = warp; k < n; k += RB / 32) {
-    const uint4 *src = (const uint4 *)(obs + (size_t)s_src[k] * p.stride);
-    uint4 *dst = (uint4 *)(p.obs + (size_t)s_dst[k] * p.stride);
-    for (int q = lane; q < n16; q += 32) __stcs(dst + q, __ldcs(src + q));
+  if (!p.compact) {
+    for (int k = warp; k < n; k += RB / 32) {
+      const uint4 *src = (const uint4 *)(obs + (size_t)s_src[k] * p.stride);
+      uint4 *dst = (uint4 *)(p.obs + (size_t)s_dst[k] * p.stride);
+      for (int q = lane; q < n16; q += 32) __stcs(dst + q, __ldcs(src + q));
+    }
+  } else {
+    // the record minus its Market and Task sections, packed
+    const int m0 = p.m_off >> 4, m1 = (p.m_off + p.m_len) >> 4, t0 = p.t_off >> 4, t1 = (p.t_off + p.t_len) >> 4;
+    for (int k = warp; k < n; k += RB / 32) {
+      const uint4 *src = (const uint4 *)(obs + (size_t)s_src[k] * p.stride);
+      uint4 *dst = (uint4 *)(p.obs + (size_t)s_dst[k] * p.row_stride);
+      for (int q = lane; q < n16; q += 32) {
+        if ((q >= m0 && q < m1) || (q >= t0 && q < t1)) continue;
+        const int skipped = (q >= m1 ? m1 - m0 : 0) + (q >= t1 ? t1 - t0 : 0);      // (sections in either order)
+        __stcs(dst + q - skipped, __ldcs(src + q));
+      }
+    }
+  }
+}
+// compact mode: per kept row the Market slot and the task id; per env the Market block of its first selected agent
+__device__ __forceinline__ bool zero_record(const RolloutParams &p, const uint8_t *obs, int i) {
+  return *(const int16_t *)(obs + (size_t)i * p.stride + p.ids_off) == 0;
+}
+__global__ void __launch_bounds__(RB) k_store_compact_keys(RolloutParams p, const uint8_t *obs, const uint8_t *mask, const uint8_t *learner,
+                                                          const int32_t *task_id, int step_index) {
+  __shared__ int s_warp[33];
+  const int i = blockIdx.x * RB + threadIdx.x;
+  const bool sel = selected(p, mask, learner, i);
+  int total;
+  const int rank = block_excl_scan(sel ? 1 : 0, s_warp, total);
+  const int pos = p.d_ptr[0] + p.blocksum[blockIdx.x] + rank;
+  if (sel && pos < p.cap) {
+    // an agent that died this tick is stored with the all-zero record: its Market and Task sections are zeros too (-1)
+    const bool z = zero_record(p, obs, i);
+    p.mslot[pos] = z ? -1 : step_index * p.n_envs + i / p.agents_per_env;
+    p.task[pos] = z ? -1 : task_id[i];
+  }
+}
+__global__ void __launch_bounds__(256) k_store_market(RolloutParams p, const uint8_t *obs, const uint8_t *mask, const uint8_t *learner,
+                                                     int step_index) {
+  const int lane = threadIdx.x & 31, env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (env >= p.n_envs) return;
+  int first = -1;
+  for (int b = 0; b < p.agents_per_env && first < 0; b += 32) {
+    const int a = b + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, a < p.agents_per_env && selected(p, mask, learner, env * p.agents_per_env + a) &&
+                                                       !zero_record(p, obs, env * p.agents_per_env + a));
+    if (m) first = b + __ffs(m) - 1;
+  }
+  if (first < 0) return;                      // nobody of this env is stored this step
+  const uint4 *src = (const uint4 *)(obs + (size_t)(env * p.agents_per_env + first) * p.stride + p.m_off);
+  uint4 *dst = (uint4 *)(p.market + ((size_t)step_index * p.n_envs + env) * p.m_len);
+  for (int q = lane; q < (p.m_len >> 4); q += 32) __stcs(dst + q, __ldcs(src + q));
+}
+// re-assemble full records: out[k] = row idxs[k] (or row k when idxs is NULL) with its Market block and Task embedding
+__global__ void __launch_bounds__(256) k_expand(RolloutParams p, const int32_t *idxs, int n, const uint16_t *embed, uint8_t *out) {
+  const int lane = threadIdx.x & 31;
+  const int m0 = p.m_off >> 4, m1 = (p.m_off + p.m_len) >> 4, t0 = p.t_off >> 4, t1 = (p.t_off + p.t_len) >> 4, n16 = p.stride >> 4;
+  for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += (gridDim.x * blockDim.x) >> 5) {
+    const int row = idxs ? idxs[k] : k;
+    const uint4 *src = (const uint4 *)(p.obs + (size_t)row * p.row_stride);
+    const bool z = p.mslot[row] < 0;
+    const uint4 *mk = (const uint4 *)(p.market + (size_t)max(p.mslot[row], 0) * p.m_len);
+    const uint4 *tk = (const uint4 *)(embed + (size_t)max(p.task[row], 0) * (p.t_len >> 1));
+    uint4 *dst = (uint4 *)(out + (size_t)k * p.stride);
+    for (int q = lane; q < n16; q += 32) {
+      uint4 v;
+      if (q >= m0 && q < m1) v = z ? make_uint4(0, 0, 0, 0) : __ldg(mk + q - m0);
+      else if (q >= t0 && q < t1) v = z ? make_uint4(0, 0, 0, 0) : __ldg(tk + q - t0);
+      else v = __ldcs(src + q - ((q >= m1 ? m1 - m0 : 0) + (q >= t1 ? t1 - t0 : 0)));
+      __stcs(dst + q, v);
+    }
   }
 }
 __global__ void k_advance_ptr(RolloutParams p) {
@@ -203,6 +284,7 @@ __global__ void k_gae_chains(RolloutParams p) {
 struct nmmo_rollout {
   RolloutParams p;
   int device;
+  int n_steps = 0;         // compact mode: store calls since the last reset (Market slot index)
   std::vector<void *> allocs;
 };
 
@@ -236,7 +318,26 @@ extern "C" int nmmo_rollout_destroy(nmmo_rollout *r) {
   return NM_OK;
 }
 
+static int rollout_create(int device, int batch_size, int n_slots, int obs_stride, int agents_per_env, int m_off, int m_len,
+                          int t_off, int t_len, int ids_off, int max_steps, nmmo_rollout **out);
+
 extern "C" int nmmo_rollout_create(int device, int batch_size, int n_slots, int obs_stride, nmmo_rollout **out) {
+  return rollout_create(device, batch_size, n_slots, obs_stride, 0, 0, 0, 0, 0, 0, 0, out);
+}
+
+extern "C" int nmmo_rollout_create_compact(int device, int batch_size, int n_slots, int obs_stride, int agents_per_env,
+                                           int market_off, int market_bytes, int task_off, int task_bytes, int ids_off, int max_steps,
+                                           nmmo_rollout **out) {
+  if (agents_per_env <= 0 || n_slots % std::max(agents_per_env, 1) || max_steps <= 0 || market_bytes <= 0 || task_bytes <= 0 ||
+      ((market_off | market_bytes | task_off | task_bytes) & 15) || market_off + market_bytes > obs_stride || task_off + task_bytes > obs_stride ||
+      !(market_off + market_bytes <= task_off || task_off + task_bytes <= market_off))
+    return rfail(NM_ERR_ARG, "compact rollout: sections must be 16-byte aligned, disjoint and inside the record; n_slots a multiple of agents_per_env");
+  if (ids_off < 0 || ids_off + 2 > obs_stride) return rfail(NM_ERR_ARG, "compact rollout: bad AgentId offset");
+  return rollout_create(device, batch_size, n_slots, obs_stride, agents_per_env, market_off, market_bytes, task_off, task_bytes, ids_off, max_steps, out);
+}
+
+static int rollout_create(int device, int batch_size, int n_slots, int obs_stride, int agents_per_env, int m_off, int m_len,
+                          int t_off, int t_len, int ids_off, int max_steps, nmmo_rollout **out) {
   if (!out || batch_size <= 0 || n_slots <= 0 || obs_stride <= 0 || (obs_stride & 15))
     return rfail(NM_ERR_ARG, "batch_size, n_slots must be positive and obs_stride a positive multiple of 16");
   int ndev = 0;
@@ -247,8 +348,12 @@ extern "C" int nmmo_rollout_create(int device, int batch_size, int n_slots, int 
   r->device = device;
   RolloutParams &p = r->p;
   p.cap = batch_size + 1; p.n_slots = n_slots; p.stride = obs_stride;
+  p.compact = agents_per_env > 0; p.agents_per_env = agents_per_env; p.n_envs = p.compact ? n_slots / agents_per_env : 0;
+  p.m_off = m_off; p.m_len = m_len; p.t_off = t_off; p.t_len = t_len; p.ids_off = ids_off; p.max_steps = max_steps;
+  p.row_stride = obs_stride - m_len - t_len;
   size_t cap = (size_t)p.cap;
-  RA(p.obs, cap * obs_stride); RA(p.actions, cap * 12); RA(p.logprobs, cap); RA(p.rewards, cap); RA(p.dones, cap); RA(p.values, cap);
+  if (p.compact) { RA(p.market, (size_t)max_steps * p.n_envs * m_len); RA(p.mslot, cap); RA(p.task, cap); }
+  RA(p.obs, cap * p.row_stride); RA(p.actions, cap * 12); RA(p.logprobs, cap); RA(p.rewards, cap); RA(p.dones, cap); RA(p.values, cap);
   RA(p.slot, cap); RA(p.rank, cap); RA(p.step, cap); RA(p.count, (size_t)n_slots); RA(p.base, (size_t)n_slots);
   RA(p.blocksum, (size_t)(n_slots + RB - 1) / RB + 1); RA(p.d_ptr, 4); RA(p.idxs, cap);
   RA(p.delta, cap); RA(p.coef, cap); RA(p.adv, cap); RA(p.starts, cap);
@@ -262,12 +367,32 @@ extern "C" int nmmo_rollout_reset(nmmo_rollout *r, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   RCU(cudaMemsetAsync(r->p.count, 0, sizeof(int32_t) * r->p.n_slots, st));
   RCU(cudaMemsetAsync(r->p.d_ptr, 0, sizeof(int32_t) * 4, st));
+  r->n_steps = 0;
   return NM_OK;
 }
+
+static int rollout_store(nmmo_rollout *r, const uint8_t *obs, const int32_t *actions, const float *logprob,
+                         const float *value, const float *reward, const float *done, const uint8_t *mask,
+                         const uint8_t *learner_mask, const int32_t *task_id, int step, void *stream);
 
 extern "C" int nmmo_rollout_store(nmmo_rollout *r, const uint8_t *obs, const int32_t *actions, const float *logprob,
                                   const float *value, const float *reward, const float *done, const uint8_t *mask,
                                   const uint8_t *learner_mask, int step, void *stream) {
+  if (r && r->p.compact) return rfail(NM_ERR_STATE, "compact rollout: use nmmo_rollout_store_compact (needs the task ids)");
+  return rollout_store(r, obs, actions, logprob, value, reward, done, mask, learner_mask, nullptr, step, stream);
+}
+
+extern "C" int nmmo_rollout_store_compact(nmmo_rollout *r, const uint8_t *obs, const int32_t *actions, const float *logprob,
+                                          const float *value, const float *reward, const float *done, const uint8_t *mask,
+                                          const uint8_t *learner_mask, const int32_t *task_id, int step, void *stream) {
+  if (!r || !r->p.compact || !task_id) return rfail(NM_ERR_ARG, "compact store needs a compact rollout and the task ids");
+  if (r->n_steps >= r->p.max_steps) return rfail(NM_ERR_LIMIT, "compact rollout: more store calls than max_steps since the last reset");
+  return rollout_store(r, obs, actions, logprob, value, reward, done, mask, learner_mask, task_id, step, stream);
+}
+
+static int rollout_store(nmmo_rollout *r, const uint8_t *obs, const int32_t *actions, const float *logprob,
+                         const float *value, const float *reward, const float *done, const uint8_t *mask,
+                         const uint8_t *learner_mask, const int32_t *task_id, int step, void *stream) {
   if (!r || !obs || !actions || !logprob || !value || !reward || !done || !mask) return rfail(NM_ERR_ARG, "null argument");
   if (((uintptr_t)obs | (uintptr_t)actions) & 15) return rfail(NM_ERR_ARG, "obs and actions must be 16-byte aligned");
   RCU(cudaSetDevice(r->device));
@@ -276,6 +401,11 @@ extern "C" int nmmo_rollout_store(nmmo_rollout *r, const uint8_t *obs, const int
   int nb = (p.n_slots + RB - 1) / RB;
   k_store_count<<<nb, RB, 0, st>>>(p, mask, learner_mask);
   k_scan_blocks<<<1, RB, 0, st>>>(p.blocksum, nb, p.d_ptr + 1);
+  if (p.compact) {
+    k_store_compact_keys<<<nb, RB, 0, st>>>(p, obs, mask, learner_mask, task_id, r->n_steps);
+    k_store_market<<<(p.n_envs * 32 + 255) / 256, 256, 0, st>>>(p, obs, mask, learner_mask, r->n_steps);
+    r->n_steps++;
+  }
   k_store_rows<<<nb, RB, 0, st>>>(p, obs, actions, logprob, value, reward, done, mask, learner_mask, step);
   k_advance_ptr<<<1, 32, 0, st>>>(p);
   RCU(cudaGetLastError());
@@ -311,6 +441,16 @@ extern "C" int nmmo_rollout_gae(nmmo_rollout *r, double gamma, double gae_lambda
   return NM_OK;
 }
 
+extern "C" int nmmo_rollout_expand(nmmo_rollout *r, const int32_t *idxs_dev, int n, const uint16_t *task_embed_dev, uint8_t *out_dev, void *stream) {
+  if (!r || !r->p.compact || !task_embed_dev || !out_dev || n < 0) return rfail(NM_ERR_ARG, "expand needs a compact rollout, the embedding table and an output buffer");
+  if ((uintptr_t)out_dev & 15) return rfail(NM_ERR_ARG, "output must be 16-byte aligned");
+  RCU(cudaSetDevice(r->device));
+  if (n == 0) return NM_OK;
+  k_expand<<<std::min((n * 32 + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(r->p, idxs_dev, n, task_embed_dev, out_dev);
+  RCU(cudaGetLastError());
+  return NM_OK;
+}
+
 extern "C" void *nmmo_rollout_buffer(nmmo_rollout *r, int which) {
   if (!r) return nullptr;
   const RolloutParams &p = r->p;
@@ -319,6 +459,7 @@ extern "C" void *nmmo_rollout_buffer(nmmo_rollout *r, int which) {
     case NM_RB_REWARDS: return p.rewards; case NM_RB_DONES: return p.dones; case NM_RB_VALUES: return p.values;
     case NM_RB_SLOT: return p.slot; case NM_RB_STEP: return p.step; case NM_RB_IDXS: return p.idxs;
     case NM_RB_ADVANTAGES: return p.adv;
+    case NM_RB_MARKET: return p.market; case NM_RB_MARKET_SLOT: return p.mslot; case NM_RB_TASK_ID: return p.task;
   }
   return nullptr;
 }

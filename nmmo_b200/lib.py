@@ -19,10 +19,10 @@ _lib = None
 EXPORTS = [
     "nmmo_create", "nmmo_destroy", "nmmo_reset", "nmmo_step", "nmmo_step_host", "nmmo_step_host_i16", "nmmo_step_host_u8", "nmmo_sample_actions", "nmmo_forage_actions",
     "nmmo_obs_ptr", "nmmo_reward_ptr", "nmmo_terminated_ptr", "nmmo_truncated_ptr", "nmmo_mask_ptr",
-    "nmmo_info_ptr", "nmmo_info_valid_ptr", "nmmo_episode_done_ptr", "nmmo_obs_stride", "nmmo_num_envs",
+    "nmmo_info_ptr", "nmmo_info_valid_ptr", "nmmo_episode_done_ptr", "nmmo_task_id_ptr", "nmmo_task_embed_ptr", "nmmo_obs_stride", "nmmo_num_envs",
     "nmmo_num_agents", "nmmo_step_kernel_name", "nmmo_obs_kernel_name", "nmmo_inject_rng", "nmmo_snapshot", "nmmo_task_state", "nmmo_stats", "nmmo_check", "nmmo_timing", "nmmo_timing_read", "nmmo_profile", "nmmo_set_obs_full", "nmmo_set_autosample",
     "nmmo_last_error",
-    "nmmo_rollout_create", "nmmo_rollout_destroy", "nmmo_rollout_reset", "nmmo_rollout_store", "nmmo_rollout_ptr",
+    "nmmo_rollout_create", "nmmo_rollout_create_compact", "nmmo_rollout_store_compact", "nmmo_rollout_expand", "nmmo_rollout_destroy", "nmmo_rollout_reset", "nmmo_rollout_store", "nmmo_rollout_ptr",
     "nmmo_rollout_gae", "nmmo_rollout_buffer", "nmmo_rollout_last_error",
 ]
 
@@ -66,7 +66,7 @@ def load(build_if_missing: bool = True):
     L.nmmo_forage_actions.restype = C.c_int
     L.nmmo_forage_actions.argtypes = [vp, C.c_uint64, vp, vp]
     for n in ("nmmo_obs_ptr", "nmmo_reward_ptr", "nmmo_terminated_ptr", "nmmo_truncated_ptr", "nmmo_mask_ptr",
-              "nmmo_info_ptr", "nmmo_info_valid_ptr", "nmmo_episode_done_ptr"):
+              "nmmo_info_ptr", "nmmo_info_valid_ptr", "nmmo_episode_done_ptr", "nmmo_task_id_ptr", "nmmo_task_embed_ptr"):
         getattr(L, n).restype = vp
         getattr(L, n).argtypes = [vp]
     for n in ("nmmo_obs_stride", "nmmo_num_envs", "nmmo_num_agents"):
@@ -98,6 +98,12 @@ def load(build_if_missing: bool = True):
     L.nmmo_last_error.restype = C.c_char_p
     L.nmmo_rollout_create.restype = C.c_int
     L.nmmo_rollout_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.nmmo_rollout_create_compact.restype = C.c_int
+    L.nmmo_rollout_create_compact.argtypes = [C.c_int] * 11 + [C.POINTER(vp)]
+    L.nmmo_rollout_store_compact.restype = C.c_int
+    L.nmmo_rollout_store_compact.argtypes = [vp] + [vp] * 9 + [C.c_int, vp]
+    L.nmmo_rollout_expand.restype = C.c_int
+    L.nmmo_rollout_expand.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     L.nmmo_rollout_destroy.argtypes = [vp]
     L.nmmo_rollout_reset.restype = C.c_int
     L.nmmo_rollout_reset.argtypes = [vp, vp]
@@ -200,6 +206,8 @@ class Simulator:
             self.info = view("nmmo_info_ptr", (n, SPEC["IN_N"]), "<f4")
             self.info_valid = view("nmmo_info_valid_ptr", (n,), "|u1")
             self.episode_done = view("nmmo_episode_done_ptr", (self.E,), "|u1")
+            self.task_id = view("nmmo_task_id_ptr", (n,), "<i4")
+            self.task_embed_ptr = self.L.nmmo_task_embed_ptr(self.h)
             self.actions = torch.zeros((self.E, self.P, 12), dtype=torch.int32, device=dev)
 
     def _check(self, rc: int):

@@ -115,3 +115,35 @@ def test_config5_limits():
         world = build_world(task_dim=64, n_maps=1, **over)
         with pytest.raises(NmmoError):
             _make(world, 1)
+
+
+def test_big_family_injected_draws_and_team_tasks(force_big):
+    """Recorded-draw injection (NPC wander, respawn, spawn, reset permutation) and team / named-target tasks through
+    the big family: same keys and same task rows on both sides, bit-exact episodes."""
+    from nmmo_b200.config import SPEC as S
+    from nmmo_b200.tasks import EVENT, TF_RELATIVE_TARGET, TF_TEAM, default_curriculum, make_task_table, task_row
+    rows = default_curriculum()[:12] + [task_row("ALL_MEMBERS_WITHIN_RANGE", 6, 0, 0, TF_TEAM), task_row("ALL_DEAD", 1, 0, 0, TF_TEAM | TF_RELATIVE_TARGET),
+                                        task_row("CAN_SEE_GROUP", -1, 0, 0, TF_RELATIVE_TARGET), task_row("COUNT_EVENT", EVENT["EAT_FOOD"], 6, 0, TF_TEAM)]
+    cfg, fcfg, maps, _, _ = build_world(task_dim=64, **SMALL, NC_HORIZON=120, NC_RES_DEPLETION=1, NC_SPAWN_IMMUNITY=2, NC_TEAM_SIZE=4)
+    tab, emb = make_task_table(rows, 64, seed=5)
+    sim, oracles = _make((cfg, fcfg, maps, tab, emb), 3)
+    assert sim.kernel_names() == ("nmmo_step_big_kernel", "nmmo_obs_big_kernel")
+    rng = np.random.default_rng(2)
+    P, R, Sz = int(cfg[S["NC_N_PLAYERS"]]), int(cfg[S["NC_N_PLAYERS"]] + cfg[S["NC_N_NPCS"]]), int(cfg[S["NC_MAP_SIZE"]])
+    for e, o in enumerate(oracles):
+        keys, vals = [], []
+        for t in range(100):
+            for row in rng.choice(np.arange(P, R), 6, replace=False):
+                keys.append((t << 36) | (S["RS_NPC_DECIDE"] << 32) | (int(row) << 8)); vals.append(int(rng.integers(0, 2 ** 32)))
+            for i in rng.choice(Sz * Sz, 30, replace=False):
+                keys.append((t << 36) | (S["RS_RESPAWN"] << 32) | (int(i) << 8)); vals.append(int(rng.integers(0, 2 ** 28)))
+            for att in range(25):
+                for k in range(6):
+                    keys.append((t << 36) | (S["RS_NPC_SPAWN"] << 32) | (att << 8) | k); vals.append(int(rng.integers(0, 2 ** 32)))
+        for i in range(1, P):
+            keys.append((S["RS_SPAWN_PERM"] << 32) | (i << 8)); vals.append(int(rng.integers(0, 2 ** 32)))
+        keys = np.array(keys, np.uint64); vals = np.array(vals, np.uint32)
+        o.inject_rng(keys, vals); sim.inject_rng(e, keys, vals)
+    stats = run_parity(sim, oracles, seeds=np.arange(3) + 90, ticks=130)
+    assert stats["infos"] > 0
+    sim.close()
