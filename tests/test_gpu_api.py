@@ -354,3 +354,32 @@ def test_forager_policy_matches_numpy_and_keeps_agents_alive():
     alive = sim.mask.cpu().numpy().reshape(3, P).sum(1)
     assert (alive >= P // 3).all(), f"foragers alive at tick 90: {alive}"
     sim.close()
+
+
+def test_vecenv_shards_reproduce_the_single_pool():
+    """Two B200VecEnv shards (env_base 0 and 2) run the envs of one 4-env pool: seeds, maps, tasks and sampled actions are
+    keyed by the GLOBAL env index, so the trajectories are identical."""
+    import torch
+    from argparse import Namespace
+    from nmmo_b200.vecenv import B200VecEnv
+    env_ns = Namespace(num_agents=16, num_npcs=32, max_episode_length=40, maps_path="maps/", map_size=32, num_maps=4,
+                       map_force_generation=False, death_fog_tick=None, task_size=64, spawn_immunity=20,
+                       resilient_population=0, curriculum_file_path=None)
+    kw = {"env": env_ns}
+    whole = B200VecEnv(env_kwargs=kw, num_envs=4, agent="takeru", collect_infos=False)
+    parts = [B200VecEnv(env_kwargs=kw, num_envs=2, agent="takeru", collect_infos=False, env_base=b) for b in (0, 2)]
+    for pool in [whole] + parts:
+        pool.async_reset(7)
+    for t in range(60):
+        o, r, d, tr, _, _, m = whole.recv()
+        got = [p.recv() for p in parts]
+        assert torch.equal(o, torch.cat([g[0] for g in got])), f"tick {t}: observations differ between the pool and its shards"
+        assert torch.equal(r, torch.cat([g[1] for g in got])) and torch.equal(m, torch.cat([g[6] for g in got]))
+        assert torch.equal(d, torch.cat([g[2] for g in got])) and torch.equal(tr, torch.cat([g[3] for g in got]))
+        whole.sim.sample_actions(3); whole.send(whole.sim.actions.reshape(-1, 12))
+        for p in parts:
+            p.sim.sample_actions(3); p.send(p.sim.actions.reshape(-1, 12))
+    st_w = whole.stats(); st_p = [p.stats() for p in parts]
+    assert st_w["episodes"] == sum(s["episodes"] for s in st_p) and st_w["episodes"] >= 4
+    for pool in [whole] + parts:
+        pool.close()
