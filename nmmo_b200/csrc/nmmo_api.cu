@@ -62,6 +62,11 @@ static size_t obs_cell_bytes(const NmParams &p, int NW) {
   const int ncx = (p.S + NM_OBS_CELL - 1) / NM_OBS_CELL, R32 = (p.R + 31) & ~31;
   return a16((size_t)(ncx * ncx + 1) * 4) + a16((size_t)R32 * 2) + a16((size_t)NW * (R32 / 32) * 4);
 }
+// observation kernels, per warp: visible-row list, batched-sampler mask words / agents / picks, Entity row buffer
+static size_t obs_warp_bytes(const NmParams &p, int NW) {
+  return a16((size_t)NW * a16((size_t)p.L.n_ent * 2)) + a16((size_t)NW * NM_OBS_BATCH * 33 * 4) + a16((size_t)NW * NM_OBS_BATCH * 2) +
+         a16((size_t)NW * NM_OBS_BATCH * AC_N * 2) + a16((size_t)NW * 512);
+}
 static size_t step_big_ws_bytes(const NmParams &p) {
   return a16((size_t)12 * p.P * 2) + a16((size_t)VBig::kEvCap * 8) + a16((size_t)p.P * 16) + a16((size_t)p.P * 8) + 128;
 }
@@ -71,8 +76,8 @@ static size_t obs_big_smem_bytes(const NmParams &p) {
   int NW = NM_OBS_THREADS / 32, AP = std::min(p.P, NM_BIG_OBS_AGENTS);
   s += a16((size_t)p.L.n_mkt * IA_N_OBS * 2); s += a16((size_t)p.L.n_mkt * 2);
   s += a16((size_t)AP * NINV * 2); s += a16((size_t)AP * 4); s += a16(64 * 4);
-  s += a16((size_t)NW * a16(p.L.m_end)); s += a16((size_t)NW * a16((size_t)p.L.n_ent * 2)); s += 16;
-  s += a16((size_t)NW * 72 * 4); s += a16((2 * AC_N + 2) * 4); s += a16((size_t)AP * 4); s += a16((size_t)AP * 2); s += a16((size_t)((p.R + 31) & ~31) * 4); s += a16(a16(p.L.m_end));
+  s += obs_warp_bytes(p, NW); s += 16;
+  s += a16((3 * AC_N + 2) * 4); s += a16((size_t)AP * 4); s += a16((size_t)AP * 2); s += a16((size_t)((p.R + 31) & ~31) * 4);
   s += obs_cell_bytes(p, NW) + 64 * 4 + a16((size_t)AP * 8);
   return s + 128;
 }
@@ -94,8 +99,8 @@ static size_t obs_smem_bytes(const NmParams &p) {
   s += a16((size_t)EA_N_OBS * p.R * 2); s += a16((size_t)p.R * 2); s += a16((size_t)IS_N * p.ICAP * 2); s += a16((size_t)p.S * p.S / 2);
   s += a16((size_t)p.L.n_mkt * IA_N_OBS * 2); s += a16((size_t)p.L.n_mkt * 2);
   s += a16((size_t)p.P * NINV * 2); s += a16((size_t)p.P * 4); s += a16(64 * 4);
-  s += a16((size_t)NW * a16(p.L.m_end)); s += a16((size_t)NW * a16((size_t)p.L.n_ent * 2)); s += 16;
-  s += a16((size_t)NW * 72 * 4); s += a16((2 * AC_N + 2) * 4); s += a16((size_t)p.P * 4); s += a16((size_t)p.P * 2); s += a16((size_t)((p.R + 31) & ~31) * 4); s += a16(a16(p.L.m_end));
+  s += obs_warp_bytes(p, NW); s += 16;
+  s += a16((3 * AC_N + 2) * 4); s += a16((size_t)p.P * 4); s += a16((size_t)p.P * 2); s += a16((size_t)((p.R + 31) & ~31) * 4);
   s += obs_cell_bytes(p, NW) + 64 * 4 + a16((size_t)p.P * 8);
   return s + 128;
 }
@@ -155,6 +160,7 @@ extern "C" int nmmo_create(const int32_t *cfg, int n_cfg, const double *fcfg, in
   if (p.N > VBig::kNpcHash / 2) { return fail(NM_ERR_LIMIT, "NPC_N must be <= 2048"); }
   if (p.cfg[NC_NPC_SPAWN_ATTEMPTS] > 32) { return fail(NM_ERR_LIMIT, "NPC_SPAWN_ATTEMPTS must be <= 32"); }
   if (p.L.n_ent > 255 || p.cfg[NC_N_INV] > 16) { return fail(NM_ERR_LIMIT, "N_ENT_OBS <= 255, N_INV <= 16"); }
+  if (p.L.m_end > 1024) { return fail(NM_ERR_LIMIT, "the ActionTargets masks must total <= 1024 entries (one 32-entry word per lane)"); }
   if (p.cfg[NC_SPAWN_PATCH] > 0 && (p.cfg[NC_SPAWN_PATCH] * p.cfg[NC_SPAWN_PATCH] < p.P || p.cfg[NC_SPAWN_PATCH] > p.cfg[NC_MAP_CENTER]))
     return fail(NM_ERR_ARG, "SPAWN_PATCH^2 must hold PLAYER_N players and fit inside the map centre");
   if (p.cfg[NC_SPAWN_PATCH] == 0 && !p.cfg[NC_ALLOW_OCCUPIED] && p.P > 4 * p.cfg[NC_MAP_CENTER])

@@ -27,6 +27,7 @@
 #define NM_BIG_ENT_STRIDE 48     // int16 per row of the row-major entity table (EA_N = 44, padded to 96 bytes)
 #define NM_BIG_OBS_AGENTS 128    // agents per CTA of the big observation kernel
 #define NM_OBS_CELL 16           // observation kernel: side of the cells the alive rows are bucketed by (>= 2 * vision)
+#define NM_OBS_BATCH 5           // observation kernel: agents per warp whose built-in-policy heads are resolved together (5 x 12 heads = 60 lanes)
 #define OM_NONZERO (1u << 16)
 #define OM_TASK (1u << 17)
 

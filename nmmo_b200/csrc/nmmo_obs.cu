@@ -121,10 +121,16 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   uint16_t *s_inv = (uint16_t *)carve((size_t)AP * NINV * 2);      // indexed by p - p_lo
   int *s_invn = (int *)carve((size_t)AP * 4);
   int *s_scan = (int *)carve(128 * 4);
+  // ActionTargets masks are built as bits: lane w of the warp that assembles a record holds mask entries [32w, 32w+32)
+  // in one register (nmmo_create rejects layouts with more than 1024 entries); they become bytes only in the store
   const int stage_bytes = nm_align16(L.m_end);
-  uint8_t *s_stage_all = carve((size_t)NW * stage_bytes);
   uint16_t *s_vis_all = (uint16_t *)carve((size_t)NW * ((L.n_ent * 2 + 15) & ~15));
-  uint32_t *s_bits_all = (uint32_t *)carve((size_t)NW * 72 * 4);   // per warp: 32 bitmap words + 33 running counts
+  // built-in policy: the mask words of the last NM_OBS_BATCH agents of each warp (row stride 33 words), the agents they
+  // belong to, and the picks on their way out
+  uint32_t *s_bb_all = (uint32_t *)carve((size_t)NW * NM_OBS_BATCH * 33 * 4);
+  uint16_t *s_ba_all = (uint16_t *)carve((size_t)NW * NM_OBS_BATCH * 2);
+  int16_t *s_pick_all = (int16_t *)carve((size_t)NW * NM_OBS_BATCH * AC_N * 2);
+  int16_t *s_ebuf_all = (int16_t *)carve((size_t)NW * 512);      // per warp: 8 Entity rows (496 bytes) on their way out
   const int R32 = (R + 31) & ~31, RW = R32 >> 5;
   uint32_t *s_pos = (uint32_t *)carve((size_t)R32 * 4);     // (row+7)<<16 | (col+7) of alive rows, padded to whole warps
   // cell index for the vision-window search: alive rows bucketed by NM_OBS_CELL x NM_OBS_CELL-tile cell.  A window
@@ -134,8 +140,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   int *s_cend = (int *)carve((size_t)(n_cells + 1) * 4);    // per cell: count, then (after the fill) the end of its row list
   uint16_t *s_crow = (uint16_t *)carve((size_t)R32 * 2);    // rows grouped by cell
   uint32_t *s_vbm_all = (uint32_t *)carve((size_t)NW * RW * 4);      // per warp: bitmap of the rows inside the agent's window
-  uint8_t *s_tmpl = carve(stage_bytes);                      // agent-independent part of the masks
-  int *s_head = (int *)carve((2 * AC_N + 2) * 4);       // + work-list length and cursor
+  int *s_head = (int *)carve((3 * AC_N + 2) * 4);       // head offsets, lengths, work-list length and cursor, heads by length
   uint64_t *s_hash = (uint64_t *)carve((size_t)AP * 8);     // built-in policy: one 64-bit draw per agent, computed by one thread each
   uint32_t *s_meta = (uint32_t *)carve((size_t)AP * 4);
   uint16_t *s_work = (uint16_t *)carve((size_t)AP * 2);
@@ -151,7 +156,10 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
                            L.m_gold_price, L.m_gold_target, L.m_move, L.m_sell_item, L.m_sell_price, L.m_use};
     const int len[AC_N] = {3, L.n_ent + 1, L.n_mkt + 1, L.n_inv + 1, L.n_inv + 1, L.n_ent + 1, L.n_price,
                            L.n_ent + 1, NM_DIR_N, L.n_inv + 1, L.n_price, L.n_inv + 1};
-    s_head[tid] = off[tid]; s_head[AC_N + tid] = len[tid];
+    // heads in the order the batched sampler walks them: longest first, so that the lanes of one pass have similar trip counts
+    const int ord[AC_N] = {AC_BUY_ITEM, AC_ATTACK_TARGET, AC_GIVE_TARGET, AC_GOLD_TARGET, AC_GOLD_PRICE, AC_SELL_PRICE,
+                           AC_DESTROY_ITEM, AC_GIVE_ITEM, AC_SELL_ITEM, AC_USE_ITEM, AC_MOVE_DIR, AC_ATTACK_STYLE};
+    s_head[tid] = off[tid]; s_head[AC_N + tid] = len[tid]; s_head[2 * AC_N + 2 + tid] = ord[tid];
   }
   __syncthreads();
   if (V::kStage && tid == 0) {
@@ -200,18 +208,6 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     }
     s_pos[r] = pos;
   }
-  // mask template: entries that do not depend on the agent (Style, Sell.Price, the no-op slots,
-  // GiveGold.Price[0]); per agent it is copied and only the agent-specific entries are touched
-  #pragma unroll 1
-  for (int i = tid; i < stage_bytes; i += T) {
-    uint8_t v = 0;
-    if (i >= L.m_style && i < L.m_style + 3) v = 1;
-    if (i >= L.m_sell_price && i < L.m_sell_price + L.n_price) v = 1;
-    if (i == L.m_buy + L.n_mkt || i == L.m_destroy + L.n_inv || i == L.m_give_item + L.n_inv || i == L.m_sell_item + L.n_inv ||
-        i == L.m_use + L.n_inv || i == L.m_give_target + L.n_ent || i == L.m_gold_target + L.n_ent || i == L.m_gold_price) v = 1;
-    s_tmpl[i] = v;
-  }
-
   // ---- inventory lists (row order) and the market list (row order, first n_mkt) -------
   const int K = (item_hi + T - 1) / T;      // consecutive rows per thread
   int my_listed = 0;
@@ -292,8 +288,22 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   OPHASE();      // 34 market rows
 
   // ---- per-agent records: one warp per agent -------------------------------------------
-  uint8_t *stage = s_stage_all + (size_t)warp * stage_bytes;
-  int8_t *m = (int8_t *)stage;
+  uint32_t *bb = s_bb_all + warp * (NM_OBS_BATCH * 33);
+  uint16_t *ba = s_ba_all + warp * NM_OBS_BATCH;
+  int16_t *picks = s_pick_all + warp * (NM_OBS_BATCH * AC_N);
+  int16_t *ebuf = s_ebuf_all + warp * 256;
+  // the bits of mask entries [lo, hi) / of entry pos that fall into this lane's word
+  auto range_bits = [&](int lo, int hi) -> uint32_t {
+    const int a = max(lo - 32 * lane, 0), b = min(hi - 32 * lane, 32);
+    if (b <= a) return 0u;
+    return (b >= 32 ? 0xffffffffu : ((1u << b) - 1u)) & ~((1u << a) - 1u);
+  };
+  auto one_bit = [&](int pos) -> uint32_t { return (pos >> 5) == lane ? 1u << (pos & 31) : 0u; };
+  // entries that do not depend on the agent (Style, Sell.Price, the no-op slots, GiveGold.Price[0])
+  const uint32_t tmpl_word = range_bits(L.m_style, L.m_style + 3) | range_bits(L.m_sell_price, L.m_sell_price + L.n_price) |
+                             one_bit(L.m_buy + L.n_mkt) | one_bit(L.m_destroy + L.n_inv) | one_bit(L.m_give_item + L.n_inv) |
+                             one_bit(L.m_sell_item + L.n_inv) | one_bit(L.m_use + L.n_inv) | one_bit(L.m_give_target + L.n_ent) |
+                             one_bit(L.m_gold_target + L.n_ent) | one_bit(L.m_gold_price);
   uint16_t *s_vis = s_vis_all + (size_t)warp * (((L.n_ent * 2 + 15) & ~15) / 2);
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
   long long n_stored = 0;                     // 16-byte chunks stored by this warp
@@ -323,6 +333,8 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   const bool tw_fast = L.win >= 8 && tw_groups <= 32;
   const int tw_dr = (lane * 8) / L.win, tw_dc = (lane * 8) - tw_dr * L.win;
   const int tw_first = min(8, L.win - tw_dc);             // tiles of the group in its first window row
+  const int tw_nval = min(8, max(0, tw_tiles - lane * 8));                 // tiles of the group that exist
+  const uint32_t tw_matmask = tw_nval >= 8 ? 0xffffffffu : ((1u << (4 * tw_nval)) - 1u);
   auto fetch8 = [&](int i) -> uint32_t {                    // the 8 nibbles of tiles i..i+7
     const int w = i >> 3, sh = (i & 7) * 4;
     return __funnelshift_r(s_map[w], s_map[w + 1], sh);
@@ -331,12 +343,80 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   // Work items are dealt round-robin when most agents are alive (items of equal cost: no queue traffic) and pulled from a
   // shared cursor otherwise (a zero fill is much cheaper than a record, so a static deal would leave warps idle)
   const bool deal = 2 * n_work > AP;
+  // obs_full = 1: every row of every section is rewritten, the Task block included
+  const int ms_shift = (lane & 1) * 16;      // mask store: which half of the source word this lane expands
+  const uint32_t meta_full = (uint32_t)L.n_ent | ((uint32_t)L.n_inv << 8) | ((uint32_t)L.n_mkt << 18);
+  int nb = 0;                                 // agents whose mask words wait in bb for the built-in policy
   #pragma unroll 1
   for (int it = 0;; it++) {
     int wi = warp + it * NW;
     if (!deal) {
       if (lane == 0) wi = atomicAdd(&s_head[2 * AC_N + 1], 1);
       wi = __shfl_sync(0xffffffffu, wi, 0);
+    }
+    // ---- built-in random policy (optional): uniform over the valid entries of every head ----
+    // Run for NM_OBS_BATCH agents at a time so that a lane resolves one (agent, head) pair and all lanes are busy:
+    // count the head's set bits in the agent's mask words, draw, find the drawn entry.  Same draws as nmmo_sample_kernel.
+    if (nb == NM_OBS_BATCH || (wi >= n_work && nb > 0)) {
+      __syncwarp();
+      const int n_items = nb * AC_N;
+      // item / nb by multiplication (exact for item < 2^10, nb <= 2^6); a full batch needs no division at all
+      const int rcp = nb == NM_OBS_BATCH ? (65536 + NM_OBS_BATCH - 1) / NM_OBS_BATCH : (65536 + nb - 1) / nb;
+      #pragma unroll 1
+      for (int i0 = 0; i0 < n_items; i0 += 32) {
+        const int item = i0 + lane;
+        if (item < n_items) {
+          const int hi = (item * rcp) >> 16, sl = item - hi * nb;          // heads of similar length share a pass
+          const int h = s_head[2 * AC_N + 2 + hi], o0 = s_head[h];
+          int o1 = o0 + s_head[AC_N + h];
+          const uint32_t *bits = bb + sl * 33;
+          const uint64_t base64 = s_hash[ba[sl]];
+          bool stay = false;
+          if (h == AC_MOVE_DIR && c[NC_SAMPLE_MOVE_PCT] > 0) {
+            // Move-biased workload (BASELINE.json configs[4]): with the given probability a valid direction other
+            // than Stay (the head then covers the four directions only), else Stay
+            const uint32_t four = __funnelshift_r(bits[o0 >> 5], bits[(o0 >> 5) + 1], o0 & 31) & 15u;
+            if (four) { if (nm_bounded(nm_action_draw(base64, AC_N), 100) < c[NC_SAMPLE_MOVE_PCT]) o1 = o0 + 4; else stay = true; }
+          }
+          // only the non-zero words of the head's range are looked at (bits[32]: which of the agent's words are non-zero)
+          const int w0 = o0 >> 5, w1 = (o1 - 1) >> 5;
+          const uint32_t wm = bits[32] & (0xffffffffu << w0) & (0xffffffffu >> (31 - w1));
+          const uint32_t lo_mask = 0xffffffffu << (o0 & 31), hi_mask = 0xffffffffu >> ((32 - o1) & 31);
+          auto word_at = [&](int w) -> uint32_t {
+            uint32_t x = bits[w];
+            if (w == w0) x &= lo_mask;
+            if (w == w1) x &= hi_mask;
+            return x;
+          };
+          int pick = 0;
+          if (stay) pick = 4;
+          else {
+            int total = 0;
+            #pragma unroll 1
+            for (uint32_t mm = wm; mm; mm &= mm - 1) total += __popc(word_at(__ffs(mm) - 1));
+            if (total > 0) {
+              int jj = nm_bounded(nm_action_draw(base64, h), total);
+              #pragma unroll 1
+              for (uint32_t mm = wm; mm; mm &= mm - 1) {
+                const int w = __ffs(mm) - 1;
+                const uint32_t x = word_at(w);
+                const int cnt = __popc(x);
+                if (jj < cnt) { pick = w * 32 + nth_set_bit(x, jj) - o0; break; }
+                jj -= cnt;
+              }
+            }
+          }
+          picks[sl * AC_N + h] = (int16_t)pick;
+        }
+      }
+      __syncwarp();
+      #pragma unroll 1
+      for (int i = lane; i < n_items; i += 32) {      // out in agent-major order: 48 contiguous bytes per agent
+        const int sl = i / AC_N;
+        prm.sample_out[((size_t)env * P + p_lo + ba[sl]) * AC_N + (i - sl * AC_N)] = picks[i];
+      }
+      __syncwarp();
+      nb = 0;
     }
     if (wi >= n_work) break;
     const int went = s_work[wi];
@@ -357,10 +437,9 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
       if (lane == 0) prm.obs_meta[a] = 0;
       continue;
     }
-    const int pv = prm.obs_full ? L.n_ent : (int)(meta & 255u);
-    const int pi = prm.obs_full ? L.n_inv : (int)((meta >> 8) & 31u);
-    const int pm = prm.obs_full ? L.n_mkt : (int)((meta >> 18) & 1023u);
-    const bool task_ok = !prm.obs_full && (meta & OM_TASK);
+    const uint32_t held = prm.obs_full ? meta_full : meta;      // what the record is taken to hold
+    const int pv = (int)(held & 255u), pi = (int)((held >> 8) & 31u), pm = (int)((held >> 18) & 1023u);
+    const bool task_ok = (held & OM_TASK) != 0;
     const int r0 = OENT(EA_ROW, p), c0 = OENT(EA_COL, p), my_id = OENT(EA_ID, p), my_gold = OENT(EA_GOLD, p);
     // visible entities: table rows inside the window, in table order, first n_ent
     int n_vis = 0;
@@ -369,8 +448,8 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
       return (uint32_t)((int)(pos >> 16) - r0) <= (uint32_t)(2 * vis) && (uint32_t)((int)(pos & 0xffffu) - c0) <= (uint32_t)(2 * vis);
     };
     // the rows listed in the (at most 2 x 2) cells under the window: two contiguous ranges of the cell-ordered row list
-    const int cr0 = max(r0 - vis, 0) / NM_OBS_CELL, cr1 = min(r0 + vis, S - 1) / NM_OBS_CELL;
-    const int cc0 = max(c0 - vis, 0) / NM_OBS_CELL, cc1 = min(c0 + vis, S - 1) / NM_OBS_CELL;
+    const int cr0 = (int)((unsigned)max(r0 - vis, 0) / NM_OBS_CELL), cr1 = (int)((unsigned)min(r0 + vis, S - 1) / NM_OBS_CELL);
+    const int cc0 = (int)((unsigned)max(c0 - vis, 0) / NM_OBS_CELL), cc1 = (int)((unsigned)min(c0 + vis, S - 1) / NM_OBS_CELL);
     int begA = 0, endA = 0, begB = 0, endB = 0;
     if (use_cells) {
       const int ca = cr0 * ncx + cc0;
@@ -385,12 +464,33 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
         const int r = s_crow[lane < nA ? begA + lane : begB + lane - nA];
         if (in_window(s_pos[r])) row = r;
       }
-      unsigned hits = __ballot_sync(0xffffffffu, row != 0x7fffffff);
-      n_vis = __popc(hits);
-      int rank = 0;
-      #pragma unroll 1
-      for (unsigned h = hits; h; h &= h - 1) rank += __shfl_sync(0xffffffffu, row, __ffs(h) - 1) < row;
-      if (row != 0x7fffffff && rank < L.n_ent) s_vis[rank] = (uint16_t)row;
+      if (RW <= 32) {
+        // a hit's place in table order = hits with a smaller row: the hits are marked in the warp's row bitmap, lane w
+        // counts word w, and a prefix sum over the words gives every hit its rank
+        uint32_t *vbm = s_vbm_all + warp * RW;
+        if (lane < RW) vbm[lane] = 0;
+        __syncwarp();
+        if (row != 0x7fffffff) atomicOr(&vbm[row >> 5], 1u << (row & 31));
+        __syncwarp();
+        const uint32_t wv = lane < RW ? vbm[lane] : 0u;
+        const int pc = __popc(wv);
+        int incl2 = pc;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) if (d < RW) { const int u = __shfl_up_sync(0xffffffffu, incl2, d); if (lane >= d) incl2 += u; }
+        n_vis = __shfl_sync(0xffffffffu, incl2, (RW - 1) & 31);
+        const int wsel = (row >> 5) & 31;
+        const int below = __shfl_sync(0xffffffffu, incl2 - pc, wsel);
+        const uint32_t wbits = __shfl_sync(0xffffffffu, wv, wsel);
+        const int rank = below + __popc(wbits & ((1u << (row & 31)) - 1u));
+        if (row != 0x7fffffff && rank < L.n_ent) s_vis[rank] = (uint16_t)row;
+      } else {
+        unsigned hits = __ballot_sync(0xffffffffu, row != 0x7fffffff);
+        n_vis = __popc(hits);
+        int rank = 0;
+        #pragma unroll 1
+        for (unsigned h = hits; h; h &= h - 1) rank += __shfl_sync(0xffffffffu, row, __ffs(h) - 1) < row;
+        if (row != 0x7fffffff && rank < L.n_ent) s_vis[rank] = (uint16_t)row;
+      }
     } else if (use_cells) {
       // many candidates: they are tested and marked in a row bitmap; walking the bitmap yields them in table order
       uint32_t *vbm = s_vbm_all + warp * RW;
@@ -436,31 +536,40 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     n_vis = min(n_vis, L.n_ent);
     const int n_inv = min(s_invn[p - p_lo], NINV);
     const uint16_t *inv = s_inv + (p - p_lo) * NINV;
-    #pragma unroll 1
-    for (int k = lane; k < stage_bytes / 16; k += 32) ((uint4 *)stage)[k] = ((const uint4 *)s_tmpl)[k];
-    __syncwarp();
-    // ---- ActionTargets ----
+    // ---- ActionTargets (as bits: this lane's word of the record's mask entries) ----
+    uint32_t mw = tmpl_word;
+    // a ballot over up to 32 consecutive entries, the first of them entry o of the masks
+    auto place = [&](uint32_t bsel, int o) {
+      // lane o / 32 takes the low part of bsel << (o % 32), the next lane what was shifted out
+      const int d = lane - (o >> 5);
+      mw |= __funnelshift_l(d == 1 ? bsel : 0u, d == 0 ? bsel : 0u, o & 31);
+    };
     {
-      bool any = false;
-      bool immune = OENT(EA_TIME_ALIVE, p) < c[NC_SPAWN_IMMUNITY];
+      unsigned any = 0;
+      const bool immune = OENT(EA_TIME_ALIVE, p) < c[NC_SPAWN_IMMUNITY];
       #pragma unroll 1
-      for (int i = lane; i < n_vis; i += 32) {
-        int row = s_vis[i], id = OENT(EA_ID, row);
-        bool same = OENT(EA_ROW, row) == r0 && OENT(EA_COL, row) == c0;
-        bool ok = nm_linf(OENT(EA_ROW, row), OENT(EA_COL, row), r0, c0) <= c[NC_REACH] && id != my_id && !(immune && id > 0);
-        any |= ok;                                   // the no-op entry is the engine's, before the wrapper edit
-        if (no_danger && OENT(EA_NPC_TYPE, row) > 1) ok = false;
-        m[L.m_target + i] = ok;
-        if (!no_give) {     // takeru's RewardWrapper.observation zeroes these anyway (reward_wrapper.py:31-35)
-          bool give = n_inv > 0 && same && OENT(EA_NPC_TYPE, row) == 0 && id != my_id;
-          m[L.m_give_target + i] = give; m[L.m_gold_target + i] = give;
+      for (int base = 0; base < n_vis; base += 32) {
+        const int i = base + lane;
+        bool ok = false, att = false, give = false;
+        if (i < n_vis) {
+          const int row = s_vis[i], id = OENT(EA_ID, row), er = OENT(EA_ROW, row), ec = OENT(EA_COL, row);
+          const int npc_type = OENT(EA_NPC_TYPE, row);
+          ok = nm_linf(er, ec, r0, c0) <= c[NC_REACH] && id != my_id && !(immune && id > 0);
+          att = ok && !(no_danger && npc_type > 1);
+          // takeru's RewardWrapper.observation zeroes the Give targets anyway (reward_wrapper.py:31-35)
+          give = !no_give && n_inv > 0 && er == r0 && ec == c0 && npc_type == 0 && id != my_id;
+        }
+        any |= __ballot_sync(0xffffffffu, ok);           // the no-op entry is the engine's, before the wrapper edit
+        place(__ballot_sync(0xffffffffu, att), L.m_target + base);
+        if (!no_give) {
+          const unsigned bg = __ballot_sync(0xffffffffu, give);
+          place(bg, L.m_give_target + base); place(bg, L.m_gold_target + base);
         }
       }
-      any = __any_sync(0xffffffffu, any);
-      if (lane == 0) m[L.m_target + L.n_ent] = any ? 0 : 1;
+      if (!any) mw |= one_bit(L.m_target + L.n_ent);
     }
     {
-      bool full = n_inv >= NINV;
+      const bool full = n_inv >= NINV;
       // does a market listing match an ammo stack I own?
       auto ammo_match = [&](int j) -> bool {
         int type = s_mkt[j * IA_N_OBS + IA_TYPE], level = s_mkt[j * IA_N_OBS + IA_LEVEL];
@@ -472,140 +581,83 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
       if (full) { for (int j = lane; j < n_mkt; j += 32) any_ammo |= ammo_match(j); any_ammo = __any_sync(0xffffffffu, any_ammo); }
       if (!(full && !any_ammo))
         #pragma unroll 1
-        for (int j = lane; j < n_mkt; j += 32) {
-          bool ok = s_mkt[j * IA_N_OBS + IA_OWNER] != my_id && s_mkt[j * IA_N_OBS + IA_LISTED_PRICE] <= my_gold;
-          if (full) ok = ok && ammo_match(j);
-          m[L.m_buy + j] = ok;
+        for (int base = 0; base < n_mkt; base += 32) {
+          const int j = base + lane;
+          bool ok = false;
+          if (j < n_mkt) {
+            ok = s_mkt[j * IA_N_OBS + IA_OWNER] != my_id && s_mkt[j * IA_N_OBS + IA_LISTED_PRICE] <= my_gold;
+            if (full) ok = ok && ammo_match(j);
+          }
+          place(__ballot_sync(0xffffffffu, ok), L.m_buy + base);
         }
     }
-    if (lane < n_inv) {
-      int i = inv[lane];
-      bool eq = OITM(IS_EQUIPPED, i) != 0, listed = OITM(IS_PRICE, i) != 0;
-      m[L.m_destroy + lane] = !eq;
-      if (!no_give) m[L.m_give_item + lane] = !eq && !listed;
-      m[L.m_sell_item + lane] = !eq && !listed;
-      m[L.m_use + lane] = !listed && OITM(IS_LEVEL, i) <= o_use_level<V>(o, p, OITM(IS_TYPE, i));
+    if (n_inv > 0) {
+      bool b_destroy = false, b_free = false, b_use = false;
+      if (lane < n_inv) {
+        const int i = inv[lane];
+        const bool eq = OITM(IS_EQUIPPED, i) != 0, listed = OITM(IS_PRICE, i) != 0;
+        b_destroy = !eq; b_free = !eq && !listed;
+        b_use = !listed && OITM(IS_LEVEL, i) <= o_use_level<V>(o, p, OITM(IS_TYPE, i));
+      }
+      const unsigned bf = __ballot_sync(0xffffffffu, b_free);
+      place(__ballot_sync(0xffffffffu, b_destroy), L.m_destroy);
+      if (!no_give) place(bf, L.m_give_item);
+      place(bf, L.m_sell_item);
+      place(__ballot_sync(0xffffffffu, b_use), L.m_use);
     }
-    if (!no_give) for (int g = 1 + lane; g < min(my_gold, L.n_price); g += 32) m[L.m_gold_price + g] = 1;
-    if (lane < 5) m[L.m_move + lane] = !nm_impassible(tile((r0 + c_dir_dr[lane]) * S + c0 + c_dir_dc[lane]));
-    __syncwarp();
+    if (!no_give) mw |= range_bits(L.m_gold_price + 1, L.m_gold_price + min(my_gold, L.n_price));
+    {
+      // North South East West Stay (c_dir_dr / c_dir_dc; computed, a constant-memory look-up by lane would serialise)
+      const int ddr = lane == 0 ? -1 : (lane == 1 ? 1 : 0), ddc = lane == 2 ? 1 : (lane == 3 ? -1 : 0);
+      const bool mv = lane < 5 && !nm_impassible(tile((r0 + ddr) * S + c0 + ddc));
+      place(__ballot_sync(0xffffffffu, mv), L.m_move);
+    }
     // RewardWrapper.observation hooks
     // (takeru: Give.InventoryItem[:-1], Give.Target[:-1], GiveGold.Target[:-1], GiveGold.Price[1:]
     //  stay at the template's zeros -- they were never filled in, see no_give above)
-    if (wrapper == NW_START_KIT) {
-      if (lane == 0) m[L.m_sell_price + prm.stats[a * ST_N + ST_PREV_PRICE]] = 0;
+    if (wrapper == NW_START_KIT) mw &= ~one_bit(L.m_sell_price + prm.stats[a * ST_N + ST_PREV_PRICE]);
+    // out: 16 mask entries (half a word) become the 16 bytes of one store
+    // (at most 1024 entries = 64 stores: two per lane; lane k's come from the words of lanes k / 2 and 16 + k / 2)
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      const uint32_t wsrc = __shfl_sync(0xffffffffu, mw, half * 16 + (lane >> 1)) >> ms_shift;
+      if (half * 32 + lane < stage_bytes / 16)
+        st16(rec + (half * 32 + lane) * 16,
+             make_uint4(((wsrc & 15u) * 0x00204081u) & 0x01010101u, (((wsrc >> 4) & 15u) * 0x00204081u) & 0x01010101u,
+                        (((wsrc >> 8) & 15u) * 0x00204081u) & 0x01010101u, (((wsrc >> 12) & 15u) * 0x00204081u) & 0x01010101u));
     }
-    __syncwarp();
-    #pragma unroll 1
-    for (int k = lane; k < stage_bytes / 16; k += 32) st16(rec + k * 16, ((const uint4 *)stage)[k]);
     n_stored += stage_bytes / 16 + 1;
-    // ---- built-in random policy (optional): uniform over the valid entries of every head ----
-    // The 946 mask bytes become 30 ballot words; lanes 0..11 then each resolve one head with
-    // popc / __fns on those words.  Same draws as nmmo_sample_kernel.
-    if (prm.sample_out) {
-      uint32_t *bits = s_bits_all + warp * 72;
-      uint32_t *cum = bits + 32;             // cum[w] = set bits in words < w (fast path, n_words <= 32)
-      uint32_t my_word = 0;
-      const int n_words = (L.m_end + 31) >> 5;
-      // lane w packs mask bytes [32w, 32w+32) into bitmap word w: two 16-byte loads, one multiply
-      // per four bytes (0/1 bytes -> nibble), no cross-lane traffic; bytes past m_end are template zeros
-      #pragma unroll 1
-      for (int wd = lane; wd < n_words; wd += 32) {
-        uint32_t wb = 0;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const int qi = wd * 2 + h;
-          const uint4 v = qi < stage_bytes / 16 ? ((const uint4 *)stage)[qi] : zero4;
-          const uint32_t n0 = ((v.x & 0x01010101u) * 0x01020408u) >> 24, n1 = ((v.y & 0x01010101u) * 0x01020408u) >> 24;
-          const uint32_t n2 = ((v.z & 0x01010101u) * 0x01020408u) >> 24, n3 = ((v.w & 0x01010101u) * 0x01020408u) >> 24;
-          wb |= ((n0 & 15u) | ((n1 & 15u) << 4) | ((n2 & 15u) << 8) | ((n3 & 15u) << 12)) << (16 * h);
-        }
-        bits[wd] = wb;
-        my_word = wb;
-      }
-      if (n_words <= 32) {
-        int pc = __popc(my_word), incl = pc;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
-        cum[lane] = (uint32_t)(incl - pc);
-        if (lane == 31) cum[32] = (uint32_t)incl;
-      }
-      __syncwarp();
-      if (lane < AC_N) {
-        const uint64_t base64 = s_hash[p - p_lo];
-        const int o0 = s_head[lane];
-        int o1 = o0 + s_head[AC_N + lane];
-        bool stay = false;
-        if (lane == AC_MOVE_DIR && c[NC_SAMPLE_MOVE_PCT] > 0) {
-          // Move-biased workload (BASELINE.json configs[4]): with the given probability a valid direction other
-          // than Stay (the head then covers the four directions only), else Stay
-          const int nv = (m[o0] != 0) + (m[o0 + 1] != 0) + (m[o0 + 2] != 0) + (m[o0 + 3] != 0);
-          if (nv > 0) { if (nm_bounded(nm_action_draw(base64, AC_N), 100) < c[NC_SAMPLE_MOVE_PCT]) o1 = o0 + 4; else stay = true; }
-        }
-        const int w0 = o0 >> 5, w1 = (o1 - 1) >> 5;
-        auto word_at = [&](int w) -> uint32_t {
-          uint32_t x = bits[w];
-          if (w == w0) x &= 0xffffffffu << (o0 & 31);
-          if (w == w1 && (o1 & 31)) x &= (1u << (o1 & 31)) - 1u;
-          return x;
-        };
-        int pick = 0;
-        if (n_words <= 32) {
-          // rank(x) = set bits below bit x of the bitmap: the head's count and the word holding the
-          // drawn entry come from the running counts, without walking the head's words
-          auto rank = [&](int x) -> int { int w = x >> 5; return (int)cum[w] + ((x & 31) ? __popc(bits[w] & ((1u << (x & 31)) - 1u)) : 0); };
-          const int rk0 = rank(o0), total = rank(o1) - rk0;
-          if (stay) pick = 4;
-          else if (total > 0) {
-            const int t = rk0 + nm_bounded(nm_action_draw(base64, lane), total);
-            int lo = w0, hi = w1;
-            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((int)cum[mid] <= t) lo = mid; else hi = mid - 1; }
-            pick = lo * 32 + nth_set_bit(bits[lo], t - (int)cum[lo]) - o0;
-          }
-          prm.sample_out[a * AC_N + lane] = pick;
-        } else {
-        int total = 0;
-        for (int w = w0; w <= w1; w++) if (bits[w]) total += __popc(word_at(w));
-        if (stay) pick = 4;
-        else if (total > 0) {
-          int jj = nm_bounded(nm_action_draw(base64, lane), total);
-          for (int w = w0; w <= w1; w++) {
-            if (!bits[w]) continue;
-            uint32_t x = word_at(w);
-            int cnt = __popc(x);
-            if (jj < cnt) { pick = w * 32 + (int)__fns(x, 0, jj + 1) - o0; break; }
-            jj -= cnt;
-          }
-        }
-        prm.sample_out[a * AC_N + lane] = pick;
-        }
-      }
-      __syncwarp();
+    if (prm.sample_out) {      // queued for the built-in policy (resolved NM_OBS_BATCH agents at a time, top of the loop)
+      const uint32_t nz = __ballot_sync(0xffffffffu, mw != 0);
+      bb[nb * 33 + lane] = mw;
+      if (lane == 0) { bb[nb * 33 + 32] = nz; ba[nb] = (uint16_t)(p - p_lo); }
+      nb++;
     }
     // ---- AgentId, CurrentTick ----
     if (lane == 0) st16(rec + L.o_ids, make_uint4(pack2(my_id, tick), 0, 0, 0));
     // ---- Entity rows ----
+    // Eight rows (8 x 62 bytes = 31 whole 16-byte chunks) at a time through a per-warp buffer: lane (j, q) copies columns
+    // q, q+4, ... of the group's j-th visible row, then 31 lanes store one chunk each.  Rows past n_vis are zeros.
     {
-      const int n_el = n_vis * EA_N_OBS;
       const int n_chunks = min(nm_align16(L.n_ent * EA_N_OBS * 2) / 16, (max(n_vis, pv) * EA_N_OBS * 2 + 15) / 16);
       n_stored += n_chunks;
+      const int ej = lane >> 2, eq = lane & 3;
       #pragma unroll 1
-      for (int k = lane; k < n_chunks; k += 32) {
-        int e0 = k * 8;
-        uint4 v = zero4;
-        if (e0 < n_el) {
-          // 8 consecutive int16 of the row-major [n_vis][31] block: at most one row change inside
-          int row = e0 / EA_N_OBS, col = e0 - row * EA_N_OBS;
-          int vr = s_vis[row], vr_next = row + 1 < n_vis ? (int)s_vis[row + 1] : -1;
-          int vals[8];
+      for (int g = 0; 31 * g < n_chunks; g++) {
+        const int i = 8 * g + ej;
+        int16_t *dst = ebuf + ej * EA_N_OBS + eq;
+        if (i < n_vis) {
+          const int vr = s_vis[i];
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            vals[j] = vr >= 0 ? (int)OENT(col, vr) : 0;
-            if (++col == EA_N_OBS) { col = 0; vr = vr_next; }
-          }
-          v = make_uint4(pack2(vals[0], vals[1]), pack2(vals[2], vals[3]), pack2(vals[4], vals[5]), pack2(vals[6], vals[7]));
+          for (int t = 0; t < 8; t++) if (eq + 4 * t < EA_N_OBS) dst[4 * t] = OENT(eq + 4 * t, vr);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 8; t++) if (eq + 4 * t < EA_N_OBS) dst[4 * t] = 0;
         }
-        st16(rec + L.o_entity + k * 16, v);
+        __syncwarp();
+        const int k = 31 * g + lane;
+        if (lane < 31 && k < n_chunks) st16(rec + L.o_entity + k * 16, ((const uint4 *)ebuf)[lane]);
+        __syncwarp();
       }
     }
     // ---- Inventory rows ----
@@ -644,22 +696,29 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
           // materials of the 8 tiles in order: the rest of window row tw_dr, then the start of the next one
           const uint32_t a8 = fetch8(rrA * S + ccA), b8 = fetch8((rrA + 1) * S + c0 - vis);
           const uint32_t mats = tw_first >= 8 ? a8 : ((a8 & ((1u << (4 * tw_first)) - 1u)) | (b8 << (4 * tw_first)));
-          int v[24];
+          // (row, col) of a tile as one word, col in the high half: tile t of the group is a lane-dependent constant away
+          // from the group's first tile; tiles past the end of the window (last group only) are zeros
+          const uint32_t rcA = pack2(rrA, ccA), mv = mats & tw_matmask;
+          uint32_t rc[8], mt[8];
 #pragma unroll
           for (int t = 0; t < 8; t++) {
-            const bool ok = w + t < n_tiles;
-            const int nx = t >= tw_first ? 1 : 0;          // in the next window row?
-            v[3 * t] = ok ? rrA + nx : 0;
-            v[3 * t + 1] = ok ? ccA + t - nx * L.win : 0;
-            v[3 * t + 2] = ok ? (int)((mats >> (4 * t)) & 15u) : 0;
+            const uint32_t d_same = (uint32_t)t << 16, d_next = ((uint32_t)(t - L.win) << 16) + 1u;
+            rc[t] = (rcA + (t >= tw_first ? d_next : d_same)) & (t < tw_nval ? 0xffffffffu : 0u);
+            mt[t] = (mv >> (4 * t)) & 15u;
+          }
+          // int16 stream row0 col0 mat0 row1 col1 mat1 ... as 12 words
+          uint32_t wd[12];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            wd[3 * u] = rc[2 * u];
+            wd[3 * u + 1] = mt[2 * u] | (rc[2 * u + 1] << 16);
+            wd[3 * u + 2] = (rc[2 * u + 1] >> 16) | (mt[2 * u + 1] << 16);
           }
           uint8_t *dst = rec + L.o_tile + lane * 48;
           const int last = nm_align16(n_tiles * 6);
 #pragma unroll
           for (int q = 0; q < 3; q++)
-            if (lane * 48 + q * 16 < last)
-              st16(dst + q * 16, make_uint4(pack2(v[8 * q], v[8 * q + 1]), pack2(v[8 * q + 2], v[8 * q + 3]),
-                                            pack2(v[8 * q + 4], v[8 * q + 5]), pack2(v[8 * q + 6], v[8 * q + 7])));
+            if (lane * 48 + q * 16 < last) st16(dst + q * 16, make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]));
         }
       } else
       #pragma unroll 1
