@@ -28,6 +28,7 @@
 #define NM_BIG_OBS_AGENTS 128    // agents per CTA of the big observation kernel
 #define NM_OBS_CELL 16           // observation kernel: side of the cells the alive rows are bucketed by (>= 2 * vision)
 #define NM_OBS_BATCH 5           // observation kernel: agents per warp whose built-in-policy heads are resolved together (5 x 12 heads = 60 lanes)
+#define NM_OBS_ENT_SKEW 8         // observation kernel (small family): int16 of padding between staged entity columns
 #define OM_NONZERO (1u << 16)
 #define OM_TASK (1u << 17)
 

@@ -23,7 +23,9 @@ struct OSmall {
   static constexpr bool kStage = true;
   static constexpr bool kStd = false;
   typedef StdShape Shape;
-  static __device__ __forceinline__ int ent_idx(int col, int row, int R) { return col * R + row; }
+  // staged columns are 16 bytes apart from a multiple of 128: the four lanes that read columns c, c+1, c+2, c+3 of one row
+  // (Entity gather) hit four different banks
+  static __device__ __forceinline__ int ent_idx(int col, int row, int R) { return col * (R + NM_OBS_ENT_SKEW) + row; }
 };
 struct OStd : OSmall {
   static constexpr bool kStd = true;
@@ -107,9 +109,10 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   size_t off = 0;
   auto carve = [&](size_t bytes) { uint8_t *q = smem + off; off = (off + bytes + 15) & ~(size_t)15; return q; };
   const uint32_t ent_bytes = (uint32_t)(EA_N_OBS * R * 2), st_bytes = (uint32_t)(R * 2);
+  const uint32_t ent_smem_bytes = (uint32_t)(EA_N_OBS * (R + NM_OBS_ENT_SKEW) * 2);
   const uint32_t item_bytes = (uint32_t)(IS_N * ICAP * 2), map_bytes = (uint32_t)(S * S / 2);
   const int16_t *const g_ent = prm.ent + (size_t)env * (V::kStage ? (size_t)EA_N * R : (size_t)NM_BIG_ENT_STRIDE * R);
-  int16_t *s_ent = V::kStage ? (int16_t *)carve(ent_bytes) : nullptr;
+  int16_t *s_ent = V::kStage ? (int16_t *)carve(ent_smem_bytes) : nullptr;
   int16_t *s_status = V::kStage ? (int16_t *)carve(st_bytes) : nullptr;
   int16_t *s_item = V::kStage ? (int16_t *)carve(item_bytes) : nullptr;
   const uint32_t *s_map = V::kStage ? (const uint32_t *)carve(map_bytes)        // 4 bits per tile
@@ -143,7 +146,9 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   int *s_head = (int *)carve((3 * AC_N + 2) * 4);       // head offsets, lengths, work-list length and cursor, heads by length
   uint64_t *s_hash = (uint64_t *)carve((size_t)AP * 8);     // built-in policy: one 64-bit draw per agent, computed by one thread each
   uint32_t *s_meta = (uint32_t *)carve((size_t)AP * 4);
-  uint16_t *s_work = (uint16_t *)carve((size_t)AP * 2);
+  // work list entries: agent (relative to p_lo) | dead << 10 | the agent's two candidate ranges of the cell-ordered row list
+  // (begin A << 12 | count A << 24 | begin B << 36 | count B << 48)
+  uint64_t *s_work = (uint64_t *)carve((size_t)AP * 8);
   uint64_t *bar = (uint64_t *)carve(16);
 
   long long t_prev = clock64();
@@ -165,7 +170,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   if (V::kStage && tid == 0) {
     mbar_expect_tx(bar, ent_bytes + st_bytes + map_bytes);
     const int16_t *ge = g_ent;
-    bulk_g2s(s_ent, ge, ent_bytes, bar);
+    for (int k = 0; k < EA_N_OBS; k++) bulk_g2s(s_ent + k * (R + NM_OBS_ENT_SKEW), ge + (size_t)k * R, (uint32_t)(R * 2), bar);
     bulk_g2s(s_status, ge + (size_t)EA_STATUS * R, st_bytes, bar);
     bulk_g2s((void *)s_map, prm.map + (size_t)env * map_bytes, map_bytes, bar);
     const uint32_t col_bytes = (uint32_t)min(item_hi, ICAP) * 2;       // only the live prefix of each item column
@@ -319,14 +324,33 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
       bool alive = p < p_hi && status_of(p) == ES_ALIVE;
       bool work = alive || (p < p_hi && ((meta & OM_NONZERO) || prm.obs_full));
       unsigned bm = __ballot_sync(0xffffffffu, work);
-      if (work) s_work[n + __popc(bm & ((1u << lane) - 1))] = (uint16_t)(p | (alive ? 0 : 0x8000));
+      if (work) s_work[n + __popc(bm & ((1u << lane) - 1))] = (uint64_t)((p - p_lo) | (alive ? 0 : 0x400));
       n += __popc(bm);
     }
     if (lane == 0) { s_head[2 * AC_N] = n; s_head[2 * AC_N + 1] = 0; }
   }
   __syncthreads();
-  OPHASE();      // 35 work list
   const int n_work = s_head[2 * AC_N];
+  if (use_cells) {
+    // the rows listed in the (at most 2 x 2) cells under an agent's window are two contiguous ranges of the cell-ordered
+    // row list; found here by one thread per agent instead of by every lane of the warp that assembles the record
+    #pragma unroll 1
+    for (int wi = tid; wi < n_work; wi += T) {
+      const uint64_t e = s_work[wi];
+      if (e & 0x400) continue;
+      const int p = p_lo + (int)(e & 0x3ff);
+      const int r0 = OENT(EA_ROW, p), c0 = OENT(EA_COL, p);
+      const int cr0 = (int)((unsigned)max(r0 - vis, 0) / NM_OBS_CELL), cr1 = (int)((unsigned)min(r0 + vis, S - 1) / NM_OBS_CELL);
+      const int cc0 = (int)((unsigned)max(c0 - vis, 0) / NM_OBS_CELL), cc1 = (int)((unsigned)min(c0 + vis, S - 1) / NM_OBS_CELL);
+      const int ca = cr0 * ncx + cc0;
+      const int begA = ca ? s_cend[ca - 1] : 0, endA = s_cend[cr0 * ncx + cc1];
+      int begB = 0, endB = 0;
+      if (cr1 > cr0) { const int cb = cr1 * ncx + cc0; begB = s_cend[cb - 1]; endB = s_cend[cr1 * ncx + cc1]; }
+      s_work[wi] = e | ((uint64_t)begA << 12) | ((uint64_t)(endA - begA) << 24) | ((uint64_t)begB << 36) | ((uint64_t)(endB - begB) << 48);
+    }
+    __syncthreads();
+  }
+  OPHASE();      // 35 work list
   // Tile window, fast path (window at least 8 wide, at most 32 groups of 8 tiles): lane g owns tiles 8g..8g+7 of
   // the row-major window, which lie in at most two window rows.  Where they lie does not depend on the agent.
   const int tw_tiles = L.win * L.win, tw_groups = (tw_tiles + 7) / 8;
@@ -396,14 +420,14 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
             for (uint32_t mm = wm; mm; mm &= mm - 1) total += __popc(word_at(__ffs(mm) - 1));
             if (total > 0) {
               int jj = nm_bounded(nm_action_draw(base64, h), total);
+              int wsel = w1;
               #pragma unroll 1
               for (uint32_t mm = wm; mm; mm &= mm - 1) {
-                const int w = __ffs(mm) - 1;
-                const uint32_t x = word_at(w);
-                const int cnt = __popc(x);
-                if (jj < cnt) { pick = w * 32 + nth_set_bit(x, jj) - o0; break; }
+                const int w = __ffs(mm) - 1, cnt = __popc(word_at(w));
+                if (jj < cnt) { wsel = w; break; }
                 jj -= cnt;
               }
+              pick = wsel * 32 + nth_set_bit(word_at(wsel), jj) - o0;
             }
           }
           picks[sl * AC_N + h] = (int16_t)pick;
@@ -419,8 +443,8 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
       nb = 0;
     }
     if (wi >= n_work) break;
-    const int went = s_work[wi];
-    const int p = went & 0x7fff;
+    const uint64_t went = s_work[wi];
+    const int p = p_lo + (int)((uint32_t)went & 0x3ffu);
     const size_t a = (size_t)env * P + p;
     uint8_t *rec = prm.obs + a * L.stride;
     // The record lives in HBM across ticks, so only bytes that can differ from last tick's
@@ -428,13 +452,13 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     // Inventory / Market that are non-zero, whether the Task block is in place, whether the
     // record is non-zero at all.  obs_full = 1 rewrites every byte (roofline / A-B mode).
     const uint32_t meta = s_meta[p - p_lo];
-    if (went & 0x8000) {                     // dead or absent agents get the zero pad record
+    if ((uint32_t)went & 0x400u) {           // dead or absent agents get the zero pad record
       // ... and every head of the built-in policy picks 0: written once, when the agent leaves (the action
       // buffer must start zeroed, which nmmo_set_autosample's caller guarantees)
       if (prm.sample_out && lane < AC_N) prm.sample_out[a * AC_N + lane] = 0;
       for (int k = lane; k < L.stride / 16; k += 32) st16(rec + k * 16, zero4);
       n_stored += L.stride / 16;
-      if (lane == 0) prm.obs_meta[a] = 0;
+      if (lane == 0) s_meta[p - p_lo] = 0;
       continue;
     }
     const uint32_t held = prm.obs_full ? meta_full : meta;      // what the record is taken to hold
@@ -447,16 +471,10 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     auto in_window = [&](uint32_t pos) -> bool {
       return (uint32_t)((int)(pos >> 16) - r0) <= (uint32_t)(2 * vis) && (uint32_t)((int)(pos & 0xffffu) - c0) <= (uint32_t)(2 * vis);
     };
-    // the rows listed in the (at most 2 x 2) cells under the window: two contiguous ranges of the cell-ordered row list
-    const int cr0 = (int)((unsigned)max(r0 - vis, 0) / NM_OBS_CELL), cr1 = (int)((unsigned)min(r0 + vis, S - 1) / NM_OBS_CELL);
-    const int cc0 = (int)((unsigned)max(c0 - vis, 0) / NM_OBS_CELL), cc1 = (int)((unsigned)min(c0 + vis, S - 1) / NM_OBS_CELL);
-    int begA = 0, endA = 0, begB = 0, endB = 0;
-    if (use_cells) {
-      const int ca = cr0 * ncx + cc0;
-      begA = ca ? s_cend[ca - 1] : 0; endA = s_cend[cr0 * ncx + cc1];
-      if (cr1 > cr0) { const int cb = cr1 * ncx + cc0; begB = s_cend[cb - 1]; endB = s_cend[cr1 * ncx + cc1]; }
-    }
-    const int nA = endA - begA, n_cand = nA + endB - begB;
+    // candidates: the agent's two ranges of the cell-ordered row list (found when the work list was built)
+    const int begA = (int)((uint32_t)(went >> 12) & 0xfffu), nA = (int)((uint32_t)(went >> 24) & 0xfffu);
+    const int begB = (int)((uint32_t)(went >> 36) & 0xfffu), nB = (int)((uint32_t)(went >> 48) & 0xfffu);
+    const int n_cand = nA + nB;
     if (use_cells && n_cand <= 32) {
       // the common case: one candidate per lane; a hit's place in table order is the number of hits with a smaller row
       int row = 0x7fffffff;
@@ -498,14 +516,9 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
       for (int w = lane; w < RW; w += 32) vbm[w] = 0;
       __syncwarp();
       #pragma unroll 1
-      for (int cr = cr0; cr <= cr1; cr++) {                  // the cells of one cell row are adjacent in the list
-        const int ca = cr * ncx + cc0;
-        const int beg = ca ? s_cend[ca - 1] : 0, end = s_cend[cr * ncx + cc1];
-        #pragma unroll 1
-        for (int i = beg + lane; i < end; i += 32) {
-          const int row = s_crow[i];
-          if (in_window(s_pos[row])) atomicOr(&vbm[row >> 5], 1u << (row & 31));
-        }
+      for (int i = lane; i < n_cand; i += 32) {
+        const int row = s_crow[i < nA ? begA + i : begB + i - nA];
+        if (in_window(s_pos[row])) atomicOr(&vbm[row >> 5], 1u << (row & 31));
       }
       __syncwarp();
       #pragma unroll 1
@@ -615,7 +628,11 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     // RewardWrapper.observation hooks
     // (takeru: Give.InventoryItem[:-1], Give.Target[:-1], GiveGold.Target[:-1], GiveGold.Price[1:]
     //  stay at the template's zeros -- they were never filled in, see no_give above)
-    if (wrapper == NW_START_KIT) mw &= ~one_bit(L.m_sell_price + prm.stats[a * ST_N + ST_PREV_PRICE]);
+    if (wrapper == NW_START_KIT) {
+      int prev = 0;
+      if (lane == 0) prev = prm.stats[a * ST_N + ST_PREV_PRICE];
+      mw &= ~one_bit(L.m_sell_price + __shfl_sync(0xffffffffu, prev, 0));
+    }
     // out: 16 mask entries (half a word) become the 16 bytes of one store
     // (at most 1024 entries = 64 stores: two per lane; lane k's come from the words of lanes k / 2 and 16 + k / 2)
 #pragma unroll
@@ -699,20 +716,22 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
           // (row, col) of a tile as one word, col in the high half: tile t of the group is a lane-dependent constant away
           // from the group's first tile; tiles past the end of the window (last group only) are zeros
           const uint32_t rcA = pack2(rrA, ccA), mv = mats & tw_matmask;
-          uint32_t rc[8], mt[8];
+          // tiles of the group's second window row: one row down, L.win columns back.  A group holds 8 tiles or (the last
+          // one: an odd square is 1 mod 8) a single tile, whose other seven stay zero
+          const uint32_t rcN = rcA + 1u - ((uint32_t)L.win << 16);
+          uint32_t rc[8];
 #pragma unroll
-          for (int t = 0; t < 8; t++) {
-            const uint32_t d_same = (uint32_t)t << 16, d_next = ((uint32_t)(t - L.win) << 16) + 1u;
-            rc[t] = (rcA + (t >= tw_first ? d_next : d_same)) & (t < tw_nval ? 0xffffffffu : 0u);
-            mt[t] = (mv >> (4 * t)) & 15u;
-          }
-          // int16 stream row0 col0 mat0 row1 col1 mat1 ... as 12 words
+          for (int t = 0; t < 8; t++) rc[t] = ((t >= tw_first ? rcN : rcA) + ((uint32_t)t << 16)) & (t == 0 || tw_nval == 8 ? 0xffffffffu : 0u);
+          // int16 stream row0 col0 mat0 row1 col1 mat1 ... as 12 words; the materials of two tiles are spread into the
+          // two halves of one word (y) and merged with the neighbouring row / col halves by byte permutes
           uint32_t wd[12];
 #pragma unroll
           for (int u = 0; u < 4; u++) {
+            const uint32_t x = (mv >> (8 * u)) & 0xffu;
+            const uint32_t y = (x | (x << 12)) & 0x000f000fu;
             wd[3 * u] = rc[2 * u];
-            wd[3 * u + 1] = mt[2 * u] | (rc[2 * u + 1] << 16);
-            wd[3 * u + 2] = (rc[2 * u + 1] >> 16) | (mt[2 * u + 1] << 16);
+            wd[3 * u + 1] = __byte_perm(y, rc[2 * u + 1], 0x5410);
+            wd[3 * u + 2] = __byte_perm(rc[2 * u + 1], y, 0x7632);
           }
           uint8_t *dst = rec + L.o_tile + lane * 48;
           const int last = nm_align16(n_tiles * 6);
@@ -742,9 +761,13 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
                                           pack2(v[8 * q + 4], v[8 * q + 5]), pack2(v[8 * q + 6], v[8 * q + 7])));
       }
     }
-    if (lane == 0) prm.obs_meta[a] = (uint32_t)n_vis | ((uint32_t)n_inv << 8) | OM_NONZERO | OM_TASK | ((uint32_t)n_mkt << 18);
+    if (lane == 0) s_meta[p - p_lo] = (uint32_t)n_vis | ((uint32_t)n_inv << 8) | OM_NONZERO | OM_TASK | ((uint32_t)n_mkt << 18);
     __syncwarp();
   }
+  // what the records hold now goes back in one coalesced pass (s_meta entries of agents without work are unchanged)
+  __syncthreads();
+  #pragma unroll 1
+  for (int i = tid; i < p_hi - p_lo; i += T) prm.obs_meta[(size_t)env * P + p_lo + i] = s_meta[i];
   if (!V::kStd && prm.prof && lane == 0) {
     long long t_ = clock64();
     atomicAdd(&prm.prof[40], (unsigned long long)(t_ - w_t0));          // warp-busy cycles in the record loop
