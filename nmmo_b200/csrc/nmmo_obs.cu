@@ -289,6 +289,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     dst[0] = make_uint4(pack2(row[0], row[1]), pack2(row[2], row[3]), pack2(row[4], row[5]), pack2(row[6], row[7]));
     dst[1] = make_uint4(pack2(row[8], row[9]), pack2(row[10], row[11]), pack2(row[12], row[13]), pack2(row[14], row[15]));
   }
+  fence_async_smem();      // the block is later read by bulk copies (async proxy)
   __syncthreads();
   OPHASE();      // 34 market rows
 
@@ -693,8 +694,12 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
       st16(rec + L.o_inventory + k * 16, v);
     }
     // ---- Market block ----
+    // one TMA bulk copy from the env's block in shared memory (identical for every agent); rows the record still holds
+    // beyond it are zeroed
     n_stored += max(n_mkt, pm) * 2;
-    for (int k = lane; k < max(n_mkt, pm) * 2; k += 32) st16(rec + L.o_market + k * 16, k < n_mkt * 2 ? ((const uint4 *)s_mkt)[k] : zero4);
+    if (lane == 0 && n_mkt > 0) { bulk_s2g(rec + L.o_market, s_mkt, (uint32_t)n_mkt * (IA_N_OBS * 2)); bulk_commit(); }
+    #pragma unroll 1
+    for (int k = n_mkt * 2 + lane; k < pm * 2; k += 32) st16(rec + L.o_market + k * 16, zero4);
     // ---- Task embedding (constant within an episode) ----
     if (!task_ok) {
       n_stored += L.task_dim * 2 / 16;
@@ -764,6 +769,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     if (lane == 0) s_meta[p - p_lo] = (uint32_t)n_vis | ((uint32_t)n_inv << 8) | OM_NONZERO | OM_TASK | ((uint32_t)n_mkt << 18);
     __syncwarp();
   }
+  if (lane == 0) bulk_wait_all();      // this warp's Market copies have left shared memory and reached the records
   // what the records hold now goes back in one coalesced pass (s_meta entries of agents without work are unchanged)
   __syncthreads();
   #pragma unroll 1
