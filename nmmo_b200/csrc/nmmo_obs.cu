@@ -360,6 +360,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   const int tw_first = min(8, L.win - tw_dc);             // tiles of the group in its first window row
   const int tw_nval = min(8, max(0, tw_tiles - lane * 8));                 // tiles of the group that exist
   const uint32_t tw_matmask = tw_nval >= 8 ? 0xffffffffu : ((1u << (4 * tw_nval)) - 1u);
+  const uint32_t tw_full = tw_nval == 8 ? 0xffffffffu : 0u, tw_unit = tw_full & 0x10000u;      // a column step; 0 where tiles 1..7 do not exist
   auto fetch8 = [&](int i) -> uint32_t {                    // the 8 nibbles of tiles i..i+7
     const int w = i >> 3, sh = (i & 7) * 4;
     return __funnelshift_r(s_map[w], s_map[w + 1], sh);
@@ -659,23 +660,46 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     {
       const int n_chunks = min(nm_align16(L.n_ent * EA_N_OBS * 2) / 16, (max(n_vis, pv) * EA_N_OBS * 2 + 15) / 16);
       n_stored += n_chunks;
-      const int ej = lane >> 2, eq = lane & 3;
-      #pragma unroll 1
-      for (int g = 0; 31 * g < n_chunks; g++) {
-        const int i = 8 * g + ej;
-        int16_t *dst = ebuf + ej * EA_N_OBS + eq;
-        if (i < n_vis) {
-          const int vr = s_vis[i];
+      if (V::kStage) {
+        const int ej = lane >> 2, eq = lane & 3;
+        #pragma unroll 1
+        for (int g = 0; 31 * g < n_chunks; g++) {
+          const int i = 8 * g + ej;
+          int16_t *dst = ebuf + ej * EA_N_OBS + eq;
+          if (i < n_vis) {
+            const int vr = s_vis[i];
 #pragma unroll
-          for (int t = 0; t < 8; t++) if (eq + 4 * t < EA_N_OBS) dst[4 * t] = OENT(eq + 4 * t, vr);
-        } else {
+            for (int t = 0; t < 8; t++) if (eq + 4 * t < EA_N_OBS) dst[4 * t] = OENT(eq + 4 * t, vr);
+          } else {
 #pragma unroll
-          for (int t = 0; t < 8; t++) if (eq + 4 * t < EA_N_OBS) dst[4 * t] = 0;
+            for (int t = 0; t < 8; t++) if (eq + 4 * t < EA_N_OBS) dst[4 * t] = 0;
+          }
+          __syncwarp();
+          const int k = 31 * g + lane;
+          if (lane < 31 && k < n_chunks) st16(rec + L.o_entity + k * 16, ((const uint4 *)ebuf)[lane]);
+          __syncwarp();
         }
-        __syncwarp();
-        const int k = 31 * g + lane;
-        if (lane < 31 && k < n_chunks) st16(rec + L.o_entity + k * 16, ((const uint4 *)ebuf)[lane]);
-        __syncwarp();
+      } else {
+        // big family: the table is read in place (HBM / L2), so the chunks are independent of each other and several
+        // iterations' loads are in flight: a lane gathers the 8 consecutive int16 of its chunk (at most one row change)
+        const int n_el = n_vis * EA_N_OBS;
+        #pragma unroll 1
+        for (int k = lane; k < n_chunks; k += 32) {
+          const int e0 = k * 8;
+          uint4 v = zero4;
+          if (e0 < n_el) {
+            int row = e0 / EA_N_OBS, col = e0 - row * EA_N_OBS;
+            int vr = s_vis[row], vr_next = row + 1 < n_vis ? (int)s_vis[row + 1] : -1;
+            int vals[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              vals[j] = vr >= 0 ? (int)OENT(col, vr) : 0;
+              if (++col == EA_N_OBS) { col = 0; vr = vr_next; }
+            }
+            v = make_uint4(pack2(vals[0], vals[1]), pack2(vals[2], vals[3]), pack2(vals[4], vals[5]), pack2(vals[6], vals[7]));
+          }
+          st16(rec + L.o_entity + k * 16, v);
+        }
       }
     }
     // ---- Inventory rows ----
@@ -723,10 +747,11 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
           const uint32_t rcA = pack2(rrA, ccA), mv = mats & tw_matmask;
           // tiles of the group's second window row: one row down, L.win columns back.  A group holds 8 tiles or (the last
           // one: an odd square is 1 mod 8) a single tile, whose other seven stay zero
-          const uint32_t rcN = rcA + 1u - ((uint32_t)L.win << 16);
+          const uint32_t rcA1 = rcA & tw_full, rcN1 = (rcA + 1u - ((uint32_t)L.win << 16)) & tw_full;
           uint32_t rc[8];
+          rc[0] = rcA;
 #pragma unroll
-          for (int t = 0; t < 8; t++) rc[t] = ((t >= tw_first ? rcN : rcA) + ((uint32_t)t << 16)) & (t == 0 || tw_nval == 8 ? 0xffffffffu : 0u);
+          for (int t = 1; t < 8; t++) rc[t] = (t >= tw_first ? rcN1 : rcA1) + (uint32_t)t * tw_unit;      // one select, one multiply-add
           // int16 stream row0 col0 mat0 row1 col1 mat1 ... as 12 words; the materials of two tiles are spread into the
           // two halves of one word (y) and merged with the neighbouring row / col halves by byte permutes
           uint32_t wd[12];
