@@ -89,7 +89,8 @@ struct OBigStd : OBig {
 template <class V>
 __device__ __forceinline__ void obs_body(const NmParams &prm) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
+  constexpr int T = NM_OBS_THREADS, NW = T >> 5;      // (compile-time: the shared-memory map of the std kernels folds into immediates)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // small: one CTA per env, all of its agents; big: AP agents per CTA, parts CTAs per env
   const NmCfg<V::kStd> c{prm.cfg};
   // record layout and table shape: immediates in the std instantiation, run-time values otherwise
@@ -809,16 +810,16 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   if (lane == 0) atomicAdd(&prm.counters[4], (unsigned long long)n_stored * 16ULL + ((warp == 0 && p_lo == 0) ? (unsigned long long)(ent_bytes + st_bytes + (uint32_t)(IS_N * 2 * item_hi) + map_bytes) : 0ULL));
 }
 
-extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, 3)
+extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, NM_OBS_CTAS_PER_SM)
 nmmo_obs_kernel(const __grid_constant__ NmParams prm) { obs_body<OSmall>(prm); }
 
-extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, 3)
+extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, NM_OBS_CTAS_PER_SM)
 nmmo_obs_std_kernel(const __grid_constant__ NmParams prm) { obs_body<OStd>(prm); }
 
-extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, 3)
+extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, NM_OBS_CTAS_PER_SM)
 nmmo_obs_big_kernel(const __grid_constant__ NmParams prm) { obs_body<OBig>(prm); }
 
-extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, 3)
+extern "C" __global__ void __launch_bounds__(NM_OBS_THREADS, NM_OBS_CTAS_PER_SM)
 nmmo_obs_big_std_kernel(const __grid_constant__ NmParams prm) { obs_body<OBigStd>(prm); }
 
 // ============================================================= action sampler kernel ===
