@@ -187,11 +187,15 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     #pragma unroll 1
     for (int i = tid; i < p_hi - p_lo; i += T)
       s_hash[i] = nm_hash64(prm.sample_seed + (uint64_t)(prm.env_base + env), (uint32_t)tick, RS_ACTION, (uint32_t)(p_lo + i), 0);
-  if (V::kStage) {
+  if (V::kStage && warp == 0) {      // one warp polls (sixteen would spin in the issue slots the SM's other CTA is using) ...
     while (!mbar_try_wait(bar, 0)) {}
     while (!mbar_try_wait(bar + 1, 0)) {}
   }
   __syncthreads();
+  if (V::kStage) {                   // ... and every thread then observes the completed phases itself (returns at once)
+    while (!mbar_try_wait(bar, 0)) {}
+    while (!mbar_try_wait(bar + 1, 0)) {}
+  }
   OPHASE();      // 32 load
 
   OCtx o;
@@ -552,6 +556,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     n_vis = min(n_vis, L.n_ent);
     const int n_inv = min(s_invn[p - p_lo], NINV);
     const uint16_t *inv = s_inv + (p - p_lo) * NINV;
+    __syncwarp();      // s_vis is complete
     // ---- ActionTargets (as bits: this lane's word of the record's mask entries) ----
     uint32_t mw = tmpl_word;
     // a ballot over up to 32 consecutive entries, the first of them entry o of the masks
