@@ -16,8 +16,10 @@
 
 #define NM_EV_CAP 1024          // per-env per-tick event ring (shared memory)
 #define NM_STEP_THREADS 256
-#define NM_OBS_THREADS 512
-#define NM_OBS_CTAS_PER_SM 2
+#ifndef NM_OBS_THREADS
+#define NM_OBS_THREADS 512         // observation kernels: 16 warps per CTA ...
+#define NM_OBS_CTAS_PER_SM 2       // ... two CTAs per SM
+#endif
 #define NM_SC_N 16              // per-env int32 scalars
 #define NM_DEPL_CAP 1024         // per-env list of depleted tiles kept across ticks (falls back to a map scan beyond)
 #define NM_AGG_REP 256           // replicas of the finished-agent sums (contention spreading)
@@ -28,7 +30,10 @@
 #define NM_BIG_ENT_STRIDE 48     // int16 per row of the row-major entity table (EA_N = 44, padded to 96 bytes)
 #define NM_BIG_OBS_AGENTS 128    // agents per CTA of the big observation kernel
 #define NM_OBS_CELL 16           // observation kernel: side of the cells the alive rows are bucketed by (>= 2 * vision)
-#define NM_OBS_BATCH 8           // observation kernel: agents per warp whose built-in-policy heads are resolved together (5 x 12 heads = 60 lanes)
+#ifndef NM_OBS_BATCH
+#define NM_OBS_BATCH 8
+#endif
+//      NM_OBS_BATCH:           // observation kernel: agents per warp whose built-in-policy heads are resolved together (5 x 12 heads = 60 lanes)
 #define NM_OBS_ENT_SKEW 8         // observation kernel (small family): int16 of padding between staged entity columns
 #define OM_NONZERO (1u << 16)
 #define OM_TASK (1u << 17)
