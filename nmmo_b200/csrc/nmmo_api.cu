@@ -77,7 +77,7 @@ static size_t obs_big_smem_bytes(const NmParams &p) {
   s += a16((size_t)p.L.n_mkt * IA_N_OBS * 2); s += a16((size_t)p.L.n_mkt * 2);
   s += a16((size_t)AP * NINV * 2); s += a16((size_t)AP * 4); s += a16(64 * 4);
   s += obs_warp_bytes(p, NW); s += 16;
-  s += a16((3 * AC_N + 2) * 4); s += a16((size_t)AP * 4); s += a16((size_t)AP * 8); s += a16((size_t)((p.R + 31) & ~31) * 4);
+  s += a16((3 * AC_N + 2) * 4); s += a16((size_t)AP * 4); s += a16((size_t)AP * 8) + a16((size_t)AP * 33 * 2) + a16((size_t)AP * 3 * 4); s += a16((size_t)((p.R + 31) & ~31) * 4);
   s += obs_cell_bytes(p, NW) + 64 * 4 + a16((size_t)AP * 8);
   return s + 128;
 }
@@ -100,7 +100,7 @@ static size_t obs_smem_bytes(const NmParams &p) {
   s += a16((size_t)p.L.n_mkt * IA_N_OBS * 2); s += a16((size_t)p.L.n_mkt * 2);
   s += a16((size_t)p.P * NINV * 2); s += a16((size_t)p.P * 4); s += a16(64 * 4);
   s += obs_warp_bytes(p, NW); s += 16;
-  s += a16((3 * AC_N + 2) * 4); s += a16((size_t)p.P * 4); s += a16((size_t)p.P * 8); s += a16((size_t)((p.R + 31) & ~31) * 4);
+  s += a16((3 * AC_N + 2) * 4); s += a16((size_t)p.P * 4); s += a16((size_t)p.P * 8) + a16((size_t)p.P * 33 * 2) + a16((size_t)p.P * 3 * 4); s += a16((size_t)((p.R + 31) & ~31) * 4);
   s += obs_cell_bytes(p, NW) + 64 * 4 + a16((size_t)p.P * 8);
   return s + 64;
 }

@@ -34,6 +34,7 @@
 #define NM_OBS_BATCH 8
 #endif
 //      NM_OBS_BATCH:           // observation kernel: agents per warp whose built-in-policy heads are resolved together (5 x 12 heads = 60 lanes)
+#define NM_OBS_PREFETCH_AHEAD 64  // observation kernel (small family): a CTA prefetches into L2 the tables of the env this many CTAs later
 #define NM_OBS_ENT_SKEW 8         // observation kernel (small family): int16 of padding between staged entity columns
 #define OM_NONZERO (1u << 16)
 #define OM_TASK (1u << 17)
@@ -263,6 +264,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // TMA 1-D bulk copy shared -> global
 __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk prefetch global -> L2 (fire and forget)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

@@ -103,7 +103,9 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   const int NINV = V::kStd ? SH::NINV : c[NC_N_INV], vis = V::kStd ? SH::VIS : c[NC_VISION];
   const int AP = V::kStage ? P : min(P, NM_BIG_OBS_AGENTS);
   const int parts = V::kStage ? 1 : (P + AP - 1) / AP;
-  const int env = V::kStage ? (int)blockIdx.x : (int)blockIdx.x / parts;
+  // small family: highest env first -- the tables the step kernel wrote last are still in L2, and the records this kernel
+  // writes last are the ones the next step kernel (lowest env first) reads first
+  const int env = V::kStage ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x / parts;
   const int p_lo = V::kStage ? 0 : ((int)blockIdx.x % parts) * AP, p_hi = min(P, p_lo + AP);
   const int tick = prm.scalars[(size_t)env * NM_SC_N + SC_TICK];
 
@@ -150,13 +152,45 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   // work list entries: agent (relative to p_lo) | dead << 10 | the agent's two candidate ranges of the cell-ordered row list
   // (begin A << 12 | count A << 24 | begin B << 36 | count B << 48)
   uint64_t *s_work = (uint64_t *)carve((size_t)AP * 8);
+  // per agent (thread-per-agent pre-pass): up to 32 visible rows in table order (+ their count in slot 32; row stride 33
+  // halfwords so that 32 threads walking 32 lists hit different banks) and the Attack / Give target bits of those rows
+  uint16_t *s_va = (uint16_t *)carve((size_t)AP * 33 * 2);
+  uint32_t *s_tg = (uint32_t *)carve((size_t)AP * 3 * 4);
   uint64_t *bar = (uint64_t *)carve(16);
 
   long long t_prev = clock64();
   int ph = 32;
 #define OPHASE() do { if (!V::kStd && prm.prof && tid == 0) { long long t_ = clock64(); atomicAdd(&prm.prof[ph], (unsigned long long)(t_ - t_prev)); t_prev = t_; } ph++; } while (0)
-  if (V::kStage && tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  // The table loads go out before anything else: 41 TMA bulk copies (an entity column each, status, map, the live prefix
+  // of each item column), one per lane of warp 0 -- not one thread issuing them one after the other while the CTA waits.
+  // Nobody else touches the mbarriers before the CTA barrier that follows the polling below.
   const int item_hi = prm.scalars[(size_t)env * NM_SC_N + SC_ITEM_HI];     // rows >= item_hi are free
+  if (V::kStage && warp == 0) {
+    if (lane == 0) {
+      mbar_init(bar, 1); mbar_init(bar + 1, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(bar, ent_bytes + st_bytes + map_bytes);
+    }
+    __syncwarp();
+    const int16_t *ge = g_ent;
+    #pragma unroll 1
+    for (int k = lane; k < EA_N_OBS; k += 32) bulk_g2s(s_ent + k * (R + NM_OBS_ENT_SKEW), ge + (size_t)k * R, (uint32_t)(R * 2), bar);
+    if (lane == 31) bulk_g2s(s_status, ge + (size_t)EA_STATUS * R, st_bytes, bar);
+    if (lane == 30) bulk_g2s((void *)s_map, prm.map + (size_t)env * map_bytes, map_bytes, bar);
+    // (the item copies wait for item_hi, a load from HBM; the copies above do not)
+    const uint32_t col_bytes = (uint32_t)min(item_hi, ICAP) * 2;       // only the live prefix of each item column
+    if (lane == 0) mbar_expect_tx(bar + 1, col_bytes * IS_N);
+    __syncwarp();
+    if (col_bytes && lane < IS_N) bulk_g2s(s_item + lane * ICAP, prm.item + ((size_t)env * IS_N + lane) * CAP, col_bytes, bar + 1);
+  } else if (V::kStage && warp == 1 && lane < 3) {
+    // L2 prefetch for a CTA that starts a few microseconds from now (envs are taken highest first): this kernel writes
+    // 1.7 GB through L2 while it reads 0.2 GB of tables, so a table fetched on demand waits behind the writes
+    const int env_next = env - NM_OBS_PREFETCH_AHEAD;
+    if (env_next >= 0) {
+      if (lane == 0) bulk_prefetch_l2(prm.ent + (size_t)env_next * EA_N * R, (uint32_t)(EA_N_OBS * R * 2));
+      else if (lane == 1) bulk_prefetch_l2(prm.ent + (size_t)env_next * EA_N * R + (size_t)EA_STATUS * R, st_bytes);
+      else bulk_prefetch_l2(prm.map + (size_t)env_next * map_bytes, map_bytes);
+    }
+  }
   if (tid < AC_N) {
     const int off[AC_N] = {L.m_style, L.m_target, L.m_buy, L.m_destroy, L.m_give_item, L.m_give_target,
                            L.m_gold_price, L.m_gold_target, L.m_move, L.m_sell_item, L.m_sell_price, L.m_use};
@@ -166,18 +200,6 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     const int ord[AC_N] = {AC_BUY_ITEM, AC_ATTACK_TARGET, AC_GIVE_TARGET, AC_GOLD_TARGET, AC_GOLD_PRICE, AC_SELL_PRICE,
                            AC_DESTROY_ITEM, AC_GIVE_ITEM, AC_SELL_ITEM, AC_USE_ITEM, AC_MOVE_DIR, AC_ATTACK_STYLE};
     s_head[tid] = off[tid]; s_head[AC_N + tid] = len[tid]; s_head[2 * AC_N + 2 + tid] = ord[tid];
-  }
-  __syncthreads();
-  if (V::kStage && tid == 0) {
-    mbar_expect_tx(bar, ent_bytes + st_bytes + map_bytes);
-    const int16_t *ge = g_ent;
-    for (int k = 0; k < EA_N_OBS; k++) bulk_g2s(s_ent + k * (R + NM_OBS_ENT_SKEW), ge + (size_t)k * R, (uint32_t)(R * 2), bar);
-    bulk_g2s(s_status, ge + (size_t)EA_STATUS * R, st_bytes, bar);
-    bulk_g2s((void *)s_map, prm.map + (size_t)env * map_bytes, map_bytes, bar);
-    const uint32_t col_bytes = (uint32_t)min(item_hi, ICAP) * 2;       // only the live prefix of each item column
-    mbar_expect_tx(bar + 1, col_bytes * IS_N);
-    if (col_bytes)
-      for (int k = 0; k < IS_N; k++) bulk_g2s(s_item + k * ICAP, prm.item + ((size_t)env * IS_N + k) * CAP, col_bytes, bar + 1);
   }
   #pragma unroll 1
   for (int i = tid; i < p_hi - p_lo; i += T) { s_invn[i] = 0; s_meta[i] = prm.obs_meta[(size_t)env * P + p_lo + i]; }
@@ -205,6 +227,23 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   const int wrapper = c[NC_WRAPPER];
   const bool no_give = (wrapper == NW_TAKERU || wrapper == NW_YAOFENG) && c[NC_DISABLE_GIVE];
   const bool no_danger = wrapper == NW_YAOFENG && c[NC_NO_DANGEROUS_NPC];      // yaofeng/reward_wrapper.py:78-81
+  // Work list.  Alive agents (a full record each) and agents that died since their record was last
+  // written (one zero fill) are compacted in id order by the last warp -- here, underneath the other warps' list-building
+  // passes, not in a barrier interval of its own.
+  if (warp == NW - 1) {
+    int n = 0;
+    #pragma unroll 1
+    for (int base = p_lo; base < p_hi; base += 32) {
+      int p = base + lane;
+      uint32_t meta = p < p_hi ? s_meta[p - p_lo] : 0u;
+      bool alive = p < p_hi && status_of(p) == ES_ALIVE;
+      bool work = alive || (p < p_hi && ((meta & OM_NONZERO) || prm.obs_full));
+      unsigned bm = __ballot_sync(0xffffffffu, work);
+      if (work) s_work[n + __popc(bm & ((1u << lane) - 1))] = (uint64_t)((p - p_lo) | (alive ? 0 : 0x400));
+      n += __popc(bm);
+    }
+    if (lane == 0) { s_head[2 * AC_N] = n; s_head[2 * AC_N + 1] = 0; }
+  }
   // one word per table row for the vision-window scan: an empty row can never match
   const bool use_cells = 2 * vis + 1 <= NM_OBS_CELL + 1;      // else (huge vision radius): every row is scanned
   #pragma unroll 1
@@ -318,41 +357,95 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   uint16_t *s_vis = s_vis_all + (size_t)warp * (((L.n_ent * 2 + 15) & ~15) / 2);
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
   long long n_stored = 0;                     // 16-byte chunks stored by this warp
-  // Work list.  Alive agents (a full record each) and agents that died since their record was last
-  // written (one zero fill) are compacted in id order by warp 0; the warps then pull entries off
-  // the list one at a time, so a warp never idles while another still has agents queued.
-  if (warp == 0) {
-    int n = 0;
-    #pragma unroll 1
-    for (int base = p_lo; base < p_hi; base += 32) {
-      int p = base + lane;
-      uint32_t meta = p < p_hi ? s_meta[p - p_lo] : 0u;
-      bool alive = p < p_hi && status_of(p) == ES_ALIVE;
-      bool work = alive || (p < p_hi && ((meta & OM_NONZERO) || prm.obs_full));
-      unsigned bm = __ballot_sync(0xffffffffu, work);
-      if (work) s_work[n + __popc(bm & ((1u << lane) - 1))] = (uint64_t)((p - p_lo) | (alive ? 0 : 0x400));
-      n += __popc(bm);
-    }
-    if (lane == 0) { s_head[2 * AC_N] = n; s_head[2 * AC_N + 1] = 0; }
-  }
-  __syncthreads();
+  // (the work list was compacted by the last warp right after the tables arrived)
   const int n_work = s_head[2 * AC_N];
   if (use_cells) {
-    // the rows listed in the (at most 2 x 2) cells under an agent's window are two contiguous ranges of the cell-ordered
-    // row list; found here by one thread per agent instead of by every lane of the warp that assembles the record
+    // Pre-pass, four threads per agent (the whole CTA for 128 agents).  The rows listed in the (at most 2 x 2) cells under
+    // an agent's window are two contiguous ranges of the cell-ordered row list.  With at most 32 candidates (the common
+    // case) the quad also finds the visible rows, puts them in table order and works out their target bits -- work that
+    // keeps one lane in three busy when a whole warp does it for one agent.
+    // (scratch: one row bitmap per agent, in the sampler's batch words, which are not in use yet; without room for them,
+    //  or with more than 32 bitmap words per agent, every agent takes the warp path)
+    uint32_t *s_pbm = s_bb_all;
+    const int WPL = (RW + 3) >> 2;                    // bitmap words per lane of a quad
+    const bool pre_ok = RW <= 32 && (size_t)AP * RW * 4 <= (size_t)NW * NM_OBS_BATCH * 33 * 4;
     #pragma unroll 1
-    for (int wi = tid; wi < n_work; wi += T) {
-      const uint64_t e = s_work[wi];
-      if (e & 0x400) continue;
-      const int p = p_lo + (int)(e & 0x3ff);
-      const int r0 = OENT(EA_ROW, p), c0 = OENT(EA_COL, p);
-      const int cr0 = (int)((unsigned)max(r0 - vis, 0) / NM_OBS_CELL), cr1 = (int)((unsigned)min(r0 + vis, S - 1) / NM_OBS_CELL);
-      const int cc0 = (int)((unsigned)max(c0 - vis, 0) / NM_OBS_CELL), cc1 = (int)((unsigned)min(c0 + vis, S - 1) / NM_OBS_CELL);
-      const int ca = cr0 * ncx + cc0;
-      const int begA = ca ? s_cend[ca - 1] : 0, endA = s_cend[cr0 * ncx + cc1];
-      int begB = 0, endB = 0;
-      if (cr1 > cr0) { const int cb = cr1 * ncx + cc0; begB = s_cend[cb - 1]; endB = s_cend[cr1 * ncx + cc1]; }
-      s_work[wi] = e | ((uint64_t)begA << 12) | ((uint64_t)(endA - begA) << 24) | ((uint64_t)begB << 36) | ((uint64_t)(endB - begB) << 48);
+    for (int wi0 = 0; wi0 < n_work; wi0 += T / 4) {
+      const int wi = wi0 + (tid >> 2), q = lane & 3;
+      const uint64_t e = wi < n_work ? s_work[wi] : (uint64_t)0x400;
+      const bool alive = !((uint32_t)e & 0x400u);
+      const int pa = (int)((uint32_t)e & 0x3ffu), p = p_lo + pa;
+      int r0 = 0, c0 = 0, begA = 0, nA = 0, begB = 0, n_cand = 0;
+      if (alive) {
+        r0 = OENT(EA_ROW, p); c0 = OENT(EA_COL, p);
+        const int cr0 = (int)((unsigned)max(r0 - vis, 0) / NM_OBS_CELL), cr1 = (int)((unsigned)min(r0 + vis, S - 1) / NM_OBS_CELL);
+        const int cc0 = (int)((unsigned)max(c0 - vis, 0) / NM_OBS_CELL), cc1 = (int)((unsigned)min(c0 + vis, S - 1) / NM_OBS_CELL);
+        const int ca = cr0 * ncx + cc0;
+        begA = ca ? s_cend[ca - 1] : 0;
+        const int endA = s_cend[cr0 * ncx + cc1];
+        int endB = 0;
+        if (cr1 > cr0) { const int cb = cr1 * ncx + cc0; begB = s_cend[cb - 1]; endB = s_cend[cr1 * ncx + cc1]; }
+        nA = endA - begA; n_cand = nA + endB - begB;
+        if (q == 0) s_work[wi] = e | ((uint64_t)begA << 12) | ((uint64_t)nA << 24) | ((uint64_t)begB << 36) | ((uint64_t)(endB - begB) << 48);
+      }
+      const bool fast = pre_ok && alive && n_cand <= 32;      // else the assembling warp searches (bitmap walk)
+      uint32_t *bm = s_pbm + pa * RW;
+      uint16_t *va = s_va + pa * 33;
+      if (fast)
+        #pragma unroll 1
+        for (int t = 0; t < WPL; t++) if (q * WPL + t < RW) bm[q * WPL + t] = 0;
+      __syncwarp();
+      // candidates q, q + 4, ...: the hits are marked in the agent's row bitmap
+      const int its = (__reduce_max_sync(0xffffffffu, fast ? n_cand : 0) + 3) >> 2;
+      #pragma unroll 1
+      for (int it = 0; it < its; it++) {
+        const int i = it * 4 + q;
+        if (fast && i < n_cand) {
+          const int row = s_crow[i < nA ? begA + i : begB + i - nA];
+          const uint32_t pos = s_pos[row];
+          if ((uint32_t)((int)(pos >> 16) - r0) <= (uint32_t)(2 * vis) && (uint32_t)((int)(pos & 0xffffu) - c0) <= (uint32_t)(2 * vis))
+            atomicOr(&bm[row >> 5], 1u << (row & 31));
+        }
+      }
+      __syncwarp();
+      // table order = bitmap order: a lane counts its words, the quad's prefix gives it its place, it writes its rows
+      int cnt = 0;
+      if (fast)
+        #pragma unroll 1
+        for (int t = 0; t < WPL; t++) if (q * WPL + t < RW) cnt += __popc(bm[q * WPL + t]);
+      const int qb = lane & 28;
+      const int c_0 = __shfl_sync(0xffffffffu, cnt, qb), c_1 = __shfl_sync(0xffffffffu, cnt, qb + 1);
+      const int c_2 = __shfl_sync(0xffffffffu, cnt, qb + 2), c_3 = __shfl_sync(0xffffffffu, cnt, qb + 3);
+      int idx = (q > 0 ? c_0 : 0) + (q > 1 ? c_1 : 0) + (q > 2 ? c_2 : 0);
+      int nv = min(c_0 + c_1 + c_2 + c_3, L.n_ent);      // (at most 32: one hit per candidate)
+      if (fast)
+        #pragma unroll 1
+        for (int t = 0; t < WPL; t++) {
+          const int w = q * WPL + t;
+          uint32_t bits = w < RW ? bm[w] : 0u;
+          #pragma unroll 1
+          while (bits && idx < nv) { const int b2 = __ffs(bits) - 1; bits &= bits - 1; va[idx++] = (uint16_t)(w * 32 + b2); }
+        }
+      if (alive && q == 0) va[32] = fast ? (uint16_t)nv : (uint16_t)0xffff;
+      __syncwarp();
+      uint32_t att = 0, give = 0, any = 0;
+      if (fast) {
+        const int my_id = OENT(EA_ID, p);
+        const bool immune = OENT(EA_TIME_ALIVE, p) < c[NC_SPAWN_IMMUNITY], has_inv = s_invn[pa] > 0;
+        #pragma unroll 1
+        for (int i = q; i < nv; i += 4) {
+          const int row = va[i], id = OENT(EA_ID, row), npc_type = OENT(EA_NPC_TYPE, row);
+          const uint32_t pos = s_pos[row];
+          const int er = (int)(pos >> 16) - vis, ec = (int)(pos & 0xffffu) - vis;
+          const bool ok = nm_linf(er, ec, r0, c0) <= c[NC_REACH] && id != my_id && !(immune && id > 0);
+          any |= ok;                                             // the no-op entry is the engine's, before the wrapper edit
+          if (ok && !(no_danger && npc_type > 1)) att |= 1u << i;
+          if (!no_give && has_inv && er == r0 && ec == c0 && npc_type == 0 && id != my_id) give |= 1u << i;
+        }
+      }
+      att |= __shfl_xor_sync(0xffffffffu, att, 1); give |= __shfl_xor_sync(0xffffffffu, give, 1); any |= __shfl_xor_sync(0xffffffffu, any, 1);
+      att |= __shfl_xor_sync(0xffffffffu, att, 2); give |= __shfl_xor_sync(0xffffffffu, give, 2); any |= __shfl_xor_sync(0xffffffffu, any, 2);
+      if (fast && q == 0) { uint32_t *tg = s_tg + pa * 3; tg[0] = att; tg[1] = give; tg[2] = any; }
     }
     __syncthreads();
   }
@@ -374,6 +467,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   // Work items are dealt round-robin when most agents are alive (items of equal cost: no queue traffic) and pulled from a
   // shared cursor otherwise (a zero fill is much cheaper than a record, so a static deal would leave warps idle)
   const bool deal = 2 * n_work > AP;
+  const int its_dealt = deal ? (n_work / NW) * 3 / 4 : 0;      // ... and the last quarter is pulled too: the warps finish together
   // obs_full = 1: every row of every section is rewritten, the Task block included
   const int ms_shift = (lane & 1) * 16;      // mask store: which half of the source word this lane expands
   const uint32_t meta_full = (uint32_t)L.n_ent | ((uint32_t)L.n_inv << 8) | ((uint32_t)L.n_mkt << 18);
@@ -381,8 +475,8 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   #pragma unroll 1
   for (int it = 0;; it++) {
     int wi = warp + it * NW;
-    if (!deal) {
-      if (lane == 0) wi = atomicAdd(&s_head[2 * AC_N + 1], 1);
+    if (it >= its_dealt) {
+      if (lane == 0) wi = its_dealt * NW + atomicAdd(&s_head[2 * AC_N + 1], 1);
       wi = __shfl_sync(0xffffffffu, wi, 0);
     }
     // ---- built-in random policy (optional): uniform over the valid entries of every head ----
@@ -482,40 +576,11 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     const int begA = (int)((uint32_t)(went >> 12) & 0xfffu), nA = (int)((uint32_t)(went >> 24) & 0xfffu);
     const int begB = (int)((uint32_t)(went >> 36) & 0xfffu), nB = (int)((uint32_t)(went >> 48) & 0xfffu);
     const int n_cand = nA + nB;
-    if (use_cells && n_cand <= 32) {
-      // the common case: one candidate per lane; a hit's place in table order is the number of hits with a smaller row
-      int row = 0x7fffffff;
-      if (lane < n_cand) {
-        const int r = s_crow[lane < nA ? begA + lane : begB + lane - nA];
-        if (in_window(s_pos[r])) row = r;
-      }
-      if (RW <= 32) {
-        // a hit's place in table order = hits with a smaller row: the hits are marked in the warp's row bitmap, lane w
-        // counts word w, and a prefix sum over the words gives every hit its rank
-        uint32_t *vbm = s_vbm_all + warp * RW;
-        if (lane < RW) vbm[lane] = 0;
-        __syncwarp();
-        if (row != 0x7fffffff) atomicOr(&vbm[row >> 5], 1u << (row & 31));
-        __syncwarp();
-        const uint32_t wv = lane < RW ? vbm[lane] : 0u;
-        const int pc = __popc(wv);
-        int incl2 = pc;
-        #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) if (d < RW) { const int u = __shfl_up_sync(0xffffffffu, incl2, d); if (lane >= d) incl2 += u; }
-        n_vis = __shfl_sync(0xffffffffu, incl2, (RW - 1) & 31);
-        const int wsel = (row >> 5) & 31;
-        const int below = __shfl_sync(0xffffffffu, incl2 - pc, wsel);
-        const uint32_t wbits = __shfl_sync(0xffffffffu, wv, wsel);
-        const int rank = below + __popc(wbits & ((1u << (row & 31)) - 1u));
-        if (row != 0x7fffffff && rank < L.n_ent) s_vis[rank] = (uint16_t)row;
-      } else {
-        unsigned hits = __ballot_sync(0xffffffffu, row != 0x7fffffff);
-        n_vis = __popc(hits);
-        int rank = 0;
-        #pragma unroll 1
-        for (unsigned h = hits; h; h &= h - 1) rank += __shfl_sync(0xffffffffu, row, __ffs(h) - 1) < row;
-        if (row != 0x7fffffff && rank < L.n_ent) s_vis[rank] = (uint16_t)row;
-      }
+    // the common case (at most 32 candidates): the list and the target bits were made by the pre-pass
+    const uint16_t *vl = s_va + (p - p_lo) * 33;      // this agent's visible rows, in table order
+    const bool pre = use_cells && vl[32] != 0xffffu;
+    if (pre) {
+      n_vis = vl[32];
     } else if (use_cells) {
       // many candidates: they are tested and marked in a row bitmap; walking the bitmap yields them in table order
       uint32_t *vbm = s_vbm_all + warp * RW;
@@ -556,6 +621,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     n_vis = min(n_vis, L.n_ent);
     const int n_inv = min(s_invn[p - p_lo], NINV);
     const uint16_t *inv = s_inv + (p - p_lo) * NINV;
+    if (!pre) vl = s_vis;
     __syncwarp();      // s_vis is complete
     // ---- ActionTargets (as bits: this lane's word of the record's mask entries) ----
     uint32_t mw = tmpl_word;
@@ -565,7 +631,12 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
       const int d = lane - (o >> 5);
       mw |= __funnelshift_l(d == 1 ? bsel : 0u, d == 0 ? bsel : 0u, o & 31);
     };
-    {
+    if (pre) {      // (at most 32 visible rows: one ballot-sized word per head)
+      const uint32_t *tg = s_tg + (p - p_lo) * 3;
+      place(tg[0], L.m_target);
+      if (!no_give) { place(tg[1], L.m_give_target); place(tg[1], L.m_gold_target); }
+      if (!tg[2]) mw |= one_bit(L.m_target + L.n_ent);
+    } else {
       unsigned any = 0;
       const bool immune = OENT(EA_TIME_ALIVE, p) < c[NC_SPAWN_IMMUNITY];
       #pragma unroll 1
@@ -573,7 +644,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
         const int i = base + lane;
         bool ok = false, att = false, give = false;
         if (i < n_vis) {
-          const int row = s_vis[i], id = OENT(EA_ID, row), er = OENT(EA_ROW, row), ec = OENT(EA_COL, row);
+          const int row = vl[i], id = OENT(EA_ID, row), er = OENT(EA_ROW, row), ec = OENT(EA_COL, row);
           const int npc_type = OENT(EA_NPC_TYPE, row);
           ok = nm_linf(er, ec, r0, c0) <= c[NC_REACH] && id != my_id && !(immune && id > 0);
           att = ok && !(no_danger && npc_type > 1);
@@ -673,7 +744,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
           const int i = 8 * g + ej;
           int16_t *dst = ebuf + ej * EA_N_OBS + eq;
           if (i < n_vis) {
-            const int vr = s_vis[i];
+            const int vr = vl[i];
 #pragma unroll
             for (int t = 0; t < 8; t++) if (eq + 4 * t < EA_N_OBS) dst[4 * t] = OENT(eq + 4 * t, vr);
           } else {
@@ -695,7 +766,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
           uint4 v = zero4;
           if (e0 < n_el) {
             int row = e0 / EA_N_OBS, col = e0 - row * EA_N_OBS;
-            int vr = s_vis[row], vr_next = row + 1 < n_vis ? (int)s_vis[row + 1] : -1;
+            int vr = vl[row], vr_next = row + 1 < n_vis ? (int)vl[row + 1] : -1;
             int vals[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
