@@ -34,8 +34,17 @@
 #define NM_OBS_BATCH 8
 #endif
 //      NM_OBS_BATCH:           // observation kernel: agents per warp whose built-in-policy heads are resolved together (5 x 12 heads = 60 lanes)
-#define NM_OBS_PREFETCH_AHEAD 64  // observation kernel (small family): a CTA prefetches into L2 the tables of the env this many CTAs later
-#define NM_OBS_ENT_SKEW 8         // observation kernel (small family): int16 of padding between staged entity columns
+#ifndef NM_OBS_DEAL_NUM
+#define NM_OBS_DEAL_NUM 8           // observation kernel: eighths of the work list dealt round-robin, the rest pulled (measured: 4/8 0.532 ms, 6/8 0.530, 7/8 0.528, all dealt 0.528)
+#endif
+#ifndef NM_OBS_PREFETCH_AHEAD
+#define NM_OBS_PREFETCH_AHEAD 64
+#endif
+//      NM_OBS_PREFETCH_AHEAD:  // observation kernel (small family): a CTA prefetches into L2 the tables of the env this many CTAs later
+#ifndef NM_OBS_ENT_SKEW
+#define NM_OBS_ENT_SKEW 8
+#endif
+//      NM_OBS_ENT_SKEW:         // observation kernel (small family): int16 of padding between staged entity columns
 #define OM_NONZERO (1u << 16)
 #define OM_TASK (1u << 17)
 

@@ -172,8 +172,10 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     }
     __syncwarp();
     const int16_t *ge = g_ent;
-    #pragma unroll 1
-    for (int k = lane; k < EA_N_OBS; k += 32) bulk_g2s(s_ent + k * (R + NM_OBS_ENT_SKEW), ge + (size_t)k * R, (uint32_t)(R * 2), bar);
+    if (NM_OBS_ENT_SKEW == 0) { if (lane == 0) bulk_g2s(s_ent, ge, ent_bytes, bar); }
+    else
+      #pragma unroll 1
+      for (int k = lane; k < EA_N_OBS; k += 32) bulk_g2s(s_ent + k * (R + NM_OBS_ENT_SKEW), ge + (size_t)k * R, (uint32_t)(R * 2), bar);
     if (lane == 31) bulk_g2s(s_status, ge + (size_t)EA_STATUS * R, st_bytes, bar);
     if (lane == 30) bulk_g2s((void *)s_map, prm.map + (size_t)env * map_bytes, map_bytes, bar);
     // (the item copies wait for item_hi, a load from HBM; the copies above do not)
@@ -467,7 +469,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   // Work items are dealt round-robin when most agents are alive (items of equal cost: no queue traffic) and pulled from a
   // shared cursor otherwise (a zero fill is much cheaper than a record, so a static deal would leave warps idle)
   const bool deal = 2 * n_work > AP;
-  const int its_dealt = deal ? (n_work / NW) * 3 / 4 : 0;      // ... and the last quarter is pulled too: the warps finish together
+  const int its_dealt = deal ? (n_work / NW) * NM_OBS_DEAL_NUM / 8 : 0;      // (NM_OBS_DEAL_NUM eighths; the remainder is pulled)
   // obs_full = 1: every row of every section is rewritten, the Task block included
   const int ms_shift = (lane & 1) * 16;      // mask store: which half of the source word this lane expands
   const uint32_t meta_full = (uint32_t)L.n_ent | ((uint32_t)L.n_inv << 8) | ((uint32_t)L.n_mkt << 18);
