@@ -167,6 +167,19 @@ def test_dense_and_incremental_writers_agree():
     a.close(); b.close()
 
 
+def test_mask_layouts_beyond_1024_entries_are_rejected():
+    """The observation kernel keeps one 32-entry mask word per lane: nmmo_create refuses layouts whose twelve heads total
+    more than 1024 entries with NM_ERR_LIMIT instead of writing wrong masks (the reference's layout has 946)."""
+    from nmmo_b200.lib import NmmoError
+    world = build_world(task_dim=64, **SMALL, NC_N_ENT_OBS=200)      # 3 * 201 + 385 + ... > 1024
+    assert ObsLayout(world[0]).m_end > 1024
+    with pytest.raises(NmmoError, match="1024"):
+        _sim(world, 2)
+    ok = build_world(task_dim=64, **SMALL, NC_N_ENT_OBS=60)
+    assert ObsLayout(ok[0]).m_end <= 1024
+    _sim(ok, 2).close()
+
+
 def test_vecenv_contract():
     import torch
     from argparse import Namespace
