@@ -1015,11 +1015,18 @@ nmmo_forage_kernel(const __grid_constant__ NmParams prm, uint64_t seed, int32_t 
     const int16_t *ent = (const int16_t *)(rec + L.o_entity);
     int food = 0, water = 0, my_r = 0, my_c = 0;
     {
+      // (rows are packed at the front of the block and entity ids are never 0: the search stops at the first empty row
+      //  instead of touching all 100 -- 6 KB of record per agent, most of this kernel's traffic)
       int found = -1;
-      for (int r = lane; r < L.n_ent && found < 0; r += 32) if (ent[r * EA_N_OBS + EA_ID] == my_id) found = r;
-      const unsigned bm = __ballot_sync(0xffffffffu, found >= 0);
-      const int src = bm ? __ffs(bm) - 1 : 0;
-      found = __shfl_sync(0xffffffffu, found, src);
+      unsigned bm = 0;
+      #pragma unroll 1
+      for (int base = 0; base < L.n_ent; base += 32) {
+        const int r = base + lane;
+        const int16_t id = r < L.n_ent ? ent[r * EA_N_OBS + EA_ID] : (int16_t)0;
+        bm = __ballot_sync(0xffffffffu, id == my_id);
+        if (bm) { found = base + __ffs(bm) - 1; break; }
+        if (__ballot_sync(0xffffffffu, id == 0)) break;
+      }
       if (bm) { food = ent[found * EA_N_OBS + EA_FOOD]; water = ent[found * EA_N_OBS + EA_WATER];
                 my_r = ent[found * EA_N_OBS + EA_ROW]; my_c = ent[found * EA_N_OBS + EA_COL]; }
     }
