@@ -517,7 +517,11 @@ def run_native(args):
                                         "note": "per-env critical path bound by instruction fetch and barrier latency "
                                                 "(DESIGN.md 4.1: 2.0 M instruction-line requests per launch), not by bandwidth"}
         dominant = "roofline_step_kernel" if step_ms >= obs_ms else "roofline_obs_kernel"
-        line["roofline"] = dict(line[dominant], dominant_by="mean launch duration in the timed region")
+        other = "roofline_obs_kernel" if dominant == "roofline_step_kernel" else "roofline_step_kernel"
+        line["roofline"] = dict(line[dominant], dominant_by="mean launch duration in the timed region",
+                                launch_ms={"step_kernel": step_ms, "obs_kernel": obs_ms},
+                                other_kernel={"kernel": line[other]["kernel"], "frac": line[other]["frac"], "achieved": line[other]["achieved"],
+                                              "see": other})
         if world_size == 1 and not args.no_cpu:
             cores = len(os.sched_getaffinity(0))
             ce = args.ref_envs or (min(1024, ref_envs_default(E, P, sim.stride)) if not big else 32)
