@@ -758,55 +758,90 @@ __device__ int border_dist(const Ctx<V> &ctx, int r, int c) {
   int b = ctx.c[NC_MAP_BORDER], ce = ctx.c[NC_MAP_CENTER];
   return min(min(r - b, ce + b - r - 1), min(c - b, ce + b - c - 1));
 }
-// NPCManager.spawn, split: one thread replays the sequential accept/reject logic of the (up to
-// 25) attempts and records the accepted ones; the rows are then filled in by one thread each
+// NPCManager.spawn, split: the accept / reject logic of the (up to 25, at most 32) attempts is replayed by warp 0 and
+// records the accepted ones; the rows are then filled in by one thread each.
+// While the danger stack is not empty an attempt's position depends on how many attempts were accepted before it
+// (the stack is popped per accept), so lane 0 walks those attempts one by one.  Once the stack is empty -- always, until
+// NPCs start dying -- the positions of all remaining attempts are known up front: one lane per attempt checks its tile,
+// an attempt loses to an earlier valid attempt on the same tile (match.any), a ballot prefix gives the n-th accepted
+// attempt the n-th free row and cuts at the population limit.  Same result as the one-by-one walk.
 template <class V>
-__device__ int npc_spawn_decide(const Ctx<V> &ctx, uint32_t *dec, const int *free_rows, const int *dng) {       // single thread
+__device__ int npc_spawn_decide(const Ctx<V> &ctx, uint32_t *dec, const int *free_rows, const int *dng, int lane) {       // warp 0
   const NmCfg<V::kStd> c = ctx.c;
-  int b = c[NC_MAP_BORDER], ce = c[NC_MAP_CENTER];
-  int count = ctx.sc[4];
-  int n = 0;
+  const int b = c[NC_MAP_BORDER], ce = c[NC_MAP_CENTER];
+  const int attempts = min(c[NC_NPC_SPAWN_ATTEMPTS], 32);
+  auto npc_type_at = [&](int d) -> int {
+    if (200 * d >= c[NC_NPC_AGGR_PCT] * ce) return 3;
+    if (200 * d >= c[NC_NPC_NEUT_PCT] * ce) return 2;
+    if (200 * d >= c[NC_NPC_PASS_PCT] * ce) return 1;
+    return 0;
+  };
+  int count = ctx.sc[4], n = 0, att = 0;
   const int nd0 = ctx.sc[2];
   int nd = nd0;
-  const int attempts = min(c[NC_NPC_SPAWN_ATTEMPTS], 32);
-  #pragma unroll 1
-  for (int att = 0; att < attempts; att++) {
-    if (count >= ctx.N) break;
-    // the n-th accepted spawn takes the n-th free row (the reference scans for the first free slot)
-    int scan = free_rows[n];
-    int r, cc;
-    if (nd > 0) {
-      int d = dng[nd0 - nd];
-      int mid = ce / 2, max_off = mid - d;
-      int offset = mid + b + nm_bounded(ctx.predraw[att * 8 + 0], 2 * max_off) - max_off;
-      int side = nm_bounded(ctx.predraw[att * 8 + 1], 4);
-      if (side == 0) { r = b + d; cc = offset; }
-      else if (side == 1) { r = b + ce - d - 1; cc = offset; }
-      else if (side == 2) { cc = b + d; r = offset; }
-      else { cc = b + ce - d - 1; r = offset; }
-    } else {
-      r = b + nm_bounded(ctx.predraw[att * 8 + 0], ce);
-      cc = b + nm_bounded(ctx.predraw[att * 8 + 1], ce);
+  if (lane == 0) {
+    #pragma unroll 1
+    for (; att < attempts && nd > 0; att++) {
+      if (count >= ctx.N) break;
+      // the n-th accepted spawn takes the n-th free row (the reference scans for the first free slot)
+      const int scan = free_rows[n];
+      const int d0 = dng[nd0 - nd];
+      const int mid = ce / 2, max_off = mid - d0;
+      const int offset = mid + b + nm_bounded(ctx.predraw[att * 8 + 0], 2 * max_off) - max_off;
+      const int side = nm_bounded(ctx.predraw[att * 8 + 1], 4);
+      int r, cc;
+      if (side == 0) { r = b + d0; cc = offset; }
+      else if (side == 1) { r = b + ce - d0 - 1; cc = offset; }
+      else if (side == 2) { cc = b + d0; r = offset; }
+      else { cc = b + ce - d0 - 1; r = offset; }
+      if (nm_impassible(tile_at(ctx, r, cc))) continue;
+      if (!c[NC_ALLOW_OCCUPIED] && occ_get(ctx, r, cc)) continue;
+      const int d = border_dist(ctx, r, cc), type = npc_type_at(d);
+      if (!type) continue;
+      uint32_t *q = dec + n * 8;
+      q[0] = (uint32_t)scan; q[1] = (uint32_t)r; q[2] = (uint32_t)cc; q[3] = (uint32_t)d; q[4] = (uint32_t)type;
+      q[5] = (uint32_t)att; q[6] = (uint32_t)ctx.sc[3];
+      ctx.sc[3]--;
+      ENT(EA_STATUS, scan) = ES_ALIVE;
+      occ_set(ctx, r, cc);
+      count++; n++; nd--;
     }
-    if (nm_impassible(tile_at(ctx, r, cc))) continue;
-    if (!c[NC_ALLOW_OCCUPIED] && occ_get(ctx, r, cc)) continue;
-    int d = border_dist(ctx, r, cc);
-    int type;
-    if (200 * d >= c[NC_NPC_AGGR_PCT] * ce) type = 3;
-    else if (200 * d >= c[NC_NPC_NEUT_PCT] * ce) type = 2;
-    else if (200 * d >= c[NC_NPC_PASS_PCT] * ce) type = 1;
-    else continue;
-    uint32_t *q = dec + n * 8;
-    q[0] = (uint32_t)scan; q[1] = (uint32_t)r; q[2] = (uint32_t)cc; q[3] = (uint32_t)d; q[4] = (uint32_t)type;
-    q[5] = (uint32_t)att; q[6] = (uint32_t)ctx.sc[3];
-    ctx.sc[3]--;
-    ENT(EA_STATUS, scan) = ES_ALIVE;
-    occ_set(ctx, r, cc);
-    count++; n++;
-    if (nd > 0) nd--;
   }
-  ctx.sc[2] = nd;
-  return n;
+  __syncwarp();
+  att = __shfl_sync(0xffffffffu, att, 0); n = __shfl_sync(0xffffffffu, n, 0);
+  count = __shfl_sync(0xffffffffu, count, 0); nd = __shfl_sync(0xffffffffu, nd, 0);
+  int n_b = 0;
+  if (nd == 0 && count < ctx.N && att < attempts) {      // (warp-uniform) the remaining attempts, one per lane
+    const int my_att = att + lane;
+    const bool active = my_att < attempts;
+    int r = 0, cc = 0, d = 0, type = 0;
+    bool valid = false;
+    if (active) {
+      r = b + nm_bounded(ctx.predraw[my_att * 8 + 0], ce);
+      cc = b + nm_bounded(ctx.predraw[my_att * 8 + 1], ce);
+      valid = !nm_impassible(tile_at(ctx, r, cc)) && (c[NC_ALLOW_OCCUPIED] || !occ_get(ctx, r, cc));
+      if (valid) { d = border_dist(ctx, r, cc); type = npc_type_at(d); valid = type != 0; }
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned vm = __ballot_sync(0xffffffffu, valid);
+    const unsigned same = __match_any_sync(0xffffffffu, valid ? r * ctx.S + cc : -1 - lane);
+    const bool acc = valid && (c[NC_ALLOW_OCCUPIED] || !(same & vm & lt));
+    const unsigned am = __ballot_sync(0xffffffffu, acc);
+    const int rank = __popc(am & lt), limit = ctx.N - count, sc3 = ctx.sc[3];
+    n_b = min(__popc(am), limit);
+    __syncwarp();
+    if (acc && rank < limit) {
+      const int slot = n + rank, scan = free_rows[slot];
+      uint32_t *q = dec + slot * 8;
+      q[0] = (uint32_t)scan; q[1] = (uint32_t)r; q[2] = (uint32_t)cc; q[3] = (uint32_t)d; q[4] = (uint32_t)type;
+      q[5] = (uint32_t)my_att; q[6] = (uint32_t)(sc3 - rank);
+      ENT(EA_STATUS, scan) = ES_ALIVE;
+      occ_set(ctx, r, cc);
+    }
+    if (lane == 0) ctx.sc[3] = sc3 - n_b;
+  }
+  if (lane == 0) ctx.sc[2] = nd;
+  return n + n_b;
 }
 template <class V>
 __device__ void npc_spawn_fill(const Ctx<V> &ctx, const uint32_t *q) {
@@ -1985,7 +2020,7 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
     ctx.predraw = s_scratch;
     uint32_t *dec = s_scratch + 256;
     HSYNC();
-    if (my_spawn && tid == 0) ctx.sc[5] = npc_spawn_decide(ctx, dec, s_free, s_dng);
+    if (my_spawn && tid < 32) { const int n_acc = npc_spawn_decide(ctx, dec, s_free, s_dng, lane); if (tid == 0) ctx.sc[5] = n_acc; }
     HSYNC();
     if (my_spawn && tid < ctx.sc[5]) npc_spawn_fill(ctx, dec + tid * 8);
   }
