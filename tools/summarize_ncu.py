@@ -40,7 +40,7 @@ d = defaultdict(list)
 for r in rows[hi + 1:]:
     d[r[ki]].append(float(r[vi].replace(",", "")) / 1e3)
 tot = sum(sum(v) for k, v in d.items() if k.startswith("nmmo"))
-lines += ["## Launch list (gpu__time_duration.sum, first 140 launches)", "", "| kernel | launches | mean us | share of nmmo time |", "|---|---|---|---|"]
+lines += ["## Launch list (gpu__time_duration.sum, first 260 launches: spin-up, warm-up, the timed window, the dense-writer leg)", "", "| kernel | launches | mean us | share of nmmo time |", "|---|---|---|---|"]
 for k, v in d.items():
     lines.append(f"| {k[:48]} | {len(v)} | {sum(v)/len(v):.1f} | {100*sum(v)/tot if k.startswith('nmmo') else 0:.1f} % |")
 summary = {}
