@@ -7,11 +7,13 @@
 // and pufferlib's flatten + pad of the nested observation (reinforcement_learning/environment.py:73),
 // writing the flat record the policy reads on-device (agent_zoo/takeru/policy.py:39-64).
 //
-// Small family (nmmo_obs_kernel): one CTA per environment, three CTAs per SM.  The entity table (31 observed
+// Small family (nmmo_obs_kernel): one 512-thread CTA per environment, two CTAs per SM.  The entity table (31 observed
 // columns + status), the live prefix of the item table and the 4-bit tile map are staged into shared memory with
 // TMA bulk copies; the env-global Market block is built once in shared memory; the agents that need a record
-// are compacted into a work list the warps pull from; each warp assembles whole agent records and
-// streams them out with 16-byte st.global.cs stores, 512 contiguous bytes per warp instruction.
+// are compacted into a work list; a pre-pass with four threads per agent finds each agent's visible rows (in table
+// order) and target bits; each warp then assembles whole agent records -- the ActionTargets masks as one 32-entry word
+// per lane -- and streams them out with 16-byte st.global.cs stores, 512 contiguous bytes per warp instruction, the
+// Market block of a record with one TMA bulk copy.  DESIGN.md section 4.2 has the measurements behind each choice.
 // Big family (nmmo_obs_big_kernel, up to 1024 agents per env): NM_BIG_OBS_AGENTS agents per CTA, several CTAs per
 // environment; the tables are read where they live (row-major entity table: an observed row is the first 62 bytes
 // of its table row), only the per-row position words, the Market block and the per-agent lists are in shared memory.
