@@ -2131,16 +2131,15 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
 #pragma unroll
       for (int k = 0; k < IS_N; k++) ITM(k, r) = 0;
     }
-  // exchange.step: listings expire; only rows in use are visited (one bitmap word per thread)
+  // exchange.step: listings expire; only rows in use are visited.  One row per thread: rows are allocated lowest-first,
+  // so the live ones share a bitmap word or two, and with the item table in place (HBM / L2) a thread that walked a whole
+  // word paid two dependent L2 round trips per row, one row after the other (9 K cycles per env-tick in the driver's window)
   #pragma unroll 1
-  for (int w = tid; w < cap_words; w += T) {
-    uint32_t bits = ctx.used[w];
-    #pragma unroll 1
-    while (bits) {
-      int i = (w << 5) + __ffs(bits) - 1; bits &= bits - 1;
-      if (ITM(IS_PRICE, i) > 0 && ctx.tick - ITM(IS_LIST_TICK, i) > c[NC_LISTING_DURATION]) { ITM(IS_PRICE, i) = 0; ITM(IS_LIST_TICK, i) = 0; }
+  for (int i = tid; i < ctx.sc[9]; i += T)
+    if (row_used(ctx, i)) {
+      const int price = ITM(IS_PRICE, i), listed_at = ITM(IS_LIST_TICK, i);
+      if (price > 0 && ctx.tick - listed_at > c[NC_LISTING_DURATION]) { ITM(IS_PRICE, i) = 0; ITM(IS_LIST_TICK, i) = 0; }
     }
-  }
   HSYNC();
 
   PHASE();
