@@ -65,7 +65,13 @@ static size_t obs_cell_bytes(const NmParams &p, int NW) {
 // observation kernels, per warp: visible-row list, batched-sampler mask words / agents / picks, Entity row buffer
 static size_t obs_warp_bytes(const NmParams &p, int NW) {
   return a16((size_t)NW * a16((size_t)p.L.n_ent * 2)) + a16((size_t)NW * NM_OBS_BATCH * 33 * 4) + a16((size_t)NW * NM_OBS_BATCH * 2) +
-         a16((size_t)NW * NM_OBS_BATCH * AC_N * 2) + a16((size_t)NW * 512);
+         a16((size_t)NW * NM_OBS_BATCH * AC_N * 2) + (p.big ? 0 : a16((size_t)NW * NM_OBS_EROWS * 64));
+}
+// observation kernels: per-agent lists and target bits of the pre-pass (where it can run; same condition as in obs_body)
+static size_t obs_pre_bytes(const NmParams &p, int AP, int NW) {
+  const int RW = ((p.R + 31) & ~31) / 32;
+  const bool pre_ok = RW <= 32 && (size_t)AP * RW * 4 <= (size_t)NW * NM_OBS_BATCH * 33 * 4;
+  return pre_ok ? a16((size_t)AP * 33 * 2) + a16((size_t)AP * 3 * 4) : 0;
 }
 static size_t step_big_ws_bytes(const NmParams &p) {
   return a16((size_t)12 * p.P * 2) + a16((size_t)VBig::kEvCap * 8) + a16((size_t)p.P * 16) + a16((size_t)p.P * 8) + 128;
@@ -77,7 +83,7 @@ static size_t obs_big_smem_bytes(const NmParams &p) {
   s += a16((size_t)p.L.n_mkt * IA_N_OBS * 2); s += a16((size_t)p.L.n_mkt * 2);
   s += a16((size_t)AP * NINV * 2); s += a16((size_t)AP * 4); s += a16(64 * 4);
   s += obs_warp_bytes(p, NW); s += 16;
-  s += a16((3 * AC_N + 2) * 4); s += a16((size_t)AP * 4); s += a16((size_t)AP * 8) + a16((size_t)AP * 33 * 2) + a16((size_t)AP * 3 * 4); s += a16((size_t)((p.R + 31) & ~31) * 4);
+  s += a16((3 * AC_N + 2) * 4); s += a16((size_t)AP * 4); s += a16((size_t)AP * 8) + obs_pre_bytes(p, AP, NW); s += a16((size_t)((p.R + 31) & ~31) * 4);
   s += obs_cell_bytes(p, NW) + 64 * 4 + a16((size_t)AP * 8);
   return s + 128;
 }
@@ -100,7 +106,7 @@ static size_t obs_smem_bytes(const NmParams &p) {
   s += a16((size_t)p.L.n_mkt * IA_N_OBS * 2); s += a16((size_t)p.L.n_mkt * 2);
   s += a16((size_t)p.P * NINV * 2); s += a16((size_t)p.P * 4); s += a16(64 * 4);
   s += obs_warp_bytes(p, NW); s += 16;
-  s += a16((3 * AC_N + 2) * 4); s += a16((size_t)p.P * 4); s += a16((size_t)p.P * 8) + a16((size_t)p.P * 33 * 2) + a16((size_t)p.P * 3 * 4); s += a16((size_t)((p.R + 31) & ~31) * 4);
+  s += a16((3 * AC_N + 2) * 4); s += a16((size_t)p.P * 4); s += a16((size_t)p.P * 8) + obs_pre_bytes(p, p.P, NW); s += a16((size_t)((p.R + 31) & ~31) * 4);
   s += obs_cell_bytes(p, NW) + 64 * 4 + a16((size_t)p.P * 8);
   return s + 64;
 }

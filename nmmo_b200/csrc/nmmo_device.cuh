@@ -41,6 +41,9 @@
 #define NM_OBS_PREFETCH_AHEAD 64
 #endif
 //      NM_OBS_PREFETCH_AHEAD:  // observation kernel (small family): a CTA prefetches into L2 the tables of the env this many CTAs later
+#ifndef NM_OBS_EROWS
+#define NM_OBS_EROWS 8             // observation kernel (small family): Entity rows a warp stages per group (8 or 16)
+#endif
 #ifndef NM_OBS_ENT_SKEW
 #define NM_OBS_ENT_SKEW 8
 #endif

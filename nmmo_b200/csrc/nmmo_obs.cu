@@ -138,7 +138,8 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   uint32_t *s_bb_all = (uint32_t *)carve((size_t)NW * NM_OBS_BATCH * 33 * 4);
   uint16_t *s_ba_all = (uint16_t *)carve((size_t)NW * NM_OBS_BATCH * 2);
   int16_t *s_pick_all = (int16_t *)carve((size_t)NW * NM_OBS_BATCH * AC_N * 2);
-  int16_t *s_ebuf_all = (int16_t *)carve((size_t)NW * 512);      // per warp: 8 Entity rows (496 bytes) on their way out
+  // per warp: NM_OBS_EROWS Entity rows on their way out (small family only: the big family gathers straight from its table)
+  int16_t *s_ebuf_all = V::kStage ? (int16_t *)carve((size_t)NW * NM_OBS_EROWS * 64) : nullptr;
   const int R32 = (R + 31) & ~31, RW = R32 >> 5;
   uint32_t *s_pos = (uint32_t *)carve((size_t)R32 * 4);     // (row+7)<<16 | (col+7) of alive rows, padded to whole warps
   // cell index for the vision-window search: alive rows bucketed by NM_OBS_CELL x NM_OBS_CELL-tile cell.  A window
@@ -156,8 +157,10 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   uint64_t *s_work = (uint64_t *)carve((size_t)AP * 8);
   // per agent (thread-per-agent pre-pass): up to 32 visible rows in table order (+ their count in slot 32; row stride 33
   // halfwords so that 32 threads walking 32 lists hit different banks) and the Attack / Give target bits of those rows
-  uint16_t *s_va = (uint16_t *)carve((size_t)AP * 33 * 2);
-  uint32_t *s_tg = (uint32_t *)carve((size_t)AP * 3 * 4);
+  // (only where the pre-pass can run: at most 32 bitmap words per agent, and room for the bitmaps in the batch words)
+  const bool pre_ok = RW <= 32 && (size_t)AP * RW * 4 <= (size_t)NW * NM_OBS_BATCH * 33 * 4;
+  uint16_t *s_va = pre_ok ? (uint16_t *)carve((size_t)AP * 33 * 2) : nullptr;
+  uint32_t *s_tg = pre_ok ? (uint32_t *)carve((size_t)AP * 3 * 4) : nullptr;
   uint64_t *bar = (uint64_t *)carve(16);
 
   long long t_prev = clock64();
@@ -345,7 +348,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   uint32_t *bb = s_bb_all + warp * (NM_OBS_BATCH * 33);
   uint16_t *ba = s_ba_all + warp * NM_OBS_BATCH;
   int16_t *picks = s_pick_all + warp * (NM_OBS_BATCH * AC_N);
-  int16_t *ebuf = s_ebuf_all + warp * 256;
+  int16_t *ebuf = s_ebuf_all + warp * (NM_OBS_EROWS * 32);
   // the bits of mask entries [lo, hi) / of entry pos that fall into this lane's word
   auto range_bits = [&](int lo, int hi) -> uint32_t {
     const int a = max(lo - 32 * lane, 0), b = min(hi - 32 * lane, 32);
@@ -372,7 +375,6 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     //  or with more than 32 bitmap words per agent, every agent takes the warp path)
     uint32_t *s_pbm = s_bb_all;
     const int WPL = (RW + 3) >> 2;                    // bitmap words per lane of a quad
-    const bool pre_ok = RW <= 32 && (size_t)AP * RW * 4 <= (size_t)NW * NM_OBS_BATCH * 33 * 4;
     #pragma unroll 1
     for (int wi0 = 0; wi0 < n_work; wi0 += T / 4) {
       const int wi = wi0 + (tid >> 2), q = lane & 3;
@@ -430,7 +432,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
           #pragma unroll 1
           while (bits && idx < nv) { const int b2 = __ffs(bits) - 1; bits &= bits - 1; va[idx++] = (uint16_t)(w * 32 + b2); }
         }
-      if (alive && q == 0) va[32] = fast ? (uint16_t)nv : (uint16_t)0xffff;
+      if (pre_ok && alive && q == 0) va[32] = fast ? (uint16_t)nv : (uint16_t)0xffff;
       __syncwarp();
       uint32_t att = 0, give = 0, any = 0;
       if (fast) {
@@ -582,7 +584,7 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
     const int n_cand = nA + nB;
     // the common case (at most 32 candidates): the list and the target bits were made by the pre-pass
     const uint16_t *vl = s_va + (p - p_lo) * 33;      // this agent's visible rows, in table order
-    const bool pre = use_cells && vl[32] != 0xffffu;
+    const bool pre = use_cells && pre_ok && vl[32] != 0xffffu;
     if (pre) {
       n_vis = vl[32];
     } else if (use_cells) {
@@ -742,22 +744,28 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
       const int n_chunks = min(nm_align16(L.n_ent * EA_N_OBS * 2) / 16, (max(n_vis, pv) * EA_N_OBS * 2 + 15) / 16);
       n_stored += n_chunks;
       if (V::kStage) {
-        const int ej = lane >> 2, eq = lane & 3;
+        // NM_OBS_EROWS rows per group (8: lane = (row, column mod 4), needs the skewed columns to stay free of bank
+        // conflicts; 16: lane = (row, column mod 2), half as many groups)
+        constexpr int ER = NM_OBS_EROWS, EL = 32 / ER, GC = ER * EA_N_OBS * 2 / 16;      // lanes per row, chunks per group
+        const int ej = lane / EL, eq = lane % EL;
         #pragma unroll 1
-        for (int g = 0; 31 * g < n_chunks; g++) {
-          const int i = 8 * g + ej;
+        for (int g = 0; GC * g < n_chunks; g++) {
+          const int i = ER * g + ej;
           int16_t *dst = ebuf + ej * EA_N_OBS + eq;
           if (i < n_vis) {
             const int vr = vl[i];
 #pragma unroll
-            for (int t = 0; t < 8; t++) if (eq + 4 * t < EA_N_OBS) dst[4 * t] = OENT(eq + 4 * t, vr);
+            for (int t = 0; t < (EA_N_OBS + EL - 1) / EL; t++) if (eq + EL * t < EA_N_OBS) dst[EL * t] = OENT(eq + EL * t, vr);
           } else {
 #pragma unroll
-            for (int t = 0; t < 8; t++) if (eq + 4 * t < EA_N_OBS) dst[4 * t] = 0;
+            for (int t = 0; t < (EA_N_OBS + EL - 1) / EL; t++) if (eq + EL * t < EA_N_OBS) dst[EL * t] = 0;
           }
           __syncwarp();
-          const int k = 31 * g + lane;
-          if (lane < 31 && k < n_chunks) st16(rec + L.o_entity + k * 16, ((const uint4 *)ebuf)[lane]);
+#pragma unroll
+          for (int h = 0; h < (GC + 31) / 32; h++) {
+            const int kk = h * 32 + lane, k = GC * g + kk;
+            if (kk < GC && k < n_chunks) st16(rec + L.o_entity + k * 16, ((const uint4 *)ebuf)[kk]);
+          }
           __syncwarp();
         }
       } else {
