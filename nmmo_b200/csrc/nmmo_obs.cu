@@ -155,8 +155,8 @@ __device__ __forceinline__ void obs_body(const NmParams &prm) {
   // work list entries: agent (relative to p_lo) | dead << 10 | the agent's two candidate ranges of the cell-ordered row list
   // (begin A << 12 | count A << 24 | begin B << 36 | count B << 48)
   uint64_t *s_work = (uint64_t *)carve((size_t)AP * 8);
-  // per agent (thread-per-agent pre-pass): up to 32 visible rows in table order (+ their count in slot 32; row stride 33
-  // halfwords so that 32 threads walking 32 lists hit different banks) and the Attack / Give target bits of those rows
+  // per agent (pre-pass, a quad of threads per agent): up to 32 visible rows in table order (+ their count in slot 32;
+  // row stride 33 halfwords so that the quads of a warp hit different banks) and the Attack / Give target bits of those rows
   // (only where the pre-pass can run: at most 32 bitmap words per agent, and room for the bitmaps in the batch words)
   const bool pre_ok = RW <= 32 && (size_t)AP * RW * 4 <= (size_t)NW * NM_OBS_BATCH * 33 * 4;
   uint16_t *s_va = pre_ok ? (uint16_t *)carve((size_t)AP * 33 * 2) : nullptr;
