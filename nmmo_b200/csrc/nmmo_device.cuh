@@ -96,6 +96,7 @@ struct NmParams {
   int no_depl_list;            // test hook: never trust the depleted-tile list (always rebuild it from a map scan)
   int envs_per_cta;            // step kernel: 2 when two environments fit in one CTA's shared memory, else 1
   int mode;                    // 0 step (auto-reset finished envs), 1 reset flagged envs only
+  int env_lo, env_hi;          // step kernel: the environments this launch covers (the host-buffer path launches it per copied range)
   int env_base;                // global env index of env 0 (multi-GPU sharding; seeds derive from it)
 };
 

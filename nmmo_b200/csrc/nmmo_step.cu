@@ -1287,13 +1287,13 @@ __device__ __forceinline__ void step_body(const NmParams &prm) {
   extern __shared__ __align__(128) uint8_t smem_all[];
   const int half = threadIdx.x / V::kThreads;
   uint8_t *smem = smem_all + (size_t)half * prm.half_smem;
-  const int env = blockIdx.x * prm.envs_per_cta + half, tid = threadIdx.x % V::kThreads, T = V::kThreads, lane = tid & 31, warp = tid >> 5;
+  const int env = prm.env_lo + blockIdx.x * prm.envs_per_cta + half, tid = threadIdx.x % V::kThreads, T = V::kThreads, lane = tid & 31, warp = tid >> 5;
   const NmCfg<V::kStd> c{prm.cfg};
   constexpr nm_obs_layout kStdL = nm_std_layout();
   typedef typename V::Shape SH;
   const int P = V::kStd ? SH::P : prm.P, N = V::kStd ? SH::N : prm.N, R = V::kStd ? SH::R : prm.R;
   const int S = V::kStd ? SH::S : prm.S, CAP = V::kStd ? SH::CAP : prm.CAP, NINV = V::kStd ? SH::NINV : c[NC_N_INV];
-  if (env >= prm.E) return;          // odd environment count: the last CTA runs one half (exited threads do not count at barriers)
+  if (env >= prm.env_hi) return;     // odd environment count: the last CTA runs one half (exited threads do not count at barriers)
   int32_t *gsc = prm.scalars + (size_t)env * NM_SC_N;
 
   // ---- reset paths -------------------------------------------------------------------

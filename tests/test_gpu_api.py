@@ -153,6 +153,33 @@ def test_step_host_equals_device_step():
     a.close(); b.close(); c.close(); d.close()
 
 
+def test_step_host_u8_in_two_ranges(monkeypatch):
+    """nmmo_step_host_u8 on a large handle copies the actions as two env ranges and runs the step kernel of the first range
+    underneath the copy of the second (NMMO_B200_H2D_SPLIT_MIN lowers the threshold for the test): same tensors as the
+    device-resident step, across an episode boundary."""
+    import torch
+    from nmmo_b200.lib import pack_actions_u8
+    world = build_world(task_dim=64, **SMALL, NC_HORIZON=30)
+    E = 13
+    a = _sim(world, E)
+    monkeypatch.setenv("NMMO_B200_H2D_SPLIT_MIN", "4")
+    b = _sim(world, E)
+    monkeypatch.delenv("NMMO_B200_H2D_SPLIT_MIN")
+    seeds = list(range(3, 3 + E))
+    a.reset(seeds); b.reset(seeds)
+    for t in range(45):
+        a.sample_actions(6)
+        torch.cuda.synchronize()
+        packed = pack_actions_u8(a.actions).cpu().numpy()
+        a.step()
+        rew, term, trunc, mask, obs = b.step_host(packed, want_obs=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(obs, a.obs.cpu().numpy()), f"tick {t}"
+        assert np.array_equal(rew, a.rewards.cpu().numpy()) and np.array_equal(mask, a.mask.cpu().numpy()), f"tick {t}"
+        assert np.array_equal(term, a.terminated.cpu().numpy()) and np.array_equal(trunc, a.truncated.cpu().numpy()), f"tick {t}"
+    a.close(); b.close()
+
+
 def test_dense_and_incremental_writers_agree():
     import torch
     world = build_world(task_dim=64, **SMALL, NC_HORIZON=70, NC_RES_DEPLETION=1)
