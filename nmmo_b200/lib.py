@@ -252,10 +252,14 @@ class Simulator:
             t = self.torch
             self._host_out = (t.empty(n, dtype=t.float32).pin_memory(), t.empty(n, dtype=t.uint8).pin_memory(),
                               t.empty(n, dtype=t.uint8).pin_memory(), t.empty(n, dtype=t.uint8).pin_memory())
-        rew, term, trunc, mask = (x.numpy() for x in self._host_out)
+            # numpy views and C pointers of the pinned result buffers, made once (this call sits on an idle GPU: a
+            # host-buffer step ends in a stream synchronise, so every microsecond of Python before the first copy counts)
+            self._host_out_np = tuple(x.numpy() for x in self._host_out)
+            self._host_out_p = tuple(_p(x) for x in self._host_out_np)
+        rew, term, trunc, mask = self._host_out_np
         obs = np.empty((n, self.stride), np.uint8) if want_obs else None
         fn = self.L.nmmo_step_host_u8 if u8 else (self.L.nmmo_step_host_i16 if i16 else self.L.nmmo_step_host)
-        self._check(fn(self.h, _p(a), _p(rew), _p(term), _p(trunc), _p(mask), _p(obs), self._stream()))
+        self._check(fn(self.h, _p(a), *self._host_out_p, _p(obs), self._stream()))
         return rew, term, trunc, mask, obs
 
     def sample_actions(self, seed: int, out=None):
