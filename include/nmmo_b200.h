@@ -76,7 +76,10 @@ int nmmo_step_host_i16(nmmo_handle *h, const int16_t *actions_host, float *rew_o
  * at most 256 entries: 3 styles, N_ent+1 targets, N_inv+1 items, 99 prices, 5 directions); the wide head,
  * Buy.MarketItem (head 2, N_mkt+1 entries), keeps bits 8.. of its index in bits 2..7 of byte 0, above the
  * two bits of Attack.Style.  A quarter of the int32 bytes over the host link.  An index outside its head
- * is a no-op for that head, as in the other variants.  NM_ERR_LIMIT if a head does not fit. */
+ * is a no-op for that head, as in the other variants.  NM_ERR_LIMIT if a head does not fit.
+ * On handles of 1024 environments or more the actions are copied as two env ranges on an internal copy stream (ordered
+ * after whatever is queued on `stream`) and the step kernel of the first range runs underneath the copy of the second;
+ * pinned host memory keeps the copies asynchronous. */
 int nmmo_step_host_u8(nmmo_handle *h, const uint8_t *actions_host, float *rew_out, uint8_t *term_out,
                       uint8_t *trunc_out, uint8_t *mask_out, uint8_t *obs_out, void *stream);
 
